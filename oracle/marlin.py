@@ -1,0 +1,717 @@
+"""Oracle restatement of Marlin's spectral hot path on libTorch CPU kernels.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Structure: a `Domain` (grid contract +
+fft/ifft), a `Problem` that owns named buffers with history (TensorProblem/TensorBuffer
+semantics), operator classes with `compute()` (the reference's `computeBuffer()`), and the
+solvers.  Every piece cites the reference file:line it follows.
+"""
+import math
+
+import torch
+
+from . import exprparser as xp
+
+F64 = torch.float64
+
+
+# =============================================================================== Domain
+class Domain:
+    """Grid contract: src/actions/DomainAction.C:227-338 (gridChanged), :1407-1434 (align),
+    :1480-1509 (k-grid, k^2), :854-867 (fftSerial), :1054-1066 (ifft NONE branch)."""
+
+    def __init__(self, dim, n, mins=(0.0, 0.0, 0.0), maxs=(1.0, 1.0, 1.0), dtype=F64):
+        self.dim = dim
+        self.n = [int(n[d]) if d < dim else 1 for d in range(3)]
+        self.min = [float(mins[d]) for d in range(3)]
+        self.max = [float(maxs[d]) for d in range(3)]
+        self.dtype = dtype
+        self.dx = [(self.max[d] - self.min[d]) / self.n[d] for d in range(3)]
+        self.axis, self.kaxis = [], []
+        for d in range(3):
+            if d < dim:
+                ax = torch.linspace(self.min[d] + self.dx[d] / 2.0, self.max[d] - self.dx[d] / 2.0,
+                                    self.n[d], dtype=dtype)
+                self.axis.append(self.align(ax, d))
+                # serial mode: the LAST spatial dim is the halved one (:274)
+                if d == dim - 1:
+                    fr = torch.fft.rfftfreq(self.n[d], self.dx[d], dtype=dtype)
+                else:
+                    fr = torch.fft.fftfreq(self.n[d], self.dx[d], dtype=dtype)
+                self.kaxis.append(self.align(fr * 2.0 * math.pi, d))
+            else:
+                self.axis.append(torch.tensor([0.0], dtype=dtype))
+                self.kaxis.append(torch.tensor([0.0], dtype=dtype))
+        self.shape = self.n[:dim]
+        self.rshape = [self.n[d] if d < dim - 1 else self.n[d] // 2 + 1 for d in range(dim)]
+        self.ncells = self.n[0] * self.n[1] * self.n[2]
+        self.volume = 1.0
+        for d in range(dim):
+            self.volume *= self.max[d] - self.min[d]
+
+    def align(self, t, d):
+        shape = [1] * self.dim
+        shape[d] = -1
+        return t.reshape(shape)
+
+    @property
+    def k2(self):  # :1504-1509
+        return self.kaxis[0] * self.kaxis[0] + self.kaxis[1] * self.kaxis[1] + \
+            self.kaxis[2] * self.kaxis[2]
+
+    @property
+    def kgrid(self):  # :1480-1501
+        if self.dim == 1:
+            return self.kaxis[0]
+        return torch.stack([self.kaxis[d].expand(self.rshape) for d in range(self.dim)], -1)
+
+    def fft(self, t):
+        return torch.fft.rfftn(t, dim=list(range(self.dim)))
+
+    def ifft(self, t):
+        return torch.fft.irfftn(t, s=self.shape, dim=list(range(self.dim)))
+
+    def sum(self, t):  # :1559-1568
+        return t.sum(dim=list(range(self.dim)))
+
+    def average(self, t):  # :1570-1574
+        return self.sum(t) / float(self.ncells)
+
+    def value_shape(self, extra):
+        return list(self.shape) + list(extra)
+
+
+# =============================================================================== Problem
+class Problem:
+    """Buffer ownership + time bookkeeping: src/problems/TensorProblem.C:154-197 (execute),
+    :451-472 (advanceState), include/tensor_buffers/TensorBuffer.h:64-79,112-116 (history)."""
+
+    def __init__(self, domain):
+        self.domain = domain
+        self.buf = {}
+        self.old = {}        # name -> list of old states (newest first)
+        self.max_states = {}  # name -> requested history length
+        self.time = 0.0
+        self.time_old = 0.0
+        self.dt = 0.0
+        self.dt_old = 0.0
+        self.t_step = 0
+        self.sub_time = 0.0
+        self.sub_dt = 0.0
+        self.ics, self.computes, self.pps = [], [], []
+        self.solver = None
+
+    def get_old(self, name, states):
+        self.max_states[name] = max(self.max_states.get(name, 0), states)
+        return self.old.setdefault(name, [])
+
+    def advance_state(self):
+        if self.t_step <= 1:  # :455-456 (quirk Q1)
+            return
+        for name, mx in self.max_states.items():
+            lst = self.old.setdefault(name, [])
+            if len(lst) < mx:
+                lst.append(None)
+            if lst:
+                for i in range(len(lst) - 1, 0, -1):
+                    lst[i] = lst[i - 1]
+                lst[0] = self.buf.get(name)
+
+    # -- MOOSE Transient loop order: TransientBase.C:315-328,390-416; FixedPointSolve.C:402,463
+    def initial(self):
+        self.sub_time = self.time
+        for ic in self.ics:
+            ic.compute()
+        for pp in self.pps:
+            pp.compute()
+
+    def step(self, dt):
+        self.time_old = self.time
+        self.t_step += 1
+        self.advance_state()
+        self.dt_old = self.dt if self.t_step > 1 else dt
+        self.dt = dt
+        self.time = self.time_old + dt
+        self.sub_time = self.time_old
+        if self.solver is not None:
+            self.solver.compute()
+        else:
+            for c in self.computes:
+                c.compute()
+        for pp in self.pps:
+            pp.compute()
+
+
+class Op:
+    def __init__(self, problem, buffer=None):
+        self.p = problem
+        self.d = problem.domain
+        self.buffer = buffer
+
+    def set(self, t):
+        self.p.buf[self.buffer] = t
+
+    def get(self, name):
+        return self.p.buf[name]
+
+
+class Group(Op):
+    """Ordered list of computes (src/tensor_computes/ComputeGroup.C:50-88)."""
+
+    def __init__(self, problem, ops):
+        super().__init__(problem)
+        self.ops = ops
+
+    def compute(self):
+        for o in self.ops:
+            o.compute()
+
+
+# =============================================================================== operators
+class RandomTensor(Op):
+    """src/tensor_computes/RandomTensor.C:37-55 (generate_on_cpu=true path)."""
+
+    def __init__(self, problem, buffer, min, max, seed=None):
+        super().__init__(problem, buffer)
+        self.min, self.max, self.seed = min, max, seed
+
+    def compute(self):
+        if self.seed is not None:
+            torch.manual_seed(self.seed)
+        self.set(torch.rand(self.d.shape, dtype=self.d.dtype) * (self.max - self.min) + self.min)
+
+
+class ConstantTensor(Op):
+    """src/tensor_computes/ConstantTensor.C:45-53."""
+
+    def __init__(self, problem, buffer, real=0.0, imaginary=0.0, reciprocal=False):
+        super().__init__(problem, buffer)
+        self.real, self.imag, self.reciprocal = real, imaginary, reciprocal
+
+    def compute(self):
+        if self.reciprocal:
+            self.set(torch.complex(torch.full(self.d.rshape, self.real, dtype=self.d.dtype),
+                                   torch.full(self.d.rshape, self.imag, dtype=self.d.dtype)))
+        else:
+            self.set(torch.full(self.d.shape, self.real, dtype=self.d.dtype))
+
+
+class ReciprocalLaplacianFactor(Op):
+    """src/tensor_computes/ReciprocalLaplacianFactor.C:30: u = -k2 * factor."""
+
+    def __init__(self, problem, buffer, factor=1.0):
+        super().__init__(problem, buffer)
+        self.factor = factor
+
+    def compute(self):
+        self.set(-self.d.k2 * self.factor)
+
+
+class ReciprocalLaplacianSquareFactor(Op):
+    """src/tensor_computes/ReciprocalLaplacianSquareFactor.C:31: u = k2 * k2 * factor."""
+
+    def __init__(self, problem, buffer, factor=1.0):
+        super().__init__(problem, buffer)
+        self.factor = factor
+
+    def compute(self):
+        self.set(self.d.k2 * self.d.k2 * self.factor)
+
+
+class ForwardFFT(Op):
+    """src/tensor_computes/PerformFFT.C:34-40."""
+
+    def __init__(self, problem, buffer, input):
+        super().__init__(problem, buffer)
+        self.input = input
+
+    def compute(self):
+        self.set(self.d.fft(self.get(self.input)))
+
+
+class InverseFFT(ForwardFFT):
+    def compute(self):
+        self.set(self.d.ifft(self.get(self.input)))
+
+
+def eval_constant_expressions(names, expressions):
+    """libMesh FParser stand-in for `constant_expressions` (ParsedCompute.C:104-123): each
+    constant may use the previously evaluated ones."""
+    vals = {}
+    for n, e in zip(names, expressions):
+        ast = xp.parse(str(e), ())
+        env = dict(vals)
+        env.update(pi=math.pi, e=math.e)
+        v = xp.evaluate(xp.simplify(ast), env)
+        vals[n] = float(v)
+    return vals
+
+
+class ParsedCompute(Op):
+    """src/tensor_computes/ParsedCompute.C:50-181 (ctor), :184-265 (computeBuffer)."""
+
+    def __init__(self, problem, buffer, expression, inputs=(), derivatives=(), constant_names=(),
+                 constant_expressions=(), extra_symbols=False, expand="NONE"):
+        super().__init__(problem, buffer)
+        self.inputs = list(inputs)
+        self.extra = extra_symbols
+        self.expand = expand
+        consts = {k: torch.tensor(v, dtype=self.d.dtype) for k, v in
+                  eval_constant_expressions(constant_names, constant_expressions).items()}
+        variables = list(self.inputs)
+        if extra_symbols:
+            consts["pi"] = torch.tensor(math.pi, dtype=self.d.dtype)
+            consts["e"] = torch.tensor(math.e, dtype=self.d.dtype)
+            consts["i"] = torch.tensor(1j, dtype=torch.complex128)
+            variables += ["x", "kx", "y", "ky", "z", "kz", "k2", "t"]
+        self.fn = xp.ParsedTensor(expression, variables, consts)
+        for dv in derivatives:
+            if dv not in self.inputs:
+                raise ValueError(f"Derivative w.r.t `{dv}` was requested, but it is not listed "
+                                 "in `inputs`.")
+            self.fn.differentiate(dv)
+        self.fn.compile()
+
+    def compute(self):
+        params = [self.get(n) for n in self.inputs]
+        if self.extra:
+            d = self.d
+            params += [d.axis[0], d.kaxis[0], d.axis[1], d.kaxis[1], d.axis[2], d.kaxis[2], d.k2,
+                       torch.tensor(self.p.sub_time, dtype=d.dtype)]
+        u = self.fn.eval(params)
+        if self.expand == "REAL":
+            u = u.expand(self.d.shape)
+        elif self.expand == "RECIPROCAL":
+            u = u.expand(self.d.rshape)
+        self.set(u)
+
+
+class FFTGradient(Op):
+    """src/tensor_computes/FFTGradient.C:36-40."""
+
+    def __init__(self, problem, buffer, input, direction, input_is_reciprocal=False):
+        super().__init__(problem, buffer)
+        self.input, self.dir, self.recip = input, direction, input_is_reciprocal
+
+    def compute(self):
+        r = self.get(self.input) if self.recip else self.d.fft(self.get(self.input))
+        self.set(self.d.ifft(r * self.d.kaxis[self.dir] * 1j))
+
+
+class FFTGradientSquare(Op):
+    """src/tensor_computes/FFTGradientSquare.C:37-48."""
+
+    def __init__(self, problem, buffer, input, factor=1.0, input_is_reciprocal=False):
+        super().__init__(problem, buffer)
+        self.input, self.factor, self.recip = input, factor, input_is_reciprocal
+
+    def compute(self):
+        r = self.get(self.input) if self.recip else self.d.fft(self.get(self.input))
+        u = self.d.ifft(r * self.d.kaxis[0] * 1j) ** 2
+        for dd in range(1, self.d.dim):
+            u = u + self.d.ifft(r * self.d.kaxis[dd] * 1j) ** 2
+        if self.factor != 1.0:
+            u = u * self.factor
+        self.set(u)
+
+
+# =============================================================================== solvers
+AB_BETA = [  # src/tensor_solver/AdamsBashforthMoulton.C:67-73 (AB5 first entry as coded: Q3)
+    [1.0, 0.0, 0.0, 0.0, 0.0],
+    [3.0 / 2.0, -1.0 / 2.0, 0.0, 0.0, 0.0],
+    [23.0 / 12.0, -16.0 / 12.0, 5.0 / 12.0, 0.0, 0.0],
+    [55.0 / 24.0, -59.0 / 24.0, 37.0 / 24.0, -9.0 / 24.0, 0.0],
+    [190.0 / 720.0, -2774.0 / 720.0, 2616.0 / 720.0, -1274.0 / 720.0, 251.0 / 720.0],
+]
+AM_ALPHA = [  # :108-114
+    [1.0, 0.0, 0.0, 0.0, 0.0],
+    [0.5, 0.5, 0.0, 0.0, 0.0],
+    [5.0 / 12.0, 8.0 / 12.0, -1.0 / 12.0, 0.0, 0.0],
+    [9.0 / 24.0, 19.0 / 24.0, -5.0 / 24.0, 1.0 / 24.0, 0.0],
+    [251.0 / 720.0, 646.0 / 720.0, -264.0 / 720.0, 106.0 / 720.0, -19.0 / 720.0],
+]
+
+
+class TensorSolver:
+    """src/tensor_solver/TensorSolver.C:93-110 (substep loop), :86-90 (forwardBuffers)."""
+
+    def __init__(self, problem, root, substeps=1, forward=()):
+        self.p, self.d = problem, problem.domain
+        self.root = root
+        self.substeps = substeps
+        self.forward = list(forward)  # (dst, src) buffer names
+        self.substep_index = 0
+
+    def forward_buffers(self):
+        for dst, src in self.forward:
+            self.p.buf[dst] = self.p.buf[src]
+
+    def compute(self):
+        p = self.p
+        p.sub_dt = p.dt / self.substeps
+        for s in range(self.substeps):
+            self.substep_index = s
+            self.substep()
+            if s < self.substeps - 1:
+                p.advance_state()
+            p.sub_time += p.sub_dt
+
+
+class SplitOperatorSolver(TensorSolver):
+    """src/tensor_solver/SplitOperatorBase.C:39-64."""
+
+    def __init__(self, problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                 nonlinear_reciprocal, substeps=1, history=0, forward=()):
+        super().__init__(problem, root, substeps, forward)
+        n = len(buffer)
+        lin = list(linear_reciprocal) if linear_reciprocal else ["0"] * n
+        self.vars = []
+        for i in range(n):
+            self.vars.append(dict(u=buffer[i], ubar=reciprocal_buffer[i],
+                                  L=None if lin[i] == "0" else lin[i], N=nonlinear_reciprocal[i],
+                                  Nold=problem.get_old(nonlinear_reciprocal[i], history)))
+
+
+class AdamsBashforthMoulton(SplitOperatorSolver):
+    """src/tensor_solver/AdamsBashforthMoulton.C:45-178."""
+
+    def __init__(self, problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                 nonlinear_reciprocal, substeps=1, predictor_order=2, corrector_order=2,
+                 corrector_steps=0, forward=()):
+        self.P = predictor_order - 1
+        self.C = corrector_order - 1
+        self.csteps = corrector_steps
+        super().__init__(problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                         nonlinear_reciprocal, substeps, max(self.P, self.C), forward)
+
+    def substep(self):
+        p, b = self.p, self.p.buf
+        self.root.compute()
+        self.forward_buffers()
+        dt = p.sub_dt
+        dt_changed = p.dt != p.dt_old
+        for v in self.vars:
+            n_old = len(v["Nold"])
+            order = min(0 if (self.substep_index < self.P and dt_changed) else n_old, self.P)
+            ubar = b[v["ubar"]] + (dt * AB_BETA[order][0]) * b[v["N"]]
+            for i in range(order):
+                ubar = ubar + (dt * AB_BETA[order][i + 1]) * v["Nold"][i]
+            if v["L"] is not None:
+                ubar = ubar / (1.0 - dt * b[v["L"]])
+            b[v["u"]] = self.d.ifft(ubar)
+        if self.csteps:
+            p.sub_time += dt
+            ubar_n = [b[v["ubar"]] for v in self.vars]
+            N_n = [b[v["N"]] for v in self.vars] if self.C > 0 else None
+            for _ in range(self.csteps):
+                self.root.compute()
+                self.forward_buffers()
+                for k, v in enumerate(self.vars):
+                    n_old = len(v["Nold"])
+                    order = min(1 if (self.substep_index < self.C and dt_changed) else n_old + 1,
+                                self.C)
+                    if order == 0:
+                        continue
+                    ubar = ubar_n[k] + (dt * AM_ALPHA[order][0]) * b[v["N"]]
+                    ubar = ubar + (dt * AM_ALPHA[order][1]) * N_n[k]
+                    for i in range(order - 1):
+                        ubar = ubar + (dt * AM_ALPHA[order][i + 2]) * v["Nold"][i]
+                    if v["L"] is not None:
+                        ubar = ubar / (1.0 - dt * b[v["L"]])
+                    b[v["u"]] = self.d.ifft(ubar)
+            p.sub_time -= dt
+
+
+class ForwardEulerSolver(TensorSolver):
+    """src/tensor_solver/ForwardEulerSolver.C:29-38 (variables may be empty: mechanics)."""
+
+    def __init__(self, problem, root, buffer=(), reciprocal_buffer=(), time_derivative_reciprocal=(),
+                 substeps=1, forward=()):
+        super().__init__(problem, root, substeps, forward)
+        self.vars = list(zip(buffer, reciprocal_buffer, time_derivative_reciprocal))
+
+    def substep(self):
+        b = self.p.buf
+        self.root.compute()
+        self.forward_buffers()
+        for u, ubar, nbar in self.vars:
+            b[u] = self.d.ifft(b[ubar] + self.p.sub_dt * b[nbar])
+
+
+class ETDRK4Solver(SplitOperatorSolver):
+    """src/tensor_solver/ETDRK4Solver.C:29-115 (as coded, not textbook Cox-Matthews)."""
+
+    def __init__(self, problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                 nonlinear_reciprocal, substeps=1, forward=()):
+        super().__init__(problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                         nonlinear_reciprocal, substeps, 1, forward)
+
+    def _nonlinear(self, stage):
+        b = self.p.buf
+        for v, ub in zip(self.vars, stage):
+            b[v["u"]] = self.d.ifft(ub)
+        self.root.compute()
+        self.forward_buffers()
+        return [b[v["N"]] for v in self.vars]
+
+    def substep(self):
+        b, dt = self.p.buf, self.p.sub_dt
+        self.root.compute()
+        self.forward_buffers()
+        un = [b[v["ubar"]] for v in self.vars]
+        N1 = [b[v["N"]] for v in self.vars]
+        lin = [b[v["L"]] if v["L"] is not None else torch.zeros_like(un[i])
+               for i, v in enumerate(self.vars)]
+        eL, eL2, ph1, ph2, ph3, ub = [], [], [], [], [], []
+        for i in range(len(self.vars)):
+            Ldt = lin[i] * dt
+            e = torch.exp(Ldt)
+            eL.append(e)
+            eL2.append(torch.exp(Ldt / 2.0))
+            den = Ldt * Ldt * Ldt
+            p1 = dt * (-4.0 - 3.0 * Ldt + e * (4.0 - Ldt)) / den
+            p2 = dt * (2.0 + Ldt + e * (-2.0 + Ldt)) / den
+            p3 = dt * (-4.0 - 3.0 * Ldt - Ldt * Ldt + e * (4.0 - Ldt)) / den
+            zm = Ldt == 0.0
+            if bool(zm.any()):
+                dtt = torch.full_like(Ldt, dt)
+                p1 = torch.where(zm, dtt, p1)
+                p2 = torch.where(zm, dtt * dtt / 2.0, p2)
+                p3 = torch.where(zm, dtt * dtt / 6.0, p3)
+            ph1.append(p1)
+            ph2.append(p2)
+            ph3.append(p3)
+            ub.append(eL2[i] * un[i] + 0.5 * dt * N1[i])
+        N2 = self._nonlinear(ub)
+        uc = [eL2[i] * un[i] + 0.5 * dt * N2[i] for i in range(len(self.vars))]
+        N3 = self._nonlinear(uc)
+        ud = [eL[i] * un[i] + dt * N3[i] for i in range(len(self.vars))]
+        N4 = self._nonlinear(ud)
+        for i, v in enumerate(self.vars):
+            ubar = eL[i] * un[i] + ph1[i] * N1[i] + 2.0 * ph2[i] * (N2[i] + N3[i]) + ph3[i] * N4[i]
+            b[v["u"]] = self.d.ifft(ubar)
+
+
+class FFTSemiImplicit(Op):
+    """Legacy per-buffer integrator used as an operator
+    (src/tensor_timeintegrators/FFTSemiImplicit.C:43-62)."""
+
+    def __init__(self, problem, buffer, reciprocal_buffer, linear_reciprocal, nonlinear_reciprocal,
+                 history_size=1):
+        super().__init__(problem, buffer)
+        self.ubar, self.L, self.N = reciprocal_buffer, linear_reciprocal, nonlinear_reciprocal
+        self.ubar_old = problem.get_old(reciprocal_buffer, history_size)
+        self.N_old = problem.get_old(nonlinear_reciprocal, history_size)
+
+    def compute(self):
+        b, dt = self.p.buf, self.p.sub_dt
+        n_old = min(len(self.ubar_old), len(self.N_old))
+        if n_old == 0:
+            ubar = (b[self.ubar] + dt * b[self.N]) / (1.0 - dt * b[self.L])
+        else:
+            ubar = (b[self.ubar] + dt / 2.0 * (3.0 * b[self.N] - self.N_old[0])) / \
+                   (1.0 - dt * b[self.L])
+        self.set(self.d.ifft(ubar))
+
+
+# =============================================================================== mechanics
+def trans2(A):  # src/utils/MarlinUtils.C:147-187
+    return torch.einsum("...ij->...ji", A)
+
+
+def ddot42(A, B):
+    return torch.einsum("...ijkl,...lk->...ij", A, B)
+
+
+def ddot44(A, B):
+    return torch.einsum("...ijkl,...lkmn->...ijmn", A, B)
+
+
+def dot22(A, B):
+    return torch.einsum("...ij,...jk->...ik", A, B)
+
+
+def dot24(A, B):
+    return torch.einsum("...ij,...jkmn->...ikmn", A, B)
+
+
+def dot42(A, B):
+    return torch.einsum("...ijkl,...lm->...ijkm", A, B)
+
+
+def dyad22(A, B):
+    return torch.einsum("...ij,...kl->...ijkl", A, B)
+
+
+def _unsq0(t, n):
+    for _ in range(n):
+        t = t.unsqueeze(0)
+    return t
+
+
+def conjugate_gradient(A, b, x0, tol, maxiter):
+    """include/utils/MarlinUtils.h:57-123 (identity preconditioner)."""
+    x = x0.clone() if x0 is not None else torch.zeros_like(b)
+    b_norm = float(torch.norm(b))
+    if b_norm == 0.0:
+        return x, 0, 0.0
+    if not maxiter:
+        maxiter = b.numel()
+    r = b - A(x)
+    p = r.clone()
+    rz_old = float(torch.sum(r * r))
+    res = 0.0
+    for k in range(maxiter):
+        Ap = A(p)
+        alpha = rz_old / float(torch.sum(p * Ap))
+        x = x + alpha * p
+        r = r - alpha * Ap
+        res = float(torch.norm(r))
+        if res <= tol * b_norm:
+            return x, k + 1, res
+        rz_new = float(torch.sum(r * r))
+        beta = rz_new / rz_old
+        p = r + beta * p
+        rz_old = rz_new
+    return x, maxiter, res
+
+
+class RankTwoIdentity(Op):
+    """src/tensor_computes/RankTwoIdentity.C:29-33."""
+
+    def compute(self):
+        dm = self.d.dim
+        self.set(torch.eye(dm, dtype=self.d.dtype).expand(self.d.value_shape([dm, dm])))
+
+
+class MacroscopicShearTensor(Op):
+    """test/src/tensor_computes/MacroscopicShearTensor.C:31-41.  `_time` there is the
+    TensorProblem sub-time reference (TensorOperatorBase), see SURVEY a12."""
+
+    def __init__(self, problem, buffer, F="F"):
+        super().__init__(problem, buffer)
+        self.F = F
+
+    def compute(self):
+        avg = self.d.average(self.get(self.F))
+        shear = torch.eye(self.d.dim, dtype=self.d.dtype)
+        shear[0, 1] = shear[0, 1] + self.p.sub_time
+        self.set(shear - avg)
+
+
+class PhaseMechanicsTest(Op):
+    """test/src/tensor_computes/PhaseMechanicsTest.C:31-50."""
+
+    def compute(self):
+        u = torch.zeros(self.d.shape, dtype=self.d.dtype)
+        s = 30 if self.d.dim == 2 else 9
+        if self.d.dim == 3:
+            u[-s:, :s, -s:] = 1.0
+        else:
+            u[-s:, :s] = 1.0
+        self.set(u)
+
+
+class HyperElasticIsotropic(Op):
+    """src/tensor_computes/HyperElasticIsotropic.C:24-52."""
+
+    def __init__(self, problem, buffer, F, K, mu, tangent_operator="dstressdstrain"):
+        super().__init__(problem, buffer)
+        self.F, self.K, self.mu, self.K4 = F, K, mu, tangent_operator
+        dm, dt = self.d.dim, self.d.dtype
+        ti = torch.eye(dm, dtype=dt)
+        self.tI = _unsq0(ti, dm)
+        self.tI4 = _unsq0(torch.einsum("il,jk", ti, ti), dm)
+        self.tI4rt = _unsq0(torch.einsum("ik,jl", ti, ti), dm)
+        self.tI4s = (self.tI4 + self.tI4rt) / 2.0
+        self.tII = dyad22(self.tI, self.tI)
+
+    def compute(self):
+        b = self.p.buf
+        F = b[self.F]
+        K = b[self.K].reshape(self.d.value_shape([1, 1, 1, 1]))
+        mu = b[self.mu].reshape(self.d.value_shape([1, 1, 1, 1]))
+        C4 = K * self.tII + 2.0 * mu * (self.tI4s - 1.0 / 3.0 * self.tII)
+        S = ddot42(C4, 0.5 * (dot22(trans2(F), F) - self.tI))
+        self.set(dot22(F, S))
+        b[self.K4] = dot24(S, self.tI4) + ddot44(ddot44(self.tI4rt, dot42(dot24(F, C4), trans2(F))),
+                                                 self.tI4rt)
+
+
+class FFTMechanics(Op):
+    """src/tensor_computes/FFTMechanics.C:48-85 (Ghat4), :96-163 (Newton-CG)."""
+
+    def __init__(self, problem, buffer, constitutive_model, K, mu, F="F", stress="stress",
+                 tangent_operator="dstressdstrain", applied_macroscopic_strain=None, l_tol=1e-2,
+                 l_max_its=None, nl_rel_tol=1e-5, nl_abs_tol=1e-8, nl_max_its=100):
+        super().__init__(problem, buffer)
+        self.cm = constitutive_model
+        self.F, self.P, self.K4 = F, stress, tangent_operator
+        self.applied = applied_macroscopic_strain
+        self.l_tol, self.l_max_its = l_tol, l_max_its or self.d.ncells
+        self.nl_rel_tol, self.nl_abs_tol, self.nl_max_its = nl_rel_tol, nl_abs_tol, nl_max_its
+        dm = self.d.dim
+        q = self.d.kgrid
+        Q = self.d.k2.unsqueeze(-1).unsqueeze(-1)
+        M = torch.where(Q == 0, 0.0, q.unsqueeze(-2) * q.unsqueeze(-1) / Q)
+        M = M.unsqueeze(-3).unsqueeze(-1)
+        ti = torch.eye(dm, dtype=self.d.dtype)
+        delta_im = ti.unsqueeze(1).unsqueeze(1).expand(dm, dm, dm, dm)
+        self.Ghat4 = (M * delta_im).to(torch.complex128)
+        self.r2 = self.d.value_shape([dm, dm])
+        self.cg_iterations = []   # per CG solve
+        self.newton_iterations = 0
+
+    def compute(self):
+        b, d = self.p.buf, self.d
+
+        def G(A2):
+            return d.ifft(ddot42(self.Ghat4, d.fft(A2))).reshape(-1)
+
+        def K_dF(dFm):
+            return trans2(ddot42(b[self.K4], trans2(dFm.reshape(self.r2))))
+
+        def G_K_dF(dFm):
+            return G(K_dF(dFm))
+
+        b[self.buffer] = b[self.F]
+        self.cm.compute()
+        if self.applied is not None:
+            rhs = -G_K_dF(b[self.applied].expand(self.r2))
+            b[self.buffer] = b[self.buffer] + b[self.applied].expand(self.r2)
+        else:
+            rhs = -G_K_dF(torch.zeros_like(b[self.F]))
+        Fn = float(torch.linalg.norm(b[self.buffer]))
+        iiter = 0
+        dFm = torch.zeros_like(rhs)
+        self.cg_iterations = []
+        while True:
+            dFm, its, _ = conjugate_gradient(G_K_dF, rhs, dFm, self.l_tol, self.l_max_its)
+            self.cg_iterations.append(its)
+            b[self.buffer] = b[self.buffer] + dFm.reshape(self.r2)
+            self.cm.compute()
+            rhs = -G(b[self.P])
+            anorm = float(torch.linalg.norm(dFm))
+            rnorm = anorm / Fn
+            if (rnorm < self.nl_rel_tol or anorm < self.nl_abs_tol) and iiter > 0:
+                break
+            iiter += 1
+            if iiter > self.nl_max_its:
+                raise RuntimeError("Exceeded the maximum number of nonlinear iterations without "
+                                   "converging.")
+        self.newton_iterations = iiter + 1
+
+
+# =============================================================================== postprocessors
+def pp_integral(problem, name):
+    """src/postprocessors/TensorIntegralPostprocessor.C:28-38: average * domain volume."""
+    return pp_average(problem, name) * problem.domain.volume
+
+
+def pp_average(problem, name):
+    """src/postprocessors/TensorAveragePostprocessor.C:34-47."""
+    return float(problem.buf[name].sum()) / float(problem.domain.ncells)
+
+
+def pp_extreme(problem, name, kind):
+    t = problem.buf[name]
+    return float(t.min()) if kind == "MIN" else float(t.max())

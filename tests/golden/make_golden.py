@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Extract the reference's own gold results for the hot path into small fixtures.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):  python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  Only NUMBERS from the reference's gold files (test data) are
+stored - no reference source code.
+
+Sources (relative to the reference root):
+  test/tests/cahnhilliard/gold/cahnhilliard_out.e   Exodus/NetCDF-3; nodal `c`, elemental `mu`
+  test/tests/solvers/gold/diagonal_*.csv            postprocessor CSVs
+  test/tests/solvers/gold/etdrk4_diffusion_rmse.csv
+  test/tests/mechanics/gold/mech3d.h5               HDF5, one deflate chunk per dataset
+  test/tests/gradient/gold/*.csv, test/tests/tensor_compute/gold/backandforth_out.csv
+"""
+import os
+import zlib
+
+import numpy as np
+from scipy.io import netcdf_file
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def exodus_ch2d():
+    f = netcdf_file(f"{REF}/test/tests/cahnhilliard/gold/cahnhilliard_out.e", "r", mmap=False)
+    v = f.variables
+    n, L = 20, 3.0
+    dx = L / n
+    x, y = v["coordx"][:].copy(), v["coordy"][:].copy()
+    nod = v["vals_nod_var1"][:].copy()           # [time, node]
+    elv = v["vals_elem_var1eb1"][:].copy()       # [time, elem]
+    conn = v["connect1"][:].copy() - 1
+    times = v["time_whole"][:].copy()
+    nt = nod.shape[0]
+    # ProjectTensorAux (src/auxkernels/ProjectTensorAux.C:38-60): nodal value at node p is
+    # buffer[int((p+dx/2)/dx) % n]; elemental value at centroid c is buffer[int(c/dx) % n]
+    c = np.full((nt, n, n), np.nan)
+    ii = np.floor((x + dx / 2) / dx + 1e-9).astype(int) % n
+    jj = np.floor((y + dx / 2) / dx + 1e-9).astype(int) % n
+    for t in range(nt):
+        # wrap-around nodes carry duplicate values; interior assignment wins consistently
+        c[t, ii, jj] = nod[t]
+    cx, cy = x[conn].mean(1), y[conn].mean(1)
+    ei = np.floor(cx / dx).astype(int) % n
+    ej = np.floor(cy / dx).astype(int) % n
+    mu = np.full((nt, n, n), np.nan)
+    for t in range(nt):
+        mu[t, ei, ej] = elv[t]
+    assert not np.isnan(c).any() and not np.isnan(mu).any()
+    np.savez_compressed(f"{OUT}/ch2d_exodus.npz", c=c, mu=mu, time=times)
+    print("ch2d_exodus", c.shape, mu.shape)
+
+
+def read_csv(path):
+    with open(path) as fh:
+        header = fh.readline().strip().split(",")
+        rows = [[float(x) for x in line.strip().split(",")] for line in fh if line.strip()]
+    return header, np.array(rows)
+
+
+def solver_csvs():
+    out = {}
+    gd = f"{REF}/test/tests/solvers/gold"
+    for fn in sorted(os.listdir(gd)):
+        if fn.startswith("diagonal_") or fn.startswith("etdrk4"):
+            h, a = read_csv(f"{gd}/{fn}")
+            out[fn[:-4]] = a
+            out[fn[:-4] + "__header"] = np.array(h)
+    for fn, key in [("test/tests/gradient/gold/gradient_out.csv", "gradient_out"),
+                    ("test/tests/gradient/gold/gradient_square_out.csv", "gradient_square_out"),
+                    ("test/tests/tensor_compute/gold/backandforth_out.csv", "backandforth_out"),
+                    ("test/tests/parsed_tensor/gold/local_vars_derivative_out.csv",
+                     "local_vars_derivative_out")]:
+        if os.path.exists(f"{REF}/{fn}"):
+            h, a = read_csv(f"{REF}/{fn}")
+            out[key] = a
+            out[key + "__header"] = np.array(h)
+    np.savez_compressed(f"{OUT}/csv_golds.npz", **out)
+    print("csv_golds", [k for k in out if not k.endswith("__header")])
+
+
+def zlib_streams(path):
+    """Every dataset is one deflate-9 chunk (XDMFTensorOutput.C:597-622): scan for zlib
+    headers and inflate."""
+    data = open(path, "rb").read()
+    pos, found = 0, []
+    while True:
+        i = data.find(b"\x78\xda", pos)
+        if i < 0:
+            break
+        try:
+            d = zlib.decompressobj()
+            out = d.decompress(data[i:])
+            used = len(data) - i - len(d.unused_data)
+            if len(out) >= 64 and d.eof:
+                found.append(out)
+                pos = i + used
+                continue
+        except zlib.error:
+            pass
+        pos = i + 1
+    return found
+
+
+def mech3d():
+    n = 16
+    streams = zlib_streams(f"{REF}/test/tests/mechanics/gold/mech3d.h5")
+    # per frame, std::map key order: F_0..F_8, disp_x, disp_y, disp_z, phase, sV
+    per = 14
+    assert len(streams) % per == 0, len(streams)
+    frames = len(streams) // per
+    F = np.zeros((frames, n, n, n, 3, 3))
+    sV = np.zeros((frames, n, n, n))
+    for fr in range(frames):
+        blk = streams[fr * per:(fr + 1) * per]
+        for k in range(9):
+            a = np.frombuffer(blk[k], dtype="<f8").reshape(n, n, n)  # stored [z,y,x]
+            F[fr, :, :, :, k // 3, k % 3] = a.transpose(2, 1, 0)
+        sV[fr] = np.frombuffer(blk[13], dtype="<f8").reshape(n, n, n).transpose(2, 1, 0)
+    np.savez_compressed(f"{OUT}/mech3d_h5.npz", F=F, sV=sV)
+    print("mech3d_h5", F.shape)
+
+
+if __name__ == "__main__":
+    exodus_ch2d()
+    solver_csvs()
+    mech3d()

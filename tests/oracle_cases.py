@@ -1,0 +1,87 @@
+"""Problem builders shared by the oracle pinning tests and the CUDA parity tests.
+
+Each builder restates one reference input file with the oracle's operator classes
+(oracle/marlin.py).  Paths cited are relative to the reference root.
+"""
+import math
+
+from oracle import marlin as om
+
+
+def ch_problem(dim, n, L, substeps, mu_expr="0.1*c^2*(c-1)^2", M=0.2, kappa=-0.001, seed=0,
+               predictor_order=2, cmin=0.44, cmax=0.56, constant_names=(),
+               constant_expressions=()):
+    """test/tests/cahnhilliard/cahnhilliard.i and examples/cahn_hilliard/cahnhilliard2.i."""
+    d = om.Domain(dim, [n] * dim, (0, 0, 0), tuple([L] * dim) + (1.0,) * (3 - dim))
+    p = om.Problem(d)
+    p.ics = [om.RandomTensor(p, "c", cmin, cmax, seed),
+             om.ReciprocalLaplacianFactor(p, "Mbar", M),
+             om.ReciprocalLaplacianSquareFactor(p, "kappabarbar", kappa)]
+    root = om.Group(p, [
+        om.ParsedCompute(p, "mu", mu_expr, inputs=["c"], derivatives=["c"],
+                         constant_names=constant_names, constant_expressions=constant_expressions),
+        om.ForwardFFT(p, "mubar", "mu"),
+        om.ParsedCompute(p, "Mbarmubar", "Mbar*mubar", inputs=["Mbar", "mubar"]),
+        om.ForwardFFT(p, "cbar", "c"),
+    ])
+    p.solver = om.AdamsBashforthMoulton(p, root, ["c"], ["cbar"], ["kappabarbar"], ["Mbarmubar"],
+                                        substeps=substeps, predictor_order=predictor_order)
+    return p
+
+
+def diagonal_problem(ss, cs, order, n=150):
+    """test/tests/solvers/diagonal.i with cli_args ss/cs/order."""
+    d = om.Domain(2, [n, n], (0, 0, 0), (2 * math.pi, 2 * math.pi, 1.0))
+    p = om.Problem(d)
+    cn, ce = ["A", "B"], ["1", "3.5"]
+    p.ics = [om.ParsedCompute(p, "u", "sin(x)*sin(y)", extra_symbols=True, expand="REAL",
+                              constant_names=cn, constant_expressions=ce),
+             om.ConstantTensor(p, "v", 0.0),
+             om.ReciprocalLaplacianFactor(p, "Du", 1e-2),
+             om.ReciprocalLaplacianFactor(p, "Dv", 1e-3)]
+    root = om.Group(p, [
+        om.ForwardFFT(p, "u_bar", "u"),
+        om.ForwardFFT(p, "v_bar", "v"),
+        om.ParsedCompute(p, "source_u", "A - (B+1)*u +u^2*v", inputs=["u", "v"],
+                         constant_names=cn, constant_expressions=ce),
+        om.ForwardFFT(p, "source_u_bar", "source_u"),
+        om.ParsedCompute(p, "source_v", "B*u - u^2*v", inputs=["u", "v"], constant_names=cn,
+                         constant_expressions=ce),
+        om.ForwardFFT(p, "source_v_bar", "source_v"),
+    ])
+    p.solver = om.AdamsBashforthMoulton(p, root, ["u", "v"], ["u_bar", "v_bar"], ["Du", "Dv"],
+                                        ["source_u_bar", "source_v_bar"], substeps=ss,
+                                        predictor_order=order, corrector_order=order,
+                                        corrector_steps=cs)
+    return p
+
+
+def diagonal_row(p):
+    """Column order of the gold CSV: time,U,V,u_max,u_min,v_max,v_min."""
+    return [p.time, om.pp_integral(p, "u"), om.pp_integral(p, "v"), om.pp_extreme(p, "u", "MAX"),
+            om.pp_extreme(p, "u", "MIN"), om.pp_extreme(p, "v", "MAX"),
+            om.pp_extreme(p, "v", "MIN")]
+
+
+def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2):
+    """test/tests/mechanics/mech3d.i."""
+    L = 2 * math.pi
+    d = om.Domain(3, [n, n, n], (0, 0, 0), (L, L, L))
+    p = om.Problem(d)
+    p.ics = [
+        om.ParsedCompute(p, "phase", "(cos(x)/2+0.5)^1*(cos(y)/2+0.5)^1*(cos(z)/2+0.5)^1",
+                         extra_symbols=True),
+        om.ParsedCompute(p, "K", "(1-phase)*Ka + phase*Kb", inputs=["phase"],
+                         constant_names=["Ka", "Kb"], constant_expressions=["1", "10"]),
+        om.ParsedCompute(p, "mu", "(1-phase)*mua + phase*mub", inputs=["phase"],
+                         constant_names=["mua", "mub"], constant_expressions=["0.5", "5"]),
+        om.RankTwoIdentity(p, "F"),
+    ]
+    hyper = om.HyperElasticIsotropic(p, "stress", "Fnew", "K", "mu")
+    mech = om.FFTMechanics(p, "Fnew", hyper, "K", "mu", F="F", stress="stress",
+                           applied_macroscopic_strain="applied_strain", l_tol=l_tol,
+                           nl_rel_tol=nl_rel_tol, nl_abs_tol=nl_abs_tol)
+    root = om.Group(p, [om.MacroscopicShearTensor(p, "applied_strain", "F"), mech])
+    p.solver = om.ForwardEulerSolver(p, root, substeps=substeps, forward=[("F", "Fnew")])
+    p.mech = mech
+    return p

@@ -1,0 +1,189 @@
+"""Pin the oracle against the reference's own gold files (fixtures in tests/golden/,
+extracted by tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_cases as oc
+from oracle import exprparser as xp
+from oracle import marlin as om
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_ch2d_matches_exodus_gold():
+    """test/tests/cahnhilliard/cahnhilliard.i vs gold/cahnhilliard_out.e (Exodiff)."""
+    g = np.load(f"{G}/ch2d_exodus.npz")
+    p = oc.ch_problem(2, 20, 3.0, substeps=10)
+    p.ics.insert(1, om.ConstantTensor(p, "mu", 0.0))
+    p.initial()
+    assert np.abs(p.buf["c"].numpy() - g["c"][0]).max() == 0.0  # IC bit-exact
+    for step in range(1, 11):
+        p.step(1e-3)
+        assert np.abs(p.buf["c"].numpy() - g["c"][step]).max() < 1e-13
+        assert np.abs(p.buf["mu"].numpy() - g["mu"][step]).max() < 1e-13
+
+
+@pytest.mark.parametrize("ss,cs,order", [(10, 0, 1), (10, 0, 2), (10, 0, 3), (20, 0, 4),
+                                         (10, 1, 1), (10, 2, 1), (10, 2, 2)])
+def test_diagonal_matches_csv_gold(ss, cs, order):
+    """test/tests/solvers/diagonal.i vs gold/diagonal_{ss}_{cs}_{order}.csv (CSVDiff)."""
+    gold = np.load(f"{G}/csv_golds.npz")[f"diagonal_{ss}_{cs}_{order}"]
+    p = oc.diagonal_problem(ss, cs, order)
+    p.initial()
+    for step in range(1, gold.shape[0]):
+        p.step(0.5)
+        row = np.array(oc.diagonal_row(p))
+        ref = gold[step]
+        err = np.abs(row - ref) / np.maximum(np.abs(ref), 1e-8)
+        assert err.max() < 5e-11, (step, row, ref)
+
+
+def test_mech3d_matches_hdf5_gold():
+    """test/tests/mechanics/mech3d.i vs gold/mech3d.h5 (HDF5Diff)."""
+    g = np.load(f"{G}/mech3d_h5.npz")["F"]
+    p = oc.mech3d_problem()
+    p.initial()
+    for fr in range(g.shape[0]):
+        p.step(0.01)
+        F = p.buf["F"].numpy()
+        rel = np.linalg.norm(F - g[fr]) / np.linalg.norm(g[fr])
+        assert rel < 1e-13, (fr, rel)
+
+
+def test_fft_roundtrip_even_odd():
+    """test/tests/tensor_compute/backandforth.i: fft->ifft is the identity for the even/odd
+    1-3-D sizes used there (gold difference exactly 0 at CSV precision)."""
+    torch.manual_seed(1)
+    for shape in [(10,), (11,), (8, 9), (9, 8), (13, 12), (4, 5, 6), (5, 4, 7)]:
+        d = om.Domain(len(shape), list(shape), (0, 0, 0), (1.0, 1.0, 1.0))
+        a = torch.rand(shape, dtype=torch.float64)
+        assert (d.ifft(d.fft(a)) - a).abs().max() < 1e-14
+
+
+def test_gradient_gold():
+    """test/tests/gradient/gradient.i vs gold/gradient_out.csv (sum of |grad - analytic|)."""
+    gold = np.load(f"{G}/csv_golds.npz")["gradient_out"]
+    import math
+    d = om.Domain(3, [40, 40, 40], (0, 0, 0), (2 * math.pi, 4 * math.pi, 6 * math.pi))
+    p = om.Problem(d)
+    ops = [om.ParsedCompute(p, "s", "sin(x)+sin(y)+sin(z)", extra_symbols=True),
+           om.ParsedCompute(p, "cx", "cos(x)", extra_symbols=True),
+           om.ParsedCompute(p, "cy", "cos(y)", extra_symbols=True),
+           om.ParsedCompute(p, "cz", "cos(z)", extra_symbols=True),
+           om.FFTGradient(p, "gx", "s", 0), om.FFTGradient(p, "gy", "s", 1),
+           om.FFTGradient(p, "gz", "s", 2),
+           om.ParsedCompute(p, "diff", "abs(gx - cx)+abs(gy - cy)+abs(gz - cz)",
+                            inputs=["gx", "gy", "gz", "cx", "cy", "cz"])]
+    for o in ops:
+        o.compute()
+    val = om.pp_integral(p, "diff")
+    # round-off sized quantity: agree in magnitude with the reference's 7.6e-12
+    assert val < 10 * gold[1, 1] and val > 0.0
+
+
+# ---------------------------------------------------------------- parser known answers
+# unit/src/ParsedTensorTest.C:206-309 (Substitute), :411-543 (Simplify), :398-407, :683-697
+def test_parser_substitute_strings():
+    s = lambda e, v, r: xp.to_string(xp.substitute(xp.parse(e), v, xp.parse(r)))  # noqa: E731
+    assert s("x + y", "x", "2*z") == "((2.000000 * z) + y)"
+    assert s("x * y", "x", "2+z") == "((2.000000 + z) * y)"
+    assert s("sin(x) + cos(x) * x", "x", "y^2") == \
+        "(sin((y ^ 2.000000)) + (cos((y ^ 2.000000)) * (y ^ 2.000000)))"
+    assert s("a := x + 1; a * x", "x", "y + z") == "a:=((y + z) + 1.000000); (a * (y + z))"
+    assert s("a := x + 1; a * x", "a", "y + z") == "a:=(x + 1.000000); (a * x)"
+    assert s("x + y + z", "y", "42") == "((x + 42.000000) + z)"
+    assert s("a := x; b := a + 1; b * x", "x", "2*z") == \
+        "a:=(2.000000 * z); b:=(a + 1.000000); (b * (2.000000 * z))"
+    assert s("r := x^2 + y^2; sqrt(r) + r", "x", "t + 1") == \
+        "r:=(((t + 1.000000) ^ 2.000000) + (y ^ 2.000000)); (sqrt(r) + r)"
+
+
+def test_parser_simplify_strings():
+    s = lambda e: xp.to_string(xp.simplify(xp.parse(e)))  # noqa: E731
+    assert s("2 + 3") == "5.000000"
+    assert s("4 * 5") == "20.000000"
+    assert s("2 ^ 3") == "8.000000"
+    assert s("x * 0") == "0.000000"
+    assert s("x * 1") == "x"
+    assert s("x + 0") == "x"
+    assert s("x - 0") == "x"
+    assert s("x / 1") == "x"
+    assert s("x ^ 0") == "1.000000"
+    assert s("x ^ 1") == "x"
+    assert s("(x + 0) * 1 + 0") == "x"
+    assert s("a := 2 + 3; a * x") == "a:=5.000000; (a * x)"
+    assert s("sqrt(4) + log(1) + exp(0)") == "3.000000"
+    assert xp.to_string(xp.simplify(xp.differentiate(xp.parse("x + y"), "z"))) == "0.000000"
+    assert xp.to_string(xp.simplify(xp.differentiate(xp.parse("x + pi", {"pi"}), "x"))) == \
+        "1.000000"
+
+
+def test_parser_rejects():
+    for bad in ["x + ", "(x + y", "x + y)", "sin(x", "a := ; x + a", "x + * y", "", "1.2.3 + x",
+                "x^-1", ".5*x"]:
+        with pytest.raises(ValueError):
+            xp.parse(bad)
+
+
+def test_parser_eval_known_answers():
+    """unit/src/ParsedTensorTest.C:138-203: expression -> gold tensor, plus finite-difference
+    check of the symbolic derivatives."""
+    x = torch.linspace(0.1, 2.01, 11, dtype=torch.float64).unsqueeze(1)
+    y = torch.linspace(0.11, 3.02, 15, dtype=torch.float64).unsqueeze(0)
+    n = torch.max(x * y) * 1.01
+    cases = {
+        "hypot(x,y)": torch.hypot(x, y), "sqrt(x^2+y^2+n)": torch.sqrt(x * x + y * y + n),
+        "tan((x-y)/2)": torch.tan((x - y) / 2.0), "tanh(x-y)": torch.tanh(x - y),
+        "atan(x + y)": torch.atan(x + y), "asin((x * y / 2) / n)": torch.asin((x * y / 2.0) / n),
+        "acosh(x+y+1)": torch.acosh(x + y + 1), "atan2(x,y)": torch.atan2(x, y),
+        "1/sqrt(x+y)": 1.0 / torch.sqrt(x + y), "-x": -x + 0 * y,
+        "rsqrt(x*y)": 1.0 / torch.sqrt(x * y), "exp2(x*y)": torch.pow(2.0, x * y),
+        "(x*y) % 1.5": torch.remainder(x * y, 1.5), "pow(y, x)": torch.pow(y, x),
+        "min(x^3,y^2)": torch.minimum(x * x * x, y * y), "pow(2, x)": torch.pow(2, x) + 0 * y,
+        "if(x<1 | y>=2, x, y)": torch.where(torch.logical_or(x < 1, y >= 2), x, y),
+        "if(x<=1 & y>2, x*x, 3*y)": torch.where(torch.logical_and(x <= 1, y > 2), x * x, y * 3),
+        "r2:=x^2+y^2; sqrt(r2)": torch.sqrt(x * x + y * y),
+    }
+    eps = 1e-6
+    for expr, gold in cases.items():
+        f = xp.ParsedTensor(expr, ["x", "y", "n"])
+        f.compile()
+        r = f.eval([x, y, n])
+        assert (r - gold).abs().max() < 1e-12, expr
+        if expr.startswith("if(") or "%" in expr:
+            continue
+        for var, pert in [("x", [x + eps, y, n]), ("y", [x, y + eps, n])]:
+            dfd = (f.eval(pert) - r) / eps
+            g = xp.ParsedTensor(expr, ["x", "y", "n"])
+            g.differentiate(var)
+            g.compile()
+            ds = g.eval([x, y, n])
+            ad = (ds - dfd).abs()
+            assert ((ad / (dfd.abs() + eps)).max() < 1e-5) or ad.max() < 1e-6, (expr, var)
+    for expr, var, deriv in [("y/x", "x", "-y/x^2"), ("y/x", "y", "1/x"),
+                             ("x2:=x^2; sinx2:=sin(x2); 4*sinx2", "x", "8*x*cos(x*x)"),
+                             ("a:=sin(x^2); a + 2*a + 3*a", "x", "12*x*cos(x^2)"),
+                             ("max(x^2,sin(4*y))", "y", "if(x^2>=sin(4*y),0,4*cos(4*y))")]:
+        a = xp.ParsedTensor(expr, ["x", "y", "n"])
+        a.differentiate(var)
+        a.compile()
+        b = xp.ParsedTensor(deriv, ["x", "y", "n"])
+        b.compile()
+        r1, r2 = a.eval([x, y, n]), b.eval([x, y, n])
+        assert ((r1 - r2).abs() / (r1.abs() + 1e-12)).max() < 1e-5, expr
+
+
+def test_conjugate_gradient_iteration_counts():
+    """unit/src/ConjugateGradientTest.C:12-37: 2x2 SPD -> 2 its, 4x4 SPD -> 4 its."""
+    A2 = torch.tensor([[4.0, 1.0], [1.0, 3.0]], dtype=torch.float64)
+    b2 = torch.tensor([1.0, 2.0], dtype=torch.float64)
+    x, its, _ = om.conjugate_gradient(lambda v: A2 @ v, b2, None, 1e-10, 0)
+    assert its == 2 and torch.allclose(A2 @ x, b2, atol=1e-9)
+    A4 = torch.tensor([[10.0, 1, 2, 3], [1, 9, -1, 2], [2, -1, 7, 3], [3, 2, 3, 12]],
+                      dtype=torch.float64)
+    b4 = torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64)
+    x, its, _ = om.conjugate_gradient(lambda v: A4 @ v, b4, None, 1e-10, 0)
+    assert its == 4 and torch.allclose(A4 @ x, b4, atol=1e-9)
