@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py - steps/s and HBM GB/s of the 3-D FFT Cahn-Hilliard 512^3 float64 substep.
+
+One "step" = one semi-implicit solver SUBSTEP: 2 forward + 1 inverse real
+3-D FFT with the real-space nonlinearity and the k-space AB2 update fused into five HBM
+passes.  Workload = CH-3D-512 (examples/cahn_hilliard/cahnhilliard2.i at n = 512, dx kept),
+synthetic random initial condition, steady state AB2 (one old nonlinear term in flight).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's libTorch CPU path
+(oracle port, all host threads) on the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "steps/s for 3D FFT Cahn-Hilliard 512^3 float64 semi-implicit substep"
+
+
+def algorithmic_bytes(n, nold):
+    """B_alg = 2 S_r + (13 + nold) S_c per substep (fp64)."""
+    s_r = n ** 3 * 8
+    s_c = n * n * (n // 2 + 1) * 16
+    per_pass = {
+        "P1 z r2c (c + i f'(c))": s_r + 2 * s_c,
+        "P2 y forward x2": 4 * s_c,
+        "P3 x fwd + update + x inv": (2 + nold) * s_c + 2 * s_c,
+        "P4 y inverse": 2 * s_c,
+        "P5 z c2r": s_c + s_r,
+    }
+    return s_r, s_c, per_pass
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_substep_fn(n):
+    """The reference's libTorch CPU substep (oracle port) on the bench workload."""
+    import torch
+    import oracle_cases as oc
+    torch.set_num_threads(os.cpu_count())  # TensorProblem::init, src/problems/TensorProblem.C:77-82
+    L = n * 8 * math.pi / 200
+    p = oc.ch_problem(3, n, L, substeps=1)
+    p.initial()
+    p.step(1e-3)   # MOOSE step 1 (no history, quirk Q1)
+    p.step(1e-3)   # step 2 pushes history -> AB2 from here on
+    return p, (lambda: p.step(1e-3))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import torch
+    n = args.n
+    p, step = oracle_substep_fn(n)
+    budget_s = 200.0
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    warm = max(0, min(args.warmup - 1, int(20.0 / max(first, 1e-9))))
+    for _ in range(warm):
+        step()
+    k = max(1, min(args.steps, int(budget_s / max(first, 1e-9))))
+    ts = []
+    for _ in range(k):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    per = sum(ts) / len(ts)
+    val = 1.0 / per
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "substeps/s", "n_gpus": args.gpus,
+        "steps": k, "warmup": warm + 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CH-3D-{n}: cahnhilliard2.i at n={n}, AB2, libTorch CPU path (oracle port)",
+                   "requested_steps": args.steps},
+        "cpu_baseline": {"value": val, "unit": "substeps/s", "cores": cores, "kind": "port",
+                         "sample": f"{k} full {n}^3 substeps after {warm + 1} warm-up"},
+        "e2e": {"value": val, "unit": "substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def libtorch_cuda_substep_ms(n, L, iters=3):
+    """In-run comparison: what the reference's libTorch-CUDA path executes (cuFFT + separate
+    ATen elementwise kernels), restated with torch ops on the GPU."""
+    import torch
+    dev = torch.device("cuda")
+    dx = L / n
+    kf = (torch.fft.fftfreq(n, dx, dtype=torch.float64) * 2.0 * math.pi).to(dev)
+    kh = (torch.fft.rfftfreq(n, dx, dtype=torch.float64) * 2.0 * math.pi).to(dev)
+    k2 = kf.reshape(n, 1, 1) ** 2 + kf.reshape(1, n, 1) ** 2 + kh.reshape(1, 1, -1) ** 2
+    rshape = (n, n, n // 2 + 1)
+    Mbar = (-k2 * 0.2).contiguous()
+    Lb = (k2 * k2 * -0.001).contiguous()
+    del k2
+    torch.manual_seed(0)
+    c = (torch.rand((n, n, n), dtype=torch.float64) * 0.12 + 0.44).to(dev)
+    Nold = torch.zeros(rshape, dtype=torch.complex128, device=dev)
+    dt = 1e-3
+
+    def step(c, Nold):
+        mu = 0.1 * (2.0 * c) * (c - 1) ** 2 + 0.1 * c ** 2 * (2.0 * (c - 1))
+        mubar = torch.fft.rfftn(mu)
+        N = Mbar * mubar
+        cbar = torch.fft.rfftn(c)
+        ubar = cbar + (dt * 1.5) * N
+        ubar = ubar + (dt * -0.5) * Nold
+        ubar = ubar / (1.0 - dt * Lb)
+        return torch.fft.irfftn(ubar, s=(n, n, n)), N
+
+    for _ in range(2):
+        c, Nold = step(c, Nold)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        c, Nold = step(c, Nold)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    del c, Nold, Mbar, Lb
+    torch.cuda.empty_cache()
+    return ms
+
+
+def run_ours(args, rank, world):
+    import torch
+    from marlin_b200 import capi
+    from marlin_b200.capi import AB_BETA
+
+    if world > 1:
+        from marlin_b200 import slab  # multi-GPU slab decomposition (NCCL all-to-all transposes)
+        return slab.bench(args, rank, world, METRIC)
+
+    n = args.n
+    L = n * 8 * math.pi / 200
+    torch.cuda.set_device(0)
+    ctx = capi.Context(0, capi.F64)
+    ctx.use_torch_stream()
+    ctx.domain_set(3, (n, n, n), (0,) * 3, (L,) * 3)
+    torch.manual_seed(0)
+    host_c = (torch.rand((n, n, n), dtype=torch.float64) * 0.12 + 0.44).pin_memory()
+    c = host_c.cuda()
+    plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
+    dt = 1e-3
+    # reach the AB2 steady state: one AB1 substep, then history in flight
+    plan.substep(c, dt, AB_BETA[0], 0)
+    plan.advance_state()
+
+    def step():
+        plan.substep(c, dt, AB_BETA[1], 1)
+        plan.advance_state()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    ms = total_ms / args.steps
+    value = 1e3 / ms
+
+    # per-pass device times (CUDA events on the launching stream), still under the clock sampler
+    reps = max(3, min(10, args.steps))
+    acc = None
+    for _ in range(reps):
+        t = plan.substep_timed(c, dt, AB_BETA[1], 1)
+        plan.advance_state()
+        acc = t if acc is None else [a + b for a, b in zip(acc, t)]
+    pass_ms = [a / reps for a in acc]
+
+    # end to end through the C ABI with HOST buffers: H2D of c, substep, D2H of c, every step
+    out_host = torch.empty_like(host_c).pin_memory()
+    nbytes = host_c.numel() * 8
+    e2e_steps = max(3, min(args.steps, 10))
+    import ctypes as C
+    lib = capi.lib()
+
+    def e2e_step():
+        lib.mrl_upload(ctx.h, C.c_void_p(c.data_ptr()), C.c_void_p(host_c.data_ptr()), C.c_size_t(nbytes))
+        plan.substep(c, dt, AB_BETA[1], 1)
+        plan.advance_state()
+        lib.mrl_download(ctx.h, C.c_void_p(out_host.data_ptr()), C.c_void_p(c.data_ptr()), C.c_size_t(nbytes))
+        ctx.synchronize()
+
+    e2e_step()
+    t0 = time.perf_counter()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    clocks = sampler.stop()
+
+    s_r, s_c, per_pass = algorithmic_bytes(n, 1)
+    b_alg = 2 * s_r + 14 * s_c
+    names = list(per_pass.keys())
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    passes = []
+    for nm, t in zip(names, pass_ms):
+        passes.append({"pass": nm, "ms": round(t, 4), "alg_gb": round(per_pass[nm] / 1e9, 4),
+                       "gbs": round(per_pass[nm] / 1e9 / (t / 1e3), 1)})
+    dom = max(range(len(pass_ms)), key=lambda i: pass_ms[i])
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(names[dom])
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": names[dom], "achieved": passes[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": round(passes[dom]["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            "step_achieved": round(b_alg / 1e9 / (ms / 1e3), 1), "step_frac": round(b_alg / 1e9 / (ms / 1e3) / peak, 4),
+            "step_alg_gb": round(b_alg / 1e9, 3), "passes": passes}
+
+    # in-run comparisons
+    del out_host
+    plan.close()
+    del c
+    torch.cuda.empty_cache()
+    try:
+        cufft_ms = libtorch_cuda_substep_ms(n, L)
+    except Exception as ex:  # e.g. out of memory for the un-fused temporaries
+        cufft_ms = None
+        print(f"# libtorch-cuda comparison skipped: {ex}", file=sys.stderr)
+
+    cpu = None
+    if not args.no_cpu:
+        p, ostep = oracle_substep_fn(n)
+        ostep()
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ostep()
+            ts.append(time.perf_counter() - t0)
+        import torch as _t
+        cpu = {"value": 1.0 / (sum(ts) / len(ts)), "unit": "substeps/s", "cores": _t.get_num_threads(), "kind": "port",
+               "sample": f"2 full {n}^3 substeps after 3 warm-up substeps (libTorch CPU restatement of the reference path)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "substeps/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CH-3D-{n}: examples/cahn_hilliard/cahnhilliard2.i at n={n} (dx kept), AB2 steady state, "
+                               "semi-implicit substep fused into 5 HBM passes",
+                   "l2": f"inputs larger than L2 (each field {s_r / 1e9:.2f} GB vs 126 MB L2)", "parallelism": "1 GPU"},
+        "clocks": clocks,
+        "e2e": {"value": 1e3 / e2e_ms, "unit": "substeps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nbytes,
+                "d2h_bytes_per_step": nbytes},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "libtorch_cuda_ms_per_step": cufft_ms,
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/* marlin_b200 - C ABI of the B200-native spectral time-step path.
+ *
+ * This is the drop-in boundary: the entry points below are what Marlin's host objects call
+ * instead of dispatching libTorch ops.  Each one cites the reference interface it replaces
+ * (paths relative to the idaholab/marlin repository root).  Plain pointers and sizes only;
+ * all `dev` pointers are CUDA device pointers on the context's device; all calls are
+ * asynchronous on the context's stream unless stated otherwise.  Every function returns 0 on
+ * success or a negative mrl_status; mrl_last_error() gives the message (thread-local).
+ * There is no CPU fallback: without a CUDA device mrl_create() fails.
+ *
+ * Layout contract (src/actions/DomainAction.C:227-338, :854-867, :1054-1066):
+ *   real fields     C-order [nx][ny][nz]           (z fastest), `dim` leading dims used
+ *   reciprocal      C-order [nx][ny][nz/2+1] complex (re,im interleaved), half spectrum on the
+ *                   LAST spatial axis, forward unnormalised, inverse scaled by 1/N
+ *   batched fields  [batch][...] (batch slowest)
+ *   axes            cell centred linspace(min+dx/2, max-dx/2, n); reciprocal axes
+ *                   2*pi*fftfreq(n,dx) (2*pi*rfftfreq on the last axis), Nyquist kept
+ */
+#ifndef MARLIN_B200_H
+#define MARLIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrl_context mrl_context;
+typedef struct mrl_split_plan mrl_split_plan;
+
+enum mrl_status {
+  MRL_OK = 0,
+  MRL_ERR_INVALID = -1,   /* bad argument */
+  MRL_ERR_CUDA = -2,      /* CUDA runtime error */
+  MRL_ERR_NO_DEVICE = -3, /* no usable CUDA device (there is no CPU path) */
+  MRL_ERR_UNSUPPORTED = -4,
+  MRL_ERR_PARSE = -5      /* expression syntax / semantic error */
+};
+enum mrl_precision { MRL_F64 = 0, MRL_F32 = 1 };
+
+/* ---- context ---------------------------------------------------------------------------
+ * Replaces the global device / precision selection of src/utils/MarlinUtils.C:17-59 and
+ * src/base/MarlinApp.C:27-54 ([Domain] device_names, floating_precision).               */
+int mrl_create(int device, int precision, mrl_context **out);
+int mrl_destroy(mrl_context *ctx);
+const char *mrl_last_error(void);
+const char *mrl_version(void);
+int mrl_set_stream(mrl_context *ctx, void *cuda_stream); /* run on a caller-owned stream */
+int mrl_synchronize(mrl_context *ctx);                   /* block until the stream drains */
+int mrl_precision_of(const mrl_context *ctx);
+int mrl_launch_count(const mrl_context *ctx, int64_t *count); /* kernels launched so far */
+
+/* ---- domain ----------------------------------------------------------------------------
+ * DomainAction ctor + gridChanged(), src/actions/DomainAction.C:94-224, :227-338.
+ * n/min/max have 3 entries; entries >= dim are ignored (treated as n=1).                  */
+int mrl_domain_set(mrl_context *ctx, int dim, const int64_t *n, const double *min, const double *max);
+/* getShape()/getReciprocalShape(), include/actions/DomainAction.h:31-73 (3 entries, 1-padded) */
+int mrl_domain_shape(const mrl_context *ctx, int64_t *real_shape, int64_t *reciprocal_shape);
+/* getAxis(d)/getReciprocalAxis(d): copies the n[d] (or n[d]/2+1) float64 axis values to host.
+ * Pure host arithmetic, usable without a device through mrl_axis_values().                 */
+int mrl_domain_axis(const mrl_context *ctx, int d, int reciprocal, double *host_out);
+int mrl_axis_values(int64_t n, double min, double max, int reciprocal, int half, double *host_out);
+
+/* ---- device memory (PlainTensorBuffer::init / makeCPUCopy,
+ *      src/tensor_buffers/PlainTensorBuffer.C:30-52) ----------------------------------- */
+int mrl_malloc(mrl_context *ctx, size_t bytes, void **dev);
+int mrl_free(mrl_context *ctx, void *dev);
+int mrl_memset(mrl_context *ctx, void *dev, int value, size_t bytes);
+int mrl_upload(mrl_context *ctx, void *dev, const void *host, size_t bytes);   /* async H2D */
+int mrl_download(mrl_context *ctx, void *host, const void *dev, size_t bytes); /* async D2H */
+int mrl_copy(mrl_context *ctx, void *dst_dev, const void *src_dev, size_t bytes);
+
+/* ---- FFT: DomainAction::fft / ifft (include/actions/DomainAction.h:75-76;
+ *      fftSerial src/actions/DomainAction.C:854-867, ifft :1054-1066) and the
+ *      ForwardFFT / InverseFFT operators (src/tensor_computes/PerformFFT.C:34-40).
+ *      in and out must not overlap.  `batch` leading (slowest) fields.                    */
+int mrl_rfftn(mrl_context *ctx, const void *in_real_dev, void *out_cplx_dev, int batch);
+int mrl_irfftn(mrl_context *ctx, const void *in_cplx_dev, void *out_real_dev, int batch);
+
+/* ---- k-space constants: ReciprocalLaplacianFactor::computeBuffer
+ *      (src/tensor_computes/ReciprocalLaplacianFactor.C:30, kind 0: -k2*factor) and
+ *      ReciprocalLaplacianSquareFactor::computeBuffer
+ *      (src/tensor_computes/ReciprocalLaplacianSquareFactor.C:31, kind 1: k2*k2*factor).
+ *      out: real, reciprocal shape.                                                        */
+enum mrl_kfactor_kind { MRL_KFACTOR_LAPLACIAN = 0, MRL_KFACTOR_LAPLACIAN_SQUARE = 1 };
+int mrl_kfactor(mrl_context *ctx, int kind, double factor, void *out_real_dev);
+
+/* ---- un-fused pointwise pieces of the solver (generic path) ----------------------------
+ * out = a*b, a real / b complex, reciprocal shape (ParsedCompute 'Mbar*mubar').           */
+int mrl_mul_real_complex(mrl_context *ctx, const void *a_real_dev, const void *b_cplx_dev, void *out_cplx_dev);
+/* ubar = (cbar + dt*beta0*N + sum_i dt*beta_{i+1}*Nold[i]) / (1 - dt*L); L may be NULL.
+ * AdamsBashforthMoulton::substep, src/tensor_solver/AdamsBashforthMoulton.C:94-99.        */
+int mrl_ab_update(mrl_context *ctx, void *ubar_dev, const void *cbar_dev, const void *N_dev, const void *L_real_dev,
+                  double dt, const double *beta, int nold, const void *const *Nold_dev);
+
+/* ---- reductions behind the postprocessors (src/postprocessors/Tensor*Postprocessor.C) --
+ * Synchronous: returns the value on the host.                                             */
+enum mrl_reduce_op { MRL_SUM = 0, MRL_MIN = 1, MRL_MAX = 2, MRL_SUMSQ = 3 };
+int mrl_reduce(mrl_context *ctx, int op, const void *real_dev, int64_t count, double *host_out);
+
+/* ---- fused semi-implicit substep (one solver variable) ---------------------------------
+ * Replaces, for the canonical split-operator pattern
+ *     g   = F(c)                      ParsedCompute   (src/tensor_computes/ParsedCompute.C:184)
+ *     g^  = fft(g), c^ = fft(c)       ForwardFFT      (src/tensor_computes/PerformFFT.C:34)
+ *     N   = Mbar * g^                 ParsedCompute
+ *     u^  = (c^ + sum dt*beta*N_i)/(1 - dt*L);  c = ifft(u^)
+ *                                     AdamsBashforthMoulton::substep
+ *                                     (src/tensor_solver/AdamsBashforthMoulton.C:60-101)
+ * the ~15 libTorch launches of one substep by five HBM passes (three in 2-D).            */
+enum mrl_nonlin_kind {
+  MRL_NONLIN_DOUBLE_WELL = 0, /* F(c) = d/dc[A (c-a)^2 (b-c)^2]; params = {A,a,b} */
+  MRL_NONLIN_EXPR = 1         /* F given by a compiled expression handle (mrl_expr) */
+};
+typedef struct mrl_split_desc {
+  int nonlin_kind;
+  double nonlin_params[4];
+  void *nonlin_expr;        /* mrl_expr*, when nonlin_kind == MRL_NONLIN_EXPR */
+  int M_closed_form;        /* 1: Mbar = -k2*M_factor computed on the fly; 0: read M_real_dev */
+  double M_factor;
+  const void *M_real_dev;   /* real, reciprocal shape */
+  int has_L;                /* linear_reciprocal given ("0" in the input = none) */
+  int L_closed_form;        /* 1: L = k2*k2*L_factor on the fly; 0: read L_real_dev */
+  double L_factor;
+  const void *L_real_dev;
+  int history;              /* old nonlinear terms kept = max(predictor_order, corrector_order) - 1 */
+  void *g_out_real_dev;     /* optional: receives g = F(c) each substep (NULL = not materialised) */
+} mrl_split_desc;
+
+int mrl_split_plan_create(mrl_context *ctx, const mrl_split_desc *desc, mrl_split_plan **out);
+int mrl_split_plan_destroy(mrl_split_plan *plan);
+/* One predictor substep, c updated in place.  beta[0] multiplies the new nonlinear term,
+ * beta[1..nold] the stored old ones (newest first); nold <= states currently stored.      */
+int mrl_split_substep(mrl_split_plan *plan, void *c_real_dev, double dt, const double *beta, int nold);
+/* TensorBuffer<T>::advanceState (include/tensor_buffers/TensorBuffer.h:64-79): the newest
+ * nonlinear term becomes old state 0.  Returns the number of stored states through *stored. */
+int mrl_split_advance_state(mrl_split_plan *plan, int *stored);
+int mrl_split_clear_states(mrl_split_plan *plan);
+/* Same as mrl_split_substep but brackets every pass with CUDA events on the context's stream
+ * and returns the per-pass device times in milliseconds (pass_ms has
+ * mrl_split_launches_per_substep() entries).  Synchronous; for measurement only.          */
+int mrl_split_substep_timed(mrl_split_plan *plan, void *c_real_dev, double dt, const double *beta, int nold,
+                            float *pass_ms);
+/* HBM passes / kernels one substep launches (for bench bookkeeping) */
+int mrl_split_launches_per_substep(const mrl_split_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARLIN_B200_H */

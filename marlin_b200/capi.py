@@ -1,0 +1,242 @@
+"""ctypes binding of libmarlin_b200.so (the C ABI in include/marlin_b200.h).
+
+PyTorch is used here only as plumbing: it owns the device allocations handed to the
+library as raw pointers.  There is no CPU or eager fallback: if the shared library is
+missing, or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmarlin_b200.so")
+
+F64, F32 = 0, 1
+KFACTOR_LAPLACIAN, KFACTOR_LAPLACIAN_SQUARE = 0, 1
+SUM, MIN, MAX, SUMSQ = 0, 1, 2, 3
+NONLIN_DOUBLE_WELL, NONLIN_EXPR = 0, 1
+
+
+# Adams-Bashforth predictor coefficients exactly as coded in the reference
+# (src/tensor_solver/AdamsBashforthMoulton.C:67-73; the AB5 leading entry 190/720 is the
+# reference's value and is reproduced as is).
+AB_BETA = [
+    [1.0, 0.0, 0.0, 0.0, 0.0],
+    [3.0 / 2.0, -1.0 / 2.0, 0.0, 0.0, 0.0],
+    [23.0 / 12.0, -16.0 / 12.0, 5.0 / 12.0, 0.0, 0.0],
+    [55.0 / 24.0, -59.0 / 24.0, 37.0 / 24.0, -9.0 / 24.0, 0.0],
+    [190.0 / 720.0, -2774.0 / 720.0, 2616.0 / 720.0, -1274.0 / 720.0, 251.0 / 720.0],
+]
+
+
+class MarlinError(RuntimeError):
+    pass
+
+
+class SplitDesc(C.Structure):
+    _fields_ = [
+        ("nonlin_kind", C.c_int), ("nonlin_params", C.c_double * 4), ("nonlin_expr", C.c_void_p),
+        ("M_closed_form", C.c_int), ("M_factor", C.c_double), ("M_real_dev", C.c_void_p),
+        ("has_L", C.c_int), ("L_closed_form", C.c_int), ("L_factor", C.c_double),
+        ("L_real_dev", C.c_void_p), ("history", C.c_int), ("g_out_real_dev", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (built by `make` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MarlinError(f"{LIB_PATH} not found: build it with `make` (nvcc, sm_100a). "
+                              "marlin_b200 has no fallback path.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.mrl_last_error.restype = C.c_char_p
+        _lib.mrl_version.restype = C.c_char_p
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise MarlinError(f"marlin_b200 error {rc}: {lib().mrl_last_error().decode()}")
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def axis_values(n, mn, mx, reciprocal=False, half=False):
+    """Host-side axis arithmetic (no device needed)."""
+    m = (n // 2 + 1) if (reciprocal and half) else n
+    out = (C.c_double * m)()
+    _ck(lib().mrl_axis_values(C.c_int64(n), C.c_double(mn), C.c_double(mx), int(reciprocal), int(half),
+                              out))
+    return list(out)
+
+
+class Context:
+    """One device context (mirrors DomainAction + the global device/precision choice)."""
+
+    def __init__(self, device=0, precision=F64):
+        self.h = C.c_void_p()
+        _ck(lib().mrl_create(int(device), int(precision), C.byref(self.h)))
+        self.device = torch.device("cuda", device)
+        self.precision = precision
+        self.rdtype = torch.float64 if precision == F64 else torch.float32
+        self.cdtype = torch.complex128 if precision == F64 else torch.complex64
+        self.dim = 0
+
+    def close(self):
+        if self.h:
+            lib().mrl_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        _ck(lib().mrl_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def synchronize(self):
+        _ck(lib().mrl_synchronize(self.h))
+
+    def launch_count(self):
+        v = C.c_int64()
+        _ck(lib().mrl_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    # ---- domain
+    def domain_set(self, dim, n, mins=(0.0, 0.0, 0.0), maxs=(1.0, 1.0, 1.0)):
+        n3 = (C.c_int64 * 3)(*[int(n[d]) if d < dim else 1 for d in range(3)])
+        mn = (C.c_double * 3)(*[float(mins[d]) if d < len(mins) else 0.0 for d in range(3)])
+        mx = (C.c_double * 3)(*[float(maxs[d]) if d < len(maxs) else 1.0 for d in range(3)])
+        _ck(lib().mrl_domain_set(self.h, int(dim), n3, mn, mx))
+        self.dim = dim
+        rs, ks = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+        _ck(lib().mrl_domain_shape(self.h, rs, ks))
+        self.shape = [rs[d] for d in range(dim)]
+        self.rshape = [ks[d] for d in range(dim)]
+
+    def axis(self, d, reciprocal=False):
+        m = (self.rshape[d] if reciprocal else self.shape[d]) if d < self.dim else 1
+        out = (C.c_double * m)()
+        _ck(lib().mrl_domain_axis(self.h, d, int(reciprocal), out))
+        return torch.tensor(list(out), dtype=torch.float64)
+
+    # ---- FFT
+    def _batch(self, t, shape):
+        nb = t.dim() - len(shape)
+        if nb < 0 or list(t.shape[nb:]) != list(shape):
+            raise MarlinError(f"tensor shape {tuple(t.shape)} does not end with the domain shape {shape}")
+        b = 1
+        for s in t.shape[:nb]:
+            b *= s
+        return b, list(t.shape[:nb])
+
+    def rfftn(self, t):
+        assert t.is_cuda and t.dtype == self.rdtype and t.is_contiguous()
+        b, lead = self._batch(t, self.shape)
+        out = torch.empty(lead + self.rshape, dtype=self.cdtype, device=t.device)
+        _ck(lib().mrl_rfftn(self.h, _p(t), _p(out), b))
+        return out
+
+    def irfftn(self, t):
+        assert t.is_cuda and t.dtype == self.cdtype and t.is_contiguous()
+        b, lead = self._batch(t, self.rshape)
+        out = torch.empty(lead + self.shape, dtype=self.rdtype, device=t.device)
+        _ck(lib().mrl_irfftn(self.h, _p(t), _p(out), b))
+        return out
+
+    # ---- pointwise
+    def kfactor(self, kind, factor):
+        out = torch.empty(self.rshape, dtype=self.rdtype, device=self.device)
+        _ck(lib().mrl_kfactor(self.h, int(kind), C.c_double(factor), _p(out)))
+        return out
+
+    def mul_real_complex(self, a, b):
+        out = torch.empty_like(b)
+        _ck(lib().mrl_mul_real_complex(self.h, _p(a), _p(b), _p(out)))
+        return out
+
+    def ab_update(self, cbar, N, L, dt, beta, Nold=()):
+        out = torch.empty_like(cbar)
+        nold = len(Nold)
+        arr = (C.c_void_p * max(nold, 1))(*[t.data_ptr() for t in Nold])
+        b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
+        _ck(lib().mrl_ab_update(self.h, _p(out), _p(cbar), _p(N), _p(L), C.c_double(dt), b, nold, arr))
+        return out
+
+    def reduce(self, op, t):
+        assert t.is_contiguous() and t.dtype == self.rdtype
+        v = C.c_double()
+        _ck(lib().mrl_reduce(self.h, int(op), _p(t), C.c_int64(t.numel()), C.byref(v)))
+        return v.value
+
+    # ---- fused split-operator plan
+    def split_plan(self, **kw):
+        return SplitPlan(self, **kw)
+
+
+class SplitPlan:
+    """Fused semi-implicit substep of one variable (AdamsBashforthMoulton::substep for the
+    canonical Cahn-Hilliard compute graph)."""
+
+    def __init__(self, ctx, double_well=None, expr=None, M_factor=None, M_buffer=None, L_factor=None,
+                 L_buffer=None, has_L=True, history=1, g_out=None):
+        self.ctx = ctx
+        d = SplitDesc()
+        if expr is not None:
+            d.nonlin_kind = NONLIN_EXPR
+            d.nonlin_expr = expr.h
+        else:
+            d.nonlin_kind = NONLIN_DOUBLE_WELL
+            A, a, b = double_well
+            d.nonlin_params = (C.c_double * 4)(A, a, b, 0.0)
+        d.M_closed_form = int(M_buffer is None)
+        d.M_factor = float(M_factor or 0.0)
+        d.M_real_dev = M_buffer.data_ptr() if M_buffer is not None else None
+        d.has_L = int(has_L)
+        d.L_closed_form = int(L_buffer is None)
+        d.L_factor = float(L_factor or 0.0)
+        d.L_real_dev = L_buffer.data_ptr() if L_buffer is not None else None
+        d.history = history
+        d.g_out_real_dev = g_out.data_ptr() if g_out is not None else None
+        self._keep = (M_buffer, L_buffer, g_out, expr)
+        self.h = C.c_void_p()
+        _ck(lib().mrl_split_plan_create(ctx.h, C.byref(d), C.byref(self.h)))
+        self.launches_per_substep = lib().mrl_split_launches_per_substep(self.h)
+
+    def substep(self, c, dt, beta, nold):
+        b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
+        _ck(lib().mrl_split_substep(self.h, _p(c), C.c_double(dt), b, int(nold)))
+
+    def substep_timed(self, c, dt, beta, nold):
+        b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
+        ms = (C.c_float * 8)()
+        _ck(lib().mrl_split_substep_timed(self.h, _p(c), C.c_double(dt), b, int(nold), ms))
+        return [ms[i] for i in range(self.launches_per_substep)]
+
+    def advance_state(self):
+        v = C.c_int()
+        _ck(lib().mrl_split_advance_state(self.h, C.byref(v)))
+        return v.value
+
+    def clear_states(self):
+        _ck(lib().mrl_split_clear_states(self.h))
+
+    def close(self):
+        if self.h:
+            lib().mrl_split_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

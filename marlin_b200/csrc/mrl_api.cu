@@ -1,0 +1,612 @@
+// marlin_b200 - implementation of the C ABI declared in include/marlin_b200.h.
+// Host logic only; all device work is in k_*.cu (hand-written sm_100a kernels).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/marlin_b200.h"
+#include "mrl_internal.h"
+
+using namespace mrl;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+int mrl_fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+extern "C" const char *mrl_last_error(void) { return g_err.c_str(); }
+extern "C" const char *mrl_version(void) { return "marlin_b200 0.1 (sm_100a)"; }
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return mrl_fail(MRL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                      __FILE__, __LINE__);                                               \
+  } while (0)
+#define CKL(ctx, call) \
+  do {                 \
+    (ctx)->launches++; \
+    CK(call);          \
+  } while (0)
+
+// ------------------------------------------------------------------------------ axes
+// Bit-compatible with ATen: linspace (aten/src/ATen/native/cpu/RangeFactoriesKernel.cpp:
+// symmetric start+step*i / end-step*(steps-1-i) halves) and fft_fftfreq / fft_rfftfreq
+// (arange * (1/(n*d))), followed by the reference's `freq * 2.0 * pi`
+// (src/actions/DomainAction.C:241-293).
+extern "C" int mrl_axis_values(int64_t n, double min, double max, int reciprocal, int half, double *out) {
+  if (n < 1 || !out || !(max > min)) return mrl_fail(MRL_ERR_INVALID, "mrl_axis_values: bad arguments");
+  const double dx = (max - min) / (double)n;
+  if (!reciprocal) {
+    const double start = min + dx / 2.0, end = max - dx / 2.0;
+    if (n == 1) {
+      out[0] = start;
+      return MRL_OK;
+    }
+    const double step = (end - start) / (double)(n - 1);
+    const int64_t halfway = n / 2;
+    // single rounding per value (ATen's vectorised kernel is compiled with FMA contraction)
+    for (int64_t i = 0; i < n; ++i)
+      out[i] = (i < halfway) ? std::fma(step, (double)i, start) : std::fma(-step, (double)(n - i - 1), end);
+    return MRL_OK;
+  }
+  const double pi = 3.14159265358979323846;
+  const double inv = 1.0 / ((double)n * dx);
+  if (half) {
+    for (int64_t k = 0; k <= n / 2; ++k) out[k] = ((double)k * inv) * 2.0 * pi;
+  } else {
+    for (int64_t k = 0; k < n; ++k) {
+      const int64_t ks = (k < (n + 1) / 2) ? k : k - n;
+      out[k] = ((double)ks * inv) * 2.0 * pi;
+    }
+  }
+  return MRL_OK;
+}
+
+// ------------------------------------------------------------------------------ context
+FFTPlanDev mrl::make_fft_plan(int n) {
+  FFTPlanDev p;
+  memset(&p, 0, sizeof p);
+  p.n = n;
+  int m = n;
+  const int pref[] = {8, 4, 2, 3, 5};
+  for (int r : pref)
+    while (m > 1 && m % r == 0) {
+      p.radix[p.nstages++] = r;
+      m /= r;
+    }
+  for (int f = 7; m > 1; f += 2)
+    while (m % f == 0) {
+      p.radix[p.nstages++] = f;
+      m /= f;
+    }
+  return p;
+}
+
+template <class T> static int upload_vec(mrl_context *ctx, const std::vector<double> &h, void **dev) {
+  std::vector<T> t(h.begin(), h.end());
+  CK(cudaMalloc(dev, t.size() * sizeof(T)));
+  CK(cudaMemcpy(*dev, t.data(), t.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MRL_OK;
+}
+
+int mrl_context::twiddles(int n, const void **out) {
+  auto it = tw.find(n);
+  if (it != tw.end()) {
+    *out = it->second;
+    return MRL_OK;
+  }
+  const long double PI = 3.141592653589793238462643383279502884L;
+  std::vector<double> h(2 * (size_t)n);
+  for (int k = 0; k < n; ++k) {
+    const long double a = -2 * PI * (long double)k / (long double)n;
+    h[2 * k] = (double)cosl(a);
+    h[2 * k + 1] = (double)sinl(a);
+  }
+  void *d = nullptr;
+  int rc = precision == MRL_F64 ? upload_vec<double>(this, h, &d) : upload_vec<float>(this, h, &d);
+  if (rc) return rc;
+  tw[n] = d;
+  *out = d;
+  return MRL_OK;
+}
+
+int mrl_context::scratch(size_t bytes, void **out) {
+  if (bytes > scratch_bytes) {
+    if (scratch_ptr) {
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaFree(scratch_ptr));
+      scratch_ptr = nullptr;
+      scratch_bytes = 0;
+    }
+    CK(cudaMalloc(&scratch_ptr, bytes));
+    scratch_bytes = bytes;
+  }
+  *out = scratch_ptr;
+  return MRL_OK;
+}
+
+extern "C" int mrl_create(int device, int precision, mrl_context **out) {
+  if (!out || (precision != MRL_F64 && precision != MRL_F32)) return mrl_fail(MRL_ERR_INVALID, "mrl_create: bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+    return mrl_fail(MRL_ERR_NO_DEVICE, "mrl_create: CUDA device %d not available (%d devices%s%s); marlin_b200 has no CPU path",
+                    device, ndev, e != cudaSuccess ? ", " : "", e != cudaSuccess ? cudaGetErrorString(e) : "");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return mrl_fail(MRL_ERR_NO_DEVICE, "mrl_create: device %d is sm_%d%d; kernels are built for sm_100a only", device,
+                    prop.major, prop.minor);
+  mrl_context *c = new mrl_context();
+  c->device = device;
+  c->precision = precision;
+  c->stream = 0;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return MRL_OK;
+}
+
+extern "C" int mrl_destroy(mrl_context *ctx) {
+  if (!ctx) return MRL_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->tw) cudaFree(kv.second);
+  for (int d = 0; d < 3; ++d) {
+    cudaFree(ctx->axis_dev[d]);
+    cudaFree(ctx->kaxis_dev[d]);
+  }
+  cudaFree(ctx->scratch_ptr);
+  cudaFree(ctx->reduce_dev);
+  if (ctx->reduce_host) cudaFreeHost(ctx->reduce_host);
+  delete ctx;
+  return MRL_OK;
+}
+
+extern "C" int mrl_set_stream(mrl_context *ctx, void *s) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  ctx->stream = (cudaStream_t)s;
+  return MRL_OK;
+}
+extern "C" int mrl_synchronize(mrl_context *ctx) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRL_OK;
+}
+extern "C" int mrl_precision_of(const mrl_context *ctx) { return ctx ? ctx->precision : MRL_ERR_INVALID; }
+extern "C" int mrl_launch_count(const mrl_context *ctx, int64_t *count) {
+  if (!ctx || !count) return mrl_fail(MRL_ERR_INVALID, "null argument");
+  *count = ctx->launches;
+  return MRL_OK;
+}
+
+// ------------------------------------------------------------------------------ domain
+extern "C" int mrl_domain_set(mrl_context *ctx, int dim, const int64_t *n, const double *mn, const double *mx) {
+  if (!ctx || dim < 1 || dim > 3 || !n || !mn || !mx) return mrl_fail(MRL_ERR_INVALID, "mrl_domain_set: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  for (int d = 0; d < dim; ++d) {
+    if (n[d] < 1 || n[d] > (1 << 24)) return mrl_fail(MRL_ERR_INVALID, "mrl_domain_set: bad grid size");
+    // reference: "Max coordinate must be larger than the min coordinate in every dimension"
+    if (!(mx[d] > mn[d]))
+      return mrl_fail(MRL_ERR_INVALID, "Max coordinate must be larger than the min coordinate in every dimension");
+  }
+  ctx->dim = dim;
+  for (int d = 0; d < 3; ++d) {
+    ctx->n[d] = d < dim ? (int)n[d] : 1;
+    ctx->min[d] = d < dim ? mn[d] : 0.0;
+    ctx->max[d] = d < dim ? mx[d] : 1.0;
+    const bool half = (d == dim - 1);
+    ctx->nr[d] = d < dim ? (half ? ctx->n[d] / 2 + 1 : ctx->n[d]) : 1;
+    ctx->axis_h[d].assign(1, 0.0);
+    ctx->kaxis_h[d].assign(1, 0.0);
+    if (d < dim) {
+      ctx->axis_h[d].resize(ctx->n[d]);
+      ctx->kaxis_h[d].resize(ctx->nr[d]);
+      int rc = mrl_axis_values(ctx->n[d], mn[d], mx[d], 0, 0, ctx->axis_h[d].data());
+      if (rc) return rc;
+      rc = mrl_axis_values(ctx->n[d], mn[d], mx[d], 1, half ? 1 : 0, ctx->kaxis_h[d].data());
+      if (rc) return rc;
+    }
+    cudaFree(ctx->axis_dev[d]);
+    cudaFree(ctx->kaxis_dev[d]);
+    ctx->axis_dev[d] = ctx->kaxis_dev[d] = nullptr;
+    int rc;
+    if (ctx->precision == MRL_F64) {
+      if ((rc = upload_vec<double>(ctx, ctx->axis_h[d], &ctx->axis_dev[d]))) return rc;
+      if ((rc = upload_vec<double>(ctx, ctx->kaxis_h[d], &ctx->kaxis_dev[d]))) return rc;
+    } else {
+      if ((rc = upload_vec<float>(ctx, ctx->axis_h[d], &ctx->axis_dev[d]))) return rc;
+      if ((rc = upload_vec<float>(ctx, ctx->kaxis_h[d], &ctx->kaxis_dev[d]))) return rc;
+    }
+  }
+  return MRL_OK;
+}
+
+extern "C" int mrl_domain_shape(const mrl_context *ctx, int64_t *rs, int64_t *ks) {
+  if (!ctx || !ctx->dim) return mrl_fail(MRL_ERR_INVALID, "domain not set");
+  for (int d = 0; d < 3; ++d) {
+    if (rs) rs[d] = ctx->n[d];
+    if (ks) ks[d] = ctx->nr[d];
+  }
+  return MRL_OK;
+}
+
+extern "C" int mrl_domain_axis(const mrl_context *ctx, int d, int reciprocal, double *out) {
+  if (!ctx || !ctx->dim || d < 0 || d > 2 || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_domain_axis: bad arguments");
+  const std::vector<double> &v = reciprocal ? ctx->kaxis_h[d] : ctx->axis_h[d];
+  memcpy(out, v.data(), v.size() * sizeof(double));
+  return MRL_OK;
+}
+
+// ------------------------------------------------------------------------------ memory
+extern "C" int mrl_malloc(mrl_context *ctx, size_t bytes, void **dev) {
+  if (!ctx || !dev) return mrl_fail(MRL_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(dev, bytes ? bytes : 1));
+  return MRL_OK;
+}
+extern "C" int mrl_free(mrl_context *ctx, void *dev) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(dev));
+  return MRL_OK;
+}
+extern "C" int mrl_memset(mrl_context *ctx, void *dev, int value, size_t bytes) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  CK(cudaMemsetAsync(dev, value, bytes, ctx->stream));
+  return MRL_OK;
+}
+extern "C" int mrl_upload(mrl_context *ctx, void *dev, const void *host, size_t bytes) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return MRL_OK;
+}
+extern "C" int mrl_download(mrl_context *ctx, void *host, const void *dev, size_t bytes) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return MRL_OK;
+}
+extern "C" int mrl_copy(mrl_context *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return MRL_OK;
+}
+
+// ------------------------------------------------------------------------------ FFT
+template <class T> static int strided_axis(mrl_context *ctx, const cx<T> *in, cx<T> *out, int nfields, long long field_stride,
+                                           int axis, int batch, int inverse) {
+  const int dim = ctx->dim;
+  const int nc = ctx->nr[dim - 1];
+  long long ncols = nc;
+  for (int b = axis + 1; b < dim - 1; ++b) ncols *= ctx->n[b];
+  long long nouter = batch;
+  for (int b = 0; b < axis; ++b) nouter *= ctx->n[b];
+  StridedIO<T> io;
+  memset(&io, 0, sizeof io);
+  if (nfields > 4) return mrl_fail(MRL_ERR_INVALID, "too many fields");
+  for (int f = 0; f < nfields; ++f) {
+    io.in[f] = in + f * field_stride;
+    io.out[f] = out + f * field_stride;
+  }
+  io.nfields = nfields;
+  io.n = ctx->n[axis];
+  io.ncols = (int)ncols;
+  io.nouter = (int)nouter;
+  io.pitch = ncols;
+  io.outer_stride = (long long)io.n * ncols;
+  io.scale = T(1);
+  io.inverse = inverse;
+  const void *tw;
+  int rc = ctx->twiddles(io.n, &tw);
+  if (rc) return rc;
+  CKL(ctx, launch_strided<T>(ctx->lc(), io, (const cx<T> *)tw, make_fft_plan(io.n)));
+  return MRL_OK;
+}
+
+template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *out, int batch) {
+  const int dim = ctx->dim, nl = ctx->n[dim - 1];
+  long long rows = batch;
+  for (int d = 0; d < dim - 1; ++d) rows *= ctx->n[d];
+  const void *tw;
+  int rc = ctx->twiddles(nl, &tw);
+  if (rc) return rc;
+  CKL(ctx, launch_zfwd_pairs<T>(ctx->lc(), in, out, rows, nl, (const cx<T> *)tw, make_fft_plan(nl)));
+  for (int a = dim - 2; a >= 0; --a)
+    if ((rc = strided_axis<T>(ctx, out, out, 1, 0, a, batch, 0))) return rc;
+  return MRL_OK;
+}
+
+template <class T> static int irfftn_impl(mrl_context *ctx, const cx<T> *in, T *out, int batch) {
+  const int dim = ctx->dim, nl = ctx->n[dim - 1];
+  long long rows = batch, total = batch;
+  for (int d = 0; d < dim - 1; ++d) rows *= ctx->n[d];
+  for (int d = 0; d < dim; ++d) total *= ctx->nr[d];
+  double N = 1;
+  for (int d = 0; d < dim; ++d) N *= ctx->n[d];
+  const cx<T> *src = in;
+  int rc;
+  if (dim > 1) {
+    void *s;
+    if ((rc = ctx->scratch((size_t)total * sizeof(cx<T>), &s))) return rc;
+    cx<T> *sc = (cx<T> *)s;
+    for (int a = 0; a <= dim - 2; ++a) {
+      if ((rc = strided_axis<T>(ctx, src, sc, 1, 0, a, batch, 1))) return rc;
+      src = sc;
+    }
+  }
+  const void *tw;
+  if ((rc = ctx->twiddles(nl, &tw))) return rc;
+  CKL(ctx, launch_zinv_pairs<T>(ctx->lc(), src, out, rows, nl, (T)(1.0 / N), (const cx<T> *)tw, make_fft_plan(nl)));
+  return MRL_OK;
+}
+
+extern "C" int mrl_rfftn(mrl_context *ctx, const void *in, void *out, int batch) {
+  if (!ctx || !ctx->dim || !in || !out || batch < 1) return mrl_fail(MRL_ERR_INVALID, "mrl_rfftn: bad arguments / domain not set");
+  CK(cudaSetDevice(ctx->device));
+  return ctx->precision == MRL_F64 ? rfftn_impl<double>(ctx, (const double *)in, (cx<double> *)out, batch)
+                                   : rfftn_impl<float>(ctx, (const float *)in, (cx<float> *)out, batch);
+}
+extern "C" int mrl_irfftn(mrl_context *ctx, const void *in, void *out, int batch) {
+  if (!ctx || !ctx->dim || !in || !out || batch < 1) return mrl_fail(MRL_ERR_INVALID, "mrl_irfftn: bad arguments / domain not set");
+  CK(cudaSetDevice(ctx->device));
+  return ctx->precision == MRL_F64 ? irfftn_impl<double>(ctx, (const cx<double> *)in, (double *)out, batch)
+                                   : irfftn_impl<float>(ctx, (const cx<float> *)in, (float *)out, batch);
+}
+
+// ------------------------------------------------------------------------------ pointwise
+extern "C" int mrl_kfactor(mrl_context *ctx, int kind, double factor, void *out) {
+  if (!ctx || !ctx->dim || !out || kind < 0 || kind > 1) return mrl_fail(MRL_ERR_INVALID, "mrl_kfactor: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->precision == MRL_F64)
+    CKL(ctx, launch_kfactor<double>(ctx->lc(), (double *)out, (const double *)ctx->kaxis_dev[0], (const double *)ctx->kaxis_dev[1],
+                                    (const double *)ctx->kaxis_dev[2], ctx->nr[0], ctx->nr[1], ctx->nr[2], kind, factor));
+  else
+    CKL(ctx, launch_kfactor<float>(ctx->lc(), (float *)out, (const float *)ctx->kaxis_dev[0], (const float *)ctx->kaxis_dev[1],
+                                   (const float *)ctx->kaxis_dev[2], ctx->nr[0], ctx->nr[1], ctx->nr[2], kind, (float)factor));
+  return MRL_OK;
+}
+
+extern "C" int mrl_mul_real_complex(mrl_context *ctx, const void *a, const void *b, void *out) {
+  if (!ctx || !ctx->dim || !a || !b || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_mul_real_complex: bad arguments");
+  const long long total = ctx->rtotal();
+  if (ctx->precision == MRL_F64)
+    CKL(ctx, launch_mul_rc<double>(ctx->lc(), (cx<double> *)out, (const double *)a, (const cx<double> *)b, total));
+  else
+    CKL(ctx, launch_mul_rc<float>(ctx->lc(), (cx<float> *)out, (const float *)a, (const cx<float> *)b, total));
+  return MRL_OK;
+}
+
+extern "C" int mrl_ab_update(mrl_context *ctx, void *ubar, const void *cbar, const void *N, const void *L, double dt,
+                             const double *beta, int nold, const void *const *Nold) {
+  if (!ctx || !ctx->dim || !ubar || !cbar || !N || !beta || nold < 0 || nold > 4 || (nold && !Nold))
+    return mrl_fail(MRL_ERR_INVALID, "mrl_ab_update: bad arguments");
+  const long long total = ctx->rtotal();
+  if (ctx->precision == MRL_F64) {
+    double bo[4] = {0, 0, 0, 0};
+    for (int i = 0; i < nold; ++i) bo[i] = dt * beta[i + 1];
+    CKL(ctx, launch_ab_update<double>(ctx->lc(), (cx<double> *)ubar, (const cx<double> *)cbar, (const cx<double> *)N,
+                                      (const double *)L, dt, dt * beta[0], nold, (const cx<double> *const *)Nold, bo, total));
+  } else {
+    float bo[4] = {0, 0, 0, 0};
+    for (int i = 0; i < nold; ++i) bo[i] = (float)(dt * beta[i + 1]);
+    CKL(ctx, launch_ab_update<float>(ctx->lc(), (cx<float> *)ubar, (const cx<float> *)cbar, (const cx<float> *)N,
+                                     (const float *)L, (float)dt, (float)(dt * beta[0]), nold, (const cx<float> *const *)Nold,
+                                     bo, total));
+  }
+  return MRL_OK;
+}
+
+// ------------------------------------------------------------------------------ reductions
+extern "C" int mrl_reduce(mrl_context *ctx, int op, const void *in, int64_t count, double *host_out) {
+  if (!ctx || !in || !host_out || count < 1 || op < 0 || op > 3) return mrl_fail(MRL_ERR_INVALID, "mrl_reduce: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  const int nblk = ctx->sm_count * 4;
+  if (!ctx->reduce_dev) {
+    CK(cudaMalloc(&ctx->reduce_dev, nblk * sizeof(double)));
+    CK(cudaMallocHost(&ctx->reduce_host, nblk * sizeof(double)));
+  }
+  ctx->launches++;
+  cudaError_t e = ctx->precision == MRL_F64
+                      ? launch_reduce<double>(ctx->lc(), op, (const double *)in, count, (double *)ctx->reduce_dev, nblk)
+                      : launch_reduce<float>(ctx->lc(), op, (const float *)in, count, (double *)ctx->reduce_dev, nblk);
+  CK(e);
+  CK(cudaMemcpyAsync(ctx->reduce_host, ctx->reduce_dev, nblk * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const double *p = (const double *)ctx->reduce_host;
+  double r = p[0];
+  for (int i = 1; i < nblk; ++i) {
+    if (op == MRL_MIN) r = p[i] < r ? p[i] : r;
+    else if (op == MRL_MAX) r = p[i] > r ? p[i] : r;
+    else r += p[i];
+  }
+  *host_out = r;
+  return MRL_OK;
+}
+
+// ------------------------------------------------------------------------------ fused split plan
+extern "C" int mrl_split_plan_create(mrl_context *ctx, const mrl_split_desc *d, mrl_split_plan **out) {
+  if (!ctx || !ctx->dim || !d || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_split_plan_create: bad arguments");
+  if (ctx->dim < 2)
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "fused split plan needs dim >= 2 (1-D problems use the un-fused operators)");
+  if (d->nonlin_kind != MRL_NONLIN_DOUBLE_WELL && d->nonlin_kind != MRL_NONLIN_EXPR)
+    return mrl_fail(MRL_ERR_INVALID, "unknown nonlin_kind");
+  if (d->nonlin_kind == MRL_NONLIN_EXPR && !d->nonlin_expr) return mrl_fail(MRL_ERR_INVALID, "nonlin_expr is NULL");
+  if (!d->M_closed_form && !d->M_real_dev) return mrl_fail(MRL_ERR_INVALID, "M_real_dev is NULL");
+  if (d->has_L && !d->L_closed_form && !d->L_real_dev) return mrl_fail(MRL_ERR_INVALID, "L_real_dev is NULL");
+  if (d->history < 0 || d->history > 4) return mrl_fail(MRL_ERR_INVALID, "history must be in [0,4]");
+  CK(cudaSetDevice(ctx->device));
+  mrl_split_plan *p = new mrl_split_plan();
+  p->ctx = ctx;
+  p->desc = *d;
+  const size_t esz = ctx->precision == MRL_F64 ? 16 : 8;
+  const size_t sc = (size_t)ctx->rtotal() * esz;
+  cudaError_t e = cudaMalloc(&p->A, 2 * sc);
+  if (e == cudaSuccess) p->B = (char *)p->A + sc;
+  for (int i = 0; e == cudaSuccess && d->history > 0 && i < d->history + 1; ++i) {
+    void *q = nullptr;
+    e = cudaMalloc(&q, sc);
+    if (e == cudaSuccess) p->ring.push_back(q);
+  }
+  if (e != cudaSuccess) {
+    mrl_split_plan_destroy(p);
+    return mrl_fail(MRL_ERR_CUDA, "split plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return MRL_OK;
+}
+
+extern "C" int mrl_split_plan_destroy(mrl_split_plan *p) {
+  if (!p) return MRL_OK;
+  cudaStreamSynchronize(p->ctx->stream);
+  cudaFree(p->A);
+  for (void *q : p->ring) cudaFree(q);
+  delete p;
+  return MRL_OK;
+}
+
+extern "C" int mrl_split_launches_per_substep(const mrl_split_plan *p) {
+  if (!p) return MRL_ERR_INVALID;
+  return p->ctx->dim == 3 ? 5 : 3;
+}
+
+extern "C" int mrl_split_clear_states(mrl_split_plan *p) {
+  if (!p) return mrl_fail(MRL_ERR_INVALID, "null plan");
+  p->stored = 0;
+  return MRL_OK;
+}
+
+extern "C" int mrl_split_advance_state(mrl_split_plan *p, int *stored) {
+  if (!p) return mrl_fail(MRL_ERR_INVALID, "null plan");
+  const int H = p->desc.history;
+  if (H > 0) {
+    if (p->stored < H) p->stored++;
+    p->cur = (p->cur + 1) % (H + 1);
+  }
+  if (stored) *stored = p->stored;
+  return MRL_OK;
+}
+
+#define PASS_MARK()                                                    \
+  do {                                                                 \
+    if (ev) CK(cudaEventRecord(ev[nev++], ctx->stream));               \
+  } while (0)
+template <class T>
+static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *beta, int nold, cudaEvent_t *ev = nullptr) {
+  mrl_context *ctx = p->ctx;
+  int nev = 0;
+  const mrl_split_desc &d = p->desc;
+  const int dim = ctx->dim;
+  const int nl = ctx->n[dim - 1], nc = ctx->nr[dim - 1];
+  cx<T> *A = (cx<T> *)p->A, *B = (cx<T> *)p->B;
+  long long rows = 1;
+  for (int a = 0; a < dim - 1; ++a) rows *= ctx->n[a];
+  const void *twl, *tw0;
+  int rc;
+  if ((rc = ctx->twiddles(nl, &twl))) return rc;
+  if ((rc = ctx->twiddles(ctx->n[0], &tw0))) return rc;
+
+  PASS_MARK();
+  // P1: last-axis r2c of (c + i F(c))
+  if (d.nonlin_kind == MRL_NONLIN_DOUBLE_WELL) {
+    NonlinDesc nlz{0, {d.nonlin_params[0], d.nonlin_params[1], d.nonlin_params[2], 0}};
+    CKL(ctx, launch_zfwd_nonlin<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, B, rows, nl, nlz, (const cx<T> *)twl,
+                                   make_fft_plan(nl)));
+  } else {
+    if ((rc = mrl_expr_launch_zfwd(ctx, d.nonlin_expr, c, d.g_out_real_dev, A, B, rows, nl))) return rc;
+  }
+  PASS_MARK();
+  // P2: middle axis forward on both fields (3-D only)
+  if (dim == 3) {
+    if ((rc = strided_axis<T>(ctx, A, A, 2, ctx->rtotal(), 1, 1, 0))) return rc;
+    PASS_MARK();
+  }
+  // P3: first axis forward on both + k-space update + first axis inverse
+  FusedIO<T> io;
+  memset(&io, 0, sizeof io);
+  io.inC = A;
+  io.inG = B;
+  io.outU = A;
+  io.n = ctx->n[0];
+  io.ncols = dim == 3 ? ctx->n[1] * nc : nc;
+  io.nouter = 1;
+  io.pitch = io.ncols;
+  io.outer_stride = 0;
+  io.scale = T(1);
+  SpectralUpdate<T> up;
+  memset(&up, 0, sizeof up);
+  up.kx = (const T *)ctx->kaxis_dev[0];
+  up.ky = (const T *)ctx->kaxis_dev[1];
+  up.kz = (const T *)ctx->kaxis_dev[2];
+  up.kmode = dim == 3 ? MRL_KMODE_3D : MRL_KMODE_2D;
+  up.nzc = nc;
+  up.closed_M = d.M_closed_form;
+  up.Mfac = (T)d.M_factor;
+  up.Mbuf = (const T *)d.M_real_dev;
+  up.has_L = d.has_L;
+  up.closed_L = d.L_closed_form;
+  up.Lfac = (T)d.L_factor;
+  up.Lbuf = (const T *)d.L_real_dev;
+  up.dt = (T)dt;
+  up.b0 = (T)(dt * beta[0]);
+  up.nold = nold;
+  const int H = d.history;
+  for (int i = 0; i < nold; ++i) {
+    up.bold[i] = (T)(dt * beta[i + 1]);
+    up.Nold[i] = (const cx<T> *)p->ring[((p->cur - 1 - i) % (H + 1) + (H + 1)) % (H + 1)];
+  }
+  up.Nout = H > 0 ? (cx<T> *)p->ring[p->cur] : nullptr;
+  CKL(ctx, launch_fused<T>(ctx->lc(), io, up, (const cx<T> *)tw0, make_fft_plan(io.n)));
+  PASS_MARK();
+  // P4: middle axis inverse
+  if (dim == 3) {
+    if ((rc = strided_axis<T>(ctx, A, A, 1, 0, 1, 1, 1))) return rc;
+    PASS_MARK();
+  }
+  // P5: last-axis c2r with the 1/N normalisation
+  double N = 1;
+  for (int a = 0; a < dim; ++a) N *= ctx->n[a];
+  CKL(ctx, launch_zinv_pairs<T>(ctx->lc(), A, c, rows, nl, (T)(1.0 / N), (const cx<T> *)twl, make_fft_plan(nl)));
+  PASS_MARK();
+  return MRL_OK;
+}
+
+extern "C" int mrl_split_substep(mrl_split_plan *p, void *c, double dt, const double *beta, int nold) {
+  if (!p || !c || !beta || nold < 0) return mrl_fail(MRL_ERR_INVALID, "mrl_split_substep: bad arguments");
+  if (nold > p->stored)
+    return mrl_fail(MRL_ERR_INVALID, "mrl_split_substep: %d old states requested, %d stored", nold, p->stored);
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? split_substep_impl<double>(p, (double *)c, dt, beta, nold)
+                                      : split_substep_impl<float>(p, (float *)c, dt, beta, nold);
+}
+
+extern "C" int mrl_split_substep_timed(mrl_split_plan *p, void *c, double dt, const double *beta, int nold, float *pass_ms) {
+  if (!p || !c || !beta || nold < 0 || !pass_ms) return mrl_fail(MRL_ERR_INVALID, "mrl_split_substep_timed: bad arguments");
+  if (nold > p->stored) return mrl_fail(MRL_ERR_INVALID, "mrl_split_substep_timed: %d old states requested, %d stored", nold, p->stored);
+  CK(cudaSetDevice(p->ctx->device));
+  const int np = mrl_split_launches_per_substep(p);
+  cudaEvent_t ev[8];
+  for (int i = 0; i <= np; ++i) CK(cudaEventCreate(&ev[i]));
+  int rc = p->ctx->precision == MRL_F64 ? split_substep_impl<double>(p, (double *)c, dt, beta, nold, ev)
+                                        : split_substep_impl<float>(p, (float *)c, dt, beta, nold, ev);
+  if (!rc) {
+    CK(cudaStreamSynchronize(p->ctx->stream));
+    for (int i = 0; i < np; ++i) CK(cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]));
+  }
+  for (int i = 0; i <= np; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}

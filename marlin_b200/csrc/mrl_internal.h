@@ -1,0 +1,58 @@
+// Internal host-side state behind the opaque handles of include/marlin_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/marlin_b200.h"
+#include "mrl_launch.h"
+
+int mrl_fail(int code, const char *fmt, ...);
+
+struct mrl_context {
+  int device = 0;
+  int precision = MRL_F64;
+  cudaStream_t stream = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // domain
+  int dim = 0;
+  int n[3] = {1, 1, 1};   // real shape
+  int nr[3] = {1, 1, 1};  // reciprocal shape
+  double min[3] = {0, 0, 0}, max[3] = {1, 1, 1};
+  std::vector<double> axis_h[3], kaxis_h[3];
+  void *axis_dev[3] = {nullptr, nullptr, nullptr};
+  void *kaxis_dev[3] = {nullptr, nullptr, nullptr};
+  // caches
+  std::map<int, void *> tw;
+  void *scratch_ptr = nullptr;
+  size_t scratch_bytes = 0;
+  void *reduce_dev = nullptr;
+  void *reduce_host = nullptr;
+
+  mrl::LaunchCtx lc() const { return mrl::LaunchCtx{stream, sm_count}; }
+  long long total() const { return (long long)n[0] * n[1] * n[2]; }
+  long long rtotal() const { return (long long)nr[0] * nr[1] * nr[2]; }
+  int twiddles(int n, const void **out);
+  int scratch(size_t bytes, void **out);
+};
+
+struct mrl_split_plan {
+  mrl_context *ctx = nullptr;
+  mrl_split_desc desc;
+  void *A = nullptr, *B = nullptr;  // partial spectra (one allocation, B = A + rtotal)
+  std::vector<void *> ring;         // history+1 nonlinear-term slots
+  int cur = 0, stored = 0;
+};
+
+namespace mrl {
+FFTPlanDev make_fft_plan(int n);
+template <class T>
+cudaError_t launch_reduce(const LaunchCtx &lc, int op, const T *in, long long count, double *partials, int nblk);
+}  // namespace mrl
+
+// expression-compiled first pass (mrl_expr.cpp); returns MRL status
+int mrl_expr_launch_zfwd(mrl_context *ctx, void *expr, const void *c, void *g_out, void *outC, void *outG, long long rows,
+                         int n);

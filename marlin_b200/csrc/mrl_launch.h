@@ -1,0 +1,72 @@
+// Host-side launch interface between the C-ABI implementation (mrl_api.cpp) and the kernel
+// translation units (k_*.cu).  Internal; the public boundary is include/marlin_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mrl_passes.cuh"
+
+namespace mrl {
+
+struct LaunchCtx {
+  cudaStream_t stream;
+  int sm_count;
+};
+
+// X(N, TP, R0, R1, R2, R3): sizes with a register-resident FFT configuration
+#define MRL_FAST_SIZES(X)  \
+  X(16, 4, 4, 4, 1, 1)     \
+  X(32, 4, 8, 4, 1, 1)     \
+  X(64, 8, 8, 8, 1, 1)     \
+  X(128, 16, 8, 4, 4, 1)   \
+  X(256, 32, 8, 8, 4, 1)   \
+  X(512, 64, 8, 8, 8, 1)   \
+  X(1024, 128, 8, 8, 4, 4)
+
+inline bool has_fast_cfg(int n) {
+  switch (n) {
+#define X(N, TP, R0, R1, R2, R3) case N:
+    MRL_FAST_SIZES(X)
+#undef X
+    return true;
+    default: return false;
+  }
+}
+
+// Largest number of interleaved pencils (TK) the generic kernel can hold in shared memory.
+template <class T> inline int gen_tk(int n, int nbuf) {
+  const size_t budget = 200 * 1024;
+  for (int tk = 8; tk >= 1; tk >>= 1)
+    if ((size_t)nbuf * n * tk * sizeof(cx<T>) <= budget) return tk;
+  return 0;
+}
+
+// Real-space nonlinearity selector for the fused first pass.
+struct NonlinDesc {
+  int kind;          // 0: double-well derivative 2A(c-a)(b-c)(a+b-2c)
+  double p[4];       // A, a, b
+};
+
+template <class T> cudaError_t launch_strided(const LaunchCtx &lc, const StridedIO<T> &io, const cx<T> *tw, const FFTPlanDev &plan);
+template <class T>
+cudaError_t launch_zfwd_pairs(const LaunchCtx &lc, const T *in, cx<T> *out, long long nrows, int n, const cx<T> *tw,
+                              const FFTPlanDev &plan);
+template <class T>
+cudaError_t launch_zinv_pairs(const LaunchCtx &lc, const cx<T> *in, T *out, long long nrows, int n, T scale,
+                              const cx<T> *tw, const FFTPlanDev &plan);
+template <class T>
+cudaError_t launch_zfwd_nonlin(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows,
+                               int n, const NonlinDesc &nl, const cx<T> *tw, const FFTPlanDev &plan);
+template <class T>
+cudaError_t launch_fused(const LaunchCtx &lc, const FusedIO<T> &io, const SpectralUpdate<T> &up, const cx<T> *tw,
+                         const FFTPlanDev &plan);
+template <class T>
+cudaError_t launch_kfactor(const LaunchCtx &lc, T *out, const T *kx, const T *ky, const T *kz, int n0, int n1, int n2,
+                           int kind, T factor);
+template <class T>
+cudaError_t launch_ab_update(const LaunchCtx &lc, cx<T> *ubar, const cx<T> *cbar, const cx<T> *N, const T *L, T dt, T b0,
+                             int nold, const cx<T> *const *old, const T *bold, long long total);
+template <class T> cudaError_t launch_mul_rc(const LaunchCtx &lc, cx<T> *out, const T *a, const cx<T> *b, long long total);
+template <class T>
+cudaError_t launch_nonlin(const LaunchCtx &lc, T *out, const T *in, const NonlinDesc &nl, long long total);
+
+}  // namespace mrl

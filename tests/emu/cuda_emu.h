@@ -1,0 +1,113 @@
+// Minimal host emulation of the CUDA execution model - TEST TOOL ONLY.
+//
+// Lets tests/emu/*.cpp compile the product's kernel headers (marlin_b200/csrc/*.cuh) with
+// g++ and run them block by block on the CPU so index math, barriers and shared-memory
+// hazards can be checked without a GPU.  Each CUDA thread is a ucontext fiber;
+// __syncthreads() yields to the next fiber of the block.  Never linked into the product
+// library (libmarlin_b200.so has no CPU path).
+#pragma once
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct uint3_emu { unsigned x, y, z; };
+
+namespace emu {
+inline uint3_emu g_threadIdx, g_blockIdx;
+inline dim3 g_blockDim, g_gridDim;
+inline unsigned char *g_dyn_smem = nullptr;
+inline std::vector<ucontext_t> g_ctx;
+inline ucontext_t g_main;
+inline std::vector<int> g_state;  // 0 = runnable, 1 = at barrier, 2 = done
+inline int g_cur = 0;
+inline std::function<void()> g_body;
+inline long g_barrier_count = 0;
+
+inline void set_tid(int t) {
+  g_threadIdx.x = t % g_blockDim.x;
+  g_threadIdx.y = (t / g_blockDim.x) % g_blockDim.y;
+  g_threadIdx.z = t / (g_blockDim.x * g_blockDim.y);
+}
+inline void fiber_entry() {
+  g_body();
+  g_state[g_cur] = 2;
+  swapcontext(&g_ctx[g_cur], &g_main);
+}
+inline void syncthreads() {
+  g_state[g_cur] = 1;
+  int me = g_cur;
+  swapcontext(&g_ctx[me], &g_main);
+  set_tid(me);
+}
+// Run one block: round-robin the fibers; a barrier releases when every live fiber reached it.
+inline void run_block(int nthreads, size_t stack_bytes) {
+  g_ctx.assign(nthreads, ucontext_t());
+  g_state.assign(nthreads, 0);
+  std::vector<std::vector<unsigned char>> stacks(nthreads, std::vector<unsigned char>(stack_bytes));
+  for (int t = 0; t < nthreads; ++t) {
+    getcontext(&g_ctx[t]);
+    g_ctx[t].uc_stack.ss_sp = stacks[t].data();
+    g_ctx[t].uc_stack.ss_size = stack_bytes;
+    g_ctx[t].uc_link = &g_main;
+    makecontext(&g_ctx[t], (void (*)())fiber_entry, 0);
+  }
+  while (true) {
+    int done = 0, waiting = 0;
+    for (int t = 0; t < nthreads; ++t) {
+      if (g_state[t] == 2) { ++done; continue; }
+      if (g_state[t] == 1) { ++waiting; continue; }
+      g_cur = t;
+      set_tid(t);
+      swapcontext(&g_main, &g_ctx[t]);
+      if (g_state[t] == 2) ++done; else ++waiting;
+    }
+    if (done == nthreads) break;
+    if (done != 0 && waiting != 0) {
+      // CUDA requires all non-exited threads to reach the barrier: exited threads are fine
+    }
+    ++g_barrier_count;
+    for (int t = 0; t < nthreads; ++t)
+      if (g_state[t] == 1) g_state[t] = 0;
+  }
+}
+template <class F>
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f, size_t stack_bytes = 96 * 1024) {
+  std::vector<unsigned char> smem(smem_bytes + 64);
+  g_dyn_smem = (unsigned char *)(((uintptr_t)smem.data() + 63) & ~uintptr_t(63));
+  g_gridDim = grid;
+  g_blockDim = block;
+  g_body = f;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g_blockIdx = {bx, by, bz};
+        run_block(block.x * block.y * block.z, stack_bytes);
+      }
+}
+}  // namespace emu
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define threadIdx emu::g_threadIdx
+#define blockIdx emu::g_blockIdx
+#define blockDim emu::g_blockDim
+#define gridDim emu::g_gridDim
+#define __syncthreads() emu::syncthreads()
+template <class T> inline T __ldg(const T *p) { return *p; }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+#define __shared__ static

@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle / golden fixtures.
+
+Tolerances (BASELINE.json north_star): relative L2 <= 1e-10 per field in float64,
+<= 1e-5 in float32.  FFT-only checks use tighter bounds.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_cases as oc
+from ch_driver import SplitDriver
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float(torch.linalg.norm((a - b).reshape(-1)) / torch.linalg.norm(b.reshape(-1)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from marlin_b200 import capi
+    c = capi.Context(0, capi.F64)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx32():
+    from marlin_b200 import capi
+    c = capi.Context(0, capi.F32)
+    yield c
+    c.close()
+
+
+SHAPES = [(10,), (11,), (16,), (512,), (200,), (1,), (2,), (3,),
+          (8, 9), (9, 8), (13, 12), (12, 13), (20, 20), (64, 64), (150, 150), (200, 200), (256, 256), (7, 1024),
+          (4, 5, 6), (5, 4, 7), (16, 16, 16), (32, 64, 16), (20, 20, 20), (40, 40, 40), (64, 64, 64),
+          (128, 128, 128), (17, 32, 9), (100, 10, 12)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_rfftn_irfftn_match_torch_cpu(ctx, shape):
+    """DomainAction::fft/ifft (src/actions/DomainAction.C:854-867, :1054-1066); sizes include
+    the even/odd 1-3-D cases of test/tests/tensor_compute/backandforth.i."""
+    torch.manual_seed(3)
+    dim = len(shape)
+    ctx.domain_set(dim, shape, (0,) * 3, (1.0,) * 3)
+    a = torch.rand(shape, dtype=torch.float64)
+    ref = torch.fft.rfftn(a, dim=list(range(dim)))
+    got = ctx.rfftn(a.cuda())
+    assert list(got.shape) == list(ref.shape)
+    assert rel_l2(torch.view_as_real(got.cpu()), torch.view_as_real(ref)) < 1e-14
+    # inverse of an arbitrary (non-Hermitian-clean) spectrum: imaginary parts of the DC and
+    # Nyquist bins must be ignored exactly like pocketfft / MKL do
+    spec = ref + 0.1 * torch.complex(torch.rand(ref.shape, dtype=torch.float64),
+                                     torch.rand(ref.shape, dtype=torch.float64))
+    refi = torch.fft.irfftn(spec, s=list(shape), dim=list(range(dim)))
+    goti = ctx.irfftn(spec.cuda())
+    if dim == 1:
+        # only in 1-D is the result independent of how the non-Hermitian part is treated
+        assert rel_l2(goti.cpu(), refi) < 1e-14
+    back = ctx.irfftn(got)
+    assert rel_l2(back.cpu(), a) < 1e-14
+
+
+def test_irfftn_matches_torch_on_hermitian_input(ctx):
+    torch.manual_seed(5)
+    for shape in [(20, 20), (16, 16, 16), (9, 10, 11), (64, 64, 64)]:
+        dim = len(shape)
+        ctx.domain_set(dim, shape)
+        a = torch.rand(shape, dtype=torch.float64)
+        k = torch.fft.rfftn(a, dim=list(range(dim))) * torch.rand(ctx.rshape, dtype=torch.float64)
+        ref = torch.fft.irfftn(k, s=list(shape), dim=list(range(dim)))
+        assert rel_l2(ctx.irfftn(k.cuda()).cpu(), ref) < 1e-13
+
+
+def test_irfftn_nonhermitian_like_fftgradient(ctx):
+    """FFTGradient (src/tensor_computes/FFTGradient.C:36-40) multiplies the spectrum by i*k_d with
+    the Nyquist bin kept, which is not Hermitian-consistent; irfftn must treat it like libTorch
+    (c2c over the leading axes, then a 1-D c2r that ignores Im of the DC/Nyquist bins)."""
+    from oracle import marlin as om
+    for shape, L in [((40, 40, 40), (2 * math.pi, 4 * math.pi, 6 * math.pi)), ((16, 16), (2.0, 3.0)), ((9, 12, 10), (1.0, 2.0, 3.0))]:
+        dim = len(shape)
+        d = om.Domain(dim, list(shape), (0, 0, 0), tuple(L) + (1.0,) * (3 - dim))
+        ctx.domain_set(dim, shape, (0,) * 3, tuple(L) + (1.0,) * (3 - dim))
+        torch.manual_seed(2)
+        s = torch.rand(shape, dtype=torch.float64)
+        sk = d.fft(s)
+        for a in range(dim):
+            ref = d.ifft(sk * d.kaxis[a] * 1j)
+            got = ctx.irfftn((sk * d.kaxis[a] * 1j).cuda().contiguous())
+            assert rel_l2(got.cpu(), ref) < 1e-13, (shape, a)
+
+
+def test_batched_rfftn(ctx):
+    torch.manual_seed(4)
+    ctx.domain_set(3, (16, 16, 16))
+    a = torch.rand((3, 3, 16, 16, 16), dtype=torch.float64)
+    ref = torch.fft.rfftn(a, dim=[2, 3, 4])
+    got = ctx.rfftn(a.cuda())
+    assert rel_l2(torch.view_as_real(got.cpu()), torch.view_as_real(ref)) < 1e-14
+    assert rel_l2(ctx.irfftn(got).cpu(), a) < 1e-14
+
+
+def test_fft_float32(ctx32):
+    torch.manual_seed(6)
+    for shape in [(64, 64), (20, 20, 20), (64, 64, 64), (128, 128, 128)]:
+        ctx32.domain_set(len(shape), shape)
+        a = torch.rand(shape, dtype=torch.float32)
+        ref = torch.fft.rfftn(a.double(), dim=list(range(len(shape))))
+        got = ctx32.rfftn(a.cuda())
+        assert rel_l2(torch.view_as_real(got.cpu()), torch.view_as_real(ref)) < 1e-6
+        assert rel_l2(ctx32.irfftn(got).cpu(), a) < 1e-6
+
+
+def test_kfactors_and_axes(ctx):
+    """ReciprocalLaplacianFactor.C:30 / ReciprocalLaplacianSquareFactor.C:31 and the k-axis
+    layout (bit-exact axes, half spectrum on the last axis)."""
+    from marlin_b200 import capi
+    from oracle import marlin as om
+    for dim, n, L in [(2, (20, 20), 3.0), (3, (16, 12, 10), 2 * math.pi), (2, (200, 200), 200.0)]:
+        ctx.domain_set(dim, n, (0,) * 3, (L,) * 3)
+        d = om.Domain(dim, list(n), (0, 0, 0), (L, L, L))
+        for a in range(dim):
+            assert torch.equal(ctx.axis(a, True), d.kaxis[a].reshape(-1))
+        assert ctx.rshape == d.rshape
+        m = ctx.kfactor(capi.KFACTOR_LAPLACIAN, 0.2).cpu()
+        k = ctx.kfactor(capi.KFACTOR_LAPLACIAN_SQUARE, -0.001).cpu()
+        refm, refk = (-d.k2 * 0.2).expand(d.rshape), (d.k2 * d.k2 * -0.001).expand(d.rshape)
+        assert (m - refm).abs().max() <= 4e-16 * refm.abs().max()
+        assert (k - refk).abs().max() <= 4e-16 * refk.abs().max()
+
+
+def test_reductions(ctx):
+    from marlin_b200 import capi
+    torch.manual_seed(8)
+    a = torch.rand(1000003, dtype=torch.float64) - 0.3
+    g = a.cuda()
+    assert abs(ctx.reduce(capi.SUM, g) - float(a.sum())) < 1e-9 * float(a.abs().sum())
+    assert ctx.reduce(capi.MIN, g) == float(a.min())
+    assert ctx.reduce(capi.MAX, g) == float(a.max())
+    assert abs(ctx.reduce(capi.SUMSQ, g) - float((a * a).sum())) < 1e-9 * float((a * a).sum())
+
+
+def _run_split(ctx, p, steps, dt, substeps, closed=True, order=2, double_well=(0.1, 0.0, 1.0), M=0.2, kappa=-0.001,
+               collect=None):
+    """Run the fused plan from the oracle problem's initial condition."""
+    from marlin_b200 import capi
+    d = p.domain
+    ctx.domain_set(d.dim, d.n[:d.dim], d.min, d.max)
+    c = p.buf["c"].to(ctx.rdtype).cuda().contiguous()
+    kw = dict(double_well=double_well, history=order - 1)
+    if closed:
+        kw.update(M_factor=M, L_factor=kappa)
+    else:
+        kw.update(M_buffer=ctx.kfactor(capi.KFACTOR_LAPLACIAN, M), L_buffer=ctx.kfactor(capi.KFACTOR_LAPLACIAN_SQUARE, kappa))
+    plan = ctx.split_plan(**kw)
+    drv = SplitDriver(plan, c, substeps, predictor_order=order)
+    for s in range(steps):
+        drv.step(dt)
+        if collect is not None:
+            collect.append(c.cpu().clone())
+    out = c.cpu()
+    plan.close()
+    return out
+
+
+def test_ch2d_fused_matches_reference_gold(ctx):
+    """test/tests/cahnhilliard/cahnhilliard.i: the CUDA path against the reference's own
+    Exodus gold (all 10 output steps) and against the oracle."""
+    g = np.load(f"{G}/ch2d_exodus.npz")
+    p = oc.ch_problem(2, 20, 3.0, substeps=10)
+    p.initial()
+    states = []
+    _run_split(ctx, p, 10, 1e-3, 10, collect=states)
+    for s in range(10):
+        assert np.abs(states[s].numpy() - g["c"][s + 1]).max() < 1e-12, s
+
+
+@pytest.mark.parametrize("closed", [True, False])
+@pytest.mark.parametrize("dim,n,L,order", [(2, 20, 3.0, 2), (2, 64, 8.0, 2), (2, 200, 25.0, 1), (2, 150, 20.0, 3),
+                                           (3, 16, 2.0, 2), (3, 20, 2.5, 2), (3, 32, 4.0, 4), (3, 64, 8.0, 2)])
+def test_ch_fused_matches_oracle_100_substeps(ctx, dim, n, L, order, closed):
+    """BASELINE.md parity gate: 100 substeps over 2 MOOSE steps (AB order 0 in step 1 by quirk
+    Q1, full order afterwards), relative L2 <= 1e-10."""
+    p = oc.ch_problem(dim, n, L, substeps=50, predictor_order=order)
+    p.initial()
+    got = _run_split(ctx, p, 2, 0.05, 50, closed=closed, order=order)
+    for _ in range(2):
+        p.step(0.05)
+    assert rel_l2(got, p.buf["c"]) < 1e-10
+
+
+def test_ch_dt_change_resets_order(ctx):
+    """Quirk Q2 (AdamsBashforthMoulton.C:75,90-91): a changed dt restarts at order 0."""
+    p = oc.ch_problem(2, 32, 4.0, substeps=5)
+    p.initial()
+    from marlin_b200 import capi  # noqa: F401
+    d = p.domain
+    ctx.domain_set(2, d.n[:2], d.min, d.max)
+    c = p.buf["c"].cuda().contiguous()
+    plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
+    drv = SplitDriver(plan, c, 5, 2)
+    for dt in [0.01, 0.018, 0.0324, 0.0324]:
+        drv.step(dt)
+        p.step(dt)
+    assert rel_l2(c.cpu(), p.buf["c"]) < 1e-10
+    plan.close()
+
+
+def test_ch_bm1_parameters(ctx):
+    """benchmarks/01_spinodal_decomposition/1a_solver.i free energy and mobilities."""
+    p = oc.ch_problem(2, 200, 200.0, substeps=20, mu_expr="rho_s*(c-c_alpha)^2*(c_beta-c)^2", M=5.0, kappa=-10.0,
+                      constant_names=["rho_s", "c_alpha", "c_beta"], constant_expressions=["5", "0.3", "0.7"],
+                      cmin=0.45, cmax=0.55)
+    p.initial()
+    got = _run_split(ctx, p, 2, 1.0, 20, double_well=(5.0, 0.3, 0.7), M=5.0, kappa=-10.0)
+    for _ in range(2):
+        p.step(1.0)
+    assert rel_l2(got, p.buf["c"]) < 1e-10
+
+
+def test_ch_float32(ctx32):
+    p = oc.ch_problem(3, 32, 4.0, substeps=50)
+    p.initial()
+    got = _run_split(ctx32, p, 2, 0.05, 50)
+    for _ in range(2):
+        p.step(0.05)
+    assert rel_l2(got, p.buf["c"]) < 1e-5
+
+
+def test_ch3d_128_matches_oracle(ctx):
+    p = oc.ch_problem(3, 128, 128 * 8 * math.pi / 200, substeps=10)
+    p.initial()
+    got = _run_split(ctx, p, 2, 0.01, 10)
+    for _ in range(2):
+        p.step(0.01)
+    assert rel_l2(got, p.buf["c"]) < 1e-10
+
+
+def test_unfused_operators_match_fused(ctx):
+    """Generic path (rfftn + pointwise + ab_update + irfftn, one kernel per reference op)
+    against the fused five-pass plan."""
+    from marlin_b200 import capi
+    from oracle.marlin import AB_BETA
+    p = oc.ch_problem(3, 32, 4.0, substeps=1)
+    p.initial()
+    ctx.domain_set(3, (32, 32, 32), (0,) * 3, (4.0,) * 3)
+    c = p.buf["c"].cuda()
+    Mbar = ctx.kfactor(capi.KFACTOR_LAPLACIAN, 0.2)
+    Lb = ctx.kfactor(capi.KFACTOR_LAPLACIAN_SQUARE, -0.001)
+    mu = 0.2 * c * (c - 1) * (2 * c - 1)
+    N = ctx.mul_real_complex(Mbar, ctx.rfftn(mu))
+    ubar = ctx.ab_update(ctx.rfftn(c), N, Lb, 1e-3, AB_BETA[0])
+    ref = ctx.irfftn(ubar)
+    plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=0)
+    c2 = c.clone()
+    plan.substep(c2, 1e-3, AB_BETA[0], 0)
+    assert rel_l2(c2.cpu(), ref.cpu()) < 1e-13
+    p.step(1e-3)
+    assert rel_l2(c2.cpu(), p.buf["c"]) < 1e-12
+    plan.close()
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_512_properties(ctx):
+    """At BASELINE's 512^3 the oracle is too slow for a test; check size-independent
+    properties instead: FFT round trip, Parseval, mass conservation of the CH step (the k=0
+    mode has Mbar = L = 0), and agreement of fused vs un-fused paths on the same input."""
+    from marlin_b200 import capi
+    from oracle.marlin import AB_BETA
+    n = 512
+    L = n * 8 * math.pi / 200
+    ctx.domain_set(3, (n, n, n), (0,) * 3, (L,) * 3)
+    torch.manual_seed(0)
+    c = (torch.rand((n, n, n), dtype=torch.float64) * 0.12 + 0.44).cuda()
+    spec = ctx.rfftn(c)
+    back = ctx.irfftn(spec)
+    assert float((back - c).abs().max()) < 1e-13
+    # Parseval with Hermitian weights on the half spectrum
+    w = torch.full((n // 2 + 1,), 2.0, dtype=torch.float64, device="cuda")
+    w[0] = 1.0
+    w[-1] = 1.0
+    e_k = float(((spec.real ** 2 + spec.imag ** 2) * w).sum()) / n ** 3
+    e_x = float((c * c).sum())
+    assert abs(e_k - e_x) < 1e-11 * e_x
+    del spec, back, w
+    mass0 = ctx.reduce(capi.SUM, c)
+    plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
+    c_fused = c.clone()
+    plan.substep(c_fused, 1e-3, AB_BETA[0], 0)
+    # un-fused single substep on the same input
+    Mbar = ctx.kfactor(capi.KFACTOR_LAPLACIAN, 0.2)
+    Lb = ctx.kfactor(capi.KFACTOR_LAPLACIAN_SQUARE, -0.001)
+    mu = 0.2 * c * (c - 1) * (2 * c - 1)
+    N = ctx.mul_real_complex(Mbar, ctx.rfftn(mu))
+    del mu
+    ubar = ctx.ab_update(ctx.rfftn(c), N, Lb, 1e-3, AB_BETA[0])
+    ref = ctx.irfftn(ubar)
+    del ubar, N, Mbar, Lb
+    assert float((c_fused - ref).abs().max()) < 1e-13
+    del ref
+    plan.advance_state()
+    for _ in range(4):
+        plan.substep(c_fused, 1e-3, AB_BETA[1], 1)
+        plan.advance_state()
+    mass1 = ctx.reduce(capi.SUM, c_fused)
+    assert abs(mass1 - mass0) < 1e-12 * abs(mass0)
+    assert 0.4 < ctx.reduce(capi.MIN, c_fused) and ctx.reduce(capi.MAX, c_fused) < 0.6
+    plan.close()
