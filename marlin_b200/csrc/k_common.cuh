@@ -10,22 +10,29 @@ namespace mrl {
 // Opt in to the dynamic shared memory a kernel needs and find how many CTAs fit on one SM;
 // grids are sized to sm_count * resident CTAs (persistent grid-stride loops over tiles).
 inline cudaError_t kernel_prep(const void *fn, int block, size_t smem, int *ctas_per_sm) {
+  struct Info {
+    size_t max_smem = 0;
+    std::unordered_map<size_t, int> occ;
+  };
   static std::mutex mu;
-  static std::unordered_map<const void *, std::unordered_map<size_t, int>> cache;
+  static std::unordered_map<const void *, Info> cache;
   std::lock_guard<std::mutex> g(mu);
-  auto &m = cache[fn];
-  auto it = m.find(smem * 4096 + block);
-  if (it != m.end()) {
+  Info &m = cache[fn];
+  if (smem > m.max_smem) {  // the attribute is sticky per function: only ever raise it
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    m.max_smem = smem;
+  }
+  auto it = m.occ.find(smem * 4096 + block);
+  if (it != m.occ.end()) {
     *ctas_per_sm = it->second;
     return cudaSuccess;
   }
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   int nb = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, block, smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, block, smem);
   if (e != cudaSuccess) return e;
   if (nb < 1) return cudaErrorLaunchOutOfResources;
-  m[smem * 4096 + block] = nb;
+  m.occ[smem * 4096 + block] = nb;
   *ctas_per_sm = nb;
   return cudaSuccess;
 }

@@ -29,7 +29,7 @@ template <class T> struct StridedIO {
   T scale;  // multiplies the result on store
   int inverse;
 
-  MRL_DI int ntiles() const { return nfields * nouter * ncb; }
+  MRL_HD int ntiles() const { return nfields * nouter * ncb; }
 };
 
 template <class T, class C, int TK>
