@@ -1,0 +1,300 @@
+// Launchers of the TMA-pipelined passes (mrl_passes_tma.cuh) + tensor-map construction.
+#include <cstdlib>
+#include <cstring>
+
+#include "k_common.cuh"
+#include "mrl_passes_tma.cuh"
+
+namespace mrl {
+
+// ------------------------------------------------------------------ tensor maps
+// cuTensorMapEncodeTiled is fetched from the driver at run time (no link-time libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// Real view [d2][d1][d0] (d0 fastest, in scalars of type T) of a complex array; strides in bytes.
+template <class T>
+static cudaError_t make_map3(CUtensorMap *tm, const void *base, unsigned long long d0, unsigned long long d1,
+                             unsigned long long d2, unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  if (((unsigned long long)base & 15ull) || (s1 & 15ull) || (s2 & 15ull)) return cudaErrorNotSupported;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(tm, dt, 3, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+bool tma_enabled() {
+  static int on = env_int("MRL_TMA", 1);
+  return on != 0;
+}
+
+static constexpr size_t kSmemBudget = 225 * 1024;
+
+// ------------------------------------------------------------------ strided
+template <class T, class C, int TK, int NG, int NS>
+static cudaError_t strided_tma_go(const LaunchCtx &lc, const StridedIO<T> &io0, const cx<T> *tw) {
+  constexpr size_t smem = (size_t)(NS * C::N * TK + C::N) * sizeof(cx<T>) + NS * 8 + 128;
+  static_assert(smem <= kSmemBudget, "strided_tma: shared memory budget");
+  static_assert(NG * TK * C::TP <= 1024, "strided_tma: block size");
+  // (field, outer) slices must be laid out back to back so that they form one tensor dimension
+  const long long slice = (long long)io0.n * io0.pitch;
+  if (io0.nouter > 1 && io0.outer_stride != slice) return cudaErrorNotSupported;
+  for (int f = 1; f < io0.nfields; ++f)
+    if (io0.in[f] != io0.in[0] + (long long)f * io0.nouter * slice || io0.out[f] != io0.out[0] + (long long)f * io0.nouter * slice)
+      return cudaErrorNotSupported;
+  StridedTmaIO<T> io;
+  io.out = io0.out[0];
+  io.n = io0.n;
+  io.ncols = io0.ncols;
+  io.nouter = io0.nouter * io0.nfields;
+  io.pitch = io0.pitch;
+  io.outer_stride = slice;
+  io.ncb = (io.ncols + TK - 1) / TK;
+  io.scale = io0.scale;
+  io.inverse = io0.inverse;
+  CUtensorMap tm;
+  const unsigned long long rowb = (unsigned long long)io.pitch * sizeof(cx<T>);
+  cudaError_t e = make_map3<T>(&tm, io0.in[0], 2ull * io.ncols, io.n, io.nouter, rowb, rowb * io.n, 2 * TK,
+                               C::N < 256 ? C::N : 256);
+  if (e != cudaSuccess) return e;
+  auto k = k_strided_tma<T, C, TK, NG, NS>;
+  int per_sm = 0;
+  e = kernel_prep((const void *)k, NG * TK * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (long long)io.nouter * io.ncb;
+  const int grid = (int)(ntiles < lc.sm_count ? ntiles : lc.sm_count);
+  k<<<grid, NG * TK * C::TP, smem, lc.stream>>>(tm, io, tw);
+  return cudaGetLastError();
+}
+
+template <class T> cudaError_t launch_strided_tma(const LaunchCtx &lc, const StridedIO<T> &io, const cx<T> *tw, int n) {
+  if (!tma_enabled()) return cudaErrorNotSupported;
+  static int variant = env_int("MRL_STRIDED_V", 0);
+  if constexpr (sizeof(T) == 8) {
+    switch (n) {
+      case 128: return strided_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 8>(lc, io, tw);
+      case 256: return strided_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 4, 6>(lc, io, tw);
+      case 512:
+        switch (variant) {
+          case 1: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1, 3>(lc, io, tw);
+          case 2: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 6>(lc, io, tw);
+          case 3: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 4, 6>(lc, io, tw);
+          default: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 2, 3>(lc, io, tw);
+        }
+      case 1024: return strided_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 2, 3>(lc, io, tw);
+      default: return cudaErrorNotSupported;
+    }
+  } else {
+    switch (n) {
+      case 128: return strided_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 16, 4, 8>(lc, io, tw);
+      case 256: return strided_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 16, 2, 6>(lc, io, tw);
+      case 512: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 16, 1, 3>(lc, io, tw);
+      case 1024: return strided_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 8, 1, 3>(lc, io, tw);
+      default: return cudaErrorNotSupported;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fused P3
+template <class T, class C, int TK, int NG>
+static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, const SpectralUpdate<T> &up0, const cx<T> *tw) {
+  constexpr size_t smem = (size_t)(NG * 3 * C::N * TK + C::N) * sizeof(cx<T>) + NG * 3 * 8 + 128;
+  static_assert(smem <= kSmemBudget, "fused_tma: shared memory budget");
+  static_assert(NG * TK * C::TP <= 1024, "fused_tma: block size");
+  if (io0.nouter != 1) return cudaErrorNotSupported;
+  FusedTmaIO<T> io;
+  io.outU = io0.outU;
+  io.n = io0.n;
+  io.ncols = io0.ncols;
+  io.ncb = (io0.ncols + TK - 1) / TK;
+  io.pitch = io0.pitch;
+  io.scale = io0.scale;
+  SpectralUpdate2<T> up;
+  memset(&up, 0, sizeof up);
+  up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz;
+  up.kmode = up0.kmode; up.nzc = up0.nzc; up.x0 = up0.x0;
+  up.closed_M = up0.closed_M; up.closed_L = up0.closed_L; up.has_L = up0.has_L;
+  up.Mfac = up0.Mfac; up.Lfac = up0.Lfac; up.Mbuf = up0.Mbuf; up.Lbuf = up0.Lbuf;
+  up.dt = up0.dt; up.b0 = up0.b0; up.nold = up0.nold;
+  up.bold0 = up0.bold[0]; up.bold1 = up0.bold[1]; up.bold2 = up0.bold[2]; up.bold3 = up0.bold[3];
+  up.Nold1 = up0.Nold[1]; up.Nold2 = up0.Nold[2]; up.Nold3 = up0.Nold[3];
+  up.Nout = up0.Nout;
+  const unsigned long long rowb = (unsigned long long)io.pitch * sizeof(cx<T>);
+  const unsigned boxr = C::N < 256 ? C::N : 256;
+  CUtensorMap tmC, tmG, tmO;
+  cudaError_t e = make_map3<T>(&tmC, io0.inC, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+  if (e != cudaSuccess) return e;
+  e = make_map3<T>(&tmG, io0.inG, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+  if (e != cudaSuccess) return e;
+  e = make_map3<T>(&tmO, up0.nold > 0 ? (const void *)up0.Nold[0] : (const void *)io0.inC, 2ull * io.ncols, io.n, 1, rowb,
+                   rowb * io.n, 2 * TK, boxr);
+  if (e != cudaSuccess) return e;
+  auto k = k_fused_tma<T, C, TK, NG>;
+  int per_sm = 0;
+  e = kernel_prep((const void *)k, NG * TK * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long nwork = (io.ncb + NG - 1) / NG;
+  const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
+  k<<<grid, NG * TK * C::TP, smem, lc.stream>>>(tmC, tmG, tmO, io, up, tw);
+  return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t launch_fused_tma(const LaunchCtx &lc, const FusedIO<T> &io, const SpectralUpdate<T> &up, const cx<T> *tw, int n) {
+  if (!tma_enabled()) return cudaErrorNotSupported;
+  static int variant = env_int("MRL_FUSED_V", 0);
+  if constexpr (sizeof(T) == 8) {
+    switch (n) {
+      case 128: return fused_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4>(lc, io, up, tw);
+      case 256: return fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 2>(lc, io, up, tw);
+      case 512:
+        switch (variant) {
+          case 1: return fused_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2>(lc, io, up, tw);
+          default: return fused_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1>(lc, io, up, tw);
+        }
+      case 1024: return fused_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 1>(lc, io, up, tw);
+      default: return cudaErrorNotSupported;
+    }
+  } else {
+    switch (n) {
+      case 128: return fused_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 16, 2>(lc, io, up, tw);
+      case 256: return fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 16, 2>(lc, io, up, tw);
+      case 512: return fused_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 2>(lc, io, up, tw);
+      case 1024: return fused_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 8, 1>(lc, io, up, tw);
+      default: return cudaErrorNotSupported;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ P1 / P5
+template <class T, class C, int PPB, int NG, int NS, class F>
+static cudaError_t zfwd_tma_go(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, const F &f,
+                               const cx<T> *tw) {
+  constexpr int NP = C::N + (C::N >> 3) + 1;
+  constexpr size_t smem = (size_t)NG * NS * PPB * C::N * sizeof(T) + (size_t)(NG * PPB * NP + C::N) * sizeof(cx<T>) + NG * NS * 8 + 128;
+  static_assert(smem <= kSmemBudget, "zfwd_tma: shared memory budget");
+  static_assert(NG * PPB * C::TP <= 1024 && NG <= 15, "zfwd_tma: block size");
+  if (((unsigned long long)c & 15ull) || (C::N * sizeof(T)) % 16) return cudaErrorNotSupported;
+  auto k = k_zfwd_tma<T, C, PPB, NG, NS, F>;
+  int per_sm = 0;
+  cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long nwork = ((nrows + PPB - 1) / PPB + NG - 1) / NG;
+  const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
+  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(c, mu_out, outC, outG, nrows, f, tw);
+  return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int n,
+                                   const NonlinDesc &nl, const cx<T> *tw) {
+  if (!tma_enabled() || nl.kind != 0) return cudaErrorNotSupported;
+  static int variant = env_int("MRL_ZFWD_V", 0);
+  typedef DoubleWellDeriv<T> F;
+  const F f{(T)nl.p[0], (T)nl.p[1], (T)nl.p[2]};
+  if constexpr (sizeof(T) == 8) {
+    switch (n) {
+      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 512:
+        switch (variant) {
+          case 1: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 3, 2, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+          case 2: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 12, 2, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+          case 3: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+          default: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 5, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+        }
+      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      default: return cudaErrorNotSupported;
+    }
+  } else {
+    switch (n) {
+      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 512: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 6, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 6, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      default: return cudaErrorNotSupported;
+    }
+  }
+}
+
+template <class T, class C, int PPB, int NG, int NS>
+static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, T *out, long long nrows, T scale, const cx<T> *tw) {
+  constexpr int NP = C::N + (C::N >> 3) + 1;
+  constexpr int NC = C::N / 2 + 1;
+  constexpr size_t smem = (size_t)(NG * NS * 2 * PPB * NC + NG * PPB * NP + C::N) * sizeof(cx<T>) + NG * NS * 8 + 128;
+  static_assert(smem <= kSmemBudget, "zinv_tma: shared memory budget");
+  static_assert(NG * PPB * C::TP <= 1024 && NG <= 15, "zinv_tma: block size");
+  if (((unsigned long long)in & 15ull) || (NC * sizeof(cx<T>)) % 16) return cudaErrorNotSupported;
+  auto k = k_zinv_tma<T, C, PPB, NG, NS>;
+  int per_sm = 0;
+  cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long npencils = (nrows + 1) / 2;
+  const long long nwork = ((npencils + PPB - 1) / PPB + NG - 1) / NG;
+  const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
+  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(in, out, nrows, scale, tw);
+  return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, T *out, long long nrows, int n, T scale, const cx<T> *tw) {
+  if (!tma_enabled()) return cudaErrorNotSupported;
+  static int variant = env_int("MRL_ZINV_V", 0);
+  if constexpr (sizeof(T) == 8) {
+    switch (n) {
+      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 2>(lc, in, out, nrows, scale, tw);
+      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 2>(lc, in, out, nrows, scale, tw);
+      case 512:
+        switch (variant) {
+          case 1: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 2>(lc, in, out, nrows, scale, tw);
+          case 2: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 2>(lc, in, out, nrows, scale, tw);
+          case 3: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 3, 3>(lc, in, out, nrows, scale, tw);
+          default: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 2>(lc, in, out, nrows, scale, tw);
+        }
+      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 2>(lc, in, out, nrows, scale, tw);
+      default: return cudaErrorNotSupported;
+    }
+  } else {
+    switch (n) {
+      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 3>(lc, in, out, nrows, scale, tw);
+      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 3>(lc, in, out, nrows, scale, tw);
+      case 512: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 3>(lc, in, out, nrows, scale, tw);
+      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 6, 3>(lc, in, out, nrows, scale, tw);
+      default: return cudaErrorNotSupported;
+    }
+  }
+}
+
+#define INST(T)                                                                                                          \
+  template cudaError_t launch_strided_tma<T>(const LaunchCtx &, const StridedIO<T> &, const cx<T> *, int);               \
+  template cudaError_t launch_fused_tma<T>(const LaunchCtx &, const FusedIO<T> &, const SpectralUpdate<T> &, const cx<T> *, \
+                                           int);                                                                         \
+  template cudaError_t launch_zfwd_nonlin_tma<T>(const LaunchCtx &, const T *, T *, cx<T> *, cx<T> *, long long, int,    \
+                                                 const NonlinDesc &, const cx<T> *);                                     \
+  template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, T *, long long, int, T, const cx<T> *);
+INST(double)
+INST(float)
+
+}  // namespace mrl

@@ -314,8 +314,18 @@ template <class T> static int strided_axis(mrl_context *ctx, const cx<T> *in, cx
   const void *tw;
   int rc = ctx->twiddles(io.n, &tw);
   if (rc) return rc;
-  CKL(ctx, launch_strided<T>(ctx->lc(), io, (const cx<T> *)tw, make_fft_plan(io.n)));
+  ctx->launches++;
+  cudaError_t te = launch_strided_tma<T>(ctx->lc(), io, (const cx<T> *)tw, io.n);
+  if (te == cudaErrorNotSupported) te = launch_strided<T>(ctx->lc(), io, (const cx<T> *)tw, make_fft_plan(io.n));
+  CK(te);
   return MRL_OK;
+}
+
+template <class T>
+static cudaError_t zinv_dispatch(mrl_context *ctx, const cx<T> *in, T *out, long long rows, int n, T scale, const cx<T> *tw) {
+  cudaError_t e = launch_zinv_pairs_tma<T>(ctx->lc(), in, out, rows, n, scale, tw);
+  if (e == cudaErrorNotSupported) e = launch_zinv_pairs<T>(ctx->lc(), in, out, rows, n, scale, tw, make_fft_plan(n));
+  return e;
 }
 
 template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *out, int batch) {
@@ -351,7 +361,7 @@ template <class T> static int irfftn_impl(mrl_context *ctx, const cx<T> *in, T *
   }
   const void *tw;
   if ((rc = ctx->twiddles(nl, &tw))) return rc;
-  CKL(ctx, launch_zinv_pairs<T>(ctx->lc(), src, out, rows, nl, (T)(1.0 / N), (const cx<T> *)tw, make_fft_plan(nl)));
+  CKL(ctx, zinv_dispatch<T>(ctx, src, out, rows, nl, (T)(1.0 / N), (const cx<T> *)tw));
   return MRL_OK;
 }
 
@@ -524,8 +534,11 @@ static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *
   // P1: last-axis r2c of (c + i F(c))
   if (d.nonlin_kind == MRL_NONLIN_DOUBLE_WELL) {
     NonlinDesc nlz{0, {d.nonlin_params[0], d.nonlin_params[1], d.nonlin_params[2], 0}};
-    CKL(ctx, launch_zfwd_nonlin<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, B, rows, nl, nlz, (const cx<T> *)twl,
-                                   make_fft_plan(nl)));
+    ctx->launches++;
+    cudaError_t te = launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, B, rows, nl, nlz, (const cx<T> *)twl);
+    if (te == cudaErrorNotSupported)
+      te = launch_zfwd_nonlin<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, B, rows, nl, nlz, (const cx<T> *)twl, make_fft_plan(nl));
+    CK(te);
   } else {
     if ((rc = mrl_expr_launch_zfwd(ctx, d.nonlin_expr, c, d.g_out_real_dev, A, B, rows, nl))) return rc;
   }
@@ -570,7 +583,10 @@ static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *
     up.Nold[i] = (const cx<T> *)p->ring[((p->cur - 1 - i) % (H + 1) + (H + 1)) % (H + 1)];
   }
   up.Nout = H > 0 ? (cx<T> *)p->ring[p->cur] : nullptr;
-  CKL(ctx, launch_fused<T>(ctx->lc(), io, up, (const cx<T> *)tw0, make_fft_plan(io.n)));
+  ctx->launches++;
+  cudaError_t fe = launch_fused_tma<T>(ctx->lc(), io, up, (const cx<T> *)tw0, io.n);
+  if (fe == cudaErrorNotSupported) fe = launch_fused<T>(ctx->lc(), io, up, (const cx<T> *)tw0, make_fft_plan(io.n));
+  CK(fe);
   PASS_MARK();
   // P4: middle axis inverse
   if (dim == 3) {
@@ -580,7 +596,7 @@ static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *
   // P5: last-axis c2r with the 1/N normalisation
   double N = 1;
   for (int a = 0; a < dim; ++a) N *= ctx->n[a];
-  CKL(ctx, launch_zinv_pairs<T>(ctx->lc(), A, c, rows, nl, (T)(1.0 / N), (const cx<T> *)twl, make_fft_plan(nl)));
+  CKL(ctx, zinv_dispatch<T>(ctx, A, c, rows, nl, (T)(1.0 / N), (const cx<T> *)twl));
   PASS_MARK();
   return MRL_OK;
 }

@@ -149,11 +149,22 @@ template <int N_, int TP_, int R0_, int R1_ = 1, int R2_ = 1, int R3_ = 1> struc
                 "every radix must divide the points per thread");
 };
 
+// Barrier policy of a RegFFT exchange: the whole CTA (default) or one named-barrier group.
+struct CtaSync {
+  MRL_DI void sync() const { __syncthreads(); }
+  MRL_DI void sync_release() const { __syncthreads(); }  // barrier after which the buffer may be re-armed
+};
+struct NoHook {
+  MRL_DI void operator()() const {}
+};
+
 template <class T, class C> struct RegFFT {
   static constexpr int E = C::E, TP = C::TP;
 
-  template <int ST, int R, int S, class SM>
-  static MRL_DI void stage(cx<T> (&v)[C::E], int t, const SM &sm, const cx<T> *tw) {
+  // HOOK runs once, right after the last shared-memory exchange has been read back (from then
+  // on the exchange buffer is no longer touched by this transform).
+  template <int ST, int R, int S, class SM, class BAR, class HOOK>
+  static MRL_DI void stage(cx<T> (&v)[C::E], int t, const SM &sm, const cx<T> *tw, const BAR &bar, const HOOK &hook) {
     constexpr int EB = E / R;
     constexpr bool last = (ST == C::NS - 1);
     MRL_UNROLL
@@ -174,19 +185,27 @@ template <class T, class C> struct RegFFT {
       }
     }
     if constexpr (!last) {
-      __syncthreads();
+      bar.sync();
       MRL_UNROLL
       for (int e = 0; e < E; ++e) v[e] = sm.ld(t + TP * e);
-      __syncthreads();
+      if constexpr (ST == C::NS - 2) {
+        bar.sync_release();
+        hook();
+      } else {
+        bar.sync();
+      }
     }
   }
 
   // tw: table of exp(-2 pi i k / N), k in [0,N)
-  template <class SM> static MRL_DI void run(cx<T> (&v)[C::E], int t, const SM &sm, const cx<T> *tw) {
-    stage<0, C::R0, 1>(v, t, sm, tw);
-    if constexpr (C::NS > 1) stage<1, C::R1, C::R0>(v, t, sm, tw);
-    if constexpr (C::NS > 2) stage<2, C::R2, C::R0 * C::R1>(v, t, sm, tw);
-    if constexpr (C::NS > 3) stage<3, C::R3, C::R0 * C::R1 * C::R2>(v, t, sm, tw);
+  template <class SM, class BAR = CtaSync, class HOOK = NoHook>
+  static MRL_DI void run(cx<T> (&v)[C::E], int t, const SM &sm, const cx<T> *tw, const BAR &bar = BAR(),
+                         const HOOK &hook = HOOK()) {
+    stage<0, C::R0, 1>(v, t, sm, tw, bar, hook);
+    if constexpr (C::NS > 1) stage<1, C::R1, C::R0>(v, t, sm, tw, bar, hook);
+    if constexpr (C::NS > 2) stage<2, C::R2, C::R0 * C::R1>(v, t, sm, tw, bar, hook);
+    if constexpr (C::NS > 3) stage<3, C::R3, C::R0 * C::R1 * C::R2>(v, t, sm, tw, bar, hook);
+    if constexpr (C::NS == 1) hook();
   }
 };
 

@@ -59,6 +59,16 @@ cudaError_t launch_zfwd_nonlin(const LaunchCtx &lc, const T *c, T *mu_out, cx<T>
 template <class T>
 cudaError_t launch_fused(const LaunchCtx &lc, const FusedIO<T> &io, const SpectralUpdate<T> &up, const cx<T> *tw,
                          const FFTPlanDev &plan);
+// TMA-pipelined versions (k_tma.cu); return cudaErrorNotSupported when the size / layout has no
+// pipelined configuration, in which case the caller uses the kernels above.
+template <class T> cudaError_t launch_strided_tma(const LaunchCtx &lc, const StridedIO<T> &io, const cx<T> *tw, int n);
+template <class T>
+cudaError_t launch_fused_tma(const LaunchCtx &lc, const FusedIO<T> &io, const SpectralUpdate<T> &up, const cx<T> *tw, int n);
+template <class T>
+cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int n,
+                                   const NonlinDesc &nl, const cx<T> *tw);
+template <class T>
+cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, T *out, long long nrows, int n, T scale, const cx<T> *tw);
 template <class T>
 cudaError_t launch_kfactor(const LaunchCtx &lc, T *out, const T *kx, const T *ky, const T *kz, int n0, int n1, int n2,
                            int kind, T factor);

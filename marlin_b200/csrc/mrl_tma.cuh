@@ -1,0 +1,114 @@
+// marlin_b200 - asynchronous-copy plumbing for sm_100a: mbarrier, TMA (cp.async.bulk and
+// cp.async.bulk.tensor), named barriers.  Thin inline-PTX wrappers; the host emulation in
+// tests/emu provides synchronous stand-ins so the index logic of the pipelined kernels can
+// be checked on the CPU.
+#pragma once
+#include "mrl_fft.cuh"
+
+#if !defined(MRL_EMU)
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched at run time, no -lcuda)
+#include <stdint.h>
+#endif
+
+namespace mrl {
+
+#if !defined(MRL_EMU)
+
+typedef CUtensorMap TensorMap;
+#define MRL_GRID_CONSTANT __grid_constant__
+
+MRL_DI uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+MRL_DI void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make the initialised barriers visible to the async proxy (TMA unit)
+MRL_DI void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+MRL_DI void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+MRL_DI void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "MRL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra MRL_DONE;\n"
+      "bra MRL_WAIT;\n"
+      "MRL_DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// order generic-proxy shared-memory accesses before subsequent async-proxy (TMA) accesses
+MRL_DI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 3-D tiled TMA load: box of the tensor map at element coordinates (c0 fastest, c1, c2)
+MRL_DI void tma_load_3d(void *smem_dst, const TensorMap *tm, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (bytes: multiple of 16, both addresses 16-byte aligned)
+MRL_DI void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"((uint64_t)gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// barrier among the `nthreads` threads that use id `id` (1..15; 0 is __syncthreads)
+MRL_DI void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+#else  // --------------------------------------------------------------- host emulation
+
+struct TensorMap {  // what the emulation needs of a 3-D tiled map
+  const unsigned char *base;
+  int esize;
+  long long dim[3], stride[3];  // stride in bytes (stride[0] = esize)
+  int box[3];
+};
+#define MRL_GRID_CONSTANT
+
+MRL_DI void mbar_init(uint64_t *bar, int) { *bar = 0; }
+MRL_DI void mbar_init_fence() {}
+// copies are performed synchronously at issue, so arming a phase also completes it: the
+// word counts armed phases, and a waiter spins (cooperatively) until its phase exists
+MRL_DI void mbar_expect_tx(uint64_t *bar, uint32_t) { *bar += 1; }
+MRL_DI void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (*(volatile uint64_t *)bar == 0 || ((*(volatile uint64_t *)bar - 1) & 1) != parity) emu::yield();
+}
+MRL_DI void fence_proxy_async() {}
+MRL_DI void tma_load_3d(void *smem_dst, const TensorMap *tm, uint64_t *bar, int c0, int c1, int c2) {
+  unsigned char *d = (unsigned char *)smem_dst;
+  for (int k = 0; k < tm->box[2]; ++k)
+    for (int j = 0; j < tm->box[1]; ++j)
+      for (int i = 0; i < tm->box[0]; ++i) {
+        const long long a = c0 + i, b = c1 + j, c = c2 + k;
+        const bool in = a < tm->dim[0] && b < tm->dim[1] && c < tm->dim[2];
+        if (in)
+          memcpy(d, tm->base + a * tm->stride[0] + b * tm->stride[1] + c * tm->stride[2], tm->esize);
+        else
+          memset(d, 0, tm->esize);
+        d += tm->esize;
+      }
+  (void)bar;
+}
+MRL_DI void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *) { memcpy(smem_dst, gsrc, bytes); }
+MRL_DI void named_bar_sync(int id, int nthreads) { emu::named_barrier(id, nthreads); }
+
+#endif
+
+// Barrier policy for RegFFT: one group of threads of a CTA (CtaSync is the whole CTA).
+struct GroupBarrier {
+  int id, nthreads;
+  MRL_DI void sync() const { named_bar_sync(id, nthreads); }
+  // every thread orders its generic-proxy accesses before the TMA write one of them issues next
+  MRL_DI void sync_release() const {
+    fence_proxy_async();
+    named_bar_sync(id, nthreads);
+  }
+};
+
+}  // namespace mrl

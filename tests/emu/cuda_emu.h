@@ -43,16 +43,31 @@ inline void fiber_entry() {
   g_state[g_cur] = 2;
   swapcontext(&g_ctx[g_cur], &g_main);
 }
-inline void syncthreads() {
+inline std::vector<int> g_bar_id, g_bar_n;  // barrier a waiting fiber sits at / its thread count
+inline void block_at(int id, int n) {
   g_state[g_cur] = 1;
+  g_bar_id[g_cur] = id;
+  g_bar_n[g_cur] = n;
   int me = g_cur;
   swapcontext(&g_ctx[me], &g_main);
   set_tid(me);
 }
-// Run one block: round-robin the fibers; a barrier releases when every live fiber reached it.
+inline void syncthreads() { block_at(0, -1); }
+// bar.sync id, n: releases when n fibers wait at barrier `id`
+inline void named_barrier(int id, int n) { block_at(id, n); }
+// cooperative spin (e.g. mbarrier try_wait loops): stay runnable, let the others run
+inline void yield() {
+  int me = g_cur;
+  swapcontext(&g_ctx[me], &g_main);
+  set_tid(me);
+}
+// Run one block: round-robin the fibers; barrier 0 releases when every live fiber reached it,
+// a named barrier when its thread count is reached.
 inline void run_block(int nthreads, size_t stack_bytes) {
   g_ctx.assign(nthreads, ucontext_t());
   g_state.assign(nthreads, 0);
+  g_bar_id.assign(nthreads, 0);
+  g_bar_n.assign(nthreads, 0);
   std::vector<std::vector<unsigned char>> stacks(nthreads, std::vector<unsigned char>(stack_bytes));
   for (int t = 0; t < nthreads; ++t) {
     getcontext(&g_ctx[t]);
@@ -61,23 +76,37 @@ inline void run_block(int nthreads, size_t stack_bytes) {
     g_ctx[t].uc_link = &g_main;
     makecontext(&g_ctx[t], (void (*)())fiber_entry, 0);
   }
+  long idle_rounds = 0;
   while (true) {
-    int done = 0, waiting = 0;
+    int done = 0;
     for (int t = 0; t < nthreads; ++t) {
       if (g_state[t] == 2) { ++done; continue; }
-      if (g_state[t] == 1) { ++waiting; continue; }
+      if (g_state[t] == 1) continue;
       g_cur = t;
       set_tid(t);
       swapcontext(&g_main, &g_ctx[t]);
-      if (g_state[t] == 2) ++done; else ++waiting;
+      if (g_state[t] == 2) ++done;
     }
     if (done == nthreads) break;
-    if (done != 0 && waiting != 0) {
-      // CUDA requires all non-exited threads to reach the barrier: exited threads are fine
-    }
-    ++g_barrier_count;
+    // release barriers
+    int count[17] = {0}, need[17] = {0}, live = nthreads - done, released = 0;
     for (int t = 0; t < nthreads; ++t)
-      if (g_state[t] == 1) g_state[t] = 0;
+      if (g_state[t] == 1) {
+        count[g_bar_id[t]]++;
+        need[g_bar_id[t]] = g_bar_n[t] < 0 ? live : g_bar_n[t];
+      }
+    for (int id = 0; id < 17; ++id)
+      if (count[id] && count[id] >= need[id]) {
+        ++g_barrier_count;
+        ++released;
+        for (int t = 0; t < nthreads; ++t)
+          if (g_state[t] == 1 && g_bar_id[t] == id) g_state[t] = 0;
+      }
+    idle_rounds = released ? 0 : idle_rounds + 1;
+    if (idle_rounds > 100000) {
+      fprintf(stderr, "emu: deadlock (no barrier released for 100000 scheduler rounds)\n");
+      abort();
+    }
   }
 }
 template <class F>

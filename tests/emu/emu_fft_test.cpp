@@ -1,7 +1,7 @@
 // Host-emulated run of the product's FFT kernels against a naive long-double DFT.
 // TEST TOOL: compiled with g++ -DMRL_EMU; validates index math / barriers without a GPU.
 #define MRL_EMU 1
-#include "../../marlin_b200/csrc/mrl_passes.cuh"
+#include "../../marlin_b200/csrc/mrl_passes_tma.cuh"
 
 #include <complex>
 #include <random>
@@ -166,7 +166,7 @@ static void real_gen_i(int n, ZInvLoadPairs<double> ld, ZInvStorePairs<double> s
 }
 
 // ---- fused pass vs composition of strided fwd + update + strided inv (computed with dft())
-template <class RUN> static void test_fused(const char *name, int n, int ny, int nzc, int kmode, RUN run) {
+template <class RUN> static void test_fused(const char *name, int n, int ny, int nzc, int kmode, RUN run, int nold = 1) {
   std::mt19937_64 rng(5);
   std::uniform_real_distribution<double> U(-1, 1);
   int ncols = (kmode == MRL_KMODE_2D) ? ny : ny * nzc;
@@ -186,7 +186,7 @@ template <class RUN> static void test_fused(const char *name, int n, int ny, int
   up.kmode = kmode; up.nzc = nzc; up.x0 = 0;
   up.closed_M = 1; up.closed_L = 1; up.has_L = 1;
   up.Mfac = 0.2; up.Lfac = -0.001; up.dt = 0.01;
-  up.b0 = 1.5 * up.dt; up.nold = 1; up.bold[0] = -0.5 * up.dt; up.Nold[0] = Nold0.data();
+  up.b0 = 1.5 * up.dt; up.nold = nold; up.bold[0] = -0.5 * up.dt; up.Nold[0] = Nold0.data();
   up.Nout = Nout.data();
   run(io, up, tw.data());
   double err = 0, errN = 0;
@@ -203,7 +203,7 @@ template <class RUN> static void test_fused(const char *name, int n, int ny, int
       long double kk = a * a + b * b + d * d;
       lc N = (-kk * 0.2L) * yg[j];
       auto no = Nold0[(size_t)j * ncols + c];
-      u[j] = (yc[j] + (long double)up.b0 * N + (long double)up.bold[0] * lc(no.x, no.y)) /
+      u[j] = (yc[j] + (long double)up.b0 * N + (nold ? (long double)up.bold[0] : 0.0L) * lc(no.x, no.y)) /
              (1.0L - (long double)up.dt * (kk * kk * -0.001L));
       auto nn = Nout[(size_t)j * ncols + c];
       errN = std::max(errN, (double)std::abs(lc(nn.x, nn.y) - N));
@@ -221,7 +221,132 @@ template <class RUN> static void test_fused(const char *name, int n, int ny, int
   report(nm, errN, 1e-12 * n);
 }
 
+
+// ======================================================================== TMA-pipelined kernels
+static TensorMap emu_map(const void *base, int esize, long long d0, long long d1, long long d2, long long s1, long long s2,
+                         int b0, int b1) {
+  TensorMap m;
+  m.base = (const unsigned char *)base;
+  m.esize = esize;
+  m.dim[0] = d0; m.dim[1] = d1; m.dim[2] = d2;
+  m.stride[0] = esize; m.stride[1] = s1; m.stride[2] = s2;
+  m.box[0] = b0; m.box[1] = b1; m.box[2] = 1;
+  return m;
+}
+
+template <class C, int TK, int NG, int NS> static void run_strided_tma(StridedIO<double> io0, const cx<double> *tw, int grid) {
+  StridedTmaIO<double> io;
+  io.out = io0.out[0];
+  io.n = io0.n; io.ncols = io0.ncols; io.nouter = io0.nouter;
+  io.pitch = io0.pitch; io.outer_stride = io0.outer_stride;
+  io.ncb = (io0.ncols + TK - 1) / TK;
+  io.scale = io0.scale; io.inverse = io0.inverse;
+  const long long rowb = io.pitch * 16;
+  TensorMap tm = emu_map(io0.in[0], 8, 2LL * io.ncols, io.n, io.nouter, rowb, rowb * io.n, 2 * TK, C::N < 256 ? C::N : 256);
+  size_t smem = (size_t)(NS * C::N * TK + C::N) * 16 + NS * 8 + 128;
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_strided_tma<double, C, TK, NG, NS>(tm, io, tw); }, 64 * 1024);
+}
+
+template <class C, int TK, int NG> static void run_fused_tma(FusedIO<double> io0, SpectralUpdate<double> up0, const cx<double> *tw, int grid) {
+  FusedTmaIO<double> io;
+  io.outU = io0.outU; io.n = io0.n; io.ncols = io0.ncols; io.ncb = (io0.ncols + TK - 1) / TK; io.pitch = io0.pitch; io.scale = io0.scale;
+  SpectralUpdate2<double> up{};
+  up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz; up.kmode = up0.kmode; up.nzc = up0.nzc; up.x0 = up0.x0;
+  up.closed_M = up0.closed_M; up.closed_L = up0.closed_L; up.has_L = up0.has_L; up.Mfac = up0.Mfac; up.Lfac = up0.Lfac;
+  up.dt = up0.dt; up.b0 = up0.b0; up.nold = up0.nold; up.bold0 = up0.bold[0]; up.Nout = up0.Nout;
+  const long long rowb = io.pitch * 16;
+  const int boxr = C::N < 256 ? C::N : 256;
+  TensorMap tmC = emu_map(io0.inC, 8, 2LL * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+  TensorMap tmG = emu_map(io0.inG, 8, 2LL * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+  TensorMap tmO = emu_map(up0.nold ? (const void *)up0.Nold[0] : (const void *)io0.inC, 8, 2LL * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+  size_t smem = (size_t)(NG * 3 * C::N * TK + C::N) * 16 + NG * 3 * 8 + 128;
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG>(tmC, tmG, tmO, io, up, tw); }, 64 * 1024);
+}
+
+// P1 (c + i F(c)) and P5 against the naive DFT
+template <class C, int PPB, int NG, int NS> static void test_zfwd_tma(const char *name, int nrows, int grid) {
+  constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1;
+  std::mt19937_64 rng(13);
+  std::uniform_real_distribution<double> U(0, 1);
+  std::vector<double> c((size_t)nrows * n), mu((size_t)nrows * n, -7.0);
+  for (auto &v : c) v = U(rng);
+  std::vector<cx<double>> oc((size_t)nrows * nc), og((size_t)nrows * nc);
+  auto tw = make_tw(n);
+  DoubleWellDeriv<double> f{0.1, 0.0, 1.0};
+  size_t smem = (size_t)NG * NS * PPB * n * 8 + (size_t)(NG * PPB * NP + n) * 16 + NG * NS * 8 + 128;
+  const double *cp = c.data();
+  double *mp = mu.data();
+  cx<double> *ocp = oc.data(), *ogp = og.data();
+  const cx<double> *twp = tw.data();
+  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem,
+              [=] { k_zfwd_tma<double, C, PPB, NG, NS, DoubleWellDeriv<double>>(cp, mp, ocp, ogp, nrows, f, twp); }, 64 * 1024);
+  double err = 0;
+  for (int r = 0; r < nrows; ++r) {
+    std::vector<lc> x(n), g(n);
+    for (int j = 0; j < n; ++j) {
+      double v = c[(size_t)r * n + j];
+      x[j] = v;
+      g[j] = f(v);
+      err = std::max(err, std::fabs(mu[(size_t)r * n + j] - f(v)));
+    }
+    auto yx = dft(x, -1), yg = dft(g, -1);
+    for (int k = 0; k < nc; ++k) {
+      auto a = oc[(size_t)r * nc + k], b = og[(size_t)r * nc + k];
+      err = std::max(err, (double)std::abs(lc(a.x, a.y) - yx[k]));
+      err = std::max(err, (double)std::abs(lc(b.x, b.y) - yg[k]));
+    }
+  }
+  report(name, err, 1e-12 * n);
+}
+
+template <class C, int PPB, int NG, int NS> static void test_zinv_tma(const char *name, int nrows, int grid) {
+  constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1;
+  std::mt19937_64 rng(17);
+  std::uniform_real_distribution<double> U(-1, 1);
+  std::vector<double> a((size_t)nrows * n), back((size_t)nrows * n);
+  for (auto &v : a) v = U(rng);
+  std::vector<cx<double>> spec((size_t)nrows * nc);
+  for (int r = 0; r < nrows; ++r) {
+    std::vector<lc> x(n);
+    for (int j = 0; j < n; ++j) x[j] = a[(size_t)r * n + j];
+    auto y = dft(x, -1);
+    for (int k = 0; k < nc; ++k) spec[(size_t)r * nc + k] = mk<double>((double)y[k].real(), (double)y[k].imag());
+    spec[(size_t)r * nc].y = 0.37;  // must be ignored
+    spec[(size_t)r * nc + n / 2].y = -0.21;
+  }
+  auto tw = make_tw(n);
+  size_t smem = (size_t)(NG * NS * 2 * PPB * nc + NG * PPB * NP + n) * 16 + NG * NS * 8 + 128;
+  const cx<double> *sp = spec.data(), *twp = tw.data();
+  double *bp = back.data();
+  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem, [=] { k_zinv_tma<double, C, PPB, NG, NS>(sp, bp, nrows, 1.0 / n, twp); },
+              64 * 1024);
+  double err = 0;
+  for (size_t i = 0; i < a.size(); ++i) err = std::max(err, std::fabs(a[i] - back[i]));
+  report(name, err, 1e-12 * n);
+}
+
+static void tma_tests() {
+  test_strided("strided tma 64 TK8 NG2 NS3", 64, 19, 3, 0, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>(io, tw, 2); });
+  test_strided("strided tma 64 TK8 NG2 NS3 inv g5", 64, 19, 3, 1, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>(io, tw, 5); });
+  test_strided("strided tma 64 TK4 NG4 NS6", 64, 9, 2, 0, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 4, 4, 6>(io, tw, 1); });
+  test_strided("strided tma 128 TK8 NG1 NS3", 128, 8, 2, 0, [](auto io, auto tw) { run_strided_tma<FFTCfg<128, 16, 8, 4, 4>, 8, 1, 3>(io, tw, 3); });
+  test_strided("strided tma 512 TK4 NG2 NS3 (2 boxes)", 512, 5, 1, 1, [](auto io, auto tw) { run_strided_tma<FFTCfg<512, 64, 8, 8, 8>, 4, 2, 3>(io, tw, 1); });
+  test_fused("fused tma 64 3D NG2", 64, 3, 5, MRL_KMODE_3D, [](auto io, auto up, auto tw) { run_fused_tma<FFTCfg<64, 8, 8, 8>, 8, 2>(io, up, tw, 1); });
+  test_fused("fused tma 64 2D NG1 g2", 64, 21, 1, MRL_KMODE_2D, [](auto io, auto up, auto tw) { run_fused_tma<FFTCfg<64, 8, 8, 8>, 8, 1>(io, up, tw, 2); });
+  test_fused("fused tma 64 3D TK4 NG2 nold=0", 64, 3, 5, MRL_KMODE_3D, [](auto io, auto up, auto tw) {
+    up.nold = 0;
+    run_fused_tma<FFTCfg<64, 8, 8, 8>, 4, 2>(io, up, tw, 1);
+  }, 0);
+  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 2, 3, 2>("zfwd tma 64 PPB2 NG3 NS2 rows=11", 11, 2);
+  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 1, 4, 3>("zfwd tma 64 PPB1 NG4 NS3 rows=30", 30, 1);
+  test_zfwd_tma<FFTCfg<128, 16, 8, 4, 4>, 4, 2, 2>("zfwd tma 128 PPB4 NG2 NS2 rows=9", 9, 2);
+  test_zinv_tma<FFTCfg<64, 8, 8, 8>, 2, 2, 2>("zinv tma 64 PPB2 NG2 NS2 rows=7", 7, 1);
+  test_zinv_tma<FFTCfg<64, 8, 8, 8>, 1, 4, 3>("zinv tma 64 PPB1 NG4 NS3 rows=40", 40, 2);
+  test_zinv_tma<FFTCfg<512, 64, 8, 8, 8>, 2, 2, 2>("zinv tma 512 PPB2 NG2 NS2 rows=9", 9, 1);
+}
+
 int main() {
+  tma_tests();
   // butterflies via single-stage configs and multi-stage register FFTs
   test_strided("strided fast 8 (R8)", 8, 11, 2, 0, [](auto io, auto tw) { run_strided_fast<FFTCfg<8, 1, 8>, 8>(io, tw); });
   test_strided("strided fast 64 (8,8)", 64, 9, 2, 0, [](auto io, auto tw) { run_strided_fast<FFTCfg<64, 8, 8, 8>, 8>(io, tw); });
