@@ -24,6 +24,16 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static CUtensorMapL2promotion l2_promotion() {
+  static int v = env_int("MRL_L2PROMO", 128);
+  return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+}
+
 // Real view [d2][d1][d0] (d0 fastest, in scalars of type T) of a complex array; strides in bytes.
 template <class T>
 static cudaError_t make_map3(CUtensorMap *tm, const void *base, unsigned long long d0, unsigned long long d1,
@@ -37,16 +47,35 @@ static cudaError_t make_map3(CUtensorMap *tm, const void *base, unsigned long lo
   cuuint32_t es[3] = {1, 1, 1};
   const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(tm, dt, 3, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-static int env_int(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return v ? atoi(v) : dflt;
+// Slab staging [d3 = ranks][d2 = x][d1 = y_local][d0]: one box = all ranks x all local rows of one x
+template <class T>
+static cudaError_t make_map4(CUtensorMap *tm, const void *base, unsigned long long d0, unsigned long long d1,
+                             unsigned long long d2, unsigned long long d3, unsigned b0) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  const unsigned long long s1 = d0 * sizeof(T), s2 = s1 * d1, s3 = s2 * d2;
+  if (((unsigned long long)base & 15ull) || (s1 & 15ull) || d1 > 256 || d3 > 256) return cudaErrorNotSupported;
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1, s2, s3};
+  cuuint32_t box[4] = {b0, (cuuint32_t)d1, 1, (cuuint32_t)d3};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(tm, dt, 4, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
+
+
 bool tma_enabled() {
-  static int on = env_int("MRL_TMA", 1);
+  static int on = [] {
+    const int dbg = env_int("MRL_DEBUG_NOFFT", 0);
+    if (dbg) cudaMemcpyToSymbol(g_debug_nofft, &dbg, sizeof(int));
+    return env_int("MRL_TMA", 1);
+  }();
   return on != 0;
 }
 
@@ -55,27 +84,31 @@ static constexpr size_t kSmemBudget = 225 * 1024;
 // ------------------------------------------------------------------ strided
 template <class T, class C, int TK, int NG, int NS>
 static cudaError_t strided_tma_go(const LaunchCtx &lc, const StridedIO<T> &io0, const cx<T> *tw) {
-  constexpr size_t smem = (size_t)(NS * C::N * TK + C::N) * sizeof(cx<T>) + NS * 8 + 128;
+  constexpr size_t smem = (size_t)(NS * C::N * TK) * sizeof(cx<T>) + NS * 8 + 128;
   static_assert(smem <= kSmemBudget, "strided_tma: shared memory budget");
   static_assert(NG * TK * C::TP <= 1024, "strided_tma: block size");
-  // (field, outer) slices must be laid out back to back so that they form one tensor dimension
+  // input (field, outer) slices must be laid out back to back so that they form one tensor
+  // dimension; the output may have its own pitch / slice stride / per-field base
   const long long slice = (long long)io0.n * io0.pitch;
   if (io0.nouter > 1 && io0.outer_stride != slice) return cudaErrorNotSupported;
+  if (io0.nfields > 2) return cudaErrorNotSupported;
   for (int f = 1; f < io0.nfields; ++f)
-    if (io0.in[f] != io0.in[0] + (long long)f * io0.nouter * slice || io0.out[f] != io0.out[0] + (long long)f * io0.nouter * slice)
-      return cudaErrorNotSupported;
+    if (io0.in[f] != io0.in[0] + (long long)f * io0.nouter * slice) return cudaErrorNotSupported;
   StridedTmaIO<T> io;
   io.out = io0.out[0];
+  io.out1 = io0.nfields > 1 ? io0.out[1] : io0.out[0];
+  io.nouter_f = io0.nouter;
   io.n = io0.n;
   io.ncols = io0.ncols;
   io.nouter = io0.nouter * io0.nfields;
-  io.pitch = io0.pitch;
-  io.outer_stride = slice;
+  io.nvalid = io0.nvalid ? io0.nvalid : io0.ncols;
+  io.pitch = io0.out_pitch ? io0.out_pitch : io0.pitch;
+  io.outer_stride = io0.out_pitch ? io0.out_outer_stride : slice;
   io.ncb = (io.ncols + TK - 1) / TK;
   io.scale = io0.scale;
   io.inverse = io0.inverse;
   CUtensorMap tm;
-  const unsigned long long rowb = (unsigned long long)io.pitch * sizeof(cx<T>);
+  const unsigned long long rowb = (unsigned long long)io0.pitch * sizeof(cx<T>);
   cudaError_t e = make_map3<T>(&tm, io0.in[0], 2ull * io.ncols, io.n, io.nouter, rowb, rowb * io.n, 2 * TK,
                                C::N < 256 ? C::N : 256);
   if (e != cudaSuccess) return e;
@@ -95,15 +128,15 @@ template <class T> cudaError_t launch_strided_tma(const LaunchCtx &lc, const Str
   if constexpr (sizeof(T) == 8) {
     switch (n) {
       case 128: return strided_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 8>(lc, io, tw);
-      case 256: return strided_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 4, 6>(lc, io, tw);
+      case 256:
+        if (variant == 1) return strided_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 16, 1, 3>(lc, io, tw);
+        return strided_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 2, 6>(lc, io, tw);
       case 512:
         switch (variant) {
-          case 1: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1, 3>(lc, io, tw);
-          case 2: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 6>(lc, io, tw);
-          case 3: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 4, 6>(lc, io, tw);
-          default: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 2, 3>(lc, io, tw);
+          case 1: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 2, 3>(lc, io, tw);
+          default: return strided_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1, 3>(lc, io, tw);
         }
-      case 1024: return strided_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 2, 3>(lc, io, tw);
+      case 1024: return strided_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 1, 3>(lc, io, tw);
       default: return cudaErrorNotSupported;
     }
   } else {
@@ -120,10 +153,11 @@ template <class T> cudaError_t launch_strided_tma(const LaunchCtx &lc, const Str
 // ------------------------------------------------------------------ fused P3
 template <class T, class C, int TK, int NG>
 static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, const SpectralUpdate<T> &up0, const cx<T> *tw) {
-  constexpr size_t smem = (size_t)(NG * 3 * C::N * TK + C::N) * sizeof(cx<T>) + NG * 3 * 8 + 128;
+  constexpr size_t smem = (size_t)(NG * 3 * C::N * TK) * sizeof(cx<T>) + NG * 3 * 8 + 128;
   static_assert(smem <= kSmemBudget, "fused_tma: shared memory budget");
   static_assert(NG * TK * C::TP <= 1024, "fused_tma: block size");
-  if (io0.nouter != 1) return cudaErrorNotSupported;
+  if (!io0.slab && io0.nouter != 1) return cudaErrorNotSupported;
+  if (io0.slab && (io0.nyl * io0.nranks != io0.n || io0.pitch != io0.ncols)) return cudaErrorNotSupported;
   FusedTmaIO<T> io;
   io.outU = io0.outU;
   io.n = io0.n;
@@ -131,10 +165,14 @@ static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, cons
   io.ncb = (io0.ncols + TK - 1) / TK;
   io.pitch = io0.pitch;
   io.scale = io0.scale;
+  io.slab = io0.slab;
+  io.nouter = io0.slab ? io0.nouter : 1;
+  io.nyl = io0.nyl;
   SpectralUpdate2<T> up;
   memset(&up, 0, sizeof up);
   up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz;
   up.kmode = up0.kmode; up.nzc = up0.nzc; up.x0 = up0.x0;
+  up.nzv = up0.nzv ? up0.nzv : up0.nzc;
   up.closed_M = up0.closed_M; up.closed_L = up0.closed_L; up.has_L = up0.has_L;
   up.Mfac = up0.Mfac; up.Lfac = up0.Lfac; up.Mbuf = up0.Mbuf; up.Lbuf = up0.Lbuf;
   up.dt = up0.dt; up.b0 = up0.b0; up.nold = up0.nold;
@@ -144,18 +182,23 @@ static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, cons
   const unsigned long long rowb = (unsigned long long)io.pitch * sizeof(cx<T>);
   const unsigned boxr = C::N < 256 ? C::N : 256;
   CUtensorMap tmC, tmG, tmO;
-  cudaError_t e = make_map3<T>(&tmC, io0.inC, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
-  if (e != cudaSuccess) return e;
-  e = make_map3<T>(&tmG, io0.inG, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
-  if (e != cudaSuccess) return e;
-  e = make_map3<T>(&tmO, up0.nold > 0 ? (const void *)up0.Nold[0] : (const void *)io0.inC, 2ull * io.ncols, io.n, 1, rowb,
-                   rowb * io.n, 2 * TK, boxr);
+  const void *oldp = up0.nold > 0 ? (const void *)up0.Nold[0] : (const void *)io0.inC;
+  cudaError_t e;
+  if (io.slab) {
+    e = make_map4<T>(&tmC, io0.inC, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
+    if (e == cudaSuccess) e = make_map4<T>(&tmG, io0.inG, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
+    if (e == cudaSuccess) e = make_map4<T>(&tmO, oldp, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
+  } else {
+    e = make_map3<T>(&tmC, io0.inC, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+    if (e == cudaSuccess) e = make_map3<T>(&tmG, io0.inG, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+    if (e == cudaSuccess) e = make_map3<T>(&tmO, oldp, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
+  }
   if (e != cudaSuccess) return e;
   auto k = k_fused_tma<T, C, TK, NG>;
   int per_sm = 0;
   e = kernel_prep((const void *)k, NG * TK * C::TP, smem, &per_sm);
   if (e != cudaSuccess) return e;
-  const long long nwork = (io.ncb + NG - 1) / NG;
+  const long long nwork = ((long long)io.nouter * io.ncb + NG - 1) / NG;
   const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
   k<<<grid, NG * TK * C::TP, smem, lc.stream>>>(tmC, tmG, tmO, io, up, tw);
   return cudaGetLastError();
@@ -190,10 +233,10 @@ cudaError_t launch_fused_tma(const LaunchCtx &lc, const FusedIO<T> &io, const Sp
 
 // ------------------------------------------------------------------ P1 / P5
 template <class T, class C, int PPB, int NG, int NS, class F>
-static cudaError_t zfwd_tma_go(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, const F &f,
-                               const cx<T> *tw) {
+static cudaError_t zfwd_tma_go(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int ncp,
+                               const F &f, const cx<T> *tw) {
   constexpr int NP = C::N + (C::N >> 3) + 1;
-  constexpr size_t smem = (size_t)NG * NS * PPB * C::N * sizeof(T) + (size_t)(NG * PPB * NP + C::N) * sizeof(cx<T>) + NG * NS * 8 + 128;
+  constexpr size_t smem = (size_t)NG * NS * PPB * C::N * sizeof(T) + (size_t)(NG * PPB * NP) * sizeof(cx<T>) + NG * NS * 8 + 128;
   static_assert(smem <= kSmemBudget, "zfwd_tma: shared memory budget");
   static_assert(NG * PPB * C::TP <= 1024 && NG <= 15, "zfwd_tma: block size");
   if (((unsigned long long)c & 15ull) || (C::N * sizeof(T)) % 16) return cudaErrorNotSupported;
@@ -203,50 +246,51 @@ static cudaError_t zfwd_tma_go(const LaunchCtx &lc, const T *c, T *mu_out, cx<T>
   if (e != cudaSuccess) return e;
   const long long nwork = ((nrows + PPB - 1) / PPB + NG - 1) / NG;
   const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
-  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(c, mu_out, outC, outG, nrows, f, tw);
+  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(c, mu_out, outC, outG, nrows, ncp, f, tw);
   return cudaGetLastError();
 }
 
 template <class T>
 cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int n,
-                                   const NonlinDesc &nl, const cx<T> *tw) {
+                                   int ncp, const NonlinDesc &nl, const cx<T> *tw) {
   if (!tma_enabled() || nl.kind != 0) return cudaErrorNotSupported;
   static int variant = env_int("MRL_ZFWD_V", 0);
   typedef DoubleWellDeriv<T> F;
   const F f{(T)nl.p[0], (T)nl.p[1], (T)nl.p[2]};
   if constexpr (sizeof(T) == 8) {
     switch (n) {
-      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
-      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
       case 512:
         switch (variant) {
-          case 1: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 3, 2, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
-          case 2: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 12, 2, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
-          case 3: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
-          default: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 5, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+          case 1: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+          case 2: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+          case 3: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+          default: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 5, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
         }
-      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
       default: return cudaErrorNotSupported;
     }
   } else {
     switch (n) {
-      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
-      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
-      case 512: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 6, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
-      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 6, 3, F>(lc, c, mu_out, outC, outG, nrows, f, tw);
+      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+      case 512: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
       default: return cudaErrorNotSupported;
     }
   }
 }
 
 template <class T, class C, int PPB, int NG, int NS>
-static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, T *out, long long nrows, T scale, const cx<T> *tw) {
+static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw) {
   constexpr int NP = C::N + (C::N >> 3) + 1;
-  constexpr int NC = C::N / 2 + 1;
-  constexpr size_t smem = (size_t)(NG * NS * 2 * PPB * NC + NG * PPB * NP + C::N) * sizeof(cx<T>) + NG * NS * 8 + 128;
+  constexpr int NC = (C::N / 2 + 1 + 15) & ~15;  // slot rows sized for the largest padded pitch
+  if (ncp > NC || ncp < C::N / 2 + 1) return cudaErrorNotSupported;
+  constexpr size_t smem = (size_t)(NG * NS * 2 * PPB * NC + NG * PPB * NP) * sizeof(cx<T>) + NG * NS * 8 + 128;
   static_assert(smem <= kSmemBudget, "zinv_tma: shared memory budget");
   static_assert(NG * PPB * C::TP <= 1024 && NG <= 15, "zinv_tma: block size");
-  if (((unsigned long long)in & 15ull) || (NC * sizeof(cx<T>)) % 16) return cudaErrorNotSupported;
+  if (((unsigned long long)in & 15ull) || (ncp * sizeof(cx<T>)) % 16) return cudaErrorNotSupported;
   auto k = k_zinv_tma<T, C, PPB, NG, NS>;
   int per_sm = 0;
   cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
@@ -254,34 +298,35 @@ static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, T *out, lon
   const long long npencils = (nrows + 1) / 2;
   const long long nwork = ((npencils + PPB - 1) / PPB + NG - 1) / NG;
   const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
-  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(in, out, nrows, scale, tw);
+  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(in, ncp, out, nrows, scale, tw);
   return cudaGetLastError();
 }
 
 template <class T>
-cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, T *out, long long nrows, int n, T scale, const cx<T> *tw) {
+cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, int n, T scale,
+                                  const cx<T> *tw) {
   if (!tma_enabled()) return cudaErrorNotSupported;
   static int variant = env_int("MRL_ZINV_V", 0);
   if constexpr (sizeof(T) == 8) {
     switch (n) {
-      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 2>(lc, in, out, nrows, scale, tw);
-      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 2>(lc, in, out, nrows, scale, tw);
+      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 3, 2>(lc, in, ncp, out, nrows, scale, tw);
+      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 2>(lc, in, ncp, out, nrows, scale, tw);
       case 512:
         switch (variant) {
-          case 1: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 2>(lc, in, out, nrows, scale, tw);
-          case 2: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 2>(lc, in, out, nrows, scale, tw);
-          case 3: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 3, 3>(lc, in, out, nrows, scale, tw);
-          default: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 2>(lc, in, out, nrows, scale, tw);
+          case 1: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 2>(lc, in, ncp, out, nrows, scale, tw);
+          case 2: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 2>(lc, in, ncp, out, nrows, scale, tw);
+          case 3: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 3, 3>(lc, in, ncp, out, nrows, scale, tw);
+          default: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 2>(lc, in, ncp, out, nrows, scale, tw);
         }
-      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 2>(lc, in, out, nrows, scale, tw);
+      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 2>(lc, in, ncp, out, nrows, scale, tw);
       default: return cudaErrorNotSupported;
     }
   } else {
     switch (n) {
-      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 3>(lc, in, out, nrows, scale, tw);
-      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 3>(lc, in, out, nrows, scale, tw);
-      case 512: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 3>(lc, in, out, nrows, scale, tw);
-      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 6, 3>(lc, in, out, nrows, scale, tw);
+      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
+      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
+      case 512: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
+      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
       default: return cudaErrorNotSupported;
     }
   }
@@ -292,8 +337,8 @@ cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, T *out, 
   template cudaError_t launch_fused_tma<T>(const LaunchCtx &, const FusedIO<T> &, const SpectralUpdate<T> &, const cx<T> *, \
                                            int);                                                                         \
   template cudaError_t launch_zfwd_nonlin_tma<T>(const LaunchCtx &, const T *, T *, cx<T> *, cx<T> *, long long, int,    \
-                                                 const NonlinDesc &, const cx<T> *);                                     \
-  template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, T *, long long, int, T, const cx<T> *);
+                                                 int, const NonlinDesc &, const cx<T> *);                                \
+  template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, int, T *, long long, int, T, const cx<T> *);
 INST(double)
 INST(float)
 

@@ -20,6 +20,7 @@
 #include "cuda_emu.h"
 #define MRL_DI inline
 #define MRL_HD inline
+#define MRL_HDC constexpr
 #define MRL_UNROLL
 #define MRL_DYN_SMEM(name) unsigned char *name = emu::g_dyn_smem
 #else
@@ -28,6 +29,7 @@
 #endif
 #define MRL_DI __device__ __forceinline__
 #define MRL_HD __host__ __device__ __forceinline__
+#define MRL_HDC __host__ __device__ constexpr
 #define MRL_UNROLL _Pragma("unroll")
 #define MRL_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
@@ -158,13 +160,82 @@ struct NoHook {
   MRL_DI void operator()() const {}
 };
 
+// Twiddle sources for the inter-stage factors W_N^{S p k}, k in [1,R).
+//  TwTable: looked up in a table of exp(-2 pi i k / N) (shared or global memory).
+//  TwRegs : for power-of-two radices the factors of one butterfly are powers of one root
+//           w = W_N^{S p}; a thread's (stage, butterfly) pairs never change, so it keeps
+//           w, w^2 (, w^4) in registers for the whole kernel and forms the other powers with a
+//           few multiplications - no shared-memory traffic for twiddles at all.
+template <class T> struct TwTable {
+  const cx<T> *tw;
+  template <int ST, int R, int S, int EB> MRL_DI void apply(cx<T> (&a)[R], int u, int b) const {
+    const int p = b / S;
+    MRL_UNROLL
+    for (int k = 1; k < R; ++k) a[k] = a[k] * tw[S * p * k];
+  }
+};
+
+// LEAN = true keeps only w per butterfly and squares it on the fly (fewer registers, 2 more
+// complex multiplications per radix-8 butterfly).
+template <class T, class C, bool LEAN = false> struct TwRegs {
+  static constexpr int E = C::E, TP = C::TP;
+  static MRL_HDC int lg(int r) { return r == 8 ? 3 : r == 4 ? 2 : r == 2 ? 1 : 0; }
+  static MRL_HDC int radix(int st) { return st == 0 ? C::R0 : st == 1 ? C::R1 : st == 2 ? C::R2 : C::R3; }
+  static MRL_HDC int span(int st) { return st == 0 ? 1 : st == 1 ? C::R0 : st == 2 ? C::R0 * C::R1 : C::R0 * C::R1 * C::R2; }
+  static MRL_HDC int nb(int r) { return LEAN ? 1 : lg(r); }  // bases kept per butterfly
+  static MRL_HDC int count(int st) { return st >= C::NS - 1 ? 0 : (E / radix(st)) * nb(radix(st)); }
+  static MRL_HDC int offset(int st) { return st == 0 ? 0 : offset(st - 1) + count(st - 1); }
+  static constexpr int TOTAL = offset(C::NS - 1) > 0 ? offset(C::NS - 1) : 1;
+  static_assert((C::R0 == 8 || C::R0 == 4 || C::R0 == 2) && (C::R1 == 8 || C::R1 == 4 || C::R1 == 2 || C::R1 == 1) &&
+                    (C::R2 == 8 || C::R2 == 4 || C::R2 == 2 || C::R2 == 1) && (C::R3 == 8 || C::R3 == 4 || C::R3 == 2 || C::R3 == 1),
+                "TwRegs needs power-of-two radices");
+  cx<T> w[TOTAL];
+
+  template <int ST> MRL_DI void init_stage(const cx<T> *tw, int t) {
+    if constexpr (ST < C::NS - 1) {
+      constexpr int R = radix(ST), S = span(ST), EB = E / R, L = nb(R);
+      MRL_UNROLL
+      for (int u = 0; u < EB; ++u) {
+        const int p = (t + TP * u) / S;
+        MRL_UNROLL
+        for (int l = 0; l < L; ++l) w[offset(ST) + u * L + l] = tw[S * p * (1 << l)];
+      }
+      init_stage<ST + 1>(tw, t);
+    }
+  }
+  // tw: table of exp(-2 pi i k / N) (any memory space); t: this thread's index within its pencil
+  MRL_DI void init(const cx<T> *tw, int t) { init_stage<0>(tw, t); }
+
+  template <int ST, int R, int S, int EB> MRL_DI void apply(cx<T> (&a)[R], int u, int) const {
+    constexpr int L = nb(R);
+    const cx<T> *b = w + offset(ST) + u * L;
+    const cx<T> w1 = b[0];
+    if constexpr (R == 2) {
+      a[1] = a[1] * w1;
+    } else {
+      const cx<T> w2 = LEAN ? w1 * w1 : b[L > 1 ? 1 : 0];
+      const cx<T> w3 = w1 * w2;
+      a[1] = a[1] * w1;
+      a[2] = a[2] * w2;
+      a[3] = a[3] * w3;
+      if constexpr (R == 8) {
+        const cx<T> w4 = LEAN ? w2 * w2 : b[L > 2 ? 2 : 0];
+        a[4] = a[4] * w4;
+        a[5] = a[5] * (w1 * w4);
+        a[6] = a[6] * (w2 * w4);
+        a[7] = a[7] * (w3 * w4);
+      }
+    }
+  }
+};
+
 template <class T, class C> struct RegFFT {
   static constexpr int E = C::E, TP = C::TP;
 
   // HOOK runs once, right after the last shared-memory exchange has been read back (from then
   // on the exchange buffer is no longer touched by this transform).
-  template <int ST, int R, int S, class SM, class BAR, class HOOK>
-  static MRL_DI void stage(cx<T> (&v)[C::E], int t, const SM &sm, const cx<T> *tw, const BAR &bar, const HOOK &hook) {
+  template <int ST, int R, int S, class SM, class TW, class BAR, class HOOK>
+  static MRL_DI void stage(cx<T> (&v)[C::E], int t, const SM &sm, const TW &tw, const BAR &bar, const HOOK &hook) {
     constexpr int EB = E / R;
     constexpr bool last = (ST == C::NS - 1);
     MRL_UNROLL
@@ -179,9 +250,9 @@ template <class T, class C> struct RegFFT {
       } else {
         const int b = t + TP * u;
         const int q = b % S, p = b / S;
-        sm.st(q + S * (R * p), a[0]);
+        tw.template apply<ST, R, S, EB>(a, u, b);
         MRL_UNROLL
-        for (int k = 1; k < R; ++k) sm.st(q + S * (R * p + k), a[k] * tw[S * p * k]);
+        for (int k = 0; k < R; ++k) sm.st(q + S * (R * p + k), a[k]);
       }
     }
     if constexpr (!last) {
@@ -197,15 +268,20 @@ template <class T, class C> struct RegFFT {
     }
   }
 
-  // tw: table of exp(-2 pi i k / N), k in [0,N)
-  template <class SM, class BAR = CtaSync, class HOOK = NoHook>
-  static MRL_DI void run(cx<T> (&v)[C::E], int t, const SM &sm, const cx<T> *tw, const BAR &bar = BAR(),
-                         const HOOK &hook = HOOK()) {
+  template <class SM, class TW, class BAR, class HOOK>
+  static MRL_DI void run_tw(cx<T> (&v)[C::E], int t, const SM &sm, const TW &tw, const BAR &bar, const HOOK &hook) {
     stage<0, C::R0, 1>(v, t, sm, tw, bar, hook);
     if constexpr (C::NS > 1) stage<1, C::R1, C::R0>(v, t, sm, tw, bar, hook);
     if constexpr (C::NS > 2) stage<2, C::R2, C::R0 * C::R1>(v, t, sm, tw, bar, hook);
     if constexpr (C::NS > 3) stage<3, C::R3, C::R0 * C::R1 * C::R2>(v, t, sm, tw, bar, hook);
     if constexpr (C::NS == 1) hook();
+  }
+
+  // tw: table of exp(-2 pi i k / N), k in [0,N)
+  template <class SM, class BAR = CtaSync, class HOOK = NoHook>
+  static MRL_DI void run(cx<T> (&v)[C::E], int t, const SM &sm, const cx<T> *tw, const BAR &bar = BAR(),
+                         const HOOK &hook = HOOK()) {
+    run_tw(v, t, sm, TwTable<T>{tw}, bar, hook);
   }
 };
 

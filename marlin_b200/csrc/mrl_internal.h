@@ -45,6 +45,7 @@ struct mrl_split_plan {
   void *A = nullptr, *B = nullptr;  // partial spectra (one allocation, B = A + rtotal)
   std::vector<void *> ring;         // history+1 nonlinear-term slots
   int cur = 0, stored = 0;
+  int ncp = 0;                      // row pitch of the work spectra (>= n_last/2+1)
 };
 
 namespace mrl {

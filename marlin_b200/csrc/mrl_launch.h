@@ -66,9 +66,11 @@ template <class T>
 cudaError_t launch_fused_tma(const LaunchCtx &lc, const FusedIO<T> &io, const SpectralUpdate<T> &up, const cx<T> *tw, int n);
 template <class T>
 cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int n,
-                                   const NonlinDesc &nl, const cx<T> *tw);
+                                   int ncp, const NonlinDesc &nl, const cx<T> *tw);
 template <class T>
-cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, T *out, long long nrows, int n, T scale, const cx<T> *tw);
+cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, int n, T scale,
+                                  const cx<T> *tw);
+bool tma_enabled();
 template <class T>
 cudaError_t launch_kfactor(const LaunchCtx &lc, T *out, const T *kx, const T *ky, const T *kz, int n0, int n1, int n2,
                            int kind, T factor);

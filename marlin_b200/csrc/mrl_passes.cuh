@@ -28,6 +28,9 @@ template <class T> struct StridedIO {
   int ncb;  // column blocks (of TK) per outer slice
   T scale;  // multiplies the result on store
   int inverse;
+  // optional separate output layout (TMA kernel only; 0 = same as the input layout)
+  long long out_pitch, out_outer_stride;
+  int nvalid;  // TMA kernel only: columns >= nvalid are padding (0 = all ncols valid)
 
   MRL_HD int ntiles() const { return nfields * nouter * ncb; }
 };
@@ -325,7 +328,8 @@ enum { MRL_KMODE_2D = 0, MRL_KMODE_3D = 1, MRL_KMODE_3D_SLAB = 2 };
 template <class T> struct SpectralUpdate {
   const T *kx, *ky, *kz;  // reciprocal axes (2 pi fftfreq / rfftfreq)
   int kmode;
-  int nzc;        // length of the last (halved) axis
+  int nzc;        // row pitch of the last (halved) axis
+  int nzv;        // valid entries of the last axis (0 = nzc; TMA kernel only)
   int x0;         // first global x index of this rank's slab (slab mode)
   int closed_M, closed_L, has_L;
   T Mfac, Lfac;
@@ -379,6 +383,8 @@ template <class T> struct FusedIO {
   long long pitch, outer_stride;
   int ncb;
   T scale;
+  // multi-GPU slab layout (TMA kernel only): data staged as [nranks][nouter][nyl][ncols]
+  int slab, nyl, nranks;
 };
 
 template <class T, class C, int TK>
@@ -469,6 +475,15 @@ __global__ void __launch_bounds__(256) k_fused_gen(FusedIO<T> io, SpectralUpdate
 }
 
 // ======================================================================== small pointwise kernels
+#if defined(MRL_EMU)
+template <class T> MRL_DI T mul_rn(T a, T b) { return a * b; }
+template <class T> MRL_DI T add_rn(T a, T b) { return a + b; }
+#else
+MRL_DI double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+MRL_DI double add_rn(double a, double b) { return __dadd_rn(a, b); }
+MRL_DI float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+MRL_DI float add_rn(float a, float b) { return __fadd_rn(a, b); }
+#endif
 // ReciprocalLaplacianFactor (kind 0: -k2*f) / ReciprocalLaplacianSquareFactor (kind 1: k2*k2*f)
 template <class T>
 __global__ void k_kfactor(T *out, const T *kx, const T *ky, const T *kz, int n0, int n1, int n2, int kind, T factor) {
@@ -477,9 +492,11 @@ __global__ void k_kfactor(T *out, const T *kx, const T *ky, const T *kz, int n0,
     const int iz = (int)(i % n2);
     const int iy = (int)((i / n2) % n1);
     const int ix = (int)(i / ((long long)n1 * n2));
+    // rounded exactly like the reference's separate libTorch ops (no FMA contraction):
+    // k2 = (kx*kx + ky*ky) + kz*kz ; -k2*f ; (k2*k2)*f
     const T a = kx[ix], b = ky[iy], c = kz[iz];
-    const T kk = a * a + b * b + c * c;
-    out[i] = kind == 0 ? (-kk * factor) : (kk * kk * factor);
+    const T kk = add_rn(add_rn(mul_rn(a, a), mul_rn(b, b)), mul_rn(c, c));
+    out[i] = kind == 0 ? mul_rn(-kk, factor) : mul_rn(mul_rn(kk, kk), factor);
   }
 }
 

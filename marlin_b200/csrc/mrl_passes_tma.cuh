@@ -18,16 +18,50 @@
 
 namespace mrl {
 
-MRL_DI unsigned char *align128(unsigned char *p) {
-  return (unsigned char *)(((unsigned long long)p + 127ull) & ~127ull);
+// Development switch (MRL_DEBUG_NOFFT=1): skip the butterflies and exchanges so that a pass
+// degenerates to "bulk-load tile, store tile" - measures the memory-side ceiling of its access
+// pattern.  Results are wrong by construction; never set outside tools/.
+#if defined(MRL_EMU)
+static int g_debug_nofft = 0;
+#else
+__device__ int g_debug_nofft = 0;
+#endif
+template <class T, class C, class V, class SM, class TW, class BAR, class HOOK>
+MRL_DI void fft_or_skip(V &v, int t, const SM &sm, const TW &tw, const BAR &bar, const HOOK &hook) {
+  if (g_debug_nofft) {
+    bar.sync_release();
+    hook();
+  } else {
+    RegFFT<T, C>::run_tw(v, t, sm, tw, bar, hook);
+  }
+}
+
+// Round a shared-memory pointer up to 128 bytes with pointer arithmetic only, so the compiler
+// keeps the shared address space (LDS/STS instead of generic LD/ST).
+MRL_DI unsigned char *align128(unsigned char *p) { return p + ((128u - (smem_u32(p) & 127u)) & 127u); }
+
+// Thread -> pencil-thread index t such that the threads holding t and (TP - t) % TP sit in the
+// same warp (needed to split/merge Hermitian pairs with warp shuffles).  wl: linear index of the
+// thread within its pencil's TP threads; returns t and the partner's lane.
+template <int TP> MRL_DI int pair_map(int wl, int lane, int &partner_lane) {
+  if constexpr (TP <= 32) {
+    partner_lane = lane - wl + (TP - wl) % TP;
+    return wl;
+  } else {
+    const int l = wl & 31, q = (wl >> 5) * 16 + (l & 15);
+    partner_lane = q == 0 ? lane : (lane ^ 16);
+    return l < 16 ? q : (q == 0 ? TP / 2 : TP - q);
+  }
 }
 
 // ======================================================================== strided pass
 // Input through a 3-D tensor map over the real view [nouter][n][2*ncols] of the complex array
 // (box = TK complex columns x min(n,256) rows); output by direct stores.
 template <class T> struct StridedTmaIO {
-  cx<T> *out;
+  cx<T> *out, *out1;     // output base of field 0 / field 1
+  int nouter_f;          // outer slices per field
   int n, ncols, nouter;  // nouter counts (field, outer) slices
+  int nvalid;            // columns >= nvalid of a slice are padding: transformed but never stored
   long long pitch, outer_stride;
   int ncb;
   T scale;
@@ -42,11 +76,12 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   constexpr int TILE = N * TK;  // complex elements per slot
   MRL_DYN_SMEM(smem_raw);
   cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));
-  cx<T> *tw = slots + (size_t)NS * TILE;
-  uint64_t *full = reinterpret_cast<uint64_t *>(tw + N);
+  uint64_t *full = reinterpret_cast<uint64_t *>(slots + (size_t)NS * TILE);
   const int tid = threadIdx.x;
   const int g = tid / GT, gt = tid - g * GT;
   const int col = gt % TK, t = gt / TK;
+  TwRegs<T, C> twr;
+  twr.init(tw_g, t);
   const int ntiles = io.nouter * io.ncb;
   const int nloc = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -64,7 +99,6 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
     mbar_init_fence();
   }
-  for (int i = tid; i < N; i += NG * GT) tw[i] = tw_g[i];
   __syncthreads();
   if (tid == 0)
     for (int j = 0; j < NS && j < nloc; ++j) issue(j);
@@ -76,7 +110,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     const SmTile<T, TK> sm{slots + (size_t)s * TILE, col};
     const int tile = blockIdx.x + j * gridDim.x;
     const int o = tile / io.ncb, c = (tile - o * io.ncb) * TK + col;
-    const bool ok = c < io.ncols;
+    const bool ok = c < io.nvalid;
     cx<T> v[E];
     MRL_UNROLL
     for (int e = 0; e < E; ++e) {
@@ -84,11 +118,12 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       if (io.inverse) v[e].y = -v[e].y;
     }
     bar.sync();  // all inputs are in registers before the exchange overwrites the slot
-    RegFFT<T, C>::run(v, t, sm, tw, bar, [&] {
+    fft_or_skip<T, C>(v, t, sm, twr, bar, [&] {
       if (gt == 0 && j + NS < nloc) issue(j + NS);
     });
     if (ok) {
-      cx<T> *dst = io.out + (long long)o * io.outer_stride + c;
+      cx<T> *dst = (o < io.nouter_f ? io.out + (long long)o * io.outer_stride
+                                    : io.out1 + (long long)(o - io.nouter_f) * io.outer_stride) + c;
       MRL_UNROLL
       for (int e = 0; e < E; ++e)
         dst[(long long)(t + TP * e) * io.pitch] = mk<T>(v[e].x * io.scale, (io.inverse ? -v[e].y : v[e].y) * io.scale);
@@ -100,16 +135,28 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
 // Per group three dedicated slots: G (nonlinearity spectrum), C (variable spectrum), O (newest
 // old nonlinear term, when the Adams-Bashforth order needs one).  Further old terms (order >= 3)
 // are read with plain loads.
+// Plain layout: [n][ncols] (one outer slice).  Slab layout (multi-GPU, reciprocal space split
+// along x): the transform axis y arrives as P blocks of nyl rows received from the P ranks,
+// stored [P][nouter = nxl][nyl][ncols = nzc]; the 4-D tensor map delivers the rows of one
+// (x, column block) in y order, and the result goes back to the same staged layout so that
+// block s is contiguous for the return all-to-all.
 template <class T> struct FusedTmaIO {
   cx<T> *outU;
   int n, ncols, ncb;
   long long pitch;
   T scale;
+  int slab, nouter, nyl;
+  MRL_DI long long row_off(int o, int row) const {
+    if (!slab) return (long long)row * pitch;
+    const int s = row / nyl, yl = row - s * nyl;
+    return (((long long)s * nouter + o) * nyl + yl) * pitch;
+  }
 };
 
 template <class T> struct SpectralUpdate2 {
   const T *kx, *ky, *kz;
   int kmode, nzc, x0;
+  int nzv;  // valid entries of the last axis (nzc may be a padded pitch)
   int closed_M, closed_L, has_L;
   T Mfac, Lfac;
   const T *Mbuf, *Lbuf;
@@ -160,12 +207,13 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   constexpr int TILE = N * TK;
   MRL_DYN_SMEM(smem_raw);
   cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));
-  cx<T> *tw = slots + (size_t)NG * 3 * TILE;
-  uint64_t *full = reinterpret_cast<uint64_t *>(tw + N);  // [NG][3]
+  uint64_t *full = reinterpret_cast<uint64_t *>(slots + (size_t)NG * 3 * TILE);  // [NG][3]
   const int tid = threadIdx.x;
   const int g = tid / GT, gt = tid - g * GT;
   const int col = gt % TK, t = gt / TK;
-  const int ntiles = io.ncb;
+  TwRegs<T, C, true> twr;
+  twr.init(tw_g, t);
+  const int ntiles = io.nouter * io.ncb;
   const int stride = gridDim.x * NG;
   const int first = blockIdx.x * NG + g;  // tiles of this group: first + j*stride
   const int nloc = (first < ntiles) ? (ntiles - first + stride - 1) / stride : 0;
@@ -174,17 +222,21 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   uint64_t *bG = &full[g * 3 + 0], *bC = &full[g * 3 + 1], *bO = &full[g * 3 + 2];
 
   auto issue = [&](const TensorMap *tm, cx<T> *dst, uint64_t *b, int j) {
-    const int cb = first + j * stride;
+    const int tile = first + j * stride;
+    const int o = tile / io.ncb, cb = tile - o * io.ncb;
     mbar_expect_tx(b, (uint32_t)(TILE * sizeof(cx<T>)));
-    MRL_UNROLL
-    for (int q = 0; q < NBOX; ++q) tma_load_3d(dst + q * BOXR * TK, tm, b, cb * TK * 2, q * BOXR, 0);
+    if (io.slab) {
+      tma_load_4d(dst, tm, b, cb * TK * 2, 0, o, 0);
+    } else {
+      MRL_UNROLL
+      for (int q = 0; q < NBOX; ++q) tma_load_3d(dst + q * BOXR * TK, tm, b, cb * TK * 2, q * BOXR, 0);
+    }
   };
 
   if (tid == 0) {
     for (int s = 0; s < NG * 3; ++s) mbar_init(&full[s], 1);
     mbar_init_fence();
   }
-  for (int i = tid; i < N; i += NG * GT) tw[i] = tw_g[i];
   __syncthreads();
   if (gt == 0 && nloc > 0) {
     issue(&tmG, sG, bG, 0);
@@ -195,8 +247,10 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   const GroupBarrier bar{1 + g, GT};
   for (int j = 0; j < nloc; ++j) {
     const uint32_t par = (uint32_t)(j & 1);
-    const int c = (first + j * stride) * TK + col;
-    const bool ok = c < io.ncols;
+    const int tile = first + j * stride;
+    const int o = tile / io.ncb;
+    const int c = (tile - o * io.ncb) * TK + col;
+    const bool ok = c < io.ncols && (up.kmode == MRL_KMODE_2D || (c % up.nzc) < up.nzv);
     const bool more = j + 1 < nloc;
     cx<T> a[E], gh[E];
     // ---- nonlinearity: forward transform, result stays in registers
@@ -206,62 +260,73 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       MRL_UNROLL
       for (int e = 0; e < E; ++e) gh[e] = sm.ld(t + TP * e);
       bar.sync();
-      RegFFT<T, C>::run(gh, t, sm, tw, bar, [&] {
+      fft_or_skip<T, C>(gh, t, sm, twr, bar, [&] {
         if (gt == 0 && more) issue(&tmG, sG, bG, j + 1);
       });
     }
-    // ---- variable: forward transform
+    // ---- variable: forward transform; its slot is re-armed as soon as the transform has left it
     mbar_wait(bC, par);
-    const SmTile<T, TK> smc{sC, col};
-    MRL_UNROLL
-    for (int e = 0; e < E; ++e) a[e] = smc.ld(t + TP * e);
-    bar.sync();
-    RegFFT<T, C>::run(a, t, smc, tw, bar);
-    // ---- k-space update
-    if (use_old) mbar_wait(bO, par);
     {
-      const SmTile<T, TK> smo{sO, col};
+      const SmTile<T, TK> smc{sC, col};
       MRL_UNROLL
-      for (int e = 0; e < E; ++e) {
-        const int jj = t + TP * e;
-        const cx<T> no = use_old ? smo.ld(jj) : mk<T>(T(0), T(0));
-        if (ok) a[e] = conj(up.apply(0, jj, c, (long long)jj * io.pitch + c, a[e], gh[e], no));
-      }
+      for (int e = 0; e < E; ++e) a[e] = smc.ld(t + TP * e);
+      bar.sync();
+      fft_or_skip<T, C>(a, t, smc, twr, bar, [&] {
+        if (gt == 0 && more) issue(&tmC, sC, bC, j + 1);
+      });
     }
-    if (use_old) {
-      bar.sync_release();
-      if (gt == 0 && more) issue(&tmO, sO, bO, j + 1);
+    // ---- k-space update (newest old nonlinear term from its slot)
+    if (use_old) mbar_wait(bO, par);
+    const SmTile<T, TK> smo{sO, col};
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const int jj = t + TP * e;
+      const cx<T> no = use_old ? smo.ld(jj) : mk<T>(T(0), T(0));
+      if (ok) a[e] = conj(up.apply(o, jj, c, io.row_off(o, jj) + c, a[e], gh[e], no));
     }
-    // ---- inverse transform of the updated variable (exchange through the C slot)
-    RegFFT<T, C>::run(a, t, smc, tw, bar, [&] {
-      if (gt == 0 && more) issue(&tmC, sC, bC, j + 1);
+    bar.sync();  // every thread has taken its old-term values: the O slot becomes the exchange buffer
+    // ---- inverse transform of the updated variable (exchange through the O slot)
+    fft_or_skip<T, C>(a, t, smo, twr, bar, [&] {
+      if (gt == 0 && more && use_old) issue(&tmO, sO, bO, j + 1);
     });
     if (ok) {
       cx<T> *dst = io.outU + c;
       MRL_UNROLL
-      for (int e = 0; e < E; ++e) dst[(long long)(t + TP * e) * io.pitch] = mk<T>(a[e].x * io.scale, -a[e].y * io.scale);
+      for (int e = 0; e < E; ++e) dst[io.row_off(o, t + TP * e)] = mk<T>(a[e].x * io.scale, -a[e].y * io.scale);
     }
   }
 }
 
 // ======================================================================== P1: z r2c of (c + i F(c))
 // A tile is PPB consecutive real rows (one contiguous bulk copy).  Each group owns NS input
-// slots and one padded complex exchange buffer per pencil.
+// slots and one padded complex exchange buffer per pencil.  The Hermitian split
+// C_k = (Z_k + conj Z_{N-k})/2, G_k = (Z_k - conj Z_{N-k})/2i needs Z_{N-k}, which lives in the
+// thread holding pencil index TP - t: pair_map() puts both in one warp and the values move with
+// warp shuffles, so the split costs no shared-memory traffic and no barrier.
+template <class T> MRL_DI cx<T> shfl_cx(cx<T> v, int lane) {
+  return mk<T>(__shfl_sync(0xffffffffu, v.x, lane), __shfl_sync(0xffffffffu, v.y, lane));
+}
+
 template <class T, class C, int PPB, int NG, int NS, class F>
 __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
-    k_zfwd_tma(const T *cin, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, F f, const cx<T> *tw_g) {
+    k_zfwd_tma(const T *cin, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int ncp, F f, const cx<T> *tw_g) {
   constexpr int N = C::N, TP = C::TP, E = C::E, GT = PPB * TP;
   constexpr int NP = N + (N >> 3) + 1;
-  constexpr int NC = N / 2 + 1;
+  // ncp: row pitch of the half spectra (>= N/2+1; padded to 128 bytes inside the split plan)
+  static_assert(E % 2 == 0, "Hermitian split by shuffles needs an even number of points per thread");
+  static_assert(GT % 32 == 0, "a group must be whole warps (full-mask shuffles inside the group loop)");
   MRL_DYN_SMEM(smem_raw);
   unsigned char *base = align128(smem_raw);
   T *slots = reinterpret_cast<T *>(base);                                       // [NG][NS][PPB*N] real
   cx<T> *xbuf = reinterpret_cast<cx<T> *>(slots + (size_t)NG * NS * PPB * N);   // [NG][PPB][NP]
-  cx<T> *tw = xbuf + (size_t)NG * PPB * NP;
-  uint64_t *full = reinterpret_cast<uint64_t *>(tw + N);                        // [NG][NS]
+  uint64_t *full = reinterpret_cast<uint64_t *>(xbuf + (size_t)NG * PPB * NP);  // [NG][NS]
   const int tid = threadIdx.x;
   const int g = tid / GT, gt = tid - g * GT;
-  const int t = gt % TP, pl = gt / TP;
+  const int pl = gt / TP;
+  int plane;
+  const int t = pair_map<TP>(gt % TP, tid & 31, plane);
+  TwRegs<T, C> twr;
+  twr.init(tw_g, t);
   const long long ntiles = (nrows + PPB - 1) / PPB;
   const long long stride = (long long)gridDim.x * NG;
   const long long first = (long long)blockIdx.x * NG + g;
@@ -283,7 +348,6 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     for (int s = 0; s < NG * NS; ++s) mbar_init(&full[s], 1);
     mbar_init_fence();
   }
-  for (int i = tid; i < N; i += NG * GT) tw[i] = tw_g[i];
   __syncthreads();
   if (gt == 0)
     for (int j = 0; j < NS && j < nloc; ++j) issue(j);
@@ -304,18 +368,32 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
       if (mu_out && ok) mu_out[p * N + t + TP * e] = b;
       v[e] = mk<T>(a, b);
     }
-    bar.sync_release();  // slot consumed; also orders the previous tile's separation reads
+    bar.sync_release();  // slot consumed by the whole group: re-arm it
     if (gt == 0 && j + NS < nloc) issue(j + NS);
-    RegFFT<T, C>::run(v, t, sm, tw, bar);
+    fft_or_skip<T, C>(v, t, sm, twr, bar, NoHook());
+    // Hermitian split: partner element of (t, e) is (TP - t, E-1-e); thread 0 pairs (0, e) with (0, E-e)
+    cx<T> w[E / 2];
     MRL_UNROLL
-    for (int e = 0; e < E; ++e) sm.st(t + TP * e, v[e]);
-    bar.sync();
+    for (int e = 0; e < E / 2; ++e) w[e] = shfl_cx(v[E - 1 - e], plane);
+    if (t == 0) {
+      w[0] = v[0];
+      MRL_UNROLL
+      for (int e = 1; e < E / 2; ++e) w[e] = v[E - e];
+    }
     if (ok) {
-      for (int k = t; k <= N / 2; k += TP) {
+      cx<T> *oc = outC + p * ncp + t, *og = outG + p * ncp + t;
+      MRL_UNROLL
+      for (int e = 0; e < E / 2; ++e) {
         cx<T> A, B;
-        r2c_separate(sm.ld(k), sm.ld(k == 0 ? 0 : N - k), A, B);
-        outC[p * NC + k] = A;
-        outG[p * NC + k] = B;
+        r2c_separate(v[e], w[e], A, B);
+        oc[TP * e] = A;
+        og[TP * e] = B;
+      }
+      if (t == 0) {
+        cx<T> A, B;
+        r2c_separate(v[E / 2], v[E / 2], A, B);
+        oc[N / 2] = A;
+        og[N / 2] = B;
       }
     }
   }
@@ -325,19 +403,20 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
 // A tile is PPB pencils = 2*PPB consecutive half-spectrum rows (one contiguous bulk copy).
 template <class T, class C, int PPB, int NG, int NS>
 __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
-    k_zinv_tma(const cx<T> *in, T *out, long long nrows, T scale, const cx<T> *tw_g) {
+    k_zinv_tma(const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw_g) {
   constexpr int N = C::N, TP = C::TP, E = C::E, GT = PPB * TP;
   constexpr int NP = N + (N >> 3) + 1;
-  constexpr int NC = N / 2 + 1;
-  constexpr int SLOT = 2 * PPB * NC;  // complex elements per slot
+  constexpr int NCMAX = (N / 2 + 1 + 15) & ~15;  // largest padded row pitch (ncp <= NCMAX)
+  constexpr int SLOT = 2 * PPB * NCMAX;          // complex elements per slot
   MRL_DYN_SMEM(smem_raw);
   cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));  // [NG][NS][SLOT]
   cx<T> *xbuf = slots + (size_t)NG * NS * SLOT;                  // [NG][PPB][NP]
-  cx<T> *tw = xbuf + (size_t)NG * PPB * NP;
-  uint64_t *full = reinterpret_cast<uint64_t *>(tw + N);
+  uint64_t *full = reinterpret_cast<uint64_t *>(xbuf + (size_t)NG * PPB * NP);
   const int tid = threadIdx.x;
   const int g = tid / GT, gt = tid - g * GT;
   const int t = gt % TP, pl = gt / TP;
+  TwRegs<T, C> twr;
+  twr.init(tw_g, t);
   const long long npencils = (nrows + 1) / 2;
   const long long ntiles = (npencils + PPB - 1) / PPB;
   const long long stride = (long long)gridDim.x * NG;
@@ -351,16 +430,15 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     const long long left = nrows - row0;
     const int rows = left < 2 * PPB ? (int)left : 2 * PPB;
     const int s = j % NS;
-    const uint32_t bytes = (uint32_t)(rows * NC * sizeof(cx<T>));
+    const uint32_t bytes = (uint32_t)(rows * ncp * sizeof(cx<T>));
     mbar_expect_tx(&gb[s], bytes);
-    bulk_load_1d(gs + (size_t)s * SLOT, in + row0 * NC, bytes, &gb[s]);
+    bulk_load_1d(gs + (size_t)s * SLOT, in + row0 * ncp, bytes, &gb[s]);
   };
 
   if (tid == 0) {
     for (int s = 0; s < NG * NS; ++s) mbar_init(&full[s], 1);
     mbar_init_fence();
   }
-  for (int i = tid; i < N; i += NG * GT) tw[i] = tw_g[i];
   __syncthreads();
   if (gt == 0)
     for (int j = 0; j < NS && j < nloc; ++j) issue(j);
@@ -373,7 +451,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     const long long r0 = 2 * p;
     const bool ok = p < npencils, ok2 = r0 + 1 < nrows;
     mbar_wait(&gb[s], (uint32_t)((j / NS) & 1));
-    const cx<T> *X = gs + (size_t)s * SLOT + (size_t)(2 * pl) * NC, *Y = X + NC;
+    const cx<T> *X = gs + (size_t)s * SLOT + (size_t)(2 * pl) * ncp, *Y = X + ncp;
     cx<T> v[E];
     MRL_UNROLL
     for (int e = 0; e < E; ++e) {
@@ -386,7 +464,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     }
     bar.sync_release();
     if (gt == 0 && j + NS < nloc) issue(j + NS);
-    RegFFT<T, C>::run(v, t, sm, tw, bar);
+    fft_or_skip<T, C>(v, t, sm, twr, bar, NoHook());
     if (ok) {
       MRL_UNROLL
       for (int e = 0; e < E; ++e) {

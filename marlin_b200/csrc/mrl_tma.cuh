@@ -51,6 +51,13 @@ MRL_DI void tma_load_3d(void *smem_dst, const TensorMap *tm, uint64_t *bar, int 
       "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+MRL_DI void tma_load_4d(void *smem_dst, const TensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // 1-D bulk copy global -> shared (bytes: multiple of 16, both addresses 16-byte aligned)
 MRL_DI void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -63,14 +70,15 @@ MRL_DI void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1
 
 #else  // --------------------------------------------------------------- host emulation
 
-struct TensorMap {  // what the emulation needs of a 3-D tiled map
+struct TensorMap {  // what the emulation needs of a tiled map (rank <= 4)
   const unsigned char *base;
   int esize;
-  long long dim[3], stride[3];  // stride in bytes (stride[0] = esize)
-  int box[3];
+  long long dim[4], stride[4];  // stride in bytes (stride[0] = esize)
+  int box[4];
 };
 #define MRL_GRID_CONSTANT
 
+MRL_DI uint32_t smem_u32(const void *p) { return (uint32_t)(uintptr_t)p; }
 MRL_DI void mbar_init(uint64_t *bar, int) { *bar = 0; }
 MRL_DI void mbar_init_fence() {}
 // copies are performed synchronously at issue, so arming a phase also completes it: the
@@ -80,20 +88,24 @@ MRL_DI void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (*(volatile uint64_t *)bar == 0 || ((*(volatile uint64_t *)bar - 1) & 1) != parity) emu::yield();
 }
 MRL_DI void fence_proxy_async() {}
-MRL_DI void tma_load_3d(void *smem_dst, const TensorMap *tm, uint64_t *bar, int c0, int c1, int c2) {
+MRL_DI void tma_load_4d(void *smem_dst, const TensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3) {
   unsigned char *d = (unsigned char *)smem_dst;
-  for (int k = 0; k < tm->box[2]; ++k)
-    for (int j = 0; j < tm->box[1]; ++j)
-      for (int i = 0; i < tm->box[0]; ++i) {
-        const long long a = c0 + i, b = c1 + j, c = c2 + k;
-        const bool in = a < tm->dim[0] && b < tm->dim[1] && c < tm->dim[2];
-        if (in)
-          memcpy(d, tm->base + a * tm->stride[0] + b * tm->stride[1] + c * tm->stride[2], tm->esize);
-        else
-          memset(d, 0, tm->esize);
-        d += tm->esize;
-      }
+  for (int m = 0; m < tm->box[3]; ++m)
+    for (int k = 0; k < tm->box[2]; ++k)
+      for (int j = 0; j < tm->box[1]; ++j)
+        for (int i = 0; i < tm->box[0]; ++i) {
+          const long long a = c0 + i, b = c1 + j, c = c2 + k, e = c3 + m;
+          const bool in = a < tm->dim[0] && b < tm->dim[1] && c < tm->dim[2] && e < tm->dim[3];
+          if (in)
+            memcpy(d, tm->base + a * tm->stride[0] + b * tm->stride[1] + c * tm->stride[2] + e * tm->stride[3], tm->esize);
+          else
+            memset(d, 0, tm->esize);
+          d += tm->esize;
+        }
   (void)bar;
+}
+MRL_DI void tma_load_3d(void *smem_dst, const TensorMap *tm, uint64_t *bar, int c0, int c1, int c2) {
+  tma_load_4d(smem_dst, tm, bar, c0, c1, c2, 0);
 }
 MRL_DI void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *) { memcpy(smem_dst, gsrc, bytes); }
 MRL_DI void named_bar_sync(int id, int nthreads) { emu::named_barrier(id, nthreads); }

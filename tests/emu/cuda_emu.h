@@ -89,13 +89,13 @@ inline void run_block(int nthreads, size_t stack_bytes) {
     }
     if (done == nthreads) break;
     // release barriers
-    int count[17] = {0}, need[17] = {0}, live = nthreads - done, released = 0;
+    int count[128] = {0}, need[128] = {0}, live = nthreads - done, released = 0;
     for (int t = 0; t < nthreads; ++t)
       if (g_state[t] == 1) {
         count[g_bar_id[t]]++;
         need[g_bar_id[t]] = g_bar_n[t] < 0 ? live : g_bar_n[t];
       }
-    for (int id = 0; id < 17; ++id)
+    for (int id = 0; id < 128; ++id)
       if (count[id] && count[id] >= need[id]) {
         ++g_barrier_count;
         ++released;
@@ -108,6 +108,20 @@ inline void run_block(int nthreads, size_t stack_bytes) {
       abort();
     }
   }
+}
+// warp shuffle: the 32 fibers of a warp meet at a per-warp barrier, publish, meet again, read
+inline double g_shfl_slot[64][32];
+template <class V> inline V shfl_sync(V val, int src_lane) {
+  const int lin = g_cur, warp = lin / 32, lane = lin % 32;
+  static_assert(sizeof(V) <= 8, "shfl_sync: value too large");
+  const int nthr = (int)(g_blockDim.x * g_blockDim.y * g_blockDim.z);
+  const int wn = nthr - warp * 32 < 32 ? nthr - warp * 32 : 32;  // threads that exist in this warp
+  memcpy(&g_shfl_slot[warp][lane], &val, sizeof(V));
+  named_barrier(32 + warp, wn);
+  V out;
+  memcpy(&out, &g_shfl_slot[warp][src_lane & 31], sizeof(V));
+  named_barrier(32 + warp, wn);
+  return out;
 }
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f, size_t stack_bytes = 96 * 1024) {
@@ -137,6 +151,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F f, size_t stack_b
 #define blockDim emu::g_blockDim
 #define gridDim emu::g_gridDim
 #define __syncthreads() emu::syncthreads()
+#define __shfl_sync(mask, val, lane) emu::shfl_sync(val, lane)
 template <class T> inline T __ldg(const T *p) { return *p; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 #define __shared__ static

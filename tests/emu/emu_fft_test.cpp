@@ -228,30 +228,31 @@ static TensorMap emu_map(const void *base, int esize, long long d0, long long d1
   TensorMap m;
   m.base = (const unsigned char *)base;
   m.esize = esize;
-  m.dim[0] = d0; m.dim[1] = d1; m.dim[2] = d2;
-  m.stride[0] = esize; m.stride[1] = s1; m.stride[2] = s2;
-  m.box[0] = b0; m.box[1] = b1; m.box[2] = 1;
+  m.dim[0] = d0; m.dim[1] = d1; m.dim[2] = d2; m.dim[3] = 1;
+  m.stride[0] = esize; m.stride[1] = s1; m.stride[2] = s2; m.stride[3] = 0;
+  m.box[0] = b0; m.box[1] = b1; m.box[2] = 1; m.box[3] = 1;
   return m;
 }
 
 template <class C, int TK, int NG, int NS> static void run_strided_tma(StridedIO<double> io0, const cx<double> *tw, int grid) {
   StridedTmaIO<double> io;
-  io.out = io0.out[0];
+  io.out = io0.out[0]; io.out1 = io0.out[0]; io.nouter_f = io0.nouter; io.nvalid = io0.ncols;
   io.n = io0.n; io.ncols = io0.ncols; io.nouter = io0.nouter;
   io.pitch = io0.pitch; io.outer_stride = io0.outer_stride;
   io.ncb = (io0.ncols + TK - 1) / TK;
   io.scale = io0.scale; io.inverse = io0.inverse;
   const long long rowb = io.pitch * 16;
   TensorMap tm = emu_map(io0.in[0], 8, 2LL * io.ncols, io.n, io.nouter, rowb, rowb * io.n, 2 * TK, C::N < 256 ? C::N : 256);
-  size_t smem = (size_t)(NS * C::N * TK + C::N) * 16 + NS * 8 + 128;
+  size_t smem = (size_t)(NS * C::N * TK) * 16 + NS * 8 + 128;
   emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_strided_tma<double, C, TK, NG, NS>(tm, io, tw); }, 64 * 1024);
 }
 
 template <class C, int TK, int NG> static void run_fused_tma(FusedIO<double> io0, SpectralUpdate<double> up0, const cx<double> *tw, int grid) {
   FusedTmaIO<double> io;
   io.outU = io0.outU; io.n = io0.n; io.ncols = io0.ncols; io.ncb = (io0.ncols + TK - 1) / TK; io.pitch = io0.pitch; io.scale = io0.scale;
+  io.slab = 0; io.nouter = 1; io.nyl = 0;
   SpectralUpdate2<double> up{};
-  up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz; up.kmode = up0.kmode; up.nzc = up0.nzc; up.x0 = up0.x0;
+  up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz; up.kmode = up0.kmode; up.nzc = up0.nzc; up.nzv = up0.nzc; up.x0 = up0.x0;
   up.closed_M = up0.closed_M; up.closed_L = up0.closed_L; up.has_L = up0.has_L; up.Mfac = up0.Mfac; up.Lfac = up0.Lfac;
   up.dt = up0.dt; up.b0 = up0.b0; up.nold = up0.nold; up.bold0 = up0.bold[0]; up.Nout = up0.Nout;
   const long long rowb = io.pitch * 16;
@@ -259,27 +260,27 @@ template <class C, int TK, int NG> static void run_fused_tma(FusedIO<double> io0
   TensorMap tmC = emu_map(io0.inC, 8, 2LL * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
   TensorMap tmG = emu_map(io0.inG, 8, 2LL * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
   TensorMap tmO = emu_map(up0.nold ? (const void *)up0.Nold[0] : (const void *)io0.inC, 8, 2LL * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
-  size_t smem = (size_t)(NG * 3 * C::N * TK + C::N) * 16 + NG * 3 * 8 + 128;
+  size_t smem = (size_t)(NG * 3 * C::N * TK) * 16 + NG * 3 * 8 + 128;
   emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG>(tmC, tmG, tmO, io, up, tw); }, 64 * 1024);
 }
 
 // P1 (c + i F(c)) and P5 against the naive DFT
 template <class C, int PPB, int NG, int NS> static void test_zfwd_tma(const char *name, int nrows, int grid) {
-  constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1;
+  constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1, ncp = (nc + 7) & ~7;
   std::mt19937_64 rng(13);
   std::uniform_real_distribution<double> U(0, 1);
   std::vector<double> c((size_t)nrows * n), mu((size_t)nrows * n, -7.0);
   for (auto &v : c) v = U(rng);
-  std::vector<cx<double>> oc((size_t)nrows * nc), og((size_t)nrows * nc);
+  std::vector<cx<double>> oc((size_t)nrows * ncp), og((size_t)nrows * ncp);
   auto tw = make_tw(n);
   DoubleWellDeriv<double> f{0.1, 0.0, 1.0};
-  size_t smem = (size_t)NG * NS * PPB * n * 8 + (size_t)(NG * PPB * NP + n) * 16 + NG * NS * 8 + 128;
+  size_t smem = (size_t)NG * NS * PPB * n * 8 + (size_t)(NG * PPB * NP) * 16 + NG * NS * 8 + 128;
   const double *cp = c.data();
   double *mp = mu.data();
   cx<double> *ocp = oc.data(), *ogp = og.data();
   const cx<double> *twp = tw.data();
   emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem,
-              [=] { k_zfwd_tma<double, C, PPB, NG, NS, DoubleWellDeriv<double>>(cp, mp, ocp, ogp, nrows, f, twp); }, 64 * 1024);
+              [=] { k_zfwd_tma<double, C, PPB, NG, NS, DoubleWellDeriv<double>>(cp, mp, ocp, ogp, nrows, ncp, f, twp); }, 64 * 1024);
   double err = 0;
   for (int r = 0; r < nrows; ++r) {
     std::vector<lc> x(n), g(n);
@@ -291,7 +292,7 @@ template <class C, int PPB, int NG, int NS> static void test_zfwd_tma(const char
     }
     auto yx = dft(x, -1), yg = dft(g, -1);
     for (int k = 0; k < nc; ++k) {
-      auto a = oc[(size_t)r * nc + k], b = og[(size_t)r * nc + k];
+      auto a = oc[(size_t)r * ncp + k], b = og[(size_t)r * ncp + k];
       err = std::max(err, (double)std::abs(lc(a.x, a.y) - yx[k]));
       err = std::max(err, (double)std::abs(lc(b.x, b.y) - yg[k]));
     }
@@ -300,29 +301,104 @@ template <class C, int PPB, int NG, int NS> static void test_zfwd_tma(const char
 }
 
 template <class C, int PPB, int NG, int NS> static void test_zinv_tma(const char *name, int nrows, int grid) {
-  constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1;
+  constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1, ncp = (nc + 7) & ~7, ncmax = (nc + 15) & ~15;
   std::mt19937_64 rng(17);
   std::uniform_real_distribution<double> U(-1, 1);
   std::vector<double> a((size_t)nrows * n), back((size_t)nrows * n);
   for (auto &v : a) v = U(rng);
-  std::vector<cx<double>> spec((size_t)nrows * nc);
+  std::vector<cx<double>> spec((size_t)nrows * ncp);
   for (int r = 0; r < nrows; ++r) {
     std::vector<lc> x(n);
     for (int j = 0; j < n; ++j) x[j] = a[(size_t)r * n + j];
     auto y = dft(x, -1);
-    for (int k = 0; k < nc; ++k) spec[(size_t)r * nc + k] = mk<double>((double)y[k].real(), (double)y[k].imag());
-    spec[(size_t)r * nc].y = 0.37;  // must be ignored
-    spec[(size_t)r * nc + n / 2].y = -0.21;
+    for (int k = 0; k < nc; ++k) spec[(size_t)r * ncp + k] = mk<double>((double)y[k].real(), (double)y[k].imag());
+    spec[(size_t)r * ncp].y = 0.37;  // must be ignored
+    spec[(size_t)r * ncp + n / 2].y = -0.21;
   }
   auto tw = make_tw(n);
-  size_t smem = (size_t)(NG * NS * 2 * PPB * nc + NG * PPB * NP + n) * 16 + NG * NS * 8 + 128;
+  size_t smem = (size_t)(NG * NS * 2 * PPB * ncmax + NG * PPB * NP) * 16 + NG * NS * 8 + 128;
   const cx<double> *sp = spec.data(), *twp = tw.data();
   double *bp = back.data();
-  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem, [=] { k_zinv_tma<double, C, PPB, NG, NS>(sp, bp, nrows, 1.0 / n, twp); },
+  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem, [=] { k_zinv_tma<double, C, PPB, NG, NS>(sp, ncp, bp, nrows, 1.0 / n, twp); },
               64 * 1024);
   double err = 0;
   for (size_t i = 0; i < a.size(); ++i) err = std::max(err, std::fabs(a[i] - back[i]));
   report(name, err, 1e-12 * n);
+}
+
+// fused pass in the multi-GPU slab layout: data staged as [P][nxl][nyl][nzc], transform along y
+template <class C, int TK, int NG> static void test_fused_slab(const char *name, int P, int nxl, int nzc, int x0, int grid) {
+  constexpr int ny = C::N;
+  const int nyl = ny / P;
+  std::mt19937_64 rng(23);
+  std::uniform_real_distribution<double> U(-1, 1);
+  const size_t total = (size_t)nxl * ny * nzc;
+  // logical [x][y][kz] arrays and their staged copies
+  std::vector<cx<double>> Cl(total), Gl(total), Ol(total), Cs(total), Gs(total), Os(total), Us(total), Ns(total);
+  for (auto &v : Cl) v = mk<double>(U(rng), U(rng));
+  for (auto &v : Gl) v = mk<double>(U(rng), U(rng));
+  for (auto &v : Ol) v = mk<double>(U(rng), U(rng));
+  auto sidx = [&](int x, int y, int kz) { return (((size_t)(y / nyl) * nxl + x) * nyl + (y % nyl)) * nzc + kz; };
+  for (int x = 0; x < nxl; ++x)
+    for (int y = 0; y < ny; ++y)
+      for (int kz = 0; kz < nzc; ++kz) {
+        size_t l = ((size_t)x * ny + y) * nzc + kz;
+        Cs[sidx(x, y, kz)] = Cl[l]; Gs[sidx(x, y, kz)] = Gl[l]; Os[sidx(x, y, kz)] = Ol[l];
+      }
+  std::vector<double> kx(x0 + nxl + 3), ky(ny), kz(nzc);
+  for (auto &v : kx) v = U(rng);
+  for (auto &v : ky) v = U(rng);
+  for (auto &v : kz) v = U(rng);
+  auto tw = make_tw(ny);
+  FusedTmaIO<double> io;
+  io.outU = Us.data(); io.n = ny; io.ncols = nzc; io.ncb = (nzc + TK - 1) / TK; io.pitch = nzc; io.scale = 1.0 / ny;
+  io.slab = 1; io.nouter = nxl; io.nyl = nyl;
+  SpectralUpdate2<double> up{};
+  up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = MRL_KMODE_3D_SLAB; up.nzc = nzc; up.nzv = nzc; up.x0 = x0;
+  up.closed_M = 1; up.closed_L = 1; up.has_L = 1; up.Mfac = 0.2; up.Lfac = -0.001; up.dt = 0.01;
+  up.b0 = 1.5 * up.dt; up.nold = 1; up.bold0 = -0.5 * up.dt; up.Nout = Ns.data();
+  auto mk4 = [&](const void *base) {
+    TensorMap m;
+    m.base = (const unsigned char *)base; m.esize = 8;
+    m.dim[0] = 2LL * nzc; m.dim[1] = nyl; m.dim[2] = nxl; m.dim[3] = P;
+    m.stride[0] = 8; m.stride[1] = 16LL * nzc; m.stride[2] = 16LL * nzc * nyl; m.stride[3] = 16LL * nzc * nyl * nxl;
+    m.box[0] = 2 * TK; m.box[1] = nyl; m.box[2] = 1; m.box[3] = P;
+    return m;
+  };
+  TensorMap tmC = mk4(Cs.data()), tmG = mk4(Gs.data()), tmO = mk4(Os.data());
+  const cx<double> *twp = tw.data();
+  size_t smem = (size_t)(NG * 3 * C::N * TK) * 16 + NG * 3 * 8 + 128;
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG>(tmC, tmG, tmO, io, up, twp); }, 64 * 1024);
+  double err = 0, errN = 0;
+  for (int x = 0; x < nxl; ++x)
+    for (int q = 0; q < nzc; ++q) {
+      std::vector<lc> xc(ny), xg(ny);
+      for (int y = 0; y < ny; ++y) {
+        auto a = Cl[((size_t)x * ny + y) * nzc + q], b = Gl[((size_t)x * ny + y) * nzc + q];
+        xc[y] = lc(a.x, a.y); xg[y] = lc(b.x, b.y);
+      }
+      auto yc = dft(xc, -1), yg = dft(xg, -1);
+      std::vector<lc> u(ny);
+      for (int y = 0; y < ny; ++y) {
+        long double a = kx[x0 + x], b = ky[y], d = kz[q];
+        long double kk = a * a + b * b + d * d;
+        lc N = (-kk * 0.2L) * yg[y];
+        auto no = Ol[((size_t)x * ny + y) * nzc + q];
+        u[y] = (yc[y] + (long double)up.b0 * N + (long double)up.bold0 * lc(no.x, no.y)) / (1.0L - (long double)up.dt * (kk * kk * -0.001L));
+        auto nn = Ns[sidx(x, y, q)];
+        errN = std::max(errN, (double)std::abs(lc(nn.x, nn.y) - N));
+      }
+      auto r = dft(u, +1);
+      for (int y = 0; y < ny; ++y) {
+        auto v = Us[sidx(x, y, q)];
+        err = std::max(err, (double)std::abs(lc(v.x, v.y) - r[y] / (long double)ny));
+      }
+    }
+  char nm[128];
+  snprintf(nm, sizeof nm, "%s u", name);
+  report(nm, err, 1e-12 * ny);
+  snprintf(nm, sizeof nm, "%s N", name);
+  report(nm, errN, 1e-12 * ny);
 }
 
 static void tma_tests() {
@@ -337,8 +413,12 @@ static void tma_tests() {
     up.nold = 0;
     run_fused_tma<FFTCfg<64, 8, 8, 8>, 4, 2>(io, up, tw, 1);
   }, 0);
-  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 2, 3, 2>("zfwd tma 64 PPB2 NG3 NS2 rows=11", 11, 2);
-  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 1, 4, 3>("zfwd tma 64 PPB1 NG4 NS3 rows=30", 30, 1);
+  test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 nxl3 nzc5", 4, 3, 5, 2, 2);
+  test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 1>("fused tma slab 64 P2 nxl2 nzc9", 2, 2, 9, 0, 1);
+  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 3, 2>("zfwd tma 64 PPB4 NG3 NS2 rows=21", 21, 2);
+  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("zfwd tma 64 PPB8 NG2 NS3 rows=50", 50, 1);
+  test_zfwd_tma<FFTCfg<512, 64, 8, 8, 8>, 1, 2, 2>("zfwd tma 512 PPB1 NG2 NS2 rows=5 (pair_map)", 5, 1);
+  test_zfwd_tma<FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 1, 2>("zfwd tma 1024 PPB1 NG1 NS2 rows=2 (pair_map)", 2, 1);
   test_zfwd_tma<FFTCfg<128, 16, 8, 4, 4>, 4, 2, 2>("zfwd tma 128 PPB4 NG2 NS2 rows=9", 9, 2);
   test_zinv_tma<FFTCfg<64, 8, 8, 8>, 2, 2, 2>("zinv tma 64 PPB2 NG2 NS2 rows=7", 7, 1);
   test_zinv_tma<FFTCfg<64, 8, 8, 8>, 1, 4, 3>("zinv tma 64 PPB1 NG4 NS3 rows=40", 40, 2);

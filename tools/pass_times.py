@@ -16,14 +16,15 @@ from marlin_b200.capi import AB_BETA  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    dims = tuple(int(v) for v in os.environ["PT_DIMS"].split(",")) if "PT_DIMS" in os.environ else (n, n, n)
     prec = capi.F32 if (len(sys.argv) > 2 and sys.argv[2] == "f32") else capi.F64
     reps = 10
     L = n * 8 * math.pi / 200
     ctx = capi.Context(0, prec)
     ctx.use_torch_stream()
-    ctx.domain_set(3, (n, n, n), (0,) * 3, (L,) * 3)
+    ctx.domain_set(3, dims, (0,) * 3, tuple(L * d / n for d in dims))
     torch.manual_seed(0)
-    c = (torch.rand((n, n, n), dtype=torch.float64) * 0.12 + 0.44).to(ctx.rdtype).cuda()
+    c = (torch.rand(dims, dtype=torch.float64) * 0.12 + 0.44).to(ctx.rdtype).cuda()
     plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
     dt = 1e-3
     plan.substep(c, dt, AB_BETA[0], 0)
@@ -47,7 +48,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     env = {k: v for k, v in os.environ.items() if k.startswith("MRL_")}
-    print(json.dumps({"n": n, "env": env, "pass_ms": [round(x, 4) for x in ms], "sum_ms": round(sum(ms), 4),
+    print(json.dumps({"n": dims, "env": env, "pass_ms": [round(x, 4) for x in ms], "sum_ms": round(sum(ms), 4),
                       "step_ms": round(e0.elapsed_time(e1) / 20, 4), "checksum": chk}), flush=True)
 
 
