@@ -144,6 +144,54 @@ int mrl_split_substep_timed(mrl_split_plan *plan, void *c_real_dev, double dt, c
 /* HBM passes / kernels one substep launches (for bench bookkeeping) */
 int mrl_split_launches_per_substep(const mrl_split_plan *plan);
 
+/* ---- multi-GPU slab decomposition -------------------------------------------------------
+ * DomainAction::partitionSlabs / partitionHepler (src/actions/DomainAction.C:511-566,
+ * include/actions/DomainAction.h:249-280) and fftSlab / ifftSlab (:870-1019): real space is
+ * split along y, reciprocal space along x, z is never split.  One context per rank (= per GPU).
+ * Differences from the reference, stated here because they are visible at the boundary:
+ *   - the half spectrum (r2c on z) travels, not the reference's full c2c spectrum: same
+ *     results, half the bytes, and the local reciprocal block is an x-slice of the serial layout;
+ *   - the exchange itself is done by the host between the three phases below (NCCL all-to-all
+ *     through torch.distributed in this repository, MPI_Alltoall in Marlin): chunks are
+ *     contiguous in both directions, so no pack / unpack pass exists;
+ *   - the fused path needs nx % nranks == 0 and ny % nranks == 0 (equal slabs).            */
+/* partitionHepler: weighted split of `total` layers over nranks (weights NULL = equal). Host only. */
+int mrl_partition(int64_t total, int nranks, const double *weights, int64_t *count);
+int mrl_domain_set_slab(mrl_context *ctx, int dim, const int64_t *n, const double *min, const double *max, int rank,
+                        int nranks);
+/* local shapes and first global index: real [nx][ny/P][nz], reciprocal [nx/P][ny][nz/2+1] */
+int mrl_domain_local(const mrl_context *ctx, int64_t *real_shape, int64_t *real_begin, int64_t *recip_shape,
+                     int64_t *recip_begin);
+
+typedef struct mrl_slab_plan mrl_slab_plan;
+/* Element counts (complex elements) of the exchange buffers the caller must allocate:
+ *   send_fwd : 2*field   two fields back to back, each [nx][ny/P][pitch]; rank s's chunk of field f
+ *                        starts at f*field + s*chunk
+ *   recv_fwd : 2*field   each [P][nx/P][ny/P][pitch] (chunk s = what rank s sent)
+ *   send_bwd : field     same staged layout; chunk s goes back to rank s
+ *   (the return exchange lands in field 0 of send_fwd)                                    */
+int mrl_slab_sizes(const mrl_context *ctx, int64_t *field_elems, int64_t *chunk_elems, int *pitch);
+int mrl_slab_plan_create(mrl_context *ctx, const mrl_split_desc *desc, void *send_fwd_dev, void *recv_fwd_dev,
+                         void *send_bwd_dev, mrl_slab_plan **out);
+/* Peer mode - the all-to-all fused into the passes: buffers are owned by the library and shared
+ * through CUDA IPC; phase 1's x pass stores every result row straight into the HBM of the rank
+ * that owns its x block, phase 2's fused pass stores rows straight into the owners' y slabs
+ * (plain stores to NVLink-mapped peer memory, overlapped with the pass's own HBM traffic), so
+ * no exchange call, no staging copy and no pack/unpack exist.  Protocol per substep:
+ *   mrl_slab_forward -> cross-rank barrier -> mrl_slab_update -> cross-rank barrier -> mrl_slab_inverse
+ * handles: 2 x 64 bytes per rank (cudaIpcMemHandle_t of send_fwd, recv_fwd).               */
+int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc *desc, mrl_slab_plan **out);
+int mrl_slab_ipc_export(mrl_slab_plan *plan, void *handles_128_bytes);
+int mrl_slab_ipc_import(mrl_slab_plan *plan, const void *all_handles /* nranks x 128 bytes, rank order */);
+int mrl_slab_plan_destroy(mrl_slab_plan *plan);
+/* phase 1: z r2c of (c + i F(c)) and x forward on the local slab -> send_fwd                */
+int mrl_slab_forward(mrl_slab_plan *plan, const void *c_real_dev);
+/* phase 2 (after the forward exchange): y forward, semi-implicit update, y inverse -> send_bwd */
+int mrl_slab_update(mrl_slab_plan *plan, double dt, const double *beta, int nold);
+/* phase 3 (after the return exchange into field 0 of send_fwd): x inverse, z c2r -> c        */
+int mrl_slab_inverse(mrl_slab_plan *plan, void *c_real_dev);
+int mrl_slab_advance_state(mrl_slab_plan *plan, int *stored);
+
 #ifdef __cplusplus
 }
 #endif

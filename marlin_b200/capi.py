@@ -240,3 +240,11 @@ class SplitPlan:
             self.close()
         except Exception:
             pass
+
+
+def partition(total, nranks, weights=None):
+    """DomainAction::partitionHepler (include/actions/DomainAction.h:249-280). Host only."""
+    cnt = (C.c_int64 * nranks)()
+    w = (C.c_double * nranks)(*[float(x) for x in weights]) if weights is not None else None
+    _ck(lib().mrl_partition(C.c_int64(total), int(nranks), w, cnt))
+    return list(cnt)

@@ -102,6 +102,10 @@ static cudaError_t strided_tma_go(const LaunchCtx &lc, const StridedIO<T> &io0, 
   io.ncols = io0.ncols;
   io.nouter = io0.nouter * io0.nfields;
   io.nvalid = io0.nvalid ? io0.nvalid : io0.ncols;
+  io.peer_tab = io0.peer_tab;
+  io.peer_rows = io0.peer_rows;
+  io.peer_field = io0.peer_field;
+  io.peer_off = io0.peer_off;
   io.pitch = io0.out_pitch ? io0.out_pitch : io0.pitch;
   io.outer_stride = io0.out_pitch ? io0.out_outer_stride : slice;
   io.ncb = (io.ncols + TK - 1) / TK;
@@ -168,6 +172,8 @@ static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, cons
   io.slab = io0.slab;
   io.nouter = io0.slab ? io0.nouter : 1;
   io.nyl = io0.nyl;
+  io.peer_tab = io0.slab ? io0.peer_tab : nullptr;
+  io.peer_x0 = io0.peer_x0;
   SpectralUpdate2<T> up;
   memset(&up, 0, sizeof up);
   up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz;

@@ -676,3 +676,329 @@ extern "C" int mrl_split_substep_timed(mrl_split_plan *p, void *c, double dt, co
   for (int i = 0; i <= np; ++i) cudaEventDestroy(ev[i]);
   return rc;
 }
+
+// ------------------------------------------------------------------------------ slab decomposition
+extern "C" int mrl_partition(int64_t total, int nranks, const double *weights, int64_t *count) {
+  // partitionHepler, include/actions/DomainAction.h:249-280 (integer weights in the reference;
+  // the arithmetic below is the same for integral values)
+  if (total < 1 || nranks < 1 || !count) return mrl_fail(MRL_ERR_INVALID, "mrl_partition: bad arguments");
+  long long remaining_w = 0;
+  std::vector<long long> w(nranks, 1);
+  for (int r = 0; r < nranks; ++r) {
+    if (weights) w[r] = (long long)weights[r];
+    remaining_w += w[r];
+  }
+  long long left = total;
+  for (int r = 0; r < nranks; ++r) {
+    if (remaining_w == 0) return mrl_fail(MRL_ERR_INVALID, "Internal partitioning error. remaining_total_weight 0 == 0");
+    long long n = (left * w[r]) / remaining_w;
+    if (n < 1) n = 1;  // assign at least one layer
+    count[r] = n;
+    remaining_w -= w[r];
+    if (left < n) return mrl_fail(MRL_ERR_INVALID, "Internal partitioning error.");
+    left -= n;
+  }
+  count[nranks - 1] += left;  // remainder to the last slice
+  return MRL_OK;
+}
+
+extern "C" int mrl_domain_set_slab(mrl_context *ctx, int dim, const int64_t *n, const double *mn, const double *mx, int rank,
+                                   int nranks) {
+  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return mrl_fail(MRL_ERR_INVALID, "mrl_domain_set_slab: bad arguments");
+  if (dim != 3) return mrl_fail(MRL_ERR_UNSUPPORTED, "slab decomposition is implemented for dim = 3");
+  int rc = mrl_domain_set(ctx, dim, n, mn, mx);
+  if (rc) return rc;
+  if (n[0] % nranks || n[1] % nranks)
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "slab decomposition needs nx and ny divisible by the number of ranks (%lld, %lld, %d)",
+                    (long long)n[0], (long long)n[1], nranks);
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->nyl = (int)(n[1] / nranks);
+  ctx->nxl = (int)(n[0] / nranks);
+  ctx->y0 = rank * ctx->nyl;
+  ctx->x0 = rank * ctx->nxl;
+  return MRL_OK;
+}
+
+extern "C" int mrl_domain_local(const mrl_context *ctx, int64_t *rs, int64_t *rb, int64_t *ks, int64_t *kb) {
+  if (!ctx || !ctx->dim) return mrl_fail(MRL_ERR_INVALID, "domain not set");
+  const bool slab = ctx->nranks > 1 || ctx->nyl;
+  for (int d = 0; d < 3; ++d) {
+    if (rs) rs[d] = (slab && d == 1) ? ctx->nyl : ctx->n[d];
+    if (rb) rb[d] = (slab && d == 1) ? ctx->y0 : 0;
+    if (ks) ks[d] = (slab && d == 0) ? ctx->nxl : ctx->nr[d];
+    if (kb) kb[d] = (slab && d == 0) ? ctx->x0 : 0;
+  }
+  return MRL_OK;
+}
+
+static int slab_pitch(const mrl_context *ctx) {
+  const int per128 = ctx->precision == MRL_F64 ? 8 : 16;
+  return (ctx->nr[2] + per128 - 1) / per128 * per128;
+}
+
+extern "C" int mrl_slab_sizes(const mrl_context *ctx, int64_t *field, int64_t *chunk, int *pitch) {
+  if (!ctx || ctx->dim != 3 || !ctx->nyl) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_sizes: slab domain not set");
+  const int ncp = slab_pitch(ctx);
+  if (field) *field = (int64_t)ctx->n[0] * ctx->nyl * ncp;
+  if (chunk) *chunk = (int64_t)ctx->nxl * ctx->nyl * ncp;
+  if (pitch) *pitch = ncp;
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_plan_create(mrl_context *ctx, const mrl_split_desc *d, void *send_fwd, void *recv_fwd, void *send_bwd,
+                                    mrl_slab_plan **out) {
+  if (!ctx || !d || !send_fwd || !recv_fwd || !send_bwd || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create: bad arguments");
+  if (ctx->dim != 3 || !ctx->nyl) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create: slab domain not set");
+  if (d->nonlin_kind != MRL_NONLIN_DOUBLE_WELL) return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: built-in nonlinearity only");
+  if (!d->M_closed_form || (d->has_L && !d->L_closed_form))
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: closed-form k-space factors only");
+  if (!tma_enabled() || !tma_size(ctx->n[0]) || !tma_size(ctx->n[1]) || !tma_size(ctx->n[2]) || ctx->nyl > 256)
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: every axis must be 128, 256, 512 or 1024 points (ny/P <= 256)");
+  if (d->history < 0 || d->history > 4) return mrl_fail(MRL_ERR_INVALID, "history must be in [0,4]");
+  CK(cudaSetDevice(ctx->device));
+  mrl_slab_plan *p = new mrl_slab_plan();
+  p->ctx = ctx;
+  p->desc = *d;
+  p->send_fwd = send_fwd;
+  p->recv_fwd = recv_fwd;
+  p->send_bwd = send_bwd;
+  p->ncp = slab_pitch(ctx);
+  p->field = (long long)ctx->n[0] * ctx->nyl * p->ncp;
+  p->chunk = (long long)ctx->nxl * ctx->nyl * p->ncp;
+  const size_t esz = ctx->precision == MRL_F64 ? 16 : 8;
+  cudaError_t e = cudaMemsetAsync(send_fwd, 0, 2 * p->field * esz, ctx->stream);  // padding columns stay zero
+  if (e == cudaSuccess) e = cudaMemsetAsync(recv_fwd, 0, 2 * p->field * esz, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(send_bwd, 0, p->field * esz, ctx->stream);
+  for (int i = 0; e == cudaSuccess && d->history > 0 && i < d->history + 1; ++i) {
+    void *q = nullptr;
+    e = cudaMalloc(&q, p->field * esz);
+    if (e == cudaSuccess) e = cudaMemsetAsync(q, 0, p->field * esz, ctx->stream);
+    if (e == cudaSuccess) p->ring.push_back(q);
+  }
+  if (e != cudaSuccess) {
+    mrl_slab_plan_destroy(p);
+    return mrl_fail(MRL_ERR_CUDA, "slab plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_plan_destroy(mrl_slab_plan *p) {
+  if (!p) return MRL_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (void *q : p->ring) cudaFree(q);
+  for (void *q : p->opened) cudaIpcCloseMemHandle(q);
+  cudaFree(p->peer_recv_tab);
+  cudaFree(p->peer_send_tab);
+  if (p->owns) {
+    cudaFree(p->send_fwd);
+    cudaFree(p->recv_fwd);
+  }
+  delete p;
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc *d, mrl_slab_plan **out) {
+  if (!ctx || !d || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create_peer: bad arguments");
+  if (ctx->dim != 3 || !ctx->nyl) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create_peer: slab domain not set");
+  CK(cudaSetDevice(ctx->device));
+  const size_t esz = ctx->precision == MRL_F64 ? 16 : 8;
+  const size_t fbytes = (size_t)ctx->n[0] * ctx->nyl * slab_pitch(ctx) * esz;
+  void *sf = nullptr, *rf = nullptr;
+  CK(cudaMalloc(&sf, 2 * fbytes));
+  cudaError_t e = cudaMalloc(&rf, 2 * fbytes);
+  if (e != cudaSuccess) {
+    cudaFree(sf);
+    return mrl_fail(MRL_ERR_CUDA, "slab plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  // send_bwd is not used in peer mode: pass recv_fwd as a placeholder for the argument check
+  int rc = mrl_slab_plan_create(ctx, d, sf, rf, rf, out);
+  if (rc) {
+    cudaFree(sf);
+    cudaFree(rf);
+    return rc;
+  }
+  (*out)->owns = true;
+  (*out)->send_bwd = nullptr;
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_ipc_export(mrl_slab_plan *p, void *handles) {
+  if (!p || !handles || !p->owns) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_ipc_export: needs a peer-mode plan");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CK(cudaSetDevice(p->ctx->device));
+  cudaIpcMemHandle_t h[2];
+  CK(cudaIpcGetMemHandle(&h[0], p->send_fwd));
+  CK(cudaIpcGetMemHandle(&h[1], p->recv_fwd));
+  memcpy(handles, h, sizeof h);
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_ipc_import(mrl_slab_plan *p, const void *all) {
+  if (!p || !all || !p->owns) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_ipc_import: needs a peer-mode plan");
+  mrl_context *ctx = p->ctx;
+  CK(cudaSetDevice(ctx->device));
+  const int P = ctx->nranks;
+  std::vector<unsigned long long> sendp(P), recvp(P);
+  const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all;
+  for (int s = 0; s < P; ++s) {
+    if (s == ctx->rank) {
+      sendp[s] = (unsigned long long)p->send_fwd;
+      recvp[s] = (unsigned long long)p->recv_fwd;
+      continue;
+    }
+    void *a = nullptr, *b = nullptr;
+    CK(cudaIpcOpenMemHandle(&a, h[2 * s], cudaIpcMemLazyEnablePeerAccess));
+    p->opened.push_back(a);
+    CK(cudaIpcOpenMemHandle(&b, h[2 * s + 1], cudaIpcMemLazyEnablePeerAccess));
+    p->opened.push_back(b);
+    sendp[s] = (unsigned long long)a;
+    recvp[s] = (unsigned long long)b;
+  }
+  CK(cudaMalloc(&p->peer_send_tab, P * sizeof(unsigned long long)));
+  CK(cudaMalloc(&p->peer_recv_tab, P * sizeof(unsigned long long)));
+  CK(cudaMemcpy(p->peer_send_tab, sendp.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->peer_recv_tab, recvp.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  p->peer = true;
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_advance_state(mrl_slab_plan *p, int *stored) {
+  if (!p) return mrl_fail(MRL_ERR_INVALID, "null plan");
+  const int H = p->desc.history;
+  if (H > 0) {
+    if (p->stored < H) p->stored++;
+    p->cur = (p->cur + 1) % (H + 1);
+  }
+  if (stored) *stored = p->stored;
+  return MRL_OK;
+}
+
+// x pass (axis 0) on the local [nx][nyl][ncp] slabs of send_fwd
+template <class T> static int slab_xpass(mrl_slab_plan *p, int nfields, int inverse) {
+  mrl_context *ctx = p->ctx;
+  cx<T> *A = (cx<T> *)p->send_fwd;
+  StridedIO<T> sio;
+  memset(&sio, 0, sizeof sio);
+  if (p->peer && !inverse) {  // forward x pass: scatter the rows to the ranks that own them
+    sio.peer_tab = (const unsigned long long *)p->peer_recv_tab;
+    sio.peer_rows = ctx->nxl;
+    sio.peer_field = p->field;
+    sio.peer_off = (long long)ctx->rank * p->chunk;
+  }
+  for (int f = 0; f < nfields; ++f) sio.in[f] = sio.out[f] = A + f * p->field;
+  sio.nfields = nfields;
+  sio.n = ctx->n[0];
+  sio.ncols = ctx->nyl * p->ncp;
+  sio.nouter = 1;
+  sio.pitch = sio.ncols;
+  sio.outer_stride = (long long)sio.n * sio.pitch;
+  sio.scale = T(1);
+  sio.inverse = inverse;
+  const void *tw;
+  int rc = ctx->twiddles(sio.n, &tw);
+  if (rc) return rc;
+  ctx->launches++;
+  CK(launch_strided_tma<T>(ctx->lc(), sio, (const cx<T> *)tw, sio.n));
+  return MRL_OK;
+}
+
+template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
+  mrl_context *ctx = p->ctx;
+  const mrl_split_desc &d = p->desc;
+  const int nl = ctx->n[2];
+  cx<T> *A = (cx<T> *)p->send_fwd;
+  const void *twl;
+  int rc = ctx->twiddles(nl, &twl);
+  if (rc) return rc;
+  NonlinDesc nlz{0, {d.nonlin_params[0], d.nonlin_params[1], d.nonlin_params[2], 0}};
+  ctx->launches++;
+  CK(launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ctx->nyl, nl, p->ncp, nlz,
+                               (const cx<T> *)twl));
+  return slab_xpass<T>(p, 2, 0);
+}
+
+template <class T> static int slab_update_impl(mrl_slab_plan *p, double dt, const double *beta, int nold) {
+  mrl_context *ctx = p->ctx;
+  const mrl_split_desc &d = p->desc;
+  cx<T> *S = (cx<T> *)p->recv_fwd;
+  FusedIO<T> io;
+  memset(&io, 0, sizeof io);
+  io.inC = S;
+  io.inG = S + p->field;
+  io.outU = (cx<T> *)p->send_bwd;
+  io.n = ctx->n[1];
+  io.ncols = p->ncp;
+  io.nouter = ctx->nxl;
+  io.pitch = p->ncp;
+  io.scale = T(1);
+  io.slab = 1;
+  io.nyl = ctx->nyl;
+  io.nranks = ctx->nranks;
+  if (p->peer) {  // rows of the updated field go straight back into the owners' y slabs
+    io.peer_tab = (const unsigned long long *)p->peer_send_tab;
+    io.peer_x0 = ctx->x0;
+  }
+  SpectralUpdate<T> up;
+  memset(&up, 0, sizeof up);
+  up.kx = (const T *)ctx->kaxis_dev[0];
+  up.ky = (const T *)ctx->kaxis_dev[1];
+  up.kz = (const T *)ctx->kaxis_dev[2];
+  up.kmode = MRL_KMODE_3D_SLAB;
+  up.nzc = p->ncp;
+  up.nzv = ctx->nr[2];
+  up.x0 = ctx->x0;
+  up.closed_M = 1;
+  up.Mfac = (T)d.M_factor;
+  up.has_L = d.has_L;
+  up.closed_L = 1;
+  up.Lfac = (T)d.L_factor;
+  up.dt = (T)dt;
+  up.b0 = (T)(dt * beta[0]);
+  up.nold = nold;
+  const int H = d.history;
+  for (int i = 0; i < nold; ++i) {
+    up.bold[i] = (T)(dt * beta[i + 1]);
+    up.Nold[i] = (const cx<T> *)p->ring[((p->cur - 1 - i) % (H + 1) + (H + 1)) % (H + 1)];
+  }
+  up.Nout = H > 0 ? (cx<T> *)p->ring[p->cur] : nullptr;
+  const void *tw;
+  int rc = ctx->twiddles(io.n, &tw);
+  if (rc) return rc;
+  ctx->launches++;
+  CK(launch_fused_tma<T>(ctx->lc(), io, up, (const cx<T> *)tw, io.n));
+  return MRL_OK;
+}
+
+template <class T> static int slab_inverse_impl(mrl_slab_plan *p, T *c) {
+  mrl_context *ctx = p->ctx;
+  int rc = slab_xpass<T>(p, 1, 1);
+  if (rc) return rc;
+  const int nl = ctx->n[2];
+  const void *twl;
+  if ((rc = ctx->twiddles(nl, &twl))) return rc;
+  const double N = (double)ctx->n[0] * ctx->n[1] * ctx->n[2];
+  ctx->launches++;
+  CK(launch_zinv_pairs_tma<T>(ctx->lc(), (const cx<T> *)p->send_fwd, p->ncp, c, (long long)ctx->n[0] * ctx->nyl, nl, (T)(1.0 / N),
+                              (const cx<T> *)twl));
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_forward(mrl_slab_plan *p, const void *c) {
+  if (!p || !c) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_forward: bad arguments");
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? slab_forward_impl<double>(p, (const double *)c) : slab_forward_impl<float>(p, (const float *)c);
+}
+extern "C" int mrl_slab_update(mrl_slab_plan *p, double dt, const double *beta, int nold) {
+  if (!p || !beta || nold < 0) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_update: bad arguments");
+  if (nold > p->stored) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_update: %d old states requested, %d stored", nold, p->stored);
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? slab_update_impl<double>(p, dt, beta, nold) : slab_update_impl<float>(p, dt, beta, nold);
+}
+extern "C" int mrl_slab_inverse(mrl_slab_plan *p, void *c) {
+  if (!p || !c) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_inverse: bad arguments");
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? slab_inverse_impl<double>(p, (double *)c) : slab_inverse_impl<float>(p, (float *)c);
+}

@@ -25,6 +25,9 @@ struct mrl_context {
   std::vector<double> axis_h[3], kaxis_h[3];
   void *axis_dev[3] = {nullptr, nullptr, nullptr};
   void *kaxis_dev[3] = {nullptr, nullptr, nullptr};
+  // slab decomposition (nranks == 1: serial)
+  int rank = 0, nranks = 1;
+  int nyl = 0, nxl = 0, y0 = 0, x0 = 0;  // local extents / first global index (y real, x reciprocal)
   // caches
   std::map<int, void *> tw;
   void *scratch_ptr = nullptr;
@@ -46,6 +49,21 @@ struct mrl_split_plan {
   std::vector<void *> ring;         // history+1 nonlinear-term slots
   int cur = 0, stored = 0;
   int ncp = 0;                      // row pitch of the work spectra (>= n_last/2+1)
+};
+
+struct mrl_slab_plan {
+  mrl_context *ctx = nullptr;
+  mrl_split_desc desc;
+  void *send_fwd = nullptr, *recv_fwd = nullptr, *send_bwd = nullptr;  // caller-owned
+  std::vector<void *> ring;  // history+1 nonlinear-term slots, staged layout
+  int cur = 0, stored = 0;
+  int ncp = 0;
+  long long field = 0, chunk = 0;
+  // peer mode
+  bool owns = false, peer = false;
+  std::vector<void *> opened;          // pointers from cudaIpcOpenMemHandle
+  void *peer_recv_tab = nullptr;       // device arrays of nranks base pointers
+  void *peer_send_tab = nullptr;
 };
 
 namespace mrl {

@@ -31,6 +31,12 @@ template <class T> struct StridedIO {
   // optional separate output layout (TMA kernel only; 0 = same as the input layout)
   long long out_pitch, out_outer_stride;
   int nvalid;  // TMA kernel only: columns >= nvalid are padding (0 = all ncols valid)
+  // TMA kernel only, multi-GPU slab: rows of the result are scattered straight into the peers'
+  // receive staging (peer_tab[s] = base of rank s's buffer, device array of nranks pointers):
+  // row r of field f goes to peer r / peer_rows at  f*peer_field + peer_off + (r % peer_rows)*pitch
+  const unsigned long long *peer_tab;
+  int peer_rows;
+  long long peer_field, peer_off;
 
   MRL_HD int ntiles() const { return nfields * nouter * ncb; }
 };
@@ -385,6 +391,10 @@ template <class T> struct FusedIO {
   T scale;
   // multi-GPU slab layout (TMA kernel only): data staged as [nranks][nouter][nyl][ncols]
   int slab, nyl, nranks;
+  // slab + peer stores: row y of the result goes to rank y / nyl, into its [nx][nyl][ncols]
+  // array at x = peer_x0 + o (peer_tab: device array of nranks base pointers; null = staged store)
+  const unsigned long long *peer_tab;
+  int peer_x0;
 };
 
 template <class T, class C, int TK>

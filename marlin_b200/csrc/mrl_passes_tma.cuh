@@ -62,6 +62,9 @@ template <class T> struct StridedTmaIO {
   int nouter_f;          // outer slices per field
   int n, ncols, nouter;  // nouter counts (field, outer) slices
   int nvalid;            // columns >= nvalid of a slice are padding: transformed but never stored
+  const unsigned long long *peer_tab;  // multi-GPU: scatter result rows to the peers (see StridedIO)
+  int peer_rows;
+  long long peer_field, peer_off;
   long long pitch, outer_stride;
   int ncb;
   T scale;
@@ -121,7 +124,16 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     fft_or_skip<T, C>(v, t, sm, twr, bar, [&] {
       if (gt == 0 && j + NS < nloc) issue(j + NS);
     });
-    if (ok) {
+    if (ok && io.peer_tab) {
+      // fused all-to-all: each row lands directly in the HBM of the rank that owns its x block
+      MRL_UNROLL
+      for (int e = 0; e < E; ++e) {
+        const int r = t + TP * e, s = r / io.peer_rows;
+        cx<T> *dst = reinterpret_cast<cx<T> *>(io.peer_tab[s]) + (long long)o * io.peer_field + io.peer_off +
+                     (long long)(r - s * io.peer_rows) * io.pitch + c;
+        *dst = mk<T>(v[e].x * io.scale, (io.inverse ? -v[e].y : v[e].y) * io.scale);
+      }
+    } else if (ok) {
       cx<T> *dst = (o < io.nouter_f ? io.out + (long long)o * io.outer_stride
                                     : io.out1 + (long long)(o - io.nouter_f) * io.outer_stride) + c;
       MRL_UNROLL
@@ -146,12 +158,29 @@ template <class T> struct FusedTmaIO {
   long long pitch;
   T scale;
   int slab, nouter, nyl;
+  const unsigned long long *peer_tab;  // slab: store the result rows into the owning ranks' arrays
+  int peer_x0;
   MRL_DI long long row_off(int o, int row) const {
     if (!slab) return (long long)row * pitch;
     const int s = row / nyl, yl = row - s * nyl;
     return (((long long)s * nouter + o) * nyl + yl) * pitch;
   }
 };
+
+// 1/d to within an ulp without the division slow path: hardware seed + two Newton steps.
+// (1 - dt*L >= 1 for the dissipative linear operators this is used with; never 0, Inf or NaN.)
+#if defined(MRL_EMU)
+template <class T> MRL_DI T fast_rcp(T d) { return T(1) / d; }
+#else
+MRL_DI double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  return r;
+}
+MRL_DI float fast_rcp(float d) { return __frcp_rn(d); }
+#endif
 
 template <class T> struct SpectralUpdate2 {
   const T *kx, *ky, *kz;
@@ -166,20 +195,23 @@ template <class T> struct SpectralUpdate2 {
   const cx<T> *Nold1, *Nold2, *Nold3;  // old terms beyond the newest (which arrives through its slot)
   cx<T> *Nout;
 
-  MRL_DI T k2(int o, int j, int col) const {
-    T a, b, c;
+  // k^2 = rowterm(j) + colterm: the part that is fixed for a thread's column during one tile is
+  // evaluated once per tile, the part that follows the transform axis once per element.
+  MRL_DI T colterm(int o, int col) const {
     if (kmode == MRL_KMODE_3D) {
-      a = kx[j]; b = ky[col / nzc]; c = kz[col % nzc];
+      const T b = ky[col / nzc], c = kz[col % nzc];
+      return b * b + c * c;
     } else if (kmode == MRL_KMODE_3D_SLAB) {
-      a = kx[x0 + o]; b = ky[j]; c = kz[col];
-    } else {
-      a = kx[j]; b = ky[col]; c = T(0);
+      const T a = kx[x0 + o], c = kz[col];
+      return a * a + c * c;
     }
-    return a * a + b * b + c * c;
+    const T b = ky[col];
+    return b * b;
   }
+  MRL_DI const T *rowaxis() const { return kmode == MRL_KMODE_3D_SLAB ? ky : kx; }
   // chat, ghat: transformed variable / nonlinearity; nold0: newest old nonlinear term
-  MRL_DI cx<T> apply(int o, int j, int col, long long off, cx<T> chat, cx<T> ghat, cx<T> nold0) const {
-    const T kk = k2(o, j, col);
+  MRL_DI cx<T> apply(T kr, T kcol, long long off, cx<T> chat, cx<T> ghat, cx<T> nold0) const {
+    const T kk = kr * kr + kcol;
     const T M = closed_M ? (-kk * Mfac) : Mbuf[off];
     const cx<T> N = mk<T>(M * ghat.x, M * ghat.y);
     if (Nout) Nout[off] = N;
@@ -190,9 +222,9 @@ template <class T> struct SpectralUpdate2 {
     if (nold > 3) { const cx<T> q = Nold3[off]; u.x += bold3 * q.x; u.y += bold3 * q.y; }
     if (has_L) {
       const T L = closed_L ? (kk * kk * Lfac) : Lbuf[off];
-      const T den = T(1) - dt * L;
-      u.x /= den;
-      u.y /= den;
+      const T r = fast_rcp(T(1) - dt * L);
+      u.x *= r;
+      u.y *= r;
     }
     return u;
   }
@@ -278,18 +310,30 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     // ---- k-space update (newest old nonlinear term from its slot)
     if (use_old) mbar_wait(bO, par);
     const SmTile<T, TK> smo{sO, col};
-    MRL_UNROLL
-    for (int e = 0; e < E; ++e) {
-      const int jj = t + TP * e;
-      const cx<T> no = use_old ? smo.ld(jj) : mk<T>(T(0), T(0));
-      if (ok) a[e] = conj(up.apply(o, jj, c, io.row_off(o, jj) + c, a[e], gh[e], no));
+    if (ok) {
+      const T kcol = up.colterm(o, c);
+      const T *kr = up.rowaxis();
+      MRL_UNROLL
+      for (int e = 0; e < E; ++e) {
+        const int jj = t + TP * e;
+        const cx<T> no = use_old ? smo.ld(jj) : mk<T>(T(0), T(0));
+        a[e] = conj(up.apply(kr[jj], kcol, io.row_off(o, jj) + c, a[e], gh[e], no));
+      }
     }
     bar.sync();  // every thread has taken its old-term values: the O slot becomes the exchange buffer
     // ---- inverse transform of the updated variable (exchange through the O slot)
     fft_or_skip<T, C>(a, t, smo, twr, bar, [&] {
       if (gt == 0 && more && use_old) issue(&tmO, sO, bO, j + 1);
     });
-    if (ok) {
+    if (ok && io.peer_tab) {
+      // fused return all-to-all: row y belongs to rank y / nyl, at x = peer_x0 + o of its slab
+      MRL_UNROLL
+      for (int e = 0; e < E; ++e) {
+        const int y = t + TP * e, s = y / io.nyl;
+        cx<T> *dst = reinterpret_cast<cx<T> *>(io.peer_tab[s]) + ((long long)(io.peer_x0 + o) * io.nyl + (y - s * io.nyl)) * io.pitch + c;
+        *dst = mk<T>(a[e].x * io.scale, -a[e].y * io.scale);
+      }
+    } else if (ok) {
       cx<T> *dst = io.outU + c;
       MRL_UNROLL
       for (int e = 0; e < E; ++e) dst[io.row_off(o, t + TP * e)] = mk<T>(a[e].x * io.scale, -a[e].y * io.scale);

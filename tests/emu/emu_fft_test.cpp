@@ -236,7 +236,7 @@ static TensorMap emu_map(const void *base, int esize, long long d0, long long d1
 
 template <class C, int TK, int NG, int NS> static void run_strided_tma(StridedIO<double> io0, const cx<double> *tw, int grid) {
   StridedTmaIO<double> io;
-  io.out = io0.out[0]; io.out1 = io0.out[0]; io.nouter_f = io0.nouter; io.nvalid = io0.ncols;
+  io.out = io0.out[0]; io.out1 = io0.out[0]; io.nouter_f = io0.nouter; io.nvalid = io0.ncols; io.peer_tab = nullptr; io.peer_rows = 0; io.peer_field = 0; io.peer_off = 0;
   io.n = io0.n; io.ncols = io0.ncols; io.nouter = io0.nouter;
   io.pitch = io0.pitch; io.outer_stride = io0.outer_stride;
   io.ncb = (io0.ncols + TK - 1) / TK;
@@ -250,7 +250,7 @@ template <class C, int TK, int NG, int NS> static void run_strided_tma(StridedIO
 template <class C, int TK, int NG> static void run_fused_tma(FusedIO<double> io0, SpectralUpdate<double> up0, const cx<double> *tw, int grid) {
   FusedTmaIO<double> io;
   io.outU = io0.outU; io.n = io0.n; io.ncols = io0.ncols; io.ncb = (io0.ncols + TK - 1) / TK; io.pitch = io0.pitch; io.scale = io0.scale;
-  io.slab = 0; io.nouter = 1; io.nyl = 0;
+  io.slab = 0; io.nouter = 1; io.nyl = 0; io.peer_tab = nullptr; io.peer_x0 = 0;
   SpectralUpdate2<double> up{};
   up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz; up.kmode = up0.kmode; up.nzc = up0.nzc; up.nzv = up0.nzc; up.x0 = up0.x0;
   up.closed_M = up0.closed_M; up.closed_L = up0.closed_L; up.has_L = up0.has_L; up.Mfac = up0.Mfac; up.Lfac = up0.Lfac;
@@ -327,7 +327,7 @@ template <class C, int PPB, int NG, int NS> static void test_zinv_tma(const char
 }
 
 // fused pass in the multi-GPU slab layout: data staged as [P][nxl][nyl][nzc], transform along y
-template <class C, int TK, int NG> static void test_fused_slab(const char *name, int P, int nxl, int nzc, int x0, int grid) {
+template <class C, int TK, int NG> static void test_fused_slab(const char *name, int P, int nxl, int nzc, int x0, int grid, bool peer = false) {
   constexpr int ny = C::N;
   const int nyl = ny / P;
   std::mt19937_64 rng(23);
@@ -352,7 +352,7 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
   auto tw = make_tw(ny);
   FusedTmaIO<double> io;
   io.outU = Us.data(); io.n = ny; io.ncols = nzc; io.ncb = (nzc + TK - 1) / TK; io.pitch = nzc; io.scale = 1.0 / ny;
-  io.slab = 1; io.nouter = nxl; io.nyl = nyl;
+  io.slab = 1; io.nouter = nxl; io.nyl = nyl; io.peer_tab = nullptr; io.peer_x0 = 0;
   SpectralUpdate2<double> up{};
   up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = MRL_KMODE_3D_SLAB; up.nzc = nzc; up.nzv = nzc; up.x0 = x0;
   up.closed_M = 1; up.closed_L = 1; up.has_L = 1; up.Mfac = 0.2; up.Lfac = -0.001; up.dt = 0.01;
@@ -367,8 +367,19 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
   };
   TensorMap tmC = mk4(Cs.data()), tmG = mk4(Gs.data()), tmO = mk4(Os.data());
   const cx<double> *twp = tw.data();
+  // peer mode: the result rows go to P separate "rank" arrays [nxtot][nyl][nzc] at x = peer_x0 + o
+  const int nxtot = x0 + nxl + 1;
+  std::vector<std::vector<cx<double>>> peerbuf(P, std::vector<cx<double>>((size_t)nxtot * nyl * nzc));
+  std::vector<unsigned long long> tab(P);
+  for (int q = 0; q < P; ++q) tab[q] = (unsigned long long)peerbuf[q].data();
+  if (peer) { io.peer_tab = tab.data(); io.peer_x0 = x0; }
   size_t smem = (size_t)(NG * 3 * C::N * TK) * 16 + NG * 3 * 8 + 128;
   emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG>(tmC, tmG, tmO, io, up, twp); }, 64 * 1024);
+  if (peer)
+    for (int x = 0; x < nxl; ++x)
+      for (int y = 0; y < ny; ++y)
+        for (int kz = 0; kz < nzc; ++kz)
+          Us[sidx(x, y, kz)] = peerbuf[y / nyl][((size_t)(x0 + x) * nyl + (y % nyl)) * nzc + kz];
   double err = 0, errN = 0;
   for (int x = 0; x < nxl; ++x)
     for (int q = 0; q < nzc; ++q) {
@@ -401,6 +412,45 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
   report(nm, errN, 1e-12 * ny);
 }
 
+// strided pass with the result rows scattered to P "ranks" (fused forward all-to-all)
+template <class C, int TK, int NG, int NS> static void test_strided_peer(const char *name, int P, int ncols) {
+  constexpr int nx = C::N;
+  const int nxl = nx / P, me = 1;
+  std::mt19937_64 rng(29);
+  std::uniform_real_distribution<double> U(-1, 1);
+  const size_t field = (size_t)nx * ncols;
+  std::vector<cx<double>> in(2 * field);
+  for (auto &v : in) v = mk<double>(U(rng), U(rng));
+  // every rank's staging: [2 fields][P sources][nxl][ncols]
+  std::vector<std::vector<cx<double>>> stage(P, std::vector<cx<double>>(2 * field));
+  std::vector<unsigned long long> tab(P);
+  for (int q = 0; q < P; ++q) tab[q] = (unsigned long long)stage[q].data();
+  auto tw = make_tw(nx);
+  StridedTmaIO<double> io;
+  io.out = io.out1 = nullptr; io.nouter_f = 1;
+  io.n = nx; io.ncols = ncols; io.nouter = 2; io.nvalid = ncols;
+  io.pitch = ncols; io.outer_stride = (long long)nx * ncols;
+  io.ncb = (ncols + TK - 1) / TK; io.scale = 1.0; io.inverse = 0;
+  io.peer_tab = tab.data(); io.peer_rows = nxl; io.peer_field = field; io.peer_off = (long long)me * nxl * ncols;
+  const long long rowb = (long long)ncols * 16;
+  TensorMap tm = emu_map(in.data(), 8, 2LL * ncols, nx, 2, rowb, rowb * nx, 2 * TK, nx < 256 ? nx : 256);
+  size_t smem = (size_t)(NS * nx * TK) * 16 + NS * 8 + 128;
+  const cx<double> *twp = tw.data();
+  emu::launch(dim3(3), dim3(NG * TK * C::TP), smem, [=] { k_strided_tma<double, C, TK, NG, NS>(tm, io, twp); }, 64 * 1024);
+  double err = 0;
+  for (int f = 0; f < 2; ++f)
+    for (int c = 0; c < ncols; ++c) {
+      std::vector<lc> x(nx);
+      for (int j = 0; j < nx; ++j) x[j] = lc(in[f * field + (size_t)j * ncols + c].x, in[f * field + (size_t)j * ncols + c].y);
+      auto y = dft(x, -1);
+      for (int j = 0; j < nx; ++j) {
+        auto v = stage[j / nxl][f * field + ((size_t)me * nxl + j % nxl) * ncols + c];
+        err = std::max(err, (double)std::abs(lc(v.x, v.y) - y[j]));
+      }
+    }
+  report(name, err, 1e-12 * nx);
+}
+
 static void tma_tests() {
   test_strided("strided tma 64 TK8 NG2 NS3", 64, 19, 3, 0, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>(io, tw, 2); });
   test_strided("strided tma 64 TK8 NG2 NS3 inv g5", 64, 19, 3, 1, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>(io, tw, 5); });
@@ -415,6 +465,8 @@ static void tma_tests() {
   }, 0);
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 nxl3 nzc5", 4, 3, 5, 2, 2);
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 1>("fused tma slab 64 P2 nxl2 nzc9", 2, 2, 9, 0, 1);
+  test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 peer stores", 4, 3, 5, 6, 2, true);
+  test_strided_peer<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("strided tma 64 peer scatter P4", 4, 11);
   test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 3, 2>("zfwd tma 64 PPB4 NG3 NS2 rows=21", 21, 2);
   test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("zfwd tma 64 PPB8 NG2 NS3 rows=50", 50, 1);
   test_zfwd_tma<FFTCfg<512, 64, 8, 8, 8>, 1, 2, 2>("zfwd tma 512 PPB1 NG2 NS2 rows=5 (pair_map)", 5, 1);

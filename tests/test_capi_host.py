@@ -60,3 +60,24 @@ def test_emulated_kernels():
     subprocess.check_call(["make", "emu"], cwd=ROOT)
     out = subprocess.run([os.path.join(ROOT, "tests/emu/_build/emu_fft_test")], capture_output=True, text=True)
     assert out.returncode == 0 and "EMU TESTS PASSED" in out.stdout, out.stdout[-2000:]
+
+
+def _partition_ref(total, weights):
+    """DomainAction::partitionHepler restated (include/actions/DomainAction.h:249-280)."""
+    ns, rem = [], sum(weights)
+    for w in weights:
+        n = max((total * w) // rem, 1)
+        ns.append(n)
+        rem -= w
+        total -= n
+    ns[-1] += total
+    return ns
+
+
+@pytest.mark.parametrize("total,weights", [(20, [1, 1, 1]), (512, [1] * 8), (10, [1, 2, 3, 4]), (7, [1, 1]), (40, [3, 1, 1]),
+                                           (257, [1] * 4), (5, [1] * 5)])
+def test_partition_matches_reference_rule(lib, total, weights):
+    from marlin_b200 import capi
+    got = capi.partition(total, len(weights), weights)
+    assert got == _partition_ref(total, weights) and sum(got) == total
+    assert capi.partition(total, len(weights)) == _partition_ref(total, [1] * len(weights))
