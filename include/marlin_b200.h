@@ -144,6 +144,42 @@ int mrl_split_substep_timed(mrl_split_plan *plan, void *c_real_dev, double dt, c
 /* HBM passes / kernels one substep launches (for bench bookkeeping) */
 int mrl_split_launches_per_substep(const mrl_split_plan *plan);
 
+/* ---- de Geus finite-strain FFT mechanics ------------------------------------------------
+ * FFTMechanics (src/tensor_computes/FFTMechanics.C:48-163) with the HyperElasticIsotropic
+ * constitutive model (src/tensor_computes/HyperElasticIsotropic.C:42-52) and the matrix-free CG
+ * of include/utils/MarlinUtils.h:57-131.  Tensor fields are COMPONENT-MAJOR here:
+ * [9][nx][ny][nz] with component c = 3*i + j; the reference layout [nx][ny][nz][3][3] is
+ * converted with mrl_components().  Ghat4 (81 complex values per wavevector) and C4 / K4 (81
+ * values per voxel) are never materialised: the contractions are evaluated in closed form from
+ * q and from (F, K, mu).  K and mu are real [nx][ny][nz] fields owned by the caller.        */
+typedef struct mrl_mech_plan mrl_mech_plan;
+typedef struct mrl_mech_desc {
+  double l_tol;       /* CG relative tolerance on |b|                    (FFTMechanics.C:33) */
+  int64_t l_max_its;  /* <= 0: number of cells                            (:63-64)            */
+  double nl_rel_tol, nl_abs_tol;
+  int nl_max_its;
+} mrl_mech_desc;
+typedef struct mrl_mech_stats {
+  int newton_iterations, cg_solves, cg_iterations_total;
+  int cg_iterations[64];
+  double final_rnorm, final_anorm;
+} mrl_mech_stats;
+int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *desc, const void *K_real_dev, const void *mu_real_dev,
+                         mrl_mech_plan **out);
+int mrl_mech_plan_destroy(mrl_mech_plan *plan);
+/* P = F . S(F)                      HyperElasticIsotropic::computeBuffer                    */
+int mrl_mech_constitutive(mrl_mech_plan *plan, const void *F_dev, void *P_dev);
+/* out = irfftn( Ghat4 : rfftn(A) )  FFTMechanics.C:104-105                                   */
+int mrl_mech_apply_G(mrl_mech_plan *plan, const void *A_dev, void *out_dev);
+/* out = G( K4(F) : x )              FFTMechanics.C:107-112 (the CG operator)                 */
+int mrl_mech_apply_GK(mrl_mech_plan *plan, const void *F_dev, const void *x_dev, void *out_dev);
+/* One FFTMechanics::computeBuffer: F is updated in place (F + applied strain + Newton
+ * increments), P receives the stress of the final state.  applied9: row-major 3x3 applied
+ * macroscopic strain or NULL.  Synchronous (iteration counts depend on device-side norms).   */
+int mrl_mech_solve(mrl_mech_plan *plan, void *F_dev, const double *applied9, void *P_dev, mrl_mech_stats *stats);
+/* [n][ncomp] (components fastest, the reference layout) <-> [ncomp][n]; in != out.           */
+int mrl_components(mrl_context *ctx, const void *in_dev, void *out_dev, int64_t n, int ncomp, int to_component_major);
+
 /* ---- multi-GPU slab decomposition -------------------------------------------------------
  * DomainAction::partitionSlabs / partitionHepler (src/actions/DomainAction.C:511-566,
  * include/actions/DomainAction.h:249-280) and fftSlab / ifftSlab (:870-1019): real space is

@@ -248,3 +248,68 @@ def partition(total, nranks, weights=None):
     w = (C.c_double * nranks)(*[float(x) for x in weights]) if weights is not None else None
     _ck(lib().mrl_partition(C.c_int64(total), int(nranks), w, cnt))
     return list(cnt)
+
+
+class MechDesc(C.Structure):
+    _fields_ = [("l_tol", C.c_double), ("l_max_its", C.c_int64), ("nl_rel_tol", C.c_double),
+                ("nl_abs_tol", C.c_double), ("nl_max_its", C.c_int)]
+
+
+class MechStats(C.Structure):
+    _fields_ = [("newton_iterations", C.c_int), ("cg_solves", C.c_int), ("cg_iterations_total", C.c_int),
+                ("cg_iterations", C.c_int * 64), ("final_rnorm", C.c_double), ("final_anorm", C.c_double)]
+
+
+def components(ctx, t, ncomp, to_component_major):
+    """[n][ncomp] (the reference's trailing value dimensions) <-> [ncomp][n]."""
+    assert t.is_cuda and t.is_contiguous()
+    out = torch.empty_like(t)
+    n = t.numel() // ncomp
+    _ck(lib().mrl_components(ctx.h, _p(t), _p(out), C.c_int64(n), int(ncomp), int(to_component_major)))
+    return out
+
+
+class MechPlan:
+    """FFTMechanics + HyperElasticIsotropic behind the C ABI (component-major tensor fields
+    [9][nx][ny][nz]); see include/marlin_b200.h."""
+
+    def __init__(self, ctx, K, mu, l_tol=1e-2, l_max_its=0, nl_rel_tol=1e-5, nl_abs_tol=1e-8, nl_max_its=100):
+        self.ctx = ctx
+        self._keep = (K, mu)
+        d = MechDesc(float(l_tol), int(l_max_its or 0), float(nl_rel_tol), float(nl_abs_tol), int(nl_max_its))
+        self.h = C.c_void_p()
+        _ck(lib().mrl_mech_plan_create(ctx.h, C.byref(d), _p(K), _p(mu), C.byref(self.h)))
+
+    def constitutive(self, F):
+        P = torch.empty_like(F)
+        _ck(lib().mrl_mech_constitutive(self.h, _p(F), _p(P)))
+        return P
+
+    def apply_G(self, A):
+        out = torch.empty_like(A)
+        _ck(lib().mrl_mech_apply_G(self.h, _p(A), _p(out)))
+        return out
+
+    def apply_GK(self, F, x):
+        out = torch.empty_like(x)
+        _ck(lib().mrl_mech_apply_GK(self.h, _p(F), _p(x), _p(out)))
+        return out
+
+    def solve(self, F, applied=None):
+        """One FFTMechanics::computeBuffer; F is updated in place. Returns (P, stats)."""
+        P = torch.empty_like(F)
+        st = MechStats()
+        a = (C.c_double * 9)(*[float(v) for v in applied]) if applied is not None else None
+        _ck(lib().mrl_mech_solve(self.h, _p(F), a, _p(P), C.byref(st)))
+        return P, st
+
+    def close(self):
+        if self.h:
+            lib().mrl_mech_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,259 @@
+// de Geus finite-strain FFT mechanics: per-voxel constitutive law / tangent action, the
+// Green-operator projection per wavevector, and the fused vector updates of the CG solver.
+//
+// Reference: FFTMechanics (src/tensor_computes/FFTMechanics.C:48-163), HyperElasticIsotropic
+// (src/tensor_computes/HyperElasticIsotropic.C:24-52), conjugateGradientSolve
+// (include/utils/MarlinUtils.h:57-131), einsum helpers (src/utils/MarlinUtils.C:147-187).
+// The reference materialises C4, K4 (81 values per voxel) and Ghat4 (81 complex values per
+// wavevector) and contracts them with einsum; here the same contractions are written out in
+// closed form and evaluated in registers, so nothing but F, K, mu and the iterate is read:
+//   S      = K tr(E) I + 2 mu (E - tr(E)/3 I),  E = (F^T F - I)/2          (C4 : E)
+//   P      = F S                                                           (dot22(F, S))
+//   K4 : x = x S + F T(F^T x),  T(W) = K tr(W) I + 2 mu (sym W - tr(W)/3 I) (trans2(ddot42(K4, trans2 x)))
+//   Ghat:A = (A q) q^T / |q|^2   (0 at q = 0)                              (ddot42(Ghat4, A))
+// Fields are component-major: [9][nx][ny][nz] real, [9][nx][ny][ncp] complex (c = 3 i + j).
+#include "k_common.cuh"
+#include "mrl_internal.h"
+
+namespace mrl {
+
+template <class T> struct M3 {
+  T a[3][3];
+};
+
+template <class T> __device__ __forceinline__ void second_pk(const M3<T> &F, T K, T mu, M3<T> &S) {
+  T E[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T s = T(0);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s += F.a[k][i] * F.a[k][j];
+      E[i][j] = T(0.5) * (s - (i == j ? T(1) : T(0)));
+    }
+  const T tr = E[0][0] + E[1][1] + E[2][2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) S.a[i][j] = T(2) * mu * E[i][j] + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
+}
+
+// mode 0: out = P = F S.   mode 1: out = K4 : x (x from memory).   mode 2: same with a spatially
+// constant x (9 values in xc) - the applied macroscopic strain.
+template <class T>
+__global__ void __launch_bounds__(256) k_mech_pointwise(int mode, const T *F, const T *Kf, const T *muf, const T *x, M3<T> xc, T *out,
+                                                        long long n, T scale) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+    M3<T> Fm, S;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) Fm.a[c / 3][c % 3] = F[c * n + v];
+    const T K = Kf[v], mu = muf[v];
+    second_pk(Fm, K, mu, S);
+    M3<T> R;
+    if (mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) R.a[i][j] = Fm.a[i][0] * S.a[0][j] + Fm.a[i][1] * S.a[1][j] + Fm.a[i][2] * S.a[2][j];
+    } else {
+      M3<T> X = xc;
+      if (mode == 1) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = x[c * n + v];
+      }
+      T W[3][3];
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) W[p][l] = Fm.a[0][p] * X.a[0][l] + Fm.a[1][p] * X.a[1][l] + Fm.a[2][p] * X.a[2][l];
+      const T tr = W[0][0] + W[1][1] + W[2][2];
+      T Tm[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Tm[i][j] = mu * (W[i][j] + W[j][i]) + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          R.a[i][j] = X.a[i][0] * S.a[0][j] + X.a[i][1] * S.a[1][j] + X.a[i][2] * S.a[2][j] + Fm.a[i][0] * Tm[0][j] + Fm.a[i][1] * Tm[1][j] +
+                      Fm.a[i][2] * Tm[2][j];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) out[c * n + v] = R.a[c / 3][c % 3] * scale;
+  }
+}
+
+// In place: A_ij <- (sum_k A_ik q_k) q_j / |q|^2 for every wavevector (0 at q = 0)
+template <class T>
+__global__ void __launch_bounds__(256) k_mech_project(cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp) {
+  const long long plane = (long long)n1 * ncp, field = (long long)n0 * plane;
+  const long long total = (long long)n0 * n1 * nzc;
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const int iz = (int)(w % nzc);
+    const int iy = (int)((w / nzc) % n1);
+    const int ix = (int)(w / ((long long)nzc * n1));
+    const long long off = (long long)ix * plane + (long long)iy * ncp + iz;
+    const T q[3] = {kx[ix], ky[iy], kz[iz]};
+    const T Q = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    const T inv = Q == T(0) ? T(0) : T(1) / Q;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const cx<T> a0 = A[(3 * i + 0) * field + off], a1 = A[(3 * i + 1) * field + off], a2 = A[(3 * i + 2) * field + off];
+      const T vx = (a0.x * q[0] + a1.x * q[1] + a2.x * q[2]) * inv;
+      const T vy = (a0.y * q[0] + a1.y * q[1] + a2.y * q[2]) * inv;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) A[(3 * i + j) * field + off] = mk<T>(vx * q[j], vy * q[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- vector algebra
+// Scalars of the CG iteration live in a small device array so that no host round trip sits
+// between the reductions and the updates that use them.
+enum { SC_RZ = 0, SC_PAP = 1, SC_ALPHA = 2, SC_RES2 = 3, SC_BETA = 4, SC_TMP = 5, SC_COUNT = 8 };
+enum { VOP_DOT = 0, VOP_CG_XR = 1, VOP_XPBY = 2, VOP_AXPY = 3, VOP_SUB = 4, VOP_COPY = 5 };
+enum { FIN_STORE = 0, FIN_ALPHA = 1, FIN_RES = 2 };
+
+template <class T> __device__ __forceinline__ double block_sum(double acc) {
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sm[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sm[warp] = acc;
+  __syncthreads();
+  double r = 0;
+  if (warp == 0) {
+    r = sm[lane & 7];
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;
+}
+
+// VOP_DOT   : partial sums of a.b
+// VOP_CG_XR : x += alpha p (a = p, y = x);  r -= alpha Ap (b = Ap, z = r);  partial sums of r.r
+// VOP_XPBY  : y = a + beta y           (p = r + beta p)
+// VOP_AXPY  : y += s a                 (s = host scalar)
+// VOP_SUB   : z = a - b                (r = b - A x)
+// VOP_COPY  : y = a
+template <class T>
+__global__ void __launch_bounds__(256) k_vec(int op, const T *a, const T *b, T *y, T *z, const double *scal, double s, long long n,
+                                             double *partials) {
+  double acc = 0;
+  const double alpha = (op == VOP_CG_XR) ? scal[SC_ALPHA] : (op == VOP_XPBY ? scal[SC_BETA] : s);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (op == VOP_DOT) {
+      acc += (double)a[i] * (double)b[i];
+    } else if (op == VOP_CG_XR) {
+      y[i] = (T)((double)y[i] + alpha * (double)a[i]);
+      const double r = (double)z[i] - alpha * (double)b[i];
+      z[i] = (T)r;
+      acc += r * r;
+    } else if (op == VOP_XPBY) {
+      y[i] = (T)((double)a[i] + alpha * (double)y[i]);
+    } else if (op == VOP_AXPY) {
+      y[i] = (T)((double)y[i] + alpha * (double)a[i]);
+    } else if (op == VOP_SUB) {
+      z[i] = (T)((double)a[i] - (double)b[i]);
+    } else {
+      y[i] = a[i];
+    }
+  }
+  if (op == VOP_DOT || op == VOP_CG_XR) {
+    const double r = block_sum<T>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = r;
+  }
+}
+
+// single block: finish a reduction and derive the dependent scalars
+__global__ void __launch_bounds__(256) k_vec_final(int fin, int slot, const double *partials, int nblk, double *scal) {
+  double acc = 0;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += partials[i];
+  const double r = block_sum<double>(acc);
+  if (threadIdx.x == 0) {
+    if (fin == FIN_STORE) {
+      scal[slot] = r;
+    } else if (fin == FIN_ALPHA) {  // r = p.Ap
+      scal[SC_PAP] = r;
+      scal[SC_ALPHA] = scal[SC_RZ] / r;
+    } else {  // r = new r.r
+      scal[SC_RES2] = r;
+      scal[SC_BETA] = r / scal[SC_RZ];
+      scal[SC_RZ] = r;
+    }
+  }
+}
+
+// y[c][v] += s[c] (9 constants): F + applied macroscopic strain
+template <class T> __global__ void __launch_bounds__(256) k_add_const9(T *y, M3<T> s, long long n) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c) y[c * n + v] += s.a[c / 3][c % 3];
+  }
+}
+
+// [n][ncomp] (reference layout, components fastest) <-> [ncomp][n]
+template <class T> __global__ void __launch_bounds__(256) k_components(const T *in, T *out, long long n, int ncomp, int to_soa) {
+  const long long total = n * ncomp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / ncomp;
+    const int c = (int)(i - v * ncomp);
+    if (to_soa) out[c * n + v] = in[i];
+    else out[i] = in[c * n + v];
+  }
+}
+
+static inline int ew_grid(long long total, const LaunchCtx &lc) {
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)lc.sm_count * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+template <class T>
+cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
+                                  long long n, double scale) {
+  M3<T> X;
+  for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = xc ? (T)xc[c] : T(0);
+  k_mech_pointwise<T><<<ew_grid(n, lc), 256, 0, lc.stream>>>(mode, F, K, mu, x, X, out, n, (T)scale);
+  return cudaGetLastError();
+}
+template <class T>
+cudaError_t launch_mech_project(const LaunchCtx &lc, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp) {
+  k_mech_project<T><<<ew_grid((long long)n0 * n1 * nzc, lc), 256, 0, lc.stream>>>(A, kx, ky, kz, n0, n1, nzc, ncp);
+  return cudaGetLastError();
+}
+template <class T>
+cudaError_t launch_vec(const LaunchCtx &lc, int op, const T *a, const T *b, T *y, T *z, double *scal, double s, long long n, int fin, int slot,
+                       double *partials, int nblk) {
+  k_vec<T><<<nblk, 256, 0, lc.stream>>>(op, a, b, y, z, scal, s, n, partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (op == VOP_DOT || op == VOP_CG_XR) {
+    k_vec_final<<<1, 256, 0, lc.stream>>>(fin, slot, partials, nblk, scal);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, T *y, const double *s, long long n) {
+  M3<T> S;
+  for (int c = 0; c < 9; ++c) S.a[c / 3][c % 3] = (T)s[c];
+  k_add_const9<T><<<ew_grid(n, lc), 256, 0, lc.stream>>>(y, S, n);
+  return cudaGetLastError();
+}
+template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *in, T *out, long long n, int ncomp, int to_soa) {
+  k_components<T><<<ew_grid(n * ncomp, lc), 256, 0, lc.stream>>>(in, out, n, ncomp, to_soa);
+  return cudaGetLastError();
+}
+
+#define INST(T)                                                                                                                   \
+  template cudaError_t launch_mech_pointwise<T>(const LaunchCtx &, int, const T *, const T *, const T *, const T *, const double *, \
+                                                T *, long long, double);                                                          \
+  template cudaError_t launch_mech_project<T>(const LaunchCtx &, cx<T> *, const T *, const T *, const T *, int, int, int, int);    \
+  template cudaError_t launch_vec<T>(const LaunchCtx &, int, const T *, const T *, T *, T *, double *, double, long long, int, int, \
+                                     double *, int);                                                                              \
+  template cudaError_t launch_add_const9<T>(const LaunchCtx &, T *, const double *, long long);                                    \
+  template cudaError_t launch_components<T>(const LaunchCtx &, const T *, T *, long long, int, int);
+INST(double)
+INST(float)
+
+}  // namespace mrl

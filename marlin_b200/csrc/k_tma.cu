@@ -289,6 +289,36 @@ cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, c
 }
 
 template <class T, class C, int PPB, int NG, int NS>
+static cudaError_t zfwd_pairs_tma_go(const LaunchCtx &lc, const T *in, cx<T> *out, long long nrows, int ncp, const cx<T> *tw) {
+  constexpr int NP = C::N + (C::N >> 3) + 1;
+  constexpr size_t smem = (size_t)NG * NS * 2 * PPB * C::N * sizeof(T) + (size_t)(NG * PPB * NP) * sizeof(cx<T>) + NG * NS * 8 + 128;
+  static_assert(smem <= kSmemBudget, "zfwd_pairs_tma: shared memory budget");
+  static_assert(NG * PPB * C::TP <= 1024 && NG <= 15, "zfwd_pairs_tma: block size");
+  if (((unsigned long long)in & 15ull) || (C::N * sizeof(T)) % 16) return cudaErrorNotSupported;
+  auto k = k_zfwd_pairs_tma<T, C, PPB, NG, NS>;
+  int per_sm = 0;
+  cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long npencils = (nrows + 1) / 2;
+  const long long nwork = ((npencils + PPB - 1) / PPB + NG - 1) / NG;
+  const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
+  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(in, out, nrows, ncp, tw);
+  return cudaGetLastError();
+}
+
+template <class T>
+cudaError_t launch_zfwd_pairs_tma(const LaunchCtx &lc, const T *in, cx<T> *out, long long nrows, int n, int ncp, const cx<T> *tw) {
+  if (!tma_enabled()) return cudaErrorNotSupported;
+  switch (n) {
+    case 128: return zfwd_pairs_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 2>(lc, in, out, nrows, ncp, tw);
+    case 256: return zfwd_pairs_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 2>(lc, in, out, nrows, ncp, tw);
+    case 512: return zfwd_pairs_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 2>(lc, in, out, nrows, ncp, tw);
+    case 1024: return zfwd_pairs_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 2>(lc, in, out, nrows, ncp, tw);
+    default: return cudaErrorNotSupported;
+  }
+}
+
+template <class T, class C, int PPB, int NG, int NS>
 static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw) {
   constexpr int NP = C::N + (C::N >> 3) + 1;
   constexpr int NC = (C::N / 2 + 1 + 15) & ~15;  // slot rows sized for the largest padded pitch
@@ -344,6 +374,7 @@ cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp,
                                            int);                                                                         \
   template cudaError_t launch_zfwd_nonlin_tma<T>(const LaunchCtx &, const T *, T *, cx<T> *, cx<T> *, long long, int,    \
                                                  int, const NonlinDesc &, const cx<T> *);                                \
+  template cudaError_t launch_zfwd_pairs_tma<T>(const LaunchCtx &, const T *, cx<T> *, long long, int, int, const cx<T> *);  \
   template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, int, T *, long long, int, T, const cx<T> *);
 INST(double)
 INST(float)

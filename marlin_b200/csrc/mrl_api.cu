@@ -289,11 +289,14 @@ extern "C" int mrl_copy(mrl_context *ctx, void *dst, const void *src, size_t byt
 }
 
 // ------------------------------------------------------------------------------ FFT
+// Complex pass along `axis` of batched [batch][n0][n1][ncp] spectra (ncp = pitch of the last axis;
+// ncp > n_last/2+1 only with the TMA kernels, whose padding columns are carried along as zeros).
 template <class T> static int strided_axis(mrl_context *ctx, const cx<T> *in, cx<T> *out, int nfields, long long field_stride,
-                                           int axis, int batch, int inverse) {
+                                           int axis, int batch, int inverse, int ncp = 0) {
   const int dim = ctx->dim;
   const int nc = ctx->nr[dim - 1];
-  long long ncols = nc;
+  if (!ncp) ncp = nc;
+  long long ncols = ncp;
   for (int b = axis + 1; b < dim - 1; ++b) ncols *= ctx->n[b];
   long long nouter = batch;
   for (int b = 0; b < axis; ++b) nouter *= ctx->n[b];
@@ -317,53 +320,88 @@ template <class T> static int strided_axis(mrl_context *ctx, const cx<T> *in, cx
   if (rc) return rc;
   ctx->launches++;
   cudaError_t te = launch_strided_tma<T>(ctx->lc(), io, (const cx<T> *)tw, io.n);
-  if (te == cudaErrorNotSupported) te = launch_strided<T>(ctx->lc(), io, (const cx<T> *)tw, make_fft_plan(io.n));
+  if (te == cudaErrorNotSupported && ncp == nc) te = launch_strided<T>(ctx->lc(), io, (const cx<T> *)tw, make_fft_plan(io.n));
   CK(te);
   return MRL_OK;
 }
 
 template <class T>
-static cudaError_t zinv_dispatch(mrl_context *ctx, const cx<T> *in, T *out, long long rows, int n, T scale, const cx<T> *tw) {
-  cudaError_t e = launch_zinv_pairs_tma<T>(ctx->lc(), in, n / 2 + 1, out, rows, n, scale, tw);
-  if (e == cudaErrorNotSupported) e = launch_zinv_pairs<T>(ctx->lc(), in, out, rows, n, scale, tw, make_fft_plan(n));
+static cudaError_t zinv_dispatch(mrl_context *ctx, const cx<T> *in, T *out, long long rows, int n, T scale, const cx<T> *tw,
+                                 int ncp = 0) {
+  if (!ncp) ncp = n / 2 + 1;
+  cudaError_t e = launch_zinv_pairs_tma<T>(ctx->lc(), in, ncp, out, rows, n, scale, tw);
+  if (e == cudaErrorNotSupported && ncp == n / 2 + 1) e = launch_zinv_pairs<T>(ctx->lc(), in, out, rows, n, scale, tw, make_fft_plan(n));
   return e;
 }
 
-template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *out, int batch) {
+template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *out, int batch, int ncp = 0) {
   const int dim = ctx->dim, nl = ctx->n[dim - 1];
+  const int nc = nl / 2 + 1;
+  if (!ncp) ncp = nc;
   long long rows = batch;
   for (int d = 0; d < dim - 1; ++d) rows *= ctx->n[d];
   const void *tw;
   int rc = ctx->twiddles(nl, &tw);
   if (rc) return rc;
-  CKL(ctx, launch_zfwd_pairs<T>(ctx->lc(), in, out, rows, nl, (const cx<T> *)tw, make_fft_plan(nl)));
+  ctx->launches++;
+  cudaError_t e = launch_zfwd_pairs_tma<T>(ctx->lc(), in, out, rows, nl, ncp, (const cx<T> *)tw);
+  if (e == cudaErrorNotSupported && ncp == nc) e = launch_zfwd_pairs<T>(ctx->lc(), in, out, rows, nl, (const cx<T> *)tw, make_fft_plan(nl));
+  CK(e);
   for (int a = dim - 2; a >= 0; --a)
-    if ((rc = strided_axis<T>(ctx, out, out, 1, 0, a, batch, 0))) return rc;
+    if ((rc = strided_axis<T>(ctx, out, out, 1, 0, a, batch, 0, ncp))) return rc;
+  return MRL_OK;
+}
+
+// src == nullptr: transform `work` in place (it is destroyed); otherwise src is preserved and
+// `work` receives the partially transformed spectra
+template <class T> static int irfftn_impl2(mrl_context *ctx, const cx<T> *src, cx<T> *work, T *out, int batch, int ncp, double scale) {
+  const int dim = ctx->dim, nl = ctx->n[dim - 1];
+  long long rows = batch;
+  for (int d = 0; d < dim - 1; ++d) rows *= ctx->n[d];
+  const cx<T> *cur = src ? src : work;
+  int rc;
+  for (int a = 0; a <= dim - 2; ++a) {
+    if ((rc = strided_axis<T>(ctx, cur, work, 1, 0, a, batch, 1, ncp))) return rc;
+    cur = work;
+  }
+  const void *tw;
+  if ((rc = ctx->twiddles(nl, &tw))) return rc;
+  CKL(ctx, zinv_dispatch<T>(ctx, cur, out, rows, nl, (T)scale, (const cx<T> *)tw, ncp));
   return MRL_OK;
 }
 
 template <class T> static int irfftn_impl(mrl_context *ctx, const cx<T> *in, T *out, int batch) {
-  const int dim = ctx->dim, nl = ctx->n[dim - 1];
-  long long rows = batch, total = batch;
-  for (int d = 0; d < dim - 1; ++d) rows *= ctx->n[d];
+  const int dim = ctx->dim;
+  long long total = batch;
   for (int d = 0; d < dim; ++d) total *= ctx->nr[d];
   double N = 1;
   for (int d = 0; d < dim; ++d) N *= ctx->n[d];
-  const cx<T> *src = in;
-  int rc;
+  cx<T> *sc = nullptr;
   if (dim > 1) {
     void *s;
-    if ((rc = ctx->scratch((size_t)total * sizeof(cx<T>), &s))) return rc;
-    cx<T> *sc = (cx<T> *)s;
-    for (int a = 0; a <= dim - 2; ++a) {
-      if ((rc = strided_axis<T>(ctx, src, sc, 1, 0, a, batch, 1))) return rc;
-      src = sc;
-    }
+    int rc = ctx->scratch((size_t)total * sizeof(cx<T>), &s);
+    if (rc) return rc;
+    sc = (cx<T> *)s;
   }
-  const void *tw;
-  if ((rc = ctx->twiddles(nl, &tw))) return rc;
-  CKL(ctx, zinv_dispatch<T>(ctx, src, out, rows, nl, (T)(1.0 / N), (const cx<T> *)tw));
-  return MRL_OK;
+  return irfftn_impl2<T>(ctx, in, sc, out, batch, 0, 1.0 / N);
+}
+
+// Internal batched transforms on padded layouts (mechanics): see mrl_internal.h
+int mrl_fftb_pitch(const mrl_context *ctx) {
+  const int dim = ctx->dim, nc = ctx->nr[dim - 1];
+  bool all = tma_enabled() && !getenv("MRL_NOPAD");
+  for (int a = 0; a < dim; ++a) all = all && (ctx->n[a] == 128 || ctx->n[a] == 256 || ctx->n[a] == 512 || ctx->n[a] == 1024);
+  if (!all) return nc;
+  const int per128 = ctx->precision == MRL_F64 ? 8 : 16;
+  return (nc + per128 - 1) / per128 * per128;
+}
+int mrl_fftb_forward(mrl_context *ctx, const void *in, void *out, int batch, int ncp) {
+  return ctx->precision == MRL_F64 ? rfftn_impl<double>(ctx, (const double *)in, (cx<double> *)out, batch, ncp)
+                                   : rfftn_impl<float>(ctx, (const float *)in, (cx<float> *)out, batch, ncp);
+}
+int mrl_fftb_inverse(mrl_context *ctx, void *work, void *out, int batch, int ncp, double scale) {
+  return ctx->precision == MRL_F64 ? irfftn_impl2<double>(ctx, nullptr, (cx<double> *)work, (double *)out, batch, ncp, scale)
+                                   : irfftn_impl2<float>(ctx, nullptr, (cx<float> *)work, (float *)out, batch, ncp, scale);
 }
 
 extern "C" int mrl_rfftn(mrl_context *ctx, const void *in, void *out, int batch) {

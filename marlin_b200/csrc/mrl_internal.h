@@ -66,6 +66,13 @@ struct mrl_slab_plan {
   void *peer_send_tab = nullptr;
 };
 
+// Internal batched real transforms on [batch][n0][n1][n2] fields with a last-axis spectrum pitch
+// ncp >= n2/2+1 (mrl_fftb_pitch: padded to 128 bytes when every axis runs on the TMA kernels).
+// forward: unnormalised; inverse: `work` is transformed in place (destroyed), result * scale.
+int mrl_fftb_pitch(const mrl_context *ctx);
+int mrl_fftb_forward(mrl_context *ctx, const void *in_real, void *out_cplx, int batch, int ncp);
+int mrl_fftb_inverse(mrl_context *ctx, void *work_cplx, void *out_real, int batch, int ncp, double scale);
+
 namespace mrl {
 FFTPlanDev make_fft_plan(int n);
 template <class T>

@@ -1,0 +1,246 @@
+// marlin_b200 - C ABI of the de Geus FFT mechanics solve (host logic; kernels in k_mech.cu and
+// the batched FFT passes).  Reference: FFTMechanics::computeBuffer
+// (src/tensor_computes/FFTMechanics.C:96-163), conjugateGradientSolve
+// (include/utils/MarlinUtils.h:57-131), HyperElasticIsotropic::computeBuffer
+// (src/tensor_computes/HyperElasticIsotropic.C:42-52).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mrl_internal.h"
+
+using namespace mrl;
+
+namespace mrl {
+enum { SC_RZ = 0, SC_PAP = 1, SC_ALPHA = 2, SC_RES2 = 3, SC_BETA = 4, SC_TMP = 5, SC_COUNT = 8 };
+enum { VOP_DOT = 0, VOP_CG_XR = 1, VOP_XPBY = 2, VOP_AXPY = 3, VOP_SUB = 4, VOP_COPY = 5 };
+enum { FIN_STORE = 0, FIN_ALPHA = 1, FIN_RES = 2 };
+template <class T>
+cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
+                                  long long n, double scale);
+template <class T>
+cudaError_t launch_mech_project(const LaunchCtx &lc, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp);
+template <class T>
+cudaError_t launch_vec(const LaunchCtx &lc, int op, const T *a, const T *b, T *y, T *z, double *scal, double s, long long n, int fin, int slot,
+                       double *partials, int nblk);
+template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, T *y, const double *s, long long n);
+template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *in, T *out, long long n, int ncomp, int to_soa);
+}  // namespace mrl
+
+#define CK(call)                                                                                                      \
+  do {                                                                                                                \
+    cudaError_t e_ = (call);                                                                                          \
+    if (e_ != cudaSuccess)                                                                                            \
+      return mrl_fail(MRL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);      \
+  } while (0)
+
+struct mrl_mech_plan {
+  mrl_context *ctx = nullptr;
+  mrl_mech_desc desc;
+  const void *K = nullptr, *mu = nullptr;
+  long long n = 0;  // voxels
+  int ncp = 0;
+  void *spec = nullptr;                                                    // [9][n0][n1][ncp] complex
+  void *tmp = nullptr, *rhs = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *Ap = nullptr, *Fk = nullptr;  // [9][n] real
+  double *scal = nullptr, *partials = nullptr, *host = nullptr;
+  int nblk = 0;
+};
+
+extern "C" int mrl_mech_plan_destroy(mrl_mech_plan *p) {
+  if (!p) return MRL_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (void *q : {p->spec, p->tmp, p->rhs, p->x, p->r, p->p, p->Ap, p->Fk, (void *)p->scal, (void *)p->partials}) cudaFree(q);
+  if (p->host) cudaFreeHost(p->host);
+  delete p;
+  return MRL_OK;
+}
+
+extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, const void *K, const void *mu, mrl_mech_plan **out) {
+  if (!ctx || !d || !K || !mu || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_plan_create: bad arguments");
+  if (ctx->dim != 3) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_mech_plan_create: the CUDA mechanics path is 3-D (dim = %d)", ctx->dim);
+  CK(cudaSetDevice(ctx->device));
+  mrl_mech_plan *p = new mrl_mech_plan();
+  p->ctx = ctx;
+  p->desc = *d;
+  p->K = K;
+  p->mu = mu;
+  p->n = ctx->total();
+  if (p->desc.l_max_its <= 0) p->desc.l_max_its = p->n;  // FFTMechanics.C:63-64: default = number of cells
+  p->ncp = mrl_fftb_pitch(ctx);
+  const size_t esz = ctx->precision == MRL_F64 ? 8 : 4;
+  const size_t vbytes = 9 * (size_t)p->n * esz;
+  const size_t sbytes = 9 * (size_t)ctx->n[0] * ctx->n[1] * p->ncp * 2 * esz;
+  p->nblk = ctx->sm_count * 4;
+  cudaError_t e = cudaMalloc(&p->spec, sbytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->spec, 0, sbytes, ctx->stream);
+  for (void **q : {&p->tmp, &p->rhs, &p->x, &p->r, &p->p, &p->Ap, &p->Fk})
+    if (e == cudaSuccess) e = cudaMalloc(q, vbytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&p->scal, SC_COUNT * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&p->partials, p->nblk * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&p->host, SC_COUNT * sizeof(double));
+  if (e != cudaSuccess) {
+    mrl_mech_plan_destroy(p);
+    return mrl_fail(MRL_ERR_CUDA, "mechanics plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return MRL_OK;
+}
+
+// ---------------------------------------------------------------------------- operators
+template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, double sign) {
+  // out = sign * irfftn( Ghat4 : rfftn(A) ), FFTMechanics.C:104-105
+  mrl_context *ctx = p->ctx;
+  int rc = mrl_fftb_forward(ctx, A, p->spec, 9, p->ncp);
+  if (rc) return rc;
+  ctx->launches++;
+  CK(launch_mech_project<T>(ctx->lc(), (cx<T> *)p->spec, (const T *)ctx->kaxis_dev[0], (const T *)ctx->kaxis_dev[1],
+                            (const T *)ctx->kaxis_dev[2], ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp));
+  return mrl_fftb_inverse(ctx, p->spec, out, 9, p->ncp, sign / (double)p->n);
+}
+
+template <class T> static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xconst, T *out, double sign) {
+  // out = sign * G( K4(F) : x ), FFTMechanics.C:107-112
+  mrl_context *ctx = p->ctx;
+  ctx->launches++;
+  CK(launch_mech_pointwise<T>(ctx->lc(), xconst ? 2 : 1, F, (const T *)p->K, (const T *)p->mu, x, xconst, (T *)p->tmp, p->n, 1.0));
+  return project_G<T>(p, (const T *)p->tmp, out, sign);
+}
+
+template <class T> static int vec(mrl_mech_plan *p, int op, const T *a, const T *b, T *y, T *z, double s, int fin = FIN_STORE, int slot = SC_TMP) {
+  p->ctx->launches++;
+  CK(launch_vec<T>(p->ctx->lc(), op, a, b, y, z, p->scal, s, 9 * p->n, fin, slot, p->partials, p->nblk));
+  return MRL_OK;
+}
+static int read_scalar(mrl_mech_plan *p, int slot, double *v) {
+  CK(cudaMemcpyAsync(p->host, p->scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  CK(cudaStreamSynchronize(p->ctx->stream));
+  *v = p->host[slot];
+  return MRL_OK;
+}
+
+// conjugateGradientSolve, include/utils/MarlinUtils.h:57-131 (identity preconditioner): solves
+// G(K4(Fk) : x) = rhs, x warm-started from p->x.  x_zero: p->x is known to be all zeros.
+template <class T> static int cg_solve(mrl_mech_plan *p, bool x_zero, int *iterations) {
+  const T *Fk = (const T *)p->Fk;
+  T *x = (T *)p->x, *r = (T *)p->r, *pp = (T *)p->p, *Ap = (T *)p->Ap;
+  const T *b = (const T *)p->rhs;
+  int rc;
+  double bb;
+  if ((rc = vec<T>(p, VOP_DOT, b, b, nullptr, nullptr, 0, FIN_STORE, SC_TMP))) return rc;
+  if ((rc = read_scalar(p, SC_TMP, &bb))) return rc;
+  const double b_norm = std::sqrt(bb);
+  *iterations = 0;
+  if (b_norm == 0.0) return MRL_OK;  // :63-66
+  if (x_zero) {
+    if ((rc = vec<T>(p, VOP_COPY, b, nullptr, r, nullptr, 0))) return rc;  // r = b - A(0)
+  } else {
+    if ((rc = apply_GK<T>(p, Fk, x, nullptr, Ap, 1.0))) return rc;
+    if ((rc = vec<T>(p, VOP_SUB, b, Ap, nullptr, r, 0))) return rc;
+  }
+  if ((rc = vec<T>(p, VOP_COPY, r, nullptr, pp, nullptr, 0))) return rc;
+  if ((rc = vec<T>(p, VOP_DOT, r, r, nullptr, nullptr, 0, FIN_STORE, SC_RZ))) return rc;
+  const long long maxit = p->desc.l_max_its;
+  for (long long k = 0; k < maxit; ++k) {
+    if ((rc = apply_GK<T>(p, Fk, pp, nullptr, Ap, 1.0))) return rc;
+    if ((rc = vec<T>(p, VOP_DOT, pp, Ap, nullptr, nullptr, 0, FIN_ALPHA))) return rc;  // alpha = rz / p.Ap
+    if ((rc = vec<T>(p, VOP_CG_XR, pp, Ap, x, r, 0, FIN_RES))) return rc;              // x, r, |r|^2, beta
+    double res2;
+    if ((rc = read_scalar(p, SC_RES2, &res2))) return rc;
+    *iterations = (int)(k + 1);
+    if (std::sqrt(res2) <= p->desc.l_tol * b_norm) return MRL_OK;
+    if ((rc = vec<T>(p, VOP_XPBY, r, nullptr, pp, nullptr, 0))) return rc;  // p = r + beta p
+  }
+  return MRL_OK;
+}
+
+template <class T> static int solve_impl(mrl_mech_plan *p, T *F, const double *applied, T *P, mrl_mech_stats *st) {
+  mrl_context *ctx = p->ctx;
+  const mrl_mech_desc &d = p->desc;
+  const size_t vbytes = 9 * (size_t)p->n * sizeof(T);
+  int rc;
+  memset(st, 0, sizeof *st);
+  // _u = F; constitutive model evaluated at F (:114-116) - the tangent stays at this state until
+  // the first Newton update even though the applied strain is added to _u right away (:118-123)
+  CK(cudaMemcpyAsync(p->Fk, F, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  const double zero9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if ((rc = apply_GK<T>(p, (const T *)p->Fk, nullptr, applied ? applied : zero9, (T *)p->rhs, -1.0))) return rc;
+  if (applied) {
+    ctx->launches++;
+    CK(launch_add_const9<T>(ctx->lc(), F, applied, p->n));
+  }
+  double fn2;
+  if ((rc = vec<T>(p, VOP_DOT, F, F, nullptr, nullptr, 0, FIN_STORE, SC_TMP))) return rc;
+  if ((rc = read_scalar(p, SC_TMP, &fn2))) return rc;
+  const double Fn = std::sqrt(fn2);
+  CK(cudaMemsetAsync(p->x, 0, vbytes, ctx->stream));
+  bool x_zero = true;
+  int iiter = 0;
+  while (true) {
+    int its = 0;
+    if ((rc = cg_solve<T>(p, x_zero, &its))) return rc;
+    if (st->cg_solves < 64) st->cg_iterations[st->cg_solves] = its;
+    st->cg_solves++;
+    st->cg_iterations_total += its;
+    if (its > 0) x_zero = false;
+    // _u += dFm; constitutive; b = -G(P)   (:137-143)
+    if ((rc = vec<T>(p, VOP_AXPY, (const T *)p->x, nullptr, F, nullptr, 1.0))) return rc;
+    CK(cudaMemcpyAsync(p->Fk, F, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->launches++;
+    CK(launch_mech_pointwise<T>(ctx->lc(), 0, (const T *)p->Fk, (const T *)p->K, (const T *)p->mu, nullptr, nullptr, P, p->n, 1.0));
+    if ((rc = project_G<T>(p, P, (T *)p->rhs, -1.0))) return rc;
+    double x2;
+    if ((rc = vec<T>(p, VOP_DOT, (const T *)p->x, (const T *)p->x, nullptr, nullptr, 0, FIN_STORE, SC_TMP))) return rc;
+    if ((rc = read_scalar(p, SC_TMP, &x2))) return rc;
+    const double anorm = std::sqrt(x2), rnorm = anorm / Fn;
+    st->final_anorm = anorm;
+    st->final_rnorm = rnorm;
+    if ((rnorm < d.nl_rel_tol || anorm < d.nl_abs_tol) && iiter > 0) break;  // :145-155
+    iiter++;
+    if (iiter > d.nl_max_its)
+      return mrl_fail(MRL_ERR_INVALID, "Exceeded the maximum number of nonlinear iterations without converging.");
+  }
+  st->newton_iterations = iiter + 1;
+  return MRL_OK;
+}
+
+#define DISPATCH(ctx, fn, ...) ((ctx)->precision == MRL_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+extern "C" int mrl_mech_constitutive(mrl_mech_plan *p, const void *F, void *P) {
+  if (!p || !F || !P) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_constitutive: bad arguments");
+  CK(cudaSetDevice(p->ctx->device));
+  p->ctx->launches++;
+  if (p->ctx->precision == MRL_F64)
+    CK(launch_mech_pointwise<double>(p->ctx->lc(), 0, (const double *)F, (const double *)p->K, (const double *)p->mu, nullptr, nullptr,
+                                     (double *)P, p->n, 1.0));
+  else
+    CK(launch_mech_pointwise<float>(p->ctx->lc(), 0, (const float *)F, (const float *)p->K, (const float *)p->mu, nullptr, nullptr,
+                                    (float *)P, p->n, 1.0));
+  return MRL_OK;
+}
+extern "C" int mrl_mech_apply_G(mrl_mech_plan *p, const void *A, void *out) {
+  if (!p || !A || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_apply_G: bad arguments");
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? project_G<double>(p, (const double *)A, (double *)out, 1.0)
+                                      : project_G<float>(p, (const float *)A, (float *)out, 1.0);
+}
+extern "C" int mrl_mech_apply_GK(mrl_mech_plan *p, const void *F, const void *x, void *out) {
+  if (!p || !F || !x || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_apply_GK: bad arguments");
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? apply_GK<double>(p, (const double *)F, (const double *)x, nullptr, (double *)out, 1.0)
+                                      : apply_GK<float>(p, (const float *)F, (const float *)x, nullptr, (float *)out, 1.0);
+}
+extern "C" int mrl_mech_solve(mrl_mech_plan *p, void *F, const double *applied, void *P, mrl_mech_stats *stats) {
+  if (!p || !F || !P || !stats) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_solve: bad arguments");
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? solve_impl<double>(p, (double *)F, applied, (double *)P, stats)
+                                      : solve_impl<float>(p, (float *)F, applied, (float *)P, stats);
+}
+extern "C" int mrl_components(mrl_context *ctx, const void *in, void *out, int64_t n, int ncomp, int to_soa) {
+  if (!ctx || !in || !out || n < 1 || ncomp < 1 || in == out) return mrl_fail(MRL_ERR_INVALID, "mrl_components: bad arguments");
+  CK(cudaSetDevice(ctx->device));
+  ctx->launches++;
+  if (ctx->precision == MRL_F64) CK(launch_components<double>(ctx->lc(), (const double *)in, (double *)out, n, ncomp, to_soa));
+  else CK(launch_components<float>(ctx->lc(), (const float *)in, (float *)out, n, ncomp, to_soa));
+  return MRL_OK;
+}

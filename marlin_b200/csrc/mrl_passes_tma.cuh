@@ -443,6 +443,96 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
   }
 }
 
+// ======================================================================== z r2c of row pairs
+// Plain batched real transform (mechanics: 9 components): pencil p = rows 2p, 2p+1 packed as
+// a + i b; a tile is 2*PPB consecutive real rows (one bulk copy); the half spectra of the two
+// rows go to rows 2p and 2p+1 of `out` (row pitch ncp).
+template <class T, class C, int PPB, int NG, int NS>
+__global__ void __launch_bounds__(NG *PPB *C::TP, 1)
+    k_zfwd_pairs_tma(const T *in, cx<T> *out, long long nrows, int ncp, const cx<T> *tw_g) {
+  constexpr int N = C::N, TP = C::TP, E = C::E, GT = PPB * TP;
+  constexpr int NP = N + (N >> 3) + 1;
+  static_assert(E % 2 == 0 && GT % 32 == 0, "whole warps per group, even points per thread");
+  MRL_DYN_SMEM(smem_raw);
+  unsigned char *base = align128(smem_raw);
+  T *slots = reinterpret_cast<T *>(base);                                          // [NG][NS][2*PPB*N] real
+  cx<T> *xbuf = reinterpret_cast<cx<T> *>(slots + (size_t)NG * NS * 2 * PPB * N);  // [NG][PPB][NP]
+  uint64_t *full = reinterpret_cast<uint64_t *>(xbuf + (size_t)NG * PPB * NP);
+  const int tid = threadIdx.x;
+  const int g = tid / GT, gt = tid - g * GT;
+  const int pl = gt / TP;
+  int plane;
+  const int t = pair_map<TP>(gt % TP, tid & 31, plane);
+  TwRegs<T, C> twr;
+  twr.init(tw_g, t);
+  const long long npencils = (nrows + 1) / 2;
+  const long long ntiles = (npencils + PPB - 1) / PPB;
+  const long long stride = (long long)gridDim.x * NG;
+  const long long first = (long long)blockIdx.x * NG + g;
+  const int nloc = (first < ntiles) ? (int)((ntiles - first + stride - 1) / stride) : 0;
+  T *gs = slots + (size_t)g * NS * 2 * PPB * N;
+  uint64_t *gb = full + g * NS;
+
+  auto issue = [&](int j) {
+    const long long row0 = (first + j * stride) * PPB * 2;
+    const long long left = nrows - row0;
+    const int rows = left < 2 * PPB ? (int)left : 2 * PPB;
+    const int s = j % NS;
+    const uint32_t bytes = (uint32_t)(rows * N * sizeof(T));
+    mbar_expect_tx(&gb[s], bytes);
+    bulk_load_1d(gs + (size_t)s * 2 * PPB * N, in + row0 * N, bytes, &gb[s]);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < NG * NS; ++s) mbar_init(&full[s], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (gt == 0)
+    for (int j = 0; j < NS && j < nloc; ++j) issue(j);
+
+  const GroupBarrier bar{1 + g, GT};
+  const SmPencil<T> sm{xbuf + (size_t)(g * PPB + pl) * NP};
+  for (int j = 0; j < nloc; ++j) {
+    const int s = j % NS;
+    const long long p = (first + j * stride) * PPB + pl;
+    const long long r0 = 2 * p;
+    const bool ok = p < npencils, ok2 = r0 + 1 < nrows;
+    mbar_wait(&gb[s], (uint32_t)((j / NS) & 1));
+    const T *src = gs + (size_t)s * 2 * PPB * N + (size_t)(2 * pl) * N;
+    cx<T> v[E];
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) v[e] = mk<T>(ok ? src[t + TP * e] : T(0), ok2 ? src[N + t + TP * e] : T(0));
+    bar.sync_release();
+    if (gt == 0 && j + NS < nloc) issue(j + NS);
+    fft_or_skip<T, C>(v, t, sm, twr, bar, NoHook());
+    cx<T> w[E / 2];
+    MRL_UNROLL
+    for (int e = 0; e < E / 2; ++e) w[e] = shfl_cx(v[E - 1 - e], plane);
+    if (t == 0) {
+      w[0] = v[0];
+      MRL_UNROLL
+      for (int e = 1; e < E / 2; ++e) w[e] = v[E - e];
+    }
+    if (ok) {
+      cx<T> *oa = out + r0 * ncp + t, *ob = oa + ncp;
+      MRL_UNROLL
+      for (int e = 0; e < E / 2; ++e) {
+        cx<T> A, B;
+        r2c_separate(v[e], w[e], A, B);
+        oa[TP * e] = A;
+        if (ok2) ob[TP * e] = B;
+      }
+      if (t == 0) {
+        cx<T> A, B;
+        r2c_separate(v[E / 2], v[E / 2], A, B);
+        oa[N / 2] = A;
+        if (ok2) ob[N / 2] = B;
+      }
+    }
+  }
+}
+
 // ======================================================================== P5: z c2r of row pairs
 // A tile is PPB pencils = 2*PPB consecutive half-spectrum rows (one contiguous bulk copy).
 template <class T, class C, int PPB, int NG, int NS>
