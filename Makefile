@@ -1,22 +1,36 @@
 # Builds libmarlin_b200.so (CUDA kernels for sm_100a + the C ABI) in-tree.
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall
 SRC       := marlin_b200/csrc
 BUILD     := marlin_b200/_build
+NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -I$(BUILD)
 LIB       := marlin_b200/libmarlin_b200.so
 CU        := $(wildcard $(SRC)/*.cu)
-OBJ       := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU))
+CPP       := $(wildcard $(SRC)/*.cpp)
+OBJ       := $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU)) $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP))
 HDR       := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/marlin_b200.h
 
+EMBED     := $(BUILD)/mrl_embedded_headers.inc
+EMBED_SRC := $(SRC)/mrl_fft.cuh $(SRC)/mrl_passes.cuh $(SRC)/mrl_tma.cuh $(SRC)/mrl_passes_tma.cuh
+
 all: $(LIB)
+
+$(EMBED): $(EMBED_SRC) tools/embed_headers.py
+	@mkdir -p $(BUILD)
+	python3 tools/embed_headers.py $@ $(EMBED_SRC)
+
+$(BUILD)/mrl_expr_zfwd.o: $(EMBED)
 
 $(BUILD)/%.o: $(SRC)/%.cu $(HDR)
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+$(BUILD)/%.o: $(SRC)/%.cpp $(HDR)
+	@mkdir -p $(BUILD)
+	g++ -std=c++17 -O2 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@
+
 $(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -ldl
 
 emu: tests/emu/_build/emu_fft_test
 tests/emu/_build/emu_fft_test: tests/emu/emu_fft_test.cpp tests/emu/cuda_emu.h $(wildcard $(SRC)/*.cuh)

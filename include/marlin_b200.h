@@ -99,6 +99,53 @@ int mrl_ab_update(mrl_context *ctx, void *ubar_dev, const void *cbar_dev, const 
 enum mrl_reduce_op { MRL_SUM = 0, MRL_MIN = 1, MRL_MAX = 2, MRL_SUMSQ = 3 };
 int mrl_reduce(mrl_context *ctx, int op, const void *real_dev, int64_t count, double *host_out);
 
+/* ---- runtime expressions: ParsedCompute (src/tensor_computes/ParsedCompute.C:24-47 parameters,
+ *      :50-181 constructor, :184-265 computeBuffer) and ParsedJITTensor
+ *      (src/utils/ParsedJITTensor.C:22-156: parse, differentiate, compile, eval).
+ * The expression is parsed, differentiated w.r.t. `derivatives` in order, simplified, lowered to
+ * ONE CUDA kernel and compiled for sm_100a with NVRTC.  Grammar, simplification and derivative rules
+ * are the reference's (include/utils/MarlinExpressionParser.h:383-427,
+ * src/utils/MarlinExpressionParser.C:51-1104).                                              */
+typedef struct mrl_expr mrl_expr;
+enum mrl_var_layout {
+  MRL_VAR_REAL = 0,          /* real field, real shape [nx][ny][nz]            */
+  MRL_VAR_RECIP_REAL = 1,    /* real field, reciprocal shape [nx][ny][nz/2+1]   */
+  MRL_VAR_RECIP_COMPLEX = 2, /* complex field, reciprocal shape                 */
+  MRL_VAR_SCALAR = 3,        /* one real value in device memory (0-d tensor)    */
+  MRL_VAR_REAL_COMPLEX = 4   /* complex field, real shape                       */
+};
+enum mrl_expand { MRL_EXPAND_NONE = 0, MRL_EXPAND_REAL = 1, MRL_EXPAND_RECIPROCAL = 2 };
+typedef struct mrl_expr_desc {
+  const char *expression;
+  int nvars;                         /* `inputs`                                             */
+  const char *const *var_names;
+  const int *var_layouts;            /* mrl_var_layout per input (NULL = all MRL_VAR_REAL)    */
+  int nderivatives;                  /* `derivatives`, applied in order                      */
+  const char *const *derivatives;
+  int nconstants;                    /* `constant_names` with already evaluated values       */
+  const char *const *constant_names;
+  const double *constant_values;
+  int extra_symbols;                 /* x y z kx ky kz k2 t pi e i                           */
+  int expand;                        /* mrl_expand                                           */
+} mrl_expr_desc;
+int mrl_expr_compile(mrl_context *ctx, const mrl_expr_desc *desc, mrl_expr **out);
+int mrl_expr_destroy(mrl_expr *e);
+/* space: 0 = a single value (all-constant expression), 1 = real shape, 2 = reciprocal shape */
+int mrl_expr_result(const mrl_expr *e, int *space, int *is_complex);
+/* toString() of the AST after derivatives + simplification (reference formatting) */
+int mrl_expr_string(const mrl_expr *e, char *buf, size_t cap);
+/* out[p] = f(inputs[0][p], ..., t); inputs in `inputs` order (unused ones may be NULL) */
+int mrl_expr_eval(mrl_expr *e, const void *const *inputs_dev, double t, void *out_dev);
+/* Host-only pieces (no device needed): the simplified string; a `constant_expressions` value
+ * (libMesh FParser stand-in, ParsedCompute.C:104-123; may use pi, e and the given constants);
+ * and a dry run that generates the CUDA source and compiles it with NVRTC for sm_100a.     */
+int mrl_expr_simplified(const mrl_expr_desc *desc, char *buf, size_t cap);
+int mrl_expr_constant(const char *expression, int nconst, const char *const *names, const double *values, double *out);
+int mrl_expr_check(const mrl_expr_desc *desc, int precision, char *cuda_source_buf, size_t cap);
+/* same dry run for the first pass of the fused split plan specialised for the expression (last-axis
+ * length n; staged_var as mrl_split_desc.nonlin_var) */
+int mrl_expr_check_fused(const mrl_expr_desc *desc, int precision, int n, int staged_var);
+
 /* ---- fused semi-implicit substep (one solver variable) ---------------------------------
  * Replaces, for the canonical split-operator pattern
  *     g   = F(c)                      ParsedCompute   (src/tensor_computes/ParsedCompute.C:184)
@@ -116,7 +163,8 @@ typedef struct mrl_split_desc {
   int nonlin_kind;
   double nonlin_params[4];
   void *nonlin_expr;        /* mrl_expr*, when nonlin_kind == MRL_NONLIN_EXPR */
-  int M_closed_form;        /* 1: Mbar = -k2*M_factor computed on the fly; 0: read M_real_dev */
+  int M_closed_form;        /* 1: Mbar = -k2*M_factor computed on the fly; 0: read M_real_dev;
+                               2: Mbar = 1 (the nonlinear term is fft(g) itself)              */
   double M_factor;
   const void *M_real_dev;   /* real, reciprocal shape */
   int has_L;                /* linear_reciprocal given ("0" in the input = none) */
@@ -125,6 +173,11 @@ typedef struct mrl_split_desc {
   const void *L_real_dev;
   int history;              /* old nonlinear terms kept = max(predictor_order, corrector_order) - 1 */
   void *g_out_real_dev;     /* optional: receives g = F(c) each substep (NULL = not materialised) */
+  /* MRL_NONLIN_EXPR only: the expression's inputs, in its `inputs` order.  nonlin_var is the index
+   * of the solver variable among them (its value arrives through the pass's staged tile; -1: the
+   * variable is not an input); the other inputs are real-space real fields read in place.      */
+  int nonlin_var;
+  const void *nonlin_inputs_dev[16];
 } mrl_split_desc;
 
 int mrl_split_plan_create(mrl_context *ctx, const mrl_split_desc *desc, mrl_split_plan **out);
@@ -132,6 +185,15 @@ int mrl_split_plan_destroy(mrl_split_plan *plan);
 /* One predictor substep, c updated in place.  beta[0] multiplies the new nonlinear term,
  * beta[1..nold] the stored old ones (newest first); nold <= states currently stored.      */
 int mrl_split_substep(mrl_split_plan *plan, void *c_real_dev, double dt, const double *beta, int nold);
+/* The same substep in two halves, for solvers with several coupled variables
+ * (SplitOperatorBase::getVariables, src/tensor_solver/SplitOperatorBase.C:39-64): the reference
+ * evaluates the whole root compute (every variable's nonlinearity, from the OLD fields) before it
+ * updates any variable, so call mrl_split_forward (passes P1-P2) on every plan first, then
+ * mrl_split_finish (P3-P5, writes c) on every plan.                                          */
+int mrl_split_forward(mrl_split_plan *plan, const void *c_real_dev);
+int mrl_split_finish(mrl_split_plan *plan, void *c_real_dev, double dt, const double *beta, int nold);
+/* sub-time `t` seen by an MRL_NONLIN_EXPR expression (TensorSolver.C:95, _sub_time) */
+int mrl_split_set_time(mrl_split_plan *plan, double t);
 /* TensorBuffer<T>::advanceState (include/tensor_buffers/TensorBuffer.h:64-79): the newest
  * nonlinear term becomes old state 0.  Returns the number of stored states through *stored. */
 int mrl_split_advance_state(mrl_split_plan *plan, int *stored);

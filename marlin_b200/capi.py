@@ -40,6 +40,7 @@ class SplitDesc(C.Structure):
         ("M_closed_form", C.c_int), ("M_factor", C.c_double), ("M_real_dev", C.c_void_p),
         ("has_L", C.c_int), ("L_closed_form", C.c_int), ("L_factor", C.c_double),
         ("L_real_dev", C.c_void_p), ("history", C.c_int), ("g_out_real_dev", C.c_void_p),
+        ("nonlin_var", C.c_int), ("nonlin_inputs_dev", C.c_void_p * 16),
     ]
 
 
@@ -188,17 +189,20 @@ class SplitPlan:
     canonical Cahn-Hilliard compute graph)."""
 
     def __init__(self, ctx, double_well=None, expr=None, M_factor=None, M_buffer=None, L_factor=None,
-                 L_buffer=None, has_L=True, history=1, g_out=None):
+                 L_buffer=None, has_L=True, history=1, g_out=None, expr_var=0, expr_inputs=(), M_identity=False):
         self.ctx = ctx
         d = SplitDesc()
         if expr is not None:
             d.nonlin_kind = NONLIN_EXPR
             d.nonlin_expr = expr.h
+            d.nonlin_var = int(expr_var)
+            for i, t in enumerate(expr_inputs):
+                d.nonlin_inputs_dev[i] = t.data_ptr() if t is not None else None
         else:
             d.nonlin_kind = NONLIN_DOUBLE_WELL
             A, a, b = double_well
             d.nonlin_params = (C.c_double * 4)(A, a, b, 0.0)
-        d.M_closed_form = int(M_buffer is None)
+        d.M_closed_form = 2 if M_identity else int(M_buffer is None)
         d.M_factor = float(M_factor or 0.0)
         d.M_real_dev = M_buffer.data_ptr() if M_buffer is not None else None
         d.has_L = int(has_L)
@@ -207,7 +211,7 @@ class SplitPlan:
         d.L_real_dev = L_buffer.data_ptr() if L_buffer is not None else None
         d.history = history
         d.g_out_real_dev = g_out.data_ptr() if g_out is not None else None
-        self._keep = (M_buffer, L_buffer, g_out, expr)
+        self._keep = (M_buffer, L_buffer, g_out, expr, tuple(expr_inputs))
         self.h = C.c_void_p()
         _ck(lib().mrl_split_plan_create(ctx.h, C.byref(d), C.byref(self.h)))
         self.launches_per_substep = lib().mrl_split_launches_per_substep(self.h)
@@ -215,6 +219,16 @@ class SplitPlan:
     def substep(self, c, dt, beta, nold):
         b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
         _ck(lib().mrl_split_substep(self.h, _p(c), C.c_double(dt), b, int(nold)))
+
+    def forward(self, c):
+        _ck(lib().mrl_split_forward(self.h, _p(c)))
+
+    def finish(self, c, dt, beta, nold):
+        b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
+        _ck(lib().mrl_split_finish(self.h, _p(c), C.c_double(dt), b, int(nold)))
+
+    def set_time(self, t):
+        _ck(lib().mrl_split_set_time(self.h, C.c_double(t)))
 
     def substep_timed(self, c, dt, beta, nold):
         b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
@@ -233,6 +247,121 @@ class SplitPlan:
     def close(self):
         if self.h:
             lib().mrl_split_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- runtime expressions (ParsedCompute) ------------------------------------------------------
+VAR_REAL, VAR_RECIP_REAL, VAR_RECIP_COMPLEX, VAR_SCALAR, VAR_REAL_COMPLEX = 0, 1, 2, 3, 4
+EXPAND_NONE, EXPAND_REAL, EXPAND_RECIPROCAL = 0, 1, 2
+
+
+class ExprDesc(C.Structure):
+    _fields_ = [("expression", C.c_char_p), ("nvars", C.c_int), ("var_names", C.POINTER(C.c_char_p)),
+                ("var_layouts", C.POINTER(C.c_int)), ("nderivatives", C.c_int),
+                ("derivatives", C.POINTER(C.c_char_p)), ("nconstants", C.c_int),
+                ("constant_names", C.POINTER(C.c_char_p)), ("constant_values", C.POINTER(C.c_double)),
+                ("extra_symbols", C.c_int), ("expand", C.c_int)]
+
+
+def _expr_desc(expression, inputs=(), layouts=None, derivatives=(), constants=None, extra_symbols=False,
+               expand=EXPAND_NONE):
+    constants = dict(constants or {})
+    d = ExprDesc()
+    d.expression = expression.encode()
+    keep = [d.expression]
+
+    def strs(xs):
+        arr = (C.c_char_p * max(len(xs), 1))(*[x.encode() for x in xs])
+        keep.append(arr)
+        return C.cast(arr, C.POINTER(C.c_char_p))
+
+    d.nvars = len(inputs)
+    d.var_names = strs(list(inputs))
+    lay = (C.c_int * max(len(inputs), 1))(*[int(x) for x in (layouts or [VAR_REAL] * len(inputs))])
+    keep.append(lay)
+    d.var_layouts = C.cast(lay, C.POINTER(C.c_int))
+    d.nderivatives = len(derivatives)
+    d.derivatives = strs(list(derivatives))
+    d.nconstants = len(constants)
+    d.constant_names = strs(list(constants.keys()))
+    vals = (C.c_double * max(len(constants), 1))(*[float(v) for v in constants.values()])
+    keep.append(vals)
+    d.constant_values = C.cast(vals, C.POINTER(C.c_double))
+    d.extra_symbols = int(bool(extra_symbols))
+    d.expand = int(expand)
+    return d, keep
+
+
+def expr_simplified(expression, **kw):
+    """Host only: toString() of the parsed, differentiated, simplified expression."""
+    d, keep = _expr_desc(expression, **kw)
+    buf = C.create_string_buffer(1 << 16)
+    _ck(lib().mrl_expr_simplified(C.byref(d), buf, C.c_size_t(len(buf))))
+    return buf.value.decode()
+
+
+def expr_constant(expression, constants=None):
+    """Host only: value of one `constant_expressions` entry (may use earlier constants, pi, e)."""
+    constants = dict(constants or {})
+    names = (C.c_char_p * max(len(constants), 1))(*[k.encode() for k in constants])
+    vals = (C.c_double * max(len(constants), 1))(*[float(v) for v in constants.values()])
+    out = C.c_double()
+    _ck(lib().mrl_expr_constant(expression.encode(), len(constants), names, vals, C.byref(out)))
+    return out.value
+
+
+def expr_check(expression, precision=F64, **kw):
+    """Host only: generate the CUDA source of the expression kernel and compile it with NVRTC for
+    sm_100a (no device needed).  Returns the generated source."""
+    d, keep = _expr_desc(expression, **kw)
+    buf = C.create_string_buffer(1 << 18)
+    _ck(lib().mrl_expr_check(C.byref(d), int(precision), buf, C.c_size_t(len(buf))))
+    return buf.value.decode()
+
+
+def expr_check_fused(expression, n, staged_var=0, precision=F64, **kw):
+    """Host only: NVRTC-compile the first FFT pass specialised for the expression (axis length n)."""
+    d, keep = _expr_desc(expression, **kw)
+    _ck(lib().mrl_expr_check_fused(C.byref(d), int(precision), int(n), int(staged_var)))
+
+
+class Expr:
+    """One compiled ParsedCompute expression on a context's device."""
+
+    def __init__(self, ctx, expression, inputs=(), layouts=None, derivatives=(), constants=None,
+                 extra_symbols=False, expand=EXPAND_NONE):
+        self.ctx = ctx
+        self.inputs = list(inputs)
+        d, keep = _expr_desc(expression, inputs=inputs, layouts=layouts, derivatives=derivatives,
+                             constants=constants, extra_symbols=extra_symbols, expand=expand)
+        self.h = C.c_void_p()
+        _ck(lib().mrl_expr_compile(ctx.h, C.byref(d), C.byref(self.h)))
+        sp, cplx = C.c_int(), C.c_int()
+        _ck(lib().mrl_expr_result(self.h, C.byref(sp), C.byref(cplx)))
+        self.space, self.is_complex = sp.value, bool(cplx.value)
+
+    def __str__(self):
+        buf = C.create_string_buffer(1 << 16)
+        _ck(lib().mrl_expr_string(self.h, buf, C.c_size_t(len(buf))))
+        return buf.value.decode()
+
+    def eval(self, tensors=(), t=0.0):
+        ctx = self.ctx
+        shape = [1] if self.space == 0 else (ctx.rshape if self.space == 2 else ctx.shape)
+        out = torch.empty(shape, dtype=ctx.cdtype if self.is_complex else ctx.rdtype, device=ctx.device)
+        arr = (C.c_void_p * max(len(tensors), 1))(*[x.data_ptr() if x is not None else None for x in tensors])
+        _ck(lib().mrl_expr_eval(self.h, arr, C.c_double(t), _p(out)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().mrl_expr_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

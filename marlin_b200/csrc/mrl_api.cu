@@ -509,7 +509,7 @@ extern "C" int mrl_split_plan_create(mrl_context *ctx, const mrl_split_desc *d, 
   // whenever every axis runs on the TMA kernels: aligned 128-byte row segments are what lets
   // the strided passes stream at full HBM rate (measured 4.4 -> 6.1 TB/s at 512^3).
   const int nc = ctx->nr[ctx->dim - 1];
-  bool all_tma = tma_enabled() && d->nonlin_kind == MRL_NONLIN_DOUBLE_WELL && !getenv("MRL_NOPAD");
+  bool all_tma = tma_enabled() && !getenv("MRL_NOPAD");
   for (int a = 0; a < ctx->dim; ++a) all_tma = all_tma && tma_size(ctx->n[a]);
   const int per128 = (int)(128 / esz);
   p->ncp = all_tma ? (nc + per128 - 1) / per128 * per128 : nc;
@@ -569,7 +569,8 @@ extern "C" int mrl_split_advance_state(mrl_split_plan *p, int *stored) {
     if (ev) CK(cudaEventRecord(ev[nev++], ctx->stream));               \
   } while (0)
 template <class T>
-static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *beta, int nold, cudaEvent_t *ev = nullptr) {
+static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *beta, int nold, cudaEvent_t *ev = nullptr,
+                              int phases = 3) {
   mrl_context *ctx = p->ctx;
   int nev = 0;
   const mrl_split_desc &d = p->desc;
@@ -614,6 +615,7 @@ static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *
   };
 
   PASS_MARK();
+  if (phases & 1) {
   // P1: last-axis r2c of (c + i F(c))
   if (d.nonlin_kind == MRL_NONLIN_DOUBLE_WELL) {
     NonlinDesc nlz{0, {d.nonlin_params[0], d.nonlin_params[1], d.nonlin_params[2], 0}};
@@ -623,7 +625,9 @@ static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *
       te = launch_zfwd_nonlin<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, B, rows, nl, nlz, (const cx<T> *)twl, make_fft_plan(nl));
     CK(te);
   } else {
-    if ((rc = mrl_expr_launch_zfwd(ctx, d.nonlin_expr, c, d.g_out_real_dev, A, B, rows, nl))) return rc;
+    if ((rc = mrl_expr_launch_zfwd(ctx, d.nonlin_expr, d.nonlin_var, d.nonlin_inputs_dev, p->time, c, d.g_out_real_dev, A, B,
+                                   rows, nl, ncp)))
+      return rc;
   }
   PASS_MARK();
   // P2: middle axis forward on both fields (3-D only)
@@ -631,6 +635,8 @@ static int split_substep_impl(mrl_split_plan *p, T *c, double dt, const double *
     if ((rc = ypass(2, 0))) return rc;
     PASS_MARK();
   }
+  }
+  if (!(phases & 2)) return MRL_OK;
   // P3: first axis forward on both + k-space update + first axis inverse
   FusedIO<T> io;
   memset(&io, 0, sizeof io);
@@ -696,6 +702,28 @@ extern "C" int mrl_split_substep(mrl_split_plan *p, void *c, double dt, const do
   CK(cudaSetDevice(p->ctx->device));
   return p->ctx->precision == MRL_F64 ? split_substep_impl<double>(p, (double *)c, dt, beta, nold)
                                       : split_substep_impl<float>(p, (float *)c, dt, beta, nold);
+}
+
+extern "C" int mrl_split_forward(mrl_split_plan *p, const void *c) {
+  if (!p || !c) return mrl_fail(MRL_ERR_INVALID, "mrl_split_forward: bad arguments");
+  CK(cudaSetDevice(p->ctx->device));
+  const double b0[5] = {1, 0, 0, 0, 0};
+  return p->ctx->precision == MRL_F64 ? split_substep_impl<double>(p, (double *)c, 0.0, b0, 0, nullptr, 1)
+                                      : split_substep_impl<float>(p, (float *)c, 0.0, b0, 0, nullptr, 1);
+}
+
+extern "C" int mrl_split_finish(mrl_split_plan *p, void *c, double dt, const double *beta, int nold) {
+  if (!p || !c || !beta || nold < 0) return mrl_fail(MRL_ERR_INVALID, "mrl_split_finish: bad arguments");
+  if (nold > p->stored) return mrl_fail(MRL_ERR_INVALID, "mrl_split_finish: %d old states requested, %d stored", nold, p->stored);
+  CK(cudaSetDevice(p->ctx->device));
+  return p->ctx->precision == MRL_F64 ? split_substep_impl<double>(p, (double *)c, dt, beta, nold, nullptr, 2)
+                                      : split_substep_impl<float>(p, (float *)c, dt, beta, nold, nullptr, 2);
+}
+
+extern "C" int mrl_split_set_time(mrl_split_plan *p, double t) {
+  if (!p) return mrl_fail(MRL_ERR_INVALID, "null plan");
+  p->time = t;
+  return MRL_OK;
 }
 
 extern "C" int mrl_split_substep_timed(mrl_split_plan *p, void *c, double dt, const double *beta, int nold, float *pass_ms) {

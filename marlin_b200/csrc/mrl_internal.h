@@ -49,6 +49,7 @@ struct mrl_split_plan {
   std::vector<void *> ring;         // history+1 nonlinear-term slots
   int cur = 0, stored = 0;
   int ncp = 0;                      // row pitch of the work spectra (>= n_last/2+1)
+  double time = 0.0;                // sub-time seen by an expression nonlinearity
 };
 
 struct mrl_slab_plan {
@@ -79,6 +80,6 @@ template <class T>
 cudaError_t launch_reduce(const LaunchCtx &lc, int op, const T *in, long long count, double *partials, int nblk);
 }  // namespace mrl
 
-// expression-compiled first pass (mrl_expr.cpp); returns MRL status
-int mrl_expr_launch_zfwd(mrl_context *ctx, void *expr, const void *c, void *g_out, void *outC, void *outG, long long rows,
-                         int n);
+// expression-specialised first pass (mrl_expr_zfwd.cu); returns MRL status
+int mrl_expr_launch_zfwd(mrl_context *ctx, void *expr, int staged_var, const void *const *inputs, double t, const void *c,
+                         void *g_out, void *outC, void *outG, long long rows, int n, int ncp);

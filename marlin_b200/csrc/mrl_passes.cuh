@@ -151,7 +151,7 @@ template <class T, class F> struct ZLoadFused {
   F f;
   MRL_DI cx<T> ld(long long p, int j) const {
     const T a = c[p * n + j];
-    const T b = f(a);
+    const T b = f(a, p * n + j);
     if (mu_out) mu_out[p * n + j] = b;
     return mk<T>(a, b);
   }
@@ -361,7 +361,7 @@ template <class T> struct SpectralUpdate {
   }
   MRL_DI cx<T> apply(int o, int j, int col, long long off, cx<T> chat, cx<T> ghat) const {
     const T kk = k2(o, j, col);
-    const T M = closed_M ? (-kk * Mfac) : Mbuf[off];
+    const T M = closed_M == 1 ? (-kk * Mfac) : closed_M == 2 ? T(1) : Mbuf[off];
     const cx<T> N = mk<T>(M * ghat.x, M * ghat.y);
     if (Nout) Nout[off] = N;
     cx<T> u = mk<T>(chat.x + b0 * N.x, chat.y + b0 * N.y);
@@ -544,7 +544,7 @@ template <class T> __global__ void k_mul_rc(cx<T> *out, const T *a, const cx<T> 
 // benchmarks/01_spinodal_decomposition/1a_solver.i: A=5,a=0.3,b=0.7)
 template <class T> struct DoubleWellDeriv {
   T A, a, b;
-  MRL_DI T operator()(T c) const {
+  MRL_DI T operator()(T c, long long = 0) const {
     const T p = c - a, q = b - c;
     return T(2) * A * p * q * (q - p);
   }

@@ -212,7 +212,7 @@ template <class T> struct SpectralUpdate2 {
   // chat, ghat: transformed variable / nonlinearity; nold0: newest old nonlinear term
   MRL_DI cx<T> apply(T kr, T kcol, long long off, cx<T> chat, cx<T> ghat, cx<T> nold0) const {
     const T kk = kr * kr + kcol;
-    const T M = closed_M ? (-kk * Mfac) : Mbuf[off];
+    const T M = closed_M == 1 ? (-kk * Mfac) : closed_M == 2 ? T(1) : Mbuf[off];
     const cx<T> N = mk<T>(M * ghat.x, M * ghat.y);
     if (Nout) Nout[off] = N;
     cx<T> u = mk<T>(chat.x + b0 * N.x, chat.y + b0 * N.y);
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     MRL_UNROLL
     for (int e = 0; e < E; ++e) {
       const T a = ok ? src[t + TP * e] : T(0);
-      const T b = f(a);
+      const T b = ok ? f(a, p * N + t + TP * e) : T(0);
       if (mu_out && ok) mu_out[p * N + t + TP * e] = b;
       v[e] = mk<T>(a, b);
     }

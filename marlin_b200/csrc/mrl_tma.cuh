@@ -5,7 +5,14 @@
 #pragma once
 #include "mrl_fft.cuh"
 
-#if !defined(MRL_EMU)
+#if defined(__CUDACC_RTC__)
+// NVRTC (expression-specialised passes): no system headers; the tensor map is an opaque 128-byte blob
+typedef unsigned long long uint64_t;
+typedef unsigned int uint32_t;
+typedef unsigned long size_t;
+struct alignas(64) CUtensorMap_st { unsigned long long opaque[16]; };
+typedef CUtensorMap_st CUtensorMap;
+#elif !defined(MRL_EMU)
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched at run time, no -lcuda)
 #include <stdint.h>
 #endif
