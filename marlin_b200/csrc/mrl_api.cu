@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -141,6 +142,24 @@ int mrl_context::scratch(size_t bytes, void **out) {
   return MRL_OK;
 }
 
+// Live contexts: handles derived from a context (plans, expressions) may outlive it when a host
+// language finalises objects out of order; their destroy functions must not touch a freed context.
+static std::mutex g_live_mu;
+static std::set<const mrl_context *> g_live;
+void mrl_quiesce(const mrl_context *ctx) {
+  bool alive;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    alive = g_live.count(ctx) != 0;
+  }
+  if (alive) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  } else {
+    cudaDeviceSynchronize();
+  }
+}
+
 extern "C" int mrl_create(int device, int precision, mrl_context **out) {
   if (!out || (precision != MRL_F64 && precision != MRL_F32)) return mrl_fail(MRL_ERR_INVALID, "mrl_create: bad arguments");
   int ndev = 0;
@@ -159,12 +178,20 @@ extern "C" int mrl_create(int device, int precision, mrl_context **out) {
   c->precision = precision;
   c->stream = 0;
   c->sm_count = prop.multiProcessorCount;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    g_live.insert(c);
+  }
   *out = c;
   return MRL_OK;
 }
 
 extern "C" int mrl_destroy(mrl_context *ctx) {
   if (!ctx) return MRL_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    if (!g_live.erase(ctx)) return mrl_fail(MRL_ERR_INVALID, "mrl_destroy: not a live context");
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto &kv : ctx->tw) cudaFree(kv.second);
@@ -535,7 +562,7 @@ extern "C" int mrl_split_plan_create(mrl_context *ctx, const mrl_split_desc *d, 
 
 extern "C" int mrl_split_plan_destroy(mrl_split_plan *p) {
   if (!p) return MRL_OK;
-  cudaStreamSynchronize(p->ctx->stream);
+  mrl_quiesce(p->ctx);
   cudaFree(p->A);
   for (void *q : p->ring) cudaFree(q);
   delete p;
@@ -852,8 +879,7 @@ extern "C" int mrl_slab_plan_create(mrl_context *ctx, const mrl_split_desc *d, v
 
 extern "C" int mrl_slab_plan_destroy(mrl_slab_plan *p) {
   if (!p) return MRL_OK;
-  cudaSetDevice(p->ctx->device);
-  cudaStreamSynchronize(p->ctx->stream);
+  mrl_quiesce(p->ctx);
   for (void *q : p->ring) cudaFree(q);
   for (void *q : p->opened) cudaIpcCloseMemHandle(q);
   cudaFree(p->peer_recv_tab);

@@ -252,6 +252,12 @@ struct Gen {
           const std::string a = l.second == TC ? l.first : real(l), b = r.second == TC ? r.first : real(r);
           return {"(" + a + " " + op + " " + b + ")", TC};
         }
+        if (l.second == TB && r.second == TB) {
+          // ATen arithmetic on two bool tensors stays bool: add = or, mul = and, sub is an error
+          if (op == "+") return {"(" + l.first + " || " + r.first + ")", TB};
+          if (op == "*") return {"(" + l.first + " && " + r.first + ")", TB};
+          if (op == "-") throw std::runtime_error("Subtraction, the `-` operator, with two bool tensors is not supported");
+        }
         return {"(" + real(l) + " " + op + " " + real(r) + ")", TR};
       }
       case Kind::Un: {
@@ -608,7 +614,7 @@ extern "C" int mrl_expr_compile(mrl_context *ctx, const mrl_expr_desc *d, mrl_ex
 
 extern "C" int mrl_expr_destroy(mrl_expr *e) {
   if (!e) return MRL_OK;
-  if (e->ctx) cudaStreamSynchronize(e->ctx->stream);
+  if (e->ctx) mrl_quiesce(e->ctx);
   mrlx_module_unload(e->module);
   mrlx_module_unload(e->zfwd_module);
   delete e;

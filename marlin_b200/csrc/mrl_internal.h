@@ -10,6 +10,9 @@
 #include "mrl_launch.h"
 
 int mrl_fail(int code, const char *fmt, ...);
+struct mrl_context;
+// waits for the context's stream (or the whole device if the context is already destroyed)
+void mrl_quiesce(const mrl_context *ctx);
 
 struct mrl_context {
   int device = 0;

@@ -48,8 +48,7 @@ struct mrl_mech_plan {
 
 extern "C" int mrl_mech_plan_destroy(mrl_mech_plan *p) {
   if (!p) return MRL_OK;
-  cudaSetDevice(p->ctx->device);
-  cudaStreamSynchronize(p->ctx->stream);
+  mrl_quiesce(p->ctx);
   for (void *q : {p->spec, p->tmp, p->rhs, p->x, p->r, p->p, p->Ap, p->Fk, (void *)p->scal, (void *)p->partials}) cudaFree(q);
   if (p->host) cudaFreeHost(p->host);
   delete p;
