@@ -13,7 +13,21 @@ HDR       := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/marlin_b200
 EMBED     := $(BUILD)/mrl_embedded_headers.inc
 EMBED_SRC := $(SRC)/mrl_fft.cuh $(SRC)/mrl_passes.cuh $(SRC)/mrl_tma.cuh $(SRC)/mrl_passes_tma.cuh
 
-all: $(LIB)
+# host side: MOOSE-style objects (TensorProblem / TensorOperator / TensorSolver ...) + the driver executable
+HOST_SRC  := $(wildcard host/src/*.C) $(wildcard host/shim/*.C)
+HOST_OBJ  := $(patsubst host/%.C,host/_build/%.o,$(HOST_SRC))
+HOST_HDR  := $(wildcard host/include/*.h) $(wildcard host/shim/*.h) include/marlin_b200.h
+HOST_FLAGS:= -std=c++17 -O2 -g -fPIC -Wall -Wno-unused-function -ffp-contract=off -Ihost/include -Ihost/shim -Iinclude
+APP       := marlin_b200/marlin_b200-opt
+
+all: $(LIB) $(APP)
+
+host/_build/%.o: host/%.C $(HOST_HDR)
+	@mkdir -p $(dir $@)
+	g++ $(HOST_FLAGS) -c $< -o $@
+
+$(APP): $(HOST_OBJ) $(LIB)
+	g++ -o $@ $(HOST_OBJ) -Lmarlin_b200 -lmarlin_b200 -Wl,-rpath,'$$ORIGIN' -Wl,-rpath-link,/usr/local/cuda/lib64
 
 $(EMBED): $(EMBED_SRC) tools/embed_headers.py
 	@mkdir -p $(BUILD)
@@ -38,5 +52,5 @@ tests/emu/_build/emu_fft_test: tests/emu/emu_fft_test.cpp tests/emu/cuda_emu.h $
 	g++ -std=c++17 -O1 -Itests/emu -o $@ $<
 
 clean:
-	rm -rf $(BUILD) $(LIB) tests/emu/_build
+	rm -rf $(BUILD) $(LIB) $(APP) host/_build tests/emu/_build
 .PHONY: all clean emu

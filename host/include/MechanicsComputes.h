@@ -1,0 +1,73 @@
+// de Geus FFT mechanics operator classes (see host/src/MechanicsComputes.C for reference citations).
+#pragma once
+#include "TensorOperatorBase.h"
+
+class RankTwoIdentity : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit RankTwoIdentity(const InputParameters &parameters);
+  void computeBuffer() override;
+};
+
+class MacroscopicShearTensor : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit MacroscopicShearTensor(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const marlin::Tensor &_tF;
+};
+
+class PhaseMechanicsTest : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit PhaseMechanicsTest(const InputParameters &parameters);
+  void computeBuffer() override;
+};
+
+// owns an mrl_mech_plan bound to one pair of (K, mu) fields
+class MechPlanHolder {
+public:
+  ~MechPlanHolder();
+  mrl_mech_plan *get(const DomainAction &domain, const mrl_mech_desc &desc, const marlin::Tensor &K, const marlin::Tensor &mu);
+  void reset();
+
+private:
+  mrl_mech_plan *_plan = nullptr;
+  const void *_K = nullptr, *_mu = nullptr;
+};
+
+class HyperElasticIsotropic : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit HyperElasticIsotropic(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const marlin::Tensor &_tF;
+  const marlin::Tensor &_tmu;
+  const marlin::Tensor &_tK;
+  MechPlanHolder _plan;
+};
+
+class FFTMechanics : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit FFTMechanics(const InputParameters &parameters);
+  void computeBuffer() override;
+  void check() override;
+  const mrl_mech_stats &stats() const { return _stats; }
+
+protected:
+  const marlin::Tensor &_tK;
+  const marlin::Tensor &_tmu;
+  const marlin::Tensor &_tF;
+  const marlin::Tensor &_tP;
+  TensorOperatorBase &_constitutive_model;
+  const marlin::Tensor *const _applied_macroscopic_strain;
+  const bool _verbose;
+  mrl_mech_desc _desc;
+  mrl_mech_stats _stats;
+  MechPlanHolder _plan;
+};

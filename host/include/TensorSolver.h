@@ -1,0 +1,125 @@
+// TensorSolver family: substep loop, split-operator variables, the concrete integrators.
+// Host mirror of include/tensor_solver/{TensorSolver,SplitOperatorBase,ExplicitSolverBase,
+// AdamsBashforthMoulton,ForwardEulerSolver,ETDRK4Solver}.h and their sources
+// (src/tensor_solver/TensorSolver.C:15-110, SplitOperatorBase.C:14-64, ExplicitSolverBase.C,
+//  AdamsBashforthMoulton.C:20-178, ForwardEulerSolver.C:29-38, ETDRK4Solver.C:29-115).
+#pragma once
+#include <array>
+
+#include "TensorOperatorBase.h"
+
+class TensorSolver : public TensorOperatorBase {
+public:
+  static InputParameters validParams();
+  explicit TensorSolver(const InputParameters &parameters);
+  void computeBuffer() override;
+  void updateDependencies() override;
+
+protected:
+  virtual void substep() = 0;
+  const std::vector<marlin::Tensor> &getBufferOld(const std::string &param, unsigned int max_states);
+  const std::vector<marlin::Tensor> &getBufferOldByName(const TensorInputBufferName &buffer_name, unsigned int max_states);
+  void forwardBuffers();
+
+  unsigned int _substeps;
+  unsigned int _substep = 0;
+  Real &_sub_dt;
+  Real &_sub_time;
+  const Real &_dt;
+  const Real &_dt_old;
+  const Real &_problem_time_old;
+  std::shared_ptr<TensorOperatorBase> _compute;
+  std::vector<std::pair<marlin::Tensor *, const marlin::Tensor *>> _forwarded_buffers;
+};
+
+class SplitOperatorBase : public TensorSolver {
+public:
+  static InputParameters validParams();
+  explicit SplitOperatorBase(const InputParameters &parameters);
+
+  struct Variable {
+    marlin::Tensor &_buffer;
+    const marlin::Tensor &_reciprocal_buffer;
+    const marlin::Tensor *_linear_reciprocal;
+    const marlin::Tensor &_nonlinear_reciprocal;
+    const std::vector<marlin::Tensor> &_old_nonlinear_reciprocal;
+    // names, used by the fused-plan pattern matcher
+    std::string _buffer_name, _reciprocal_name, _linear_name, _nonlinear_name;
+  };
+
+protected:
+  void getVariables(unsigned int history_size);
+  std::vector<Variable> _variables;
+};
+
+class ExplicitSolverBase : public TensorSolver {
+public:
+  static InputParameters validParams();
+  explicit ExplicitSolverBase(const InputParameters &parameters);
+  struct Variable {
+    marlin::Tensor &_buffer;
+    const marlin::Tensor &_reciprocal_buffer;
+    const marlin::Tensor &_time_derivative_reciprocal;
+  };
+
+protected:
+  std::vector<Variable> _variables;
+};
+
+class ForwardEulerSolver : public ExplicitSolverBase {
+public:
+  static InputParameters validParams();
+  explicit ForwardEulerSolver(const InputParameters &parameters);
+
+protected:
+  void substep() override;
+};
+
+struct mrl_split_plan;
+struct mrl_expr;
+
+class AdamsBashforthMoulton : public SplitOperatorBase {
+public:
+  static InputParameters validParams();
+  explicit AdamsBashforthMoulton(const InputParameters &parameters);
+  ~AdamsBashforthMoulton() override;
+  static constexpr std::size_t max_order = 5;
+  void check() override;
+  bool fused() const { return !_plans.empty(); }
+
+protected:
+  void substep() override;
+  void fusedSubstep();
+  void tryBuildFusedPlans();
+  void decideFusion();
+  bool _fusion_decided = false;
+
+  std::size_t _predictor_order;
+  std::size_t _corrector_order;
+  std::size_t _corrector_steps;
+  const bool _allow_fusion;
+
+  // fused five-pass plans (one per solver variable) when the root compute matches the canonical
+  // split-operator pattern; empty = generic operator-by-operator path
+  struct FusedVariable {
+    mrl_split_plan *plan = nullptr;
+    mrl_expr *expr = nullptr;
+    int stored = 0;  // old nonlinear terms currently held by the plan's ring
+    std::string g_name;  // real-space nonlinearity buffer to materialise (observed), or empty
+  };
+  std::vector<FusedVariable> _plans;
+  int _fused_last_step = -1;
+  std::string _fusion_note;
+};
+
+class ETDRK4Solver : public SplitOperatorBase {
+public:
+  static InputParameters validParams();
+  explicit ETDRK4Solver(const InputParameters &parameters);
+  ~ETDRK4Solver() override;
+
+protected:
+  void substep() override;
+  mrl_expr *_e_stage_half = nullptr, *_e_stage_full = nullptr, *_e_final = nullptr;
+  mrl_expr *kernel(mrl_expr *&slot, const char *expression, const std::vector<std::string> &names, const std::vector<int> &layouts);
+};

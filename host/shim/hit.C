@@ -2,6 +2,7 @@
 
 #include <cctype>
 #include <cmath>
+#include <cstring>
 #include <functional>
 #include <map>
 #include <sstream>

@@ -1,0 +1,204 @@
+#include "DomainAction.h"
+
+#include <cstring>
+
+using marlin::Space;
+using marlin::Tensor;
+
+namespace marlin {
+
+TensorStorage::~TensorStorage() {
+  if (pool && dev) pool->put(dev, bytes);
+}
+
+TensorPool::~TensorPool() {
+  for (auto &kv : _free) mrl_free(_ctx, kv.second);
+}
+
+std::shared_ptr<TensorStorage> TensorPool::get(size_t bytes) {
+  auto st = std::make_shared<TensorStorage>();
+  st->pool = this;
+  st->bytes = bytes;
+  auto it = _free.find(bytes);
+  if (it != _free.end()) {
+    st->dev = it->second;
+    _free.erase(it);
+    return st;
+  }
+  void *p = nullptr;
+  if (mrl_malloc(_ctx, bytes, &p) != MRL_OK) {
+    // release the cached blocks and retry once before giving up
+    for (auto &kv : _free) mrl_free(_ctx, kv.second);
+    _free.clear();
+    if (mrl_malloc(_ctx, bytes, &p) != MRL_OK) {
+      st->pool = nullptr;
+      ::mooseError("marlin_b200: device allocation of ", bytes, " bytes failed: ", mrl_last_error());
+    }
+  }
+  _allocated += bytes;
+  ++_n_alloc;
+  st->dev = p;
+  return st;
+}
+
+void TensorPool::put(void *dev, size_t bytes) { _free.emplace(bytes, dev); }
+
+}  // namespace marlin
+
+InputParameters DomainAction::validParams() {
+  InputParameters params = MooseObject::validParams();
+  params.addClassDescription("Set up the domain and compute devices.");
+  params.addRequiredParam<MooseEnum>("dim", MooseEnum("1=1 2 3"), "Problem dimension");
+  params.addParam<MooseEnum>("parallel_mode", MooseEnum("NONE REAL_SPACE FFT_SLAB FFT_PENCIL", "NONE"), "Parallelization mode.");
+  params.addParam<std::vector<std::string>>("periodic_directions", {}, "Periodic directions of the simulation cell.");
+  params.addParam<unsigned int>("nx", 1, "Number of elements in the X direction");
+  params.addParam<unsigned int>("ny", 1, "Number of elements in the Y direction");
+  params.addParam<unsigned int>("nz", 1, "Number of elements in the Z direction");
+  params.addParam<Real>("xmax", 1.0, "Upper X Coordinate of the generated mesh");
+  params.addParam<Real>("ymax", 1.0, "Upper Y Coordinate of the generated mesh");
+  params.addParam<Real>("zmax", 1.0, "Upper Z Coordinate of the generated mesh");
+  params.addParam<Real>("xmin", 0.0, "Lower X Coordinate of the generated mesh");
+  params.addParam<Real>("ymin", 0.0, "Lower Y Coordinate of the generated mesh");
+  params.addParam<Real>("zmin", 0.0, "Lower Z Coordinate of the generated mesh");
+  params.addParam<MooseEnum>("mesh_mode", MooseEnum("DUMMY DOMAIN MANUAL", "DUMMY"), "Mesh generation mode.");
+  params.addParam<std::vector<std::string>>("device_names", {}, "Compute devices to run on.");
+  params.addParam<std::vector<unsigned int>>("device_weights", {}, "Device weights (or speeds) to influence the partitioning.");
+  params.addParam<MooseEnum>("floating_precision", MooseEnum("DEVICE_DEFAULT SINGLE DOUBLE", "DEVICE_DEFAULT"), "Floating point precision.");
+  params.addParam<bool>("debug", false, "Enable additional debugging and diagnostics, such a checking for initialized tensors.");
+  params.addParam<bool>("gpu_aware_mpi", false, "Enable GPU-aware MPI.");
+  return params;
+}
+
+DomainAction::DomainAction(const InputParameters &parameters)
+  : MooseObject(parameters),
+    _dim(int(getParam<MooseEnum>("dim"))),
+    _n_global({getParam<unsigned int>("nx"), getParam<unsigned int>("ny"), getParam<unsigned int>("nz")}),
+    _min_global({getParam<Real>("xmin"), getParam<Real>("ymin"), getParam<Real>("zmin")}),
+    _max_global({getParam<Real>("xmax"), getParam<Real>("ymax"), getParam<Real>("zmax")}),
+    _parallel_mode(getParam<MooseEnum>("parallel_mode").getEnum<ParallelMode>()),
+    _debug(getParam<bool>("debug")) {
+  if (_parallel_mode != ParallelMode::NONE)
+    paramError("parallel_mode", "The single-process host driver runs ParallelMode NONE; the slab-decomposed path is driven one "
+                                "process per GPU through mrl_slab_* (see marlin_b200/slab.py).");
+  // [Domain] device_names: "cuda", "cuda:1" (src/base/MarlinApp.C:27-54).  There is no CPU path.
+  const auto names = getParam<std::vector<std::string>>("device_names");
+  if (!names.empty()) {
+    const std::string &d = names[0];
+    if (d.rfind("cuda", 0) != 0)
+      paramError("device_names", "marlin_b200 runs on CUDA devices only (sm_100a); got '", d, "'. There is no CPU fallback.");
+    const size_t colon = d.find(':');
+    if (colon != std::string::npos) _device = std::atoi(d.c_str() + colon + 1);
+  }
+  // DEVICE_DEFAULT / DOUBLE -> float64 on CUDA (src/utils/MarlinUtils.C:42)
+  _single = getParam<MooseEnum>("floating_precision") == "SINGLE";
+  for (unsigned int d = _dim; d < 3; ++d)
+    if (_n_global[d] != 1) _n_global[d] = 1;  // unused dimensions collapse (DomainAction.C:296)
+  check(mrl_create(_device, _single ? MRL_F32 : MRL_F64, &_ctx), "mrl_create");
+  _pool = std::make_unique<marlin::TensorPool>(_ctx);
+  gridChanged();
+}
+
+DomainAction::~DomainAction() {
+  _pool.reset();
+  if (_ctx) mrl_destroy(_ctx);
+}
+
+void DomainAction::check(int rc, const char *what) const {
+  if (rc != MRL_OK) ::mooseError("marlin_b200: ", what, " failed: ", mrl_last_error());
+}
+
+void DomainAction::gridChanged() {
+  check(mrl_domain_set(_ctx, (int)_dim, _n_global.data(), _min_global.data(), _max_global.data()), "mrl_domain_set");
+  check(mrl_domain_shape(_ctx, _shape.data(), _reciprocal_shape.data()), "mrl_domain_shape");
+  _volume = 1.0;
+  for (unsigned int d = 0; d < 3; ++d) {
+    if (d < _dim) {
+      _grid_spacing[d] = (_max_global[d] - _min_global[d]) / Real(_n_global[d]);  // DomainAction.C:241
+      _volume *= _max_global[d] - _min_global[d];
+      _axis[d].assign(_shape[d], 0.0);
+      _raxis[d].assign(_reciprocal_shape[d], 0.0);
+      check(mrl_domain_axis(_ctx, (int)d, 0, _axis[d].data()), "mrl_domain_axis");
+      check(mrl_domain_axis(_ctx, (int)d, 1, _raxis[d].data()), "mrl_domain_axis");
+    } else {
+      _grid_spacing[d] = 0.0;
+      _axis[d] = {0.0};
+      _raxis[d] = {0.0};
+    }
+  }
+}
+
+Tensor DomainAction::empty(Space space, bool is_complex, int ncomp) const {
+  const int64_t count = space == Space::SCALAR ? 1 : (space == Space::REAL ? getNumberOfCells() : getNumberOfReciprocalCells());
+  const size_t bytes = size_t(count) * ncomp * realBytes() * (is_complex ? 2 : 1);
+  return Tensor(_pool->get(bytes), space, is_complex, ncomp, count);
+}
+
+Tensor DomainAction::zeros(Space space, bool is_complex, int ncomp) const {
+  Tensor t = empty(space, is_complex, ncomp);
+  check(mrl_memset(_ctx, t.data_ptr(), 0, t.nbytes()), "mrl_memset");
+  return t;
+}
+
+Tensor DomainAction::fromHost(const std::vector<double> &values, Space space, bool is_complex, int ncomp) const {
+  Tensor t = empty(space, is_complex, ncomp);
+  const size_t n = size_t(t.numel()) * (is_complex ? 2 : 1);
+  if (values.size() != n) ::mooseError("fromHost: expected ", n, " values, got ", values.size());
+  if (_single) {
+    std::vector<float> f(values.begin(), values.end());
+    check(mrl_upload(_ctx, t.data_ptr(), f.data(), n * 4), "mrl_upload");
+    synchronize();  // the staging vector dies at scope exit
+  } else {
+    check(mrl_upload(_ctx, t.data_ptr(), values.data(), n * 8), "mrl_upload");
+    synchronize();
+  }
+  return t;
+}
+
+std::vector<double> DomainAction::toHost(const Tensor &t) const {
+  const size_t n = size_t(t.numel()) * (t.is_complex() ? 2 : 1);
+  std::vector<double> out(n);
+  if (_single) {
+    std::vector<float> f(n);
+    check(mrl_download(_ctx, f.data(), t.data_ptr(), n * 4), "mrl_download");
+    synchronize();
+    for (size_t i = 0; i < n; ++i) out[i] = f[i];
+  } else {
+    check(mrl_download(_ctx, out.data(), t.data_ptr(), n * 8), "mrl_download");
+    synchronize();
+  }
+  return out;
+}
+
+Tensor DomainAction::clone(const Tensor &t) const {
+  Tensor c = empty(t.space(), t.is_complex(), t.ncomp());
+  check(mrl_copy(_ctx, c.data_ptr(), t.data_ptr(), t.nbytes()), "mrl_copy");
+  return c;
+}
+
+Tensor DomainAction::fft(const Tensor &t) const {
+  if (!t.defined()) ::mooseError("fft of an undefined tensor");
+  if (t.space() != Space::REAL || t.is_complex()) ::mooseError("fft expects a real tensor in real space");
+  Tensor out = empty(Space::RECIPROCAL, true, t.ncomp());
+  check(mrl_rfftn(_ctx, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_rfftn");
+  return out;
+}
+
+Tensor DomainAction::ifft(const Tensor &t) const {
+  if (!t.defined()) ::mooseError("ifft of an undefined tensor");
+  if (t.space() != Space::RECIPROCAL || !t.is_complex()) ::mooseError("ifft expects a complex tensor in reciprocal space");
+  Tensor out = empty(Space::REAL, false, t.ncomp());
+  check(mrl_irfftn(_ctx, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_irfftn");
+  return out;
+}
+
+Real DomainAction::reduce(int op, const Tensor &t) const {
+  if (!t.defined()) ::mooseError("reduction of an undefined tensor");
+  if (t.is_complex()) ::mooseError("reductions are defined for real tensors");
+  double v = 0;
+  check(mrl_reduce(_ctx, op, t.data_ptr(), t.numel(), &v), "mrl_reduce");
+  return v;
+}
+
+Real DomainAction::sum(const Tensor &t) const { return reduce(MRL_SUM, t); }
+
+void DomainAction::synchronize() const { check(mrl_synchronize(_ctx), "mrl_synchronize"); }

@@ -1,0 +1,420 @@
+// marlin_b200-opt: reads an unmodified Marlin input file and runs the spectral path on the GPU.
+//
+// Stands in for the pieces of MOOSE that sit around Marlin's objects and cannot be built here:
+//   * syntax -> object wiring of MarlinApp::registerAll (src/base/MarlinApp.C:94-172):
+//     [Domain], [TensorBuffers], [TensorComputes/{Initialize,Solve,Postprocess}] (five levels deep,
+//     untyped sub-blocks become ComputeGroups: src/actions/AddTensorComputeAction.C:33-80),
+//     [TensorSolver] (automatic root compute: src/actions/CreateTensorSolverAction.C:33-62),
+//     [Problem], [Postprocessors], [GlobalParams]
+//   * the Transient executioner's step loop with ConstantDT / IterationAdaptiveDT
+//     (moose/framework/src/executioners/TransientBase.C, src/timesteppers/IterationAdaptiveDT.C:243-300,
+//      TimeStepper.C:103-135)
+//   * the CSV postprocessor output ([Outputs] csv = true)
+// Blocks that belong to the finite-element side of MOOSE (Mesh, Variables, AuxKernels, ...) and the
+// XDMF tensor output are outside the spectral time-step path; they are reported and skipped.
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#include "MechanicsComputes.h"
+#include "TensorComputes.h"
+#include "TensorPostprocessor.h"
+#include "TensorSolver.h"
+#include "hit.h"
+
+namespace {
+
+struct Options {
+  std::string input;
+  std::vector<std::string> overrides;
+  bool check_only = false;
+  bool list_objects = false;
+  std::string output_dir;
+  std::vector<std::string> dump;
+  std::string dump_dir = ".";
+  bool quiet = false;
+};
+
+std::string dirName(const std::string &p) {
+  const size_t s = p.rfind('/');
+  return s == std::string::npos ? "." : p.substr(0, s);
+}
+std::string baseName(const std::string &p) {
+  const size_t s = p.rfind('/');
+  std::string b = s == std::string::npos ? p : p.substr(s + 1);
+  const size_t d = b.rfind('.');
+  return d == std::string::npos ? b : b.substr(0, d);
+}
+
+class MarlinApp {
+public:
+  explicit MarlinApp(Options opt) : _opt(std::move(opt)) {}
+  int run();
+
+private:
+  // fill an object's parameters from its block (+ GlobalParams), reject unknown keys
+  InputParameters fill(const std::string &type, const hit::Node &block, const std::string &name, const std::set<std::string> &also_allowed = {});
+  void addComputes(const hit::Node &parent, int task, int depth);
+  void buildObjects();
+  void transient();
+  void writeCSVRow(bool header);
+  void dumpBuffers();
+
+  Options _opt;
+  std::unique_ptr<hit::Node> _root;
+  std::unique_ptr<DomainAction> _domain;
+  std::shared_ptr<TensorProblem> _problem;
+  std::vector<std::string> _skipped;
+  std::ofstream _csv;
+  std::vector<std::shared_ptr<TensorPostprocessor>> _csv_pps;
+};
+
+InputParameters MarlinApp::fill(const std::string &type, const hit::Node &block, const std::string &name, const std::set<std::string> &also_allowed) {
+  InputParameters p = type == "DomainAction" ? DomainAction::validParams() : Factory::instance().getValidParams(type);
+  p.set<std::string>("_object_name", name);
+  p.set<std::string>("_type", type);
+  p.set<std::string>("_object_path", block.fullpath());
+  if (const hit::Node *gp = _root->find("GlobalParams"))
+    for (const hit::Node *f : gp->fields())
+      if (p.have(f->name) && !p.entries().at(f->name).is_private) p.setFromInput(f->name, f->value);
+  for (const hit::Node *f : block.fields()) {
+    if (f->name == "type" || f->name == "active" || f->name == "inactive") {
+      if (f->name == "type") p.setFromInput("type", f->value);
+      continue;
+    }
+    if (!p.have(f->name) || p.entries().at(f->name).is_private) {
+      if (also_allowed.count(f->name)) continue;
+      mooseError(_opt.input, ":", f->line, ": unused parameter '", block.fullpath(), "/", f->name, "' (object type ", type, ")");
+    }
+    p.setFromInput(f->name, f->value);
+  }
+  p.setPointer("_domain", _domain.get());
+  p.setPointer("_tensor_problem", _problem.get());
+  p.check(block.fullpath());
+  return p;
+}
+
+// task: 0 = Initialize, 1 = Solve, 2 = Postprocess
+void MarlinApp::addComputes(const hit::Node &parent, int task, int depth) {
+  if (depth > 5) mooseError(parent.fullpath(), ": TensorComputes blocks may nest at most five levels deep");
+  for (hit::Node *blk : parent.sections()) {
+    const hit::Node *tf = blk->field("type");
+    std::string type = tf ? tf->value : "ComputeGroup";
+    if (!Factory::instance().isRegistered(type)) mooseError(_opt.input, ":", blk->line, ": A '", type, "' is not a registered object (block ", blk->fullpath(), ")");
+    // sub-blocks first?  No: MOOSE acts on the blocks in input order, parents before children.
+    InputParameters p = fill(type, *blk, blk->name);
+    if (type == "ComputeGroup") {
+      // automatically populate `computes` with the sub-blocks
+      auto computes = p.get<std::vector<TensorComputeName>>("computes", blk->fullpath());
+      std::set<TensorComputeName> s(computes.begin(), computes.end());
+      for (hit::Node *child : blk->sections()) s.insert(child->name);
+      p.set<std::vector<TensorComputeName>>("computes", std::vector<TensorComputeName>(s.begin(), s.end()));
+    }
+    auto obj = std::dynamic_pointer_cast<TensorOperatorBase>(Factory::instance().create(type, p));
+    if (!obj) mooseError(blk->fullpath(), ": '", type, "' is not a TensorOperator");
+    if (task == 0) _problem->addTensorIC(obj);
+    if (task == 1) _problem->addTensorCompute(obj);
+    if (task == 2) _problem->addTensorPostprocess(obj);
+    addComputes(*blk, task, depth + 1);
+  }
+}
+
+void MarlinApp::buildObjects() {
+  static const std::set<std::string> known = {"Domain", "GlobalParams", "TensorBuffers", "TensorComputes", "TensorSolver", "Problem", "Postprocessors", "Executioner", "Outputs"};
+  for (hit::Node *s : _root->sections())
+    if (!known.count(s->name)) _skipped.push_back(s->name);
+
+  const hit::Node *dom = _root->find("Domain");
+  if (!dom || !dom->is_section) mooseError(_opt.input, ": missing [Domain] block");
+  _domain = std::make_unique<DomainAction>(fill("DomainAction", *dom, "Domain"));
+
+  // [Problem]
+  {
+    hit::Node empty;
+    const hit::Node *pb = _root->find("Problem");
+    std::string type = "TensorProblem";
+    if (pb && pb->field("type")) type = pb->field("type")->value;
+    if (type != "TensorProblem") mooseError("Tensor objects are only supported if the problem class is set to `TensorProblem` (got '", type, "')");
+    empty.name = "Problem";
+    _problem = std::dynamic_pointer_cast<TensorProblem>(Factory::instance().create(type, fill(type, pb ? *pb : empty, "Problem")));
+  }
+  // [TensorBuffers]
+  if (const hit::Node *tb = _root->find("TensorBuffers"))
+    for (hit::Node *b : tb->sections()) {
+      const hit::Node *tf = b->field("type");
+      if (tf && tf->value != "PlainTensorBuffer") mooseError(b->fullpath(), ": buffer type '", tf->value, "' is not on the spectral path (only PlainTensorBuffer)");
+      _problem->getBuffer(b->name);
+    }
+  // [TensorComputes]
+  if (const hit::Node *tc = _root->find("TensorComputes")) {
+    for (hit::Node *s : tc->sections()) {
+      if (s->name == "Initialize")
+        addComputes(*s, 0, 1);
+      else if (s->name == "Solve")
+        addComputes(*s, 1, 1);
+      else if (s->name == "Postprocess")
+        addComputes(*s, 2, 1);
+      else if (s->name == "Boundary")
+        _skipped.push_back("TensorComputes/Boundary");
+      else
+        mooseError(s->fullpath(), ": unknown TensorComputes section");
+    }
+  }
+  // [TensorSolver]
+  if (const hit::Node *ts = _root->find("TensorSolver")) {
+    const hit::Node *tf = ts->field("type");
+    if (!tf) mooseError("[TensorSolver]: missing 'type'");
+    if (!Factory::instance().isRegistered(tf->value)) mooseError(_opt.input, ":", ts->line, ": A '", tf->value, "' is not a registered object (block TensorSolver)");
+    InputParameters p = fill(tf->value, *ts, "TensorSolver");
+    if (!p.isParamValid("root_compute")) {
+      // CreateTensorSolverAction.C:43-60
+      std::vector<TensorComputeName> names;
+      for (const auto &cmp : _problem->getComputes()) names.push_back(cmp->name());
+      InputParameters gp = Factory::instance().getValidParams("ComputeGroup");
+      gp.set<std::string>("_object_name", "automatic_root_compute");
+      gp.set<std::string>("_type", "ComputeGroup");
+      gp.set<std::string>("_object_path", "TensorComputes/Solve/automatic_root_compute");
+      gp.set<std::vector<TensorComputeName>>("computes", names);
+      gp.setPointer("_domain", _domain.get());
+      gp.setPointer("_tensor_problem", _problem.get());
+      _problem->addTensorCompute(std::dynamic_pointer_cast<TensorOperatorBase>(Factory::instance().create("ComputeGroup", gp)));
+      p.set<TensorComputeName>("root_compute", "automatic_root_compute");
+    }
+    auto solver = std::dynamic_pointer_cast<TensorSolver>(Factory::instance().create(tf->value, p));
+    if (!solver) mooseError("[TensorSolver]: '", tf->value, "' is not a TensorSolver");
+    for (hit::Node *s : ts->sections()) _skipped.push_back("TensorSolver/" + s->name);
+    _problem->setSolver(solver);
+  }
+  // [Postprocessors]
+  if (const hit::Node *pps = _root->find("Postprocessors"))
+    for (hit::Node *b : pps->sections()) {
+      const hit::Node *tf = b->field("type");
+      if (!tf) mooseError(b->fullpath(), ": missing 'type'");
+      if (!Factory::instance().isRegistered(tf->value)) {
+        _skipped.push_back(b->fullpath() + " (type " + tf->value + ")");
+        continue;
+      }
+      auto pp = std::dynamic_pointer_cast<TensorPostprocessor>(Factory::instance().create(tf->value, fill(tf->value, *b, b->name)));
+      if (!pp) mooseError(b->fullpath(), ": '", tf->value, "' is not a Postprocessor");
+      _problem->addPostprocessor(pp);
+    }
+}
+
+void MarlinApp::writeCSVRow(bool header) {
+  if (!_csv.is_open()) return;
+  if (header) {
+    _csv << "time";
+    for (const auto &pp : _csv_pps) _csv << "," << pp->name();
+    _csv << "\n";
+    return;
+  }
+  _csv << std::setprecision(14) << _problem->time();
+  for (const auto &pp : _csv_pps) _csv << "," << std::setprecision(14) << pp->getValue();
+  _csv << "\n";
+  _csv.flush();
+}
+
+void MarlinApp::dumpBuffers() {
+  for (const auto &name : _opt.dump) {
+    if (!_problem->hasBuffer(name)) mooseError("--dump: no buffer named '", name, "'");
+    const marlin::Tensor &t = _problem->getRawBuffer(name);
+    if (!t.defined()) mooseError("--dump: buffer '", name, "' is not defined");
+    const std::vector<double> host = _domain->toHost(t);
+    // little-endian float64, C order; complex tensors interleaved; rank-two fields component major
+    std::ofstream f(_opt.dump_dir + "/" + name + ".f64", std::ios::binary);
+    f.write(reinterpret_cast<const char *>(host.data()), std::streamsize(host.size() * sizeof(double)));
+  }
+}
+
+void MarlinApp::transient() {
+  hit::Node empty;
+  const hit::Node *ex = _root->find("Executioner");
+  if (!ex) ex = &empty;
+  auto num = [&](const hit::Node *blk, const char *key, double dflt) {
+    const hit::Node *f = blk ? blk->field(key) : nullptr;
+    return f ? shim_detail::Conv<double>::from(f->value, blk->fullpath() + "/" + key) : dflt;
+  };
+  if (const hit::Node *t = ex->field("type"))
+    if (t->value != "Transient") mooseError("[Executioner]: only type = Transient drives a TensorProblem (got '", t->value, "')");
+  const double start_time = num(ex, "start_time", 0.0);
+  const double end_time = num(ex, "end_time", 1e30);
+  const double dtmax = num(ex, "dtmax", 1e30);
+  const double dtmin = num(ex, "dtmin", 0.0);
+  const long num_steps = (long)num(ex, "num_steps", 4294967295.0);
+  double dt0 = num(ex, "dt", 1.0);
+  double growth = 1.0;
+  const hit::Node *ts = ex->find("TimeStepper");
+  if (ts && ts->is_section) {
+    const hit::Node *t = ts->field("type");
+    const std::string type = t ? t->value : "ConstantDT";
+    dt0 = num(ts, "dt", dt0);
+    if (type == "IterationAdaptiveDT" || type == "TensorSolveIterationAdaptiveDT")
+      growth = num(ts, "growth_factor", 2.0);
+    else if (type != "ConstantDT")
+      mooseError("[Executioner/TimeStepper]: time stepper '", type, "' is not supported by the stand-alone driver");
+    if (type == "TensorSolveIterationAdaptiveDT")
+      mooseWarning("TensorSolveIterationAdaptiveDT: iteration feedback applies to the iterative solvers (Secant / Broyden); growing by growth_factor every step.");
+  }
+
+  // [Outputs]
+  const hit::Node *out = _root->find("Outputs");
+  bool csv = false;
+  std::string file_base = dirName(_opt.input) + "/" + baseName(_opt.input) + "_out";
+  int out_on = EXEC_INITIAL | EXEC_TIMESTEP_END;
+  if (out) {
+    if (const hit::Node *f = out->field("csv")) csv = shim_detail::Conv<bool>::from(f->value, "Outputs/csv");
+    if (const hit::Node *f = out->field("file_base")) file_base = f->value[0] == '/' ? f->value : dirName(_opt.input) + "/" + f->value;
+    if (const hit::Node *f = out->field("execute_on")) out_on = parseExecFlags(f->value, "Outputs/execute_on");
+    for (hit::Node *s : out->sections()) {
+      const hit::Node *t = s->field("type");
+      if (t && t->value == "CSV") {
+        csv = true;
+        if (const hit::Node *f = s->field("file_base")) file_base = f->value[0] == '/' ? f->value : dirName(_opt.input) + "/" + f->value;
+        if (const hit::Node *f = s->field("execute_on")) out_on = parseExecFlags(f->value, s->fullpath() + "/execute_on");
+      } else {
+        _skipped.push_back(s->fullpath());
+      }
+    }
+  }
+  if (!_opt.output_dir.empty()) file_base = _opt.output_dir + "/" + file_base.substr(file_base.rfind('/') + 1);
+
+  if (!_skipped.empty() && !_opt.quiet) {
+    std::cerr << "marlin_b200: blocks outside the spectral time-step path were skipped:";
+    for (const auto &s : _skipped) std::cerr << " [" << s << "]";
+    std::cerr << "\n";
+  }
+
+  _problem->init();
+  if (_opt.check_only) {
+    std::cout << "Syntax OK\n";
+    return;
+  }
+
+  _csv_pps = _problem->getPostprocessors();
+  std::sort(_csv_pps.begin(), _csv_pps.end(), [](const auto &a, const auto &b) { return a->name() < b->name(); });
+  if (csv && !_csv_pps.empty()) {
+    _csv.open(file_base + ".csv");
+    if (!_csv) mooseError("cannot write '", file_base, ".csv'");
+    writeCSVRow(true);
+  }
+
+  Real &time = _problem->time();
+  Real &time_old = _problem->timeOld();
+  Real &dt = _problem->dt();
+  Real &dt_old = _problem->dtOld();
+  int &t_step = _problem->timeStep();
+  time = time_old = start_time;
+  t_step = 0;
+  _problem->execute(EXEC_INITIAL);
+  if (out_on & EXEC_INITIAL) writeCSVRow(false);
+
+  double next_dt = dt0;
+  while (t_step < num_steps && time < end_time - 1e-14 * std::max(1.0, std::fabs(end_time))) {
+    // TimeStepper::constrainStep
+    double step = next_dt;
+    if (step > dtmax) step = dtmax;
+    if (step < dtmin) step = dtmin;
+    if (time + step > end_time) step = end_time - time;
+
+    time_old = time;
+    t_step += 1;
+    _problem->advanceState();
+    dt_old = t_step > 1 ? dt : step;
+    dt = step;
+    time = time_old + dt;
+    _problem->execute(EXEC_TIMESTEP_BEGIN);
+    _problem->execute(EXEC_TIMESTEP_END);
+    if (out_on & EXEC_TIMESTEP_END) writeCSVRow(false);
+    if (!_opt.quiet) std::cerr << "Time Step " << t_step << ", time = " << std::setprecision(8) << time << ", dt = " << dt << "\n";
+    next_dt = dt * growth;
+  }
+  _problem->execute(EXEC_FINAL);
+  if ((out_on & EXEC_FINAL) && !(out_on & EXEC_TIMESTEP_END)) writeCSVRow(false);
+  _domain->synchronize();
+  dumpBuffers();
+  if (!_opt.quiet) {
+    int64_t launches = 0;
+    mrl_launch_count(_domain->context(), &launches);
+    std::cerr << "marlin_b200: " << launches << " kernel launches, " << _domain->pool().allocations() << " device allocations ("
+              << _domain->pool().bytesAllocated() / double(1 << 20) << " MiB)\n";
+  }
+}
+
+int MarlinApp::run() {
+  if (_opt.list_objects) {
+    for (const auto &n : Factory::instance().registeredNames()) std::cout << n << "\n";
+    return 0;
+  }
+  std::ifstream in(_opt.input);
+  if (!in) mooseError("Unable to open file \"", _opt.input, "\".");
+  std::stringstream ss;
+  ss << in.rdbuf();
+  try {
+    _root = hit::parse(ss.str(), _opt.input, _opt.overrides);
+  } catch (const std::exception &e) {
+    mooseError(e.what());
+  }
+  buildObjects();
+  transient();
+  // tear down in dependency order: objects -> buffers -> pool -> context
+  _csv_pps.clear();
+  _problem.reset();
+  _domain.reset();
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Options opt;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto need = [&](const char *what) -> std::string {
+      if (i + 1 >= argc) {
+        std::cerr << "missing value after " << what << "\n";
+        std::exit(2);
+      }
+      return argv[++i];
+    };
+    if (a == "-i")
+      opt.input = need("-i");
+    else if (a == "--check-input" || a == "--check")
+      opt.check_only = true;
+    else if (a == "--list-objects")
+      opt.list_objects = true;
+    else if (a == "--output-dir")
+      opt.output_dir = need("--output-dir");
+    else if (a == "--dump") {
+      std::stringstream s(need("--dump"));
+      std::string w;
+      while (std::getline(s, w, ',')) opt.dump.push_back(w);
+    } else if (a == "--dump-dir")
+      opt.dump_dir = need("--dump-dir");
+    else if (a == "--quiet")
+      opt.quiet = true;
+    else if (a == "--n-threads" || a == "--color")
+      need(a.c_str());
+    else if (a.find('=') != std::string::npos)
+      opt.overrides.push_back(a);
+    else if (a.rfind("--n-threads=", 0) == 0 || a == "--error" || a == "--allow-unused")
+      continue;
+    else {
+      std::cerr << "unknown argument '" << a << "'\nusage: marlin_b200-opt -i input.i [Block/param=value ...] [--check-input] [--output-dir DIR] [--dump buf1,buf2 --dump-dir DIR]\n";
+      return 2;
+    }
+  }
+  if (opt.input.empty() && !opt.list_objects) {
+    std::cerr << "usage: marlin_b200-opt -i input.i [Block/param=value ...] [--check-input] [--list-objects]\n";
+    return 2;
+  }
+  try {
+    MarlinApp app(opt);
+    return app.run();
+  } catch (const std::exception &e) {
+    std::cerr << "\n*** ERROR ***\n" << e.what() << "\n";
+    return 1;
+  }
+}

@@ -1,0 +1,203 @@
+// de Geus finite-strain FFT mechanics as MOOSE-style objects on top of mrl_mech_*.
+//   FFTMechanics              src/tensor_computes/FFTMechanics.C:20-163
+//   HyperElasticIsotropic     src/tensor_computes/HyperElasticIsotropic.C:14-52
+//   RankTwoIdentity           src/tensor_computes/RankTwoIdentity.C:14-33
+//   MacroscopicShearTensor    test/src/tensor_computes/MacroscopicShearTensor.C:15-41 (test fixture)
+//   PhaseMechanicsTest        test/src/tensor_computes/PhaseMechanicsTest.C:15-50     (test fixture)
+// Rank-two fields are stored component major on the device ([9][nx][ny][nz], c = 3 i + j; see
+// include/marlin_b200.h); Ghat4, C4 and the tangent K4 are never materialised.
+#include "MechanicsComputes.h"
+
+#include <cstring>
+
+using marlin::Space;
+using marlin::Tensor;
+
+// ------------------------------------------------------------------------------- RankTwoIdentity
+registerMooseObject("MarlinApp", RankTwoIdentity);
+
+InputParameters RankTwoIdentity::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Second order identity tensor field.");
+  return params;
+}
+RankTwoIdentity::RankTwoIdentity(const InputParameters &parameters) : TensorOperator<>(parameters) {}
+
+void RankTwoIdentity::computeBuffer() {
+  if (_dim != 3) mooseError("the CUDA mechanics path is 3-D");
+  const size_t n = size_t(_domain.getNumberOfCells());
+  std::vector<double> host(9 * n, 0.0);
+  for (int c : {0, 4, 8}) std::fill(host.begin() + c * n, host.begin() + (c + 1) * n, 1.0);
+  _u = _domain.fromHost(host, Space::REAL, false, 9);
+}
+
+// ------------------------------------------------------------------------ MacroscopicShearTensor
+registerMooseObject("MarlinApp", MacroscopicShearTensor);
+
+InputParameters MacroscopicShearTensor::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Macroscopic shear deformation gradient increment (test object).");
+  params.addParam<TensorInputBufferName>("F", "F", "Deformation gradient tensor.");
+  return params;
+}
+MacroscopicShearTensor::MacroscopicShearTensor(const InputParameters &parameters) : TensorOperator<>(parameters), _tF(getInputBuffer("F")) {}
+
+void MacroscopicShearTensor::computeBuffer() {
+  if (!_tF.defined() || _tF.ncomp() != 9) mooseError("F must be an initialised rank-two field");
+  // I + t e0 e1^T - <F>, nine device reductions (DomainAction::average, src/actions/DomainAction.C:1570-1574)
+  std::vector<double> applied(9);
+  const size_t stride = size_t(_tF.count()) * _domain.realBytes();
+  for (int c = 0; c < 9; ++c) {
+    double s = 0;
+    checkC(mrl_reduce(_domain.context(), MRL_SUM, static_cast<const char *>(_tF.data_ptr()) + c * stride, _tF.count(), &s), "mrl_reduce");
+    applied[c] = ((c == 0 || c == 4 || c == 8) ? 1.0 : 0.0) - s / Real(_domain.getNumberOfCells());
+  }
+  applied[1] += _time;
+  _u = _domain.fromHost(applied, Space::SCALAR, false, 9);
+}
+
+// ---------------------------------------------------------------------------- PhaseMechanicsTest
+registerMooseObject("MarlinApp", PhaseMechanicsTest);
+
+InputParameters PhaseMechanicsTest::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Inclusion indicator of the de Geus example (test object).");
+  return params;
+}
+PhaseMechanicsTest::PhaseMechanicsTest(const InputParameters &parameters) : TensorOperator<>(parameters) {}
+
+void PhaseMechanicsTest::computeBuffer() {
+  const auto &n = _domain.getGridSize();
+  const int64_t s = _dim == 2 ? 30 : 9;
+  if (_dim != 2 && _dim != 3) mooseError("Unsupported problem dimension");
+  std::vector<double> host(size_t(_domain.getNumberOfCells()), 0.0);
+  // phase[-s:, :s, -s:] = 1 (python slicing semantics: clipped to the grid)
+  for (int64_t i = std::max<int64_t>(0, n[0] - s); i < n[0]; ++i)
+    for (int64_t j = 0; j < std::min<int64_t>(s, n[1]); ++j) {
+      if (_dim == 2)
+        host[size_t(i * n[1] + j)] = 1.0;
+      else
+        for (int64_t k = std::max<int64_t>(0, n[2] - s); k < n[2]; ++k) host[size_t((i * n[1] + j) * n[2] + k)] = 1.0;
+    }
+  _u = _domain.fromHost(host, Space::REAL, false, 1);
+}
+
+// ------------------------------------------------------------------------------------ MechPlanHolder
+MechPlanHolder::~MechPlanHolder() { reset(); }
+void MechPlanHolder::reset() {
+  if (_plan) mrl_mech_plan_destroy(_plan);
+  _plan = nullptr;
+}
+mrl_mech_plan *MechPlanHolder::get(const DomainAction &domain, const mrl_mech_desc &desc, const Tensor &K, const Tensor &mu) {
+  if (!K.defined() || !mu.defined()) ::mooseError("mechanics: the K and mu fields must be initialised");
+  if (_plan && _K == K.data_ptr() && _mu == mu.data_ptr()) return _plan;
+  reset();
+  if (mrl_mech_plan_create(domain.context(), &desc, K.data_ptr(), mu.data_ptr(), &_plan) != MRL_OK) ::mooseError("marlin_b200: ", mrl_last_error());
+  _K = K.data_ptr();
+  _mu = mu.data_ptr();
+  return _plan;
+}
+
+// ------------------------------------------------------------------------- HyperElasticIsotropic
+registerMooseObject("MarlinApp", HyperElasticIsotropic);
+
+InputParameters HyperElasticIsotropic::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Hyperelastic isotropic constitutive model.");
+  params.addRequiredParam<TensorInputBufferName>("F", "Deformation gradient tensor");
+  params.addRequiredParam<TensorInputBufferName>("mu", "Shear modulus");
+  params.addRequiredParam<TensorInputBufferName>("K", "Bulk modulus");
+  params.addParam<TensorOutputBufferName>("tangent_operator", "dstressdstrain", "Stiffness tensor");
+  return params;
+}
+
+HyperElasticIsotropic::HyperElasticIsotropic(const InputParameters &parameters)
+  : TensorOperator<>(parameters), _tF(getInputBuffer("F")), _tmu(getInputBuffer("mu")), _tK(getInputBuffer("K")) {
+  // the tangent is applied in closed form from (F, K, mu) inside the CG operator; the buffer name is
+  // still announced so that dependency resolution sees the same graph as the reference
+  _supplied_buffers.insert(getParam<TensorOutputBufferName>("tangent_operator"));
+}
+
+void HyperElasticIsotropic::computeBuffer() {
+  mrl_mech_desc d;
+  std::memset(&d, 0, sizeof d);
+  d.l_tol = 1e-2;
+  d.nl_rel_tol = 1e-5;
+  d.nl_abs_tol = 1e-8;
+  d.nl_max_its = 100;
+  mrl_mech_plan *plan = _plan.get(_domain, d, _tK, _tmu);
+  Tensor P = _domain.empty(Space::REAL, false, 9);
+  checkC(mrl_mech_constitutive(plan, _tF.data_ptr(), P.data_ptr()), "mrl_mech_constitutive");
+  _u = P;
+}
+
+// ---------------------------------------------------------------------------------- FFTMechanics
+registerMooseObject("MarlinApp", FFTMechanics);
+
+InputParameters FFTMechanics::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("deGeus variational mechanics solve. Updates the coupled buffer holding the deformation gradient tensor.");
+  params.addRequiredParam<TensorInputBufferName>("K", "Bulk modulus");
+  params.addParam<TensorInputBufferName>("mu", "Shear modulus");
+  params.addParam<Real>("l_tol", 1e-2, "Linear congugate gradient solve tolerance");
+  params.addParam<unsigned int>("l_max_its", "Maximum number of congugate gradient solve iterations");
+  params.addParam<Real>("nl_rel_tol", 1e-5, "Nonlinear solve absolute tolerance");
+  params.addParam<Real>("nl_abs_tol", 1e-8, "Nonlinear solve relative tolerance");
+  params.addParam<unsigned int>("nl_max_its", 100, "Maximum number of nonlinear solve iterations");
+  params.addParam<TensorInputBufferName>("stress", "stress", "Computed stress");
+  params.addParam<TensorInputBufferName>("tangent_operator", "dstressdstrain", "Tangent operator");
+  params.addRequiredParam<TensorComputeName>("constitutive_model", "Tensor compute for the constitutive model (computes stress from displacement gradeint tensor)");
+  params.addParam<TensorInputBufferName>("applied_macroscopic_strain", "Applied macroscopic strain");
+  params.addParam<TensorInputBufferName>("F", "F", "Deformation gradient tensor.");
+  params.addParam<bool>("verbose", false, "Print non-linear residuals.");
+  return params;
+}
+
+FFTMechanics::FFTMechanics(const InputParameters &parameters)
+  : TensorOperator<>(parameters),
+    _tK(getInputBuffer("K")),
+    _tmu(getInputBuffer("mu")),
+    _tF(getInputBuffer("F")),
+    _tP(getInputBuffer("stress")),
+    _constitutive_model(getCompute("constitutive_model")),
+    _applied_macroscopic_strain(isParamValid("applied_macroscopic_strain") ? &getInputBuffer("applied_macroscopic_strain") : nullptr),
+    _verbose(getParam<bool>("verbose")) {
+  getInputBuffer("tangent_operator");
+  std::memset(&_desc, 0, sizeof _desc);
+  _desc.l_tol = getParam<Real>("l_tol");
+  _desc.l_max_its = isParamValid("l_max_its") ? (int64_t)getParam<unsigned int>("l_max_its") : 0;  // <= 0: number of cells
+  _desc.nl_rel_tol = getParam<Real>("nl_rel_tol");
+  _desc.nl_abs_tol = getParam<Real>("nl_abs_tol");
+  _desc.nl_max_its = (int)getParam<unsigned int>("nl_max_its");
+  if (!dynamic_cast<HyperElasticIsotropic *>(&_constitutive_model))
+    paramError("constitutive_model", "the CUDA mechanics path evaluates the HyperElasticIsotropic model in closed form; '", _constitutive_model.type(),
+               "' is not supported.");
+}
+
+void FFTMechanics::check() {
+  const auto stress_name = getParam<TensorOutputBufferName>("stress");
+  if (!_constitutive_model.getSuppliedItems().count(stress_name)) paramError("constitutive_model", "does not provide stress tensor '", stress_name, "'.");
+}
+
+void FFTMechanics::computeBuffer() {
+  mrl_mech_plan *plan = _plan.get(_domain, _desc, _tK, _tmu);
+  // _u = _tF (+ applied strain + Newton increments): the solve updates its F argument in place
+  Tensor F = _domain.clone(_tF);
+  Tensor P = _domain.empty(Space::REAL, false, 9);
+  std::vector<double> applied;
+  if (_applied_macroscopic_strain) {
+    if (_applied_macroscopic_strain->numel() != 9) mooseError("applied_macroscopic_strain must be a 3x3 tensor");
+    applied = _domain.toHost(*_applied_macroscopic_strain);
+  }
+  std::memset(&_stats, 0, sizeof _stats);
+  const int rc = mrl_mech_solve(plan, F.data_ptr(), applied.empty() ? nullptr : applied.data(), P.data_ptr(), &_stats);
+  if (rc != MRL_OK) {
+    const std::string why = mrl_last_error();
+    if (why.find("nonlinear") != std::string::npos) paramError("nl_max_its", "Exceeded the maximum number of nonlinear iterations without converging.");
+    mooseError("marlin_b200: ", why);
+  }
+  if (_verbose) std::cerr << "|R|=" << _stats.final_anorm << "\t|R/R0|=" << _stats.final_rnorm << '\n';
+  _u = F;
+  // the stress of the final state is what the constitutive model's last evaluation leaves behind
+  _tensor_problem.getBuffer(getParam<TensorOutputBufferName>("stress")) = P;
+}

@@ -1,0 +1,448 @@
+// The operators of the spectral path as MOOSE-style objects on top of the C ABI.
+//   ConstantTensor / ConstantReciprocalTensor   src/tensor_computes/ConstantTensor.C:17-53
+//   RandomTensor                                src/tensor_computes/RandomTensor.C:17-55
+//   ForwardFFT / InverseFFT                     src/tensor_computes/PerformFFT.C:17-40
+//   ReciprocalLaplacianFactor                   src/tensor_computes/ReciprocalLaplacianFactor.C:14-33
+//   ReciprocalLaplacianSquareFactor             src/tensor_computes/ReciprocalLaplacianSquareFactor.C:14-34
+//   ParsedCompute                               src/tensor_computes/ParsedCompute.C:20-265
+//   FFTGradient / FFTGradientSquare             src/tensor_computes/FFTGradient.C:15-40, FFTGradientSquare.C:15-48
+//   FFTSemiImplicit                             src/tensor_timeintegrators/FFTSemiImplicit.C:16-62
+#include "TensorComputes.h"
+
+#include <cmath>
+#include <cstring>
+
+using marlin::Space;
+using marlin::Tensor;
+
+// ------------------------------------------------------------------------------------ ExprKernel
+ExprKernel::~ExprKernel() { reset(); }
+void ExprKernel::reset() {
+  if (_expr) mrl_expr_destroy(_expr);
+  _expr = nullptr;
+}
+
+int ExprKernel::layoutOf(const Tensor &t) {
+  if (t.space() == Space::SCALAR) return MRL_VAR_SCALAR;
+  if (t.space() == Space::REAL) return t.is_complex() ? MRL_VAR_REAL_COMPLEX : MRL_VAR_REAL;
+  return t.is_complex() ? MRL_VAR_RECIP_COMPLEX : MRL_VAR_RECIP_REAL;
+}
+
+void ExprKernel::configure(const std::string &expression, std::vector<std::string> inputs, std::vector<std::string> derivatives,
+                           std::vector<std::string> constant_names, std::vector<double> constant_values, bool extra_symbols, int expand) {
+  reset();
+  _expression = expression;
+  _inputs = std::move(inputs);
+  _derivatives = std::move(derivatives);
+  _constant_names = std::move(constant_names);
+  _constant_values = std::move(constant_values);
+  _extra = extra_symbols;
+  _expand = expand;
+  _layouts.clear();
+}
+
+void ExprKernel::fillDesc(mrl_expr_desc &d, std::vector<const char *> &in, std::vector<const char *> &der, std::vector<const char *> &cn,
+                          const std::vector<int> &layouts) const {
+  in.clear();
+  der.clear();
+  cn.clear();
+  for (const auto &s : _inputs) in.push_back(s.c_str());
+  for (const auto &s : _derivatives) der.push_back(s.c_str());
+  for (const auto &s : _constant_names) cn.push_back(s.c_str());
+  std::memset(&d, 0, sizeof d);
+  d.expression = _expression.c_str();
+  d.nvars = (int)in.size();
+  d.var_names = in.data();
+  d.var_layouts = layouts.empty() ? nullptr : layouts.data();
+  d.nderivatives = (int)der.size();
+  d.derivatives = der.data();
+  d.nconstants = (int)cn.size();
+  d.constant_names = cn.data();
+  d.constant_values = _constant_values.data();
+  d.extra_symbols = _extra ? 1 : 0;
+  d.expand = _expand;
+}
+
+std::string ExprKernel::simplified() const {
+  mrl_expr_desc d;
+  std::vector<const char *> in, der, cn;
+  fillDesc(d, in, der, cn, {});
+  std::vector<char> buf(1 << 16);
+  if (mrl_expr_simplified(&d, buf.data(), buf.size()) != MRL_OK) ::mooseError(mrl_last_error());
+  return buf.data();
+}
+
+Tensor ExprKernel::eval(const DomainAction &domain, const std::vector<const Tensor *> &inputs, double t) {
+  std::vector<int> layouts;
+  for (const Tensor *in : inputs) {
+    if (!in->defined()) ::mooseError("an input tensor of the expression '", _expression, "' is not defined yet");
+    if (in->ncomp() != 1) ::mooseError("expressions act on scalar fields; got a tensor with ", in->ncomp(), " components");
+    layouts.push_back(layoutOf(*in));
+  }
+  if (!_expr || layouts != _layouts) {
+    reset();
+    mrl_expr_desc d;
+    std::vector<const char *> in, der, cn;
+    fillDesc(d, in, der, cn, layouts);
+    if (mrl_expr_compile(domain.context(), &d, &_expr) != MRL_OK) ::mooseError(mrl_last_error());
+    _layouts = layouts;
+    domain.check(mrl_expr_result(_expr, &_space, &_is_complex), "mrl_expr_result");
+  }
+  Tensor out = domain.empty(_space == 0 ? Space::SCALAR : (_space == 1 ? Space::REAL : Space::RECIPROCAL), _is_complex != 0, 1);
+  std::vector<const void *> ptrs;
+  for (const Tensor *in : inputs) ptrs.push_back(in->data_ptr());
+  domain.check(mrl_expr_eval(_expr, ptrs.data(), t, out.data_ptr()), "mrl_expr_eval");
+  return out;
+}
+
+// -------------------------------------------------------------------------------- ConstantTensor
+registerMooseObject("MarlinApp", ConstantTensor);
+registerMooseObject("MarlinApp", ConstantReciprocalTensor);
+
+template <bool reciprocal>
+InputParameters ConstantTensorTempl<reciprocal>::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addParam<MarlinConstantName>("imaginary", "0.0", "Imaginary part of the constant value.");
+  if (reciprocal)
+    params.addClassDescription("Constant tensor in reciprocal space.");
+  else {
+    params.addClassDescription("Constant tensor in real space.");
+    params.suppressParameter<MarlinConstantName>("imaginary");
+  }
+  params.addParam<MarlinConstantName>("real", "0.0", "Real part of the constant value.");
+  params.addParam<bool>("full", false, "Construct a full tensor will all entries");
+  return params;
+}
+
+template <bool reciprocal>
+ConstantTensorTempl<reciprocal>::ConstantTensorTempl(const InputParameters &parameters) : TensorOperator<>(parameters) {}
+
+template <bool reciprocal>
+void ConstantTensorTempl<reciprocal>::computeBuffer() {
+  // the reference builds a one-element tensor expanded to the grid shape; here the field is filled
+  const Real re = getConstant("real");
+  const Real im = reciprocal ? getConstant("imaginary") : 0.0;
+  const Space sp = reciprocal ? Space::RECIPROCAL : Space::REAL;
+  Tensor t = _domain.empty(sp, reciprocal, 1);
+  const size_t n = size_t(t.count());
+  if (re == 0.0 && im == 0.0) {
+    checkC(mrl_memset(_domain.context(), t.data_ptr(), 0, t.nbytes()), "mrl_memset");
+  } else {
+    std::vector<double> host(reciprocal ? 2 * n : n);
+    if (reciprocal)
+      for (size_t i = 0; i < n; ++i) {
+        host[2 * i] = re;
+        host[2 * i + 1] = im;
+      }
+    else
+      std::fill(host.begin(), host.end(), re);
+    t = _domain.fromHost(host, sp, reciprocal, 1);
+  }
+  _u = t;
+}
+template class ConstantTensorTempl<false>;
+template class ConstantTensorTempl<true>;
+
+// ---------------------------------------------------------------------------------- RandomTensor
+registerMooseObject("MarlinApp", RandomTensor);
+
+namespace {
+// ATen's CPU generator (at::mt19937 + uniform_real_distribution): bit-for-bit torch::rand on the host.
+struct TorchMT19937 {
+  uint32_t mt[624];
+  int idx = 624;
+  void seed(uint64_t s) {
+    mt[0] = uint32_t(s & 0xffffffffu);
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + uint32_t(i);
+    idx = 624;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+};
+TorchMT19937 &globalGenerator() {
+  static TorchMT19937 g = [] {
+    TorchMT19937 x;
+    x.seed(67280421310721ull);  // c10::detail::default_rng_seed_val
+    return x;
+  }();
+  return g;
+}
+}  // namespace
+
+void marlinTorchRand(std::vector<double> &out, size_t n, bool single, double min, double max, const int *seed) {
+  auto &g = globalGenerator();
+  if (seed) g.seed(uint64_t(int64_t(*seed)));
+  out.resize(n);
+  if (single) {
+    const float fmin = float(min), fr = float(max - min);
+    for (size_t i = 0; i < n; ++i) {
+      const float r = float(g.next() & ((1u << 24) - 1)) * (1.0f / float(1u << 24));
+      volatile float scaled = r * fr;  // two roundings, like the separate mul and add in ATen
+      out[i] = double(float(scaled + fmin));
+    }
+  } else {
+    const double range = max - min;
+    for (size_t i = 0; i < n; ++i) {
+      const uint64_t hi = g.next(), lo = g.next();
+      const uint64_t x = ((hi << 32) | lo) & ((1ull << 53) - 1);
+      const double r = double(x) * (1.0 / double(1ull << 53));
+      volatile double scaled = r * range;
+      out[i] = scaled + min;
+    }
+  }
+}
+
+InputParameters RandomTensor::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Uniform random IC with values between `min` and `max`.");
+  params.addRequiredParam<Real>("min", "Minimum value.");
+  params.addRequiredParam<Real>("max", "Maximum value.");
+  params.addParam<int>("seed", "Random number seed.");
+  params.addParam<bool>("generate_on_cpu", true, "To ensure reproducibility across devices it is recommended to generate random tensors on the CPU.");
+  return params;
+}
+
+RandomTensor::RandomTensor(const InputParameters &parameters) : TensorOperator<>(parameters) {
+  if (!getParam<bool>("generate_on_cpu"))
+    mooseWarning("generate_on_cpu = false: the device generator of libTorch is not reproduced; generating on the host (bit-identical to torch::rand on the CPU).");
+}
+
+void RandomTensor::computeBuffer() {
+  std::vector<double> host;
+  int seed = 0;
+  const bool has_seed = isParamValid("seed");
+  if (has_seed) seed = getParam<int>("seed");
+  marlinTorchRand(host, size_t(_domain.getNumberOfCells()), _domain.single(), getParam<Real>("min"), getParam<Real>("max"), has_seed ? &seed : nullptr);
+  _u = _domain.fromHost(host, Space::REAL, false, 1);
+}
+
+// ------------------------------------------------------------------------------------ PerformFFT
+registerMooseObject("MarlinApp", ForwardFFT);
+registerMooseObject("MarlinApp", InverseFFT);
+
+template <bool forward>
+InputParameters PerformFFTTempl<forward>::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("PerformFFT object.");
+  params.addParam<TensorInputBufferName>("input", "Input buffer name");
+  return params;
+}
+template <bool forward>
+PerformFFTTempl<forward>::PerformFFTTempl(const InputParameters &parameters) : TensorOperator<>(parameters), _input(getInputBuffer("input")) {}
+template <bool forward>
+void PerformFFTTempl<forward>::computeBuffer() {
+  if (forward)
+    _u = _domain.fft(_input);
+  else
+    _u = _domain.ifft(_input);
+}
+template class PerformFFTTempl<true>;
+template class PerformFFTTempl<false>;
+
+// ------------------------------------------------------------------------ ReciprocalLaplacian*Factor
+registerMooseObject("MarlinApp", ReciprocalLaplacianFactor);
+registerMooseObject("MarlinApp", ReciprocalLaplacianSquareFactor);
+
+template <int kind>
+InputParameters ReciprocalLaplacianFactorTempl<kind>::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription(kind == MRL_KFACTOR_LAPLACIAN ? "Reciprocal space Laplacian IC." : "Reciprocal space square Laplacian IC.");
+  params.addParam<Real>("factor", 1.0, "Prefactor");
+  return params;
+}
+template <int kind>
+ReciprocalLaplacianFactorTempl<kind>::ReciprocalLaplacianFactorTempl(const InputParameters &parameters)
+  : TensorOperator<>(parameters), _factor(getParam<Real>("factor")) {}
+template <int kind>
+void ReciprocalLaplacianFactorTempl<kind>::computeBuffer() {
+  Tensor t = _domain.empty(Space::RECIPROCAL, false, 1);
+  checkC(mrl_kfactor(_domain.context(), kind, _factor, t.data_ptr()), "mrl_kfactor");
+  _u = t;
+}
+template class ReciprocalLaplacianFactorTempl<MRL_KFACTOR_LAPLACIAN>;
+template class ReciprocalLaplacianFactorTempl<MRL_KFACTOR_LAPLACIAN_SQUARE>;
+
+// --------------------------------------------------------------------------------- ParsedCompute
+registerMooseObject("MarlinApp", ParsedCompute);
+
+InputParameters ParsedCompute::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("ParsedCompute object.");
+  params.addRequiredParam<std::string>("expression", "Parsed expression");
+  params.addParam<std::vector<TensorInputBufferName>>("inputs", {}, "Buffer names used in the expression");
+  params.addParam<std::vector<TensorInputBufferName>>("derivatives", {}, "List of inputs to take the derivative w.r.t. (or none)");
+  params.addParam<bool>("enable_fpoptimizer", true, "Use algebraic optimizer");
+  params.addParam<bool>("extra_symbols", false,
+                        "Provide i (imaginary unit), kx,ky,kz (reciprocal space frequency), k2 (square of the k-vector), x,y,z "
+                        "(real space coordinates), time t, pi, and e.");
+  params.addParam<std::vector<std::string>>("constant_names", {}, "Vector of constants used in the parsed function");
+  params.addParam<std::vector<std::string>>("constant_expressions", {}, "Vector of values for the constants in constant_names (can be an FParser expression)");
+  params.addParam<MooseEnum>("expand", MooseEnum("REAL RECIPROCAL NONE", "NONE"), "Expand the tensor to full size.");
+  params.addParam<bool>("is_integer", false, "Turn the function result into an integer tensor");
+  return params;
+}
+
+ParsedCompute::ParsedCompute(const InputParameters &parameters) : TensorOperator<>(parameters), _extra_symbols(getParam<bool>("extra_symbols")) {
+  const auto expression = getParam<std::string>("expression");
+  const auto names = getParam<std::vector<TensorInputBufferName>>("inputs");
+  const auto derivatives = getParam<std::vector<TensorInputBufferName>>("derivatives");
+  if (getParam<bool>("is_integer")) paramError("is_integer", "integer tensors are not on the spectral path and are not supported by marlin_b200");
+
+  // derivatives must name inputs (ParsedCompute.C:150-157)
+  for (const auto &d : derivatives) {
+    bool ok = false;
+    for (const auto &n : names) ok = ok || n == d;
+    if (!ok) paramError("derivatives", "Derivative w.r.t `", d, "` was requested, but it is not listed in `inputs`.");
+  }
+  // constants: each expression may use the previously evaluated ones (ParsedCompute.C:104-123)
+  const auto cnames = getParam<std::vector<std::string>>("constant_names");
+  const auto cexprs = getParam<std::vector<std::string>>("constant_expressions");
+  if (cnames.size() != cexprs.size()) paramError("constant_names", "Must have the same number of entries as 'constant_expressions'.");
+  std::vector<double> cvals;
+  for (size_t i = 0; i < cnames.size(); ++i) {
+    std::vector<const char *> nm;
+    for (size_t j = 0; j < i; ++j) nm.push_back(cnames[j].c_str());
+    double v = 0;
+    if (mrl_expr_constant(cexprs[i].c_str(), (int)i, nm.data(), cvals.data(), &v) != MRL_OK)
+      paramError("constant_expressions", "Invalid constant expression '", cexprs[i], "': ", mrl_last_error());
+    cvals.push_back(v);
+  }
+  for (const auto &n : names) _params.push_back(&getInputBufferByName(n));
+
+  const auto expand = getParam<MooseEnum>("expand");
+  const int ex = expand == "REAL" ? MRL_EXPAND_REAL : (expand == "RECIPROCAL" ? MRL_EXPAND_RECIPROCAL : MRL_EXPAND_NONE);
+  _kernel.configure(expression, names, derivatives, cnames, cvals, _extra_symbols, ex);
+  // parse now so that syntax errors surface at construction, like the reference
+  try {
+    _kernel.simplified();
+  } catch (const MooseException &e) {
+    paramError("expression", "Invalid function\n", expression, "\nin ParsedCompute.\n", e.what());
+  }
+}
+
+void ParsedCompute::computeBuffer() { _u = _kernel.eval(_domain, _params, _time); }
+
+// ----------------------------------------------------------------------------------- FFTGradient
+registerMooseObject("MarlinApp", FFTGradient);
+
+InputParameters FFTGradient::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Tensor gradient.");
+  params.addRequiredParam<TensorInputBufferName>("input", "Input buffer name");
+  params.addParam<bool>("input_is_reciprocal", false, "Input buffer is already in reciprocal space");
+  params.addRequiredParam<MooseEnum>("direction", MooseEnum("X=0 Y=1 Z=2"), "Which axis to take the gradient along.");
+  return params;
+}
+
+static const char *const kAxisName[3] = {"kx", "ky", "kz"};
+
+FFTGradient::FFTGradient(const InputParameters &parameters)
+  : TensorOperator<>(parameters),
+    _input(getInputBuffer("input")),
+    _input_is_reciprocal(getParam<bool>("input_is_reciprocal")),
+    _direction(int(getParam<MooseEnum>("direction"))) {
+  // ifft(ubar * k_d * i): the multiplication is one generated kernel
+  _kernel.configure(std::string("ubar*") + kAxisName[_direction] + "*i", {"ubar"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+}
+
+void FFTGradient::computeBuffer() {
+  Tensor ubar = _input_is_reciprocal ? _input : _domain.fft(_input);
+  _u = _domain.ifft(_kernel.eval(_domain, {&ubar}, _time));
+}
+
+// ----------------------------------------------------------------------------- FFTGradientSquare
+registerMooseObject("MarlinApp", FFTGradientSquare);
+
+InputParameters FFTGradientSquare::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Tensor gradient.");
+  params.addRequiredParam<TensorInputBufferName>("input", "Input buffer name");
+  params.addParam<bool>("input_is_reciprocal", false, "Input buffer is already in reciprocal space");
+  params.addParam<Real>("factor", 1.0, "Prefactor to the gradient square");
+  return params;
+}
+
+FFTGradientSquare::FFTGradientSquare(const InputParameters &parameters)
+  : TensorOperator<>(parameters), _input(getInputBuffer("input")), _input_is_reciprocal(getParam<bool>("input_is_reciprocal")), _factor(getParam<Real>("factor")) {
+  for (unsigned int d = 0; d < _dim; ++d) _grad[d].configure(std::string("ubar*") + kAxisName[d] + "*i", {"ubar"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+  // (gx^2 [+ gy^2 [+ gz^2]]) [* factor], summed in the reference's order
+  std::string e = "gx*gx";
+  std::vector<std::string> in = {"gx"};
+  if (_dim > 1) {
+    e = e + " + gy*gy";
+    in.push_back("gy");
+  }
+  if (_dim > 2) {
+    e = e + " + gz*gz";
+    in.push_back("gz");
+  }
+  if (_factor != 1.0) e = "(" + e + ")*factor";
+  _square.configure(e, in, {}, {"factor"}, {_factor}, false, MRL_EXPAND_NONE);
+}
+
+void FFTGradientSquare::computeBuffer() {
+  Tensor ubar = _input_is_reciprocal ? _input : _domain.fft(_input);
+  std::vector<Tensor> g(_dim);
+  std::vector<const Tensor *> gp;
+  for (unsigned int d = 0; d < _dim; ++d) {
+    g[d] = _domain.ifft(_grad[d].eval(_domain, {&ubar}, _time));
+    gp.push_back(&g[d]);
+  }
+  _u = _square.eval(_domain, gp, _time);
+}
+
+// ------------------------------------------------------------------------------- FFTSemiImplicit
+registerMooseObject("MarlinApp", FFTSemiImplicit);
+
+InputParameters FFTSemiImplicit::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Semi-implicit time integrator.");
+  params.addRequiredParam<TensorInputBufferName>("reciprocal_buffer", "Buffer with the reciprocal of the integrated buffer");
+  params.addRequiredParam<TensorInputBufferName>("linear_reciprocal", "Buffer with the reciprocal of the linear prefactor (e.g. kappa*k^2)");
+  params.addRequiredParam<TensorInputBufferName>("nonlinear_reciprocal", "Buffer with the reciprocal of the non-linear contribution");
+  params.addParam<unsigned int>("history_size", 1, "How many old states to use (determines time integration order).");
+  return params;
+}
+
+FFTSemiImplicit::FFTSemiImplicit(const InputParameters &parameters)
+  : TensorOperator<>(parameters),
+    _history_size(getParam<unsigned int>("history_size")),
+    _sub_dt(_tensor_problem.subDt()),
+    _reciprocal_buffer(getInputBuffer("reciprocal_buffer")),
+    _linear_reciprocal(getInputBuffer("linear_reciprocal")),
+    _non_linear_reciprocal(getInputBuffer("nonlinear_reciprocal")),
+    _old_reciprocal_buffer(_tensor_problem.getBufferOld(getParam<TensorInputBufferName>("reciprocal_buffer"), _history_size)),
+    _old_non_linear_reciprocal(_tensor_problem.getBufferOld(getParam<TensorInputBufferName>("nonlinear_reciprocal"), _history_size)) {}
+
+void FFTSemiImplicit::computeBuffer() {
+  // the legacy integrator is used as a plain compute: the sub step equals the MOOSE step unless a solver set it
+  const Real dt = _sub_dt != 0.0 ? _sub_dt : _tensor_problem.dt();
+  const auto n_old = std::min(_old_reciprocal_buffer.size(), _old_non_linear_reciprocal.size());
+  Tensor ubar = _domain.empty(Space::RECIPROCAL, true, 1);
+  if (n_old == 0) {
+    const double beta[1] = {1.0};
+    checkC(mrl_ab_update(_domain.context(), ubar.data_ptr(), _reciprocal_buffer.data_ptr(), _non_linear_reciprocal.data_ptr(), _linear_reciprocal.data_ptr(), dt,
+                         beta, 0, nullptr),
+           "mrl_ab_update");
+  } else {
+    const double beta[2] = {1.5, -0.5};
+    const void *old[1] = {_old_non_linear_reciprocal[0].data_ptr()};
+    checkC(mrl_ab_update(_domain.context(), ubar.data_ptr(), _reciprocal_buffer.data_ptr(), _non_linear_reciprocal.data_ptr(), _linear_reciprocal.data_ptr(), dt,
+                         beta, 1, old),
+           "mrl_ab_update");
+  }
+  _u = _domain.ifft(ubar);
+}

@@ -1,0 +1,148 @@
+// Postprocessors on tensor buffers (reference citations in include/TensorPostprocessor.h).
+#include "TensorPostprocessor.h"
+
+#include <cmath>
+
+#include "TensorComputes.h"
+
+using marlin::Space;
+using marlin::Tensor;
+
+InputParameters TensorPostprocessor::validParams() {
+  InputParameters params = MooseObject::validParams();
+  params.registerBase("Postprocessor");
+  params.addClassDescription("A normal Postprocessor acting on a Tensor buffer.");
+  params.addRequiredParam<TensorInputBufferName>("buffer", "The buffer this compute is operating on");
+  params.addParam<std::string>("execute_on", "TIMESTEP_END", "When to execute (INITIAL, TIMESTEP_BEGIN, TIMESTEP_END, FINAL)");
+  params.addParam<std::vector<std::string>>("outputs", "Accepted for input compatibility");
+  params.addPrivateParam<TensorProblem *>("_tensor_problem", nullptr);
+  return params;
+}
+
+TensorPostprocessor::TensorPostprocessor(const InputParameters &parameters)
+  : MooseObject(parameters),
+    _tensor_problem(*getCheckedPointerParam<TensorProblem>("_tensor_problem")),
+    _domain(_tensor_problem.domain()),
+    _buffer_name(getParam<TensorInputBufferName>("buffer")),
+    _buffer_base(_tensor_problem.getBufferBase(_buffer_name)),
+    _u(_buffer_base.getRawTensor()),
+    _execute_on(parseExecFlags(getParam<std::string>("execute_on"), _path + "/execute_on")) {}
+
+namespace {
+
+class TensorAveragePostprocessor : public TensorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Compute the average value over a buffer.");
+    return params;
+  }
+  using TensorPostprocessor::TensorPostprocessor;
+  void execute() override {
+    if (!_u.defined()) mooseError("buffer '", _buffer_name, "' is not defined");
+    _sum = _domain.sum(_u);
+    _numel = Real(_u.numel());
+  }
+  void finalize() override { _average = _sum / _numel; }
+  Real getValue() const override { return _average; }
+
+protected:
+  Real _sum = 0, _numel = 0, _average = 0;
+};
+
+class TensorIntegralPostprocessor : public TensorAveragePostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorAveragePostprocessor::validParams();
+    params.addClassDescription("Compute the integral over a buffer");
+    return params;
+  }
+  using TensorAveragePostprocessor::TensorAveragePostprocessor;
+  void finalize() override {
+    TensorAveragePostprocessor::finalize();
+    Real volume = 1.0;
+    for (unsigned int d = 0; d < _domain.getDim(); ++d) volume *= _domain.getDomainMax()[d] - _domain.getDomainMin()[d];
+    _integral = _average * volume;
+  }
+  Real getValue() const override { return _integral; }
+
+protected:
+  Real _integral = 0;
+};
+
+class TensorExtremeValuePostprocessor : public TensorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Find extreme values in the Tensor buffer");
+    params.addRequiredParam<MooseEnum>("value_type", MooseEnum("MIN MAX"), "Extreme value type");
+    return params;
+  }
+  explicit TensorExtremeValuePostprocessor(const InputParameters &p) : TensorPostprocessor(p), _is_min(getParam<MooseEnum>("value_type") == "MIN") {}
+  void execute() override {
+    if (!_u.defined()) mooseError("buffer '", _buffer_name, "' is not defined");
+    _value = _domain.reduce(_is_min ? MRL_MIN : MRL_MAX, _u);
+  }
+  Real getValue() const override { return _value; }
+
+protected:
+  const bool _is_min;
+  Real _value = 0;
+};
+
+class TensorIntegralChangePostprocessor : public TensorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Compute the integral of the absolute change of a buffer over a time step");
+    return params;
+  }
+  explicit TensorIntegralChangePostprocessor(const InputParameters &p) : TensorPostprocessor(p), _u_old(_tensor_problem.getBufferOld(_buffer_name, 1)) {
+    _diff.configure("abs(u - u_old)", {"u", "u_old"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+    _abs.configure("abs(u)", {"u"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  }
+  void execute() override {
+    if (!_u.defined()) mooseError("buffer '", _buffer_name, "' is not defined");
+    Tensor d = !_u_old.empty() && _u_old[0].defined() ? _diff.eval(_domain, {&_u, &_u_old[0]}, 0.0) : _abs.eval(_domain, {&_u}, 0.0);
+    _integral = _domain.sum(d);
+    for (unsigned int dd = 0; dd < _domain.getDim(); ++dd) _integral *= _domain.getGridSpacing()[dd];
+  }
+  Real getValue() const override { return _integral; }
+
+protected:
+  const std::vector<Tensor> &_u_old;
+  ExprKernel _diff, _abs;
+  Real _integral = 0;
+};
+
+class SemiImplicitCriticalTimeStep : public TensorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Compute the critical timestep given the reciprocal space representation of the linear operator in a semi-implicit time integrator.");
+    params.addParam<Real>("c", 1.0, "Courant number (CFL factor)");
+    return params;
+  }
+  explicit SemiImplicitCriticalTimeStep(const InputParameters &p) : TensorPostprocessor(p) {
+    _norm.configure("L*L", {"L"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  }
+  void execute() override {
+    if (!_u.defined()) mooseError("buffer '", _buffer_name, "' is not defined");
+    if (_u.is_complex()) mooseError("the linear operator buffer is expected to be real");
+    const Real max_norm_k = std::sqrt(_domain.reduce(MRL_MAX, _norm.eval(_domain, {&_u}, 0.0)));
+    _critical_dt = max_norm_k > 0.0 ? 1.0 / max_norm_k : 1e30;
+  }
+  Real getValue() const override { return _critical_dt; }
+
+protected:
+  ExprKernel _norm;
+  Real _critical_dt = 0;
+};
+
+}  // namespace
+
+registerMooseObject("MarlinApp", TensorAveragePostprocessor);
+registerMooseObject("MarlinApp", TensorIntegralPostprocessor);
+registerMooseObject("MarlinApp", TensorExtremeValuePostprocessor);
+registerMooseObject("MarlinApp", TensorIntegralChangePostprocessor);
+registerMooseObject("MarlinApp", SemiImplicitCriticalTimeStep);
