@@ -3,6 +3,7 @@
 #include <cctype>
 #include <cmath>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <map>
 #include <sstream>
@@ -215,7 +216,7 @@ void parse_into(Node *root, const std::string &text, const std::string &fname) {
 }
 
 // ${...} expansion ----------------------------------------------------------------------
-const Node *lookup(const Node *from, const std::string &name) {
+const Node *lookup(const Node *from, const std::string &name, const Node *self = nullptr) {
   // search the enclosing scopes from the innermost outwards (hit semantics)
   if (name.find('/') != std::string::npos) {
     const Node *root = from;
@@ -223,8 +224,11 @@ const Node *lookup(const Node *from, const std::string &name) {
     const Node *n = root->find(name);
     return (n && !n->is_section) ? n : nullptr;
   }
+  // the field being expanded never resolves to itself: `dt = ${dt}` inside a block refers to the
+  // enclosing scope's dt (MOOSE inputs rely on this, e.g. [Executioner] dt = ${dt})
   for (const Node *s = from; s; s = s->parent)
-    if (const Node *f = s->field(name)) return f;
+    if (const Node *f = s->field(name))
+      if (f != self) return f;
   return nullptr;
 }
 
@@ -237,6 +241,7 @@ std::string fmt_num(double v) {
 struct Expander {
   const std::string &fname;
   std::map<const Node *, int> state;  // 1 = in progress, 2 = done
+  const Node *current = nullptr;      // field whose value is being expanded
   explicit Expander(const std::string &f) : fname(f) {}
 
   std::string expand_text(const Node *scope, const std::string &v, int line) {
@@ -277,7 +282,7 @@ struct Expander {
           while (j < expr.size() && (std::isalnum((unsigned char)expr[j]) || expr[j] == '_')) ++j;
           const std::string id = expr.substr(i, j - i);
           const bool is_call = j < expr.size() && expr[j] == '(';
-          const Node *f = is_call ? nullptr : lookup(scope, id);
+          const Node *f = is_call ? nullptr : lookup(scope, id, current);
           resolved += (f && id != "pi" && id != "e") ? "(" + value_of(f) + ")" : id;
           i = j;
         } else {
@@ -306,7 +311,7 @@ struct Expander {
     }
     std::string extra;
     if (is >> extra) throw err("unknown brace command '" + cmd + "'");
-    const Node *f = lookup(scope, cmd);
+    const Node *f = lookup(scope, cmd, current);
     if (!f) throw err("no variable '" + cmd + "' found for substitution");
     return value_of(f);
   }
@@ -316,7 +321,11 @@ struct Expander {
     if (st == 1) throw std::runtime_error(fname + ":" + std::to_string(f->line) + ": circular variable reference '" + f->name + "'");
     if (st == 0) {
       st = 1;
-      const_cast<Node *>(f)->value = expand_text(f->parent, f->value, f->line);
+      const Node *outer = current;
+      current = f;
+      const std::string v = expand_text(f->parent, f->value, f->line);
+      current = outer;
+      const_cast<Node *>(f)->value = v;
       state[f] = 2;
     }
     return f->value;
@@ -331,12 +340,41 @@ struct Expander {
     }
   }
 };
+// `!include other.i` on a line of its own pulls that file in (path relative to the including file)
+std::string splice_includes(const std::string &text, const std::string &fname, int depth) {
+  if (text.find("!include") == std::string::npos) return text;
+  if (depth > 16) throw std::runtime_error(fname + ": !include nested too deeply");
+  const size_t sl = fname.rfind('/');
+  const std::string dir = sl == std::string::npos ? "" : fname.substr(0, sl + 1);
+  std::istringstream is(text);
+  std::string line, out;
+  int lineno = 0;
+  while (std::getline(is, line)) {
+    ++lineno;
+    const size_t b = line.find_first_not_of(" \t");
+    if (b != std::string::npos && line.compare(b, 8, "!include") == 0) {
+      std::vector<std::string> w = split_ws(line.substr(b + 8));
+      if (w.size() != 1) throw std::runtime_error(fname + ":" + std::to_string(lineno) + ": !include takes one file name");
+      const std::string path = w[0][0] == '/' ? w[0] : dir + w[0];
+      std::ifstream in(path);
+      if (!in) throw std::runtime_error(fname + ":" + std::to_string(lineno) + ": cannot open included file '" + path + "'");
+      std::stringstream ss;
+      ss << in.rdbuf();
+      out += splice_includes(ss.str(), path, depth + 1);
+      out += "\n";
+    } else {
+      out += line;
+      out += "\n";
+    }
+  }
+  return out;
+}
 }  // namespace
 
 std::unique_ptr<Node> parse(const std::string &text, const std::string &fname, const std::vector<std::string> &overrides) {
   auto root = std::make_unique<Node>();
   root->name = "";
-  parse_into(root.get(), text, fname);
+  parse_into(root.get(), splice_includes(text, fname, 0), fname);
   for (const std::string &o : overrides) {
     const size_t eq = o.find('=');
     if (eq == std::string::npos) throw std::runtime_error("command line override '" + o + "' is not of the form path/key=value");

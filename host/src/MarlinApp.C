@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
@@ -32,6 +33,7 @@ struct Options {
   std::vector<std::string> overrides;
   bool check_only = false;
   bool list_objects = false;
+  bool parse_only = false;  // print the resolved input tree (no device needed)
   std::string output_dir;
   std::vector<std::string> dump;
   std::string dump_dir = ".";
@@ -357,6 +359,18 @@ int MarlinApp::run() {
   } catch (const std::exception &e) {
     mooseError(e.what());
   }
+  if (_opt.parse_only) {
+    // one `path = value` line per field, after ${...} expansion, overrides and active/inactive filtering
+    std::function<void(const hit::Node &)> walk = [&](const hit::Node &n) {
+      for (const hit::Node *f : n.fields()) std::cout << f->fullpath() << " = " << f->value << "\n";
+      for (const hit::Node *s : n.sections()) {
+        std::cout << "[" << s->fullpath() << "]\n";
+        walk(*s);
+      }
+    };
+    walk(*_root);
+    return 0;
+  }
   buildObjects();
   transient();
   // tear down in dependency order: objects -> buffers -> pool -> context
@@ -385,6 +399,8 @@ int main(int argc, char **argv) {
       opt.check_only = true;
     else if (a == "--list-objects")
       opt.list_objects = true;
+    else if (a == "--parse-only")
+      opt.parse_only = true;
     else if (a == "--output-dir")
       opt.output_dir = need("--output-dir");
     else if (a == "--dump") {

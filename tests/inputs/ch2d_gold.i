@@ -1,0 +1,124 @@
+# 20x20 Cahn-Hilliard spinodal decomposition, semi-implicit AB2, 10 steps x 10 substeps.
+# Same physical setup as the reference's test/tests/cahnhilliard (whose gold results the host test
+# compares with).  The finite-element side blocks ([AuxVariables], [AuxKernels], exodus output) are
+# left in on purpose: the stand-alone driver must report and skip them.
+[Domain]
+  dim = 2
+  nx = 20
+  ny = 20
+  xmax = 3
+  ymax = 3
+  mesh_mode = DOMAIN
+[]
+
+[TensorComputes]
+  [Initialize]
+    [c]
+      type = RandomTensor
+      buffer = c
+      min = 0.44
+      max = 0.56
+      seed = 0
+    []
+    [mu_init]
+      type = ConstantTensor
+      buffer = mu
+    []
+    [Mbar]
+      type = ReciprocalLaplacianFactor
+      buffer = Mbar
+      factor = 0.2
+    []
+    [kappabarbar]
+      type = ReciprocalLaplacianSquareFactor
+      buffer = kappabarbar
+      factor = -0.001
+    []
+  []
+  [Solve]
+    [cahn_hilliard]
+      [mu]
+        type = ParsedCompute
+        buffer = mu
+        expression = '0.1*c^2*(c-1)^2'
+        derivatives = c
+        inputs = c
+      []
+      [mubar]
+        type = ForwardFFT
+        buffer = mubar
+        input = mu
+      []
+      [Mbarmubar]
+        type = ParsedCompute
+        buffer = Mbarmubar
+        expression = 'Mbar*mubar'
+        inputs = 'Mbar mubar'
+      []
+      [cbar]
+        type = ForwardFFT
+        buffer = cbar
+        input = c
+      []
+    []
+  []
+[]
+
+[TensorSolver]
+  type = AdamsBashforthMoulton
+  root_compute = cahn_hilliard
+  buffer = c
+  reciprocal_buffer = cbar
+  linear_reciprocal = kappabarbar
+  nonlinear_reciprocal = Mbarmubar
+  substeps = 10
+[]
+
+[AuxVariables]
+  [mu]
+    family = MONOMIAL
+    order = CONSTANT
+  []
+  [c]
+  []
+[]
+
+[AuxKernels]
+  active = ''
+  [c]
+    type = ProjectTensorAux
+    buffer = c
+    variable = c
+  []
+[]
+
+[Postprocessors]
+  [dt_crit]
+    type = SemiImplicitCriticalTimeStep
+    buffer = kappabarbar
+    execute_on = 'INITIAL TIMESTEP_END'
+  []
+  [delta_int_c]
+    type = TensorIntegralChangePostprocessor
+    buffer = c
+  []
+  [int_c]
+    type = TensorIntegralPostprocessor
+    buffer = c
+  []
+[]
+
+[Problem]
+  type = TensorProblem
+[]
+
+[Executioner]
+  type = Transient
+  num_steps = 10
+  dt = 1e-3
+[]
+
+[Outputs]
+  exodus = true
+  csv = true
+[]

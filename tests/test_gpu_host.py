@@ -1,0 +1,132 @@
+"""The stand-alone host driver (marlin_b200-opt: MOOSE-style TensorProblem / TensorOperator /
+TensorSolver objects over the C ABI) run on input files, against the reference's own gold
+results (tests/golden/*.npz) and the oracle.  GPU only."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_cases as oc
+from oracle import marlin as om
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APP = os.path.join(ROOT, "marlin_b200", "marlin_b200-opt")
+INP = os.path.join(ROOT, "tests", "inputs")
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def run(tmp, inp, *args, dump=()):
+    cmd = [APP, "-i", f"{INP}/{inp}", "--output-dir", str(tmp), *args]
+    if dump:
+        cmd += ["--dump", ",".join(dump), "--dump-dir", str(tmp)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r
+
+
+def field(tmp, name, shape):
+    return np.fromfile(f"{tmp}/{name}.f64", dtype=np.float64).reshape(shape)
+
+
+def csv(path):
+    with open(path) as fh:
+        head = fh.readline().strip().split(",")
+        rows = np.array([[float(x) for x in ln.split(",")] for ln in fh if ln.strip()])
+    return head, rows
+
+
+@pytest.mark.parametrize("steps", [1, 3, 10])
+def test_ch2d_input_matches_exodus_gold(tmp_path, steps):
+    """test/tests/cahnhilliard/cahnhilliard.i -> gold/cahnhilliard_out.e; AB1 during the first
+    MOOSE step (quirk Q1), AB2 afterwards."""
+    g = np.load(f"{G}/ch2d_exodus.npz")
+    r = run(tmp_path, "ch2d_gold.i", f"Executioner/num_steps={steps}", dump=("c", "mu"))
+    assert "AuxKernels" in r.stderr                      # finite-element blocks reported, skipped
+    c, mu = field(tmp_path, "c", (20, 20)), field(tmp_path, "mu", (20, 20))
+    assert np.abs(c - g["c"][steps]).max() < 1e-12
+    assert np.abs(mu - g["mu"][steps]).max() < 1e-12
+    head, rows = csv(f"{tmp_path}/ch2d_gold_out.csv")
+    assert head == ["time", "delta_int_c", "dt_crit", "int_c"] and rows.shape[0] == steps + 1
+    assert abs(rows[-1, 0] - steps * 1e-3) < 1e-15
+    dx = 3.0 / 20
+    assert abs(rows[-1, 3] - g["c"][steps].sum() * dx * dx) < 1e-12
+    assert np.abs(rows[:, 1]).max() < 1e-12              # mass is conserved
+
+
+@pytest.mark.parametrize("ss,cs,order", [(10, 0, 1), (10, 0, 2), (10, 0, 3), (20, 0, 4),
+                                         (10, 1, 1), (10, 2, 1), (10, 2, 2)])
+def test_abm_diagonal_input_matches_csv_gold(tmp_path, ss, cs, order):
+    """test/tests/solvers/diagonal.i with the cli_args of test/tests/solvers/tests."""
+    gold = np.load(f"{G}/csv_golds.npz")[f"diagonal_{ss}_{cs}_{order}"]
+    run(tmp_path, "abm_diagonal.i", f"ss={ss}", f"cs={cs}", f"order={order}")
+    head, rows = csv(f"{tmp_path}/abm_diagonal_{ss}_{cs}_{order}.csv")
+    assert head == ["time", "U", "V", "u_max", "u_min", "v_max", "v_min"]
+    assert rows.shape == gold.shape
+    err = np.abs(rows - gold) / np.maximum(np.abs(gold), 1e-8)
+    assert err[1:].max() < 1e-9, err.max()
+
+
+def test_etdrk4_input_matches_csv_gold(tmp_path):
+    """test/tests/solvers/etdrk4_diffusion.i -> gold/etdrk4_diffusion_rmse.csv (time,mse,rmse);
+    rmse is a MOOSE ParsedPostprocessor = sqrt(mse) (skipped by the driver, formed here)."""
+    gold = np.load(f"{G}/csv_golds.npz")["etdrk4_diffusion_rmse"]
+    run(tmp_path, "etdrk4_decay.i")
+    head, rows = csv(f"{tmp_path}/etdrk4_decay.csv")
+    assert head == ["time", "mse"] and rows.shape[0] == gold.shape[0]
+    assert np.abs(rows[:, 0] - gold[:, 0]).max() < 1e-12
+    # the gold values are round-off sized (1e-30 .. 1e-29): CSVDiff passes on abs_zero; same here
+    assert np.abs(rows[:, 1]).max() < 1e-10 and np.abs(np.sqrt(rows[:, 1]) - gold[:, 2]).max() < 1e-10
+
+
+def test_gradient_input(tmp_path):
+    """test/tests/gradient/gradient.i (+ gradient_square.i): error integrals at round-off level
+    like the gold CSVs (7.6e-12 / 1.5e-11)."""
+    run(tmp_path, "fft_gradient.i")
+    head, rows = csv(f"{tmp_path}/fft_gradient_out.csv")
+    assert head == ["time", "diff", "gsq"]
+    vol = 2 * math.pi * 4 * math.pi * 6 * math.pi
+    assert 0 <= rows[-1, 1] < 1e-10
+    assert abs(rows[-1, 2] - 0.5 * 1.5 * vol) < 1e-9 * vol
+
+
+def test_mech3d_input_matches_hdf5_gold(tmp_path):
+    """test/tests/mechanics/mech3d.i -> gold/mech3d.h5 (deformation gradient after 3 steps)."""
+    g = np.load(f"{G}/mech3d_h5.npz")["F"]
+    run(tmp_path, "mech3d_shear.i", dump=("F",))
+    F = field(tmp_path, "F", (9, 16, 16, 16))            # rank-two fields are component major
+    ref = np.moveaxis(g[2].reshape(16, 16, 16, 9), -1, 0)
+    rel = np.linalg.norm(F - ref) / np.linalg.norm(ref)
+    assert rel < 1e-9, rel
+    for k in (1, 2):
+        run(tmp_path, "mech3d_shear.i", f"Executioner/num_steps={k}", dump=("F",))
+        F = field(tmp_path, "F", (9, 16, 16, 16))
+        ref = np.moveaxis(g[k - 1].reshape(16, 16, 16, 9), -1, 0)
+        assert np.linalg.norm(F - ref) / np.linalg.norm(ref) < 1e-9
+
+
+def test_ch3d_input_matches_oracle(tmp_path):
+    """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
+    the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""
+    n, L = 32, 32 * (8 * math.pi / 200)
+    run(tmp_path, "ch2d_gold.i", "Domain/dim=3", f"Domain/nx={n}", f"Domain/ny={n}", f"Domain/nz={n}",
+        f"Domain/xmax={L!r}", f"Domain/ymax={L!r}", f"Domain/zmax={L!r}", "Executioner/num_steps=2",
+        "Executioner/dt=0.01", dump=("c",))
+    c = field(tmp_path, "c", (n, n, n))
+    p = oc.ch_problem(3, n, L, substeps=10)
+    p.initial()
+    for _ in range(2):
+        p.step(0.01)
+    ref = p.buf["c"].numpy()
+    assert np.linalg.norm(c - ref) / np.linalg.norm(ref) < 1e-10
+
+
+def test_unknown_parameter_and_type_are_errors(tmp_path):
+    r = subprocess.run([APP, "-i", f"{INP}/ch2d_gold.i", "TensorSolver/bogus=1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "bogus" in r.stderr
+    r = subprocess.run([APP, "-i", f"{INP}/ch2d_gold.i", "TensorSolver/type=NoSuchSolver"], capture_output=True, text=True)
+    assert r.returncode != 0 and "NoSuchSolver" in r.stderr

@@ -1,0 +1,105 @@
+"""Host layer checks that need no device: the stand-alone driver's object registry and its
+hit-subset input reader (host/shim/hit.C), on this repository's inputs and - in the build
+container only - on every input file the reference ships."""
+import glob
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+APP = os.path.join(ROOT, "marlin_b200", "marlin_b200-opt")
+INP = os.path.join(ROOT, "tests", "inputs")
+REF = "/root/reference"
+
+pytestmark = pytest.mark.skipif(not os.path.exists(APP), reason="host driver not built (make)")
+
+
+def run(*args, ok=True):
+    r = subprocess.run([APP, *args], capture_output=True, text=True, timeout=60)
+    assert (r.returncode == 0) == ok, r.stdout + r.stderr
+    return r
+
+
+def tree(*args):
+    out = {}
+    for line in run(*args, "--parse-only").stdout.splitlines():
+        if " = " in line:
+            k, v = line.split(" = ", 1)
+            out[k] = v
+    return out
+
+
+def test_registry_holds_the_hot_path_objects():
+    """registerMooseObject names of SURVEY.md 8(a)/(b) (src/base/MarlinApp.C:94-172 wiring)."""
+    names = set(run("--list-objects").stdout.split())
+    for n in ["TensorProblem", "ComputeGroup", "ForwardFFT", "InverseFFT", "ParsedCompute",
+              "ReciprocalLaplacianFactor", "ReciprocalLaplacianSquareFactor", "RandomTensor",
+              "ConstantTensor", "ConstantReciprocalTensor", "FFTGradient", "FFTGradientSquare",
+              "FFTSemiImplicit", "AdamsBashforthMoulton", "SemiImplicitSolver", "ForwardEulerSolver",
+              "ETDRK4Solver", "FFTMechanics", "HyperElasticIsotropic", "RankTwoIdentity",
+              "TensorAveragePostprocessor", "TensorIntegralPostprocessor",
+              "TensorExtremeValuePostprocessor", "TensorIntegralChangePostprocessor",
+              "SemiImplicitCriticalTimeStep"]:
+        assert n in names, n
+
+
+def test_fparse_units_and_top_level_variables():
+    t = tree("-i", f"{INP}/etdrk4_decay.i")
+    assert float(t["Domain/xmax"]) == pytest.approx(6.283185307179586, abs=0)
+    assert t["dt"] == "10" and t["Executioner/dt"] == "10"          # ${units 10 s}; dt = ${dt}
+    assert t["TensorComputes/Solve/u_exact/expression"] == "u0*exp(-0.05*1.0^2*t)"
+    assert t["TensorSolver/substeps"] == "1"
+
+
+def test_command_line_overrides():
+    t = tree("-i", f"{INP}/abm_diagonal.i", "ss=20", "cs=2", "order=4", "Domain/nx=64",
+             "Executioner/num_steps=3")
+    assert t["TensorSolver/substeps"] == "20" and t["TensorSolver/corrector_steps"] == "2"
+    assert t["TensorSolver/predictor_order"] == "4" and t["Domain/nx"] == "64"
+    assert t["Outputs/file_base"] == "abm_diagonal_20_2_4" and t["Executioner/num_steps"] == "3"
+    r = run("-i", f"{INP}/abm_diagonal.i", "--parse-only", ok=False)  # ${ss} undefined
+    assert "ss" in r.stderr
+
+
+def test_active_filter_and_quoted_lists():
+    out = run("-i", f"{INP}/ch2d_gold.i", "--parse-only").stdout
+    assert "[AuxKernels]" in out and "[AuxKernels/c]" not in out      # active = ''
+    t = tree("-i", f"{INP}/ch2d_gold.i")
+    assert t["TensorComputes/Solve/cahn_hilliard/Mbarmubar/inputs"] == "Mbar mubar"
+
+
+def test_syntax_errors_are_reported_with_line(tmp_path):
+    p = tmp_path / "bad.i"
+    p.write_text("[Domain]\n  dim = 2\n[TensorComputes]\n")
+    r = run("-i", str(p), "--parse-only", ok=False)
+    assert "bad.i" in r.stderr
+    p.write_text("[Domain]\n  dim = ${nope}\n[]\n")
+    r = run("-i", str(p), "--parse-only", ok=False)
+    assert "nope" in r.stderr and ":2" in r.stderr
+
+
+def test_include(tmp_path):
+    (tmp_path / "a.i").write_text("n = 7\n!include b.i\n")
+    (tmp_path / "b.i").write_text("[Domain]\n  nx = ${n}\n[]\n")
+    assert tree("-i", str(tmp_path / "a.i"))["Domain/nx"] == "7"
+
+
+def test_no_device_is_a_loud_error():
+    """There is no CPU path: building the objects without a GPU must fail, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    r = run("-i", f"{INP}/ch2d_gold.i", ok=False)
+    assert "no CPU path" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_every_reference_input_parses():
+    files = [f for d in ("examples", "benchmarks", "test/tests")
+             for f in glob.glob(f"{REF}/{d}/**/*.i", recursive=True)]
+    assert len(files) > 50
+    for f in files:
+        r = subprocess.run([APP, "-i", f, "--parse-only", "ss=10", "cs=0", "order=2"],
+                           capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, f + "\n" + r.stderr
