@@ -186,6 +186,66 @@ def libtorch_cuda_substep_ms(n, L, iters=3):
     return ms
 
 
+def mechanics_bench(n=256, peak=None):
+    """MECH-3D-n: test/tests/mechanics/mech3d.i at n^3 (two-phase cosine inclusion, one FFTMechanics
+    substep with applied shear 1e-3).  Times the CG operator G(K4:x) and the whole Newton-CG solve;
+    HBM rates against the algorithmic bytes of SURVEY.md 8(d): 29 S_r + 72 S_c per operator
+    application, 110 S_r + 72 S_c per CG iteration."""
+    import torch
+    from marlin_b200 import capi
+    L = 2 * math.pi
+    ctx = capi.Context(0, capi.F64)
+    ctx.use_torch_stream()
+    ctx.domain_set(3, (n, n, n), (0,) * 3, (L,) * 3)
+    ax = [ctx.axis(a).cuda() for a in range(3)]
+    ph = ((torch.cos(ax[0]) / 2 + 0.5).view(n, 1, 1) * (torch.cos(ax[1]) / 2 + 0.5).view(1, n, 1) *
+          (torch.cos(ax[2]) / 2 + 0.5).view(1, 1, n)).contiguous()
+    K = ((1 - ph) * 1.0 + ph * 10.0).contiguous()
+    mu = ((1 - ph) * 0.5 + ph * 5.0).contiguous()
+    plan = capi.MechPlan(ctx, K, mu, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2)
+    F = torch.zeros(9, n, n, n, dtype=torch.float64, device="cuda")
+    F[0] = F[4] = F[8] = 1.0
+    x = torch.rand(9, n, n, n, dtype=torch.float64, device="cuda") - 0.5
+    for _ in range(2):
+        plan.apply_GK(F, x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        plan.apply_GK(F, x)
+    e1.record()
+    torch.cuda.synchronize()
+    op_ms = e0.elapsed_time(e1) / reps
+    s_r, s_c = n ** 3 * 8, n * n * (n // 2 + 1) * 16
+    b_op, b_it = 29 * s_r + 72 * s_c, 110 * s_r + 72 * s_c
+    # one substep of mech3d.i: applied shear 0.001 (sub-time of the second substep)
+    applied = [0.0, 0.001, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+    l0 = ctx.launch_count()
+    e0.record()
+    P, st = plan.solve(F, applied)
+    e1.record()
+    torch.cuda.synchronize()
+    solve_ms = e0.elapsed_time(e1)
+    its = st.cg_iterations_total
+    it_ms = solve_ms / max(its, 1)
+    out = {
+        "workload": f"MECH-3D-{n}", "GK_ms": round(op_ms, 3), "GK_alg_gb": round(b_op / 1e9, 3),
+        "GK_gbs": round(b_op / 1e9 / (op_ms / 1e3), 1), "solve_ms": round(solve_ms, 2), "newton": st.newton_iterations,
+        "cg_iterations": list(st.cg_iterations[:st.cg_solves]), "ms_per_cg_iteration": round(it_ms, 3),
+        "cg_iteration_alg_gb": round(b_it / 1e9, 3), "cg_iteration_gbs": round(b_it / 1e9 / (it_ms / 1e3), 1),
+        "launches": ctx.launch_count() - l0, "final_rnorm": st.final_rnorm,
+        "Fmax": float(F.abs().max()), "Pnorm": float(torch.linalg.norm(P.reshape(-1)))}
+    if peak:
+        out["GK_frac"] = round(out["GK_gbs"] / peak, 4)
+        out["cg_iteration_frac"] = round(out["cg_iteration_gbs"] / peak, 4)
+    plan.close()
+    ctx.close()
+    del F, x, P, K, mu, ph
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world):
     import torch
     from marlin_b200 import capi
@@ -242,29 +302,35 @@ def run_ours(args, rank, world):
         acc = t if acc is None else [a + b for a, b in zip(acc, t)]
     pass_ms = [a / reps for a in acc]
 
-    # end to end through the C ABI with HOST buffers: H2D of c, substep, D2H of c, every step
-    out_host = torch.empty_like(host_c).pin_memory()
+    # end to end through the C ABI with HOST buffers: H2D of c, substep, D2H of c, every step.
+    # Two device fields and two pinned result buffers alternate, and the copies go through the
+    # staged-transfer entry points, so step k+1's upload and step k's download share the PCIe link
+    # in both directions while the kernels of step k run (mrl_upload_staged / mrl_download_staged).
     nbytes = host_c.numel() * 8
-    e2e_steps = max(3, min(args.steps, 10))
-    import ctypes as C
-    lib = capi.lib()
+    e2e_steps = max(4, min(args.steps, 10))
+    cbuf = [c, torch.empty_like(c)]
+    out_host = [torch.empty_like(host_c).pin_memory() for _ in range(2)]
 
-    def e2e_step():
-        lib.mrl_upload(ctx.h, C.c_void_p(c.data_ptr()), C.c_void_p(host_c.data_ptr()), C.c_size_t(nbytes))
-        plan.substep(c, dt, AB_BETA[1], 1)
+    def e2e_step(k):
+        b = k & 1
+        ctx.upload_staged(cbuf[b], host_c)
+        plan.substep(cbuf[b], dt, AB_BETA[1], 1)
         plan.advance_state()
-        lib.mrl_download(ctx.h, C.c_void_p(out_host.data_ptr()), C.c_void_p(c.data_ptr()), C.c_size_t(nbytes))
-        ctx.synchronize()
+        ctx.download_staged(out_host[b], cbuf[b])
 
-    e2e_step()
-    t0 = time.perf_counter()
+    def e2e_run(nsteps):
+        t0 = time.perf_counter()
+        for k in range(nsteps):
+            e2e_step(k)
+        ctx.staged_wait()
+        ctx.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    e2e_run(2)
     torch.cuda.synchronize()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e_ms = e2e_run(e2e_steps) / e2e_steps
+    # un-overlapped latency of ONE step (upload -> substep -> download -> host sees the result)
+    e2e_single_ms = min(e2e_run(1) for _ in range(3))
     clocks = sampler.stop()
 
     s_r, s_c, per_pass = algorithmic_bytes(n, 1)
@@ -293,7 +359,7 @@ def run_ours(args, rank, world):
             "step_alg_gb": round(b_alg / 1e9, 3), "passes": passes}
 
     # in-run comparisons
-    del out_host
+    del out_host, cbuf
     plan.close()
     del c
     torch.cuda.empty_cache()
@@ -302,6 +368,12 @@ def run_ours(args, rank, world):
     except Exception as ex:  # e.g. out of memory for the un-fused temporaries
         cufft_ms = None
         print(f"# libtorch-cuda comparison skipped: {ex}", file=sys.stderr)
+
+    try:
+        mech = mechanics_bench(256, peak)
+    except Exception as ex:
+        mech = None
+        print(f"# mechanics measurement skipped: {ex}", file=sys.stderr)
 
     cpu = None
     if not args.no_cpu:
@@ -325,11 +397,13 @@ def run_ours(args, rank, world):
                    "l2": f"inputs larger than L2 (each field {s_r / 1e9:.2f} GB vs 126 MB L2)", "parallelism": "1 GPU"},
         "clocks": clocks,
         "e2e": {"value": 1e3 / e2e_ms, "unit": "substeps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nbytes,
-                "d2h_bytes_per_step": nbytes},
+                "d2h_bytes_per_step": nbytes, "single_step_latency_ms": e2e_single_ms,
+                "note": "host wall clock over the pipelined steps; uploads/downloads of neighbouring steps overlap"},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
         "libtorch_cuda_ms_per_step": cufft_ms,
+        "mechanics": mech,
     }
     print(json.dumps(line), flush=True)
     ctx.close()

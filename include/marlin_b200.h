@@ -70,6 +70,19 @@ int mrl_memset(mrl_context *ctx, void *dev, int value, size_t bytes);
 int mrl_upload(mrl_context *ctx, void *dev, const void *host, size_t bytes);   /* async H2D */
 int mrl_download(mrl_context *ctx, void *host, const void *dev, size_t bytes); /* async D2H */
 int mrl_copy(mrl_context *ctx, void *dst_dev, const void *src_dev, size_t bytes);
+/* Staged transfers on the context's own copy streams, ordered against the compute stream by
+ * events so that they overlap the kernels of neighbouring steps (the reference overlaps output
+ * with compute through makeCPUCopy + one std::thread per output object,
+ * src/problems/TensorProblem.C:225-240, src/tensor_outputs/TensorOutput.C:44-81).
+ *  mrl_download_staged: D2H of `dev` as it is once the work queued so far has finished; returns
+ *    at once; the compute stream may run ahead (but must not overwrite `dev` - use a second buffer).
+ *  mrl_upload_staged: H2D into `dev` without waiting for the compute stream (it waits only for a
+ *    staged download of the same `dev`); work queued on the compute stream afterwards sees the data.
+ *  mrl_staged_wait: blocks the host until every staged transfer has completed.
+ * Host memory should be pinned.                                                            */
+int mrl_upload_staged(mrl_context *ctx, void *dev, const void *host, size_t bytes);
+int mrl_download_staged(mrl_context *ctx, void *host, const void *dev, size_t bytes);
+int mrl_staged_wait(mrl_context *ctx);
 
 /* ---- FFT: DomainAction::fft / ifft (include/actions/DomainAction.h:75-76;
  *      fftSerial src/actions/DomainAction.C:854-867, ifft :1054-1066) and the

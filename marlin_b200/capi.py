@@ -107,6 +107,20 @@ class Context:
     def synchronize(self):
         _ck(lib().mrl_synchronize(self.h))
 
+    # ---- staged host transfers (overlap with the compute stream; host tensors should be pinned)
+    def upload_staged(self, dev, host):
+        assert host.is_contiguous() and dev.is_contiguous() and host.numel() * host.element_size() == dev.numel() * dev.element_size()
+        _ck(lib().mrl_upload_staged(self.h, C.c_void_p(dev.data_ptr()), C.c_void_p(host.data_ptr()),
+                                    C.c_size_t(host.numel() * host.element_size())))
+
+    def download_staged(self, host, dev):
+        assert host.is_contiguous() and dev.is_contiguous() and host.numel() * host.element_size() == dev.numel() * dev.element_size()
+        _ck(lib().mrl_download_staged(self.h, C.c_void_p(host.data_ptr()), C.c_void_p(dev.data_ptr()),
+                                      C.c_size_t(host.numel() * host.element_size())))
+
+    def staged_wait(self):
+        _ck(lib().mrl_staged_wait(self.h))
+
     def launch_count(self):
         v = C.c_int64()
         _ck(lib().mrl_launch_count(self.h, C.byref(v)))

@@ -40,10 +40,12 @@ template <class T> __device__ __forceinline__ void second_pk(const M3<T> &F, T K
 }
 
 // mode 0: out = P = F S.   mode 1: out = K4 : x (x from memory).   mode 2: same with a spatially
-// constant x (9 values in xc) - the applied macroscopic strain.
+// constant x (9 values in xc) - the applied macroscopic strain.   mode 3: the CG direction update
+// fused in: x <- r + beta x (beta = scal[SC_BETA], x written back through xw), then out = K4 : x.
 template <class T>
 __global__ void __launch_bounds__(256) k_mech_pointwise(int mode, const T *F, const T *Kf, const T *muf, const T *x, M3<T> xc, T *out,
-                                                        long long n, T scale) {
+                                                        long long n, T scale, const T *r, T *xw, const double *scal) {
+  const double beta = mode == 3 ? scal[4 /* SC_BETA */] : 0.0;
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
     M3<T> Fm, S;
 #pragma unroll
@@ -61,6 +63,13 @@ __global__ void __launch_bounds__(256) k_mech_pointwise(int mode, const T *F, co
       if (mode == 1) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = x[c * n + v];
+      } else if (mode == 3) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const T pn = (T)((double)r[c * n + v] + beta * (double)x[c * n + v]);  // same arithmetic as VOP_XPBY
+          xw[c * n + v] = pn;
+          X.a[c / 3][c % 3] = pn;
+        }
       }
       T W[3][3];
 #pragma unroll
@@ -136,30 +145,57 @@ template <class T> __device__ __forceinline__ double block_sum(double acc) {
 // VOP_AXPY  : y += s a                 (s = host scalar)
 // VOP_SUB   : z = a - b                (r = b - A x)
 // VOP_COPY  : y = a
-template <class T>
-__global__ void __launch_bounds__(256) k_vec(int op, const T *a, const T *b, T *y, T *z, const double *scal, double s, long long n,
-                                             double *partials) {
-  double acc = 0;
-  const double alpha = (op == VOP_CG_XR) ? scal[SC_ALPHA] : (op == VOP_XPBY ? scal[SC_BETA] : s);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (op == VOP_DOT) {
-      acc += (double)a[i] * (double)b[i];
-    } else if (op == VOP_CG_XR) {
-      y[i] = (T)((double)y[i] + alpha * (double)a[i]);
-      const double r = (double)z[i] - alpha * (double)b[i];
-      z[i] = (T)r;
-      acc += r * r;
-    } else if (op == VOP_XPBY) {
-      y[i] = (T)((double)a[i] + alpha * (double)y[i]);
-    } else if (op == VOP_AXPY) {
-      y[i] = (T)((double)y[i] + alpha * (double)a[i]);
-    } else if (op == VOP_SUB) {
-      z[i] = (T)((double)a[i] - (double)b[i]);
-    } else {
-      y[i] = a[i];
-    }
+template <class T> struct Vec2 {};
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+
+template <class T> __device__ __forceinline__ double vec_elem(int op, double alpha, T a, T b, T &y, T &z) {
+  if (op == VOP_DOT) return (double)a * (double)b;
+  if (op == VOP_CG_XR) {
+    y = (T)((double)y + alpha * (double)a);
+    const double r = (double)z - alpha * (double)b;
+    z = (T)r;
+    return r * r;
   }
-  if (op == VOP_DOT || op == VOP_CG_XR) {
+  if (op == VOP_XPBY) y = (T)((double)a + alpha * (double)y);
+  else if (op == VOP_AXPY) y = (T)((double)y + alpha * (double)a);
+  else if (op == VOP_SUB) z = (T)((double)a - (double)b);
+  else y = a;
+  return 0.0;
+}
+
+// OP is a template parameter so that each operation loads and stores only its own operands;
+// two elements per thread and iteration (128-bit accesses for fp64), all loads of an iteration
+// issued before the first use.
+template <class T, int OP>
+__global__ void __launch_bounds__(256) k_vec(const T *a, const T *b, T *y, T *z, const double *scal, double s, long long n,
+                                             double *partials) {
+  typedef typename Vec2<T>::type V;
+  constexpr bool RA = true, RB = (OP == VOP_DOT || OP == VOP_CG_XR || OP == VOP_SUB);
+  constexpr bool RY = (OP == VOP_CG_XR || OP == VOP_XPBY || OP == VOP_AXPY), RZ = (OP == VOP_CG_XR);
+  constexpr bool WY = (OP == VOP_CG_XR || OP == VOP_XPBY || OP == VOP_AXPY || OP == VOP_COPY), WZ = (OP == VOP_CG_XR || OP == VOP_SUB);
+  double acc = 0;
+  const double alpha = (OP == VOP_CG_XR) ? scal[SC_ALPHA] : (OP == VOP_XPBY ? scal[SC_BETA] : s);
+  const long long n2 = n >> 1;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n2; i += nth) {
+    V va = RA ? reinterpret_cast<const V *>(a)[i] : V{0, 0};
+    V vb = RB ? reinterpret_cast<const V *>(b)[i] : V{0, 0};
+    V vy = RY ? reinterpret_cast<const V *>(y)[i] : V{0, 0};
+    V vz = RZ ? reinterpret_cast<const V *>(z)[i] : V{0, 0};
+    acc += vec_elem<T>(OP, alpha, va.x, vb.x, vy.x, vz.x);
+    acc += vec_elem<T>(OP, alpha, va.y, vb.y, vy.y, vz.y);
+    if (WY) reinterpret_cast<V *>(y)[i] = vy;
+    if (WZ) reinterpret_cast<V *>(z)[i] = vz;
+  }
+  if ((n & 1) && tid == 0) {
+    const long long i = n - 1;
+    T ea = a[i], eb = RB ? b[i] : T(0), ey = RY ? y[i] : T(0), ez = RZ ? z[i] : T(0);
+    acc += vec_elem<T>(OP, alpha, ea, eb, ey, ez);
+    if (WY) y[i] = ey;
+    if (WZ) z[i] = ez;
+  }
+  if (OP == VOP_DOT || OP == VOP_CG_XR) {
     const double r = block_sum<T>(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = r;
   }
@@ -211,10 +247,10 @@ static inline int ew_grid(long long total, const LaunchCtx &lc) {
 
 template <class T>
 cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
-                                  long long n, double scale) {
+                                  long long n, double scale, const T *r, T *xw, const double *scal) {
   M3<T> X;
   for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = xc ? (T)xc[c] : T(0);
-  k_mech_pointwise<T><<<ew_grid(n, lc), 256, 0, lc.stream>>>(mode, F, K, mu, x, X, out, n, (T)scale);
+  k_mech_pointwise<T><<<ew_grid(n, lc), 256, 0, lc.stream>>>(mode, F, K, mu, x, X, out, n, (T)scale, r, xw, scal);
   return cudaGetLastError();
 }
 template <class T>
@@ -225,7 +261,16 @@ cudaError_t launch_mech_project(const LaunchCtx &lc, cx<T> *A, const T *kx, cons
 template <class T>
 cudaError_t launch_vec(const LaunchCtx &lc, int op, const T *a, const T *b, T *y, T *z, double *scal, double s, long long n, int fin, int slot,
                        double *partials, int nblk) {
-  k_vec<T><<<nblk, 256, 0, lc.stream>>>(op, a, b, y, z, scal, s, n, partials);
+  for (const void *q : {(const void *)a, (const void *)b, (const void *)y, (const void *)z})
+    if ((unsigned long long)q & 15ull) return cudaErrorMisalignedAddress;
+  switch (op) {
+    case VOP_DOT: k_vec<T, VOP_DOT><<<nblk, 256, 0, lc.stream>>>(a, b, y, z, scal, s, n, partials); break;
+    case VOP_CG_XR: k_vec<T, VOP_CG_XR><<<nblk, 256, 0, lc.stream>>>(a, b, y, z, scal, s, n, partials); break;
+    case VOP_XPBY: k_vec<T, VOP_XPBY><<<nblk, 256, 0, lc.stream>>>(a, b, y, z, scal, s, n, partials); break;
+    case VOP_AXPY: k_vec<T, VOP_AXPY><<<nblk, 256, 0, lc.stream>>>(a, b, y, z, scal, s, n, partials); break;
+    case VOP_SUB: k_vec<T, VOP_SUB><<<nblk, 256, 0, lc.stream>>>(a, b, y, z, scal, s, n, partials); break;
+    default: k_vec<T, VOP_COPY><<<nblk, 256, 0, lc.stream>>>(a, b, y, z, scal, s, n, partials); break;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (op == VOP_DOT || op == VOP_CG_XR) {
@@ -247,7 +292,7 @@ template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *i
 
 #define INST(T)                                                                                                                   \
   template cudaError_t launch_mech_pointwise<T>(const LaunchCtx &, int, const T *, const T *, const T *, const T *, const double *, \
-                                                T *, long long, double);                                                          \
+                                                T *, long long, double, const T *, T *, const double *);                                                        \
   template cudaError_t launch_mech_project<T>(const LaunchCtx &, cx<T> *, const T *, const T *, const T *, int, int, int, int);    \
   template cudaError_t launch_vec<T>(const LaunchCtx &, int, const T *, const T *, T *, T *, double *, double, long long, int, int, \
                                      double *, int);                                                                              \

@@ -237,6 +237,62 @@ cudaError_t launch_fused_tma(const LaunchCtx &lc, const FusedIO<T> &io, const Sp
   }
 }
 
+// ------------------------------------------------------------------ mechanics: fused Green projection
+template <class T, class C, int TK, int NG>
+static cudaError_t mech_fused_tma_go(const LaunchCtx &lc, cx<T> *spec, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzv,
+                                     int ncp, const cx<T> *tw) {
+  constexpr size_t smem = (size_t)(NG * 3 * C::N * TK) * sizeof(cx<T>) + NG * 3 * 8 + 128;
+  static_assert(smem <= kSmemBudget, "mech_fused_tma: shared memory budget");
+  static_assert(NG * TK * C::TP <= 1024, "mech_fused_tma: block size");
+  MechFusedTmaIO<T> io;
+  io.out = spec;
+  io.n = n0;
+  io.ncols = n1 * ncp;
+  io.ncb = (io.ncols + TK - 1) / TK;
+  io.pitch = io.ncols;
+  io.field = (long long)n0 * io.ncols;
+  io.kx = kx; io.ky = ky; io.kz = kz;
+  io.ncp = ncp;
+  io.nzv = nzv;
+  io.scale = T(1);
+  CUtensorMap tm;
+  const unsigned long long rowb = (unsigned long long)io.pitch * sizeof(cx<T>);
+  cudaError_t e = make_map3<T>(&tm, spec, 2ull * io.ncols, io.n, 9, rowb, rowb * io.n, 2 * TK, C::N < 256 ? C::N : 256);
+  if (e != cudaSuccess) return e;
+  auto k = k_mech_fused_tma<T, C, TK, NG>;
+  int per_sm = 0;
+  e = kernel_prep((const void *)k, NG * TK * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long nwork = (3ll * io.ncb + NG - 1) / NG;
+  const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
+  k<<<grid, NG * TK * C::TP, smem, lc.stream>>>(tm, io, tw);
+  return cudaGetLastError();
+}
+
+// In place on spec = [9][n0][n1][ncp]: x-forward, Green projection, x-inverse (unnormalised).
+template <class T>
+cudaError_t launch_mech_fused_tma(const LaunchCtx &lc, cx<T> *spec, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzv,
+                                  int ncp, const cx<T> *tw) {
+  if (!tma_enabled() || env_int("MRL_MECH_FUSED", 1) == 0) return cudaErrorNotSupported;
+  if constexpr (sizeof(T) == 8) {
+    switch (n0) {
+      case 128: return mech_fused_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      case 256: return mech_fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 2>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      case 512: return mech_fused_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      case 1024: return mech_fused_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 1>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      default: return cudaErrorNotSupported;
+    }
+  } else {
+    switch (n0) {
+      case 128: return mech_fused_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 16, 2>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      case 256: return mech_fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 16, 2>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      case 512: return mech_fused_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 2>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      case 1024: return mech_fused_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 8, 1>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      default: return cudaErrorNotSupported;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ P1 / P5
 template <class T, class C, int PPB, int NG, int NS, class F>
 static cudaError_t zfwd_tma_go(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int ncp,
@@ -369,6 +425,8 @@ cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp,
 }
 
 #define INST(T)                                                                                                          \
+  template cudaError_t launch_mech_fused_tma<T>(const LaunchCtx &, cx<T> *, const T *, const T *, const T *, int, int, int, int, \
+                                                const cx<T> *);                                                          \
   template cudaError_t launch_strided_tma<T>(const LaunchCtx &, const StridedIO<T> &, const cx<T> *, int);               \
   template cudaError_t launch_fused_tma<T>(const LaunchCtx &, const FusedIO<T> &, const SpectralUpdate<T> &, const cx<T> *, \
                                            int);                                                                         \

@@ -202,6 +202,15 @@ extern "C" int mrl_destroy(mrl_context *ctx) {
   cudaFree(ctx->scratch_ptr);
   cudaFree(ctx->reduce_dev);
   if (ctx->reduce_host) cudaFreeHost(ctx->reduce_host);
+  if (ctx->s_in) {
+    cudaStreamSynchronize(ctx->s_in);
+    cudaStreamSynchronize(ctx->s_out);
+    cudaStreamDestroy(ctx->s_in);
+    cudaStreamDestroy(ctx->s_out);
+    cudaEventDestroy(ctx->ev_in);
+    cudaEventDestroy(ctx->ev_compute);
+    for (auto &kv : ctx->dl_done) cudaEventDestroy(kv.second);
+  }
   delete ctx;
   return MRL_OK;
 }
@@ -291,6 +300,12 @@ extern "C" int mrl_malloc(mrl_context *ctx, size_t bytes, void **dev) {
 extern "C" int mrl_free(mrl_context *ctx, void *dev) {
   if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
   CK(cudaStreamSynchronize(ctx->stream));
+  auto it = ctx->dl_done.find(dev);
+  if (it != ctx->dl_done.end()) {
+    CK(cudaEventSynchronize(it->second));
+    cudaEventDestroy(it->second);
+    ctx->dl_done.erase(it);
+  }
   CK(cudaFree(dev));
   return MRL_OK;
 }
@@ -307,6 +322,45 @@ extern "C" int mrl_upload(mrl_context *ctx, void *dev, const void *host, size_t 
 extern "C" int mrl_download(mrl_context *ctx, void *host, const void *dev, size_t bytes) {
   if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
   CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return MRL_OK;
+}
+static int staged_init(mrl_context *ctx) {
+  if (ctx->s_in) return MRL_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+  return MRL_OK;
+}
+extern "C" int mrl_upload_staged(mrl_context *ctx, void *dev, const void *host, size_t bytes) {
+  if (!ctx || !dev || !host) return mrl_fail(MRL_ERR_INVALID, "mrl_upload_staged: bad arguments");
+  int rc = staged_init(ctx);
+  if (rc) return rc;
+  auto it = ctx->dl_done.find(dev);
+  if (it != ctx->dl_done.end()) CK(cudaStreamWaitEvent(ctx->s_in, it->second, 0));  // WAR against its last download
+  CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->s_in));
+  CK(cudaEventRecord(ctx->ev_in, ctx->s_in));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in, 0));
+  return MRL_OK;
+}
+extern "C" int mrl_download_staged(mrl_context *ctx, void *host, const void *dev, size_t bytes) {
+  if (!ctx || !dev || !host) return mrl_fail(MRL_ERR_INVALID, "mrl_download_staged: bad arguments");
+  int rc = staged_init(ctx);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev_compute, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_compute, 0));
+  CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+  cudaEvent_t &ev = ctx->dl_done[dev];
+  if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(ev, ctx->s_out));
+  return MRL_OK;
+}
+extern "C" int mrl_staged_wait(mrl_context *ctx) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  if (!ctx->s_in) return MRL_OK;
+  CK(cudaStreamSynchronize(ctx->s_in));
+  CK(cudaStreamSynchronize(ctx->s_out));
   return MRL_OK;
 }
 extern "C" int mrl_copy(mrl_context *ctx, void *dst, const void *src, size_t bytes) {
@@ -361,7 +415,9 @@ static cudaError_t zinv_dispatch(mrl_context *ctx, const cx<T> *in, T *out, long
   return e;
 }
 
-template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *out, int batch, int ncp = 0) {
+// stop_axis: strided axes below it are left untransformed (mechanics: the x pass is fused with the
+// Green projection)
+template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *out, int batch, int ncp = 0, int stop_axis = 0) {
   const int dim = ctx->dim, nl = ctx->n[dim - 1];
   const int nc = nl / 2 + 1;
   if (!ncp) ncp = nc;
@@ -374,20 +430,21 @@ template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *o
   cudaError_t e = launch_zfwd_pairs_tma<T>(ctx->lc(), in, out, rows, nl, ncp, (const cx<T> *)tw);
   if (e == cudaErrorNotSupported && ncp == nc) e = launch_zfwd_pairs<T>(ctx->lc(), in, out, rows, nl, (const cx<T> *)tw, make_fft_plan(nl));
   CK(e);
-  for (int a = dim - 2; a >= 0; --a)
+  for (int a = dim - 2; a >= stop_axis; --a)
     if ((rc = strided_axis<T>(ctx, out, out, 1, 0, a, batch, 0, ncp))) return rc;
   return MRL_OK;
 }
 
 // src == nullptr: transform `work` in place (it is destroyed); otherwise src is preserved and
 // `work` receives the partially transformed spectra
-template <class T> static int irfftn_impl2(mrl_context *ctx, const cx<T> *src, cx<T> *work, T *out, int batch, int ncp, double scale) {
+template <class T>
+static int irfftn_impl2(mrl_context *ctx, const cx<T> *src, cx<T> *work, T *out, int batch, int ncp, double scale, int start_axis = 0) {
   const int dim = ctx->dim, nl = ctx->n[dim - 1];
   long long rows = batch;
   for (int d = 0; d < dim - 1; ++d) rows *= ctx->n[d];
   const cx<T> *cur = src ? src : work;
   int rc;
-  for (int a = 0; a <= dim - 2; ++a) {
+  for (int a = start_axis; a <= dim - 2; ++a) {
     if ((rc = strided_axis<T>(ctx, cur, work, 1, 0, a, batch, 1, ncp))) return rc;
     cur = work;
   }
@@ -422,13 +479,19 @@ int mrl_fftb_pitch(const mrl_context *ctx) {
   const int per128 = ctx->precision == MRL_F64 ? 8 : 16;
   return (nc + per128 - 1) / per128 * per128;
 }
-int mrl_fftb_forward(mrl_context *ctx, const void *in, void *out, int batch, int ncp) {
-  return ctx->precision == MRL_F64 ? rfftn_impl<double>(ctx, (const double *)in, (cx<double> *)out, batch, ncp)
-                                   : rfftn_impl<float>(ctx, (const float *)in, (cx<float> *)out, batch, ncp);
+int mrl_fftb_forward(mrl_context *ctx, const void *in, void *out, int batch, int ncp, int first_axis) {
+  return ctx->precision == MRL_F64 ? rfftn_impl<double>(ctx, (const double *)in, (cx<double> *)out, batch, ncp, first_axis)
+                                   : rfftn_impl<float>(ctx, (const float *)in, (cx<float> *)out, batch, ncp, first_axis);
 }
-int mrl_fftb_inverse(mrl_context *ctx, void *work, void *out, int batch, int ncp, double scale) {
-  return ctx->precision == MRL_F64 ? irfftn_impl2<double>(ctx, nullptr, (cx<double> *)work, (double *)out, batch, ncp, scale)
-                                   : irfftn_impl2<float>(ctx, nullptr, (cx<float> *)work, (float *)out, batch, ncp, scale);
+int mrl_fftb_strided(mrl_context *ctx, void *spec, int batch, int ncp, int axis, int inverse) {
+  return ctx->precision == MRL_F64
+             ? strided_axis<double>(ctx, (const cx<double> *)spec, (cx<double> *)spec, 1, 0, axis, batch, inverse, ncp)
+             : strided_axis<float>(ctx, (const cx<float> *)spec, (cx<float> *)spec, 1, 0, axis, batch, inverse, ncp);
+}
+int mrl_fftb_inverse(mrl_context *ctx, void *work, void *out, int batch, int ncp, double scale, int first_axis) {
+  return ctx->precision == MRL_F64
+             ? irfftn_impl2<double>(ctx, nullptr, (cx<double> *)work, (double *)out, batch, ncp, scale, first_axis)
+             : irfftn_impl2<float>(ctx, nullptr, (cx<float> *)work, (float *)out, batch, ncp, scale, first_axis);
 }
 
 extern "C" int mrl_rfftn(mrl_context *ctx, const void *in, void *out, int batch) {

@@ -37,6 +37,10 @@ struct mrl_context {
   size_t scratch_bytes = 0;
   void *reduce_dev = nullptr;
   void *reduce_host = nullptr;
+  // staged transfers (mrl_upload_staged / mrl_download_staged)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_compute = nullptr;
+  std::map<const void *, cudaEvent_t> dl_done;  // device buffer -> completion of its last staged download
 
   mrl::LaunchCtx lc() const { return mrl::LaunchCtx{stream, sm_count}; }
   long long total() const { return (long long)n[0] * n[1] * n[2]; }
@@ -74,8 +78,10 @@ struct mrl_slab_plan {
 // ncp >= n2/2+1 (mrl_fftb_pitch: padded to 128 bytes when every axis runs on the TMA kernels).
 // forward: unnormalised; inverse: `work` is transformed in place (destroyed), result * scale.
 int mrl_fftb_pitch(const mrl_context *ctx);
-int mrl_fftb_forward(mrl_context *ctx, const void *in_real, void *out_cplx, int batch, int ncp);
-int mrl_fftb_inverse(mrl_context *ctx, void *work_cplx, void *out_real, int batch, int ncp, double scale);
+// first_axis > 0: the strided axes below it are skipped (left to a fused pass of the caller).
+int mrl_fftb_forward(mrl_context *ctx, const void *in_real, void *out_cplx, int batch, int ncp, int first_axis = 0);
+int mrl_fftb_strided(mrl_context *ctx, void *spec_cplx, int batch, int ncp, int axis, int inverse);  // one complex pass, in place
+int mrl_fftb_inverse(mrl_context *ctx, void *work_cplx, void *out_real, int batch, int ncp, double scale, int first_axis = 0);
 
 namespace mrl {
 FFTPlanDev make_fft_plan(int n);

@@ -17,7 +17,7 @@ enum { VOP_DOT = 0, VOP_CG_XR = 1, VOP_XPBY = 2, VOP_AXPY = 3, VOP_SUB = 4, VOP_
 enum { FIN_STORE = 0, FIN_ALPHA = 1, FIN_RES = 2 };
 template <class T>
 cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
-                                  long long n, double scale);
+                                  long long n, double scale, const T *r = nullptr, T *xw = nullptr, const double *scal = nullptr);
 template <class T>
 cudaError_t launch_mech_project(const LaunchCtx &lc, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp);
 template <class T>
@@ -44,6 +44,7 @@ struct mrl_mech_plan {
   void *tmp = nullptr, *rhs = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *Ap = nullptr, *Fk = nullptr;  // [9][n] real
   double *scal = nullptr, *partials = nullptr, *host = nullptr;
   int nblk = 0;
+  bool fused_x = true;  // x pass fused with the Green projection (sizes with a TMA configuration)
 };
 
 extern "C" int mrl_mech_plan_destroy(mrl_mech_plan *p) {
@@ -90,19 +91,38 @@ extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, co
 template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, double sign) {
   // out = sign * irfftn( Ghat4 : rfftn(A) ), FFTMechanics.C:104-105
   mrl_context *ctx = p->ctx;
-  int rc = mrl_fftb_forward(ctx, A, p->spec, 9, p->ncp);
-  if (rc) return rc;
+  const T *kx = (const T *)ctx->kaxis_dev[0], *ky = (const T *)ctx->kaxis_dev[1], *kz = (const T *)ctx->kaxis_dev[2];
+  int rc;
+  if (p->fused_x) {
+    // z, y forward; x forward + projection + x inverse in ONE pass over the spectra; y, z inverse
+    if ((rc = mrl_fftb_forward(ctx, A, p->spec, 9, p->ncp, 1))) return rc;
+    const void *tw;
+    if ((rc = ctx->twiddles(ctx->n[0], &tw))) return rc;
+    cudaError_t e = launch_mech_fused_tma<T>(ctx->lc(), (cx<T> *)p->spec, kx, ky, kz, ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp,
+                                             (const cx<T> *)tw);
+    if (e == cudaSuccess) {
+      ctx->launches++;
+      return mrl_fftb_inverse(ctx, p->spec, out, 9, p->ncp, sign / (double)p->n, 1);
+    }
+    if (e != cudaErrorNotSupported) CK(e);
+    p->fused_x = false;  // no pipelined configuration for this size: finish with the separate passes
+    if ((rc = mrl_fftb_strided(ctx, p->spec, 9, p->ncp, 0, 0))) return rc;
+  } else if ((rc = mrl_fftb_forward(ctx, A, p->spec, 9, p->ncp))) {
+    return rc;
+  }
   ctx->launches++;
-  CK(launch_mech_project<T>(ctx->lc(), (cx<T> *)p->spec, (const T *)ctx->kaxis_dev[0], (const T *)ctx->kaxis_dev[1],
-                            (const T *)ctx->kaxis_dev[2], ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp));
+  CK(launch_mech_project<T>(ctx->lc(), (cx<T> *)p->spec, kx, ky, kz, ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp));
   return mrl_fftb_inverse(ctx, p->spec, out, 9, p->ncp, sign / (double)p->n);
 }
 
-template <class T> static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xconst, T *out, double sign) {
+// r_update != nullptr: x is the CG direction, first replaced by r_update + beta x (beta on the device)
+template <class T>
+static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xconst, T *out, double sign, const T *r_update = nullptr) {
   // out = sign * G( K4(F) : x ), FFTMechanics.C:107-112
   mrl_context *ctx = p->ctx;
   ctx->launches++;
-  CK(launch_mech_pointwise<T>(ctx->lc(), xconst ? 2 : 1, F, (const T *)p->K, (const T *)p->mu, x, xconst, (T *)p->tmp, p->n, 1.0));
+  CK(launch_mech_pointwise<T>(ctx->lc(), r_update ? 3 : xconst ? 2 : 1, F, (const T *)p->K, (const T *)p->mu, x, xconst, (T *)p->tmp, p->n,
+                              1.0, r_update, const_cast<T *>(x), p->scal));
   return project_G<T>(p, (const T *)p->tmp, out, sign);
 }
 
@@ -141,14 +161,14 @@ template <class T> static int cg_solve(mrl_mech_plan *p, bool x_zero, int *itera
   if ((rc = vec<T>(p, VOP_DOT, r, r, nullptr, nullptr, 0, FIN_STORE, SC_RZ))) return rc;
   const long long maxit = p->desc.l_max_its;
   for (long long k = 0; k < maxit; ++k) {
-    if ((rc = apply_GK<T>(p, Fk, pp, nullptr, Ap, 1.0))) return rc;
+    // p = r + beta p of the previous iteration rides in the load of the tangent kernel
+    if ((rc = apply_GK<T>(p, Fk, pp, nullptr, Ap, 1.0, k > 0 ? r : nullptr))) return rc;
     if ((rc = vec<T>(p, VOP_DOT, pp, Ap, nullptr, nullptr, 0, FIN_ALPHA))) return rc;  // alpha = rz / p.Ap
     if ((rc = vec<T>(p, VOP_CG_XR, pp, Ap, x, r, 0, FIN_RES))) return rc;              // x, r, |r|^2, beta
     double res2;
     if ((rc = read_scalar(p, SC_RES2, &res2))) return rc;
     *iterations = (int)(k + 1);
     if (std::sqrt(res2) <= p->desc.l_tol * b_norm) return MRL_OK;
-    if ((rc = vec<T>(p, VOP_XPBY, r, nullptr, pp, nullptr, 0))) return rc;  // p = r + beta p
   }
   return MRL_OK;
 }

@@ -341,6 +341,136 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   }
 }
 
+// ======================================================================== mechanics: fused Green projection
+// de Geus projection  A_ij <- (sum_l A_il q_l) q_j / |q|^2  (FFTMechanics.C:48-85,104-105;
+// Ghat4_ijlm = delta_im q_j q_l / |q|^2, zero at q = 0) fused between the forward and the inverse
+// transform along the axis that is transformed last (x).  The contraction couples only the three
+// components of one tensor row i, so a tile is (row i, TK columns): three forward transforms
+// accumulate s = sum_l q_l A_il in registers, then three inverse transforms of q_j s / |q|^2 go
+// back to the same locations.  9 S_c read + 9 S_c written instead of the 36 + 36 of
+// x-forward / projection kernel / x-inverse.
+// Layout [9][n][ncols] (ncols = n1 * ncp), one 3-D tensor map over all nine components; in place.
+// Slot schedule per group: slots 0 and 1 are re-armed with the next tile right after their forward
+// transform; slot 2 serves as exchange buffer of the three inverse transforms and is re-armed
+// after the last one.
+template <class T> struct MechFusedTmaIO {
+  cx<T> *out;
+  int n, ncols, ncb;
+  long long pitch, field;
+  const T *kx, *ky, *kz;
+  int ncp, nzv;
+  T scale;
+};
+
+template <class T, class C, int TK, int NG>
+__global__ void __launch_bounds__(NG *TK *C::TP, 1)
+    k_mech_fused_tma(const MRL_GRID_CONSTANT TensorMap tm, MechFusedTmaIO<T> io, const cx<T> *tw_g) {
+  constexpr int N = C::N, TP = C::TP, E = C::E, GT = TK * TP;
+  constexpr int BOXR = N < 256 ? N : 256, NBOX = N / BOXR;
+  constexpr int TILE = N * TK;
+  MRL_DYN_SMEM(smem_raw);
+  cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));
+  uint64_t *full = reinterpret_cast<uint64_t *>(slots + (size_t)NG * 3 * TILE);  // [NG][3]
+  const int tid = threadIdx.x;
+  const int g = tid / GT, gt = tid - g * GT;
+  const int col = gt % TK, t = gt / TK;
+  TwRegs<T, C, true> twr;
+  twr.init(tw_g, t);
+  const int ntiles = 3 * io.ncb;
+  const int stride = gridDim.x * NG;
+  const int first = blockIdx.x * NG + g;
+  const int nloc = (first < ntiles) ? (ntiles - first + stride - 1) / stride : 0;
+  cx<T> *sl = slots + (size_t)(g * 3) * TILE;
+  uint64_t *bl = &full[g * 3];
+
+  auto issue = [&](int l, int j) {
+    const int tile = first + j * stride;
+    const int i = tile / io.ncb, cb = tile - i * io.ncb;
+    mbar_expect_tx(&bl[l], (uint32_t)(TILE * sizeof(cx<T>)));
+    MRL_UNROLL
+    for (int q = 0; q < NBOX; ++q) tma_load_3d(sl + (size_t)l * TILE + q * BOXR * TK, &tm, &bl[l], cb * TK * 2, q * BOXR, 3 * i + l);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < NG * 3; ++s) mbar_init(&full[s], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (gt == 0 && nloc > 0) {
+    issue(0, 0);
+    issue(1, 0);
+    issue(2, 0);
+  }
+
+  const GroupBarrier bar{1 + g, GT};
+  const SmTile<T, TK> sm0{sl, col}, sm1{sl + TILE, col}, sm2{sl + 2 * (size_t)TILE, col};
+  for (int j = 0; j < nloc; ++j) {
+    const uint32_t par = (uint32_t)(j & 1);
+    const int tile = first + j * stride;
+    const int i = tile / io.ncb;
+    const int c = (tile - i * io.ncb) * TK + col;
+    const bool ok = c < io.ncols && (c % io.ncp) < io.nzv;
+    const bool more = j + 1 < nloc;
+    const T qy = ok ? io.ky[c / io.ncp] : T(0), qz = ok ? io.kz[c % io.ncp] : T(0);
+    cx<T> a[E], s[E];
+    // ---- forward transforms of A_i0, A_i1, A_i2; s accumulates sum_l q_l A_il
+    mbar_wait(&bl[0], par);
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) a[e] = sm0.ld(t + TP * e);
+    bar.sync();
+    fft_or_skip<T, C>(a, t, sm0, twr, bar, [&] {
+      if (gt == 0 && more) issue(0, j + 1);
+    });
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const T qx = io.kx[t + TP * e];
+      s[e] = mk<T>(a[e].x * qx, a[e].y * qx);
+    }
+    mbar_wait(&bl[1], par);
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) a[e] = sm1.ld(t + TP * e);
+    bar.sync();
+    fft_or_skip<T, C>(a, t, sm1, twr, bar, [&] {
+      if (gt == 0 && more) issue(1, j + 1);
+    });
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) {
+      s[e].x += a[e].x * qy;
+      s[e].y += a[e].y * qy;
+    }
+    mbar_wait(&bl[2], par);
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) a[e] = sm2.ld(t + TP * e);
+    bar.sync();
+    fft_or_skip<T, C>(a, t, sm2, twr, bar, NoHook());
+    MRL_UNROLL
+    for (int e = 0; e < E; ++e) {
+      const T qx = io.kx[t + TP * e];
+      const T Q = qx * qx + qy * qy + qz * qz;
+      const T inv = Q == T(0) ? T(0) : fast_rcp(Q);
+      s[e].x = (s[e].x + a[e].x * qz) * inv;
+      s[e].y = (s[e].y + a[e].y * qz) * inv;
+    }
+    // ---- inverse transforms of q_j s (conj . FFT . conj), exchange through slot 2
+    MRL_UNROLL
+    for (int jj = 0; jj < 3; ++jj) {
+      MRL_UNROLL
+      for (int e = 0; e < E; ++e) {
+        const T q = jj == 0 ? io.kx[t + TP * e] : jj == 1 ? qy : qz;
+        a[e] = mk<T>(s[e].x * q, -s[e].y * q);
+      }
+      fft_or_skip<T, C>(a, t, sm2, twr, bar, [&] {
+        if (jj == 2 && gt == 0 && more) issue(2, j + 1);
+      });
+      if (ok) {
+        cx<T> *dst = io.out + (long long)(3 * i + jj) * io.field + c;
+        MRL_UNROLL
+        for (int e = 0; e < E; ++e) dst[(long long)(t + TP * e) * io.pitch] = mk<T>(a[e].x * io.scale, -a[e].y * io.scale);
+      }
+    }
+  }
+}
+
 // ======================================================================== P1: z r2c of (c + i F(c))
 // A tile is PPB consecutive real rows (one contiguous bulk copy).  Each group owns NS input
 // slots and one padded complex exchange buffer per pencil.  The Hermitian split

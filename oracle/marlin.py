@@ -421,6 +421,90 @@ class AdamsBashforthMoulton(SplitOperatorSolver):
             p.sub_time -= dt
 
 
+class AdamsBashforthMoultonCoupled(SplitOperatorSolver):
+    """src/tensor_solver/AdamsBashforthMoultonCoupled.C:51-273: Adams-Bashforth-Moulton with a dense
+    (per wavevector) linear operator, solved with a batched `linalg_solve`.  As coded there:
+    * the dense operator is assembled as stack(stack(cols,-1) per row, -1), i.e. the matrix that
+      reaches linalg_solve is the TRANSPOSE of the user's L_ij table (:151-164);
+    * a missing diagonal entry dereferences a null pointer in the reference; here it is zero;
+    * the sub-time is advanced inside substep() (:177) in addition to TensorSolver::computeBuffer;
+    * a corrector step of order 0 still solves A u = u_n (:213-217), unlike AdamsBashforthMoulton."""
+
+    def __init__(self, problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                 nonlinear_reciprocal, substeps=1, predictor_order=2, corrector_order=2,
+                 corrector_steps=0, linear_offdiag_rows=(), linear_offdiag_cols=(),
+                 linear_offdiag=(), assume_symmetric=False, forward=()):
+        self.P = predictor_order - 1
+        self.C = corrector_order - 1
+        self.csteps = corrector_steps
+        self.offdiag = list(zip(linear_offdiag_rows, linear_offdiag_cols, linear_offdiag))
+        self.assume_symmetric = assume_symmetric
+        super().__init__(problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                         nonlinear_reciprocal, substeps, max(self.P, self.C), forward)
+
+    def _solve(self, rhs_list):
+        b, n = self.p.buf, len(self.vars)
+        base = b[self.vars[0]["L"]]
+        zero = torch.zeros_like(base)
+        tab = [[zero] * n for _ in range(n)]
+        given = set()
+        for i, v in enumerate(self.vars):
+            if v["L"] is not None:
+                tab[i][i] = b[v["L"]]
+        for i, j, name in self.offdiag:
+            tab[i][j] = b[name]
+            given.add((i, j))
+        if self.assume_symmetric:
+            for i, j, name in self.offdiag:
+                if i != j and tab[j][i] is zero:
+                    tab[j][i] = b[name]
+        rows = [torch.stack([tab[i][j] for j in range(n)], -1) for i in range(n)]
+        Lm = torch.stack(rows, -1)
+        A = torch.eye(n, dtype=base.dtype) - self.p.sub_dt * Lm
+        rhs = torch.stack(rhs_list, -1)
+        sol = torch.linalg.solve(A.to(rhs.dtype), rhs)
+        return torch.unbind(sol, -1)
+
+    def substep(self):
+        p, b = self.p, self.p.buf
+        self.root.compute()
+        self.forward_buffers()
+        dt = p.sub_dt
+        dt_changed = p.dt != p.dt_old
+        rhs = []
+        for v in self.vars:
+            n_old = len(v["Nold"])
+            order = min(0 if (self.substep_index < self.P and dt_changed) else n_old, self.P)
+            r = b[v["ubar"]] + (dt * AB_BETA[order][0]) * b[v["N"]]
+            for i in range(order):
+                r = r + (dt * AB_BETA[order][i + 1]) * v["Nold"][i]
+            rhs.append(r)
+        for v, ubar in zip(self.vars, self._solve(rhs)):
+            b[v["u"]] = self.d.ifft(ubar)
+        p.sub_time += dt
+        if self.csteps:
+            ubar_n = [b[v["ubar"]] for v in self.vars]
+            N_n = [b[v["N"]] for v in self.vars] if self.C > 0 else None
+            for _ in range(self.csteps):
+                self.root.compute()
+                self.forward_buffers()
+                rhs = []
+                for k, v in enumerate(self.vars):
+                    n_old = len(v["Nold"])
+                    order = min(1 if (self.substep_index < self.C and dt_changed) else n_old + 1,
+                                self.C)
+                    if order == 0:
+                        rhs.append(ubar_n[k])
+                        continue
+                    r = ubar_n[k] + (dt * AM_ALPHA[order][0]) * b[v["N"]]
+                    r = r + (dt * AM_ALPHA[order][1]) * N_n[k]
+                    for i in range(order - 1):
+                        r = r + (dt * AM_ALPHA[order][i + 2]) * v["Nold"][i]
+                    rhs.append(r)
+                for v, ubar in zip(self.vars, self._solve(rhs)):
+                    b[v["u"]] = self.d.ifft(ubar)
+
+
 class ForwardEulerSolver(TensorSolver):
     """src/tensor_solver/ForwardEulerSolver.C:29-38 (variables may be empty: mechanics)."""
 

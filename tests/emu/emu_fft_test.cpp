@@ -451,7 +451,68 @@ template <class C, int TK, int NG, int NS> static void test_strided_peer(const c
   report(name, err, 1e-12 * nx);
 }
 
+// mechanics: x-forward + Green projection + x-inverse in one pass vs dft() composition
+template <class C, int TK, int NG> static void test_mech_fused(const char *name, int ny, int nzv, int ncp, int grid) {
+  constexpr int n = C::N;
+  std::mt19937_64 rng(23);
+  std::uniform_real_distribution<double> U(-1, 1);
+  const int ncols = ny * ncp;
+  const size_t field = (size_t)n * ncols;
+  std::vector<cx<double>> A(9 * field), A0;
+  for (auto &v : A) v = mk<double>(U(rng), U(rng));
+  A0 = A;
+  std::vector<double> kx(n), ky(ny), kz(ncp);
+  for (auto &v : kx) v = U(rng);
+  for (auto &v : ky) v = U(rng);
+  for (auto &v : kz) v = U(rng);
+  kx[0] = ky[0] = kz[0] = 0.0;  // q = 0 -> projection 0
+  auto tw = make_tw(n);
+  MechFusedTmaIO<double> io;
+  io.out = A.data(); io.n = n; io.ncols = ncols; io.ncb = (ncols + TK - 1) / TK; io.pitch = ncols; io.field = (long long)field;
+  io.kx = kx.data(); io.ky = ky.data(); io.kz = kz.data(); io.ncp = ncp; io.nzv = nzv; io.scale = 1.0;
+  const long long rowb = (long long)ncols * 16;
+  TensorMap tm = emu_map(A.data(), 8, 2LL * ncols, n, 9, rowb, rowb * n, 2 * TK, n < 256 ? n : 256);
+  const cx<double> *twp = tw.data();
+  size_t smem = (size_t)(NG * 3 * n * TK) * 16 + NG * 3 * 8 + 128;
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_mech_fused_tma<double, C, TK, NG>(tm, io, twp); }, 64 * 1024);
+  double err = 0, pad = 0;
+  for (int c = 0; c < ncols; ++c) {
+    const bool valid = (c % ncp) < nzv;
+    for (int i = 0; i < 3; ++i) {
+      std::vector<lc> y[3];
+      for (int l = 0; l < 3; ++l) {
+        std::vector<lc> x(n);
+        for (int j = 0; j < n; ++j) x[j] = lc(A0[(3 * i + l) * field + (size_t)j * ncols + c].x, A0[(3 * i + l) * field + (size_t)j * ncols + c].y);
+        y[l] = dft(x, -1);
+      }
+      for (int jj = 0; jj < 3; ++jj) {
+        std::vector<lc> u(n);
+        for (int j = 0; j < n; ++j) {
+          long double q[3] = {kx[j], ky[c / ncp], kz[c % ncp]};
+          long double Q = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+          lc sacc = y[0][j] * q[0] + y[1][j] * q[1] + y[2][j] * q[2];
+          u[j] = Q == 0 ? lc(0, 0) : sacc * (q[jj] / Q);
+        }
+        auto r = dft(u, +1);
+        for (int j = 0; j < n; ++j) {
+          auto v = A[(3 * i + jj) * field + (size_t)j * ncols + c];
+          auto v0 = A0[(3 * i + jj) * field + (size_t)j * ncols + c];
+          if (valid) err = std::max(err, (double)std::abs(lc(v.x, v.y) - r[j]));
+          else pad = std::max(pad, std::abs(v.x - v0.x) + std::abs(v.y - v0.y));  // padding columns untouched
+        }
+      }
+    }
+  }
+  report(name, err, 1e-11 * n);
+  char nm[160];
+  snprintf(nm, sizeof nm, "%s (padding untouched)", name);
+  report(nm, pad, 1e-300);
+}
+
 static void tma_tests() {
+  test_mech_fused<FFTCfg<64, 8, 8, 8>, 8, 2>("mech fused tma 64 TK8 NG2 ny3 nzv5 ncp8 g2", 3, 5, 8, 2);
+  test_mech_fused<FFTCfg<64, 8, 8, 8>, 4, 1>("mech fused tma 64 TK4 NG1 ny2 nzv3 ncp3 g1", 2, 3, 3, 1);
+  test_mech_fused<FFTCfg<512, 64, 8, 8, 8>, 4, 1>("mech fused tma 512 TK4 NG1 (2 boxes) g3", 1, 3, 4, 3);
   test_strided("strided tma 64 TK8 NG2 NS3", 64, 19, 3, 0, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>(io, tw, 2); });
   test_strided("strided tma 64 TK8 NG2 NS3 inv g5", 64, 19, 3, 1, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>(io, tw, 5); });
   test_strided("strided tma 64 TK4 NG4 NS6", 64, 9, 2, 0, [](auto io, auto tw) { run_strided_tma<FFTCfg<64, 8, 8, 8>, 4, 4, 6>(io, tw, 1); });

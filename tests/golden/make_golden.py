@@ -8,7 +8,7 @@ stored - no reference source code.
 
 Sources (relative to the reference root):
   test/tests/cahnhilliard/gold/cahnhilliard_out.e   Exodus/NetCDF-3; nodal `c`, elemental `mu`
-  test/tests/solvers/gold/diagonal_*.csv            postprocessor CSVs
+  test/tests/solvers/gold/{diagonal,coupled,nl_coupled}_*.csv   postprocessor CSVs
   test/tests/solvers/gold/etdrk4_diffusion_rmse.csv
   test/tests/mechanics/gold/mech3d.h5               HDF5, one deflate chunk per dataset
   test/tests/gradient/gold/*.csv, test/tests/tensor_compute/gold/backandforth_out.csv
@@ -64,7 +64,7 @@ def solver_csvs():
     out = {}
     gd = f"{REF}/test/tests/solvers/gold"
     for fn in sorted(os.listdir(gd)):
-        if fn.startswith("diagonal_") or fn.startswith("etdrk4"):
+        if fn.startswith(("diagonal_", "etdrk4", "coupled_", "nl_coupled_")):
             h, a = read_csv(f"{gd}/{fn}")
             out[fn[:-4]] = a
             out[fn[:-4] + "__header"] = np.array(h)

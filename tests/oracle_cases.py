@@ -56,6 +56,33 @@ def diagonal_problem(ss, cs, order, n=150):
     return p
 
 
+def coupled_problem(ss, cs, order, n=150, nonlinear=False):
+    """test/tests/solvers/coupled.i (AdamsBashforthMoultonCoupled, off-diagonal linear operator) and
+    nl_coupled.i (the same coupling moved into the nonlinear term of AdamsBashforthMoulton)."""
+    d = om.Domain(2, [n, n], (0, 0, 0), (2 * math.pi, 2 * math.pi, 1.0))
+    p = om.Problem(d)
+    p.ics = [om.ParsedCompute(p, "u", "sin(x)*sin(y)", extra_symbols=True, expand="REAL"),
+             om.ParsedCompute(p, "v", "cos(x)*cos(y)", extra_symbols=True, expand="REAL"),
+             om.ConstantTensor(p, "zero", 0.0, reciprocal=True),
+             om.ReciprocalLaplacianFactor(p, "D1", 1e-2),
+             om.ReciprocalLaplacianFactor(p, "D2", 1e-3)]
+    ops = [om.ForwardFFT(p, "u_bar", "u"), om.ForwardFFT(p, "v_bar", "v")]
+    if nonlinear:
+        ops += [om.ParsedCompute(p, "Du", "D2*v_bar", inputs=["D2", "v_bar"]),
+                om.ParsedCompute(p, "Dv", "D2*u_bar", inputs=["D2", "u_bar"])]
+        root = om.Group(p, ops)
+        p.solver = om.AdamsBashforthMoulton(p, root, ["u", "v"], ["u_bar", "v_bar"], ["D1", "D1"],
+                                            ["Du", "Dv"], substeps=ss, predictor_order=order,
+                                            corrector_order=order, corrector_steps=cs)
+    else:
+        root = om.Group(p, ops)
+        p.solver = om.AdamsBashforthMoultonCoupled(
+            p, root, ["u", "v"], ["u_bar", "v_bar"], ["D1", "D1"], ["zero", "zero"], substeps=ss,
+            predictor_order=order, corrector_order=order, corrector_steps=cs,
+            linear_offdiag_rows=[1, 0], linear_offdiag_cols=[0, 1], linear_offdiag=["D2", "D2"])
+    return p
+
+
 def diagonal_row(p):
     """Column order of the gold CSV: time,U,V,u_max,u_min,v_max,v_min."""
     return [p.time, om.pp_integral(p, "u"), om.pp_integral(p, "v"), om.pp_extreme(p, "u", "MAX"),

@@ -96,7 +96,7 @@ def test_mech3d_matches_gold_and_oracle_iterations(ctx):
     plan.close()
 
 
-@pytest.mark.parametrize("n", [128])
+@pytest.mark.parametrize("n", [128, 256])
 def test_mech_large_properties(ctx, n):
     """Sizes on the TMA kernels (padded spectra): the Green operator is a projection on
     band-limited fields (G(G(A)) = G(A); the un-zeroed Nyquist planes of the reference's k-grid
