@@ -112,6 +112,27 @@ protected:
   std::string _fusion_note;
 };
 
+// src/tensor_solver/AdamsBashforthMoultonCoupled.C: Adams-Bashforth-Moulton with a dense linear
+// operator (off-diagonal reciprocal-space couplings), one N x N solve per wavevector.
+class AdamsBashforthMoultonCoupled : public SplitOperatorBase {
+public:
+  static InputParameters validParams();
+  explicit AdamsBashforthMoultonCoupled(const InputParameters &parameters);
+  static constexpr std::size_t max_order = 5;
+
+protected:
+  void substep() override;
+  void solveAndInvert(const std::vector<marlin::Tensor> &rhs);
+
+  std::size_t _predictor_order;
+  std::size_t _corrector_order;
+  std::size_t _corrector_steps;
+  const bool _assume_symmetric;
+  std::vector<std::pair<unsigned int, unsigned int>> _L_offdiag_indices;
+  std::vector<TensorInputBufferName> _L_offdiag_names;
+  std::vector<const marlin::Tensor *> _L_offdiag_buffer;
+};
+
 class ETDRK4Solver : public SplitOperatorBase {
 public:
   static InputParameters validParams();

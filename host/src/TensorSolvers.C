@@ -491,6 +491,135 @@ void AdamsBashforthMoulton::substep() {
   }
 }
 
+// ========================================================================= AdamsBashforthMoultonCoupled
+registerMooseObject("MarlinApp", AdamsBashforthMoultonCoupled);
+
+InputParameters AdamsBashforthMoultonCoupled::validParams() {
+  InputParameters params = SplitOperatorBase::validParams();
+  params.addClassDescription("Coupled Adams-Bashforth-Moulton solver with dense linear operator and batched solve in reciprocal space.");
+  params.addParam<unsigned int>("substeps", 1, "semi-implicit substeps per time step.");
+  params.addRangeCheckedParam<std::size_t>("predictor_order", 2, "predictor_order > 0 & predictor_order <= 5", "Order of the Adams-Bashforth predictor.");
+  params.addRangeCheckedParam<std::size_t>("corrector_order", 2, "corrector_order > 0 & corrector_order <= 5", "Order of the Adams-Moulton corrector.");
+  params.addParam<std::size_t>("corrector_steps", 0, "Number of Adams-Moulton corrector steps (0 disables the corrector).");
+  params.addParam<std::vector<unsigned int>>("linear_offdiag_rows", {}, "Row indices for L_ij.");
+  params.addParam<std::vector<unsigned int>>("linear_offdiag_cols", {}, "Column indices for L_ij.");
+  params.addParam<std::vector<TensorInputBufferName>>("linear_offdiag", {}, "Off-diagonal linear operator buffers.");
+  params.addParam<bool>("assume_symmetric", false, "Mirror off-diagonal entries (i,j) into (j,i) if not explicitly provided.");
+  return params;
+}
+
+AdamsBashforthMoultonCoupled::AdamsBashforthMoultonCoupled(const InputParameters &parameters)
+  : SplitOperatorBase(parameters),
+    _predictor_order(getParam<std::size_t>("predictor_order") - 1),
+    _corrector_order(getParam<std::size_t>("corrector_order") - 1),
+    _corrector_steps(getParam<std::size_t>("corrector_steps")),
+    _assume_symmetric(getParam<bool>("assume_symmetric")),
+    _L_offdiag_indices(getParam<unsigned int, unsigned int>("linear_offdiag_rows", "linear_offdiag_cols")),
+    _L_offdiag_names(getParam<std::vector<TensorInputBufferName>>("linear_offdiag")) {
+  getVariables(std::max(_predictor_order, _corrector_order));
+  if (_L_offdiag_indices.size() != _L_offdiag_names.size())
+    paramError("linear_offdiag", "'linear_offdiag_rows', 'linear_offdiag_cols', and 'linear_offdiag' must all have the same length.");
+  const auto N = _variables.size();
+  for (const auto &[i, j] : _L_offdiag_indices) {
+    if (i >= N) paramError("linear_offdiag_rows", "Off-diagonal indices out of range.");
+    if (j >= N) paramError("linear_offdiag_cols", "Off-diagonal indices out of range.");
+  }
+  if (N > 6) paramError("buffer", "The CUDA per-wavevector solve supports at most 6 coupled variables.");
+  for (const auto &name : _L_offdiag_names) _L_offdiag_buffer.push_back(&getInputBufferByName(name));
+}
+
+// :131-171 (and :225-257 for the corrector): assemble L, solve (I - dt L) ubar = rhs per
+// wavevector, inverse transform.  As coded in the reference:
+//  * L is assembled as stack(stack(cols) per row, -1), so the matrix that reaches linalg_solve
+//    is the TRANSPOSE of the L_ij table: equation a, unknown b  <-  table entry (b, a);
+//  * the right-hand side is cast to the dtype of the first variable's linear operator (real):
+//    only its real part is used (gold coupled_*.csv pin this).
+void AdamsBashforthMoultonCoupled::solveAndInvert(const std::vector<Tensor> &rhs) {
+  const auto N = _variables.size();
+  if (!_variables[0]._linear_reciprocal) paramError("linear_reciprocal", "The first variable needs a linear operator buffer (the reference dereferences it).");
+  std::vector<const Tensor *> table(N * N, nullptr);
+  for (std::size_t i = 0; i < N; ++i) table[i * N + i] = _variables[i]._linear_reciprocal;
+  for (std::size_t k = 0; k < _L_offdiag_buffer.size(); ++k) {
+    const auto &[i, j] = _L_offdiag_indices[k];
+    table[i * N + j] = _L_offdiag_buffer[k];
+  }
+  if (_assume_symmetric)
+    for (std::size_t k = 0; k < _L_offdiag_buffer.size(); ++k) {
+      const auto &[i, j] = _L_offdiag_indices[k];
+      if (i != j && !table[j * N + i]) table[j * N + i] = _L_offdiag_buffer[k];
+    }
+  std::vector<const void *> L(N * N, nullptr), b(N);
+  std::vector<void *> out(N);
+  std::vector<Tensor> ubar(N);
+  for (std::size_t a = 0; a < N; ++a)
+    for (std::size_t c = 0; c < N; ++c)
+      if (const Tensor *t = table[c * N + a]) {
+        if (!t->defined()) mooseError("AdamsBashforthMoultonCoupled: a linear operator buffer is not defined");
+        if (t->is_complex()) mooseError("AdamsBashforthMoultonCoupled: linear operator buffers are expected to be real");
+        L[a * N + c] = t->data_ptr();
+      }
+  for (std::size_t i = 0; i < N; ++i) {
+    ubar[i] = _domain.empty(Space::RECIPROCAL, true, 1);
+    b[i] = rhs[i].data_ptr();
+    out[i] = ubar[i].data_ptr();
+  }
+  const bool drop_imag = !_variables[0]._linear_reciprocal->is_complex();
+  checkC(mrl_coupled_solve(_domain.context(), (int)N, L.data(), b.data(), out.data(), _sub_dt, drop_imag ? 1 : 0), "mrl_coupled_solve");
+  for (std::size_t i = 0; i < N; ++i) _variables[i]._buffer = _domain.ifft(ubar[i]);
+}
+
+void AdamsBashforthMoultonCoupled::substep() {
+  _compute->computeBuffer();
+  forwardBuffers();
+  const bool dt_changed = (_dt != _dt_old);
+  const auto N = _variables.size();
+  if (N == 0) return;
+  // right-hand side cbar + dt * sum_i coef_i N_i: the AB update without a linear operator
+  auto combine = [&](const Tensor &base, const Tensor &Nl, const double *coef, const std::vector<const void *> &old) {
+    Tensor r = _domain.empty(Space::RECIPROCAL, true, 1);
+    checkC(mrl_ab_update(_domain.context(), r.data_ptr(), base.data_ptr(), Nl.data_ptr(), nullptr, _sub_dt, coef, (int)old.size(),
+                         old.empty() ? nullptr : old.data()),
+           "mrl_ab_update");
+    return r;
+  };
+  std::vector<Tensor> rhs(N);
+  for (std::size_t i = 0; i < N; ++i) {
+    auto &v = _variables[i];
+    const auto n_old = v._old_nonlinear_reciprocal.size();
+    const auto order = std::min(_substep < _predictor_order && dt_changed ? std::size_t(0) : n_old, _predictor_order);
+    std::vector<const void *> old;
+    for (std::size_t j = 0; j < order; ++j) old.push_back(v._old_nonlinear_reciprocal[j].data_ptr());
+    rhs[i] = combine(v._reciprocal_buffer, v._nonlinear_reciprocal, AB_BETA[order], old);
+  }
+  solveAndInvert(rhs);
+  // :177 advances the sub-time here, in addition to TensorSolver::computeBuffer (as coded)
+  _sub_time += _sub_dt;
+
+  if (_corrector_steps) {
+    std::vector<Tensor> ubar_n(N), N_n(N);
+    for (std::size_t i = 0; i < N; ++i) ubar_n[i] = _variables[i]._reciprocal_buffer;
+    if (_corrector_order > 0)
+      for (std::size_t i = 0; i < N; ++i) N_n[i] = _variables[i]._nonlinear_reciprocal;
+    for (std::size_t jc = 0; jc < _corrector_steps; ++jc) {
+      _compute->computeBuffer();
+      forwardBuffers();
+      for (std::size_t i = 0; i < N; ++i) {
+        auto &v = _variables[i];
+        const auto n_old = v._old_nonlinear_reciprocal.size();
+        const auto order = std::min(_substep < _corrector_order && dt_changed ? std::size_t(1) : n_old + 1, _corrector_order);
+        if (order == 0) {  // :213-217: the solve still runs on the old spectrum
+          rhs[i] = ubar_n[i];
+          continue;
+        }
+        std::vector<const void *> old = {N_n[i].data_ptr()};
+        for (std::size_t j = 0; j + 1 < order; ++j) old.push_back(v._old_nonlinear_reciprocal[j].data_ptr());
+        rhs[i] = combine(ubar_n[i], v._nonlinear_reciprocal, AM_ALPHA[order], old);
+      }
+      solveAndInvert(rhs);
+    }
+  }
+}
+
 // ========================================================================================== ETDRK4Solver
 registerMooseObject("MarlinApp", ETDRK4Solver);
 

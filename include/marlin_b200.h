@@ -107,6 +107,16 @@ int mrl_mul_real_complex(mrl_context *ctx, const void *a_real_dev, const void *b
 int mrl_ab_update(mrl_context *ctx, void *ubar_dev, const void *cbar_dev, const void *N_dev, const void *L_real_dev,
                   double dt, const double *beta, int nold, const void *const *Nold_dev);
 
+/* Coupled semi-implicit update: solves, for every wavevector, (I - dt*L) ubar = rhs with a dense
+ * real nvar x nvar operator (LU with partial pivoting) - the batched at::linalg_solve of
+ * AdamsBashforthMoultonCoupled::substep, src/tensor_solver/AdamsBashforthMoultonCoupled.C:131-171.
+ * L_real_dev[r*nvar + c] is the reciprocal-space buffer that multiplies unknown c in equation r
+ * (NULL = zero).  drop_imag != 0 reproduces the reference's cast of the right-hand side to the real
+ * dtype of the first linear operator (:141,167): only Re(rhs) enters the solve.  out may alias rhs.
+ * nvar <= 6.                                                                                */
+int mrl_coupled_solve(mrl_context *ctx, int nvar, const void *const *L_real_dev, const void *const *rhs_cplx_dev,
+                      void *const *out_cplx_dev, double dt, int drop_imag);
+
 /* ---- reductions behind the postprocessors (src/postprocessors/Tensor*Postprocessor.C) --
  * Synchronous: returns the value on the host.                                             */
 enum mrl_reduce_op { MRL_SUM = 0, MRL_MIN = 1, MRL_MAX = 2, MRL_SUMSQ = 3 };

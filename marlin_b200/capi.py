@@ -187,6 +187,17 @@ class Context:
         _ck(lib().mrl_ab_update(self.h, _p(out), _p(cbar), _p(N), _p(L), C.c_double(dt), b, nold, arr))
         return out
 
+    def coupled_solve(self, L, rhs, dt, drop_imag=False):
+        """(I - dt*L) ubar = rhs per wavevector; L: nvar x nvar nested list of real reciprocal-space
+        tensors (None = 0), rhs: list of complex tensors.  Returns the list of solutions."""
+        n = len(rhs)
+        out = [torch.empty_like(r) for r in rhs]
+        Lp = (C.c_void_p * (n * n))(*[(L[r][c].data_ptr() if L[r][c] is not None else None) for r in range(n) for c in range(n)])
+        bp = (C.c_void_p * n)(*[t.data_ptr() for t in rhs])
+        op = (C.c_void_p * n)(*[t.data_ptr() for t in out])
+        _ck(lib().mrl_coupled_solve(self.h, n, Lp, bp, op, C.c_double(dt), int(bool(drop_imag))))
+        return out
+
     def reduce(self, op, t):
         assert t.is_contiguous() and t.dtype == self.rdtype
         v = C.c_double()

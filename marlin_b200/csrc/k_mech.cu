@@ -39,58 +39,107 @@ template <class T> __device__ __forceinline__ void second_pk(const M3<T> &F, T K
     for (int j = 0; j < 3; ++j) S.a[i][j] = T(2) * mu * E[i][j] + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
 }
 
+// mode 0: R = P = F S.   mode 1-3: R = K4 : X.
+template <class T> __device__ __forceinline__ void mech_point(int mode, const M3<T> &Fm, T K, T mu, const M3<T> &X, M3<T> &R) {
+  M3<T> S;
+  second_pk(Fm, K, mu, S);
+  if (mode == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R.a[i][j] = Fm.a[i][0] * S.a[0][j] + Fm.a[i][1] * S.a[1][j] + Fm.a[i][2] * S.a[2][j];
+  } else {
+    T W[3][3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int l = 0; l < 3; ++l) W[p][l] = Fm.a[0][p] * X.a[0][l] + Fm.a[1][p] * X.a[1][l] + Fm.a[2][p] * X.a[2][l];
+    const T tr = W[0][0] + W[1][1] + W[2][2];
+    T Tm[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Tm[i][j] = mu * (W[i][j] + W[j][i]) + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        R.a[i][j] = X.a[i][0] * S.a[0][j] + X.a[i][1] * S.a[1][j] + X.a[i][2] * S.a[2][j] + Fm.a[i][0] * Tm[0][j] + Fm.a[i][1] * Tm[1][j] +
+                    Fm.a[i][2] * Tm[2][j];
+  }
+}
+
+template <class T, int W> struct VecW {};
+template <> struct VecW<double, 2> { typedef double2 type; };
+template <> struct VecW<float, 2> { typedef float2 type; };
+template <> struct VecW<double, 1> { typedef double type; };
+template <> struct VecW<float, 1> { typedef float type; };
+template <class T, int W> struct Lanes {
+  T v[W];
+};
+template <class T, int W> __device__ __forceinline__ Lanes<T, W> ldw(const T *p) {
+  typedef typename VecW<T, W>::type V;
+  union { V vec; Lanes<T, W> l; } u;
+  u.vec = *reinterpret_cast<const V *>(p);
+  return u.l;
+}
+template <class T, int W> __device__ __forceinline__ void stw(T *p, const Lanes<T, W> &l) {
+  typedef typename VecW<T, W>::type V;
+  union { V vec; Lanes<T, W> l; } u;
+  u.l = l;
+  *reinterpret_cast<V *>(p) = u.vec;
+}
+
 // mode 0: out = P = F S.   mode 1: out = K4 : x (x from memory).   mode 2: same with a spatially
 // constant x (9 values in xc) - the applied macroscopic strain.   mode 3: the CG direction update
 // fused in: x <- r + beta x (beta = scal[SC_BETA], x written back through xw), then out = K4 : x.
-template <class T>
-__global__ void __launch_bounds__(256) k_mech_pointwise(int mode, const T *F, const T *Kf, const T *muf, const T *x, M3<T> xc, T *out,
-                                                        long long n, T scale, const T *r, T *xw, const double *scal) {
-  const double beta = mode == 3 ? scal[4 /* SC_BETA */] : 0.0;
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
-    M3<T> Fm, S;
+// W consecutive voxels per thread (W = 2: 128-bit accesses in fp64); n must be a multiple of W.
+template <class T, int MODE, int W>
+__global__ void __launch_bounds__(256) k_mech_pointwise(const T *F, const T *Kf, const T *muf, const T *x, M3<T> xc, T *out, long long n,
+                                                        T scale, const T *r, T *xw, const double *scal) {
+  const double beta = MODE == 3 ? scal[4 /* SC_BETA */] : 0.0;
+  const long long nw = n / W;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nw; q += (long long)gridDim.x * blockDim.x) {
+    const long long v = q * W;
+    Lanes<T, W> f[9], xv[9], rv[9];
 #pragma unroll
-    for (int c = 0; c < 9; ++c) Fm.a[c / 3][c % 3] = F[c * n + v];
-    const T K = Kf[v], mu = muf[v];
-    second_pk(Fm, K, mu, S);
-    M3<T> R;
-    if (mode == 0) {
+    for (int c = 0; c < 9; ++c) f[c] = ldw<T, W>(F + c * n + v);
+    if (MODE == 1 || MODE == 3) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
+      for (int c = 0; c < 9; ++c) xv[c] = ldw<T, W>(x + c * n + v);
+    }
+    if (MODE == 3) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) R.a[i][j] = Fm.a[i][0] * S.a[0][j] + Fm.a[i][1] * S.a[1][j] + Fm.a[i][2] * S.a[2][j];
-    } else {
-      M3<T> X = xc;
-      if (mode == 1) {
+      for (int c = 0; c < 9; ++c) rv[c] = ldw<T, W>(r + c * n + v);
+    }
+    const Lanes<T, W> Kv = ldw<T, W>(Kf + v), muv = ldw<T, W>(muf + v);
+    Lanes<T, W> o[9];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = x[c * n + v];
-      } else if (mode == 3) {
+    for (int w = 0; w < W; ++w) {
+      M3<T> Fm, X = xc, R;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) Fm.a[c / 3][c % 3] = f[c].v[w];
+      if (MODE == 1) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = xv[c].v[w];
+      } else if (MODE == 3) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
-          const T pn = (T)((double)r[c * n + v] + beta * (double)x[c * n + v]);  // same arithmetic as VOP_XPBY
-          xw[c * n + v] = pn;
+          const T pn = (T)((double)rv[c].v[w] + beta * (double)xv[c].v[w]);  // same arithmetic as VOP_XPBY
+          xv[c].v[w] = pn;
           X.a[c / 3][c % 3] = pn;
         }
       }
-      T W[3][3];
+      mech_point<T>(MODE, Fm, Kv.v[w], muv.v[w], X, R);
 #pragma unroll
-      for (int p = 0; p < 3; ++p)
+      for (int c = 0; c < 9; ++c) o[c].v[w] = R.a[c / 3][c % 3] * scale;
+    }
+    if (MODE == 3) {
 #pragma unroll
-        for (int l = 0; l < 3; ++l) W[p][l] = Fm.a[0][p] * X.a[0][l] + Fm.a[1][p] * X.a[1][l] + Fm.a[2][p] * X.a[2][l];
-      const T tr = W[0][0] + W[1][1] + W[2][2];
-      T Tm[3][3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Tm[i][j] = mu * (W[i][j] + W[j][i]) + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          R.a[i][j] = X.a[i][0] * S.a[0][j] + X.a[i][1] * S.a[1][j] + X.a[i][2] * S.a[2][j] + Fm.a[i][0] * Tm[0][j] + Fm.a[i][1] * Tm[1][j] +
-                      Fm.a[i][2] * Tm[2][j];
+      for (int c = 0; c < 9; ++c) stw<T, W>(xw + c * n + v, xv[c]);
     }
 #pragma unroll
-    for (int c = 0; c < 9; ++c) out[c * n + v] = R.a[c / 3][c % 3] * scale;
+    for (int c = 0; c < 9; ++c) stw<T, W>(out + c * n + v, o[c]);
   }
 }
 
@@ -245,12 +294,27 @@ static inline int ew_grid(long long total, const LaunchCtx &lc) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+template <class T, int W>
+static void mech_pointwise_go(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const M3<T> &X, T *out,
+                              long long n, T scale, const T *r, T *xw, const double *scal) {
+  const int grid = ew_grid(n / W, lc);
+  switch (mode) {
+    case 0: k_mech_pointwise<T, 0, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+    case 1: k_mech_pointwise<T, 1, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+    case 2: k_mech_pointwise<T, 2, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+    default: k_mech_pointwise<T, 3, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+  }
+}
 template <class T>
 cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
                                   long long n, double scale, const T *r, T *xw, const double *scal) {
   M3<T> X;
   for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = xc ? (T)xc[c] : T(0);
-  k_mech_pointwise<T><<<ew_grid(n, lc), 256, 0, lc.stream>>>(mode, F, K, mu, x, X, out, n, (T)scale, r, xw, scal);
+  bool wide = (n % 2) == 0;
+  for (const void *q : {(const void *)F, (const void *)K, (const void *)mu, (const void *)x, (const void *)out, (const void *)r, (const void *)xw})
+    wide = wide && (((unsigned long long)q & (2 * sizeof(T) - 1)) == 0);
+  if (wide) mech_pointwise_go<T, 2>(lc, mode, F, K, mu, x, X, out, n, (T)scale, r, xw, scal);
+  else mech_pointwise_go<T, 1>(lc, mode, F, K, mu, x, X, out, n, (T)scale, r, xw, scal);
   return cudaGetLastError();
 }
 template <class T>

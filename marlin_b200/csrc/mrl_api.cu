@@ -551,6 +551,23 @@ extern "C" int mrl_ab_update(mrl_context *ctx, void *ubar, const void *cbar, con
 }
 
 // ------------------------------------------------------------------------------ reductions
+namespace mrl {
+template <class T>
+cudaError_t launch_coupled_solve(const LaunchCtx &lc, int nvar, const void *const *L, const void *const *rhs, void *const *out, double dt,
+                                 int drop_imag, long long total);
+}
+extern "C" int mrl_coupled_solve(mrl_context *ctx, int nvar, const void *const *L, const void *const *rhs, void *const *out, double dt,
+                                 int drop_imag) {
+  if (!ctx || !ctx->dim || !L || !rhs || !out || nvar < 1) return mrl_fail(MRL_ERR_INVALID, "mrl_coupled_solve: bad arguments");
+  if (nvar > 6) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_coupled_solve: at most 6 coupled variables (got %d)", nvar);
+  for (int i = 0; i < nvar; ++i)
+    if (!rhs[i] || !out[i]) return mrl_fail(MRL_ERR_INVALID, "mrl_coupled_solve: null right-hand side / output %d", i);
+  const long long total = ctx->rtotal();
+  if (ctx->precision == MRL_F64) CKL(ctx, launch_coupled_solve<double>(ctx->lc(), nvar, L, rhs, out, dt, drop_imag, total));
+  else CKL(ctx, launch_coupled_solve<float>(ctx->lc(), nvar, L, rhs, out, dt, drop_imag, total));
+  return MRL_OK;
+}
+
 extern "C" int mrl_reduce(mrl_context *ctx, int op, const void *in, int64_t count, double *host_out) {
   if (!ctx || !in || !host_out || count < 1 || op < 0 || op > 3) return mrl_fail(MRL_ERR_INVALID, "mrl_reduce: bad arguments");
   CK(cudaSetDevice(ctx->device));

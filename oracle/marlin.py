@@ -428,7 +428,10 @@ class AdamsBashforthMoultonCoupled(SplitOperatorSolver):
       reaches linalg_solve is the TRANSPOSE of the user's L_ij table (:151-164);
     * a missing diagonal entry dereferences a null pointer in the reference; here it is zero;
     * the sub-time is advanced inside substep() (:177) in addition to TensorSolver::computeBuffer;
-    * a corrector step of order 0 still solves A u = u_n (:213-217), unlike AdamsBashforthMoulton."""
+    * a corrector step of order 0 still solves A u = u_n (:213-217), unlike AdamsBashforthMoulton;
+    * the right-hand side is cast to the dtype of the first variable's linear operator (:141,167),
+      which is real, so only the REAL part of each spectrum enters the solve and the inverse
+      transform (the gold files coupled_*.csv pin exactly this behaviour)."""
 
     def __init__(self, problem, root, buffer, reciprocal_buffer, linear_reciprocal,
                  nonlinear_reciprocal, substeps=1, predictor_order=2, corrector_order=2,
@@ -460,9 +463,12 @@ class AdamsBashforthMoultonCoupled(SplitOperatorSolver):
                     tab[j][i] = b[name]
         rows = [torch.stack([tab[i][j] for j in range(n)], -1) for i in range(n)]
         Lm = torch.stack(rows, -1)
-        A = torch.eye(n, dtype=base.dtype) - self.p.sub_dt * Lm
+        A = torch.eye(n, dtype=base.dtype) - self.p.sub_dt * Lm.to(base.dtype)
+        # :167 casts the (complex) right-hand side to the dtype of the first linear operator, which
+        # is REAL: the imaginary part of every spectrum is dropped before the solve (as coded)
         rhs = torch.stack(rhs_list, -1)
-        sol = torch.linalg.solve(A.to(rhs.dtype), rhs)
+        rhs = rhs.real.to(base.dtype) if (rhs.is_complex() and not base.is_complex()) else rhs.to(base.dtype)
+        sol = torch.linalg.solve(A, rhs)
         return torch.unbind(sol, -1)
 
     def substep(self):

@@ -83,6 +83,34 @@ def test_abm_diagonal_input_matches_csv_gold(tmp_path, ss, cs, order):
     assert err[1:].max() < 1e-9, err.max()
 
 
+COUPLED = [(10, 0, 1), (10, 0, 2), (10, 0, 3), (20, 0, 4), (10, 1, 1), (10, 2, 1), (10, 2, 2)]
+
+
+@pytest.mark.parametrize("ss,cs,order", COUPLED + [(1, 0, 1), (5, 0, 1)])
+def test_abm_coupled_input_matches_csv_gold(tmp_path, ss, cs, order):
+    """test/tests/solvers/coupled.i (AdamsBashforthMoultonCoupled, dense linear operator solved per
+    wavevector by mrl_coupled_solve) with the cli_args of test/tests/solvers/tests."""
+    gold = np.load(f"{G}/csv_golds.npz")[f"coupled_{ss}_{cs}_{order}"]
+    run(tmp_path, "abm_coupled.i", f"ss={ss}", f"cs={cs}", f"order={order}")
+    head, rows = csv(f"{tmp_path}/abm_coupled_{ss}_{cs}_{order}.csv")
+    assert head == ["time", "U", "V", "u_max", "u_min", "v_max", "v_min"]
+    assert rows.shape == gold.shape
+    err = np.abs(rows - gold) / np.maximum(np.abs(gold), 1e-4)   # U, V are round-off sums (1e-17)
+    assert err[1:].max() < 1e-9, err.max()
+
+
+@pytest.mark.parametrize("ss,cs,order", COUPLED)
+def test_abm_nl_coupled_input_matches_csv_gold(tmp_path, ss, cs, order):
+    """test/tests/solvers/nl_coupled.i: complex-valued ParsedCompute nonlinear terms, correctors."""
+    gold = np.load(f"{G}/csv_golds.npz")[f"nl_coupled_{ss}_{cs}_{order}"]
+    run(tmp_path, "abm_nl_coupled.i", f"ss={ss}", f"cs={cs}", f"order={order}")
+    head, rows = csv(f"{tmp_path}/abm_nl_coupled_{ss}_{cs}_{order}.csv")
+    assert head == ["time", "U", "V", "u_max", "u_min", "v_max", "v_min"]
+    assert rows.shape == gold.shape
+    err = np.abs(rows - gold) / np.maximum(np.abs(gold), 1e-4)
+    assert err[1:].max() < 1e-9, err.max()
+
+
 def test_etdrk4_input_matches_csv_gold(tmp_path):
     """test/tests/solvers/etdrk4_diffusion.i -> gold/etdrk4_diffusion_rmse.csv (time,mse,rmse);
     rmse is a MOOSE ParsedPostprocessor = sqrt(mse) (skipped by the driver, formed here)."""
