@@ -273,11 +273,15 @@ static cudaError_t mech_fused_tma_go(const LaunchCtx &lc, cx<T> *spec, const T *
 template <class T>
 cudaError_t launch_mech_fused_tma(const LaunchCtx &lc, cx<T> *spec, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzv,
                                   int ncp, const cx<T> *tw) {
-  if (!tma_enabled() || env_int("MRL_MECH_FUSED", 1) == 0) return cudaErrorNotSupported;
+  static const int enabled = env_int("MRL_MECH_FUSED", 1), variant = env_int("MRL_MECH_V", 0);
+  if (!tma_enabled() || !enabled) return cudaErrorNotSupported;
   if constexpr (sizeof(T) == 8) {
     switch (n0) {
       case 128: return mech_fused_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
-      case 256: return mech_fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 2>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+      case 256:
+        if (variant == 1) return mech_fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+        if (variant == 2) return mech_fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 3>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
+        return mech_fused_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 2>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
       case 512: return mech_fused_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
       case 1024: return mech_fused_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 1>(lc, spec, kx, ky, kz, n0, n1, nzv, ncp, tw);
       default: return cudaErrorNotSupported;
