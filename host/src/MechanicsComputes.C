@@ -4,8 +4,8 @@
 //   RankTwoIdentity           src/tensor_computes/RankTwoIdentity.C:14-33
 //   MacroscopicShearTensor    test/src/tensor_computes/MacroscopicShearTensor.C:15-41 (test fixture)
 //   PhaseMechanicsTest        test/src/tensor_computes/PhaseMechanicsTest.C:15-50     (test fixture)
-// Rank-two fields are stored component major on the device ([9][nx][ny][nz], c = 3 i + j; see
-// include/marlin_b200.h); Ghat4, C4 and the tangent K4 are never materialised.
+// Rank-two fields are dim x dim and stored component major on the device ([D*D][nx][ny][nz],
+// c = D i + j; see include/marlin_b200.h); Ghat4, C4 and the tangent K4 are never materialised.
 #include "MechanicsComputes.h"
 
 #include <cstring>
@@ -24,11 +24,12 @@ InputParameters RankTwoIdentity::validParams() {
 RankTwoIdentity::RankTwoIdentity(const InputParameters &parameters) : TensorOperator<>(parameters) {}
 
 void RankTwoIdentity::computeBuffer() {
-  if (_dim != 3) mooseError("the CUDA mechanics path is 3-D");
+  if (_dim != 3 && _dim != 2) mooseError("the CUDA mechanics path is 2-D or 3-D");
   const size_t n = size_t(_domain.getNumberOfCells());
-  std::vector<double> host(9 * n, 0.0);
-  for (int c : {0, 4, 8}) std::fill(host.begin() + c * n, host.begin() + (c + 1) * n, 1.0);
-  _u = _domain.fromHost(host, Space::REAL, false, 9);
+  const int D = (int)_dim, nc = D * D;
+  std::vector<double> host(nc * n, 0.0);
+  for (int i = 0; i < D; ++i) std::fill(host.begin() + (D * i + i) * n, host.begin() + (D * i + i + 1) * n, 1.0);
+  _u = _domain.fromHost(host, Space::REAL, false, nc);
 }
 
 // ------------------------------------------------------------------------ MacroscopicShearTensor
@@ -43,17 +44,18 @@ InputParameters MacroscopicShearTensor::validParams() {
 MacroscopicShearTensor::MacroscopicShearTensor(const InputParameters &parameters) : TensorOperator<>(parameters), _tF(getInputBuffer("F")) {}
 
 void MacroscopicShearTensor::computeBuffer() {
-  if (!_tF.defined() || _tF.ncomp() != 9) mooseError("F must be an initialised rank-two field");
-  // I + t e0 e1^T - <F>, nine device reductions (DomainAction::average, src/actions/DomainAction.C:1570-1574)
-  std::vector<double> applied(9);
+  const int D = (int)_dim, nc = D * D;
+  if (!_tF.defined() || _tF.ncomp() != nc) mooseError("F must be an initialised rank-two field");
+  // I + t e0 e1^T - <F>, one device reduction per component (DomainAction::average, src/actions/DomainAction.C:1570-1574)
+  std::vector<double> applied(nc);
   const size_t stride = size_t(_tF.count()) * _domain.realBytes();
-  for (int c = 0; c < 9; ++c) {
+  for (int c = 0; c < nc; ++c) {
     double s = 0;
     checkC(mrl_reduce(_domain.context(), MRL_SUM, static_cast<const char *>(_tF.data_ptr()) + c * stride, _tF.count(), &s), "mrl_reduce");
-    applied[c] = ((c == 0 || c == 4 || c == 8) ? 1.0 : 0.0) - s / Real(_domain.getNumberOfCells());
+    applied[c] = ((c / D == c % D) ? 1.0 : 0.0) - s / Real(_domain.getNumberOfCells());
   }
   applied[1] += _time;
-  _u = _domain.fromHost(applied, Space::SCALAR, false, 9);
+  _u = _domain.fromHost(applied, Space::SCALAR, false, nc);
 }
 
 // ---------------------------------------------------------------------------- PhaseMechanicsTest
@@ -126,7 +128,7 @@ void HyperElasticIsotropic::computeBuffer() {
   d.nl_abs_tol = 1e-8;
   d.nl_max_its = 100;
   mrl_mech_plan *plan = _plan.get(_domain, d, _tK, _tmu);
-  Tensor P = _domain.empty(Space::REAL, false, 9);
+  Tensor P = _domain.empty(Space::REAL, false, int(_dim * _dim));
   checkC(mrl_mech_constitutive(plan, _tF.data_ptr(), P.data_ptr()), "mrl_mech_constitutive");
   _u = P;
 }
@@ -183,10 +185,12 @@ void FFTMechanics::computeBuffer() {
   mrl_mech_plan *plan = _plan.get(_domain, _desc, _tK, _tmu);
   // _u = _tF (+ applied strain + Newton increments): the solve updates its F argument in place
   Tensor F = _domain.clone(_tF);
-  Tensor P = _domain.empty(Space::REAL, false, 9);
+  const int nc = int(_dim * _dim);
+  if (_tF.ncomp() != nc) mooseError("F must be a ", _dim, "x", _dim, " tensor field");
+  Tensor P = _domain.empty(Space::REAL, false, nc);
   std::vector<double> applied;
   if (_applied_macroscopic_strain) {
-    if (_applied_macroscopic_strain->numel() != 9) mooseError("applied_macroscopic_strain must be a 3x3 tensor");
+    if (_applied_macroscopic_strain->numel() != nc) mooseError("applied_macroscopic_strain must be a ", _dim, "x", _dim, " tensor");
     applied = _domain.toHost(*_applied_macroscopic_strain);
   }
   std::memset(&_stats, 0, sizeof _stats);

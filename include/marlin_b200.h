@@ -232,9 +232,10 @@ int mrl_split_launches_per_substep(const mrl_split_plan *plan);
 /* ---- de Geus finite-strain FFT mechanics ------------------------------------------------
  * FFTMechanics (src/tensor_computes/FFTMechanics.C:48-163) with the HyperElasticIsotropic
  * constitutive model (src/tensor_computes/HyperElasticIsotropic.C:42-52) and the matrix-free CG
- * of include/utils/MarlinUtils.h:57-131.  Tensor fields are COMPONENT-MAJOR here:
- * [9][nx][ny][nz] with component c = 3*i + j; the reference layout [nx][ny][nz][3][3] is
- * converted with mrl_components().  Ghat4 (81 complex values per wavevector) and C4 / K4 (81
+ * of include/utils/MarlinUtils.h:57-131.  The domain is 3-D or 2-D; tensors are D x D with
+ * D = dim (test/tests/mechanics/mech3d.i, mech.i).  Tensor fields are COMPONENT-MAJOR here:
+ * [D*D][nx][ny][nz] with component c = D*i + j; the reference layout [nx][ny][nz][D][D] is
+ * converted with mrl_components().  Ghat4 (D^4 complex values per wavevector) and C4 / K4 (D^4
  * values per voxel) are never materialised: the contractions are evaluated in closed form from
  * q and from (F, K, mu).  K and mu are real [nx][ny][nz] fields owned by the caller.        */
 typedef struct mrl_mech_plan mrl_mech_plan;
@@ -259,8 +260,9 @@ int mrl_mech_apply_G(mrl_mech_plan *plan, const void *A_dev, void *out_dev);
 /* out = G( K4(F) : x )              FFTMechanics.C:107-112 (the CG operator)                 */
 int mrl_mech_apply_GK(mrl_mech_plan *plan, const void *F_dev, const void *x_dev, void *out_dev);
 /* One FFTMechanics::computeBuffer: F is updated in place (F + applied strain + Newton
- * increments), P receives the stress of the final state.  applied9: row-major 3x3 applied
- * macroscopic strain or NULL.  Synchronous (iteration counts depend on device-side norms).   */
+ * increments), P receives the stress of the final state.  applied9: row-major D x D applied
+ * macroscopic strain (D*D values) or NULL.  Synchronous (iteration counts depend on
+ * device-side norms).                                                                        */
 int mrl_mech_solve(mrl_mech_plan *plan, void *F_dev, const double *applied9, void *P_dev, mrl_mech_stats *stats);
 /* [n][ncomp] (components fastest, the reference layout) <-> [ncomp][n]; in != out.           */
 int mrl_components(mrl_context *ctx, const void *in_dev, void *out_dev, int64_t n, int ncomp, int to_component_major);

@@ -425,7 +425,7 @@ def components(ctx, t, ncomp, to_component_major):
 
 class MechPlan:
     """FFTMechanics + HyperElasticIsotropic behind the C ABI (component-major tensor fields
-    [9][nx][ny][nz]); see include/marlin_b200.h."""
+    [D*D][nx][ny][nz], D = dim = 2 or 3); see include/marlin_b200.h."""
 
     def __init__(self, ctx, K, mu, l_tol=1e-2, l_max_its=0, nl_rel_tol=1e-5, nl_abs_tol=1e-8, nl_max_its=100):
         self.ctx = ctx
@@ -453,7 +453,7 @@ class MechPlan:
         """One FFTMechanics::computeBuffer; F is updated in place. Returns (P, stats)."""
         P = torch.empty_like(F)
         st = MechStats()
-        a = (C.c_double * 9)(*[float(v) for v in applied]) if applied is not None else None
+        a = (C.c_double * len(applied))(*[float(v) for v in applied]) if applied is not None else None
         _ck(lib().mrl_mech_solve(self.h, _p(F), a, _p(P), C.byref(st)))
         return P, st
 

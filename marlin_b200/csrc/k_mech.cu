@@ -11,61 +11,82 @@
 //   P      = F S                                                           (dot22(F, S))
 //   K4 : x = x S + F T(F^T x),  T(W) = K tr(W) I + 2 mu (sym W - tr(W)/3 I) (trans2(ddot42(K4, trans2 x)))
 //   Ghat:A = (A q) q^T / |q|^2   (0 at q = 0)                              (ddot42(Ghat4, A))
-// Fields are component-major: [9][nx][ny][nz] real, [9][nx][ny][ncp] complex (c = 3 i + j).
+// Fields are component-major: [D*D][nx][ny][nz] real, [D*D][nx][ny][ncp] complex (c = D i + j), with
+// D = 2 or 3 the problem dimension (the reference's tensors are dim x dim, FFTMechanics.C:50-58; the
+// literal 1/3 of the deviatoric split stays 1/3 in 2-D, HyperElasticIsotropic.C:45).
 #include "k_common.cuh"
 #include "mrl_internal.h"
 
 namespace mrl {
 
-template <class T> struct M3 {
-  T a[3][3];
+template <class T, int D> struct MD {
+  T a[D][D];
 };
 
-template <class T> __device__ __forceinline__ void second_pk(const M3<T> &F, T K, T mu, M3<T> &S) {
-  T E[3][3];
+template <class T, int D> __device__ __forceinline__ void second_pk(const MD<T, D> &F, T K, T mu, MD<T, D> &S) {
+  T E[D][D];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < D; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
+    for (int j = 0; j < D; ++j) {
       T s = T(0);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) s += F.a[k][i] * F.a[k][j];
+      for (int k = 0; k < D; ++k) s += F.a[k][i] * F.a[k][j];
       E[i][j] = T(0.5) * (s - (i == j ? T(1) : T(0)));
     }
-  const T tr = E[0][0] + E[1][1] + E[2][2];
+  T tr = T(0);
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < D; ++i) tr += E[i][i];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) S.a[i][j] = T(2) * mu * E[i][j] + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) S.a[i][j] = T(2) * mu * E[i][j] + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
 }
 
 // mode 0: R = P = F S.   mode 1-3: R = K4 : X.
-template <class T> __device__ __forceinline__ void mech_point(int mode, const M3<T> &Fm, T K, T mu, const M3<T> &X, M3<T> &R) {
-  M3<T> S;
+template <class T, int D> __device__ __forceinline__ void mech_point(int mode, const MD<T, D> &Fm, T K, T mu, const MD<T, D> &X, MD<T, D> &R) {
+  MD<T, D> S;
   second_pk(Fm, K, mu, S);
   if (mode == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < D; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) R.a[i][j] = Fm.a[i][0] * S.a[0][j] + Fm.a[i][1] * S.a[1][j] + Fm.a[i][2] * S.a[2][j];
+      for (int j = 0; j < D; ++j) {
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) s += Fm.a[i][k] * S.a[k][j];
+        R.a[i][j] = s;
+      }
   } else {
-    T W[3][3];
+    T W[D][D];
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+    for (int p = 0; p < D; ++p)
 #pragma unroll
-      for (int l = 0; l < 3; ++l) W[p][l] = Fm.a[0][p] * X.a[0][l] + Fm.a[1][p] * X.a[1][l] + Fm.a[2][p] * X.a[2][l];
-    const T tr = W[0][0] + W[1][1] + W[2][2];
-    T Tm[3][3];
+      for (int l = 0; l < D; ++l) {
+        T s = T(0);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < D; ++k) s += Fm.a[k][p] * X.a[k][l];
+        W[p][l] = s;
+      }
+    T tr = T(0);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) Tm[i][j] = mu * (W[i][j] + W[j][i]) + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
+    for (int i = 0; i < D; ++i) tr += W[i][i];
+    T Tm[D][D];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < D; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        R.a[i][j] = X.a[i][0] * S.a[0][j] + X.a[i][1] * S.a[1][j] + X.a[i][2] * S.a[2][j] + Fm.a[i][0] * Tm[0][j] + Fm.a[i][1] * Tm[1][j] +
-                    Fm.a[i][2] * Tm[2][j];
+      for (int j = 0; j < D; ++j) Tm[i][j] = mu * (W[i][j] + W[j][i]) + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) s += X.a[i][k] * S.a[k][j];
+#pragma unroll
+        for (int k = 0; k < D; ++k) s += Fm.a[i][k] * Tm[k][j];
+        R.a[i][j] = s;
+      }
   }
 }
 
@@ -94,57 +115,60 @@ template <class T, int W> __device__ __forceinline__ void stw(T *p, const Lanes<
 // constant x (9 values in xc) - the applied macroscopic strain.   mode 3: the CG direction update
 // fused in: x <- r + beta x (beta = scal[SC_BETA], x written back through xw), then out = K4 : x.
 // W consecutive voxels per thread (W = 2: 128-bit accesses in fp64); n must be a multiple of W.
-template <class T, int MODE, int W>
-__global__ void __launch_bounds__(256) k_mech_pointwise(const T *F, const T *Kf, const T *muf, const T *x, M3<T> xc, T *out, long long n,
+template <class T, int MODE, int W, int D>
+__global__ void __launch_bounds__(256) k_mech_pointwise(const T *F, const T *Kf, const T *muf, const T *x, MD<T, D> xc, T *out, long long n,
                                                         T scale, const T *r, T *xw, const double *scal) {
+  constexpr int NC = D * D;
   const double beta = MODE == 3 ? scal[4 /* SC_BETA */] : 0.0;
   const long long nw = n / W;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nw; q += (long long)gridDim.x * blockDim.x) {
     const long long v = q * W;
-    Lanes<T, W> f[9], xv[9], rv[9];
+    Lanes<T, W> f[NC], xv[NC], rv[NC];
 #pragma unroll
-    for (int c = 0; c < 9; ++c) f[c] = ldw<T, W>(F + c * n + v);
+    for (int c = 0; c < NC; ++c) f[c] = ldw<T, W>(F + c * n + v);
     if (MODE == 1 || MODE == 3) {
 #pragma unroll
-      for (int c = 0; c < 9; ++c) xv[c] = ldw<T, W>(x + c * n + v);
+      for (int c = 0; c < NC; ++c) xv[c] = ldw<T, W>(x + c * n + v);
     }
     if (MODE == 3) {
 #pragma unroll
-      for (int c = 0; c < 9; ++c) rv[c] = ldw<T, W>(r + c * n + v);
+      for (int c = 0; c < NC; ++c) rv[c] = ldw<T, W>(r + c * n + v);
     }
     const Lanes<T, W> Kv = ldw<T, W>(Kf + v), muv = ldw<T, W>(muf + v);
-    Lanes<T, W> o[9];
+    Lanes<T, W> o[NC];
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-      M3<T> Fm, X = xc, R;
+      MD<T, D> Fm, X = xc, R;
 #pragma unroll
-      for (int c = 0; c < 9; ++c) Fm.a[c / 3][c % 3] = f[c].v[w];
+      for (int c = 0; c < NC; ++c) Fm.a[c / D][c % D] = f[c].v[w];
       if (MODE == 1) {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = xv[c].v[w];
+        for (int c = 0; c < NC; ++c) X.a[c / D][c % D] = xv[c].v[w];
       } else if (MODE == 3) {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) {
+        for (int c = 0; c < NC; ++c) {
           const T pn = (T)((double)rv[c].v[w] + beta * (double)xv[c].v[w]);  // same arithmetic as VOP_XPBY
           xv[c].v[w] = pn;
-          X.a[c / 3][c % 3] = pn;
+          X.a[c / D][c % D] = pn;
         }
       }
-      mech_point<T>(MODE, Fm, Kv.v[w], muv.v[w], X, R);
+      mech_point<T, D>(MODE, Fm, Kv.v[w], muv.v[w], X, R);
 #pragma unroll
-      for (int c = 0; c < 9; ++c) o[c].v[w] = R.a[c / 3][c % 3] * scale;
+      for (int c = 0; c < NC; ++c) o[c].v[w] = R.a[c / D][c % D] * scale;
     }
     if (MODE == 3) {
 #pragma unroll
-      for (int c = 0; c < 9; ++c) stw<T, W>(xw + c * n + v, xv[c]);
+      for (int c = 0; c < NC; ++c) stw<T, W>(xw + c * n + v, xv[c]);
     }
 #pragma unroll
-    for (int c = 0; c < 9; ++c) stw<T, W>(out + c * n + v, o[c]);
+    for (int c = 0; c < NC; ++c) stw<T, W>(out + c * n + v, o[c]);
   }
 }
 
-// In place: A_ij <- (sum_k A_ik q_k) q_j / |q|^2 for every wavevector (0 at q = 0)
-template <class T>
+// In place: A_ij <- (sum_k A_ik q_k) q_j / |q|^2 for every wavevector (0 at q = 0).
+// D = 3: [9][n0][n1][ncp], q = (kx[ix], ky[iy], kz[iz]).  D = 2: [4][n0][ncp] (n1 = 1), q = (kx[ix], ky[iz])
+// with ky the half-spectrum axis passed in `kz`.
+template <class T, int D>
 __global__ void __launch_bounds__(256) k_mech_project(cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp) {
   const long long plane = (long long)n1 * ncp, field = (long long)n0 * plane;
   const long long total = (long long)n0 * n1 * nzc;
@@ -153,16 +177,27 @@ __global__ void __launch_bounds__(256) k_mech_project(cx<T> *A, const T *kx, con
     const int iy = (int)((w / nzc) % n1);
     const int ix = (int)(w / ((long long)nzc * n1));
     const long long off = (long long)ix * plane + (long long)iy * ncp + iz;
-    const T q[3] = {kx[ix], ky[iy], kz[iz]};
-    const T Q = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    T q[D];
+    q[0] = kx[ix];
+    if (D == 3) q[1] = ky[iy];
+    q[D - 1] = kz[iz];
+    T Q = T(0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) Q += q[d] * q[d];
     const T inv = Q == T(0) ? T(0) : T(1) / Q;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const cx<T> a0 = A[(3 * i + 0) * field + off], a1 = A[(3 * i + 1) * field + off], a2 = A[(3 * i + 2) * field + off];
-      const T vx = (a0.x * q[0] + a1.x * q[1] + a2.x * q[2]) * inv;
-      const T vy = (a0.y * q[0] + a1.y * q[1] + a2.y * q[2]) * inv;
+    for (int i = 0; i < D; ++i) {
+      T vx = T(0), vy = T(0);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) A[(3 * i + j) * field + off] = mk<T>(vx * q[j], vy * q[j]);
+      for (int l = 0; l < D; ++l) {
+        const cx<T> a = A[(D * i + l) * field + off];
+        vx += a.x * q[l];
+        vy += a.y * q[l];
+      }
+      vx *= inv;
+      vy *= inv;
+#pragma unroll
+      for (int j = 0; j < D; ++j) A[(D * i + j) * field + off] = mk<T>(vx * q[j], vy * q[j]);
     }
   }
 }
@@ -269,11 +304,11 @@ __global__ void __launch_bounds__(256) k_vec_final(int fin, int slot, const doub
   }
 }
 
-// y[c][v] += s[c] (9 constants): F + applied macroscopic strain
-template <class T> __global__ void __launch_bounds__(256) k_add_const9(T *y, M3<T> s, long long n) {
+// y[c][v] += s[c] (D*D constants): F + applied macroscopic strain
+template <class T, int D> __global__ void __launch_bounds__(256) k_add_const9(T *y, MD<T, D> s, long long n) {
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) y[c * n + v] += s.a[c / 3][c % 3];
+    for (int c = 0; c < D * D; ++c) y[c * n + v] += s.a[c / D][c % D];
   }
 }
 
@@ -294,32 +329,40 @@ static inline int ew_grid(long long total, const LaunchCtx &lc) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
-template <class T, int W>
-static void mech_pointwise_go(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const M3<T> &X, T *out,
+template <class T, int W, int D>
+static void mech_pointwise_go(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
                               long long n, T scale, const T *r, T *xw, const double *scal) {
+  MD<T, D> X;
+  for (int c = 0; c < D * D; ++c) X.a[c / D][c % D] = xc ? (T)xc[c] : T(0);
   const int grid = ew_grid(n / W, lc);
   switch (mode) {
-    case 0: k_mech_pointwise<T, 0, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
-    case 1: k_mech_pointwise<T, 1, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
-    case 2: k_mech_pointwise<T, 2, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
-    default: k_mech_pointwise<T, 3, W><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+    case 0: k_mech_pointwise<T, 0, W, D><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+    case 1: k_mech_pointwise<T, 1, W, D><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+    case 2: k_mech_pointwise<T, 2, W, D><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
+    default: k_mech_pointwise<T, 3, W, D><<<grid, 256, 0, lc.stream>>>(F, K, mu, x, X, out, n, scale, r, xw, scal); break;
   }
 }
+// dim = 2 or 3: tensors are dim x dim, xc holds dim*dim values
 template <class T>
-cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
-                                  long long n, double scale, const T *r, T *xw, const double *scal) {
-  M3<T> X;
-  for (int c = 0; c < 9; ++c) X.a[c / 3][c % 3] = xc ? (T)xc[c] : T(0);
+cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int dim, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc,
+                                  T *out, long long n, double scale, const T *r, T *xw, const double *scal) {
   bool wide = (n % 2) == 0;
   for (const void *q : {(const void *)F, (const void *)K, (const void *)mu, (const void *)x, (const void *)out, (const void *)r, (const void *)xw})
     wide = wide && (((unsigned long long)q & (2 * sizeof(T) - 1)) == 0);
-  if (wide) mech_pointwise_go<T, 2>(lc, mode, F, K, mu, x, X, out, n, (T)scale, r, xw, scal);
-  else mech_pointwise_go<T, 1>(lc, mode, F, K, mu, x, X, out, n, (T)scale, r, xw, scal);
+  if (dim == 3) {
+    if (wide) mech_pointwise_go<T, 2, 3>(lc, mode, F, K, mu, x, xc, out, n, (T)scale, r, xw, scal);
+    else mech_pointwise_go<T, 1, 3>(lc, mode, F, K, mu, x, xc, out, n, (T)scale, r, xw, scal);
+  } else {
+    if (wide) mech_pointwise_go<T, 2, 2>(lc, mode, F, K, mu, x, xc, out, n, (T)scale, r, xw, scal);
+    else mech_pointwise_go<T, 1, 2>(lc, mode, F, K, mu, x, xc, out, n, (T)scale, r, xw, scal);
+  }
   return cudaGetLastError();
 }
 template <class T>
-cudaError_t launch_mech_project(const LaunchCtx &lc, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp) {
-  k_mech_project<T><<<ew_grid((long long)n0 * n1 * nzc, lc), 256, 0, lc.stream>>>(A, kx, ky, kz, n0, n1, nzc, ncp);
+cudaError_t launch_mech_project(const LaunchCtx &lc, int dim, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp) {
+  const int grid = ew_grid((long long)n0 * n1 * nzc, lc);
+  if (dim == 3) k_mech_project<T, 3><<<grid, 256, 0, lc.stream>>>(A, kx, ky, kz, n0, n1, nzc, ncp);
+  else k_mech_project<T, 2><<<grid, 256, 0, lc.stream>>>(A, kx, ky, kz, n0, n1, nzc, ncp);
   return cudaGetLastError();
 }
 template <class T>
@@ -343,10 +386,16 @@ cudaError_t launch_vec(const LaunchCtx &lc, int op, const T *a, const T *b, T *y
   }
   return e;
 }
-template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, T *y, const double *s, long long n) {
-  M3<T> S;
-  for (int c = 0; c < 9; ++c) S.a[c / 3][c % 3] = (T)s[c];
-  k_add_const9<T><<<ew_grid(n, lc), 256, 0, lc.stream>>>(y, S, n);
+template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, int dim, T *y, const double *s, long long n) {
+  if (dim == 3) {
+    MD<T, 3> S;
+    for (int c = 0; c < 9; ++c) S.a[c / 3][c % 3] = (T)s[c];
+    k_add_const9<T, 3><<<ew_grid(n, lc), 256, 0, lc.stream>>>(y, S, n);
+  } else {
+    MD<T, 2> S;
+    for (int c = 0; c < 4; ++c) S.a[c / 2][c % 2] = (T)s[c];
+    k_add_const9<T, 2><<<ew_grid(n, lc), 256, 0, lc.stream>>>(y, S, n);
+  }
   return cudaGetLastError();
 }
 template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *in, T *out, long long n, int ncomp, int to_soa) {
@@ -355,12 +404,12 @@ template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *i
 }
 
 #define INST(T)                                                                                                                   \
-  template cudaError_t launch_mech_pointwise<T>(const LaunchCtx &, int, const T *, const T *, const T *, const T *, const double *, \
-                                                T *, long long, double, const T *, T *, const double *);                                                        \
-  template cudaError_t launch_mech_project<T>(const LaunchCtx &, cx<T> *, const T *, const T *, const T *, int, int, int, int);    \
+  template cudaError_t launch_mech_pointwise<T>(const LaunchCtx &, int, int, const T *, const T *, const T *, const T *, const double *, \
+                                                T *, long long, double, const T *, T *, const double *);                          \
+  template cudaError_t launch_mech_project<T>(const LaunchCtx &, int, cx<T> *, const T *, const T *, const T *, int, int, int, int); \
   template cudaError_t launch_vec<T>(const LaunchCtx &, int, const T *, const T *, T *, T *, double *, double, long long, int, int, \
                                      double *, int);                                                                              \
-  template cudaError_t launch_add_const9<T>(const LaunchCtx &, T *, const double *, long long);                                    \
+  template cudaError_t launch_add_const9<T>(const LaunchCtx &, int, T *, const double *, long long);                                    \
   template cudaError_t launch_components<T>(const LaunchCtx &, const T *, T *, long long, int, int);
 INST(double)
 INST(float)

@@ -16,14 +16,14 @@ enum { SC_RZ = 0, SC_PAP = 1, SC_ALPHA = 2, SC_RES2 = 3, SC_BETA = 4, SC_TMP = 5
 enum { VOP_DOT = 0, VOP_CG_XR = 1, VOP_XPBY = 2, VOP_AXPY = 3, VOP_SUB = 4, VOP_COPY = 5 };
 enum { FIN_STORE = 0, FIN_ALPHA = 1, FIN_RES = 2 };
 template <class T>
-cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc, T *out,
-                                  long long n, double scale, const T *r = nullptr, T *xw = nullptr, const double *scal = nullptr);
+cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int dim, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc,
+                                  T *out, long long n, double scale, const T *r = nullptr, T *xw = nullptr, const double *scal = nullptr);
 template <class T>
-cudaError_t launch_mech_project(const LaunchCtx &lc, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp);
+cudaError_t launch_mech_project(const LaunchCtx &lc, int dim, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp);
 template <class T>
 cudaError_t launch_vec(const LaunchCtx &lc, int op, const T *a, const T *b, T *y, T *z, double *scal, double s, long long n, int fin, int slot,
                        double *partials, int nblk);
-template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, T *y, const double *s, long long n);
+template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, int dim, T *y, const double *s, long long n);
 template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *in, T *out, long long n, int ncomp, int to_soa);
 }  // namespace mrl
 
@@ -39,9 +39,10 @@ struct mrl_mech_plan {
   mrl_mech_desc desc;
   const void *K = nullptr, *mu = nullptr;
   long long n = 0;  // voxels
+  int dim = 3, nc = 9;  // tensors are dim x dim (FFTMechanics.C:50-58), nc = dim*dim components
   int ncp = 0;
-  void *spec = nullptr;                                                    // [9][n0][n1][ncp] complex
-  void *tmp = nullptr, *rhs = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *Ap = nullptr, *Fk = nullptr;  // [9][n] real
+  void *spec = nullptr;                                                    // [nc][n0][n1][ncp] complex
+  void *tmp = nullptr, *rhs = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *Ap = nullptr, *Fk = nullptr;  // [nc][n] real
   double *scal = nullptr, *partials = nullptr, *host = nullptr;
   int nblk = 0;
   bool fused_x = true;  // x pass fused with the Green projection (sizes with a TMA configuration)
@@ -58,7 +59,8 @@ extern "C" int mrl_mech_plan_destroy(mrl_mech_plan *p) {
 
 extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, const void *K, const void *mu, mrl_mech_plan **out) {
   if (!ctx || !d || !K || !mu || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_plan_create: bad arguments");
-  if (ctx->dim != 3) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_mech_plan_create: the CUDA mechanics path is 3-D (dim = %d)", ctx->dim);
+  if (ctx->dim != 3 && ctx->dim != 2)
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_mech_plan_create: the CUDA mechanics path is 2-D or 3-D (dim = %d)", ctx->dim);
   CK(cudaSetDevice(ctx->device));
   mrl_mech_plan *p = new mrl_mech_plan();
   p->ctx = ctx;
@@ -66,11 +68,14 @@ extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, co
   p->K = K;
   p->mu = mu;
   p->n = ctx->total();
+  p->dim = ctx->dim;
+  p->nc = ctx->dim * ctx->dim;
+  p->fused_x = ctx->dim == 3;
   if (p->desc.l_max_its <= 0) p->desc.l_max_its = p->n;  // FFTMechanics.C:63-64: default = number of cells
   p->ncp = mrl_fftb_pitch(ctx);
   const size_t esz = ctx->precision == MRL_F64 ? 8 : 4;
-  const size_t vbytes = 9 * (size_t)p->n * esz;
-  const size_t sbytes = 9 * (size_t)ctx->n[0] * ctx->n[1] * p->ncp * 2 * esz;
+  const size_t vbytes = p->nc * (size_t)p->n * esz;
+  const size_t sbytes = p->nc * (size_t)ctx->n[0] * (ctx->dim == 3 ? ctx->n[1] : 1) * p->ncp * 2 * esz;
   p->nblk = ctx->sm_count * 4;
   cudaError_t e = cudaMalloc(&p->spec, sbytes);
   if (e == cudaSuccess) e = cudaMemsetAsync(p->spec, 0, sbytes, ctx->stream);
@@ -91,28 +96,32 @@ extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, co
 template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, double sign) {
   // out = sign * irfftn( Ghat4 : rfftn(A) ), FFTMechanics.C:104-105
   mrl_context *ctx = p->ctx;
+  const int nc = p->nc;
   const T *kx = (const T *)ctx->kaxis_dev[0], *ky = (const T *)ctx->kaxis_dev[1], *kz = (const T *)ctx->kaxis_dev[2];
+  // 2-D: the half-spectrum axis is y; the projection kernel sees [nc][n0][1][ncp] with q = (kx, ky)
+  const T *klast = p->dim == 3 ? kz : ky;
+  const int n1 = p->dim == 3 ? ctx->n[1] : 1, nlast = ctx->nr[p->dim - 1];
   int rc;
   if (p->fused_x) {
     // z, y forward; x forward + projection + x inverse in ONE pass over the spectra; y, z inverse
-    if ((rc = mrl_fftb_forward(ctx, A, p->spec, 9, p->ncp, 1))) return rc;
+    if ((rc = mrl_fftb_forward(ctx, A, p->spec, nc, p->ncp, 1))) return rc;
     const void *tw;
     if ((rc = ctx->twiddles(ctx->n[0], &tw))) return rc;
     cudaError_t e = launch_mech_fused_tma<T>(ctx->lc(), (cx<T> *)p->spec, kx, ky, kz, ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp,
                                              (const cx<T> *)tw);
     if (e == cudaSuccess) {
       ctx->launches++;
-      return mrl_fftb_inverse(ctx, p->spec, out, 9, p->ncp, sign / (double)p->n, 1);
+      return mrl_fftb_inverse(ctx, p->spec, out, nc, p->ncp, sign / (double)p->n, 1);
     }
     if (e != cudaErrorNotSupported) CK(e);
     p->fused_x = false;  // no pipelined configuration for this size: finish with the separate passes
-    if ((rc = mrl_fftb_strided(ctx, p->spec, 9, p->ncp, 0, 0))) return rc;
-  } else if ((rc = mrl_fftb_forward(ctx, A, p->spec, 9, p->ncp))) {
+    if ((rc = mrl_fftb_strided(ctx, p->spec, nc, p->ncp, 0, 0))) return rc;
+  } else if ((rc = mrl_fftb_forward(ctx, A, p->spec, nc, p->ncp))) {
     return rc;
   }
   ctx->launches++;
-  CK(launch_mech_project<T>(ctx->lc(), (cx<T> *)p->spec, kx, ky, kz, ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp));
-  return mrl_fftb_inverse(ctx, p->spec, out, 9, p->ncp, sign / (double)p->n);
+  CK(launch_mech_project<T>(ctx->lc(), p->dim, (cx<T> *)p->spec, kx, ky, klast, ctx->n[0], n1, nlast, p->ncp));
+  return mrl_fftb_inverse(ctx, p->spec, out, nc, p->ncp, sign / (double)p->n);
 }
 
 // r_update != nullptr: x is the CG direction, first replaced by r_update + beta x (beta on the device)
@@ -121,14 +130,14 @@ static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xcon
   // out = sign * G( K4(F) : x ), FFTMechanics.C:107-112
   mrl_context *ctx = p->ctx;
   ctx->launches++;
-  CK(launch_mech_pointwise<T>(ctx->lc(), r_update ? 3 : xconst ? 2 : 1, F, (const T *)p->K, (const T *)p->mu, x, xconst, (T *)p->tmp, p->n,
+  CK(launch_mech_pointwise<T>(ctx->lc(), p->dim, r_update ? 3 : xconst ? 2 : 1, F, (const T *)p->K, (const T *)p->mu, x, xconst, (T *)p->tmp, p->n,
                               1.0, r_update, const_cast<T *>(x), p->scal));
   return project_G<T>(p, (const T *)p->tmp, out, sign);
 }
 
 template <class T> static int vec(mrl_mech_plan *p, int op, const T *a, const T *b, T *y, T *z, double s, int fin = FIN_STORE, int slot = SC_TMP) {
   p->ctx->launches++;
-  CK(launch_vec<T>(p->ctx->lc(), op, a, b, y, z, p->scal, s, 9 * p->n, fin, slot, p->partials, p->nblk));
+  CK(launch_vec<T>(p->ctx->lc(), op, a, b, y, z, p->scal, s, p->nc * p->n, fin, slot, p->partials, p->nblk));
   return MRL_OK;
 }
 static int read_scalar(mrl_mech_plan *p, int slot, double *v) {
@@ -176,7 +185,7 @@ template <class T> static int cg_solve(mrl_mech_plan *p, bool x_zero, int *itera
 template <class T> static int solve_impl(mrl_mech_plan *p, T *F, const double *applied, T *P, mrl_mech_stats *st) {
   mrl_context *ctx = p->ctx;
   const mrl_mech_desc &d = p->desc;
-  const size_t vbytes = 9 * (size_t)p->n * sizeof(T);
+  const size_t vbytes = p->nc * (size_t)p->n * sizeof(T);
   int rc;
   memset(st, 0, sizeof *st);
   // _u = F; constitutive model evaluated at F (:114-116) - the tangent stays at this state until
@@ -186,7 +195,7 @@ template <class T> static int solve_impl(mrl_mech_plan *p, T *F, const double *a
   if ((rc = apply_GK<T>(p, (const T *)p->Fk, nullptr, applied ? applied : zero9, (T *)p->rhs, -1.0))) return rc;
   if (applied) {
     ctx->launches++;
-    CK(launch_add_const9<T>(ctx->lc(), F, applied, p->n));
+    CK(launch_add_const9<T>(ctx->lc(), p->dim, F, applied, p->n));
   }
   double fn2;
   if ((rc = vec<T>(p, VOP_DOT, F, F, nullptr, nullptr, 0, FIN_STORE, SC_TMP))) return rc;
@@ -206,7 +215,7 @@ template <class T> static int solve_impl(mrl_mech_plan *p, T *F, const double *a
     if ((rc = vec<T>(p, VOP_AXPY, (const T *)p->x, nullptr, F, nullptr, 1.0))) return rc;
     CK(cudaMemcpyAsync(p->Fk, F, vbytes, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->launches++;
-    CK(launch_mech_pointwise<T>(ctx->lc(), 0, (const T *)p->Fk, (const T *)p->K, (const T *)p->mu, nullptr, nullptr, P, p->n, 1.0));
+    CK(launch_mech_pointwise<T>(ctx->lc(), p->dim, 0, (const T *)p->Fk, (const T *)p->K, (const T *)p->mu, nullptr, nullptr, P, p->n, 1.0));
     if ((rc = project_G<T>(p, P, (T *)p->rhs, -1.0))) return rc;
     double x2;
     if ((rc = vec<T>(p, VOP_DOT, (const T *)p->x, (const T *)p->x, nullptr, nullptr, 0, FIN_STORE, SC_TMP))) return rc;
@@ -230,10 +239,10 @@ extern "C" int mrl_mech_constitutive(mrl_mech_plan *p, const void *F, void *P) {
   CK(cudaSetDevice(p->ctx->device));
   p->ctx->launches++;
   if (p->ctx->precision == MRL_F64)
-    CK(launch_mech_pointwise<double>(p->ctx->lc(), 0, (const double *)F, (const double *)p->K, (const double *)p->mu, nullptr, nullptr,
+    CK(launch_mech_pointwise<double>(p->ctx->lc(), p->dim, 0, (const double *)F, (const double *)p->K, (const double *)p->mu, nullptr, nullptr,
                                      (double *)P, p->n, 1.0));
   else
-    CK(launch_mech_pointwise<float>(p->ctx->lc(), 0, (const float *)F, (const float *)p->K, (const float *)p->mu, nullptr, nullptr,
+    CK(launch_mech_pointwise<float>(p->ctx->lc(), p->dim, 0, (const float *)F, (const float *)p->K, (const float *)p->mu, nullptr, nullptr,
                                     (float *)P, p->n, 1.0));
   return MRL_OK;
 }

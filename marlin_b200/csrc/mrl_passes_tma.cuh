@@ -27,8 +27,10 @@ static int g_debug_nofft = 0;
 __device__ int g_debug_nofft = 0;
 #endif
 template <class T, class C, class V, class SM, class TW, class BAR, class HOOK>
-MRL_DI void fft_or_skip(V &v, int t, const SM &sm, const TW &tw, const BAR &bar, const HOOK &hook) {
-  if (g_debug_nofft) {
+MRL_DI void fft_or_skip(bool nofft, V &v, int t, const SM &sm, const TW &tw, const BAR &bar, const HOOK &hook) {
+  // nofft: g_debug_nofft read ONCE per kernel into a register (a load + dependent branch per
+  // transform showed up as 8 % of the stall samples of the fused passes)
+  if (nofft) {
     bar.sync_release();
     hook();
   } else {
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   constexpr int BOXR = N < 256 ? N : 256, NBOX = N / BOXR;
   constexpr int TILE = N * TK;  // complex elements per slot
   MRL_DYN_SMEM(smem_raw);
+  const bool nofft = g_debug_nofft != 0;
   cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));
   uint64_t *full = reinterpret_cast<uint64_t *>(slots + (size_t)NS * TILE);
   const int tid = threadIdx.x;
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       if (io.inverse) v[e].y = -v[e].y;
     }
     bar.sync();  // all inputs are in registers before the exchange overwrites the slot
-    fft_or_skip<T, C>(v, t, sm, twr, bar, [&] {
+    fft_or_skip<T, C>(nofft, v, t, sm, twr, bar, [&] {
       if (gt == 0 && j + NS < nloc) issue(j + NS);
     });
     if (ok && io.peer_tab) {
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   constexpr int BOXR = N < 256 ? N : 256, NBOX = N / BOXR;
   constexpr int TILE = N * TK;
   MRL_DYN_SMEM(smem_raw);
+  const bool nofft = g_debug_nofft != 0;
   cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));
   uint64_t *full = reinterpret_cast<uint64_t *>(slots + (size_t)NG * 3 * TILE);  // [NG][3]
   const int tid = threadIdx.x;
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       MRL_UNROLL
       for (int e = 0; e < E; ++e) gh[e] = sm.ld(t + TP * e);
       bar.sync();
-      fft_or_skip<T, C>(gh, t, sm, twr, bar, [&] {
+      fft_or_skip<T, C>(nofft, gh, t, sm, twr, bar, [&] {
         if (gt == 0 && more) issue(&tmG, sG, bG, j + 1);
       });
     }
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       MRL_UNROLL
       for (int e = 0; e < E; ++e) a[e] = smc.ld(t + TP * e);
       bar.sync();
-      fft_or_skip<T, C>(a, t, smc, twr, bar, [&] {
+      fft_or_skip<T, C>(nofft, a, t, smc, twr, bar, [&] {
         if (gt == 0 && more) issue(&tmC, sC, bC, j + 1);
       });
     }
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     }
     bar.sync();  // every thread has taken its old-term values: the O slot becomes the exchange buffer
     // ---- inverse transform of the updated variable (exchange through the O slot)
-    fft_or_skip<T, C>(a, t, smo, twr, bar, [&] {
+    fft_or_skip<T, C>(nofft, a, t, smo, twr, bar, [&] {
       if (gt == 0 && more && use_old) issue(&tmO, sO, bO, j + 1);
     });
     if (ok && io.peer_tab) {
@@ -369,6 +373,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   constexpr int BOXR = N < 256 ? N : 256, NBOX = N / BOXR;
   constexpr int TILE = N * TK;
   MRL_DYN_SMEM(smem_raw);
+  const bool nofft = g_debug_nofft != 0;
   cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));
   uint64_t *full = reinterpret_cast<uint64_t *>(slots + (size_t)NG * 3 * TILE);  // [NG][3]
   const int tid = threadIdx.x;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     MRL_UNROLL
     for (int e = 0; e < E; ++e) a[e] = sm0.ld(t + TP * e);
     bar.sync();
-    fft_or_skip<T, C>(a, t, sm0, twr, bar, [&] {
+    fft_or_skip<T, C>(nofft, a, t, sm0, twr, bar, [&] {
       if (gt == 0 && more) issue(0, j + 1);
     });
     MRL_UNROLL
@@ -430,7 +435,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     MRL_UNROLL
     for (int e = 0; e < E; ++e) a[e] = sm1.ld(t + TP * e);
     bar.sync();
-    fft_or_skip<T, C>(a, t, sm1, twr, bar, [&] {
+    fft_or_skip<T, C>(nofft, a, t, sm1, twr, bar, [&] {
       if (gt == 0 && more) issue(1, j + 1);
     });
     MRL_UNROLL
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     MRL_UNROLL
     for (int e = 0; e < E; ++e) a[e] = sm2.ld(t + TP * e);
     bar.sync();
-    fft_or_skip<T, C>(a, t, sm2, twr, bar, NoHook());
+    fft_or_skip<T, C>(nofft, a, t, sm2, twr, bar, NoHook());
     MRL_UNROLL
     for (int e = 0; e < E; ++e) {
       const T qx = io.kx[t + TP * e];
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
         const T q = jj == 0 ? io.kx[t + TP * e] : jj == 1 ? qy : qz;
         a[e] = mk<T>(s[e].x * q, -s[e].y * q);
       }
-      fft_or_skip<T, C>(a, t, sm2, twr, bar, [&] {
+      fft_or_skip<T, C>(nofft, a, t, sm2, twr, bar, [&] {
         if (jj == 2 && gt == 0 && more) issue(2, j + 1);
       });
       if (ok) {
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
   static_assert(E % 2 == 0, "Hermitian split by shuffles needs an even number of points per thread");
   static_assert(GT % 32 == 0, "a group must be whole warps (full-mask shuffles inside the group loop)");
   MRL_DYN_SMEM(smem_raw);
+  const bool nofft = g_debug_nofft != 0;
   unsigned char *base = align128(smem_raw);
   T *slots = reinterpret_cast<T *>(base);                                       // [NG][NS][PPB*N] real
   cx<T> *xbuf = reinterpret_cast<cx<T> *>(slots + (size_t)NG * NS * PPB * N);   // [NG][PPB][NP]
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     }
     bar.sync_release();  // slot consumed by the whole group: re-arm it
     if (gt == 0 && j + NS < nloc) issue(j + NS);
-    fft_or_skip<T, C>(v, t, sm, twr, bar, NoHook());
+    fft_or_skip<T, C>(nofft, v, t, sm, twr, bar, NoHook());
     // Hermitian split: partner element of (t, e) is (TP - t, E-1-e); thread 0 pairs (0, e) with (0, E-e)
     cx<T> w[E / 2];
     MRL_UNROLL
@@ -584,6 +590,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
   constexpr int NP = N + (N >> 3) + 1;
   static_assert(E % 2 == 0 && GT % 32 == 0, "whole warps per group, even points per thread");
   MRL_DYN_SMEM(smem_raw);
+  const bool nofft = g_debug_nofft != 0;
   unsigned char *base = align128(smem_raw);
   T *slots = reinterpret_cast<T *>(base);                                          // [NG][NS][2*PPB*N] real
   cx<T> *xbuf = reinterpret_cast<cx<T> *>(slots + (size_t)NG * NS * 2 * PPB * N);  // [NG][PPB][NP]
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     for (int e = 0; e < E; ++e) v[e] = mk<T>(ok ? src[t + TP * e] : T(0), ok2 ? src[N + t + TP * e] : T(0));
     bar.sync_release();
     if (gt == 0 && j + NS < nloc) issue(j + NS);
-    fft_or_skip<T, C>(v, t, sm, twr, bar, NoHook());
+    fft_or_skip<T, C>(nofft, v, t, sm, twr, bar, NoHook());
     cx<T> w[E / 2];
     MRL_UNROLL
     for (int e = 0; e < E / 2; ++e) w[e] = shfl_cx(v[E - 1 - e], plane);
@@ -673,6 +680,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
   constexpr int NCMAX = (N / 2 + 1 + 15) & ~15;  // largest padded row pitch (ncp <= NCMAX)
   constexpr int SLOT = 2 * PPB * NCMAX;          // complex elements per slot
   MRL_DYN_SMEM(smem_raw);
+  const bool nofft = g_debug_nofft != 0;
   cx<T> *slots = reinterpret_cast<cx<T> *>(align128(smem_raw));  // [NG][NS][SLOT]
   cx<T> *xbuf = slots + (size_t)NG * NS * SLOT;                  // [NG][PPB][NP]
   uint64_t *full = reinterpret_cast<uint64_t *>(xbuf + (size_t)NG * PPB * NP);
@@ -728,7 +736,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     }
     bar.sync_release();
     if (gt == 0 && j + NS < nloc) issue(j + NS);
-    fft_or_skip<T, C>(v, t, sm, twr, bar, NoHook());
+    fft_or_skip<T, C>(nofft, v, t, sm, twr, bar, NoHook());
     if (ok) {
       MRL_UNROLL
       for (int e = 0; e < E; ++e) {

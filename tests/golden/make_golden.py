@@ -10,7 +10,7 @@ Sources (relative to the reference root):
   test/tests/cahnhilliard/gold/cahnhilliard_out.e   Exodus/NetCDF-3; nodal `c`, elemental `mu`
   test/tests/solvers/gold/{diagonal,coupled,nl_coupled}_*.csv   postprocessor CSVs
   test/tests/solvers/gold/etdrk4_diffusion_rmse.csv
-  test/tests/mechanics/gold/mech3d.h5               HDF5, one deflate chunk per dataset
+  test/tests/mechanics/gold/{mech3d,mech}.h5        HDF5, one deflate chunk per dataset
   test/tests/gradient/gold/*.csv, test/tests/tensor_compute/gold/backandforth_out.csv
 """
 import os
@@ -123,7 +123,28 @@ def mech3d():
     print("mech3d_h5", F.shape)
 
 
+def mech2d():
+    """test/tests/mechanics/gold/mech.h5 (32^2, 2x2 tensors): per frame F_0..F_3, disp_x, disp_y,
+    phase (nodal 33^2), sV."""
+    n = 32
+    streams = zlib_streams(f"{REF}/test/tests/mechanics/gold/mech.h5")
+    per = 8
+    assert len(streams) % per == 0, len(streams)
+    frames = len(streams) // per
+    F = np.zeros((frames, n, n, 2, 2))
+    sV = np.zeros((frames, n, n))
+    for fr in range(frames):
+        blk = streams[fr * per:(fr + 1) * per]
+        for k in range(4):
+            a = np.frombuffer(blk[k], dtype="<f8").reshape(n, n)  # stored [y,x]
+            F[fr, :, :, k // 2, k % 2] = a.T
+        sV[fr] = np.frombuffer(blk[7], dtype="<f8").reshape(n, n).T
+    np.savez_compressed(f"{OUT}/mech2d_h5.npz", F=F, sV=sV)
+    print("mech2d_h5", F.shape)
+
+
 if __name__ == "__main__":
     exodus_ch2d()
     solver_csvs()
     mech3d()
+    mech2d()

@@ -1,0 +1,96 @@
+# de Geus finite-strain FFT mechanics in 2-D (2x2 tensors) on a 32^2 RVE with a smooth stiff inclusion
+# under macroscopic shear; ForwardEulerSolver forwards Fnew -> F over 3 substeps for 3 steps.  Same
+# setup as the reference's test/tests/mechanics/mech.i (gold mech.h5).
+[Domain]
+  dim = 2
+  nx = 32
+  ny = 32
+  xmax = ${fparse 2*pi}
+  ymax = ${fparse 2*pi}
+  zmax = ${fparse 2*pi}
+  mesh_mode = DUMMY
+[]
+
+[TensorComputes]
+  [Initialize]
+    [phase]
+      type = ParsedCompute
+      buffer = phase
+      expression = '(cos(x)/2+0.5)^1*(cos(y)/2+0.5)^1*(cos(z)/2+0.5)^1'
+      extra_symbols = true
+    []
+    [K]
+      type = ParsedCompute
+      buffer = K
+      expression = '(1-phase)*Ka + phase*Kb'
+      inputs = phase
+      constant_names = 'Ka Kb'
+      constant_expressions = '1 10'
+    []
+    [mu]
+      type = ParsedCompute
+      buffer = mu
+      expression = '(1-phase)*mua + phase*mub'
+      inputs = phase
+      constant_names = 'mua mub'
+      constant_expressions = '0.5 5'
+    []
+    [Finit]
+      type = RankTwoIdentity
+      buffer = F
+    []
+  []
+  [Solve]
+    [hyper_elasticity]
+      type = HyperElasticIsotropic
+      buffer = stress
+      F = Fnew
+      K = K
+      mu = mu
+    []
+    [root]
+      [applied_strain]
+        type = MacroscopicShearTensor
+        buffer = applied_strain
+      []
+      [mech]
+        type = FFTMechanics
+        buffer = Fnew
+        F = F
+        K = K
+        mu = mu
+        l_max_its = 40
+        l_tol = 1e-5
+        nl_rel_tol = 2e-4
+        nl_abs_tol = 2e-3
+        constitutive_model = hyper_elasticity
+        stress = stress
+        applied_macroscopic_strain = applied_strain
+      []
+    []
+  []
+[]
+
+[TensorSolver]
+  type = ForwardEulerSolver
+  root_compute = root
+  forward_buffer = F
+  forward_buffer_new = Fnew
+  substeps = 3
+[]
+
+[TensorOutputs]
+  [deformation_tensor]
+    type = XDMFTensorOutput
+    buffer = 'F phase'
+    output_mode = 'CELL NODE'
+    enable_hdf5 = true
+    execute_on = 'TIMESTEP_END'
+  []
+[]
+
+[Executioner]
+  type = Transient
+  num_steps = 3
+  dt = 0.02
+[]

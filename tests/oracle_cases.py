@@ -90,10 +90,15 @@ def diagonal_row(p):
             om.pp_extreme(p, "v", "MIN")]
 
 
-def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2):
+def mech2d_problem(n=32):
+    """test/tests/mechanics/mech.i (2-D, 2x2 tensors; zmax is set but unused)."""
+    return mech3d_problem(n, substeps=3, l_tol=1e-5, nl_rel_tol=2e-4, nl_abs_tol=2e-3, dim=2, l_max_its=40)
+
+
+def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2, dim=3, l_max_its=None):
     """test/tests/mechanics/mech3d.i."""
     L = 2 * math.pi
-    d = om.Domain(3, [n, n, n], (0, 0, 0), (L, L, L))
+    d = om.Domain(dim, [n] * dim, (0, 0, 0), (L, L, L))
     p = om.Problem(d)
     p.ics = [
         om.ParsedCompute(p, "phase", "(cos(x)/2+0.5)^1*(cos(y)/2+0.5)^1*(cos(z)/2+0.5)^1",
@@ -107,7 +112,7 @@ def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e
     hyper = om.HyperElasticIsotropic(p, "stress", "Fnew", "K", "mu")
     mech = om.FFTMechanics(p, "Fnew", hyper, "K", "mu", F="F", stress="stress",
                            applied_macroscopic_strain="applied_strain", l_tol=l_tol,
-                           nl_rel_tol=nl_rel_tol, nl_abs_tol=nl_abs_tol)
+                           l_max_its=l_max_its, nl_rel_tol=nl_rel_tol, nl_abs_tol=nl_abs_tol)
     root = om.Group(p, [om.MacroscopicShearTensor(p, "applied_strain", "F"), mech])
     p.solver = om.ForwardEulerSolver(p, root, substeps=substeps, forward=[("F", "Fnew")])
     p.mech = mech

@@ -151,6 +151,16 @@ def test_mech3d_input_matches_hdf5_gold(tmp_path):
         assert np.linalg.norm(F - ref) / np.linalg.norm(ref) < 1e-9
 
 
+def test_mech2d_input_matches_hdf5_gold(tmp_path):
+    """test/tests/mechanics/mech.i (2-D, 2x2 tensors) -> gold/mech.h5."""
+    g = np.load(f"{G}/mech2d_h5.npz")["F"]
+    for k in (1, 3):
+        run(tmp_path, "mech2d_shear.i", f"Executioner/num_steps={k}", dump=("F",))
+        F = field(tmp_path, "F", (4, 32, 32))
+        ref = np.moveaxis(g[k - 1].reshape(32, 32, 4), -1, 0)            # rank-two fields are component major
+        assert np.linalg.norm(F - ref) / np.linalg.norm(ref) < 1e-9
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

@@ -96,6 +96,63 @@ def test_mech3d_matches_gold_and_oracle_iterations(ctx):
     plan.close()
 
 
+@pytest.mark.parametrize("n", [32, 20, 128])
+def test_mech2d_operators_match_oracle(ctx, n):
+    """2-D (2x2 tensors, test/tests/mechanics/mech.i): constitutive law, Green projection, CG operator."""
+    from marlin_b200 import capi
+    p = oc.mech3d_problem(n=n, dim=2)
+    p.initial()
+    L = 2 * math.pi
+    ctx.domain_set(2, (n, n), (0,) * 2, (L,) * 2)
+    plan = capi.MechPlan(ctx, p.buf["K"].contiguous().cuda(), p.buf["mu"].contiguous().cuda())
+    to_soa = lambda t: capi.components(ctx, t.contiguous().cuda(), 4, True).view(4, n, n)
+    to_aos = lambda t: capi.components(ctx, t.contiguous(), 4, False).view(n, n, 2, 2).cpu()
+    torch.manual_seed(5)
+    F = torch.eye(2, dtype=torch.float64).expand(n, n, 2, 2) + 0.1 * torch.rand(n, n, 2, 2, dtype=torch.float64)
+    x = torch.rand(n, n, 2, 2, dtype=torch.float64) - 0.5
+    p.buf["Fnew"] = F
+    p.mech.cm.compute()
+    assert rel_l2(to_aos(plan.constitutive(to_soa(F))), p.buf["stress"]) < 1e-13
+    d = p.domain
+    Gx = d.ifft(om.ddot42(p.mech.Ghat4, d.fft(x)))
+    assert rel_l2(to_aos(plan.apply_G(to_soa(x))), Gx) < 1e-12
+    KdF = om.trans2(om.ddot42(p.buf[p.mech.K4], om.trans2(x)))
+    GK = d.ifft(om.ddot42(p.mech.Ghat4, d.fft(KdF)))
+    assert rel_l2(to_aos(plan.apply_GK(to_soa(F), to_soa(x))), GK) < 1e-12
+    plan.close()
+
+
+def test_mech2d_matches_gold_and_oracle_iterations(ctx):
+    """test/tests/mechanics/mech.i (2-D, 2x2 tensors, l_max_its = 40): 3 steps x 3 substeps at 32^2
+    vs gold/mech.h5 and the oracle's CG / Newton iteration counts."""
+    from marlin_b200 import capi
+    n = 32
+    g = torch.from_numpy(np.load(f"{G}/mech2d_h5.npz")["F"])
+    p = oc.mech2d_problem()
+    p.initial()
+    ctx.domain_set(2, (n, n), (0,) * 2, (2 * math.pi,) * 2)
+    plan = capi.MechPlan(ctx, p.buf["K"].contiguous().cuda(), p.buf["mu"].contiguous().cuda(), l_tol=1e-5, l_max_its=40,
+                         nl_rel_tol=2e-4, nl_abs_tol=2e-3)
+    to_aos = lambda t: capi.components(ctx, t.contiguous(), 4, False).view(n, n, 2, 2).cpu()
+    F = capi.components(ctx, p.buf["F"].contiguous().cuda(), 4, True).view(4, n, n)
+    t, dt, substeps = 0.0, 0.02, 3
+    for fr in range(g.shape[0]):
+        p.step(dt)
+        its = None
+        for s in range(substeps):
+            sub_time = t + s * dt / substeps
+            avg = [ctx.reduce(0, F[c]) / n ** 2 for c in range(4)]
+            applied = [(1.0 if c in (0, 3) else 0.0) - avg[c] for c in range(4)]
+            applied[1] += sub_time
+            P, st = plan.solve(F, applied)
+            its = (st.newton_iterations, list(st.cg_iterations[:st.cg_solves]))
+        t += dt
+        assert rel_l2(to_aos(F), g[fr]) < 1e-9, fr
+        assert rel_l2(to_aos(F), p.buf["F"]) < 1e-9
+        assert its[0] == p.mech.newton_iterations and its[1] == p.mech.cg_iterations, (its, p.mech.cg_iterations)
+    plan.close()
+
+
 @pytest.mark.parametrize("n", [128, 256])
 def test_mech_large_properties(ctx, n):
     """Sizes on the TMA kernels (padded spectra): the Green operator is a projection on

@@ -93,6 +93,18 @@ def test_mech3d_matches_hdf5_gold():
         assert rel < 1e-13, (fr, rel)
 
 
+def test_mech2d_matches_hdf5_gold():
+    """test/tests/mechanics/mech.i (2-D, 2x2 tensors, l_max_its = 40) vs gold/mech.h5."""
+    g = np.load(f"{G}/mech2d_h5.npz")["F"]
+    p = oc.mech2d_problem()
+    p.initial()
+    for fr in range(g.shape[0]):
+        p.step(0.02)
+        F = p.buf["F"].numpy()
+        rel = np.linalg.norm(F - g[fr]) / np.linalg.norm(g[fr])
+        assert rel < 1e-12, (fr, rel)
+
+
 def test_fft_roundtrip_even_odd():
     """test/tests/tensor_compute/backandforth.i: fft->ifft is the identity for the even/odd
     1-3-D sizes used there (gold difference exactly 0 at CSV precision)."""
