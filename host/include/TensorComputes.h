@@ -140,3 +140,27 @@ protected:
   const std::vector<marlin::Tensor> &_old_reciprocal_buffer;
   const std::vector<marlin::Tensor> &_old_non_linear_reciprocal;
 };
+
+// src/tensor_computes/SwiftHohenbergLinear.C: r - alpha^2 (1 - k^2)^2
+class SwiftHohenbergLinear : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit SwiftHohenbergLinear(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  ExprKernel _kernel;
+};
+
+// src/tensor_computes/MooseFunctionTensor.C: a MOOSE Function ([Functions], type ParsedFunction)
+// sampled at the cell centres
+class MooseFunctionTensor : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit MooseFunctionTensor(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  marlin::Tensor evaluate(const std::string &function, int depth);
+  const std::string _function;
+};

@@ -90,6 +90,18 @@ public:
   bool hasBuffer(const std::string &buffer_name) const { return _tensor_buffer.count(buffer_name) != 0; }
   const std::map<std::string, std::shared_ptr<TensorBuffer<marlin::Tensor>>> &getBuffers() const { return _tensor_buffer; }
 
+  // [Functions] of type ParsedFunction (MOOSE ParsedFunction: expression, symbol_names, symbol_values);
+  // sampled by MooseFunctionTensor
+  struct ParsedFunctionDesc {
+    std::string expression;
+    std::vector<std::string> symbol_names, symbol_values;
+  };
+  void addFunction(const std::string &name, ParsedFunctionDesc f) { _functions[name] = std::move(f); }
+  const ParsedFunctionDesc *getFunction(const std::string &name) const {
+    auto it = _functions.find(name);
+    return it == _functions.end() ? nullptr : &it->second;
+  }
+
   // scalar constants (MarlinConstantInterface: a name declared in [Problem] or a literal number)
   void declareConstant(const std::string &name, Real value) { _constants[name] = value; }
   Real getConstant(const std::string &name_or_number, const std::string &what) const;
@@ -113,6 +125,11 @@ public:
   void gridChanged();
   // objects that keep history outside the buffer table (fused solver plans) follow advanceState
   void addAdvanceStateHook(std::function<void()> hook) { _advance_hooks.push_back(std::move(hook)); }
+
+private:
+  std::map<std::string, ParsedFunctionDesc> _functions;
+
+public:
 
   // time bookkeeping (FEProblemBase::time() etc.; owned here because MOOSE is not linked)
   Real &time() { return _time; }

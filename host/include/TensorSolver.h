@@ -4,6 +4,7 @@
 // (src/tensor_solver/TensorSolver.C:15-110, SplitOperatorBase.C:14-64, ExplicitSolverBase.C,
 //  AdamsBashforthMoulton.C:20-178, ForwardEulerSolver.C:29-38, ETDRK4Solver.C:29-115).
 #pragma once
+#include "TensorComputes.h"
 #include <array>
 
 #include "TensorOperatorBase.h"
@@ -131,6 +132,35 @@ protected:
   std::vector<std::pair<unsigned int, unsigned int>> _L_offdiag_indices;
   std::vector<TensorInputBufferName> _L_offdiag_names;
   std::vector<const marlin::Tensor *> _L_offdiag_buffer;
+};
+
+// include/tensor_solver/IterativeTensorSolverInterface.h: what TensorSolveIterationAdaptiveDT reads
+class IterativeTensorSolverInterface {
+public:
+  virtual ~IterativeTensorSolverInterface() = default;
+  const unsigned int &getIterations() const { return _iterations; }
+  bool isConverged() const { return _is_converged; }
+
+protected:
+  unsigned int _iterations = 0;
+  bool _is_converged = true;
+};
+
+// src/tensor_solver/SecantSolver.C: implicit Euler, secant iteration per wavevector
+class SecantSolver : public SplitOperatorBase, public IterativeTensorSolverInterface {
+public:
+  static InputParameters validParams();
+  explicit SecantSolver(const InputParameters &parameters);
+
+protected:
+  void substep() override;
+  const unsigned int _max_iterations;
+  const Real _relative_tolerance, _absolute_tolerance;
+  const bool _verbose;
+  const Real _damping, _dt_epsilon;
+  // generated pointwise kernels, with / without a linear operator
+  ExprKernel _r0[2], _start[2], _res[2], _update;
+  Real complexNorm(const marlin::Tensor &t) const;
 };
 
 class ETDRK4Solver : public SplitOperatorBase {

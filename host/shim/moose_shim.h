@@ -22,6 +22,7 @@ using Real = double;
 using TensorInputBufferName = std::string;
 using TensorOutputBufferName = std::string;
 using TensorComputeName = std::string;
+using FunctionName = std::string;
 using MarlinConstantName = std::string;
 using PostprocessorName = std::string;
 

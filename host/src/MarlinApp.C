@@ -125,7 +125,7 @@ void MarlinApp::addComputes(const hit::Node &parent, int task, int depth) {
 }
 
 void MarlinApp::buildObjects() {
-  static const std::set<std::string> known = {"Domain", "GlobalParams", "TensorBuffers", "TensorComputes", "TensorSolver", "Problem", "Postprocessors", "Executioner", "Outputs"};
+  static const std::set<std::string> known = {"Domain", "GlobalParams", "TensorBuffers", "TensorComputes", "TensorSolver", "Problem", "Postprocessors", "Executioner", "Outputs", "Functions"};
   for (hit::Node *s : _root->sections())
     if (!known.count(s->name)) _skipped.push_back(s->name);
 
@@ -143,6 +143,28 @@ void MarlinApp::buildObjects() {
     empty.name = "Problem";
     _problem = std::dynamic_pointer_cast<TensorProblem>(Factory::instance().create(type, fill(type, pb ? *pb : empty, "Problem")));
   }
+  // [Functions]: ParsedFunction objects, sampled by MooseFunctionTensor
+  if (const hit::Node *fb = _root->find("Functions"))
+    for (hit::Node *b : fb->sections()) {
+      const hit::Node *tf = b->field("type");
+      if (!tf || tf->value != "ParsedFunction") {
+        _skipped.push_back(b->fullpath() + (tf ? " (type " + tf->value + ")" : ""));
+        continue;
+      }
+      TensorProblem::ParsedFunctionDesc f;
+      const hit::Node *e = b->field("expression");
+      if (!e) e = b->field("value");
+      if (!e) mooseError(b->fullpath(), ": missing 'expression'");
+      f.expression = e->value;
+      auto list = [&](const char *key) {
+        std::vector<std::string> out;
+        if (const hit::Node *n = b->field(key)) out = shim_detail::Conv<std::vector<std::string>>::from(n->value, b->fullpath() + "/" + key);
+        return out;
+      };
+      f.symbol_names = list("symbol_names");
+      f.symbol_values = list("symbol_values");
+      _problem->addFunction(b->name, f);
+    }
   // [TensorBuffers]
   if (const hit::Node *tb = _root->find("TensorBuffers"))
     for (hit::Node *b : tb->sections()) {
@@ -247,7 +269,9 @@ void MarlinApp::transient() {
   const double dtmin = num(ex, "dtmin", 0.0);
   const long num_steps = (long)num(ex, "num_steps", 4294967295.0);
   double dt0 = num(ex, "dt", 1.0);
-  double growth = 1.0;
+  double growth = 1.0, cutback = 0.5;
+  bool iteration_feedback = false;
+  unsigned int min_iterations = 0, max_iterations = 4294967295u;
   const hit::Node *ts = ex->find("TimeStepper");
   if (ts && ts->is_section) {
     const hit::Node *t = ts->field("type");
@@ -257,8 +281,14 @@ void MarlinApp::transient() {
       growth = num(ts, "growth_factor", 2.0);
     else if (type != "ConstantDT")
       mooseError("[Executioner/TimeStepper]: time stepper '", type, "' is not supported by the stand-alone driver");
-    if (type == "TensorSolveIterationAdaptiveDT")
-      mooseWarning("TensorSolveIterationAdaptiveDT: iteration feedback applies to the iterative solvers (Secant / Broyden); growing by growth_factor every step.");
+    if (type == "TensorSolveIterationAdaptiveDT") {
+      // src/timesteppers/TensorSolveIterationAdaptiveDT.C:161-174
+      iteration_feedback = dynamic_cast<IterativeTensorSolverInterface *>(_problem->getSolver()) != nullptr;
+      if (!iteration_feedback) mooseError("TensorSolveIterationAdaptiveDT needs an iterative tensor solver (SecantSolver)");
+      if (ts->field("min_iterations")) min_iterations = (unsigned int)num(ts, "min_iterations", 0);
+      if (ts->field("max_iterations")) max_iterations = (unsigned int)num(ts, "max_iterations", 0);
+      cutback = num(ts, "cutback_factor", 0.5);
+    }
   }
 
   // [Outputs]
@@ -331,7 +361,23 @@ void MarlinApp::transient() {
     _problem->execute(EXEC_TIMESTEP_END);
     if (out_on & EXEC_TIMESTEP_END) writeCSVRow(false);
     if (!_opt.quiet) std::cerr << "Time Step " << t_step << ", time = " << std::setprecision(8) << time << ", dt = " << dt << "\n";
-    next_dt = dt * growth;
+    if (iteration_feedback) {
+      const auto *it = dynamic_cast<IterativeTensorSolverInterface *>(_problem->getSolver());
+      if (!it->isConverged()) {
+        // TimeStepper::computeFailedDT: repeat the step with cutback_factor_at_failure (0.5)
+        if (!_opt.quiet) std::cerr << "Solve failed, cutting timestep.\n";
+        time = time_old;
+        t_step -= 1;
+        next_dt = dt * 0.5;
+        if (next_dt < std::max(dtmin, 1e-14)) mooseError("Solve failed and timestep already at dtmin, cannot continue!");
+        continue;
+      }
+      next_dt = dt;
+      if (it->getIterations() < min_iterations) next_dt = dt * growth;
+      else if (it->getIterations() > max_iterations) next_dt = dt * cutback;
+    } else {
+      next_dt = dt * growth;
+    }
   }
   _problem->execute(EXEC_FINAL);
   if ((out_on & EXEC_FINAL) && !(out_on & EXEC_TIMESTEP_END)) writeCSVRow(false);

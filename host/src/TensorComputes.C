@@ -446,3 +446,65 @@ void FFTSemiImplicit::computeBuffer() {
   }
   _u = _domain.ifft(ubar);
 }
+
+// --------------------------------------------------------------------------- SwiftHohenbergLinear
+registerMooseObject("MarlinApp", SwiftHohenbergLinear);
+
+InputParameters SwiftHohenbergLinear::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Reciprocal space linear term in the semi-implicit time integration of the Swift-Hohenberg equation IC.");
+  params.addParam<Real>("r", -0.5, "Phase field crystal parameter r");
+  params.addParam<Real>("alpha", 1.0, "Regularization factor <=1");
+  return params;
+}
+SwiftHohenbergLinear::SwiftHohenbergLinear(const InputParameters &parameters) : TensorOperator<>(parameters) {
+  // src/tensor_computes/SwiftHohenbergLinear.C:33-36
+  _kernel.configure("r - alpha*alpha*(1 - k2)*(1 - k2)", {}, {}, {"r", "alpha"}, {getParam<Real>("r"), getParam<Real>("alpha")}, true, MRL_EXPAND_RECIPROCAL);
+}
+void SwiftHohenbergLinear::computeBuffer() { _u = _kernel.eval(_domain, {}, _time); }
+
+// ---------------------------------------------------------------------------- MooseFunctionTensor
+registerMooseObject("MarlinApp", MooseFunctionTensor);
+
+InputParameters MooseFunctionTensor::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Map a MooseFunction to a tensor.");
+  params.addRequiredParam<FunctionName>("function", "Function to map.");
+  return params;
+}
+MooseFunctionTensor::MooseFunctionTensor(const InputParameters &parameters) : TensorOperator<>(parameters), _function(getParam<FunctionName>("function")) {}
+
+// The reference samples Function::value at the points i*dx + dx/2 on the host
+// (src/tensor_computes/MooseFunctionTensor.C:31-72).  Here the ParsedFunction expression (FParser
+// grammar: `:=` bindings, if(), ^, elementary functions, pi - a subset of the Marlin grammar) is
+// compiled into a device kernel over the cell-centre axes; symbols bound to other functions are
+// evaluated first and enter as input fields.
+Tensor MooseFunctionTensor::evaluate(const std::string &function, int depth) {
+  if (depth > 16) mooseError("[Functions]: symbol_values of '", function, "' are nested too deep (cyclic?)");
+  const auto *f = _tensor_problem.getFunction(function);
+  if (!f) paramError("function", "no ParsedFunction named '", function, "' in [Functions]");
+  if (f->symbol_names.size() != f->symbol_values.size()) mooseError("[Functions/", function, "]: symbol_names and symbol_values differ in length");
+  std::vector<std::string> inputs, cnames;
+  std::vector<double> cvalues;
+  std::vector<Tensor> held;
+  for (std::size_t i = 0; i < f->symbol_names.size(); ++i) {
+    if (_tensor_problem.getFunction(f->symbol_values[i])) {
+      inputs.push_back(f->symbol_names[i]);
+      held.push_back(evaluate(f->symbol_values[i], depth + 1));
+    } else {
+      cnames.push_back(f->symbol_names[i]);
+      cvalues.push_back(shim_detail::Conv<double>::from(f->symbol_values[i], "Functions/" + function + "/symbol_values"));
+    }
+  }
+  ExprKernel k;
+  k.configure(f->expression, inputs, {}, cnames, cvalues, true, MRL_EXPAND_REAL);
+  std::vector<const Tensor *> in;
+  for (const auto &t : held) in.push_back(&t);
+  return k.eval(_domain, in, _tensor_problem.time());
+}
+
+void MooseFunctionTensor::computeBuffer() {
+  for (unsigned int d = 0; d < _dim; ++d)
+    if (_domain.getDomainMin()[d] != 0.0) mooseError("MooseFunctionTensor samples at i*dx + dx/2 (the reference ignores the domain minimum); use a domain starting at 0");
+  _u = evaluate(_function, 0);
+}

@@ -2,6 +2,7 @@
 // (+ alias SemiImplicitSolver), ETDRK4Solver.  Reference citations in include/TensorSolver.h.
 #include "TensorSolver.h"
 
+#include <cmath>
 #include <cstring>
 
 #include "TensorComputes.h"
@@ -617,6 +618,110 @@ void AdamsBashforthMoultonCoupled::substep() {
       }
       solveAndInvert(rhs);
     }
+  }
+}
+
+// ========================================================================================== SecantSolver
+registerMooseObject("MarlinApp", SecantSolver);
+
+InputParameters SecantSolver::validParams() {
+  InputParameters params = SplitOperatorBase::validParams();
+  params.addClassDescription("Implicit secant solver time integration.");
+  params.addParam<unsigned int>("substeps", 1, "secant solver substeps per time step.");
+  params.addParam<unsigned int>("max_iterations", 30, "Maximum number of secant solver iteration.");
+  params.addParam<Real>("relative_tolerance", 1e-9, "Convergence tolerance.");
+  params.addParam<Real>("absolute_tolerance", 1e-9, "Convergence tolerance.");
+  params.addParam<Real>("damping", 1.0, "Damping factor for the update step.");
+  params.addParam<Real>("dt_epsilon", 1e-4, "Semi-implicit stable timestep to bootstrap secant solve.");
+  params.addParam<bool>("verbose", false, "Show convergence history.");
+  return params;
+}
+
+SecantSolver::SecantSolver(const InputParameters &parameters)
+  : SplitOperatorBase(parameters),
+    _max_iterations(getParam<unsigned int>("max_iterations")),
+    _relative_tolerance(getParam<Real>("relative_tolerance")),
+    _absolute_tolerance(getParam<Real>("absolute_tolerance")),
+    _verbose(getParam<bool>("verbose")),
+    _damping(getParam<Real>("damping")),
+    _dt_epsilon(getParam<Real>("dt_epsilon")) {
+  getVariables(0);  // no history required
+  if (_variables.size() > 1)
+    mooseWarning("The secant solver only work well for uncoupled variables. Use the BroydenSolver for solves with multiple coupled variables.");
+  // SecantSolver.C:71-75,85-88 (bootstrap), :122-126 (residual), :129-139 (secant update); `t` is the sub step
+  const int E = MRL_EXPAND_NONE;
+  _r0[1].configure("(N + L*u)*t", {"N", "L", "u"}, {}, {}, {}, true, E);
+  _r0[0].configure("N*t", {"N"}, {}, {}, {}, true, E);
+  _start[1].configure("(u + eps*N)/(1 - eps*L)", {"N", "L", "u"}, {}, {"eps"}, {_dt_epsilon}, false, E);
+  _start[0].configure("u + eps*N", {"N", "u"}, {}, {"eps"}, {_dt_epsilon}, false, E);
+  _res[1].configure("(N + L*u)*t + uold - u", {"N", "L", "u", "uold"}, {}, {}, {}, true, E);
+  _res[0].configure("N*t + uold - u", {"N", "u", "uold"}, {}, {}, {}, true, E);
+  _update.configure(_damping == 1.0 ? "dy := R - Rp; u + if(dy != 0, -R*(u - up)/dy, 0)" : "dy := R - Rp; u + if(dy != 0, -R*(u - up)/dy, 0)*damping",
+                    {"u", "up", "R", "Rp"}, {}, {"damping"}, {_damping}, false, E);
+}
+
+// torch::norm of a complex tensor: sqrt(sum |z|^2)
+Real SecantSolver::complexNorm(const Tensor &t) const {
+  double s = 0;
+  checkC(mrl_reduce(_domain.context(), MRL_SUMSQ, t.data_ptr(), t.numel() * (t.is_complex() ? 2 : 1), &s), "mrl_reduce");
+  return std::sqrt(s);
+}
+
+void SecantSolver::substep() {
+  const auto n = _variables.size();
+  std::vector<Tensor> u_old(n), Rprev(n), uprev(n);
+  std::vector<Real> R0norm(n);
+  if (_verbose) std::cerr << "Substep " << _substep << "\n";
+
+  // initial guess computed using semi-implicit Euler
+  _compute->computeBuffer();
+  forwardBuffers();
+  for (std::size_t i = 0; i < n; ++i) {
+    auto &v = _variables[i];
+    const Tensor &u = v._reciprocal_buffer, &N = v._nonlinear_reciprocal;
+    const Tensor *L = v._linear_reciprocal;
+    Rprev[i] = L ? _r0[1].eval(_domain, {&N, L, &u}, _sub_dt) : _r0[0].eval(_domain, {&N}, _sub_dt);
+    uprev[i] = u;
+    R0norm[i] = complexNorm(Rprev[i]);
+    u_old[i] = u;
+    v._buffer = _domain.ifft(L ? _start[1].eval(_domain, {&N, L, &u}, 0.0) : _start[0].eval(_domain, {&N, &u}, 0.0));
+    if (_verbose) std::cerr << "|R0|=" << R0norm[i] << std::endl;
+  }
+
+  bool all_converged = false;
+  for (_iterations = 0; _iterations < _max_iterations; ++_iterations) {
+    _compute->computeBuffer();
+    forwardBuffers();
+    all_converged = true;
+    for (std::size_t i = 0; i < n; ++i) {
+      auto &v = _variables[i];
+      const Tensor u = v._reciprocal_buffer;  // keep this state alive: it becomes uprev
+      const Tensor &N = v._nonlinear_reciprocal;
+      const Tensor *L = v._linear_reciprocal;
+      Tensor R = L ? _res[1].eval(_domain, {&N, L, &u, &u_old[i]}, _sub_dt) : _res[0].eval(_domain, {&N, &u, &u_old[i]}, _sub_dt);
+      Tensor unew = _update.eval(_domain, {&u, &uprev[i], &R, &Rprev[i]}, 0.0);
+      uprev[i] = u;
+      Rprev[i] = R;
+      v._buffer = _domain.ifft(unew);
+      const Real Rnorm = complexNorm(R);
+      if (_verbose) std::cerr << _iterations << " |R|=" << Rnorm << std::endl;
+      if (std::isnan(Rnorm)) {
+        all_converged = false;
+        _iterations = _max_iterations;
+        std::cerr << "NaN detected, aborting solve.\n";
+        break;
+      }
+      all_converged = all_converged && (Rnorm < _absolute_tolerance || Rnorm / R0norm[i] < _relative_tolerance);
+    }
+    if (all_converged) {
+      _is_converged = true;
+      break;
+    }
+  }
+  if (!all_converged) {
+    std::cerr << "Solve not converged.\n";
+    for (std::size_t i = 0; i < n; ++i) _variables[i]._buffer = _domain.ifft(u_old[i]);
+    _is_converged = false;
   }
 }
 

@@ -511,6 +511,119 @@ class AdamsBashforthMoultonCoupled(SplitOperatorSolver):
                     b[v["u"]] = self.d.ifft(ubar)
 
 
+class SwiftHohenbergLinear(Op):
+    """src/tensor_computes/SwiftHohenbergLinear.C:33-36: r - alpha^2 (1 - k^2)^2 (real, reciprocal shape)."""
+
+    def __init__(self, problem, buffer, r=-0.5, alpha=1.0):
+        super().__init__(problem, buffer)
+        self.r, self.alpha = r, alpha
+
+    def compute(self):
+        k2 = self.d.k2
+        self.set(self.r - self.alpha * self.alpha * (1.0 - k2) * (1.0 - k2))
+
+
+class MooseFunctionTensor(Op):
+    """src/tensor_computes/MooseFunctionTensor.C:31-72: a MOOSE Function sampled at the cell centres
+    i*dx + dx/2 (note: not the linspace axis of DomainAction).  `functions` maps a ParsedFunction
+    name to (expression, symbol_names, symbol_values); symbol values are other functions (evaluated
+    at the same points, as MOOSE's ParsedFunction does) or numbers.  The FParser grammar of these
+    expressions (`:=` bindings, `if`, `^`, sin/cos, pi) is a subset of the Marlin grammar, so the
+    oracle's expression evaluator is reused."""
+
+    def __init__(self, problem, buffer, function, functions):
+        super().__init__(problem, buffer)
+        self.function, self.functions = function, functions
+
+    def _eval(self, name, pts):
+        expr, names, values = self.functions[name]
+        consts = {"pi": torch.tensor(math.pi, dtype=torch.float64), "e": torch.tensor(math.e, dtype=torch.float64)}
+        variables, params = ["x", "y", "z", "t"], list(pts) + [torch.tensor(self.p.time, dtype=torch.float64)]
+        for n, v in zip(names, values):
+            variables.append(n)
+            params.append(self._eval(v, pts) if v in self.functions else torch.tensor(float(v), dtype=torch.float64))
+        fn = xp.ParsedTensor(expr, variables, consts)
+        fn.compile()
+        return fn.eval(params)
+
+    def compute(self):
+        d = self.d
+        pts = []
+        for a in range(3):
+            if a < d.dim:
+                n, dx = d.n[a], d.dx[a]
+                c = torch.arange(n, dtype=torch.float64) * dx + dx / 2.0
+                shape = [1] * d.dim
+                shape[a] = n
+                pts.append(c.reshape(shape))
+            else:
+                pts.append(torch.tensor(0.0, dtype=torch.float64))
+        self.set(self._eval(self.function, pts).expand(d.shape).contiguous().to(d.dtype))
+
+
+class SecantSolver(SplitOperatorSolver):
+    """src/tensor_solver/SecantSolver.C:32-185: implicit Euler solved per wavevector with a secant
+    iteration on the reciprocal-space residual R = (N + L u) dt + u_old - u, bootstrapped by one
+    semi-implicit step of size dt_epsilon.  `iterations`/`converged` are what
+    TensorSolveIterationAdaptiveDT reads (IterativeTensorSolverInterface)."""
+
+    def __init__(self, problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                 nonlinear_reciprocal, substeps=1, max_iterations=30, relative_tolerance=1e-9,
+                 absolute_tolerance=1e-9, damping=1.0, dt_epsilon=1e-4, forward=()):
+        super().__init__(problem, root, buffer, reciprocal_buffer, linear_reciprocal,
+                         nonlinear_reciprocal, substeps, 0, forward)
+        self.max_iterations, self.rtol, self.atol = max_iterations, relative_tolerance, absolute_tolerance
+        self.damping, self.dt_epsilon = damping, dt_epsilon
+        self.iterations, self.converged = 0, True
+
+    def substep(self):
+        p, b, d = self.p, self.p.buf, self.d
+        dt = p.sub_dt
+        n = len(self.vars)
+        u_old, Rprev, uprev, R0 = [None] * n, [None] * n, [None] * n, [0.0] * n
+        self.root.compute()
+        self.forward_buffers()
+        for i, v in enumerate(self.vars):
+            u, N = b[v["ubar"]], b[v["N"]]
+            L = b[v["L"]] if v["L"] is not None else None
+            Rprev[i] = (N + L * u) * dt if L is not None else N * dt
+            uprev[i] = u
+            R0[i] = float(torch.linalg.norm(Rprev[i]))
+            u_old[i] = u
+            eps = self.dt_epsilon
+            b[v["u"]] = d.ifft((u + eps * N) / (1.0 - eps * L)) if L is not None else d.ifft(u + eps * N)
+        all_converged = False
+        it = 0
+        while it < self.max_iterations:
+            self.root.compute()
+            self.forward_buffers()
+            all_converged = True
+            for i, v in enumerate(self.vars):
+                u, N = b[v["ubar"]], b[v["N"]]
+                L = b[v["L"]] if v["L"] is not None else None
+                R = ((N + L * u) * dt if L is not None else N * dt) + u_old[i] - u
+                dx = u - uprev[i]
+                dy = R - Rprev[i]
+                du = torch.where(dy != 0, -R * dx / dy, torch.zeros((), dtype=R.dtype))
+                uprev[i], Rprev[i] = u, R
+                b[v["u"]] = d.ifft(u + du) if self.damping == 1.0 else d.ifft(u + du * self.damping)
+                Rnorm = float(torch.linalg.norm(R))
+                if math.isnan(Rnorm):
+                    all_converged = False
+                    it = self.max_iterations
+                    break
+                all_converged = all_converged and (Rnorm < self.atol or Rnorm / R0[i] < self.rtol)
+            if all_converged:
+                self.converged = True
+                break
+            it += 1
+        self.iterations = it
+        if not all_converged:
+            for i, v in enumerate(self.vars):
+                b[v["u"]] = d.ifft(u_old[i])
+            self.converged = False
+
+
 class ForwardEulerSolver(TensorSolver):
     """src/tensor_solver/ForwardEulerSolver.C:29-38 (variables may be empty: mechanics)."""
 

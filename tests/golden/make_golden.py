@@ -143,8 +143,18 @@ def mech2d():
     print("mech2d_h5", F.shape)
 
 
+def rotating_grain():
+    """test/tests/tensor_compute/gold/rotating_grain_secant.h5: psi (40^2, CELL, transpose = false) at
+    the initial condition and after each of the 10 steps."""
+    streams = zlib_streams(f"{REF}/test/tests/tensor_compute/gold/rotating_grain_secant.h5")
+    psi = np.stack([np.frombuffer(s, dtype="<f8").reshape(40, 40) for s in streams])
+    np.savez_compressed(f"{OUT}/rotating_grain_secant_h5.npz", psi=psi)
+    print("rotating_grain_secant_h5", psi.shape)
+
+
 if __name__ == "__main__":
     exodus_ch2d()
     solver_csvs()
     mech3d()
     mech2d()
+    rotating_grain()

@@ -117,3 +117,48 @@ def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e
     p.solver = om.ForwardEulerSolver(p, root, substeps=substeps, forward=[("F", "Fnew")])
     p.mech = mech
     return p
+
+
+CRYSTAL = ("-(sin(sin(a)*y/2+cos(a)*x/2)^2 + sin(sin(a+1/3*pi)*y/2+cos(a+1/3*pi)*x/2)^2 + "
+           "sin(sin(a-1/3*pi)*y/2+cos(a-1/3*pi)*x/2)^2 - 1.5)*0.25")
+
+
+def rotating_grain_problem(n=40, w=6, substeps=3):
+    """test/tests/tensor_compute/rotating_grain_secant.i: Swift-Hohenberg (phase-field crystal) rotated
+    grain in a matrix, SecantSolver, TensorSolveIterationAdaptiveDT (see rotating_grain_run)."""
+    d = om.Domain(2, [n, n], (0, 0, 0), (w * math.pi * 2, w * math.pi * 2 / math.sin(math.pi / 3), 1.0))
+    p = om.Problem(d)
+    functions = {
+        "grain1": ("a := 0; " + CRYSTAL, [], []),
+        "grain2": ("a := 0.95; " + CRYSTAL, [], []),
+        "domain": (f"r := (x-{w}*pi)^2+(y-{w}*pi)^2; if(r<({w}*2/3*pi)^2, grain2, grain1)",
+                   ["grain1", "grain2"], ["grain1", "grain2"]),
+    }
+    p.ics = [om.MooseFunctionTensor(p, "psi", "domain", functions),
+             om.SwiftHohenbergLinear(p, "linear", r=0.025, alpha=1.0)]
+    root = om.Group(p, [om.ParsedCompute(p, "psi3", "0.20*psi^2-psi^3", inputs=["psi"]),
+                        om.ForwardFFT(p, "psibar", "psi"),
+                        om.ForwardFFT(p, "psi3bar", "psi3")])
+    p.solver = om.SecantSolver(p, root, ["psi"], ["psibar"], ["linear"], ["psi3bar"], substeps=substeps)
+    return p
+
+
+def rotating_grain_run(p, num_steps=10, dt=1.0, min_iterations=100, max_iterations=400, growth_factor=1.4,
+                       cutback_factor=0.9, dtmax=500.0, on_step=None):
+    """Transient + TensorSolveIterationAdaptiveDT (src/timesteppers/TensorSolveIterationAdaptiveDT.C:
+    computeInitialDT :71-75, computeDT/computeAdaptiveDT :77-93,161-174): the next dt grows when the
+    solver's last substep took fewer than min_iterations secant iterations, shrinks above
+    max_iterations.  (A failed solve would repeat the step with half the dt; the gold run never fails.)"""
+    p.initial()
+    for step in range(num_steps):
+        if step > 0:
+            it = p.solver.iterations
+            if it < min_iterations:
+                dt *= growth_factor
+            elif it > max_iterations:
+                dt *= cutback_factor
+        dt = min(dt, dtmax)
+        p.step(dt)
+        assert p.solver.converged, "secant solve failed: step repetition is not restated"
+        if on_step:
+            on_step(step, dt)

@@ -161,6 +161,19 @@ def test_mech2d_input_matches_hdf5_gold(tmp_path):
         assert np.linalg.norm(F - ref) / np.linalg.norm(ref) < 1e-9
 
 
+def test_swift_hohenberg_secant_input_matches_hdf5_gold(tmp_path):
+    """test/tests/tensor_compute/rotating_grain_secant.i -> gold/rotating_grain_secant.h5 (abs_tol 1e-10
+    in the reference's HDF5Diff): [Functions]/MooseFunctionTensor IC, SwiftHohenbergLinear, SecantSolver,
+    TensorSolveIterationAdaptiveDT."""
+    g = np.load(f"{G}/rotating_grain_secant_h5.npz")["psi"]
+    run(tmp_path, "swift_hohenberg_secant.i", "Executioner/num_steps=0", dump=("psi",))
+    assert np.abs(field(tmp_path, "psi", (40, 40)) - g[0]).max() < 1e-13
+    for k in (1, 4, 10):
+        r = run(tmp_path, "swift_hohenberg_secant.i", f"Executioner/num_steps={k}", dump=("psi",))
+        assert np.abs(field(tmp_path, "psi", (40, 40)) - g[k]).max() < 1e-10, k
+    assert f"dt = {1.4 ** 9:.8g}"[:12] in r.stderr            # the step grew by growth_factor every step
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

@@ -105,6 +105,26 @@ def test_mech2d_matches_hdf5_gold():
         assert rel < 1e-12, (fr, rel)
 
 
+def test_rotating_grain_secant_matches_hdf5_gold():
+    """test/tests/tensor_compute/rotating_grain_secant.i (MooseFunctionTensor IC, SwiftHohenbergLinear,
+    SecantSolver, TensorSolveIterationAdaptiveDT) vs gold/rotating_grain_secant.h5 (HDF5Diff abs_tol
+    1e-10): psi at the initial condition and after each of the 10 steps."""
+    g = np.load(f"{G}/rotating_grain_secant_h5.npz")["psi"]
+    p = oc.rotating_grain_problem()
+    errs, dts = [], []
+
+    def on_step(step, dt):
+        errs.append(np.abs(p.buf["psi"].numpy() - g[step + 1]).max())
+        dts.append(dt)
+
+    oc.rotating_grain_run(p, on_step=on_step)
+    assert len(errs) == 10 and max(errs) < 1e-10, errs
+    assert abs(dts[-1] - 1.4 ** 9) < 1e-12          # < min_iterations secant iterations: dt grows every step
+    p2 = oc.rotating_grain_problem()
+    p2.initial()
+    assert np.abs(p2.buf["psi"].numpy() - g[0]).max() < 1e-14
+
+
 def test_fft_roundtrip_even_odd():
     """test/tests/tensor_compute/backandforth.i: fft->ifft is the identity for the even/odd
     1-3-D sizes used there (gold difference exactly 0 at CSV precision)."""
