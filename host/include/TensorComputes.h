@@ -163,4 +163,32 @@ public:
 protected:
   marlin::Tensor evaluate(const std::string &function, int depth);
   const std::string _function;
+  std::vector<marlin::Tensor> _coords;
+};
+
+// src/tensor_computes/ReciprocalMatDiffusion.C: i k . fft(M grad mu) + fft(grad(psi)/psi . J)
+class ReciprocalMatDiffusion : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit ReciprocalMatDiffusion(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const marlin::Tensor &_chem_pot, &_M, &_psi;
+  bool _update_psi = true;
+  const bool _always_update_psi;
+  marlin::Tensor _grad_psi_by_psi[3];
+  ExprKernel _grad[3], _by_psi, _flux, _dot[3], _div[3];
+};
+
+// src/tensor_computes/ReciprocalAllenCahn.C: fft(where(psi > 0, -L dF/deta, 0))
+class ReciprocalAllenCahn : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit ReciprocalAllenCahn(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const marlin::Tensor &_dF_chem_deta, &_L, &_psi;
+  ExprKernel _rate;
 };

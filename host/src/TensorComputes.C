@@ -484,8 +484,18 @@ Tensor MooseFunctionTensor::evaluate(const std::string &function, int depth) {
   const auto *f = _tensor_problem.getFunction(function);
   if (!f) paramError("function", "no ParsedFunction named '", function, "' in [Functions]");
   if (f->symbol_names.size() != f->symbol_values.size()) mooseError("[Functions/", function, "]: symbol_names and symbol_values differ in length");
-  std::vector<std::string> inputs, cnames;
-  std::vector<double> cvalues;
+  // sample points i*dx + dx/2: the cell-centre axes shifted by the domain minimum (the reference
+  // ignores the minimum, MooseFunctionTensor.C:45-66), materialised as coordinate fields
+  if (_coords.empty()) {
+    static const char *axis[3] = {"x", "y", "z"};
+    for (unsigned int d = 0; d < 3; ++d) {
+      ExprKernel k;
+      k.configure(std::string(axis[d]) + " - shift", {}, {}, {"shift"}, {d < _dim ? _domain.getDomainMin()[d] : 0.0}, true, MRL_EXPAND_REAL);
+      _coords.push_back(k.eval(_domain, {}, 0.0));
+    }
+  }
+  std::vector<std::string> inputs = {"x", "y", "z"}, cnames = {"pi", "e", "t"};
+  std::vector<double> cvalues = {M_PI, M_E, _tensor_problem.time()};
   std::vector<Tensor> held;
   for (std::size_t i = 0; i < f->symbol_names.size(); ++i) {
     if (_tensor_problem.getFunction(f->symbol_values[i])) {
@@ -497,14 +507,95 @@ Tensor MooseFunctionTensor::evaluate(const std::string &function, int depth) {
     }
   }
   ExprKernel k;
-  k.configure(f->expression, inputs, {}, cnames, cvalues, true, MRL_EXPAND_REAL);
-  std::vector<const Tensor *> in;
+  k.configure(f->expression, inputs, {}, cnames, cvalues, false, MRL_EXPAND_REAL);
+  std::vector<const Tensor *> in = {&_coords[0], &_coords[1], &_coords[2]};
   for (const auto &t : held) in.push_back(&t);
-  return k.eval(_domain, in, _tensor_problem.time());
+  return k.eval(_domain, in, 0.0);
 }
 
 void MooseFunctionTensor::computeBuffer() {
-  for (unsigned int d = 0; d < _dim; ++d)
-    if (_domain.getDomainMin()[d] != 0.0) mooseError("MooseFunctionTensor samples at i*dx + dx/2 (the reference ignores the domain minimum); use a domain starting at 0");
   _u = evaluate(_function, 0);
+  _coords.clear();
 }
+
+// -------------------------------------------------------------------------- ReciprocalMatDiffusion
+registerMooseObject("MarlinApp", ReciprocalMatDiffusion);
+
+InputParameters ReciprocalMatDiffusion::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Calculates the divergence of flux for a variable mobility in reciprocal space.");
+  params.addRequiredParam<TensorInputBufferName>("chemical_potential", "Chemical potential buffer name");
+  params.addRequiredParam<TensorInputBufferName>("mobility", "Mobility buffer name");
+  params.addParam<TensorInputBufferName>("psi", "Variable to impose Neuamnn BC.");
+  params.addParam<bool>("always_update_psi", false, "Set to true if the BC changes .");
+  return params;
+}
+
+ReciprocalMatDiffusion::ReciprocalMatDiffusion(const InputParameters &parameters)
+  : TensorOperator<>(parameters),
+    _chem_pot(getInputBuffer("chemical_potential")),
+    _M(getInputBuffer("mobility")),
+    _psi(getInputBuffer("psi")),
+    _always_update_psi(getParam<bool>("always_update_psi")) {
+  // src/tensor_computes/ReciprocalMatDiffusion.C:43-66, each line one generated kernel
+  for (int d = 0; d < 3; ++d) _grad[d].configure(std::string("ubar*") + kAxisName[d] + "*i", {"ubar"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+  _by_psi.configure("if(psi > 0, g/psi, 0)", {"psi", "g"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  _flux.configure("if(psi > 0, M, 0)*g", {"M", "psi", "g"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  _dot[0].configure("gx*Jx", {"gx", "Jx"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  _dot[1].configure("gx*Jx + gy*Jy", {"gx", "Jx", "gy", "Jy"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  _dot[2].configure("gx*Jx + gy*Jy + gz*Jz", {"gx", "Jx", "gy", "Jy", "gz", "Jz"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  _div[0].configure("i*(kx*Jx) + nf", {"Jx", "nf"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+  _div[1].configure("i*(kx*Jx + ky*Jy) + nf", {"Jx", "Jy", "nf"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+  _div[2].configure("i*(kx*Jx + ky*Jy + kz*Jz) + nf", {"Jx", "Jy", "Jz", "nf"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+}
+
+void ReciprocalMatDiffusion::computeBuffer() {
+  const unsigned int D = _dim;  // the components along unused dimensions vanish (their k axis is {0})
+  if (_update_psi || _always_update_psi) {
+    const Tensor psibar = _domain.fft(_psi);
+    for (unsigned int d = 0; d < D; ++d) {
+      const Tensor g = _domain.ifft(_grad[d].eval(_domain, {&psibar}, _time));
+      _grad_psi_by_psi[d] = _by_psi.eval(_domain, {&_psi, &g}, _time);
+    }
+    _update_psi = false;
+  }
+  const Tensor mubar = _domain.fft(_chem_pot);
+  Tensor J[3], Jbar[3];
+  for (unsigned int d = 0; d < D; ++d) {
+    const Tensor g = _domain.ifft(_grad[d].eval(_domain, {&mubar}, _time));
+    J[d] = _flux.eval(_domain, {&_M, &_psi, &g}, _time);
+    Jbar[d] = _domain.fft(J[d]);
+  }
+  std::vector<const Tensor *> in;
+  for (unsigned int d = 0; d < D; ++d) {
+    in.push_back(&_grad_psi_by_psi[d]);
+    in.push_back(&J[d]);
+  }
+  const Tensor nf = _domain.fft(_dot[D - 1].eval(_domain, in, _time));
+  in.clear();
+  for (unsigned int d = 0; d < D; ++d) in.push_back(&Jbar[d]);
+  in.push_back(&nf);
+  _u = _div[D - 1].eval(_domain, in, _time);
+}
+
+// ----------------------------------------------------------------------------- ReciprocalAllenCahn
+registerMooseObject("MarlinApp", ReciprocalAllenCahn);
+
+InputParameters ReciprocalAllenCahn::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Calculates the Allen-Cahn bulk driving force masked using psi.");
+  params.addRequiredParam<TensorInputBufferName>("dF_chem_deta", "Driving force buffer name");
+  params.addRequiredParam<TensorInputBufferName>("L", "Allen-Cahn mobility buffer name");
+  params.addRequiredParam<TensorInputBufferName>("psi", "Variable to impose Neumann BC.");
+  params.addParam<bool>("always_update_psi", false, "Set to true if the BC changes .");
+  return params;
+}
+
+ReciprocalAllenCahn::ReciprocalAllenCahn(const InputParameters &parameters)
+  : TensorOperator<>(parameters), _dF_chem_deta(getInputBuffer("dF_chem_deta")), _L(getInputBuffer("L")), _psi(getInputBuffer("psi")) {
+  // src/tensor_computes/ReciprocalAllenCahn.C:39-50 (psi itself is re-read every time: same values
+  // as the cached threshold unless always_update_psi semantics are needed, which re-reading covers)
+  _rate.configure("if(psi > 0, -1*L*dF, 0)", {"psi", "L", "dF"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+}
+
+void ReciprocalAllenCahn::computeBuffer() { _u = _domain.fft(_rate.eval(_domain, {&_psi, &_L, &_dF_chem_deta}, _time)); }

@@ -511,6 +511,49 @@ class AdamsBashforthMoultonCoupled(SplitOperatorSolver):
                     b[v["u"]] = self.d.ifft(ubar)
 
 
+class ReciprocalMatDiffusion(Op):
+    """src/tensor_computes/ReciprocalMatDiffusion.C:43-66: divergence of the flux -M grad(mu) for a
+    spatially varying mobility, with the smoothed-boundary no-flux term grad(psi)/psi . J; psi and its
+    gradients are captured at the first evaluation (always_update_psi = false)."""
+
+    def __init__(self, problem, buffer, chemical_potential, mobility, psi, always_update_psi=False):
+        super().__init__(problem, buffer)
+        self.mu, self.M, self.psi, self.always = chemical_potential, mobility, psi, always_update_psi
+        self.cache = None
+
+    def compute(self):
+        d = self.d
+        k = [d.kaxis[a] for a in range(3)]
+        i = torch.tensor(1j, dtype=torch.complex128)
+        if self.cache is None or self.always:
+            psi = self.get(self.psi)
+            thresh = psi > 0.0
+            g = [torch.where(thresh, d.ifft(k[a] * d.fft(psi) * i) / psi, 0.0) for a in range(3)]
+            self.cache = (thresh, g)
+        thresh, g = self.cache
+        psi_M = self.get(self.M) * thresh
+        mu = self.get(self.mu)
+        J = [psi_M * d.ifft(k[a] * d.fft(mu) * i) for a in range(3)]
+        div_J_hat = i * (k[0] * d.fft(J[0]) + k[1] * d.fft(J[1]) + k[2] * d.fft(J[2]))
+        no_flux_hat = d.fft(g[0] * J[0] + g[1] * J[1] + g[2] * J[2])
+        self.set(div_J_hat + no_flux_hat)
+
+
+class ReciprocalAllenCahn(Op):
+    """src/tensor_computes/ReciprocalAllenCahn.C:39-50: fft(where(psi > 0, -L dF/deta, 0))."""
+
+    def __init__(self, problem, buffer, dF_chem_deta, L, psi, always_update_psi=False):
+        super().__init__(problem, buffer)
+        self.dF, self.L, self.psi, self.always = dF_chem_deta, L, psi, always_update_psi
+        self.thresh = None
+
+    def compute(self):
+        if self.thresh is None or self.always:
+            self.thresh = self.get(self.psi) > 0.0
+        rate = torch.where(self.thresh, -1 * self.get(self.L) * self.get(self.dF), 0.0)
+        self.set(self.d.fft(rate))
+
+
 class SwiftHohenbergLinear(Op):
     """src/tensor_computes/SwiftHohenbergLinear.C:33-36: r - alpha^2 (1 - k^2)^2 (real, reciprocal shape)."""
 

@@ -152,9 +152,29 @@ def rotating_grain():
     print("rotating_grain_secant_h5", psi.shape)
 
 
+def kks_no_flux():
+    """test/tests/kks/gold/KKS_no_flux_bc.h5 (20^2, transpose = false; per frame c, eta, mu, psi in
+    std::map key order) and KKS_no_flux_bc_out.csv."""
+    streams = zlib_streams(f"{REF}/test/tests/kks/gold/KKS_no_flux_bc.h5")
+    a = np.stack([np.frombuffer(s, dtype="<f8").reshape(20, 20) for s in streams])
+    # file order of the chunks: frame 0 (c, eta, mu, psi), the ten later copies of the static psi, then
+    # (c, eta, mu) of steps 1..10
+    assert a.shape[0] == 44 and all(np.array_equal(a[3], a[j]) for j in range(4, 14))
+    frames = np.zeros((11, 4, 20, 20))
+    frames[0] = a[0:4]
+    for k in range(1, 11):
+        frames[k, 0:3] = a[14 + 3 * (k - 1):17 + 3 * (k - 1)]
+        frames[k, 3] = a[3]
+    a = frames
+    h, csv = read_csv(f"{REF}/test/tests/kks/gold/KKS_no_flux_bc_out.csv")
+    np.savez_compressed(f"{OUT}/kks_no_flux_bc.npz", c=a[:, 0], eta=a[:, 1], mu=a[:, 2], psi=a[:, 3], csv=csv, csv_header=np.array(h))
+    print("kks_no_flux_bc", a.shape, csv.shape)
+
+
 if __name__ == "__main__":
     exodus_ch2d()
     solver_csvs()
     mech3d()
     mech2d()
     rotating_grain()
+    kks_no_flux()

@@ -162,3 +162,37 @@ def rotating_grain_run(p, num_steps=10, dt=1.0, min_iterations=100, max_iteratio
         assert p.solver.converged, "secant solve failed: step repetition is not restated"
         if on_step:
             on_step(step, dt)
+
+
+def kks_no_flux_problem(n=20, substeps=1000):
+    """test/tests/kks/KKS_no_flux_bc.i: two-phase KKS-type model (c conserved through ReciprocalMatDiffusion,
+    eta through ReciprocalAllenCahn) inside a smoothed-boundary mask psi, AdamsBashforthMoulton order 3."""
+    r, l = 30, 4.2
+    kappa_eta, rho_sq, w, M, L, c0_a, c0_b = 5, 2, 1, 5, 5, 0.3, 0.7
+    eta_ic = f"0.5*(1-tanh(2*(sqrt(x^2+y^2)-{r})/{l}))"
+    h = "eta^3*(6*eta^2-15*eta+10)"
+    F = (f"{h}*({rho_sq}*((c - (1-{h})*({c0_b} - {c0_a}))-{c0_a})^2) + (1-{h})*({rho_sq}*((c + ({h})*({c0_b} - {c0_a}))-{c0_b})^2 ) "
+         f"+ {w}*(eta^2)*(1-eta)^2")
+    d = om.Domain(2, [n, n], (-50, -50, 0), (50, 50, 1.0))
+    p = om.Problem(d)
+    psi_expr = (f"if(x<x_min-{l},0,if(x>x_min+{l},1,0.5-0.5*cos(pi*(x-(x_min-{l}))/2/{l}) )) * "
+                f"if(x<x_max-{l},1,if(x>x_max+{l},0,0.5+0.5*cos(pi*(x-(x_max-{l}))/2/{l}) ))")
+    functions = {"psi_func": (psi_expr, ["x_min", "x_max", "y_min", "y_max"], ["30", "70", "0", "100"])}
+    p.ics = [om.ParsedCompute(p, "c", f"0.6 + ({c0_a}-0.6)*{eta_ic}", extra_symbols=True),
+             om.ParsedCompute(p, "eta", eta_ic, extra_symbols=True),
+             om.MooseFunctionTensor(p, "psi", "psi_func", functions),
+             om.ConstantTensor(p, "zero", 0.0, reciprocal=True),
+             om.ConstantTensor(p, "M", float(M)), om.ConstantTensor(p, "L", float(L)),
+             om.ConstantTensor(p, "L_kappa", float(L * kappa_eta))]
+    root = om.Group(p, [
+        om.ForwardFFT(p, "cbar", "c"), om.ForwardFFT(p, "etabar", "eta"),
+        om.ParsedCompute(p, "mu", F, inputs=["c", "eta"], derivatives=["c"]),
+        om.ReciprocalMatDiffusion(p, "div_J", "mu", "M", "psi"),
+        om.ParsedCompute(p, "domega_chem_deta", f"{F} - mu*c", inputs=["mu", "c", "eta"], derivatives=["eta"]),
+        om.ReciprocalAllenCahn(p, "AC_bulk", "domega_chem_deta", "L", "psi"),
+        om.ReciprocalMatDiffusion(p, "kappa_grad_eta", "eta", "L_kappa", "psi"),
+        om.ParsedCompute(p, "AC_bar", "kappa_grad_eta + AC_bulk", inputs=["AC_bulk", "kappa_grad_eta"]),
+    ])
+    p.solver = om.AdamsBashforthMoulton(p, root, ["c", "eta"], ["cbar", "etabar"], ["zero", "zero"], ["div_J", "AC_bar"],
+                                        substeps=substeps, predictor_order=3)
+    return p

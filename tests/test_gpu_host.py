@@ -174,6 +174,25 @@ def test_swift_hohenberg_secant_input_matches_hdf5_gold(tmp_path):
     assert f"dt = {1.4 ** 9:.8g}"[:12] in r.stderr            # the step grew by growth_factor every step
 
 
+def test_kks_no_flux_input_matches_gold(tmp_path):
+    """test/tests/kks/KKS_no_flux_bc.i -> gold KKS_no_flux_bc.h5 (abs_tol 1e-10) and KKS_no_flux_bc_out.csv:
+    ReciprocalMatDiffusion, ReciprocalAllenCahn, mask from a ParsedFunction on a domain with a non-zero
+    minimum, two coupled variables, AB3, 10 x 1000 substeps."""
+    g = np.load(f"{G}/kks_no_flux_bc.npz")
+    run(tmp_path, "kks_no_flux.i", "Executioner/num_steps=0", dump=("c", "eta", "psi"))
+    for k in ("c", "eta", "psi"):
+        assert np.abs(field(tmp_path, k, (20, 20)) - g[k][0]).max() < 1e-13, k
+    run(tmp_path, "kks_no_flux.i", "Executioner/num_steps=1", dump=("c", "eta", "mu"))
+    for k in ("c", "eta", "mu"):
+        assert np.abs(field(tmp_path, k, (20, 20)) - g[k][1]).max() < 1e-10, k
+    run(tmp_path, "kks_no_flux.i", dump=("c", "eta", "mu"))
+    for k in ("c", "eta", "mu"):
+        assert np.abs(field(tmp_path, k, (20, 20)) - g[k][10]).max() < 1e-9, k
+    head, rows = csv(f"{tmp_path}/kks_no_flux_out.csv")
+    assert head == ["time", "total_C", "total_eta"] and rows.shape == g["csv"].shape
+    assert (np.abs(rows - g["csv"]) / np.maximum(np.abs(g["csv"]), 1.0)).max() < 1e-9
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

@@ -125,6 +125,23 @@ def test_rotating_grain_secant_matches_hdf5_gold():
     assert np.abs(p2.buf["psi"].numpy() - g[0]).max() < 1e-14
 
 
+def test_kks_no_flux_matches_gold():
+    """test/tests/kks/KKS_no_flux_bc.i (ReciprocalMatDiffusion, ReciprocalAllenCahn, smoothed-boundary
+    mask from a ParsedFunction, AB3, 1000 substeps per step) vs gold KKS_no_flux_bc.h5 (abs_tol 1e-10)
+    and KKS_no_flux_bc_out.csv; three of the ten steps to bound the CPU time."""
+    g = np.load(f"{G}/kks_no_flux_bc.npz")
+    p = oc.kks_no_flux_problem()
+    p.initial()
+    for k in ("c", "eta", "psi"):
+        assert np.abs(p.buf[k].numpy() - g[k][0]).max() < 1e-14
+    for step in range(1, 4):
+        p.step(0.1)
+        for k in ("c", "eta", "mu"):
+            assert np.abs(p.buf[k].numpy() - g[k][step]).max() < 1e-10, (step, k)
+        row = g["csv"][step]
+        assert abs(om.pp_integral(p, "c") - row[1]) < 1e-9 * row[1] and abs(om.pp_integral(p, "eta") - row[2]) < 1e-9 * row[2]
+
+
 def test_fft_roundtrip_even_odd():
     """test/tests/tensor_compute/backandforth.i: fft->ifft is the identity for the even/odd
     1-3-D sizes used there (gold difference exactly 0 at CSV precision)."""
