@@ -192,3 +192,16 @@ protected:
   const marlin::Tensor &_dF_chem_deta, &_L, &_psi;
   ExprKernel _rate;
 };
+
+// src/tensor_computes/DeAliasingTensor.C: 2/3-rule (SHARP) or Hou-Li exponential de-aliasing filter
+class DeAliasingTensor : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit DeAliasingTensor(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const bool _houli;
+  const Real _p, _alpha;
+  ExprKernel _kernel;
+};

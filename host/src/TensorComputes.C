@@ -599,3 +599,32 @@ ReciprocalAllenCahn::ReciprocalAllenCahn(const InputParameters &parameters)
 }
 
 void ReciprocalAllenCahn::computeBuffer() { _u = _domain.fft(_rate.eval(_domain, {&_psi, &_L, &_dF_chem_deta}, _time)); }
+
+// -------------------------------------------------------------------------------- DeAliasingTensor
+registerMooseObject("MarlinApp", DeAliasingTensor);
+
+InputParameters DeAliasingTensor::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Create a de-aliasing filter.");
+  params.addRequiredParam<MooseEnum>("method", MooseEnum("SHARP HOULI"), "Prefactor");
+  params.addParam<Real>("p", 16, "Hou-Li filter exponent");
+  params.addParam<Real>("alpha", 36, "Hou-Li filter pre-factor");
+  return params;
+}
+DeAliasingTensor::DeAliasingTensor(const InputParameters &parameters)
+  : TensorOperator<>(parameters), _houli(getParam<MooseEnum>("method") == "HOULI"), _p(getParam<Real>("p")), _alpha(getParam<Real>("alpha")) {}
+
+// src/tensor_computes/DeAliasingTensor.C:37-62; the maximum frequencies come from the host copies of
+// the reciprocal axes (unused dimensions: the one-element axis {0})
+void DeAliasingTensor::computeBuffer() {
+  double kmax[3] = {0, 0, 0};
+  for (unsigned int d = 0; d < _dim; ++d)
+    for (double v : _domain.getReciprocalAxis(d)) kmax[d] = std::max(kmax[d], std::fabs(v));
+  if (_houli)
+    _kernel.configure("exp(-alpha*((abs(kx)/a)^p + (abs(ky)/b)^p + (abs(kz)/c)^p))", {}, {}, {"alpha", "p", "a", "b", "c"},
+                      {_alpha, _p, kmax[0] ? kmax[0] : 1.0, kmax[1] ? kmax[1] : 1.0, kmax[2] ? kmax[2] : 1.0}, true, MRL_EXPAND_RECIPROCAL);
+  else
+    _kernel.configure("if((abs(kx) > a) | (abs(ky) > b) | (abs(kz) > c), 0, 1)", {}, {}, {"a", "b", "c"},
+                      {2 * kmax[0] / 3, 2 * kmax[1] / 3, 2 * kmax[2] / 3}, true, MRL_EXPAND_RECIPROCAL);
+  _u = _kernel.eval(_domain, {}, _time);
+}

@@ -139,8 +139,67 @@ protected:
   Real _critical_dt = 0;
 };
 
+// src/postprocessors/ReciprocalIntegral.C:31-52: Re(ubar[0,0,0]) / #cells * volume
+class ReciprocalIntegral : public TensorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Extract the zero k-vector value (corresponding to the integral).");
+    return params;
+  }
+  using TensorPostprocessor::TensorPostprocessor;
+  void execute() override {
+    if (!_u.defined() || !_u.is_complex()) mooseError("buffer '", _buffer_name, "' must be a defined reciprocal-space (complex) buffer");
+    double z[2] = {0, 0};
+    if (_domain.realBytes() == 8) {
+      _domain.check(mrl_download(_domain.context(), z, _u.data_ptr(), sizeof z), "mrl_download");
+      _domain.synchronize();
+    } else {
+      float zf[2] = {0, 0};
+      _domain.check(mrl_download(_domain.context(), zf, _u.data_ptr(), sizeof zf), "mrl_download");
+      _domain.synchronize();
+      z[0] = zf[0];
+    }
+    _integral = z[0] / Real(_domain.getNumberOfCells()) * _domain.getVolume();
+  }
+  Real getValue() const override { return _integral; }
+
+protected:
+  Real _integral = 0;
+};
+
+// src/postprocessors/ComputeGroupExecutionCount.C: computeBuffer() calls issued to a ComputeGroup
+class ComputeGroupExecutionCount : public TensorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Return the number of computeBuffer() calls issued to the given compute group object.");
+    params.addParam<TensorComputeName>("compute_group", "root", "ComputeGroup TensorCompute object to get execution count from.");
+    // not a buffer postprocessor in the reference (GeneralPostprocessor): the base parameter is unused
+    params.addParam<TensorInputBufferName>("buffer", "_compute_group_execution_count_unused", "unused");
+    return params;
+  }
+  explicit ComputeGroupExecutionCount(const InputParameters &p) : TensorPostprocessor(p), _group_name(getParam<TensorComputeName>("compute_group")) {}
+  void execute() override {}
+  Real getValue() const override {
+    for (const auto &cmp : _tensor_problem.getComputes())
+      if (cmp->name() == _group_name) {
+        const auto *g = dynamic_cast<const ComputeGroup *>(cmp.get());
+        if (!g) mooseError("'", _group_name, "' is not a ComputeGroup");
+        return Real(g->computeCount());
+      }
+    mooseError("compute_group '", _group_name, "' not found");
+    return 0;
+  }
+
+protected:
+  const std::string _group_name;
+};
+
 }  // namespace
 
+registerMooseObject("MarlinApp", ReciprocalIntegral);
+registerMooseObject("MarlinApp", ComputeGroupExecutionCount);
 registerMooseObject("MarlinApp", TensorAveragePostprocessor);
 registerMooseObject("MarlinApp", TensorIntegralPostprocessor);
 registerMooseObject("MarlinApp", TensorExtremeValuePostprocessor);

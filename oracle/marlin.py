@@ -554,6 +554,24 @@ class ReciprocalAllenCahn(Op):
         self.set(self.d.fft(rate))
 
 
+class DeAliasingTensor(Op):
+    """src/tensor_computes/DeAliasingTensor.C:37-62: 2/3-rule (SHARP) or Hou-Li exponential filter."""
+
+    def __init__(self, problem, buffer, method, p=16.0, alpha=36.0):
+        super().__init__(problem, buffer)
+        self.method, self.pw, self.alpha = method, p, alpha
+
+    def compute(self):
+        k = [self.d.kaxis[a] for a in range(3)]
+        kmax = [float(torch.max(torch.abs(t))) for t in k]
+        if self.method == "SHARP":
+            cut = (torch.abs(k[0]) > 2 * kmax[0] / 3) | (torch.abs(k[1]) > 2 * kmax[1] / 3) | (torch.abs(k[2]) > 2 * kmax[2] / 3)
+            self.set(torch.where(cut, 0.0, 1.0).to(self.d.dtype))
+        else:
+            pw = [torch.pow(torch.abs(k[a]) / (kmax[a] if kmax[a] else 1.0), self.pw) for a in range(3)]
+            self.set(torch.exp(-self.alpha * (pw[0] + pw[1] + pw[2])))
+
+
 class SwiftHohenbergLinear(Op):
     """src/tensor_computes/SwiftHohenbergLinear.C:33-36: r - alpha^2 (1 - k^2)^2 (real, reciprocal shape)."""
 

@@ -53,6 +53,44 @@ def exodus_ch2d():
     print("ch2d_exodus", c.shape, mu.shape)
 
 
+def exodus_fields(path, n, L, frames=None):
+    """Nodal variable 1 -> c, elemental variable 1 -> mu of a ProjectTensorAux exodus file on an
+    n^dim grid of extent L (2-D or 3-D), mapped back to the tensor layout."""
+    f = netcdf_file(path, "r", mmap=False)
+    v = f.variables
+    dim = 3 if "coordz" in v and np.abs(v["coordz"][:]).max() > 0 else 2
+    dx = L / n
+    xyz = [v[k][:].copy() for k in ("coordx", "coordy", "coordz")[:dim]]
+    nod, elv = v["vals_nod_var1"][:].copy(), v["vals_elem_var1eb1"][:].copy()
+    conn = v["connect1"][:].copy() - 1
+    times = v["time_whole"][:].copy()
+    sel = list(range(nod.shape[0])) if frames is None else frames
+    ni = tuple(np.floor((a + dx / 2) / dx + 1e-9).astype(int) % n for a in xyz)
+    ei = tuple(np.floor(a[conn].mean(1) / dx).astype(int) % n for a in xyz)
+    c = np.full((len(sel),) + (n,) * dim, np.nan)
+    mu = np.full((len(sel),) + (n,) * dim, np.nan)
+    for k, t in enumerate(sel):
+        c[(k,) + ni] = nod[t]
+        mu[(k,) + ei] = elv[t]
+    assert not np.isnan(c).any() and not np.isnan(mu).any()
+    return c, mu, times[sel]
+
+
+def exodus_more():
+    c, mu, t = exodus_fields(f"{REF}/test/tests/cahnhilliard/gold/map_to_aux_3d.e", 5, 3.0)
+    np.savez_compressed(f"{OUT}/ch3d_map_to_aux_exodus.npz", c=c, mu=mu, time=t)
+    print("ch3d_map_to_aux_exodus", c.shape)
+    frames = [0, 1, 2, 5, 10, 20, 50, 100]
+    c, mu, t = exodus_fields(f"{REF}/test/tests/cahnhilliard/gold/cahnhilliard_explicit_out.e", 50, 3.0, frames)
+    np.savez_compressed(f"{OUT}/ch2d_explicit_exodus.npz", c=c, mu=mu, time=t, frames=np.array(frames))
+    print("ch2d_explicit_exodus", c.shape, t)
+    frames = [0, 1, 5, 20]
+    for name in ("sharp", "houli"):
+        c, mu, t = exodus_fields(f"{REF}/test/tests/cahnhilliard/gold/{name}.e", 50, 3.0, frames)
+        np.savez_compressed(f"{OUT}/ch2d_explicit_{name}_exodus.npz", c=c, mu=mu, time=t, frames=np.array(frames))
+        print(name, c.shape, t)
+
+
 def read_csv(path):
     with open(path) as fh:
         header = fh.readline().strip().split(",")
@@ -178,3 +216,4 @@ if __name__ == "__main__":
     mech2d()
     rotating_grain()
     kks_no_flux()
+    exodus_more()

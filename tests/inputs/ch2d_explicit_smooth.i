@@ -1,0 +1,93 @@
+# The explicit Cahn-Hilliard run of ch2d_explicit.i with a de-aliasing filter (DeAliasingTensor, method
+# given on the command line: smooth=SHARP or smooth=HOULI) multiplying the reciprocal-space time
+# derivative.  Same setup as the reference's test/tests/cahnhilliard/cahnhilliard_explicit_smooth.i
+# (gold sharp.e, houli.e).
+[Domain]
+  dim = 2
+  nx = 50
+  ny = 50
+  xmax = 3
+  ymax = 3
+  mesh_mode = DOMAIN
+[]
+
+[TensorComputes]
+  [Initialize]
+    [c]
+      type = RandomTensor
+      buffer = c
+      min = 0.44
+      max = 0.56
+      seed = 0
+    []
+    [mu_init]
+      type = ConstantTensor
+      buffer = mu
+    []
+    [Mbar]
+      type = ReciprocalLaplacianFactor
+      buffer = Mbar
+      factor = 0.2
+    []
+    [Mkappabarbar]
+      type = ReciprocalLaplacianSquareFactor
+      buffer = Mkappabarbar
+      factor = '${fparse 0.2 * 1e-4}'
+    []
+    [dc_dt_bar_IC]
+      type = ConstantReciprocalTensor
+      buffer = dc_dt_bar
+    []
+    [smooth]
+      type = DeAliasingTensor
+      buffer = smooth
+      method = ${smooth}
+    []
+  []
+  [Solve]
+    [cahn_hilliard]
+      [mu]
+        type = ParsedCompute
+        buffer = mu
+        expression = '0.1*c^2*(c-1)^2'
+        derivatives = c
+        inputs = c
+      []
+      [mubar]
+        type = ForwardFFT
+        buffer = mubar
+        input = mu
+      []
+      [dc_dt_bar]
+        type = ParsedCompute
+        buffer = dc_dt_bar
+        expression = 'smooth * (Mbar*mubar - Mkappabarbar*cbar)'
+        inputs = 'Mbar mubar Mkappabarbar cbar smooth'
+      []
+      [cbar]
+        type = ForwardFFT
+        buffer = cbar
+        input = c
+      []
+    []
+  []
+[]
+
+[TensorSolver]
+  type = ForwardEulerSolver
+  root_compute = cahn_hilliard
+  buffer = c
+  reciprocal_buffer = cbar
+  time_derivative_reciprocal = dc_dt_bar
+  substeps = 50
+[]
+
+[Problem]
+  type = TensorProblem
+[]
+
+[Executioner]
+  type = Transient
+  num_steps = 20
+  dt = 0.5
+[]

@@ -196,3 +196,26 @@ def kks_no_flux_problem(n=20, substeps=1000):
     p.solver = om.AdamsBashforthMoulton(p, root, ["c", "eta"], ["cbar", "etabar"], ["zero", "zero"], ["div_J", "AC_bar"],
                                         substeps=substeps, predictor_order=3)
     return p
+
+
+def ch_explicit_problem(n=50, L=3.0, substeps=50, smooth=None):
+    """test/tests/cahnhilliard/cahnhilliard_explicit.i: explicit (ForwardEulerSolver) Cahn-Hilliard, the
+    time derivative Mbar*mubar - Mkappabarbar*cbar assembled by one ParsedCompute in reciprocal space."""
+    d = om.Domain(2, [n, n], (0, 0, 0), (L, L, 1.0))
+    p = om.Problem(d)
+    p.ics = [om.RandomTensor(p, "c", 0.44, 0.56, 0), om.ConstantTensor(p, "mu", 0.0),
+             om.ReciprocalLaplacianFactor(p, "Mbar", 0.2),
+             om.ReciprocalLaplacianSquareFactor(p, "Mkappabarbar", 0.2 * 1e-4),
+             om.ConstantTensor(p, "dc_dt_bar", 0.0, reciprocal=True)]
+    rate, rate_in = "Mbar*mubar - Mkappabarbar*cbar", ["Mbar", "mubar", "Mkappabarbar", "cbar"]
+    if smooth:  # cahnhilliard_explicit_smooth.i: de-aliasing filter on the time derivative
+        p.ics.append(om.DeAliasingTensor(p, "smooth", smooth))
+        rate, rate_in = f"smooth * ({rate})", rate_in + ["smooth"]
+    root = om.Group(p, [
+        om.ParsedCompute(p, "mu", "0.1*c^2*(c-1)^2", inputs=["c"], derivatives=["c"]),
+        om.ForwardFFT(p, "mubar", "mu"),
+        om.ForwardFFT(p, "cbar", "c"),   # dependency order (ComputeGroup sorts; the input lists it last)
+        om.ParsedCompute(p, "dc_dt_bar", rate, inputs=rate_in),
+    ])
+    p.solver = om.ForwardEulerSolver(p, root, ["c"], ["cbar"], ["dc_dt_bar"], substeps=substeps)
+    return p

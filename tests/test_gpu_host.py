@@ -193,6 +193,52 @@ def test_kks_no_flux_input_matches_gold(tmp_path):
     assert (np.abs(rows - g["csv"]) / np.maximum(np.abs(g["csv"]), 1.0)).max() < 1e-9
 
 
+def test_ch2d_explicit_input_matches_exodus_gold(tmp_path):
+    """test/tests/cahnhilliard/cahnhilliard_explicit.i (ForwardEulerSolver) -> gold cahnhilliard_explicit_out.e."""
+    g = np.load(f"{G}/ch2d_explicit_exodus.npz")
+    frames = list(g["frames"])
+    for step in (1, 10, 20):
+        run(tmp_path, "ch2d_explicit.i", f"Executioner/num_steps={step}", dump=("c", "mu"))
+        k = frames.index(step)
+        assert np.abs(field(tmp_path, "c", (50, 50)) - g["c"][k]).max() < 1e-10, step
+        assert np.abs(field(tmp_path, "mu", (50, 50)) - g["mu"][k]).max() < 1e-10, step
+
+
+@pytest.mark.parametrize("method", ["SHARP", "HOULI"])
+def test_ch2d_explicit_smooth_input_matches_exodus_gold(tmp_path, method):
+    """test/tests/cahnhilliard/cahnhilliard_explicit_smooth.i (DeAliasingTensor) -> gold sharp.e / houli.e."""
+    g = np.load(f"{G}/ch2d_explicit_{method.lower()}_exodus.npz")
+    frames = list(g["frames"])
+    for step in (1, 5, 20):
+        run(tmp_path, "ch2d_explicit_smooth.i", f"smooth={method}", f"Executioner/num_steps={step}", dump=("c", "mu"))
+        k = frames.index(step)
+        assert np.abs(field(tmp_path, "c", (50, 50)) - g["c"][k]).max() < 1e-9, step
+        assert np.abs(field(tmp_path, "mu", (50, 50)) - g["mu"][k]).max() < 1e-9, step
+
+
+def test_ch3d_map_to_aux_input_matches_exodus_gold(tmp_path):
+    """test/tests/cahnhilliard/cahnhilliard.i with the 3-D cli_args of the reference's tests file (gold map_to_aux_3d.e)."""
+    g = np.load(f"{G}/ch3d_map_to_aux_exodus.npz")
+    for step in (1, 10):
+        run(tmp_path, "ch2d_gold.i", "Domain/dim=3", "Domain/nx=5", "Domain/ny=5", "Domain/nz=5", "Domain/zmax=3",
+            f"Executioner/num_steps={step}", dump=("c", "mu"))
+        assert np.abs(field(tmp_path, "c", (5, 5, 5)) - g["c"][step]).max() < 1e-12, step
+        assert np.abs(field(tmp_path, "mu", (5, 5, 5)) - g["mu"][step]).max() < 1e-12, step
+
+
+def test_postprocessors_input_matches_csv_golds(tmp_path):
+    """test/tests/postprocessors/postprocessors.i -> gold average.csv (0.8), integral.csv (4.8),
+    extreme_value.csv (3.2375 / -1.6375), reciprocal_integral.csv (4.8), count.csv (0, 10, 20)."""
+    run(tmp_path, "pp_basic.i")
+    head, rows = csv(f"{tmp_path}/pp_basic.csv")
+    assert head == ["time", "avg_c", "count", "int_c", "int_c_bar", "max_c", "min_c"]
+    col = {h: rows[:, i] for i, h in enumerate(head)}
+    assert np.abs(col["avg_c"] - 0.8).max() < 1e-13 and np.abs(col["int_c"] - 4.8).max() < 1e-12
+    assert np.abs(col["int_c_bar"] - 4.8).max() < 1e-12
+    assert np.abs(col["max_c"] - 3.2375).max() < 1e-13 and np.abs(col["min_c"] + 1.6375).max() < 1e-13
+    assert list(col["count"]) == [0.0, 10.0, 20.0] and list(col["time"]) == [0.0, 1.0, 2.0]
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""
