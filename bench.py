@@ -414,7 +414,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--n", type=int, default=512)
+    # grid size; MRL_BENCH_N is the spelling to use under torchrun (its own parser claims "--n")
+    ap.add_argument("--n", type=int, default=int(os.environ.get("MRL_BENCH_N", "512")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -306,6 +306,11 @@ int mrl_slab_plan_create(mrl_context *ctx, const mrl_split_desc *desc, void *sen
 int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc *desc, mrl_slab_plan **out);
 int mrl_slab_ipc_export(mrl_slab_plan *plan, void *handles_128_bytes);
 int mrl_slab_ipc_import(mrl_slab_plan *plan, const void *all_handles /* nranks x 128 bytes, rank order */);
+/* Peer mode only: stream-ordered barrier across the ranks of the plan (flags in the IPC-mapped
+ * buffers, system-scope release/acquire; no host involvement, no NCCL call).  Every rank must call
+ * it the same number of times.  Separates a pass that stores into the peers' memory from the pass
+ * that reads it.                                                                              */
+int mrl_slab_barrier(mrl_slab_plan *plan);
 int mrl_slab_plan_destroy(mrl_slab_plan *plan);
 /* phase 1: z r2c of (c + i F(c)) and x forward on the local slab -> send_fwd                */
 int mrl_slab_forward(mrl_slab_plan *plan, const void *c_real_dev);

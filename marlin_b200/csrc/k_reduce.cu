@@ -48,4 +48,28 @@ cudaError_t launch_reduce(const LaunchCtx &lc, int op, const T *in, long long co
 template cudaError_t launch_reduce<double>(const LaunchCtx &, int, const double *, long long, double *, int);
 template cudaError_t launch_reduce<float>(const LaunchCtx &, int, const float *, long long, double *, int);
 
+// Cross-GPU barrier of the peer-mode slab plan.  Thread s signals rank s (a system-scope release store
+// of the epoch into that rank's flag slot for this rank) and then waits for rank s's signal in the local
+// slot.  Launched after a pass whose peer stores must be visible before the next pass reads them: the
+// stream order + the release/acquire pair give that.  A peer that never arrives trips the timeout
+// (~4 s) and traps instead of hanging the device.
+__global__ void k_slab_barrier(const unsigned long long *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch) {
+  const int s = threadIdx.x;
+  if (s >= nranks) return;
+  unsigned long long *theirs = reinterpret_cast<unsigned long long *>(recv_tab[s] + flag_off) + rank;
+  unsigned long long *mine = reinterpret_cast<unsigned long long *>(recv_tab[rank] + flag_off) + s;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v < epoch && clock64() - t0 > 8000000000ll) __trap();
+  } while (v < epoch);
+}
+cudaError_t launch_slab_barrier(const LaunchCtx &lc, const void *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch) {
+  k_slab_barrier<<<1, 32, 0, lc.stream>>>((const unsigned long long *)recv_tab, flag_off, rank, nranks, epoch);
+  return cudaGetLastError();
+}
+
 }  // namespace mrl

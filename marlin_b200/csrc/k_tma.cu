@@ -300,49 +300,50 @@ cudaError_t launch_mech_fused_tma(const LaunchCtx &lc, cx<T> *spec, const T *kx,
 // ------------------------------------------------------------------ P1 / P5
 template <class T, class C, int PPB, int NG, int NS, class F>
 static cudaError_t zfwd_tma_go(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int ncp,
-                               const F &f, const cx<T> *tw) {
+                               const F &f, const cx<T> *tw, const RowMap &rm) {
   constexpr int NP = C::N + (C::N >> 3) + 1;
   constexpr size_t smem = (size_t)NG * NS * PPB * C::N * sizeof(T) + (size_t)(NG * PPB * NP) * sizeof(cx<T>) + NG * NS * 8 + 128;
   static_assert(smem <= kSmemBudget, "zfwd_tma: shared memory budget");
   static_assert(NG * PPB * C::TP <= 1024 && NG <= 15, "zfwd_tma: block size");
   if (((unsigned long long)c & 15ull) || (C::N * sizeof(T)) % 16) return cudaErrorNotSupported;
+  if (rm.ych && rm.ych % PPB) return cudaErrorNotSupported;
   auto k = k_zfwd_tma<T, C, PPB, NG, NS, F>;
   int per_sm = 0;
   cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
   if (e != cudaSuccess) return e;
   const long long nwork = ((nrows + PPB - 1) / PPB + NG - 1) / NG;
   const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
-  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(c, mu_out, outC, outG, nrows, ncp, f, tw);
+  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
   return cudaGetLastError();
 }
 
 template <class T>
 cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int n,
-                                   int ncp, const NonlinDesc &nl, const cx<T> *tw) {
+                                   int ncp, const NonlinDesc &nl, const cx<T> *tw, const RowMap &rm) {
   if (!tma_enabled() || nl.kind != 0) return cudaErrorNotSupported;
   static int variant = env_int("MRL_ZFWD_V", 0);
   typedef DoubleWellDeriv<T> F;
   const F f{(T)nl.p[0], (T)nl.p[1], (T)nl.p[2]};
   if constexpr (sizeof(T) == 8) {
     switch (n) {
-      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
-      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
+      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
       case 512:
         switch (variant) {
-          case 1: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
-          case 2: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
-          case 3: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
-          default: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 5, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+          case 1: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
+          case 2: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
+          case 3: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
+          default: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 5, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
         }
-      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
       default: return cudaErrorNotSupported;
     }
   } else {
     switch (n) {
-      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
-      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
-      case 512: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
-      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw);
+      case 128: return zfwd_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
+      case 256: return zfwd_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
+      case 512: return zfwd_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 4, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
+      case 1024: return zfwd_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3, F>(lc, c, mu_out, outC, outG, nrows, ncp, f, tw, rm);
       default: return cudaErrorNotSupported;
     }
   }
@@ -435,7 +436,7 @@ cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp,
   template cudaError_t launch_fused_tma<T>(const LaunchCtx &, const FusedIO<T> &, const SpectralUpdate<T> &, const cx<T> *, \
                                            int);                                                                         \
   template cudaError_t launch_zfwd_nonlin_tma<T>(const LaunchCtx &, const T *, T *, cx<T> *, cx<T> *, long long, int,    \
-                                                 int, const NonlinDesc &, const cx<T> *);                                \
+                                                 int, const NonlinDesc &, const cx<T> *, const RowMap &);                \
   template cudaError_t launch_zfwd_pairs_tma<T>(const LaunchCtx &, const T *, cx<T> *, long long, int, int, const cx<T> *);  \
   template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, int, T *, long long, int, T, const cx<T> *);
 INST(double)

@@ -960,6 +960,13 @@ extern "C" int mrl_slab_plan_create(mrl_context *ctx, const mrl_split_desc *d, v
 extern "C" int mrl_slab_plan_destroy(mrl_slab_plan *p) {
   if (!p) return MRL_OK;
   mrl_quiesce(p->ctx);
+  if (p->s_aux) {
+    cudaStreamSynchronize(p->s_aux);
+    cudaStreamDestroy(p->s_aux);
+    cudaEventDestroy(p->ev_begin);
+    cudaEventDestroy(p->ev_done);
+    for (auto &e : p->ev_chunk) cudaEventDestroy(e);
+  }
   for (void *q : p->ring) cudaFree(q);
   for (void *q : p->opened) cudaIpcCloseMemHandle(q);
   cudaFree(p->peer_recv_tab);
@@ -980,7 +987,10 @@ extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc 
   const size_t fbytes = (size_t)ctx->n[0] * ctx->nyl * slab_pitch(ctx) * esz;
   void *sf = nullptr, *rf = nullptr;
   CK(cudaMalloc(&sf, 2 * fbytes));
-  cudaError_t e = cudaMalloc(&rf, 2 * fbytes);
+  // recv_fwd carries the cross-rank barrier flags (one 8-byte slot per rank) behind the spectra
+  const size_t flag_off = (2 * fbytes + 255) & ~(size_t)255, flag_bytes = 256 * sizeof(unsigned long long);
+  cudaError_t e = cudaMalloc(&rf, flag_off + flag_bytes);
+  if (e == cudaSuccess) e = cudaMemset((char *)rf + flag_off, 0, flag_bytes);
   if (e != cudaSuccess) {
     cudaFree(sf);
     return mrl_fail(MRL_ERR_CUDA, "slab plan allocation failed: %s", cudaGetErrorString(e));
@@ -994,6 +1004,18 @@ extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc 
   }
   (*out)->owns = true;
   (*out)->send_bwd = nullptr;
+  (*out)->flag_off = (long long)flag_off;
+  if (const char *v = getenv("MRL_SLAB_CHUNKS")) (*out)->chunks = atoi(v) > 0 ? atoi(v) : 1;
+  if (const char *v = getenv("MRL_SLAB_XCTAS")) (*out)->x_ctas = atoi(v) > 0 ? atoi(v) : 96;
+  return MRL_OK;
+}
+
+extern "C" int mrl_slab_barrier(mrl_slab_plan *p) {
+  if (!p || !p->peer) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_barrier: needs a peer-mode plan with imported handles");
+  if (p->ctx->nranks > 32) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_slab_barrier: at most 32 ranks");
+  CK(cudaSetDevice(p->ctx->device));
+  p->ctx->launches++;
+  CK(launch_slab_barrier(p->ctx->lc(), p->peer_recv_tab, p->flag_off, p->ctx->rank, p->ctx->nranks, ++p->epoch));
   return MRL_OK;
 }
 
@@ -1049,23 +1071,26 @@ extern "C" int mrl_slab_advance_state(mrl_slab_plan *p, int *stored) {
 }
 
 // x pass (axis 0) on the local [nx][nyl][ncp] slabs of send_fwd
-template <class T> static int slab_xpass(mrl_slab_plan *p, int nfields, int inverse) {
+// y0, ych: restrict the pass to the columns of the y-chunk [y0, y0 + ych) (ych = 0: all); lc: stream and
+// CTA budget of the launch
+template <class T> static int slab_xpass(mrl_slab_plan *p, int nfields, int inverse, int y0 = 0, int ych = 0, const LaunchCtx *lcp = nullptr) {
   mrl_context *ctx = p->ctx;
-  cx<T> *A = (cx<T> *)p->send_fwd;
+  const long long col0 = (long long)y0 * p->ncp;
+  cx<T> *A = (cx<T> *)p->send_fwd + col0;
   StridedIO<T> sio;
   memset(&sio, 0, sizeof sio);
   if (p->peer && !inverse) {  // forward x pass: scatter the rows to the ranks that own them
     sio.peer_tab = (const unsigned long long *)p->peer_recv_tab;
     sio.peer_rows = ctx->nxl;
     sio.peer_field = p->field;
-    sio.peer_off = (long long)ctx->rank * p->chunk;
+    sio.peer_off = (long long)ctx->rank * p->chunk + col0;
   }
   for (int f = 0; f < nfields; ++f) sio.in[f] = sio.out[f] = A + f * p->field;
   sio.nfields = nfields;
   sio.n = ctx->n[0];
-  sio.ncols = ctx->nyl * p->ncp;
+  sio.ncols = (ych ? ych : ctx->nyl) * p->ncp;
   sio.nouter = 1;
-  sio.pitch = sio.ncols;
+  sio.pitch = (long long)ctx->nyl * p->ncp;
   sio.outer_stride = (long long)sio.n * sio.pitch;
   sio.scale = T(1);
   sio.inverse = inverse;
@@ -1073,7 +1098,7 @@ template <class T> static int slab_xpass(mrl_slab_plan *p, int nfields, int inve
   int rc = ctx->twiddles(sio.n, &tw);
   if (rc) return rc;
   ctx->launches++;
-  CK(launch_strided_tma<T>(ctx->lc(), sio, (const cx<T> *)tw, sio.n));
+  CK(launch_strided_tma<T>(lcp ? *lcp : ctx->lc(), sio, (const cx<T> *)tw, sio.n));
   return MRL_OK;
 }
 
@@ -1086,6 +1111,35 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
   int rc = ctx->twiddles(nl, &twl);
   if (rc) return rc;
   NonlinDesc nlz{0, {d.nonlin_params[0], d.nonlin_params[1], d.nonlin_params[2], 0}};
+  const int C = p->chunks, nyl = ctx->nyl;
+  if (C > 1 && p->peer && nyl % C == 0 && (nyl / C) % 8 == 0) {
+    // z pass of chunk i+1 on the main stream while the x pass of chunk i pushes its rows over NVLink
+    // from a few SMs on the aux stream (that pass is bound by the link, not by the SMs)
+    const int ych = nyl / C;
+    if (!p->s_aux) {
+      CK(cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+      p->ev_chunk.resize(C);
+      for (auto &e : p->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int xc = p->x_ctas < ctx->sm_count ? p->x_ctas : ctx->sm_count / 2;
+    CK(cudaEventRecord(p->ev_begin, ctx->stream));
+    CK(cudaStreamWaitEvent(p->s_aux, p->ev_begin, 0));
+    for (int i = 0; i < C; ++i) {
+      const LaunchCtx lz{ctx->stream, i == 0 ? ctx->sm_count : ctx->sm_count - xc};
+      const LaunchCtx lx{p->s_aux, i == C - 1 ? ctx->sm_count : xc};
+      ctx->launches++;
+      CK(launch_zfwd_nonlin_tma<T>(lz, c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ych, nl, p->ncp, nlz,
+                                   (const cx<T> *)twl, RowMap{ych, nyl, i * ych}));
+      CK(cudaEventRecord(p->ev_chunk[i], ctx->stream));
+      CK(cudaStreamWaitEvent(p->s_aux, p->ev_chunk[i], 0));
+      if ((rc = slab_xpass<T>(p, 2, 0, i * ych, ych, &lx))) return rc;
+    }
+    CK(cudaEventRecord(p->ev_done, p->s_aux));
+    CK(cudaStreamWaitEvent(ctx->stream, p->ev_done, 0));
+    return MRL_OK;
+  }
   ctx->launches++;
   CK(launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ctx->nyl, nl, p->ncp, nlz,
                                (const cx<T> *)twl));

@@ -167,7 +167,8 @@ static int launch_typed(mrl_context *ctx, mrl_expr *e, const void *const *inputs
     long long nrows = rows;
     const long long nwork = (rows + e->zfwd_ppb - 1) / e->zfwd_ppb;
     const unsigned grid = (unsigned)(nwork < ctx->sm_count ? nwork : ctx->sm_count);
-    void *params[] = {(void *)&c, &g_out, &outC, &outG, &nrows, &ncp, &f, (void *)&tw};
+    mrl::RowMap rm{0, 0, 0};
+    void *params[] = {(void *)&c, &g_out, &outC, &outG, &nrows, &ncp, &f, (void *)&tw, &rm};
     return mrlx_launch(e->zfwd_fn, grid, e->zfwd_block, e->zfwd_smem, ctx->stream, params);
   }
   if (ncp != n / 2 + 1) return mrl_fail(MRL_ERR_UNSUPPORTED, "padded work spectra need the TMA first pass");

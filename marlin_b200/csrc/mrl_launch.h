@@ -66,7 +66,7 @@ template <class T>
 cudaError_t launch_fused_tma(const LaunchCtx &lc, const FusedIO<T> &io, const SpectralUpdate<T> &up, const cx<T> *tw, int n);
 template <class T>
 cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int n,
-                                   int ncp, const NonlinDesc &nl, const cx<T> *tw);
+                                   int ncp, const NonlinDesc &nl, const cx<T> *tw, const RowMap &rm = RowMap{0, 0, 0});
 template <class T>
 cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, int n, T scale,
                                   const cx<T> *tw);

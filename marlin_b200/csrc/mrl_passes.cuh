@@ -17,6 +17,15 @@
 
 namespace mrl {
 
+// Row remap for a pass over a y-chunk of a slab [nx][nyl][..]: the pass enumerates rows r' of the chunk
+// [nx][ych] and works on row (r' / ych) * nyl + y0 + r' % ych of the full arrays.  ych = 0: identity.
+// (PPB must divide ych so that the rows of a tile stay consecutive.)
+struct RowMap {
+  int ych, nyl, y0;
+  MRL_DI long long operator()(long long r) const { return ych ? (r / ych) * nyl + y0 + r % ych : r; }
+};
+
+
 // ======================================================================== strided c2c pass
 // Data is [nfields][nouter][n][ncols] complex, transform along n (stride `pitch`).
 template <class T> struct StridedIO {

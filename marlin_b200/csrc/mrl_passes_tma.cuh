@@ -488,7 +488,7 @@ template <class T> MRL_DI cx<T> shfl_cx(cx<T> v, int lane) {
 
 template <class T, class C, int PPB, int NG, int NS, class F>
 __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
-    k_zfwd_tma(const T *cin, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int ncp, F f, const cx<T> *tw_g) {
+    k_zfwd_tma(const T *cin, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int ncp, F f, const cx<T> *tw_g, RowMap rm) {
   constexpr int N = C::N, TP = C::TP, E = C::E, GT = PPB * TP;
   constexpr int NP = N + (N >> 3) + 1;
   // ncp: row pitch of the half spectra (>= N/2+1; padded to 128 bytes inside the split plan)
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
     const int s = j % NS;
     const uint32_t bytes = (uint32_t)(rows * N * sizeof(T));
     mbar_expect_tx(&gb[s], bytes);
-    bulk_load_1d(gs + (size_t)s * PPB * N, cin + row0 * N, bytes, &gb[s]);
+    bulk_load_1d(gs + (size_t)s * PPB * N, cin + rm(row0) * N, bytes, &gb[s]);
   };
 
   if (tid == 0) {
@@ -536,8 +536,9 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
   const SmPencil<T> sm{xbuf + (size_t)(g * PPB + pl) * NP};
   for (int j = 0; j < nloc; ++j) {
     const int s = j % NS;
-    const long long p = (first + j * stride) * PPB + pl;
-    const bool ok = p < nrows;
+    const long long pc = (first + j * stride) * PPB + pl;  // row of the (chunk) enumeration
+    const bool ok = pc < nrows;
+    const long long p = rm(pc);                            // row of the full arrays
     mbar_wait(&gb[s], (uint32_t)((j / NS) & 1));
     const T *src = gs + (size_t)s * PPB * N + pl * N;
     cx<T> v[E];

@@ -52,6 +52,10 @@ class SlabPlan:
         memory, CUDA IPC); mode "nccl": the three phases with torch.distributed all-to-all calls
         between them (the baseline the fused mode is measured against)."""
         self.ctx, self.group, self.mode = ctx, group, mode
+        # barrier between the phases in peer mode: "dev" = flags in peer memory (mrl_slab_barrier),
+        # "nccl" = a 1-element all-reduce
+        import os
+        self.barrier_kind = os.environ.get("MRL_SLAB_BARRIER", "dev")
         dev = ctx.device
         f = ctx.field_elems
         d = capi.SplitDesc()
@@ -93,9 +97,9 @@ class SlabPlan:
             # stream-ordered cross-rank barriers (a 1-element all-reduce) separate the phases: a
             # rank's pass may only read what every peer's previous pass has finished storing
             _ck(lib().mrl_slab_forward(self.h, _p(c)))
-            dist.all_reduce(self._flag, group=self.group)
+            self._barrier()
             _ck(lib().mrl_slab_update(self.h, C.c_double(dt), b, int(nold)))
-            dist.all_reduce(self._flag, group=self.group)
+            self._barrier()
             _ck(lib().mrl_slab_inverse(self.h, _p(c)))
             return
         _ck(lib().mrl_slab_forward(self.h, _p(c)))
@@ -104,6 +108,39 @@ class SlabPlan:
         _ck(lib().mrl_slab_update(self.h, C.c_double(dt), b, int(nold)))
         exchange_backward(self._sf[0], self._sb, self.group)
         _ck(lib().mrl_slab_inverse(self.h, _p(c)))
+
+    def _barrier(self):
+        if self.barrier_kind == "dev":
+            _ck(lib().mrl_slab_barrier(self.h))
+        else:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def substep_timed(self, c, dt, beta, nold):
+        """substep() with CUDA events between the phases (on the launching stream); returns the five
+        intervals in ms: forward passes, exchange/barrier, fused update pass, exchange/barrier,
+        inverse passes."""
+        b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        _ck(lib().mrl_slab_forward(self.h, _p(c)))
+        ev[1].record()
+        if self.mode == "peer":
+            self._barrier()
+        else:
+            for i in (1, 0):
+                exchange_forward(self._rf[i], self._sf[i], self.group)
+        ev[2].record()
+        _ck(lib().mrl_slab_update(self.h, C.c_double(dt), b, int(nold)))
+        ev[3].record()
+        if self.mode == "peer":
+            self._barrier()
+        else:
+            exchange_backward(self._sf[0], self._sb, self.group)
+        ev[4].record()
+        _ck(lib().mrl_slab_inverse(self.h, _p(c)))
+        ev[5].record()
+        torch.cuda.synchronize()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
 
     def advance_state(self):
         v = C.c_int()
@@ -179,6 +216,17 @@ def bench(args, rank, world, metric):
     total_ms = float(t.item())
     launches = ctx.launch_count() - l0
 
+    # per-phase device times (CUDA events between the phases), max over ranks
+    reps, acc = 10, None
+    for _ in range(reps):
+        dist.barrier()
+        tph = plan.substep_timed(c, dt, AB_BETA[1], 1)
+        plan.advance_state()
+        acc = tph if acc is None else [a + b for a, b in zip(acc, tph)]
+    tph = torch.tensor([a / reps for a in acc], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tph, op=dist.ReduceOp.MAX)
+    phases_ms = [round(float(v), 4) for v in tph.tolist()]
+
     # end to end: H2D of the local slab, substep, D2H of the local slab, every step
     out_host = torch.empty_like(host_c).pin_memory()
     nbytes = host_c.numel() * 8
@@ -222,7 +270,7 @@ def bench(args, rank, world, metric):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"CH-3D-{n}: cahnhilliard2.i at n={n}, AB2 steady state, slab-decomposed "
                                    f"(y real / x reciprocal) over {world} GPUs, half spectrum on the wire, "
-                                   + ("all-to-all fused into the passes (peer stores over NVLink)" if mode == "peer"
+                                   + (f"all-to-all fused into the passes (peer stores over NVLink), {plan.barrier_kind} barrier" if mode == "peer"
                                       else "NCCL all-to-all between the phases"),
                        "l2": "inputs larger than L2" if s_r / world > 126e6 else "per-GPU slab comparable to L2",
                        "parallelism": f"slab{world}"},
@@ -235,6 +283,9 @@ def bench(args, rank, world, metric):
                          "note": "per-GPU algorithmic HBM bytes / step time; the step also moves "
                                  f"{a2a / 1e9:.3f} GB per GPU over NVLink ({a2a / 1e9 / (ms / 1e3):.0f} GB/s achieved "
                                  "if it were the only cost; 770 GB/s per direction measured peer copy)"},
+            "phases_ms": dict(zip(["forward (z r2c, x fwd + peer stores)", "barrier 1", "fused y pass (+ peer stores)",
+                                   "barrier 2", "inverse (x inv, z c2r)"], phases_ms)),
+            "forward_chunks": os.environ.get("MRL_SLAB_CHUNKS", "4 (default)"),
             "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)

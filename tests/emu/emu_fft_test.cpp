@@ -265,7 +265,9 @@ template <class C, int TK, int NG> static void run_fused_tma(FusedIO<double> io0
 }
 
 // P1 (c + i F(c)) and P5 against the naive DFT
-template <class C, int PPB, int NG, int NS> static void test_zfwd_tma(const char *name, int nrows, int grid) {
+// `chunks` > 0: the rows are a slab [nx][nyl] and the pass runs once per y-chunk with a RowMap (the
+// multi-GPU forward phase overlaps such chunk passes with the x passes of the previous chunk)
+template <class C, int PPB, int NG, int NS> static void test_zfwd_tma(const char *name, int nrows, int grid, int nyl = 0, int ych = 0) {
   constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1, ncp = (nc + 7) & ~7;
   std::mt19937_64 rng(13);
   std::uniform_real_distribution<double> U(0, 1);
@@ -279,8 +281,19 @@ template <class C, int PPB, int NG, int NS> static void test_zfwd_tma(const char
   double *mp = mu.data();
   cx<double> *ocp = oc.data(), *ogp = og.data();
   const cx<double> *twp = tw.data();
-  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem,
-              [=] { k_zfwd_tma<double, C, PPB, NG, NS, DoubleWellDeriv<double>>(cp, mp, ocp, ogp, nrows, ncp, f, twp); }, 64 * 1024);
+  if (!ych) {
+    emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem,
+                [=] { k_zfwd_tma<double, C, PPB, NG, NS, DoubleWellDeriv<double>>(cp, mp, ocp, ogp, nrows, ncp, f, twp, RowMap{0, 0, 0}); }, 64 * 1024);
+  } else {
+    const int nx = nrows / nyl;
+    for (int y0 = 0; y0 < nyl; y0 += ych) {
+      const int w = std::min(ych, nyl - y0);
+      const long long rows = (long long)nx * w;
+      const RowMap rm{w, nyl, y0};
+      emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem,
+                  [=] { k_zfwd_tma<double, C, PPB, NG, NS, DoubleWellDeriv<double>>(cp, mp, ocp, ogp, rows, ncp, f, twp, rm); }, 64 * 1024);
+    }
+  }
   double err = 0;
   for (int r = 0; r < nrows; ++r) {
     std::vector<lc> x(n), g(n);
@@ -529,6 +542,8 @@ static void tma_tests() {
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 peer stores", 4, 3, 5, 6, 2, true);
   test_strided_peer<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("strided tma 64 peer scatter P4", 4, 11);
   test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 3, 2>("zfwd tma 64 PPB4 NG3 NS2 rows=21", 21, 2);
+  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 2, 2>("zfwd tma 64 PPB4 y-chunks of 4 in a [5][12] slab", 60, 2, 12, 4);
+  test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 1, 2>("zfwd tma 64 PPB4 y-chunks of 8 (last 4) in a [3][12] slab", 36, 1, 12, 8);
   test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("zfwd tma 64 PPB8 NG2 NS3 rows=50", 50, 1);
   test_zfwd_tma<FFTCfg<512, 64, 8, 8, 8>, 1, 2, 2>("zfwd tma 512 PPB1 NG2 NS2 rows=5 (pair_map)", 5, 1);
   test_zfwd_tma<FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 1, 2>("zfwd tma 1024 PPB1 NG1 NS2 rows=2 (pair_map)", 2, 1);

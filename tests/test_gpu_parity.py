@@ -297,6 +297,34 @@ def test_coupled_solve_matches_linalg_solve(ctx, nvar):
             assert rel_l2(torch.view_as_real(got[i].cpu()), torch.view_as_real(ref[..., i].contiguous())) < 1e-11
 
 
+def test_staged_transfers_pipeline_matches_plain_path(ctx):
+    """mrl_upload_staged / mrl_download_staged / mrl_staged_wait (copy streams ordered against the compute
+    stream by events): a pipelined sequence of independent steps on alternating buffers gives the same
+    results as upload -> substep -> download with full synchronisation."""
+    from oracle.marlin import AB_BETA
+    n = 64
+    ctx.domain_set(3, (n, n, n), (0,) * 3, (8.0,) * 3)
+    torch.manual_seed(11)
+    hosts = [(torch.rand(n, n, n, dtype=torch.float64) * 0.12 + 0.44).pin_memory() for _ in range(5)]
+    plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=0)
+    ref = []
+    for h in hosts:
+        c = h.cuda()
+        plan.substep(c, 1e-3, AB_BETA[0], 0)
+        ref.append(c.cpu())
+    dev = [torch.empty(n, n, n, dtype=torch.float64, device="cuda") for _ in range(2)]
+    outs = [torch.empty(n, n, n, dtype=torch.float64).pin_memory() for _ in hosts]
+    for k, h in enumerate(hosts):
+        ctx.upload_staged(dev[k & 1], h)
+        plan.substep(dev[k & 1], 1e-3, AB_BETA[0], 0)
+        ctx.download_staged(outs[k], dev[k & 1])
+    ctx.staged_wait()
+    ctx.synchronize()
+    for a, b in zip(outs, ref):
+        assert torch.equal(a, b)
+    plan.close()
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_512_properties(ctx):
     """At BASELINE's 512^3 the oracle is too slow for a test; check size-independent

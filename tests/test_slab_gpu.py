@@ -10,10 +10,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, nsub, mode, q):
+def _worker(rank, world, port, n, nsub, mode, q, chunks=1):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["MRL_SLAB_CHUNKS"] = str(chunks)   # read at plan creation: forward phase in y-chunks
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from marlin_b200 import capi, slab
@@ -61,16 +62,16 @@ def _worker(rank, world, port, n, nsub, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,mode", [(128, "nccl"), (128, "peer"), (256, "peer")])
-def test_slab_matches_single_gpu(n, mode):
+@pytest.mark.parametrize("n,mode,chunks", [(128, "nccl", 1), (128, "peer", 1), (256, "peer", 1), (128, "peer", 2), (256, "peer", 4)])
+def test_slab_matches_single_gpu(n, mode, chunks):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + (7 if mode == "peer" else 0) + n // 128
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, 6, mode, q)) for r in range(world)]
+    port = 29700 + (os.getpid() % 1000) + (7 if mode == "peer" else 0) + n // 128 + 11 * chunks
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, 6, mode, q, chunks)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in range(world))
