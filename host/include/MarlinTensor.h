@@ -13,7 +13,7 @@
 
 namespace marlin {
 
-enum class Space { SCALAR = 0, REAL = 1, RECIPROCAL = 2 };
+enum class Space { SCALAR = 0, REAL = 1, RECIPROCAL = 2, NODAL = 3 };  // NODAL: (n+1)^dim oversized nodal fields (ComputeDisplacements)
 
 class TensorPool;
 

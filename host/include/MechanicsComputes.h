@@ -71,3 +71,25 @@ protected:
   mrl_mech_stats _stats;
   MechPlanHolder _plan;
 };
+
+// src/tensor_computes/ComputeVonMisesStress.C
+class ComputeVonMisesStress : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit ComputeVonMisesStress(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const marlin::Tensor &_stress;
+};
+
+// src/tensor_computes/ComputeDisplacements.C
+class ComputeDisplacements : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit ComputeDisplacements(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const marlin::Tensor &_deformation_gradient_tensor;
+};

@@ -128,7 +128,11 @@ void DomainAction::gridChanged() {
 }
 
 Tensor DomainAction::empty(Space space, bool is_complex, int ncomp) const {
-  const int64_t count = space == Space::SCALAR ? 1 : (space == Space::REAL ? getNumberOfCells() : getNumberOfReciprocalCells());
+  int64_t count = space == Space::SCALAR ? 1 : (space == Space::REAL ? getNumberOfCells() : getNumberOfReciprocalCells());
+  if (space == Space::NODAL) {
+    count = 1;
+    for (unsigned int d = 0; d < _dim; ++d) count *= _n_global[d] + 1;
+  }
   const size_t bytes = size_t(count) * ncomp * realBytes() * (is_complex ? 2 : 1);
   return Tensor(_pool->get(bytes), space, is_complex, ncomp, count);
 }

@@ -205,3 +205,46 @@ void FFTMechanics::computeBuffer() {
   // the stress of the final state is what the constitutive model's last evaluation leaves behind
   _tensor_problem.getBuffer(getParam<TensorOutputBufferName>("stress")) = P;
 }
+
+// ------------------------------------------------------------------------- ComputeVonMisesStress
+registerMooseObject("MarlinApp", ComputeVonMisesStress);
+
+InputParameters ComputeVonMisesStress::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Compute vonMises stress.");
+  params.addParam<TensorInputBufferName>("stress", "stress", "Stress tensor.");
+  return params;
+}
+ComputeVonMisesStress::ComputeVonMisesStress(const InputParameters &parameters) : TensorOperator<>(parameters), _stress(getInputBuffer("stress")) {}
+
+void ComputeVonMisesStress::computeBuffer() {
+  if (!_stress.defined()) return;  // ComputeVonMisesStress.C:33-34
+  if (_dim != 2 && _dim != 3) mooseError("Unsupported problem dimension ", _dim);
+  if (_stress.ncomp() != int(_dim * _dim)) mooseError("stress must be a ", _dim, "x", _dim, " tensor field");
+  Tensor out = _domain.empty(Space::REAL, false, 1);
+  checkC(mrl_von_mises(_domain.context(), _stress.data_ptr(), out.data_ptr()), "mrl_von_mises");
+  _u = out;
+}
+
+// -------------------------------------------------------------------------- ComputeDisplacements
+registerMooseObject("MarlinApp", ComputeDisplacements);
+
+InputParameters ComputeDisplacements::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Compute updated displacements from the deformation gradient tensor.");
+  params.addRequiredParam<TensorInputBufferName>("F", "Deformation gradient tensor.");
+  return params;
+}
+ComputeDisplacements::ComputeDisplacements(const InputParameters &parameters)
+  : TensorOperator<>(parameters), _deformation_gradient_tensor(getInputBuffer("F")) {}
+
+void ComputeDisplacements::computeBuffer() {
+  const Tensor &F = _deformation_gradient_tensor;
+  if (!F.defined()) return;  // ComputeDisplacements.C:56-58
+  if (_dim != 2 && _dim != 3) mooseError("Unsupported problem dimension");
+  if (F.ncomp() != int(_dim * _dim)) mooseError("Value dimensions of the deformation gradient tensor to not match the problem dimension");
+  // (n+1)^dim nodal field, component major
+  Tensor out = _domain.empty(Space::NODAL, false, int(_dim));
+  checkC(mrl_displacements(_domain.context(), F.data_ptr(), out.data_ptr()), "mrl_displacements");
+  _u = out;
+}

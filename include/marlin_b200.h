@@ -264,6 +264,15 @@ int mrl_mech_apply_GK(mrl_mech_plan *plan, const void *F_dev, const void *x_dev,
  * macroscopic strain (D*D values) or NULL.  Synchronous (iteration counts depend on
  * device-side norms).                                                                        */
 int mrl_mech_solve(mrl_mech_plan *plan, void *F_dev, const double *applied9, void *P_dev, mrl_mech_stats *stats);
+/* von Mises stress of a component-major D x D stress field (ComputeVonMisesStress::computeBuffer,
+ * src/tensor_computes/ComputeVonMisesStress.C:30-67; 3-D and 2-D forms as coded there).        */
+int mrl_von_mises(mrl_context *ctx, const void *stress_dev, void *out_real_dev);
+/* Displacement field of a periodic deformation gradient on the (n+1)^D NODAL grid
+ * (ComputeDisplacements::computeBuffer, src/tensor_computes/ComputeDisplacements.C:53-107):
+ * u = (<F> - I) X + irfftn( rfftn(F - <F>) q (-i) / |q|^2 ), then (bi/tri)linear resampling with
+ * align_corners = true.  F: component-major [D*D][cells]; out: component-major [D][nodes].
+ * Synchronous (uses device reductions for <F>).                                               */
+int mrl_displacements(mrl_context *ctx, const void *F_dev, void *out_nodal_dev);
 /* [n][ncomp] (components fastest, the reference layout) <-> [ncomp][n]; in != out.           */
 int mrl_components(mrl_context *ctx, const void *in_dev, void *out_dev, int64_t n, int ncomp, int to_component_major);
 

@@ -19,6 +19,12 @@
 
 namespace mrl {
 
+static inline int ew_grid_fwd(long long total, const LaunchCtx &lc) {
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)lc.sm_count * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
 template <class T, int D> struct MD {
   T a[D][D];
 };
@@ -312,6 +318,148 @@ template <class T, int D> __global__ void __launch_bounds__(256) k_add_const9(T 
   }
 }
 
+// von Mises stress of a component-major stress field (ComputeVonMisesStress.C:37-63, both forms as coded)
+template <class T, int D> __global__ void __launch_bounds__(256) k_von_mises(const T *s, T *out, long long n) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+    auto S = [&](int i, int j) { return s[(D * i + j) * n + v]; };
+    T t;
+    if (D == 3) {
+      const T a = S(0, 0) - S(1, 1), b = S(1, 1) - S(2, 2), c = S(2, 2) - S(0, 0);
+      const T xy = S(0, 1), yz = S(1, 2), zx = S(2, 0);
+      t = a * a + b * b + c * c + T(6) * (xy * xy + yz * yz + zx * zx);
+    } else {
+      const T a = S(0, 0) - S(1, 1), xy = S(0, 1);
+      t = a * a + T(6) * (xy * xy);
+    }
+    out[v] = sqrt(T(0.5) * t);
+  }
+}
+template <class T> cudaError_t launch_von_mises(const LaunchCtx &lc, int dim, const T *s, T *out, long long n) {
+  if (dim == 3) k_von_mises<T, 3><<<ew_grid_fwd(n, lc), 256, 0, lc.stream>>>(s, out, n);
+  else k_von_mises<T, 2><<<ew_grid_fwd(n, lc), 256, 0, lc.stream>>>(s, out, n);
+  return cudaGetLastError();
+}
+
+// ComputeDisplacements.C:74-78: per wavevector u_i = sum_j Hbar_ij q_j (-i) / |q|^2 (0 at q = 0), written in
+// place into component i of the spectra (row i = components D i .. D i + D - 1 is read first).
+template <class T, int D>
+__global__ void __launch_bounds__(256) k_disp_contract(cx<T> *H, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp) {
+  const long long plane = (long long)n1 * ncp, field = (long long)n0 * plane;
+  const long long total = (long long)n0 * n1 * nzc;
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const int iz = (int)(w % nzc);
+    const int iy = (int)((w / nzc) % n1);
+    const int ix = (int)(w / ((long long)nzc * n1));
+    const long long off = (long long)ix * plane + (long long)iy * ncp + iz;
+    T q[D];
+    q[0] = kx[ix];
+    if (D == 3) q[1] = ky[iy];
+    q[D - 1] = kz[iz];
+    T Q = T(0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) Q += q[d] * q[d];
+    cx<T> u[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      T sx = T(0), sy = T(0);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const cx<T> h = H[(D * i + j) * field + off];
+        sx += h.x * q[j];
+        sy += h.y * q[j];
+      }
+      // (sx + i sy) * (-i) = sy - i sx
+      u[i] = Q == T(0) ? mk<T>(T(0), T(0)) : mk<T>(sy / Q, -sx / Q);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) H[i * field + off] = u[i];
+  }
+}
+
+// ComputeDisplacements.C:84-106: out_i(node) = interpolate(u_aff_i + u_per_i) on the (n+1)^D nodal grid,
+// (bi/tri)linear with align_corners = true (source coordinate = node * (n-1)/n);
+// u_aff_i(cell) = sum_j A_ij X_j(cell), A = <F> - I, X the cell-centre axes.
+template <class T, int D> struct DispArgs {
+  const T *uper;   // [D][n0*n1*n2]
+  T *out;          // [D][(n0+1)(n1+1)(n2+1)]
+  const T *ax[3];  // cell-centre axes
+  int n[3];
+  T A[D][D];
+};
+template <class T, int D> __global__ void __launch_bounds__(256) k_disp_nodal(DispArgs<T, D> a) {
+  const int m0 = a.n[0] + 1, m1 = D >= 2 ? a.n[1] + 1 : 1, m2 = D == 3 ? a.n[2] + 1 : 1;
+  const long long nodes = (long long)m0 * m1 * m2, cells = (long long)a.n[0] * (D >= 2 ? a.n[1] : 1) * (D == 3 ? a.n[2] : 1);
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < nodes; w += (long long)gridDim.x * blockDim.x) {
+    int p[3] = {0, 0, 0};
+    long long r = w;
+    for (int d = D - 1; d >= 0; --d) {
+      const int m = a.n[d] + 1;
+      p[d] = (int)(r % m);
+      r /= m;
+    }
+    int i0[3] = {0, 0, 0}, i1[3] = {0, 0, 0};
+    double l1[3] = {0, 0, 0};
+    for (int d = 0; d < D; ++d) {
+      const double src = a.n[d] > 0 ? (double)p[d] * ((double)(a.n[d] - 1) / (double)a.n[d]) : 0.0;
+      i0[d] = (int)src;
+      i1[d] = i0[d] + (i0[d] < a.n[d] - 1 ? 1 : 0);
+      l1[d] = src - i0[d];
+    }
+    double acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.0;
+    for (int corner = 0; corner < (1 << D); ++corner) {
+      double wgt = 1.0;
+      int c[3] = {0, 0, 0};
+      for (int d = 0; d < D; ++d) {
+        const int hi = (corner >> d) & 1;
+        c[d] = hi ? i1[d] : i0[d];
+        wgt *= hi ? l1[d] : 1.0 - l1[d];
+      }
+      long long cell = c[0];
+      if (D >= 2) cell = cell * a.n[1] + c[1];
+      if (D == 3) cell = cell * a.n[2] + c[2];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double v = (double)a.uper[i * cells + cell];
+#pragma unroll
+        for (int j = 0; j < D; ++j) v += (double)a.A[i][j] * (double)a.ax[j][c[j]];
+        acc[i] += wgt * v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) a.out[i * nodes + w] = (T)acc[i];
+  }
+}
+
+template <class T>
+cudaError_t launch_disp_contract(const LaunchCtx &lc, int dim, cx<T> *H, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp) {
+  const int grid = ew_grid_fwd((long long)n0 * n1 * nzc, lc);
+  if (dim == 3) k_disp_contract<T, 3><<<grid, 256, 0, lc.stream>>>(H, kx, ky, kz, n0, n1, nzc, ncp);
+  else k_disp_contract<T, 2><<<grid, 256, 0, lc.stream>>>(H, kx, ky, kz, n0, n1, nzc, ncp);
+  return cudaGetLastError();
+}
+template <class T, int D>
+static cudaError_t disp_nodal_go(const LaunchCtx &lc, const T *uper, T *out, const T *const *ax, const int *n, const double *A) {
+  DispArgs<T, D> a;
+  a.uper = uper;
+  a.out = out;
+  long long nodes = 1;
+  for (int d = 0; d < 3; ++d) {
+    a.ax[d] = ax[d];
+    a.n[d] = d < D ? n[d] : 1;
+    if (d < D) nodes *= n[d] + 1;
+  }
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) a.A[i][j] = (T)A[D * i + j];
+  k_disp_nodal<T, D><<<ew_grid_fwd(nodes, lc), 256, 0, lc.stream>>>(a);
+  return cudaGetLastError();
+}
+template <class T>
+cudaError_t launch_disp_nodal(const LaunchCtx &lc, int dim, const T *uper, T *out, const T *const *ax, const int *n, const double *A) {
+  return dim == 3 ? disp_nodal_go<T, 3>(lc, uper, out, ax, n, A) : disp_nodal_go<T, 2>(lc, uper, out, ax, n, A);
+}
+
 // [n][ncomp] (reference layout, components fastest) <-> [ncomp][n]
 template <class T> __global__ void __launch_bounds__(256) k_components(const T *in, T *out, long long n, int ncomp, int to_soa) {
   const long long total = n * ncomp;
@@ -410,7 +558,10 @@ template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *i
   template cudaError_t launch_vec<T>(const LaunchCtx &, int, const T *, const T *, T *, T *, double *, double, long long, int, int, \
                                      double *, int);                                                                              \
   template cudaError_t launch_add_const9<T>(const LaunchCtx &, int, T *, const double *, long long);                                    \
-  template cudaError_t launch_components<T>(const LaunchCtx &, const T *, T *, long long, int, int);
+  template cudaError_t launch_components<T>(const LaunchCtx &, const T *, T *, long long, int, int);                              \
+  template cudaError_t launch_von_mises<T>(const LaunchCtx &, int, const T *, T *, long long);                                    \
+  template cudaError_t launch_disp_contract<T>(const LaunchCtx &, int, cx<T> *, const T *, const T *, const T *, int, int, int, int); \
+  template cudaError_t launch_disp_nodal<T>(const LaunchCtx &, int, const T *, T *, const T *const *, const int *, const double *);
 INST(double)
 INST(float)
 

@@ -25,6 +25,11 @@ cudaError_t launch_vec(const LaunchCtx &lc, int op, const T *a, const T *b, T *y
                        double *partials, int nblk);
 template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, int dim, T *y, const double *s, long long n);
 template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *in, T *out, long long n, int ncomp, int to_soa);
+template <class T> cudaError_t launch_von_mises(const LaunchCtx &lc, int dim, const T *s, T *out, long long n);
+template <class T>
+cudaError_t launch_disp_contract(const LaunchCtx &lc, int dim, cx<T> *H, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp);
+template <class T>
+cudaError_t launch_disp_nodal(const LaunchCtx &lc, int dim, const T *uper, T *out, const T *const *ax, const int *n, const double *A);
 }  // namespace mrl
 
 #define CK(call)                                                                                                      \
@@ -271,4 +276,69 @@ extern "C" int mrl_components(mrl_context *ctx, const void *in, void *out, int64
   if (ctx->precision == MRL_F64) CK(launch_components<double>(ctx->lc(), (const double *)in, (double *)out, n, ncomp, to_soa));
   else CK(launch_components<float>(ctx->lc(), (const float *)in, (float *)out, n, ncomp, to_soa));
   return MRL_OK;
+}
+
+extern "C" int mrl_von_mises(mrl_context *ctx, const void *stress, void *out) {
+  if (!ctx || !stress || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_von_mises: bad arguments");
+  if (ctx->dim != 2 && ctx->dim != 3) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_von_mises: Unsupported problem dimension %d", ctx->dim);
+  CK(cudaSetDevice(ctx->device));
+  ctx->launches++;
+  if (ctx->precision == MRL_F64) CK(launch_von_mises<double>(ctx->lc(), ctx->dim, (const double *)stress, (double *)out, ctx->total()));
+  else CK(launch_von_mises<float>(ctx->lc(), ctx->dim, (const float *)stress, (float *)out, ctx->total()));
+  return MRL_OK;
+}
+
+// ComputeDisplacements::computeBuffer (src/tensor_computes/ComputeDisplacements.C:53-107)
+template <class T> static int displacements_impl(mrl_context *ctx, const T *F, T *out) {
+  const int D = ctx->dim, nc = D * D;
+  const long long n = ctx->total();
+  const int ncp = mrl_fftb_pitch(ctx);
+  const size_t vbytes = (size_t)nc * n * sizeof(T);
+  const size_t sbytes = (size_t)nc * ctx->n[0] * (D == 3 ? ctx->n[1] : 1) * ncp * 2 * sizeof(T);
+  void *tmp = nullptr, *spec = nullptr;
+  CK(cudaMalloc(&tmp, vbytes));
+  cudaError_t e = cudaMalloc(&spec, sbytes);
+  if (e != cudaSuccess) {
+    cudaFree(tmp);
+    return mrl_fail(MRL_ERR_CUDA, "mrl_displacements: allocation failed: %s", cudaGetErrorString(e));
+  }
+  auto done = [&](int rc) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    cudaFree(spec);
+    return rc;
+  };
+  // Fbox = <F> (DomainAction::average), H = F - Fbox
+  double Fbox[9], A[9], neg[9];
+  for (int c = 0; c < nc; ++c) {
+    int rc = mrl_reduce(ctx, MRL_SUM, F + (long long)c * n, n, &Fbox[c]);
+    if (rc) return done(rc);
+    Fbox[c] /= (double)n;
+    neg[c] = -Fbox[c];
+    A[c] = Fbox[c] - (c / D == c % D ? 1.0 : 0.0);
+  }
+  if (cudaMemcpyAsync(tmp, F, vbytes, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) return done(mrl_fail(MRL_ERR_CUDA, "copy failed"));
+  ctx->launches++;
+  if (launch_add_const9<T>(ctx->lc(), D, (T *)tmp, neg, n) != cudaSuccess) return done(mrl_fail(MRL_ERR_CUDA, "launch failed"));
+  if (cudaMemsetAsync(spec, 0, sbytes, ctx->stream) != cudaSuccess) return done(mrl_fail(MRL_ERR_CUDA, "memset failed"));
+  int rc = mrl_fftb_forward(ctx, tmp, spec, nc, ncp);
+  if (rc) return done(rc);
+  const T *kx = (const T *)ctx->kaxis_dev[0], *ky = (const T *)ctx->kaxis_dev[1], *kz = (const T *)ctx->kaxis_dev[2];
+  ctx->launches++;
+  if (launch_disp_contract<T>(ctx->lc(), D, (cx<T> *)spec, kx, ky, D == 3 ? kz : ky, ctx->n[0], D == 3 ? ctx->n[1] : 1, ctx->nr[D - 1], ncp) != cudaSuccess)
+    return done(mrl_fail(MRL_ERR_CUDA, "launch failed"));
+  // u_periodic = irfftn of the first D spectra (into tmp)
+  if ((rc = mrl_fftb_inverse(ctx, spec, tmp, D, ncp, 1.0 / (double)n))) return done(rc);
+  const T *ax[3] = {(const T *)ctx->axis_dev[0], (const T *)ctx->axis_dev[1], (const T *)ctx->axis_dev[2]};
+  ctx->launches++;
+  if (launch_disp_nodal<T>(ctx->lc(), D, (const T *)tmp, out, ax, ctx->n, A) != cudaSuccess) return done(mrl_fail(MRL_ERR_CUDA, "launch failed"));
+  return done(MRL_OK);
+}
+
+extern "C" int mrl_displacements(mrl_context *ctx, const void *F, void *out) {
+  if (!ctx || !F || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_displacements: bad arguments");
+  if (ctx->dim != 2 && ctx->dim != 3) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_displacements: Unsupported problem dimension %d", ctx->dim);
+  CK(cudaSetDevice(ctx->device));
+  return ctx->precision == MRL_F64 ? displacements_impl<double>(ctx, (const double *)F, (double *)out)
+                                   : displacements_impl<float>(ctx, (const float *)F, (float *)out);
 }

@@ -965,6 +965,58 @@ class FFTMechanics(Op):
         self.newton_iterations = iiter + 1
 
 
+class ComputeVonMisesStress(Op):
+    """src/tensor_computes/ComputeVonMisesStress.C:30-67 (3-D and 2-D forms as coded)."""
+
+    def __init__(self, problem, buffer, stress="stress"):
+        super().__init__(problem, buffer)
+        self.stress = stress
+
+    def compute(self):
+        s = self.p.buf.get(self.stress)
+        if s is None:
+            return
+        if self.d.dim == 3:
+            t = (s[..., 0, 0] - s[..., 1, 1]) ** 2 + (s[..., 1, 1] - s[..., 2, 2]) ** 2 + (s[..., 2, 2] - s[..., 0, 0]) ** 2
+            t = t + 6 * (s[..., 0, 1] ** 2 + s[..., 1, 2] ** 2 + s[..., 2, 0] ** 2)
+        else:
+            t = (s[..., 0, 0] - s[..., 1, 1]) ** 2 + 6 * s[..., 0, 1] ** 2
+        self.set(torch.sqrt(0.5 * t))
+
+
+class ComputeDisplacements(Op):
+    """src/tensor_computes/ComputeDisplacements.C:53-107: displacement field of a periodic deformation
+    gradient: u = (<F> - I) X + ifft( Hbar q (-i) / |q|^2 ), Hbar = fft(F - <F>), resampled onto the
+    (n+1)^dim nodal grid with (bi/tri)linear interpolation, align_corners = true."""
+
+    def __init__(self, problem, buffer, F):
+        super().__init__(problem, buffer)
+        self.F = F
+
+    def compute(self):
+        d = self.d
+        F = self.p.buf.get(self.F)
+        if F is None:
+            return
+        dm = d.dim
+        I3 = torch.eye(dm, dtype=F.dtype)
+        Fbox = d.average(F)
+        Hbar = d.fft(F - Fbox)
+        q = d.kgrid * (-1j)
+        Q = d.k2
+        numer = torch.einsum("...ij,...j->...i", Hbar, q.to(Hbar.dtype))
+        denom = Q.unsqueeze(-1)
+        u_periodic_bar = torch.where(denom == 0, 0.0, numer / denom)
+        X = torch.stack([d.axis[a].expand(d.shape) for a in range(dm)], -1) if dm > 1 else d.axis[0]
+        u_aff = torch.einsum("ij,...j->...i", Fbox - I3, X)
+        u_periodic = torch.fft.irfftn(u_periodic_bar, s=d.shape, dim=list(range(dm)))
+        shape = [n + 1 for n in d.shape]
+        mode = {1: "linear", 2: "bilinear", 3: "trilinear"}[dm]
+        u = torch.nn.functional.interpolate((u_aff + u_periodic).movedim(-1, 0).unsqueeze(1), size=shape, mode=mode,
+                                            align_corners=True).squeeze(1).movedim(0, -1)
+        self.set(u)
+
+
 # =============================================================================== postprocessors
 def pp_integral(problem, name):
     """src/postprocessors/TensorIntegralPostprocessor.C:28-38: average * domain volume."""

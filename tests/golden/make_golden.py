@@ -157,7 +157,12 @@ def mech3d():
             a = np.frombuffer(blk[k], dtype="<f8").reshape(n, n, n)  # stored [z,y,x]
             F[fr, :, :, :, k // 3, k % 3] = a.transpose(2, 1, 0)
         sV[fr] = np.frombuffer(blk[13], dtype="<f8").reshape(n, n, n).transpose(2, 1, 0)
-    np.savez_compressed(f"{OUT}/mech3d_h5.npz", F=F, sV=sV)
+    # disp_x, disp_y, disp_z: OVERSIZED_NODAL (n+1)^3, stored transposed like the cell data
+    disp = np.zeros((frames, n + 1, n + 1, n + 1, 3))
+    for fr in range(frames):
+        for k in range(3):
+            disp[fr, ..., k] = np.frombuffer(streams[fr * per + 9 + k], dtype="<f8").reshape(n + 1, n + 1, n + 1).transpose(2, 1, 0)
+    np.savez_compressed(f"{OUT}/mech3d_h5.npz", F=F, sV=sV, disp=disp)
     print("mech3d_h5", F.shape)
 
 
@@ -177,7 +182,11 @@ def mech2d():
             a = np.frombuffer(blk[k], dtype="<f8").reshape(n, n)  # stored [y,x]
             F[fr, :, :, k // 2, k % 2] = a.T
         sV[fr] = np.frombuffer(blk[7], dtype="<f8").reshape(n, n).T
-    np.savez_compressed(f"{OUT}/mech2d_h5.npz", F=F, sV=sV)
+    disp = np.zeros((frames, n + 1, n + 1, 2))
+    for fr in range(frames):
+        for k in range(2):
+            disp[fr, ..., k] = np.frombuffer(streams[fr * per + 4 + k], dtype="<f8").reshape(n + 1, n + 1).T
+    np.savez_compressed(f"{OUT}/mech2d_h5.npz", F=F, sV=sV, disp=disp)
     print("mech2d_h5", F.shape)
 
 

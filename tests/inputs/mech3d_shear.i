@@ -69,6 +69,17 @@
       []
     []
   []
+  [Postprocess]
+    [displacements]
+      type = ComputeDisplacements
+      buffer = disp
+      F = F
+    []
+    [vonmises]
+      type = ComputeVonMisesStress
+      buffer = sV
+    []
+  []
 []
 
 [TensorSolver]

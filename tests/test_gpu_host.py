@@ -139,11 +139,15 @@ def test_gradient_input(tmp_path):
 def test_mech3d_input_matches_hdf5_gold(tmp_path):
     """test/tests/mechanics/mech3d.i -> gold/mech3d.h5 (deformation gradient after 3 steps)."""
     g = np.load(f"{G}/mech3d_h5.npz")["F"]
-    run(tmp_path, "mech3d_shear.i", dump=("F",))
+    run(tmp_path, "mech3d_shear.i", dump=("F", "sV", "disp"))
+    disp = np.moveaxis(np.load(f"{G}/mech3d_h5.npz")["disp"][2], -1, 0)   # [Postprocess] ComputeDisplacements, nodal 17^3
+    assert np.abs(field(tmp_path, "disp", (3, 17, 17, 17)) - disp).max() < 1e-10
     F = field(tmp_path, "F", (9, 16, 16, 16))            # rank-two fields are component major
     ref = np.moveaxis(g[2].reshape(16, 16, 16, 9), -1, 0)
     rel = np.linalg.norm(F - ref) / np.linalg.norm(ref)
     assert rel < 1e-9, rel
+    sV = np.load(f"{G}/mech3d_h5.npz")["sV"][2]             # [Postprocess] ComputeVonMisesStress
+    assert np.abs(field(tmp_path, "sV", (16, 16, 16)) - sV).max() < 1e-9 * np.abs(sV).max()
     for k in (1, 2):
         run(tmp_path, "mech3d_shear.i", f"Executioner/num_steps={k}", dump=("F",))
         F = field(tmp_path, "F", (9, 16, 16, 16))
@@ -155,7 +159,11 @@ def test_mech2d_input_matches_hdf5_gold(tmp_path):
     """test/tests/mechanics/mech.i (2-D, 2x2 tensors) -> gold/mech.h5."""
     g = np.load(f"{G}/mech2d_h5.npz")["F"]
     for k in (1, 3):
-        run(tmp_path, "mech2d_shear.i", f"Executioner/num_steps={k}", dump=("F",))
+        run(tmp_path, "mech2d_shear.i", f"Executioner/num_steps={k}", dump=("F", "sV", "disp"))
+        disp = np.moveaxis(np.load(f"{G}/mech2d_h5.npz")["disp"][k - 1], -1, 0)
+        assert np.abs(field(tmp_path, "disp", (2, 33, 33)) - disp).max() < 1e-10
+        sV = np.load(f"{G}/mech2d_h5.npz")["sV"][k - 1]
+        assert np.abs(field(tmp_path, "sV", (32, 32)) - sV).max() < 1e-9 * np.abs(sV).max()
         F = field(tmp_path, "F", (4, 32, 32))
         ref = np.moveaxis(g[k - 1].reshape(32, 32, 4), -1, 0)            # rank-two fields are component major
         assert np.linalg.norm(F - ref) / np.linalg.norm(ref) < 1e-9

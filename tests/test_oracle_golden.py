@@ -91,6 +91,13 @@ def test_mech3d_matches_hdf5_gold():
         F = p.buf["F"].numpy()
         rel = np.linalg.norm(F - g[fr]) / np.linalg.norm(g[fr])
         assert rel < 1e-13, (fr, rel)
+        vm = om.ComputeVonMisesStress(p, "sV")   # [Postprocess] vonmises of mech3d.i
+        vm.compute()
+        sV = np.load(f"{G}/mech3d_h5.npz")["sV"][fr]
+        assert np.abs(p.buf["sV"].numpy() - sV).max() < 1e-12 * max(1.0, np.abs(sV).max())
+        om.ComputeDisplacements(p, "disp", "F").compute()    # [Postprocess] displacements of mech3d.i
+        disp = np.load(f"{G}/mech3d_h5.npz")["disp"][fr]
+        assert np.abs(p.buf["disp"].numpy() - disp).max() < 1e-12
 
 
 def test_mech2d_matches_hdf5_gold():
@@ -103,6 +110,13 @@ def test_mech2d_matches_hdf5_gold():
         F = p.buf["F"].numpy()
         rel = np.linalg.norm(F - g[fr]) / np.linalg.norm(g[fr])
         assert rel < 1e-12, (fr, rel)
+        vm = om.ComputeVonMisesStress(p, "sV")
+        vm.compute()
+        sV = np.load(f"{G}/mech2d_h5.npz")["sV"][fr]
+        assert np.abs(p.buf["sV"].numpy() - sV).max() < 1e-11 * max(1.0, np.abs(sV).max())
+        om.ComputeDisplacements(p, "disp", "F").compute()
+        disp = np.load(f"{G}/mech2d_h5.npz")["disp"][fr]
+        assert np.abs(p.buf["disp"].numpy() - disp).max() < 1e-12
 
 
 def test_rotating_grain_secant_matches_hdf5_gold():
