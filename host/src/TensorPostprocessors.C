@@ -139,6 +139,45 @@ protected:
   Real _critical_dt = 0;
 };
 
+// src/postprocessors/TensorInterfaceVelocityPostprocessor.C:41-65: max over the grid of |du/dt / grad u|
+class TensorInterfaceVelocityPostprocessor : public TensorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Compute the integral over a buffer");
+    params.addParam<Real>("gradient_threshold", 1e-3, "Ignore cells with a gradient component magnitude below this threshold.");
+    return params;
+  }
+  explicit TensorInterfaceVelocityPostprocessor(const InputParameters &p) : TensorPostprocessor(p), _u_old(_tensor_problem.getBufferOld(_buffer_name, 1)) {
+    static const char *const k[3] = {"kx", "ky", "kz"};
+    for (int d = 0; d < 3; ++d) _grad[d].configure(std::string("ubar*") + k[d] + "*i", {"ubar"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+    // `t` carries dt; the threshold is the literal of the reference code (:55), not the parameter
+    _first.configure("v := if(abs(g) > 1e-3, ((u - uo)/t)/g, 0); v*v", {"u", "uo", "g"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+    _next.configure("v := if(abs(g) > 1e-3, ((u - uo)/t)/g, 0); acc + v*v", {"u", "uo", "g", "acc"}, {}, {}, {}, true, MRL_EXPAND_NONE);
+  }
+  void execute() override {
+    if (_u_old.empty() || !_u_old[0].defined()) {
+      _velocity = 0.0;
+      return;
+    }
+    if (!_u.defined()) mooseError("buffer '", _buffer_name, "' is not defined");
+    const Tensor ubar = _domain.fft(_u);
+    const Real dt = _tensor_problem.dt();
+    Tensor vsq;
+    for (unsigned int d = 0; d < _domain.getDim(); ++d) {
+      const Tensor g = _domain.ifft(_grad[d].eval(_domain, {&ubar}, 0.0));
+      vsq = d == 0 ? _first.eval(_domain, {&_u, &_u_old[0], &g}, dt) : _next.eval(_domain, {&_u, &_u_old[0], &g, &vsq}, dt);
+    }
+    _velocity = std::sqrt(_domain.reduce(MRL_MAX, vsq));
+  }
+  Real getValue() const override { return _velocity; }
+
+protected:
+  const std::vector<Tensor> &_u_old;
+  ExprKernel _grad[3], _first, _next;
+  Real _velocity = 0;
+};
+
 // src/postprocessors/ReciprocalIntegral.C:31-52: Re(ubar[0,0,0]) / #cells * volume
 class ReciprocalIntegral : public TensorPostprocessor {
 public:
@@ -198,6 +237,7 @@ protected:
 
 }  // namespace
 
+registerMooseObject("MarlinApp", TensorInterfaceVelocityPostprocessor);
 registerMooseObject("MarlinApp", ReciprocalIntegral);
 registerMooseObject("MarlinApp", ComputeGroupExecutionCount);
 registerMooseObject("MarlinApp", TensorAveragePostprocessor);

@@ -1031,3 +1031,19 @@ def pp_average(problem, name):
 def pp_extreme(problem, name, kind):
     t = problem.buf[name]
     return float(t.min()) if kind == "MIN" else float(t.max())
+
+
+def pp_interface_velocity(problem, name, old):
+    """src/postprocessors/TensorInterfaceVelocityPostprocessor.C:41-65 (`old` = getBufferOld(name, 1);
+    the gradient threshold is the literal 1e-3 of the code, not the parameter)."""
+    if not old or old[0] is None:
+        return 0.0
+    d = problem.domain
+    u = problem.buf[name]
+    du = (u - old[0]) / problem.dt
+    vsq = None
+    for a in range(d.dim):
+        grad = d.ifft(d.fft(u) * d.kaxis[a] * 1j)
+        v = torch.where(torch.abs(grad) > 1e-3, du / grad, 0.0)
+        vsq = v * v if vsq is None else vsq + v * v
+    return math.sqrt(float(torch.max(vsq)))

@@ -110,7 +110,8 @@ def solver_csvs():
                     ("test/tests/gradient/gold/gradient_square_out.csv", "gradient_square_out"),
                     ("test/tests/tensor_compute/gold/backandforth_out.csv", "backandforth_out"),
                     ("test/tests/parsed_tensor/gold/local_vars_derivative_out.csv",
-                     "local_vars_derivative_out")]:
+                     "local_vars_derivative_out"),
+                    ("test/tests/postprocessors/gold/interface_velocity_out.csv", "interface_velocity_out")]:
         if os.path.exists(f"{REF}/{fn}"):
             h, a = read_csv(f"{REF}/{fn}")
             out[key] = a

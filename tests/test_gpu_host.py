@@ -247,6 +247,16 @@ def test_postprocessors_input_matches_csv_golds(tmp_path):
     assert list(col["count"]) == [0.0, 10.0, 20.0] and list(col["time"]) == [0.0, 1.0, 2.0]
 
 
+def test_interface_velocity_input_matches_csv_gold(tmp_path):
+    """test/tests/postprocessors/interface_velocity.i -> gold interface_velocity_out.csv (no solver: the
+    [Solve] computes run every step; history of c through getBufferOld)."""
+    gold = np.load(f"{G}/csv_golds.npz")["interface_velocity_out"]
+    run(tmp_path, "interface_velocity.i")
+    head, rows = csv(f"{tmp_path}/interface_velocity_out.csv")
+    assert head == ["time", "v"] and rows.shape == gold.shape
+    assert np.abs(rows - gold).max() < 1e-10, (rows, gold)
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

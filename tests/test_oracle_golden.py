@@ -1,5 +1,6 @@
 """Pin the oracle against the reference's own gold files (fixtures in tests/golden/,
 extracted by tests/golden/make_golden.py).  CPU only."""
+import math
 import os
 
 import numpy as np
@@ -198,6 +199,22 @@ def test_ch2d_explicit_smooth_matches_exodus_gold(method):
             k = frames.index(step)
             assert np.abs(p.buf["c"].numpy() - g["c"][k]).max() < 1e-10, step
             assert np.abs(p.buf["mu"].numpy() - g["mu"][k]).max() < 1e-10, step
+
+
+def test_interface_velocity_matches_csv_gold():
+    """test/tests/postprocessors/interface_velocity.i: a travelling sine sin(x + 0.2 t); the postprocessor
+    recovers the front velocity 0.2 from du/dt / grad u (gold interface_velocity_out.csv)."""
+    gold = np.load(f"{G}/csv_golds.npz")["interface_velocity_out"]
+    d = om.Domain(2, [10, 2], (0, 0, 0), (4 * math.pi, 1.0, 1.0))
+    p = om.Problem(d)
+    p.computes = [om.ParsedCompute(p, "c", "sin(x+0.2*t)", extra_symbols=True, expand="REAL")]
+    old = p.get_old("c", 1)
+    p.initial()
+    rows = [[0.0, om.pp_interface_velocity(p, "c", old) if "c" in p.buf else 0.0]]
+    for _ in range(10):
+        p.step(0.01)
+        rows.append([p.time, om.pp_interface_velocity(p, "c", old)])
+    assert np.abs(np.array(rows) - gold).max() < 1e-11, (rows, gold)
 
 
 def test_fft_roundtrip_even_odd():
