@@ -163,6 +163,23 @@ protected:
   Real complexNorm(const marlin::Tensor &t) const;
 };
 
+// src/tensor_solver/BroydenSolver.C: implicit Euler, Broyden update of a per-wavevector inverse Jacobian
+class BroydenSolver : public SplitOperatorBase, public IterativeTensorSolverInterface {
+public:
+  static InputParameters validParams();
+  explicit BroydenSolver(const InputParameters &parameters);
+
+protected:
+  void substep() override;
+  Real stackedNorm(const std::vector<marlin::Tensor> &R) const;
+  const unsigned int _max_iterations;
+  const Real _relative_tolerance, _absolute_tolerance;
+  const bool _verbose;
+  const Real _eye_factor;
+  marlin::Tensor _M;  // [n*n][reciprocal points] complex, component major; built at the first substep
+  ExprKernel _res0[2], _res[2];
+};
+
 class ETDRK4Solver : public SplitOperatorBase {
 public:
   static InputParameters validParams();

@@ -725,6 +725,121 @@ void SecantSolver::substep() {
   }
 }
 
+// ========================================================================================== BroydenSolver
+registerMooseObject("MarlinApp", BroydenSolver);
+
+InputParameters BroydenSolver::validParams() {
+  InputParameters params = SplitOperatorBase::validParams();
+  params.addClassDescription("Implicit secant solver time integration.");
+  params.addParam<unsigned int>("substeps", 1, "secant solver substeps per time step.");
+  params.addParam<unsigned int>("max_iterations", 5, "Maximum number of secant solver iteration.");
+  params.addParam<Real>("relative_tolerance", 1e-9, "Convergence tolerance.");
+  params.addParam<Real>("absolute_tolerance", 1e-9, "Convergence tolerance.");
+  params.addParam<Real>("damping", 1.0, "Damping factor for the update step.");
+  params.addParam<Real>("initial_jacobian_guess", 1.0, "Factor for the initial inverse jacobian guess.");
+  params.addParam<Real>("dt_epsilon", 1e-4, "Semi-implicit stable timestep to bootstrap secant solve.");
+  params.addParam<bool>("verbose", false, "Show convergence history.");
+  return params;
+}
+
+BroydenSolver::BroydenSolver(const InputParameters &parameters)
+  : SplitOperatorBase(parameters),
+    _max_iterations(getParam<unsigned int>("max_iterations")),
+    _relative_tolerance(getParam<Real>("relative_tolerance")),
+    _absolute_tolerance(getParam<Real>("absolute_tolerance")),
+    _verbose(getParam<bool>("verbose")),
+    _eye_factor(getParam<Real>("initial_jacobian_guess")) {
+  getVariables(0);
+  if (_variables.size() > 6) paramError("buffer", "The CUDA per-wavevector Broyden update supports at most 6 coupled variables.");
+  // BroydenSolver.C:97 (first residual, u = u_old) and :137 (later residuals); `t` is the sub step
+  const int E = MRL_EXPAND_NONE;
+  _res0[1].configure("(N + L*u)*t", {"N", "L", "u"}, {}, {}, {}, true, E);
+  _res0[0].configure("N*t", {"N"}, {}, {}, {}, true, E);
+  _res[1].configure("(N + L*u)*t + uold - u", {"N", "L", "u", "uold"}, {}, {}, {}, true, E);
+  _res[0].configure("N*t + uold - u", {"N", "u", "uold"}, {}, {}, {}, true, E);
+}
+
+// torch::norm of the stacked residual: sqrt(sum_i sum |R_i|^2)
+Real BroydenSolver::stackedNorm(const std::vector<Tensor> &R) const {
+  double total = 0;
+  for (const Tensor &t : R) {
+    double s = 0;
+    checkC(mrl_reduce(_domain.context(), MRL_SUMSQ, t.data_ptr(), t.numel() * (t.is_complex() ? 2 : 1), &s), "mrl_reduce");
+    total += s;
+  }
+  return std::sqrt(total);
+}
+
+// BroydenSolver.C:69-176, as coded: the step is u + 0.5 sk (`damping` and `dt_epsilon` are read but unused)
+void BroydenSolver::substep() {
+  const auto n = _variables.size();
+  if (!_M.defined()) {
+    // eye(n) * initial_jacobian_guess at every wavevector (:50-63)
+    const size_t pts = size_t(_domain.getNumberOfReciprocalCells());
+    std::vector<double> host(2 * n * n * pts, 0.0);
+    for (std::size_t i = 0; i < n; ++i)
+      for (size_t q = 0; q < pts; ++q) host[2 * ((i * n + i) * pts + q)] = _eye_factor;
+    _M = _domain.fromHost(host, Space::RECIPROCAL, true, int(n * n));
+  }
+  _compute->computeBuffer();
+  forwardBuffers();
+
+  std::vector<Tensor> u_old(n), u(n), R(n), Rnew(n), sk(n), unew(n);
+  auto residual = [&](bool first, std::vector<Tensor> &out) {
+    for (std::size_t i = 0; i < n; ++i) {
+      auto &v = _variables[i];
+      u[i] = v._reciprocal_buffer;
+      const Tensor &N = v._nonlinear_reciprocal;
+      const Tensor *L = v._linear_reciprocal;
+      if (first)
+        out[i] = L ? _res0[1].eval(_domain, {&N, L, &u[i]}, _sub_dt) : _res0[0].eval(_domain, {&N}, _sub_dt);
+      else
+        out[i] = L ? _res[1].eval(_domain, {&N, L, &u[i], &u_old[i]}, _sub_dt) : _res[0].eval(_domain, {&N, &u[i], &u_old[i]}, _sub_dt);
+    }
+  };
+  for (std::size_t i = 0; i < n; ++i) u_old[i] = _variables[i]._reciprocal_buffer;
+  residual(true, R);
+  const Real R0norm = stackedNorm(R);
+
+  std::vector<const void *> pa(n), pb(n), pc(n);
+  std::vector<void *> po0(n), po1(n);
+  for (_iterations = 0; _iterations < _max_iterations; ++_iterations) {
+    const Real Rnorm = stackedNorm(R);
+    if (std::isnan(Rnorm)) mooseError("NAN!");
+    if (_iterations > 4 && Rnorm * 10.0 / _iterations > R0norm) mooseWarning("Diverging residual ", Rnorm, " ", Rnorm * 10.0 / _iterations, ' ', R0norm);
+    if (Rnorm < _absolute_tolerance || Rnorm / R0norm < _relative_tolerance) {
+      if (_verbose) std::cout << "Broyden solve converged after " << _iterations << " iterations. |R|=" << Rnorm << " |R|/|R0|=" << Rnorm / R0norm << '\n';
+      _is_converged = true;
+      return;
+    } else if (_verbose)
+      std::cout << _iterations << " |R|=" << Rnorm << std::endl;
+
+    for (std::size_t i = 0; i < n; ++i) {
+      sk[i] = _domain.empty(Space::RECIPROCAL, true, 1);
+      unew[i] = _domain.empty(Space::RECIPROCAL, true, 1);
+      pa[i] = R[i].data_ptr();
+      pb[i] = u[i].data_ptr();
+      po0[i] = sk[i].data_ptr();
+      po1[i] = unew[i].data_ptr();
+    }
+    checkC(mrl_broyden_step(_domain.context(), (int)n, _M.data_ptr(), pa.data(), pb.data(), po0.data(), po1.data()), "mrl_broyden_step");
+    for (std::size_t i = 0; i < n; ++i) _variables[i]._buffer = _domain.ifft(unew[i]);
+
+    _compute->computeBuffer();
+    forwardBuffers();
+    residual(false, Rnew);
+    for (std::size_t i = 0; i < n; ++i) {
+      pa[i] = sk[i].data_ptr();
+      pb[i] = R[i].data_ptr();
+      pc[i] = Rnew[i].data_ptr();
+    }
+    checkC(mrl_broyden_update(_domain.context(), (int)n, _M.data_ptr(), pa.data(), pb.data(), pc.data()), "mrl_broyden_update");
+    R = Rnew;
+  }
+  std::cerr << "Broyden solve did not converge within the maximum number of iterations.\n";
+  _is_converged = false;
+}
+
 // ========================================================================================== ETDRK4Solver
 registerMooseObject("MarlinApp", ETDRK4Solver);
 

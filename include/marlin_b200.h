@@ -117,6 +117,17 @@ int mrl_ab_update(mrl_context *ctx, void *ubar_dev, const void *cbar_dev, const 
 int mrl_coupled_solve(mrl_context *ctx, int nvar, const void *const *L_real_dev, const void *const *rhs_cplx_dev,
                       void *const *out_cplx_dev, double dt, int drop_imag);
 
+/* Broyden inverse-Jacobian iteration per wavevector (BroydenSolver::substep,
+ * src/tensor_solver/BroydenSolver.C:118-168).  M: nvar*nvar complex reciprocal-space fields,
+ * component major ([r*nvar + c][points]), owned by the caller and kept between calls.
+ *   step  : sk = -M R;  unew = u + 0.5*sk                         (the reference's fixed 0.5)
+ *   update: yk = Rnew - R;  d = sk^T yk;  M += (sk - M yk) sk^T / d  where |d| > 1e-12
+ * nvar <= 6.                                                                                  */
+int mrl_broyden_step(mrl_context *ctx, int nvar, const void *M_cplx_dev, const void *const *R_cplx_dev, const void *const *u_cplx_dev,
+                     void *const *sk_out_dev, void *const *unew_out_dev);
+int mrl_broyden_update(mrl_context *ctx, int nvar, void *M_cplx_dev, const void *const *sk_cplx_dev, const void *const *R_cplx_dev,
+                       const void *const *Rnew_cplx_dev);
+
 /* ---- reductions behind the postprocessors (src/postprocessors/Tensor*Postprocessor.C) --
  * Synchronous: returns the value on the host.                                             */
 enum mrl_reduce_op { MRL_SUM = 0, MRL_MIN = 1, MRL_MAX = 2, MRL_SUMSQ = 3 };

@@ -198,6 +198,21 @@ class Context:
         _ck(lib().mrl_coupled_solve(self.h, n, Lp, bp, op, C.c_double(dt), int(bool(drop_imag))))
         return out
 
+    def broyden_step(self, M, R, u):
+        """sk = -M R, unew = u + 0.5 sk per wavevector; M: [n*n, *rshape] complex (component major)."""
+        n = len(R)
+        sk = [torch.empty_like(r) for r in R]
+        un = [torch.empty_like(r) for r in R]
+        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        _ck(lib().mrl_broyden_step(self.h, n, _p(M), arr(R), arr(u), arr(sk), arr(un)))
+        return sk, un
+
+    def broyden_update(self, M, sk, R, Rnew):
+        """in place: M += (sk - M yk) sk^T / (sk^T yk) where |sk^T yk| > 1e-12, yk = Rnew - R."""
+        n = len(R)
+        arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+        _ck(lib().mrl_broyden_update(self.h, n, _p(M), arr(sk), arr(R), arr(Rnew)))
+
     def reduce(self, op, t):
         assert t.is_contiguous() and t.dtype == self.rdtype
         v = C.c_double()

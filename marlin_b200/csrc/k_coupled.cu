@@ -102,4 +102,125 @@ template cudaError_t launch_coupled_solve<double>(const LaunchCtx &, int, const 
 template cudaError_t launch_coupled_solve<float>(const LaunchCtx &, int, const void *const *, const void *const *, void *const *, double, int,
                                                  long long);
 
+// ------------------------------------------------------------------------------------------ Broyden
+// BroydenSolver (src/tensor_solver/BroydenSolver.C:118-168): per wavevector an NV x NV complex inverse
+// Jacobian estimate M (component-major [NV*NV][points], kept between calls).
+//   step  : sk = -M R;  unew = u + 0.5 sk                                            (:118-128)
+//   update: yk = Rnew - R;  d = sk^T yk (no conjugation);  M += (sk - M yk) sk^T / d  if |d| > 1e-12 (:141-157)
+template <class T, int NV> struct BroydenArgs {
+  cx<T> *M;
+  const cx<T> *a[NV];  // step: R      update: sk
+  const cx<T> *b[NV];  // step: u      update: R
+  const cx<T> *c[NV];  //              update: Rnew
+  cx<T> *o0[NV];       // step: sk
+  cx<T> *o1[NV];       // step: unew
+};
+template <class T> __device__ __forceinline__ cx<T> cmul(cx<T> x, cx<T> y) { return mk<T>(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x); }
+
+template <class T, int NV> __global__ void __launch_bounds__(256) k_broyden_step(BroydenArgs<T, NV> g, long long total) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    cx<T> R[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) R[j] = g.a[j][p];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cx<T> s = mk<T>(T(0), T(0));
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const cx<T> m = cmul(g.M[(long long)(i * NV + j) * total + p], R[j]);
+        s.x += m.x;
+        s.y += m.y;
+      }
+      s = mk<T>(-s.x, -s.y);
+      g.o0[i][p] = s;
+      const cx<T> u = g.b[i][p];
+      g.o1[i][p] = mk<T>(u.x + s.x * T(0.5), u.y + s.y * T(0.5));
+    }
+  }
+}
+
+template <class T, int NV> __global__ void __launch_bounds__(256) k_broyden_update(BroydenArgs<T, NV> g, long long total) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    cx<T> sk[NV], yk[NV];
+    cx<T> d = mk<T>(T(0), T(0));
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      sk[j] = g.a[j][p];
+      const cx<T> r = g.b[j][p], rn = g.c[j][p];
+      yk[j] = mk<T>(rn.x - r.x, rn.y - r.y);
+      const cx<T> m = cmul(sk[j], yk[j]);
+      d.x += m.x;
+      d.y += m.y;
+    }
+    if (!(hypot(d.x, d.y) > T(1e-12))) continue;  // torch::where(abs(denom) > 1e-12, ..., 0)
+    // 1/d (Smith's algorithm is what c10::complex division uses; the quotient below follows it)
+    cx<T> M[NV][NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) M[i][j] = g.M[(long long)(i * NV + j) * total + p];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cx<T> my = mk<T>(T(0), T(0));
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const cx<T> m = cmul(M[i][j], yk[j]);
+        my.x += m.x;
+        my.y += m.y;
+      }
+      const cx<T> w = mk<T>(sk[i].x - my.x, sk[i].y - my.y);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const cx<T> num = cmul(w, sk[j]);
+        cx<T> q;
+        if (fabs(d.x) >= fabs(d.y)) {
+          const T r = d.y / d.x, den = d.x + d.y * r;
+          q = mk<T>((num.x + num.y * r) / den, (num.y - num.x * r) / den);
+        } else {
+          const T r = d.x / d.y, den = d.x * r + d.y;
+          q = mk<T>((num.x * r + num.y) / den, (num.y * r - num.x) / den);
+        }
+        g.M[(long long)(i * NV + j) * total + p] = mk<T>(M[i][j].x + q.x, M[i][j].y + q.y);
+      }
+    }
+  }
+}
+
+template <class T, int NV>
+static cudaError_t broyden_go(const LaunchCtx &lc, int update, void *M, const void *const *a, const void *const *b, const void *const *c,
+                              void *const *o0, void *const *o1, long long total) {
+  BroydenArgs<T, NV> g;
+  g.M = (cx<T> *)M;
+  for (int i = 0; i < NV; ++i) {
+    g.a[i] = (const cx<T> *)a[i];
+    g.b[i] = (const cx<T> *)b[i];
+    g.c[i] = c ? (const cx<T> *)c[i] : nullptr;
+    g.o0[i] = o0 ? (cx<T> *)o0[i] : nullptr;
+    g.o1[i] = o1 ? (cx<T> *)o1[i] : nullptr;
+  }
+  long long gr = (total + 255) / 256;
+  const long long cap = (long long)lc.sm_count * 8;
+  const int grid = (int)(gr < cap ? gr : cap);
+  if (update) k_broyden_update<T, NV><<<grid, 256, 0, lc.stream>>>(g, total);
+  else k_broyden_step<T, NV><<<grid, 256, 0, lc.stream>>>(g, total);
+  return cudaGetLastError();
+}
+template <class T>
+cudaError_t launch_broyden(const LaunchCtx &lc, int nvar, int update, void *M, const void *const *a, const void *const *b,
+                           const void *const *c, void *const *o0, void *const *o1, long long total) {
+  switch (nvar) {
+    case 1: return broyden_go<T, 1>(lc, update, M, a, b, c, o0, o1, total);
+    case 2: return broyden_go<T, 2>(lc, update, M, a, b, c, o0, o1, total);
+    case 3: return broyden_go<T, 3>(lc, update, M, a, b, c, o0, o1, total);
+    case 4: return broyden_go<T, 4>(lc, update, M, a, b, c, o0, o1, total);
+    case 5: return broyden_go<T, 5>(lc, update, M, a, b, c, o0, o1, total);
+    case 6: return broyden_go<T, 6>(lc, update, M, a, b, c, o0, o1, total);
+    default: return cudaErrorNotSupported;
+  }
+}
+template cudaError_t launch_broyden<double>(const LaunchCtx &, int, int, void *, const void *const *, const void *const *, const void *const *,
+                                            void *const *, void *const *, long long);
+template cudaError_t launch_broyden<float>(const LaunchCtx &, int, int, void *, const void *const *, const void *const *, const void *const *,
+                                           void *const *, void *const *, long long);
+
 }  // namespace mrl

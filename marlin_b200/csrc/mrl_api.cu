@@ -568,6 +568,36 @@ extern "C" int mrl_coupled_solve(mrl_context *ctx, int nvar, const void *const *
   return MRL_OK;
 }
 
+namespace mrl {
+template <class T>
+cudaError_t launch_broyden(const LaunchCtx &lc, int nvar, int update, void *M, const void *const *a, const void *const *b,
+                           const void *const *c, void *const *o0, void *const *o1, long long total);
+}
+static int broyden_check(mrl_context *ctx, int nvar, const void *M, const char *who) {
+  if (!ctx || !ctx->dim || !M || nvar < 1) return mrl_fail(MRL_ERR_INVALID, "%s: bad arguments", who);
+  if (nvar > 6) return mrl_fail(MRL_ERR_UNSUPPORTED, "%s: at most 6 coupled variables (got %d)", who, nvar);
+  return MRL_OK;
+}
+extern "C" int mrl_broyden_step(mrl_context *ctx, int nvar, const void *M, const void *const *R, const void *const *u, void *const *sk,
+                                void *const *unew) {
+  int rc = broyden_check(ctx, nvar, M, "mrl_broyden_step");
+  if (rc) return rc;
+  if (!R || !u || !sk || !unew) return mrl_fail(MRL_ERR_INVALID, "mrl_broyden_step: null argument");
+  const long long total = ctx->rtotal();
+  if (ctx->precision == MRL_F64) CKL(ctx, launch_broyden<double>(ctx->lc(), nvar, 0, const_cast<void *>(M), R, u, nullptr, sk, unew, total));
+  else CKL(ctx, launch_broyden<float>(ctx->lc(), nvar, 0, const_cast<void *>(M), R, u, nullptr, sk, unew, total));
+  return MRL_OK;
+}
+extern "C" int mrl_broyden_update(mrl_context *ctx, int nvar, void *M, const void *const *sk, const void *const *R, const void *const *Rnew) {
+  int rc = broyden_check(ctx, nvar, M, "mrl_broyden_update");
+  if (rc) return rc;
+  if (!sk || !R || !Rnew) return mrl_fail(MRL_ERR_INVALID, "mrl_broyden_update: null argument");
+  const long long total = ctx->rtotal();
+  if (ctx->precision == MRL_F64) CKL(ctx, launch_broyden<double>(ctx->lc(), nvar, 1, M, sk, R, Rnew, nullptr, nullptr, total));
+  else CKL(ctx, launch_broyden<float>(ctx->lc(), nvar, 1, M, sk, R, Rnew, nullptr, nullptr, total));
+  return MRL_OK;
+}
+
 extern "C" int mrl_reduce(mrl_context *ctx, int op, const void *in, int64_t count, double *host_out) {
   if (!ctx || !in || !host_out || count < 1 || op < 0 || op > 3) return mrl_fail(MRL_ERR_INVALID, "mrl_reduce: bad arguments");
   CK(cudaSetDevice(ctx->device));

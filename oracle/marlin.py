@@ -685,6 +685,63 @@ class SecantSolver(SplitOperatorSolver):
             self.converged = False
 
 
+class BroydenSolver(SplitOperatorSolver):
+    """src/tensor_solver/BroydenSolver.C:34-176: implicit Euler with a per-wavevector Broyden update of the
+    inverse Jacobian M ([grid..., n, n] complex, kept across substeps and steps).  As coded there: the
+    step is u + 0.5 * sk (the `damping` parameter is not used), `dt_epsilon` is not used, the residual of
+    the first iteration omits u_old - u (it is zero), and the rank-one update uses the plain transpose
+    (no conjugation) with a |denominator| > 1e-12 guard."""
+
+    def __init__(self, problem, root, buffer, reciprocal_buffer, linear_reciprocal, nonlinear_reciprocal,
+                 substeps=1, max_iterations=5, relative_tolerance=1e-9, absolute_tolerance=1e-9,
+                 initial_jacobian_guess=1.0, forward=()):
+        super().__init__(problem, root, buffer, reciprocal_buffer, linear_reciprocal, nonlinear_reciprocal, substeps, 0, forward)
+        self.max_iterations, self.rtol, self.atol = max_iterations, relative_tolerance, absolute_tolerance
+        n = len(self.vars)
+        self.M = (torch.eye(n, dtype=torch.complex128) * initial_jacobian_guess).expand(list(self.d.rshape) + [n, n])
+        self.iterations, self.converged = 0, True
+
+    def _stack(self):
+        b = self.p.buf
+        u = torch.stack([b[v["ubar"]] for v in self.vars], -1)
+        N = torch.stack([b[v["N"]] for v in self.vars], -1)
+        L = torch.stack([b[v["L"]] if v["L"] is not None else torch.zeros(self.d.rshape, dtype=self.d.dtype) for v in self.vars], -1)
+        return u, N, L
+
+    def substep(self):
+        p, d = self.p, self.d
+        dt = p.sub_dt
+        self.root.compute()
+        self.forward_buffers()
+        u_old = torch.stack([p.buf[v["ubar"]] for v in self.vars], -1)
+        u, N, L = self._stack()
+        R = (N + L * u) * dt
+        R0 = float(torch.linalg.norm(R))
+        it = 0
+        while it < self.max_iterations:
+            Rnorm = float(torch.linalg.norm(R))
+            if math.isnan(Rnorm):
+                raise RuntimeError("NAN!")
+            if Rnorm < self.atol or Rnorm / R0 < self.rtol:
+                self.iterations, self.converged = it, True
+                return
+            sk = -torch.matmul(self.M, R.unsqueeze(-1))
+            skT = sk.squeeze(-1).unsqueeze(-2)
+            u_out = torch.unbind(u + sk.squeeze(-1) * 0.5, -1)
+            for i, v in enumerate(self.vars):
+                p.buf[v["u"]] = d.ifft(u_out[i])
+            self.root.compute()
+            self.forward_buffers()
+            u, N, L = self._stack()
+            Rnew = (N + L * u) * dt + u_old - u
+            yk = (Rnew - R).unsqueeze(-1)
+            denom = torch.matmul(skT, yk)
+            self.M = self.M + torch.where(torch.abs(denom) > 1e-12, torch.matmul(sk - torch.matmul(self.M, yk), skT) / denom, 0.0)
+            R = Rnew
+            it += 1
+        self.iterations, self.converged = it, False
+
+
 class ForwardEulerSolver(TensorSolver):
     """src/tensor_solver/ForwardEulerSolver.C:29-38 (variables may be empty: mechanics)."""
 

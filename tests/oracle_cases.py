@@ -219,3 +219,19 @@ def ch_explicit_problem(n=50, L=3.0, substeps=50, smooth=None):
     ])
     p.solver = om.ForwardEulerSolver(p, root, ["c"], ["cbar"], ["dc_dt_bar"], substeps=substeps)
     return p
+
+
+def broyden_problem(n=32):
+    """tests/inputs/broyden_coupled.i: two coupled Allen-Cahn-type fields, BroydenSolver."""
+    L = 2 * math.pi
+    d = om.Domain(2, [n, n], (0, 0, 0), (L, L, 1.0))
+    p = om.Problem(d)
+    p.ics = [om.ParsedCompute(p, "u", "0.5+0.1*sin(x)*sin(y)", extra_symbols=True, expand="REAL"),
+             om.ParsedCompute(p, "v", "0.4+0.1*cos(x)*cos(2*y)", extra_symbols=True, expand="REAL"),
+             om.ReciprocalLaplacianFactor(p, "Lu", 0.1), om.ReciprocalLaplacianFactor(p, "Lv", 0.05)]
+    root = om.Group(p, [om.ForwardFFT(p, "ub", "u"), om.ForwardFFT(p, "vb", "v"),
+                        om.ParsedCompute(p, "fu", "-(u^3-u) - 0.3*v", inputs=["u", "v"]), om.ForwardFFT(p, "fub", "fu"),
+                        om.ParsedCompute(p, "fv", "-(v^3-v) - 0.3*u", inputs=["u", "v"]), om.ForwardFFT(p, "fvb", "fv")])
+    p.solver = om.BroydenSolver(p, root, ["u", "v"], ["ub", "vb"], ["Lu", "Lv"], ["fub", "fvb"], substeps=2, max_iterations=12,
+                                relative_tolerance=0.0, absolute_tolerance=0.0)
+    return p

@@ -257,6 +257,24 @@ def test_interface_velocity_input_matches_csv_gold(tmp_path):
     assert np.abs(rows - gold).max() < 1e-10, (rows, gold)
 
 
+def test_broyden_input_matches_oracle(tmp_path):
+    """BroydenSolver (src/tensor_solver/BroydenSolver.C; no gold file in the reference) through the host
+    objects (mrl_broyden_step / mrl_broyden_update) vs the oracle's restatement, two steps of two substeps.
+    The kernels themselves are checked at round-off level in test_gpu_parity.py; the trajectory is not
+    round-off stable (rank-one updates divide by sk.yk down to the 1e-12 guard, and yk = Rnew - R cancels),
+    so two correct implementations agree to ~1e-7 here, not to 1e-10."""
+    run(tmp_path, "broyden_coupled.i", dump=("u", "v"))
+    p = oc.broyden_problem()
+    p.initial()
+    for _ in range(2):
+        p.step(0.05)
+        assert p.solver.iterations == 12          # fixed iteration count (tolerances 0 in the input)
+    for k in ("u", "v"):
+        ref = p.buf[k].numpy()
+        got = field(tmp_path, k, (32, 32))
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-6, k
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

@@ -325,6 +325,36 @@ def test_staged_transfers_pipeline_matches_plain_path(ctx):
     plan.close()
 
 
+@pytest.mark.parametrize("nvar", [1, 2, 5])
+def test_broyden_kernels_match_torch(ctx, nvar):
+    """mrl_broyden_step / mrl_broyden_update against the torch expressions of BroydenSolver.C:118-157
+    (matmul with the plain transpose, |denominator| > 1e-12 guard) on the same data."""
+    shape = (12, 10, 9)
+    ctx.domain_set(3, shape, (0,) * 3, (1.0,) * 3)
+    rs = (12, 10, 5)
+    torch.manual_seed(70 + nvar)
+    cplx = lambda *sh: torch.randn(*sh, dtype=torch.complex128)
+    M = cplx(*rs, nvar, nvar)
+    R, Rnew, u = cplx(*rs, nvar), cplx(*rs, nvar), cplx(*rs, nvar)
+    R[0, 0, 0] = Rnew[0, 0, 0]          # yk = 0 there: denominator 0, the update must be skipped
+    sk_ref = -torch.matmul(M, R.unsqueeze(-1))
+    unew_ref = u + sk_ref.squeeze(-1) * 0.5
+    yk = (Rnew - R).unsqueeze(-1)
+    skT = sk_ref.squeeze(-1).unsqueeze(-2)
+    denom = torch.matmul(skT, yk)
+    M_ref = M + torch.where(torch.abs(denom) > 1e-12, torch.matmul(sk_ref - torch.matmul(M, yk), skT) / denom, 0.0)
+    Md = M.permute(3, 4, 0, 1, 2).reshape(nvar * nvar, *rs).contiguous().cuda()
+    split = lambda t: [t[..., i].contiguous().cuda() for i in range(nvar)]
+    sk, unew = ctx.broyden_step(Md, split(R), split(u))
+    for i in range(nvar):
+        assert rel_l2(torch.view_as_real(sk[i].cpu()), torch.view_as_real(sk_ref[..., i, 0].contiguous())) < 1e-13
+        assert rel_l2(torch.view_as_real(unew[i].cpu()), torch.view_as_real(unew_ref[..., i].contiguous())) < 1e-13
+    ctx.broyden_update(Md, sk, split(R), split(Rnew))
+    got = Md.cpu().reshape(nvar, nvar, *rs).permute(2, 3, 4, 0, 1)
+    assert rel_l2(torch.view_as_real(got.contiguous()), torch.view_as_real(M_ref.contiguous())) < 1e-11
+    assert torch.equal(got[0, 0, 0], M[0, 0, 0])
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_512_properties(ctx):
     """At BASELINE's 512^3 the oracle is too slow for a test; check size-independent
