@@ -128,6 +128,7 @@ public:
 
 private:
   std::map<std::string, ParsedFunctionDesc> _functions;
+  std::set<std::string> _extra_observed;
 
 public:
 
@@ -143,6 +144,9 @@ public:
 
   // names of buffers read by postprocessors / outputs (a fused solver must keep those materialised)
   std::set<std::string> observedBuffers() const;
+  // buffers an output object (or the driver's --dump) reads: they must stay materialised when a solver
+  // fuses the computes that produce them
+  void observeBuffer(const std::string &name) { _extra_observed.insert(name); }
 
 private:
   const DomainAction &_domain;

@@ -319,6 +319,13 @@ void MarlinApp::transient() {
     std::cerr << "\n";
   }
 
+  for (const auto &name : _opt.dump) _problem->observeBuffer(name);
+  // [TensorOutputs] are not written by this driver, but the buffers they name are part of the run's
+  // observable state: keep them materialised
+  if (const hit::Node *to = _root->find("TensorOutputs"))
+    for (hit::Node *o : to->sections())
+      if (const hit::Node *b = o->field("buffer"))
+        for (const auto &name : shim_detail::Conv<std::vector<std::string>>::from(b->value, o->fullpath() + "/buffer")) _problem->observeBuffer(name);
   _problem->init();
   if (_opt.check_only) {
     std::cout << "Syntax OK\n";

@@ -73,7 +73,7 @@ Real TensorProblem::getConstant(const std::string &name_or_number, const std::st
 void TensorProblem::setSolver(std::shared_ptr<TensorSolver> solver) { _solver = std::move(solver); }
 
 std::set<std::string> TensorProblem::observedBuffers() const {
-  std::set<std::string> out;
+  std::set<std::string> out = _extra_observed;
   for (const auto &pp : _postprocessors) out.insert(pp->bufferName());
   for (const auto &pp : _pps)
     for (const auto &n : pp->getRequestedItems()) out.insert(n);

@@ -281,10 +281,14 @@ void AdamsBashforthMoulton::tryBuildFusedPlans() {
       used.insert(prod);
       const auto &in = prod->kernel().inputs();
       if (in.size() != 2 || !prod->kernel().derivatives().empty()) return note("nonlinear term is not a two-factor product");
-      const std::string s = prod->kernel().simplified();
+      // toString() of a product is "(a * b)": compare without blanks and the enclosing parentheses
+      std::string s;
+      for (char ch : prod->kernel().simplified())
+        if (ch != ' ') s += ch;
+      if (s.size() > 2 && s.front() == '(' && s.back() == ')' && s.find('(', 1) == std::string::npos) s = s.substr(1, s.size() - 2);
       int which = -1;
-      if (s == in[0] + " * " + in[1] || s == in[0] + "*" + in[1]) which = 0;
-      if (s == in[1] + " * " + in[0] || s == in[1] + "*" + in[0]) which = 1;
+      if (s == in[0] + "*" + in[1]) which = 0;
+      if (s == in[1] + "*" + in[0]) which = 1;
       if (which < 0) return note("nonlinear term '" + s + "' is not a plain product of its inputs");
       // one factor is the transformed nonlinearity, the other an IC-time mobility
       for (int a = 0; a < 2 && !gfft; ++a) {

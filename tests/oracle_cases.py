@@ -235,3 +235,41 @@ def broyden_problem(n=32):
     p.solver = om.BroydenSolver(p, root, ["u", "v"], ["ub", "vb"], ["Lu", "Lv"], ["fub", "fvb"], substeps=2, max_iterations=12,
                                 relative_tolerance=0.0, absolute_tolerance=0.0)
     return p
+
+
+BM2_FCHEM = ("fa:=rho^2*(c-ca)^2; fb:=rho^2*(cb-c)^2; h:=n1^3*(6*n1^2-15*n1+10) + n2^3*(6*n2^2-15*n2+10) + "
+             "n3^3*(6*n3^2-15*n3+10) + n4^3*(6*n4^2-15*n4+10); g:=n1^2*(1-n1)^2 + n2^2*(1-n2)^2 + n3^2*(1-n3)^2 + "
+             "n4^2*(1-n4)^2 + alpha*(n1^2*n2^2 + n1^2*n3^2 + n1^2*n4^2 + n2^2*n1^2 + n2^2*n3^2 + n2^2*n4^2 + n3^2*n1^2 + "
+             "n3^2*n2^2 + n3^2*n4^2 + n4^2*n1^2 + n4^2*n2^2 + n4^2*n3^2); (fa*(1-h) + fb*h + w*g)")
+BM2_NIC = ("epsilon*(cos((0.01*idx)*x-4)*cos((0.007+0.01*idx)*y) +cos((0.11+0.01*idx)*x)*cos((0.11+0.01*idx)*y) "
+           "+psi*(cos((0.046+0.001*idx)*x+(0.0405+0.001*idx)*y) *cos((0.031+0.001*idx)*x-(0.004+0.001*idx)*y))^2)^2")
+
+
+def bm2_problem(n=200, substeps=2000):
+    """benchmarks/02_oswald_ripening/2a.i (PFHub benchmark 2a, BASELINE.json configs[2])."""
+    d = om.Domain(2, [n, n], (0, 0, 0), (200.0, 200.0, 1.0))
+    p = om.Problem(d)
+    cn, cv = ["rho", "ca", "cb", "alpha", "w", "L", "M"], ["sqrt(2)", "0.3", "0.7", "5", "1", "5", "5"]
+    ns = ["n1", "n2", "n3", "n4"]
+    p.ics = [om.ParsedCompute(p, "c", "c0+epsilon*(cos(0.105*x)*cos(0.11*y)+(cos(0.13*x)*cos(0.087*y))^2+"
+                                      "cos(0.025*x-0.15*y)*cos(0.07*x-0.02*y))", extra_symbols=True,
+                              constant_names=["c0", "epsilon"], constant_expressions=["0.5", "0.01"]),
+             om.ReciprocalLaplacianFactor(p, "Lbar", 1.0),
+             om.ReciprocalLaplacianSquareFactor(p, "MkappaL2bar", -15.0),
+             om.ReciprocalLaplacianFactor(p, "kappaLbar", 15.0)]
+    for k, nm in enumerate(ns):
+        p.ics.append(om.ParsedCompute(p, nm, BM2_NIC, extra_symbols=True, constant_names=["idx", "epsilon", "psi"],
+                                      constant_expressions=[str(k + 1), "0.1", "1.5"]))
+    allv = ["c"] + ns
+    ops = [om.ParsedCompute(p, "mu_c", f"{BM2_FCHEM}*M", inputs=allv, derivatives=["c"], constant_names=cn, constant_expressions=cv)]
+    ops += [om.ParsedCompute(p, f"mu_{nm}", f"{BM2_FCHEM}*(-L)", inputs=allv, derivatives=[nm], constant_names=cn,
+                             constant_expressions=cv) for nm in ns]
+    ops += [om.ForwardFFT(p, f"mu_{nm}_bar", f"mu_{nm}") for nm in allv]
+    ops += [om.ParsedCompute(p, "Mbar_mu_c_bar", "Lbar*mu_c_bar", inputs=["Lbar", "mu_c_bar"])]
+    ops += [om.ForwardFFT(p, f"{nm}_bar", nm) for nm in allv]
+    root = om.Group(p, ops)
+    p.solver = om.AdamsBashforthMoulton(p, root, allv, [f"{nm}_bar" for nm in allv],
+                                        ["MkappaL2bar"] + ["kappaLbar"] * 4,
+                                        ["Mbar_mu_c_bar"] + [f"mu_{nm}_bar" for nm in ns], substeps=substeps,
+                                        predictor_order=2, corrector_order=2, corrector_steps=0)
+    return p

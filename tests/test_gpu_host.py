@@ -275,6 +275,45 @@ def test_broyden_input_matches_oracle(tmp_path):
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-6, k
 
 
+def test_bm2_ostwald_input_matches_oracle(tmp_path):
+    """benchmarks/02_oswald_ripening/2a.i (PFHub BM2a, BASELINE.json configs[2]: five coupled fields, parsed free
+    energy with let-bindings and symbolic derivatives, IterationAdaptiveDT growth 1.1) through the host objects vs
+    the oracle: 3 steps x 50 substeps (the first step at AB1 by quirk Q1, order reset on every dt change by Q2),
+    rel L2 <= 1e-10 per field."""
+    run(tmp_path, "bm2_ostwald.i", "TensorSolver/substeps=50", "Executioner/num_steps=3", dump=("c", "n1", "n2", "n3", "n4", "F"))
+    p = oc.bm2_problem(substeps=50)
+    p.initial()
+    dt = 0.001
+    for _ in range(3):
+        p.step(dt)
+        dt *= 1.1
+    for k in ("c", "n1", "n2", "n3", "n4"):
+        ref = p.buf[k].numpy()
+        got = field(tmp_path, k, (200, 200))
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-10, k
+    head, rows = csv(f"{tmp_path}/bm2_ostwald.csv")
+    assert head == ["time", "F", "max_c", "min_c"]
+    assert abs(rows[-1, 2] - float(p.buf["c"].max())) < 1e-12 and abs(rows[-1, 3] - float(p.buf["c"].min())) < 1e-12
+
+
+def test_solver_fuses_canonical_inputs_and_matches_unfused(tmp_path):
+    """The AdamsBashforthMoulton host object recognises the canonical split-operator compute graph and
+    replaces it by the fused CUDA plan (reported with Problem/print_debug_output=true); `fuse=false` keeps
+    the operator-by-operator path.  Both give the same fields."""
+    args = ("Domain/dim=3", "Domain/nx=32", "Domain/ny=32", "Domain/nz=32", "Domain/zmax=3", "Executioner/num_steps=2",
+            "Problem/print_debug_output=true")
+    r = run(tmp_path, "ch2d_gold.i", *args, dump=("c",))
+    assert "fused five-pass plan" in r.stderr + r.stdout, (r.stderr + r.stdout)[-2000:]
+    fused = field(tmp_path, "c", (32, 32, 32)).copy()
+    r = run(tmp_path, "ch2d_gold.i", *args, "TensorSolver/fuse=false", dump=("c",))
+    assert "operator-by-operator path" in r.stderr + r.stdout
+    plain = field(tmp_path, "c", (32, 32, 32))
+    assert np.linalg.norm(fused - plain) / np.linalg.norm(plain) < 1e-12
+    # PFHub BM2a: five coupled variables, compiled nonlinearities with symbolic derivatives
+    r = run(tmp_path, "bm2_ostwald.i", "TensorSolver/substeps=5", "Executioner/num_steps=1", "Problem/print_debug_output=true")
+    assert "fused five-pass plan" in r.stderr + r.stdout, (r.stderr + r.stdout)[-2000:]
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""
