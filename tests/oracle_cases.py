@@ -273,3 +273,21 @@ def bm2_problem(n=200, substeps=2000):
                                         ["Mbar_mu_c_bar"] + [f"mu_{nm}_bar" for nm in ns], substeps=substeps,
                                         predictor_order=2, corrector_order=2, corrector_steps=0)
     return p
+
+
+def bm1_problem(n=200, substeps=1000):
+    """benchmarks/01_spinodal_decomposition/1a_solver.i (PFHub benchmark 1a, BASELINE.json configs[1])."""
+    d = om.Domain(2, [n, n], (0, 0, 0), (200.0, 200.0, 1.0))
+    p = om.Problem(d)
+    cn, cv = ["rho_s", "c_alpha", "c_beta"], ["5", "0.3", "0.7"]
+    p.ics = [om.ParsedCompute(p, "c", "c0+epsilon*(cos(0.105*x)*cos(0.11*y)+(cos(0.13*x)*cos(0.087*y))^2+"
+                                      "cos(0.025*x-0.15*y)*cos(0.07*x-0.02*y))", extra_symbols=True,
+                              constant_names=["c0", "epsilon"], constant_expressions=["0.5", "0.01"]),
+             om.ReciprocalLaplacianFactor(p, "Mbar", 5.0), om.ReciprocalLaplacianSquareFactor(p, "kappabarbar", -10.0)]
+    root = om.Group(p, [om.ParsedCompute(p, "mu", "rho_s*(c-c_alpha)^2*(c_beta-c)^2", inputs=["c"], derivatives=["c"],
+                                         constant_names=cn, constant_expressions=cv),
+                        om.ForwardFFT(p, "mubar", "mu"),
+                        om.ParsedCompute(p, "Mbarmubar", "Mbar*mubar", inputs=["Mbar", "mubar"]),
+                        om.ForwardFFT(p, "cbar", "c")])
+    p.solver = om.AdamsBashforthMoulton(p, root, ["c"], ["cbar"], ["kappabarbar"], ["Mbarmubar"], substeps=substeps)
+    return p

@@ -275,6 +275,32 @@ def test_broyden_input_matches_oracle(tmp_path):
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-6, k
 
 
+def test_bm1_spinodal_input_matches_oracle(tmp_path):
+    """benchmarks/01_spinodal_decomposition/1a_solver.i (PFHub BM1a, BASELINE.json configs[1]) through the host objects
+    (fused plan) vs the oracle: 3 steps x 1000 substeps, dt = 1, 1.1, 1.21; rel L2 <= 1e-10; free energy and extrema
+    from the CSV."""
+    r = run(tmp_path, "bm1_spinodal.i", "Executioner/num_steps=3", "Problem/print_debug_output=true", dump=("c",))
+    assert "fused five-pass plan" in r.stderr + r.stdout
+    p = oc.bm1_problem()
+    p.initial()
+    dt = 1.0
+    for _ in range(3):
+        p.step(dt)
+        dt *= 1.1
+    ref = p.buf["c"].numpy()
+    got = field(tmp_path, "c", (200, 200))
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-10
+    fg = om.FFTGradientSquare(p, "Fgrad", "c", 1.0)
+    fg.compute()
+    F = om.ParsedCompute(p, "F", "rho_s * (c-c_alpha)^2 * (c_beta-c)^2 + Fgrad", inputs=["c", "Fgrad"],
+                         constant_names=["rho_s", "c_alpha", "c_beta"], constant_expressions=["5", "0.3", "0.7"])
+    F.compute()
+    head, rows = csv(f"{tmp_path}/bm1_spinodal.csv")
+    assert head == ["time", "F", "change", "max_c", "min_c"]
+    assert abs(rows[-1, 1] - om.pp_integral(p, "F")) < 1e-9 * abs(rows[-1, 1])
+    assert abs(rows[-1, 3] - float(p.buf["c"].max())) < 1e-11 and abs(rows[-1, 4] - float(p.buf["c"].min())) < 1e-11
+
+
 def test_bm2_ostwald_input_matches_oracle(tmp_path):
     """benchmarks/02_oswald_ripening/2a.i (PFHub BM2a, BASELINE.json configs[2]: five coupled fields, parsed free
     energy with let-bindings and symbolic derivatives, IterationAdaptiveDT growth 1.1) through the host objects vs
