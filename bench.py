@@ -246,6 +246,55 @@ def mechanics_bench(n=256, peak=None):
     return out
 
 
+def bm1_bench():
+    """BASELINE.json configs[1]: PFHub BM1a (benchmarks/01_spinodal_decomposition/1a_solver.i, 200^2 fp64, AB2,
+    1000 substeps per step).  A field is 0.3 MB, so the substep is launch bound: the figure is microseconds per
+    substep, with the steady-state sequence replayed from a CUDA graph (mrl_split_substeps) and launched one by
+    one, next to the libTorch CPU oracle on a bounded sample."""
+    import torch
+    from marlin_b200 import capi
+    from marlin_b200.capi import AB_BETA
+    n, L = 200, 200.0
+    out = {"workload": "BM1a-2D-200: benchmarks/01_spinodal_decomposition/1a_solver.i, AB2 steady state"}
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ctx = capi.Context(0, capi.F64)
+        ctx.use_torch_stream()
+        ctx.domain_set(2, (n, n), (0, 0), (L, L))
+        ax = [ctx.axis(a).cuda() for a in range(2)]
+        x, y = ax[0].view(n, 1), ax[1].view(1, n)
+        c = (0.5 + 0.01 * (torch.cos(0.105 * x) * torch.cos(0.11 * y) + (torch.cos(0.13 * x) * torch.cos(0.087 * y)) ** 2 +
+                           torch.cos(0.025 * x - 0.15 * y) * torch.cos(0.07 * x - 0.02 * y))).contiguous()
+        plan = ctx.split_plan(double_well=(5.0, 0.3, 0.7), M_factor=5.0, L_factor=-10.0, history=1)
+        plan.substep(c, 1e-3, AB_BETA[0], 0)
+        plan.advance_state()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for key, fn in (("graph", lambda k: plan.substeps(c, 1e-3, AB_BETA[1], 1, k)),
+                        ("launches", lambda k: [(plan.substep(c, 1e-3, AB_BETA[1], 1), plan.advance_state()) for _ in range(k)])):
+            fn(200)
+            side.synchronize()
+            e0.record()
+            fn(2000)
+            e1.record()
+            side.synchronize()
+            out[f"us_per_substep_{key}"] = round(e0.elapsed_time(e1) / 2000 * 1e3, 2)
+        out["launches_per_substep"] = 3
+        plan.close()
+        ctx.close()
+    try:
+        import oracle_cases as oc
+        p = oc.bm1_problem(substeps=100)
+        p.initial()
+        p.step(1.0)
+        t0 = time.perf_counter()
+        p.step(1.0)
+        out["cpu_oracle_us_per_substep"] = round((time.perf_counter() - t0) / 100 * 1e6, 1)
+    except Exception as ex:
+        out["cpu_oracle_us_per_substep"] = None
+        print(f"# BM1a cpu sample skipped: {ex}", file=sys.stderr)
+    return out
+
+
 def run_ours(args, rank, world):
     import torch
     from marlin_b200 import capi
@@ -375,6 +424,12 @@ def run_ours(args, rank, world):
         mech = None
         print(f"# mechanics measurement skipped: {ex}", file=sys.stderr)
 
+    try:
+        bm1 = bm1_bench()
+    except Exception as ex:
+        bm1 = None
+        print(f"# BM1a measurement skipped: {ex}", file=sys.stderr)
+
     cpu = None
     if not args.no_cpu:
         p, ostep = oracle_substep_fn(n)
@@ -404,6 +459,7 @@ def run_ours(args, rank, world):
         "cpu_baseline": cpu,
         "libtorch_cuda_ms_per_step": cufft_ms,
         "mechanics": mech,
+        "bm1a_2d": bm1,
     }
     print(json.dumps(line), flush=True)
     ctx.close()

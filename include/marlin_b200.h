@@ -224,6 +224,11 @@ int mrl_split_substep(mrl_split_plan *plan, void *c_real_dev, double dt, const d
  * evaluates the whole root compute (every variable's nonlinearity, from the OLD fields) before it
  * updates any variable, so call mrl_split_forward (passes P1-P2) on every plan first, then
  * mrl_split_finish (P3-P5, writes c) on every plan.                                          */
+/* `count` substeps, each followed by mrl_split_advance_state, all with the same dt / beta / nold
+ * (the steady state inside one MOOSE step of TensorSolver::computeBuffer, TensorSolver.C:93-110).
+ * On a capturable stream the periodic part runs as a replayed CUDA graph (small grids are launch bound).
+ * Results are identical to calling mrl_split_substep + mrl_split_advance_state `count` times.        */
+int mrl_split_substeps(mrl_split_plan *plan, void *c_real_dev, double dt, const double *beta, int nold, int count);
 int mrl_split_forward(mrl_split_plan *plan, const void *c_real_dev);
 int mrl_split_finish(mrl_split_plan *plan, void *c_real_dev, double dt, const double *beta, int nold);
 /* sub-time `t` seen by an MRL_NONLIN_EXPR expression (TensorSolver.C:95, _sub_time) */

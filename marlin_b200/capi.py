@@ -260,6 +260,12 @@ class SplitPlan:
         b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
         _ck(lib().mrl_split_substep(self.h, _p(c), C.c_double(dt), b, int(nold)))
 
+    def substeps(self, c, dt, beta, nold, count):
+        """`count` x (substep + advance_state) with fixed dt / beta / nold; the periodic part is replayed
+        from a CUDA graph when the context runs on a capturable (non-default) stream."""
+        b = (C.c_double * 5)(*(list(beta) + [0.0] * 5)[:5])
+        _ck(lib().mrl_split_substeps(self.h, _p(c), C.c_double(dt), b, int(nold), int(count)))
+
     def forward(self, c):
         _ck(lib().mrl_split_forward(self.h, _p(c)))
 

@@ -41,7 +41,7 @@ cudaError_t launch_fused(const LaunchCtx &lc, const FusedIO<T> &io, const Spectr
 #undef X
     default: break;
   }
-  switch (gen_tk<T>(plan.n, 3)) {
+  switch (gen_tk_for<T>(plan.n, 3, (long long)(io.nouter > 0 ? io.nouter : 1) * io.ncols, lc.sm_count)) {
     case 8: return fused_gen<T, 8>(lc, io, up, tw, plan);
     case 4: return fused_gen<T, 4>(lc, io, up, tw, plan);
     case 2: return fused_gen<T, 2>(lc, io, up, tw, plan);

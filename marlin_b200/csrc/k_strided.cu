@@ -39,7 +39,7 @@ cudaError_t launch_strided(const LaunchCtx &lc, const StridedIO<T> &io, const cx
 #undef X
     default: break;
   }
-  switch (gen_tk<T>(plan.n, 2)) {
+  switch (gen_tk_for<T>(plan.n, 2, (long long)io.nfields * io.nouter * io.ncols, lc.sm_count)) {
     case 8: return strided_gen<T, 8>(lc, io, tw, plan);
     case 4: return strided_gen<T, 4>(lc, io, tw, plan);
     case 2: return strided_gen<T, 2>(lc, io, tw, plan);

@@ -44,7 +44,7 @@ static cudaError_t zfwd_any(const LaunchCtx &lc, const LD &ld, const ST &st, con
 #undef X
     default: break;
   }
-  switch (gen_tk<T>(plan.n, 2)) {
+  switch (gen_tk_for<T>(plan.n, 2, npencils, lc.sm_count)) {
     case 8: return zfwd_gen<T, 8, LD, ST>(lc, ld, st, tw, plan, npencils);
     case 4: return zfwd_gen<T, 4, LD, ST>(lc, ld, st, tw, plan, npencils);
     case 2: return zfwd_gen<T, 2, LD, ST>(lc, ld, st, tw, plan, npencils);
@@ -99,7 +99,7 @@ cudaError_t launch_zinv_pairs(const LaunchCtx &lc, const cx<T> *in, T *out, long
 #undef X
     default: break;
   }
-  switch (gen_tk<T>(plan.n, 2)) {
+  switch (gen_tk_for<T>(plan.n, 2, npencils, lc.sm_count)) {
     case 8: return zinv_gen<T, 8>(lc, ld, st, tw, plan, npencils);
     case 4: return zinv_gen<T, 4>(lc, ld, st, tw, plan, npencils);
     case 2: return zinv_gen<T, 2>(lc, ld, st, tw, plan, npencils);

@@ -673,6 +673,7 @@ extern "C" int mrl_split_plan_create(mrl_context *ctx, const mrl_split_desc *d, 
 extern "C" int mrl_split_plan_destroy(mrl_split_plan *p) {
   if (!p) return MRL_OK;
   mrl_quiesce(p->ctx);
+  if (p->graph) cudaGraphExecDestroy(p->graph);
   cudaFree(p->A);
   for (void *q : p->ring) cudaFree(q);
   delete p;
@@ -839,6 +840,71 @@ extern "C" int mrl_split_substep(mrl_split_plan *p, void *c, double dt, const do
   CK(cudaSetDevice(p->ctx->device));
   return p->ctx->precision == MRL_F64 ? split_substep_impl<double>(p, (double *)c, dt, beta, nold)
                                       : split_substep_impl<float>(p, (float *)c, dt, beta, nold);
+}
+
+// `count` substeps, each followed by mrl_split_advance_state, with the same dt / beta / nold (the steady
+// state of AdamsBashforthMoulton inside one MOOSE step).  On small grids a substep is a handful of
+// microsecond-sized kernels and the launch gaps dominate: one period of the sequence (the ring of old
+// nonlinear terms repeats after history+1 substeps) is captured as a CUDA graph and replayed.
+extern "C" int mrl_split_substeps(mrl_split_plan *p, void *c, double dt, const double *beta, int nold, int count) {
+  if (!p || !c || !beta || nold < 0 || count < 0) return mrl_fail(MRL_ERR_INVALID, "mrl_split_substeps: bad arguments");
+  mrl_context *ctx = p->ctx;
+  CK(cudaSetDevice(ctx->device));
+  const int period = p->desc.history + 1;
+  auto one = [&]() -> int {
+    int rc = mrl_split_substep(p, c, dt, beta, nold);
+    if (rc) return rc;
+    return mrl_split_advance_state(p, nullptr);
+  };
+  static const bool use_graph = !getenv("MRL_NO_GRAPH");
+  int done = 0;
+  // graphs need a capturable (non-legacy) stream, a full ring, and enough substeps to amortise the capture
+  if (use_graph && ctx->stream != nullptr && ctx->stream != cudaStreamLegacy && p->stored >= p->desc.history && nold <= p->stored &&
+      count >= 4 * period) {
+    mrl_split_plan::GraphKey key;
+    key.c = c;
+    key.dt = dt;
+    key.nold = nold;
+    key.cur = p->cur;
+    key.time = p->time;
+    for (int i = 0; i < 5 && i <= nold; ++i) key.beta[i] = beta[i];
+    if (!p->graph || !(key == p->graph_key)) {
+      // lazily initialised state (twiddles, kernel attributes, NVRTC modules) must exist before capturing
+      for (int i = 0; i < period; ++i, ++done) {
+        int rc = one();
+        if (rc) return rc;
+      }
+      if (p->graph) {
+        cudaGraphExecDestroy(p->graph);
+        p->graph = nullptr;
+      }
+      const int64_t l0 = ctx->launches;
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = MRL_OK;
+      for (int i = 0; i < period && !rc; ++i) rc = one();
+      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+      if (rc || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        return rc ? rc : mrl_fail(MRL_ERR_CUDA, "mrl_split_substeps: stream capture failed: %s", cudaGetErrorString(ce));
+      }
+      p->graph_launches = ctx->launches - l0;
+      ctx->launches = l0;  // nothing ran during the capture
+      ce = cudaGraphInstantiate(&p->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) return mrl_fail(MRL_ERR_CUDA, "mrl_split_substeps: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      p->graph_key = key;  // the ring position is back where the capture started (one full period)
+    }
+    for (; count - done >= period; done += period) {
+      CK(cudaGraphLaunch(p->graph, ctx->stream));
+      ctx->launches += p->graph_launches;
+    }
+  }
+  for (; done < count; ++done) {
+    int rc = one();
+    if (rc) return rc;
+  }
+  return MRL_OK;
 }
 
 extern "C" int mrl_split_forward(mrl_split_plan *p, const void *c) {

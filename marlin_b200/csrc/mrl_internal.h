@@ -57,6 +57,19 @@ struct mrl_split_plan {
   int cur = 0, stored = 0;
   int ncp = 0;                      // row pitch of the work spectra (>= n_last/2+1)
   double time = 0.0;                // sub-time seen by an expression nonlinearity
+  // mrl_split_substeps: one period (history+1 substeps) of the steady-state sequence captured as a CUDA graph
+  cudaGraphExec_t graph = nullptr;
+  struct GraphKey {
+    const void *c = nullptr;
+    double dt = 0, beta[5] = {0, 0, 0, 0, 0}, time = 0;
+    int nold = -1, cur = -1;
+    bool operator==(const GraphKey &o) const {
+      for (int i = 0; i < 5; ++i)
+        if (beta[i] != o.beta[i]) return false;
+      return c == o.c && dt == o.dt && time == o.time && nold == o.nold && cur == o.cur;
+    }
+  } graph_key;
+  int64_t graph_launches = 0;       // kernel launches inside the captured period
 };
 
 struct mrl_slab_plan {

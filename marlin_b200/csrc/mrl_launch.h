@@ -40,6 +40,14 @@ template <class T> inline int gen_tk(int n, int nbuf) {
   return 0;
 }
 
+// Same, but no more pencils per CTA than leaves every SM a tile: small 2-D grids (PFHub 200^2) would
+// otherwise run on a dozen CTAs.  work = pencils (columns x slices) of the pass.
+template <class T> inline int gen_tk_for(int n, int nbuf, long long work, int sm_count) {
+  int tk = gen_tk<T>(n, nbuf);
+  while (tk > 1 && (work + tk - 1) / tk < sm_count) tk >>= 1;
+  return tk;
+}
+
 // Real-space nonlinearity selector for the fused first pass.
 struct NonlinDesc {
   int kind;          // 0: double-well derivative 2A(c-a)(b-c)(a+b-2c)

@@ -355,6 +355,42 @@ def test_broyden_kernels_match_torch(ctx, nvar):
     assert torch.equal(got[0, 0, 0], M[0, 0, 0])
 
 
+@pytest.mark.parametrize("dim,n,history", [(2, 200, 1), (2, 64, 2), (3, 32, 1)])
+def test_substeps_graph_replay_is_bit_identical(dim, n, history):
+    """mrl_split_substeps (one period of the steady-state sequence captured as a CUDA graph and replayed on
+    a side stream) gives exactly the same field as the substep / advance_state loop."""
+    from marlin_b200 import capi
+    from oracle.marlin import AB_BETA
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        c2 = capi.Context(0, capi.F64)
+        c2.use_torch_stream()
+        c2.domain_set(dim, (n,) * dim, (0,) * dim, (n * 0.5,) * dim)
+        torch.manual_seed(3)
+        c0 = (torch.rand((n,) * dim, dtype=torch.float64) * 0.12 + 0.44).cuda()
+        res = []
+        for batched in (False, True):
+            c = c0.clone()
+            plan = c2.split_plan(double_well=(5.0, 0.3, 0.7), M_factor=5.0, L_factor=-10.0, history=history)
+            for k in range(history):      # fill the ring: orders 1 .. history
+                plan.substep(c, 1e-3, AB_BETA[k], k)
+                plan.advance_state()
+            count = 37
+            l0 = c2.launch_count()
+            if batched:
+                plan.substeps(c, 1e-3, AB_BETA[history], history, count)
+            else:
+                for _ in range(count):
+                    plan.substep(c, 1e-3, AB_BETA[history], history)
+                    plan.advance_state()
+            side.synchronize()
+            res.append((c.cpu(), c2.launch_count() - l0))
+            plan.close()
+        assert torch.equal(res[0][0], res[1][0])
+        assert res[0][1] == res[1][1]            # the launch counter counts the kernels inside the replays
+        c2.close()
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_512_properties(ctx):
     """At BASELINE's 512^3 the oracle is too slow for a test; check size-independent
