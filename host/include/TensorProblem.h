@@ -27,6 +27,7 @@ public:
   virtual ~TensorBufferBase() = default;
   const std::string &name() const { return _name; }
   virtual std::size_t advanceState() = 0;
+  virtual std::size_t maxStates() const = 0;
   virtual void clearStates() = 0;
   virtual const marlin::Tensor &getRawTensor() const = 0;
   virtual void makeCPUCopy(const DomainAction &domain) = 0;
@@ -49,6 +50,7 @@ public:
     return _u_old.size();
   }
   void clearStates() override { _u_old.clear(); }
+  std::size_t maxStates() const override { return _max_states; }
   T &getTensor() { return _u; }
   const std::vector<T> &getOldTensor(std::size_t states_requested) {
     _max_states = std::max(_max_states, states_requested);
@@ -147,6 +149,13 @@ public:
   // buffers an output object (or the driver's --dump) reads: they must stay materialised when a solver
   // fuses the computes that produce them
   void observeBuffer(const std::string &name) { _extra_observed.insert(name); }
+  // deepest history any object asked for (getBufferOld): after that many + 1 substeps issued one by
+  // one, every old state is what an all-single-substep run would hold
+  std::size_t maxOldStates() const {
+    std::size_t m = 0;
+    for (const auto &pair : _tensor_buffer) m = std::max(m, pair.second->maxStates());
+    return m;
+  }
 
 private:
   const DomainAction &_domain;

@@ -86,6 +86,7 @@ public:
   ~AdamsBashforthMoulton() override;
   static constexpr std::size_t max_order = 5;
   void check() override;
+  void computeBuffer() override;
   bool fused() const { return !_plans.empty(); }
 
 protected:
@@ -99,6 +100,7 @@ protected:
   std::size_t _corrector_order;
   std::size_t _corrector_steps;
   const bool _allow_fusion;
+  const bool _allow_batching;
 
   // fused five-pass plans (one per solver variable) when the root compute matches the canonical
   // split-operator pattern; empty = generic operator-by-operator path

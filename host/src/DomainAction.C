@@ -94,6 +94,7 @@ DomainAction::DomainAction(const InputParameters &parameters)
   for (unsigned int d = _dim; d < 3; ++d)
     if (_n_global[d] != 1) _n_global[d] = 1;  // unused dimensions collapse (DomainAction.C:296)
   check(mrl_create(_device, _single ? MRL_F32 : MRL_F64, &_ctx), "mrl_create");
+  check(mrl_own_stream(_ctx), "mrl_own_stream");  // everything this process launches goes through the context
   _pool = std::make_unique<marlin::TensorPool>(_ctx);
   gridChanged();
 }

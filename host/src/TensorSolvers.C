@@ -182,6 +182,8 @@ InputParameters AdamsBashforthMoulton::validParams() {
   params.addRangeCheckedParam<std::size_t>("corrector_order", 2, "corrector_order > 0 & corrector_order <= 5", "Order of the Adams-Moulton corrector.");
   params.addParam<std::size_t>("corrector_steps", 0, "Number the Adams-Moulton corrector steps to take (one is usually sufficient).");
   // not a reference parameter: lets a user (or a test) force the operator-by-operator path
+  params.addParam<bool>("batch_substeps", true, "Run the steady-state part of a step's substep loop as one batched call (CUDA graph replay) when the "
+                                                "fused plan is active (marlin_b200 extension; results and postprocessor histories are identical).");
   params.addParam<bool>("fuse", true, "Replace the root compute and the update by the fused five-pass CUDA plan when the root compute has the canonical "
                                       "split-operator structure (marlin_b200 extension; results are identical).");
   return params;
@@ -192,7 +194,8 @@ AdamsBashforthMoulton::AdamsBashforthMoulton(const InputParameters &parameters)
     _predictor_order(getParam<std::size_t>("predictor_order") - 1),
     _corrector_order(getParam<std::size_t>("corrector_order") - 1),
     _corrector_steps(getParam<std::size_t>("corrector_steps")),
-    _allow_fusion(getParam<bool>("fuse")) {
+    _allow_fusion(getParam<bool>("fuse")),
+    _allow_batching(getParam<bool>("batch_substeps")) {
   const auto history = std::max(_predictor_order, _corrector_order);
   getVariables(history);
 }
@@ -418,6 +421,43 @@ void AdamsBashforthMoulton::tryBuildFusedPlans() {
   _tensor_problem.addAdvanceStateHook([this]() {
     for (auto &p : _plans) checkC(mrl_split_advance_state(p.plan, &p.stored), "mrl_split_advance_state");
   });
+}
+
+// TensorSolver::computeBuffer (TensorSolver.C:93-110) with the steady-state middle of the substep loop
+// handed to mrl_split_substeps.  The first substeps (until the predictor runs at full order with a full
+// ring) and the last maxOldStates()+1 substeps are issued one by one with TensorProblem::advanceState in
+// between, so every old state a postprocessor or output reads at the end of the step is exactly what the
+// plain loop leaves behind.
+void AdamsBashforthMoulton::computeBuffer() {
+  if (!_fusion_decided) decideFusion();
+  const std::size_t tail = _tensor_problem.maxOldStates() + 1;
+  const std::size_t P = _predictor_order;
+  if (!_allow_batching || !fused() || _variables.size() != 1 || _tensor_problem.timeStep() <= 1 || _substeps < tail + P + 4 * (P + 1) + 1)
+    return TensorSolver::computeBuffer();
+  _sub_dt = _dt / _substeps;
+  const bool dt_changed = (_dt != _dt_old);
+  _substep = 0;
+  auto single = [&]() {
+    substep();
+    if (_substep < _substeps - 1) _tensor_problem.advanceState();
+    _sub_time += _sub_dt;
+    ++_substep;
+  };
+  while (_substep + tail < _substeps && !((!dt_changed || _substep >= P) && (std::size_t)_plans[0].stored >= P)) single();
+  const long nbatch = (long)_substeps - (long)tail - (long)_substep;
+  if (nbatch >= (long)(4 * (P + 1))) {
+    Tensor &u = _variables[0]._buffer;
+    if (u.use_count() > 1) {  // as in fusedSubstep: the plan updates the block in place
+      Tensor copy = _domain.clone(u);
+      Tensor::swapBlocks(u, copy);
+      u = copy;
+    }
+    checkC(mrl_split_set_time(_plans[0].plan, _sub_time), "mrl_split_set_time");
+    checkC(mrl_split_substeps(_plans[0].plan, u.data_ptr(), _sub_dt, AB_BETA[P], (int)P, (int)nbatch), "mrl_split_substeps");
+    for (long i = 0; i < nbatch; ++i) _sub_time += _sub_dt;  // same summation order as the loop
+    _substep += (unsigned int)nbatch;
+  }
+  while (_substep < _substeps) single();
 }
 
 void AdamsBashforthMoulton::fusedSubstep() {

@@ -47,6 +47,8 @@ int mrl_destroy(mrl_context *ctx);
 const char *mrl_last_error(void);
 const char *mrl_version(void);
 int mrl_set_stream(mrl_context *ctx, void *cuda_stream); /* run on a caller-owned stream */
+int mrl_own_stream(mrl_context *ctx);                    /* create a stream owned by the context and run on it
+                                                            (capturable: enables the CUDA-graph paths)        */
 int mrl_synchronize(mrl_context *ctx);                   /* block until the stream drains */
 int mrl_precision_of(const mrl_context *ctx);
 int mrl_launch_count(const mrl_context *ctx, int64_t *count); /* kernels launched so far */

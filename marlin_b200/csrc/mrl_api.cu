@@ -202,6 +202,7 @@ extern "C" int mrl_destroy(mrl_context *ctx) {
   cudaFree(ctx->scratch_ptr);
   cudaFree(ctx->reduce_dev);
   if (ctx->reduce_host) cudaFreeHost(ctx->reduce_host);
+  if (ctx->owned_stream) cudaStreamDestroy(ctx->owned_stream);
   if (ctx->s_in) {
     cudaStreamSynchronize(ctx->s_in);
     cudaStreamSynchronize(ctx->s_out);
@@ -218,6 +219,16 @@ extern "C" int mrl_destroy(mrl_context *ctx) {
 extern "C" int mrl_set_stream(mrl_context *ctx, void *s) {
   if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
   ctx->stream = (cudaStream_t)s;
+  return MRL_OK;
+}
+extern "C" int mrl_own_stream(mrl_context *ctx) {
+  if (!ctx) return mrl_fail(MRL_ERR_INVALID, "null context");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->owned_stream) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamCreateWithFlags(&ctx->owned_stream, cudaStreamNonBlocking));
+  }
+  ctx->stream = ctx->owned_stream;
   return MRL_OK;
 }
 extern "C" int mrl_synchronize(mrl_context *ctx) {

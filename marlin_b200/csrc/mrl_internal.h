@@ -18,6 +18,7 @@ struct mrl_context {
   int device = 0;
   int precision = MRL_F64;
   cudaStream_t stream = 0;
+  cudaStream_t owned_stream = nullptr;  // mrl_own_stream
   int sm_count = 148;
   int64_t launches = 0;
   // domain
