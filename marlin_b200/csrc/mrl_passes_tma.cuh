@@ -212,10 +212,12 @@ template <class T> struct SpectralUpdate2 {
     return b * b;
   }
   MRL_DI const T *rowaxis() const { return kmode == MRL_KMODE_3D_SLAB ? ky : kx; }
-  // chat, ghat: transformed variable / nonlinearity; nold0: newest old nonlinear term
-  MRL_DI cx<T> apply(T kr, T kcol, long long off, cx<T> chat, cx<T> ghat, cx<T> nold0) const {
+  // chat, ghat: transformed variable / nonlinearity; nold0: newest old nonlinear term.
+  // off: element offset in the work / ring arrays (row pitch nzc, possibly padded); moff: offset of the
+  // same wavevector in the caller's mobility / linear-operator buffers (natural layout, row length nzv)
+  MRL_DI cx<T> apply(T kr, T kcol, long long off, long long moff, cx<T> chat, cx<T> ghat, cx<T> nold0) const {
     const T kk = kr * kr + kcol;
-    const T M = closed_M == 1 ? (-kk * Mfac) : closed_M == 2 ? T(1) : Mbuf[off];
+    const T M = closed_M == 1 ? (-kk * Mfac) : closed_M == 2 ? T(1) : Mbuf[moff];
     const cx<T> N = mk<T>(M * ghat.x, M * ghat.y);
     if (Nout) Nout[off] = N;
     cx<T> u = mk<T>(chat.x + b0 * N.x, chat.y + b0 * N.y);
@@ -224,7 +226,7 @@ template <class T> struct SpectralUpdate2 {
     if (nold > 2) { const cx<T> q = Nold2[off]; u.x += bold2 * q.x; u.y += bold2 * q.y; }
     if (nold > 3) { const cx<T> q = Nold3[off]; u.x += bold3 * q.x; u.y += bold3 * q.y; }
     if (has_L) {
-      const T L = closed_L ? (kk * kk * Lfac) : Lbuf[off];
+      const T L = closed_L ? (kk * kk * Lfac) : Lbuf[moff];
       const T r = fast_rcp(T(1) - dt * L);
       u.x *= r;
       u.y *= r;
@@ -317,11 +319,13 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     if (ok) {
       const T kcol = up.colterm(o, c);
       const T *kr = up.rowaxis();
+      // the caller's M / L buffers are not padded: [n][ncols / nzc][nzv]
+      const long long mrow = (long long)(io.ncols / up.nzc) * up.nzv, mcol = (long long)(c / up.nzc) * up.nzv + (c % up.nzc);
       MRL_UNROLL
       for (int e = 0; e < E; ++e) {
         const int jj = t + TP * e;
         const cx<T> no = use_old ? smo.ld(jj) : mk<T>(T(0), T(0));
-        a[e] = conj(up.apply(kr[jj], kcol, io.row_off(o, jj) + c, a[e], gh[e], no));
+        a[e] = conj(up.apply(kr[jj], kcol, io.row_off(o, jj) + c, jj * mrow + mcol, a[e], gh[e], no));
       }
     }
     bar.sync();  // every thread has taken its old-term values: the O slot becomes the exchange buffer

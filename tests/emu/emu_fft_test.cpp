@@ -522,7 +522,71 @@ template <class C, int TK, int NG> static void test_mech_fused(const char *name,
   report(nm, pad, 1e-300);
 }
 
+// fused pass on PADDED work spectra (row pitch ncp > nzv) with the mobility / linear operator read from
+// caller buffers in their natural, unpadded layout [n][ny][nzv] (kmode 3D) or [n][nzv] (kmode 2D)
+template <class C, int TK, int NG> static void test_fused_padded_buffers(const char *name, int kmode, int ny, int nzv, int ncp, int grid) {
+  constexpr int n = C::N;
+  std::mt19937_64 rng(31);
+  std::uniform_real_distribution<double> U(-1, 1);
+  const int nyy = kmode == MRL_KMODE_2D ? 1 : ny;
+  const int ncols = nyy * ncp;
+  const size_t total = (size_t)n * ncols, mtotal = (size_t)n * nyy * nzv;
+  std::vector<cx<double>> Cc(total), G(total), Uo(total), Nout(total), Nold0(total);
+  for (size_t i = 0; i < total; ++i) {
+    const bool valid = (int)(i % ncp) < nzv;
+    Cc[i] = valid ? mk<double>(U(rng), U(rng)) : mk<double>(0, 0);
+    G[i] = valid ? mk<double>(U(rng), U(rng)) : mk<double>(0, 0);
+    Nold0[i] = valid ? mk<double>(U(rng), U(rng)) : mk<double>(0, 0);
+  }
+  std::vector<double> Mb(mtotal), Lb(mtotal), kx(n, 0.0), ky(std::max(nyy, ncp), 0.0), kz(ncp, 0.0);
+  for (auto &v : Mb) v = U(rng);
+  for (auto &v : Lb) v = -std::fabs(U(rng));
+  auto tw = make_tw(n);
+  FusedTmaIO<double> io;
+  io.outU = Uo.data(); io.n = n; io.ncols = ncols; io.ncb = (ncols + TK - 1) / TK; io.pitch = ncols; io.scale = 1.0 / n;
+  io.slab = 0; io.nouter = 1; io.nyl = 0; io.peer_tab = nullptr; io.peer_x0 = 0;
+  SpectralUpdate2<double> up{};
+  up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = kmode; up.nzc = ncp; up.nzv = nzv; up.x0 = 0;
+  up.closed_M = 0; up.closed_L = 0; up.has_L = 1; up.Mbuf = Mb.data(); up.Lbuf = Lb.data();
+  up.dt = 0.01; up.b0 = 1.5 * up.dt; up.nold = 1; up.bold0 = -0.5 * up.dt; up.Nout = Nout.data();
+  const long long rowb = (long long)ncols * 16;
+  const int boxr = n < 256 ? n : 256;
+  TensorMap tmC = emu_map(Cc.data(), 8, 2LL * ncols, n, 1, rowb, rowb * n, 2 * TK, boxr);
+  TensorMap tmG = emu_map(G.data(), 8, 2LL * ncols, n, 1, rowb, rowb * n, 2 * TK, boxr);
+  TensorMap tmO = emu_map(Nold0.data(), 8, 2LL * ncols, n, 1, rowb, rowb * n, 2 * TK, boxr);
+  const cx<double> *twp = tw.data();
+  size_t smem = (size_t)(NG * 3 * n * TK) * 16 + NG * 3 * 8 + 128;
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG>(tmC, tmG, tmO, io, up, twp); }, 64 * 1024);
+  double err = 0;
+  for (int c = 0; c < ncols; ++c) {
+    if (c % ncp >= nzv) continue;
+    std::vector<lc> xc(n), xg(n);
+    for (int j = 0; j < n; ++j) {
+      xc[j] = lc(Cc[(size_t)j * ncols + c].x, Cc[(size_t)j * ncols + c].y);
+      xg[j] = lc(G[(size_t)j * ncols + c].x, G[(size_t)j * ncols + c].y);
+    }
+    auto yc = dft(xc, -1), yg = dft(xg, -1);
+    std::vector<lc> u(n);
+    for (int j = 0; j < n; ++j) {
+      const size_t m = ((size_t)j * nyy + c / ncp) * nzv + c % ncp;
+      lc N = (long double)Mb[m] * yg[j];
+      auto no = Nold0[(size_t)j * ncols + c];
+      u[j] = (yc[j] + (long double)up.b0 * N + (long double)up.bold0 * lc(no.x, no.y)) / (1.0L - (long double)up.dt * (long double)Lb[m]);
+      auto nn = Nout[(size_t)j * ncols + c];
+      err = std::max(err, (double)std::abs(lc(nn.x, nn.y) - N));
+    }
+    auto r = dft(u, +1);
+    for (int j = 0; j < n; ++j) {
+      auto v = Uo[(size_t)j * ncols + c];
+      err = std::max(err, (double)std::abs(lc(v.x, v.y) - r[j] / (long double)n));
+    }
+  }
+  report(name, err, 1e-12 * n);
+}
+
 static void tma_tests() {
+  test_fused_padded_buffers<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma 64 3D padded pitch, M/L from buffers", MRL_KMODE_3D, 3, 5, 8, 2);
+  test_fused_padded_buffers<FFTCfg<64, 8, 8, 8>, 8, 1>("fused tma 64 2D padded pitch, M/L from buffers", MRL_KMODE_2D, 1, 33, 40, 1);
   test_mech_fused<FFTCfg<64, 8, 8, 8>, 8, 2>("mech fused tma 64 TK8 NG2 ny3 nzv5 ncp8 g2", 3, 5, 8, 2);
   test_mech_fused<FFTCfg<64, 8, 8, 8>, 4, 1>("mech fused tma 64 TK4 NG1 ny2 nzv3 ncp3 g1", 2, 3, 3, 1);
   test_mech_fused<FFTCfg<512, 64, 8, 8, 8>, 4, 1>("mech fused tma 512 TK4 NG1 (2 boxes) g3", 1, 3, 4, 3);

@@ -185,6 +185,8 @@ def test_ch2d_fused_matches_reference_gold(ctx):
 
 @pytest.mark.parametrize("closed", [True, False])
 @pytest.mark.parametrize("dim,n,L,order", [(2, 20, 3.0, 2), (2, 64, 8.0, 2), (2, 200, 25.0, 1), (2, 150, 20.0, 3),
+                                           (2, 256, 256 * 8 * math.pi / 200, 2),   # BASELINE.json configs[0] (2-D 256^2)
+                                           (2, 128, 16.0, 3),                      # 2-D on the TMA-pipelined passes
                                            (3, 16, 2.0, 2), (3, 20, 2.5, 2), (3, 32, 4.0, 4), (3, 64, 8.0, 2)])
 def test_ch_fused_matches_oracle_100_substeps(ctx, dim, n, L, order, closed):
     """BASELINE.md parity gate: 100 substeps over 2 MOOSE steps (AB order 0 in step 1 by quirk

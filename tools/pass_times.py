@@ -22,7 +22,7 @@ def main():
     L = n * 8 * math.pi / 200
     ctx = capi.Context(0, prec)
     ctx.use_torch_stream()
-    ctx.domain_set(3, dims, (0,) * 3, tuple(L * d / n for d in dims))
+    ctx.domain_set(len(dims), dims, (0,) * len(dims), tuple(L * d / n for d in dims))
     torch.manual_seed(0)
     c = (torch.rand(dims, dtype=torch.float64) * 0.12 + 0.44).to(ctx.rdtype).cuda()
     plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
