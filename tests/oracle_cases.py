@@ -12,7 +12,10 @@ def ch_problem(dim, n, L, substeps, mu_expr="0.1*c^2*(c-1)^2", M=0.2, kappa=-0.0
                predictor_order=2, cmin=0.44, cmax=0.56, constant_names=(),
                constant_expressions=()):
     """test/tests/cahnhilliard/cahnhilliard.i and examples/cahn_hilliard/cahnhilliard2.i."""
-    d = om.Domain(dim, [n] * dim, (0, 0, 0), tuple([L] * dim) + (1.0,) * (3 - dim))
+    # n, L: one value for all axes or one per axis
+    ns = list(n) if isinstance(n, (tuple, list)) else [n] * dim
+    Ls = list(L) if isinstance(L, (tuple, list)) else [L] * dim
+    d = om.Domain(dim, ns, (0, 0, 0), tuple(Ls) + (1.0,) * (3 - dim))
     p = om.Problem(d)
     p.ics = [om.RandomTensor(p, "c", cmin, cmax, seed),
              om.ReciprocalLaplacianFactor(p, "Mbar", M),

@@ -246,6 +246,30 @@ def test_ch3d_128_matches_oracle(ctx):
     assert rel_l2(got, p.buf["c"]) < 1e-10
 
 
+@pytest.mark.parametrize("shape,closed,order", [((128, 128, 128), False, 2), ((128, 256, 128), True, 2), ((256, 128, 128), False, 3)])
+def test_ch3d_tma_sizes_match_oracle(ctx, shape, closed, order):
+    """3-D power-of-two sizes (padded work spectra, TMA-pipelined passes): mixed axis lengths, mobility and
+    linear operator from caller buffers, AB3."""
+    dx = 8 * math.pi / 200
+    p = oc.ch_problem(3, shape, [n * dx for n in shape], substeps=6, predictor_order=order)
+    p.initial()
+    got = _run_split(ctx, p, 2, 0.006, 6, closed=closed, order=order)
+    for _ in range(2):
+        p.step(0.006)
+    assert rel_l2(got, p.buf["c"]) < 1e-10
+
+
+@pytest.mark.parametrize("dim,n", [(3, 128), (2, 256)])
+def test_ch_float32_tma_sizes(ctx32, dim, n):
+    """floating_precision = SINGLE on the TMA-pipelined passes: relative L2 <= 1e-5 (BASELINE.json north_star)."""
+    p = oc.ch_problem(dim, n, n * 8 * math.pi / 200, substeps=10)
+    p.initial()
+    got = _run_split(ctx32, p, 2, 0.01, 10)
+    for _ in range(2):
+        p.step(0.01)
+    assert rel_l2(got, p.buf["c"]) < 1e-5
+
+
 def test_unfused_operators_match_fused(ctx):
     """Generic path (rfftn + pointwise + ab_update + irfftn, one kernel per reference op)
     against the fused five-pass plan."""
