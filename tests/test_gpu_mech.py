@@ -192,3 +192,33 @@ def test_mech_large_properties(ctx, n):
     lin = plan.apply_GK(F, 2.0 * A - 3.0 * B)
     assert rel_l2(lin, 2.0 * plan.apply_GK(F, A) - 3.0 * plan.apply_GK(F, B)) < 1e-11
     plan.close()
+
+
+def test_mech_float32_tma_size():
+    """floating_precision = SINGLE on the fused Green-projection pass (128^3): G(A) against its closed form
+    evaluated with torch.fft in float64, and the CG operator's linearity, at float32 accuracy."""
+    from marlin_b200 import capi
+    n, L = 128, 2 * math.pi
+    c32 = capi.Context(0, capi.F32)
+    c32.domain_set(3, (n, n, n), (0,) * 3, (L,) * 3)
+    torch.manual_seed(8)
+    K = (1.0 + 9.0 * torch.rand(n, n, n)).cuda()
+    mu = (0.5 + 4.5 * torch.rand(n, n, n)).cuda()
+    plan = capi.MechPlan(c32, K, mu)
+    A = (torch.rand(9, n, n, n, device="cuda") - 0.5)
+    GA = plan.apply_G(A)
+    k = [c32.axis(a, True).double().cuda() for a in range(3)]
+    q = torch.stack(torch.meshgrid(k[0], k[1], k[2], indexing="ij"))
+    Q = (q * q).sum(0)
+    Ah = torch.fft.rfftn(A[0:3].double(), dim=(1, 2, 3))
+    v = (Ah * q).sum(0) / torch.where(Q == 0, torch.ones_like(Q), Q)
+    v = torch.where(Q == 0, torch.zeros_like(v), v)
+    ref = torch.fft.irfftn(v.unsqueeze(0) * q, s=(n, n, n), dim=(1, 2, 3))
+    assert rel_l2(GA[0:3], ref) < 2e-6
+    F = torch.zeros(9, n, n, n, device="cuda")
+    F[0] = F[4] = F[8] = 1.0
+    B = torch.rand(9, n, n, n, device="cuda") - 0.5
+    lin = plan.apply_GK(F, 2.0 * A - 3.0 * B)
+    assert rel_l2(lin, 2.0 * plan.apply_GK(F, A) - 3.0 * plan.apply_GK(F, B)) < 1e-4
+    plan.close()
+    c32.close()
