@@ -19,6 +19,7 @@
 class TensorOperatorBase;
 class TensorSolver;
 class TensorPostprocessor;
+class TensorOutput;
 
 // ---- buffers ------------------------------------------------------------------------------------
 class TensorBufferBase {
@@ -114,6 +115,7 @@ public:
   void addTensorPostprocess(std::shared_ptr<TensorOperatorBase> op) { _pps.push_back(std::move(op)); }
   void setSolver(std::shared_ptr<TensorSolver> solver);
   void addPostprocessor(std::shared_ptr<TensorPostprocessor> pp) { _postprocessors.push_back(std::move(pp)); }
+  void addTensorOutput(std::shared_ptr<TensorOutput> out) { _outputs.push_back(std::move(out)); }
   const std::vector<std::shared_ptr<TensorOperatorBase>> &getComputes() const { return _computes; }
   const std::vector<std::shared_ptr<TensorOperatorBase>> &getICs() const { return _ics; }
   const std::vector<std::shared_ptr<TensorOperatorBase>> &getPostprocessComputes() const { return _pps; }
@@ -129,6 +131,7 @@ public:
   void addAdvanceStateHook(std::function<void()> hook) { _advance_hooks.push_back(std::move(hook)); }
 
 private:
+  std::vector<std::shared_ptr<TensorOutput>> _outputs;
   std::map<std::string, ParsedFunctionDesc> _functions;
   std::set<std::string> _extra_observed;
 

@@ -23,6 +23,7 @@
 #include "MechanicsComputes.h"
 #include "TensorComputes.h"
 #include "TensorPostprocessor.h"
+#include "TensorOutput.h"
 #include "TensorSolver.h"
 #include "hit.h"
 
@@ -125,7 +126,7 @@ void MarlinApp::addComputes(const hit::Node &parent, int task, int depth) {
 }
 
 void MarlinApp::buildObjects() {
-  static const std::set<std::string> known = {"Domain", "GlobalParams", "TensorBuffers", "TensorComputes", "TensorSolver", "Problem", "Postprocessors", "Executioner", "Outputs", "Functions"};
+  static const std::set<std::string> known = {"Domain", "GlobalParams", "TensorBuffers", "TensorComputes", "TensorSolver", "Problem", "Postprocessors", "Executioner", "Outputs", "Functions", "TensorOutputs"};
   for (hit::Node *s : _root->sections())
     if (!known.count(s->name)) _skipped.push_back(s->name);
 
@@ -212,6 +213,25 @@ void MarlinApp::buildObjects() {
     for (hit::Node *s : ts->sections()) _skipped.push_back("TensorSolver/" + s->name);
     _problem->setSolver(solver);
   }
+  // [TensorOutputs] (AddTensorOutputAction): XDMFTensorOutput; other types are reported and skipped
+  if (const hit::Node *to = _root->find("TensorOutputs"))
+    for (hit::Node *b : to->sections()) {
+      const hit::Node *tf = b->field("type");
+      if (!tf) mooseError(b->fullpath(), ": missing 'type'");
+      if (!Factory::instance().isRegistered(tf->value)) {
+        _skipped.push_back(b->fullpath() + " (type " + tf->value + ")");
+        continue;
+      }
+      InputParameters p = fill(tf->value, *b, b->name);
+      // MooseApp::getOutputFileBase: <input dir>/<input base>_<object name> unless file_base is given
+      std::string base = dirName(_opt.input) + "/" + baseName(_opt.input);  // e.g. cahnhilliard.i -> cahnhilliard.xmf
+      if (p.isParamValid("file_base")) base = p.get<std::string>("file_base", b->fullpath());
+      if (!_opt.output_dir.empty()) base = _opt.output_dir + "/" + base.substr(base.rfind('/') + 1);
+      p.set<std::string>("file_base", base);
+      auto out = std::dynamic_pointer_cast<TensorOutput>(Factory::instance().create(tf->value, p));
+      if (!out) mooseError(b->fullpath(), ": '", tf->value, "' is not a TensorOutput");
+      _problem->addTensorOutput(out);
+    }
   // [Postprocessors]
   if (const hit::Node *pps = _root->find("Postprocessors"))
     for (hit::Node *b : pps->sections()) {
@@ -435,6 +455,29 @@ int MarlinApp::run() {
 
 }  // namespace
 
+// --xdmf-selftest DIR: exercises the XDMF writer on synthetic host data (no device needed; used by the
+// CPU test-suite): a 3 x 2 grid, NODE / CELL / OVERSIZED_NODAL fields, two frames, with and without transpose
+static int xdmfSelfTest(const std::string &dir) {
+  const std::array<int64_t, 3> n = {3, 2, 1};
+  const std::array<double, 3> dx = {0.5, 0.25, 1.0}, mn = {0.0, -1.0, 0.0};
+  std::vector<double> c(6), mu(6), disp(2 * 12);
+  for (int i = 0; i < 6; ++i) {
+    c[i] = 10 + i;
+    mu[i] = 20 + i;
+  }
+  for (int i = 0; i < 24; ++i) disp[i] = 100 + i;
+  for (int tr = 0; tr < 2; ++tr) {
+    XDMFWriter w(2, n, dx, mn, tr != 0, dir + (tr ? "/selftest_t" : "/selftest"));
+    for (int f = 0; f < 2; ++f) {
+      for (int i = 0; i < 6; ++i) c[i] = 10 + i + 100 * f;
+      w.addFrame(0.001 * 3 * f, {{"c", XDMFWriter::Mode::NODE, 1, c.data()},
+                                 {"disp", XDMFWriter::Mode::OVERSIZED_NODAL, 2, disp.data()},
+                                 {"mu", XDMFWriter::Mode::CELL, 1, mu.data()}});
+    }
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
   Options opt;
   for (int i = 1; i < argc; ++i) {
@@ -462,6 +505,8 @@ int main(int argc, char **argv) {
       while (std::getline(s, w, ',')) opt.dump.push_back(w);
     } else if (a == "--dump-dir")
       opt.dump_dir = need("--dump-dir");
+    else if (a == "--xdmf-selftest")
+      return xdmfSelfTest(need("--xdmf-selftest"));
     else if (a == "--quiet")
       opt.quiet = true;
     else if (a == "--n-threads" || a == "--color")

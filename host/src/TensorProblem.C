@@ -4,6 +4,7 @@
 
 #include "TensorOperatorBase.h"
 #include "TensorPostprocessor.h"
+#include "TensorOutput.h"
 #include "TensorSolver.h"
 
 using marlin::Tensor;
@@ -108,15 +109,20 @@ void TensorProblem::init() {
       for (const auto &si : cmp->getSuppliedItems()) std::cerr << "    -> " << si << '\n';
     }
   }
+  for (auto &out : _outputs) out->init();
   for (auto &cmp : _computes) cmp->check();
   if (_solver) static_cast<TensorOperatorBase *>(_solver.get())->check();
 }
 
 // TensorProblem::execute, src/problems/TensorProblem.C:154-197
 void TensorProblem::execute(ExecFlagType exec_type) {
+  // executeTensorOutputs (src/problems/TensorProblem.C:219-248): postprocess computes, CPU copies of the
+  // buffers the outputs asked for, then the outputs scheduled for this flag
   auto run_pps = [&]() {
     for (auto &pp : _pps) pp->computeBuffer();
     for (auto &kv : _tensor_buffer) kv.second->makeCPUCopy(_domain);
+    for (auto &out : _outputs)
+      if (out->shouldRun(exec_type)) out->output();
   };
   if (exec_type == EXEC_INITIAL) {
     _sub_time = _time;

@@ -219,6 +219,13 @@ def kks_no_flux():
     print("kks_no_flux_bc", a.shape, csv.shape)
 
 
+def xmf_gold():
+    """test/tests/cahnhilliard/gold/cahnhilliard.xmf (XMLDiff gold of the XDMF output), kept verbatim."""
+    import shutil
+    shutil.copyfile(f"{REF}/test/tests/cahnhilliard/gold/cahnhilliard.xmf", f"{OUT}/cahnhilliard_gold.xmf")
+    print("cahnhilliard_gold.xmf")
+
+
 if __name__ == "__main__":
     exodus_ch2d()
     solver_csvs()
@@ -227,3 +234,4 @@ if __name__ == "__main__":
     rotating_grain()
     kks_no_flux()
     exodus_more()
+    xmf_gold()

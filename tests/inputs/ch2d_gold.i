@@ -118,6 +118,17 @@
   dt = 1e-3
 []
 
+[TensorOutputs]
+  active = ''
+  [xdmf]
+    type = XDMFTensorOutput
+    buffer = 'c mu'
+    output_mode = 'Node Cell'
+    enable_hdf5 = true
+    transpose = false
+  []
+[]
+
 [Outputs]
   exodus = true
   csv = true

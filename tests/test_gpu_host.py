@@ -340,6 +340,27 @@ def test_solver_fuses_canonical_inputs_and_matches_unfused(tmp_path):
     assert "fused five-pass plan" in r.stderr + r.stdout, (r.stderr + r.stdout)[-2000:]
 
 
+def test_xdmf_output_matches_gold_xmf_and_fields(tmp_path):
+    """test/tests/cahnhilliard/cahnhilliard.i with TensorOutputs/active="xdmf" -> gold cahnhilliard.xmf (XMLDiff in the
+    reference).  The document must equal the gold one except for the DataItem storage (raw binary files here, HDF5
+    datasets there); the data files hold c (NODE: periodic continuation to 21x21) and mu (CELL) of every frame."""
+    import re
+    gold = open(f"{G}/cahnhilliard_gold.xmf").read()
+    run(tmp_path, "ch2d_gold.i", "TensorOutputs/active=xdmf")
+    mine = open(f"{tmp_path}/ch2d_gold.xmf").read()
+    norm_gold = re.sub(r' Format="HDF">cahnhilliard\.h5:/([a-z]+)\.(\d+)<', r' STORAGE>\1.\2<', gold)
+    norm_mine = re.sub(r' Format="Binary" Endian="Little" Precision="8">[^<]*ch2d_gold\.([a-z]+)\.(\d+)\.bin<', r' STORAGE>\1.\2<', mine)
+    assert norm_mine == norm_gold
+    g = np.load(f"{G}/ch2d_exodus.npz")
+    for frame in (0, 3, 10):
+        c = np.fromfile(f"{tmp_path}/ch2d_gold.c.{frame}.bin", dtype="<f8").reshape(21, 21)
+        assert np.abs(c[:20, :20] - g["c"][frame]).max() < 1e-12
+        assert np.array_equal(c[20, :20], c[0, :20]) and np.array_equal(c[:, 20], c[:, 0])
+        if frame:
+            mu = np.fromfile(f"{tmp_path}/ch2d_gold.mu.{frame}.bin", dtype="<f8").reshape(20, 20)
+            assert np.abs(mu - g["mu"][frame]).max() < 1e-12
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

@@ -103,3 +103,42 @@ def test_every_reference_input_parses():
         r = subprocess.run([APP, "-i", f, "--parse-only", "ss=10", "cs=0", "order=2"],
                            capture_output=True, text=True, timeout=60)
         assert r.returncode == 0, f + "\n" + r.stderr
+
+
+def test_xdmf_writer_selftest(tmp_path):
+    """XDMFTensorOutput's writer (src/tensor_outputs/XDMFTensorOutput.C:118-221 skeleton, :266-355 data, :358-426
+    per-frame XML, :529-553 periodic continuation for NODE, buildAttributeNames :654-668) on synthetic host data:
+    document structure as in the reference's gold cahnhilliard.xmf (binary DataItems instead of HDF), data files
+    with the extension / transpose applied."""
+    import xml.etree.ElementTree as ET
+
+    import numpy as np
+    r = subprocess.run([APP, "--xdmf-selftest", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(tmp_path / "selftest.xmf").read()
+    # the skeleton, character for character in the layout pugixml gives the reference (tabs, attribute order)
+    assert text.startswith('<?xml version="1.0"?>\n<Xdmf xmlns:xi="http://www.w3.org/2003/XInclude" Version="2.2">\n\t<Domain>\n'
+                           '\t\t<Topology TopologyType="2DCoRectMesh" Dimensions="4 3" />\n\t\t<Geometry Type="ORIGIN_DXDY">\n'
+                           '\t\t\t<DataItem Format="XML" Dimensions="2">0 -1</DataItem>\n'
+                           '\t\t\t<DataItem Format="XML" Dimensions="2">0.5 0.25</DataItem>\n\t\t</Geometry>\n'
+                           '\t\t<Grid Name="TimeSeries" GridType="Collection" CollectionType="Temporal">\n'
+                           '\t\t\t<Grid Name="T0" GridType="Uniform">\n\t\t\t\t<Time Value="0" />\n'
+                           '\t\t\t\t<xi:include xpointer="xpointer(//Xdmf/Domain/Topology)" />\n')
+    assert '<Time Value="0.0030000000000000001" />' in text and text.endswith("\t\t</Grid>\n\t</Domain>\n</Xdmf>\n")
+    root = ET.fromstring(text)
+    grids = root.find("Domain").find("Grid").findall("Grid")
+    assert [g.get("Name") for g in grids] == ["T0", "T1"]
+    attrs = [(a.get("Name"), a.get("Center"), a.find("DataItem").get("Dimensions"), a.find("DataItem").get("Format"))
+             for a in grids[1].findall("Attribute")]
+    assert attrs == [("c", "Node", "4 3", "Binary"), ("disp_x", "Node", "4 3", "Binary"), ("disp_y", "Node", "4 3", "Binary"),
+                     ("mu", "Cell", "3 2", "Binary")]
+    rd = lambda name, shape: np.fromfile(tmp_path / name, dtype="<f8").reshape(shape)
+    c = np.arange(10.0, 16.0).reshape(3, 2)
+    ext = np.concatenate([np.concatenate([c, c[:1]], 0), np.concatenate([c, c[:1]], 0)[:, :1]], 1)   # periodic continuation
+    assert np.array_equal(rd("selftest.c.0.bin", (4, 3)), ext)
+    assert np.array_equal(rd("selftest_t.c.0.bin", (3, 4)), ext.T)                                  # transpose = true swaps x and y
+    assert np.array_equal(rd("selftest.c.1.bin", (4, 3)), ext + 100)
+    assert np.array_equal(rd("selftest.mu.0.bin", (3, 2)), np.arange(20.0, 26.0).reshape(3, 2))
+    assert np.array_equal(rd("selftest.disp_y.1.bin", (4, 3)), np.arange(112.0, 124.0).reshape(4, 3))  # oversized nodal: as is
+    tt = open(tmp_path / "selftest_t.xmf").read()
+    assert 'Dimensions="3 4" />' in tt and ">-1 0<" in tt and ">0.25 0.5<" in tt                     # mapped axes
