@@ -142,3 +142,24 @@ def test_xdmf_writer_selftest(tmp_path):
     assert np.array_equal(rd("selftest.disp_y.1.bin", (4, 3)), np.arange(112.0, 124.0).reshape(4, 3))  # oversized nodal: as is
     tt = open(tmp_path / "selftest_t.xmf").read()
     assert 'Dimensions="3 4" />' in tt and ">-1 0<" in tt and ">0.25 0.5<" in tt                     # mapped axes
+
+
+def test_every_repository_input_parses_and_names_registered_types():
+    """tests/inputs/*.i (the restated reference inputs the GPU host tests run): the hit reader accepts them
+    and every `type =` of a tensor object is registered with the factory (--list-objects)."""
+    import re
+    registered = set(run("--list-objects").stdout.split())
+    files = sorted(glob.glob(f"{INP}/*.i"))
+    assert len(files) >= 15
+    for f in files:
+        r = subprocess.run([APP, "-i", f, "--parse-only", "ss=10", "cs=0", "order=2", "smooth=SHARP"], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, f + "\n" + r.stderr
+        block = None
+        for line in r.stdout.splitlines():
+            m = re.match(r"(\S+)/type = (\S+)$", line)
+            if not m:
+                continue
+            path, typ = m.groups()
+            top = path.split("/")[0]
+            if top in ("TensorComputes", "TensorSolver", "TensorOutputs") or (top == "Postprocessors" and typ.startswith(("Tensor", "Reciprocal", "SemiImplicit", "ComputeGroup"))):
+                assert typ in registered, f"{f}: {path} uses unregistered type {typ}"
