@@ -1,6 +1,6 @@
 // de Geus FFT mechanics operator classes (see host/src/MechanicsComputes.C for reference citations).
 #pragma once
-#include "TensorOperatorBase.h"
+#include "TensorComputes.h"
 
 class RankTwoIdentity : public TensorOperator<> {
 public:
@@ -92,4 +92,32 @@ public:
 
 protected:
   const marlin::Tensor &_deformation_gradient_tensor;
+};
+
+// src/tensor_computes/FFTQuasistaticElasticity.C: per-wavevector 3x3 solve for the displacements (3-D)
+class FFTQuasistaticElasticity : public TensorOperatorBase {
+public:
+  static InputParameters validParams();
+  explicit FFTQuasistaticElasticity(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const Real _mu, _lambda, _e0;
+  const marlin::Tensor &_cbar;
+  std::vector<marlin::Tensor *> _displacements;
+  ExprKernel _coef[6], _rhs[3];  // L = I - A entries (xx yy zz xy xz yz), right-hand sides
+  marlin::Tensor _L[6];
+};
+
+// src/tensor_computes/FFTElasticChemicalPotential.C
+class FFTElasticChemicalPotential : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit FFTElasticChemicalPotential(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const marlin::Tensor &_cbar;
+  std::vector<const marlin::Tensor *> _displacements;
+  ExprKernel _kernel;
 };

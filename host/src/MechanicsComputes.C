@@ -248,3 +248,83 @@ void ComputeDisplacements::computeBuffer() {
   checkC(mrl_displacements(_domain.context(), F.data_ptr(), out.data_ptr()), "mrl_displacements");
   _u = out;
 }
+
+// ---------------------------------------------------------------------- FFTQuasistaticElasticity
+registerMooseObject("MarlinApp", FFTQuasistaticElasticity);
+
+InputParameters FFTQuasistaticElasticity::validParams() {
+  InputParameters params = TensorOperatorBase::validParams();
+  params.addClassDescription("FFT based monolithic homogeneous quasistatic elasticity solve.");
+  params.addParam<std::vector<TensorOutputBufferName>>("displacements", "Displacements");
+  params.addParam<TensorInputBufferName>("cbar", "FFT of concentration buffer");
+  params.addRequiredParam<Real>("mu", "Lame mu");
+  params.addRequiredParam<Real>("lambda", "Lame lambda");
+  params.addRequiredParam<Real>("e0", "volumetric eigenstrain");
+  return params;
+}
+
+FFTQuasistaticElasticity::FFTQuasistaticElasticity(const InputParameters &parameters)
+  : TensorOperatorBase(parameters), _mu(getParam<Real>("mu")), _lambda(getParam<Real>("lambda")), _e0(getParam<Real>("e0")), _cbar(getInputBuffer("cbar")) {
+  for (const auto &name : getParam<std::vector<TensorOutputBufferName>>("displacements")) _displacements.push_back(&getOutputBufferByName(name));
+  if (_domain.getDim() != _displacements.size()) paramError("displacements", "Need one displacement variable per mesh dimension");
+  if (_dim != 3) paramError("displacements", "FFTQuasistaticElasticity is written for three dimensions");
+  // FFTQuasistaticElasticity.C:62-91.  With k_d = 2 pi i * (reciprocal axis) every matrix entry
+  // A_ab = coef * k_a k_b is REAL (-(2 pi)^2 coef axis_a axis_b); the diagonal is 1 at k = 0.  The solve
+  // goes through mrl_coupled_solve, which solves (I - dt L) x = b: L = I - A with dt = 1.
+  const std::vector<std::string> cn = {"mu", "lambda", "e0"};
+  const std::vector<double> cv = {_mu, _lambda, _e0};
+  const char *diag[3] = {"(2*mu + lambda)*kx*kx + mu*ky*ky + mu*kz*kz", "(2*mu + lambda)*ky*ky + mu*kx*kx + mu*kz*kz",
+                         "(2*mu + lambda)*kz*kz + mu*kx*kx + mu*ky*ky"};
+  const char *off[3] = {"kx*ky", "kx*kz", "ky*kz"};
+  const char *axis[3] = {"kx", "ky", "kz"};
+  for (int a = 0; a < 3; ++a) {
+    _coef[a].configure(std::string("if(k2 == 0, 0, 1 + 4*pi*pi*(") + diag[a] + "))", {}, {}, cn, cv, true, MRL_EXPAND_RECIPROCAL);
+    _coef[3 + a].configure(std::string("4*pi*pi*(lambda + mu)*") + off[a], {}, {}, cn, cv, true, MRL_EXPAND_RECIPROCAL);
+    _rhs[a].configure(std::string("if(k2 == 0, 0, (2*pi*i*") + axis[a] + ")*(2*e0*cbar*(3*lambda + mu)))", {"cbar"}, {}, cn, cv, true, MRL_EXPAND_NONE);
+  }
+}
+
+void FFTQuasistaticElasticity::computeBuffer() {
+  if (!_L[0].defined())
+    for (int a = 0; a < 6; ++a) _L[a] = _coef[a].eval(_domain, {}, _time);
+  Tensor b[3], x[3];
+  for (int a = 0; a < 3; ++a) {
+    b[a] = _rhs[a].eval(_domain, {&_cbar}, _time);
+    x[a] = _domain.empty(Space::RECIPROCAL, true, 1);
+  }
+  // symmetric matrix: xx xy xz / xy yy yz / xz yz zz
+  const void *L[9] = {_L[0].data_ptr(), _L[3].data_ptr(), _L[4].data_ptr(), _L[3].data_ptr(), _L[1].data_ptr(),
+                      _L[5].data_ptr(), _L[4].data_ptr(), _L[5].data_ptr(), _L[2].data_ptr()};
+  const void *rhs[3] = {b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr()};
+  void *out[3] = {x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr()};
+  checkC(mrl_coupled_solve(_domain.context(), 3, L, rhs, out, 1.0, 0), "mrl_coupled_solve");
+  for (int a = 0; a < 3; ++a) *_displacements[a] = _domain.ifft(x[a]);
+}
+
+// ------------------------------------------------------------------- FFTElasticChemicalPotential
+registerMooseObject("MarlinApp", FFTElasticChemicalPotential);
+
+InputParameters FFTElasticChemicalPotential::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("FFT based elastic strain energy chemical potential solve.");
+  params.addParam<std::vector<TensorInputBufferName>>("displacements", "Displacements");
+  params.addParam<TensorInputBufferName>("cbar", "FFT of concentration buffer");
+  params.addRequiredParam<Real>("mu", "Lame mu");
+  params.addRequiredParam<Real>("lambda", "Lame lambda");
+  params.addRequiredParam<Real>("e0", "volumetric eigenstrain");
+  return params;
+}
+
+FFTElasticChemicalPotential::FFTElasticChemicalPotential(const InputParameters &parameters) : TensorOperator<>(parameters), _cbar(getInputBuffer("cbar")) {
+  for (const auto &name : getParam<std::vector<TensorInputBufferName>>("displacements")) _displacements.push_back(&getInputBufferByName(name));
+  if (_domain.getDim() != _displacements.size()) paramError("displacements", "Need one displacement variable per mesh dimension");
+  if (_dim != 3) paramError("displacements", "FFTElasticChemicalPotential is written for three dimensions");
+  // FFTElasticChemicalPotential.C:49-60
+  _kernel.configure("-e0*(e0*(9*lambda*cbar + mu*6*cbar) - (2*mu + 3*lambda)*(2*pi*i)*(kx*ux + ky*uy + kz*uz))", {"cbar", "ux", "uy", "uz"}, {},
+                    {"mu", "lambda", "e0"}, {getParam<Real>("mu"), getParam<Real>("lambda"), getParam<Real>("e0")}, true, MRL_EXPAND_NONE);
+}
+
+void FFTElasticChemicalPotential::computeBuffer() {
+  const Tensor ux = _domain.fft(*_displacements[0]), uy = _domain.fft(*_displacements[1]), uz = _domain.fft(*_displacements[2]);
+  _u = _kernel.eval(_domain, {&_cbar, &ux, &uy, &uz}, _time);
+}

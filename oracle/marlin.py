@@ -1074,6 +1074,58 @@ class ComputeDisplacements(Op):
         self.set(u)
 
 
+class FFTQuasistaticElasticity(Op):
+    """src/tensor_computes/FFTQuasistaticElasticity.C:45-104: homogeneous isotropic quasistatic elasticity with
+    a volumetric eigenstrain e0*c, solved per wavevector (3x3 system, batched linalg_solve); 3-D only (the
+    code indexes {0,0,0}).  The wave vector is 2 pi i times the reciprocal axis, which already carries 2 pi
+    (as coded)."""
+
+    def __init__(self, problem, displacements, cbar, mu, lam, e0):
+        super().__init__(problem)
+        self.disp, self.cbar, self.mu, self.lam, self.e0 = list(displacements), cbar, mu, lam, e0
+
+    def compute(self):
+        d, mu, lam = self.d, self.mu, self.lam
+        tpi = torch.tensor(2j * math.pi, dtype=torch.complex128)
+        kx, ky, kz = tpi * d.kaxis[0], tpi * d.kaxis[1], tpi * d.kaxis[2]
+        ul = 2.0 * mu + lam
+        Axx = ul * kx * kx + mu * ky * ky + mu * kz * kz
+        s = Axx.shape
+        Axy = ((lam + mu) * kx * ky).expand(s)
+        Axz = ((lam + mu) * kx * kz).expand(s)
+        Ayy = ul * ky * ky + mu * kx * kx + mu * kz * kz
+        Ayz = ((lam + mu) * ky * kz).expand(s)
+        Azz = ul * kz * kz + mu * kx * kx + mu * ky * ky
+        Axx[0, 0, 0] = 1.0
+        Ayy[0, 0, 0] = 1.0
+        Azz[0, 0, 0] = 1.0
+        e = 2.0 * self.e0 * self.get(self.cbar) * (3.0 * lam + mu)
+        e[0, 0, 0] = 0.0
+        b = torch.stack([kx * e, ky * e, kz * e], -1)
+        A = torch.stack([torch.stack([Axx, Axy, Axz], -1), torch.stack([Axy, Ayy, Ayz], -1), torch.stack([Axz, Ayz, Azz], -1)], -1)
+        x = torch.linalg.solve(A, b)
+        for i, name in enumerate(self.disp):
+            self.p.buf[name] = d.ifft(x[..., i])
+
+
+class FFTElasticChemicalPotential(Op):
+    """src/tensor_computes/FFTElasticChemicalPotential.C:46-61 (reciprocal-space elastic contribution to the
+    chemical potential)."""
+
+    def __init__(self, problem, buffer, displacements, cbar, mu, lam, e0):
+        super().__init__(problem, buffer)
+        self.disp, self.cbar, self.mu, self.lam, self.e0 = list(displacements), cbar, mu, lam, e0
+
+    def compute(self):
+        d = self.d
+        tpi = torch.tensor(2j * math.pi, dtype=torch.complex128)
+        kx, ky, kz = tpi * d.kaxis[0], tpi * d.kaxis[1], tpi * d.kaxis[2]
+        ux, uy, uz = [d.fft(self.get(n)) for n in self.disp]
+        cbar = self.get(self.cbar)
+        self.set(-self.e0 * (self.e0 * (9.0 * self.lam * cbar + self.mu * 6.0 * cbar) -
+                             (2.0 * self.mu + 3.0 * self.lam) * (kx * ux + ky * uy + kz * uz)))
+
+
 # =============================================================================== postprocessors
 def pp_integral(problem, name):
     """src/postprocessors/TensorIntegralPostprocessor.C:28-38: average * domain volume."""

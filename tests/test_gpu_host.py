@@ -361,6 +361,27 @@ def test_xdmf_output_matches_gold_xmf_and_fields(tmp_path):
             assert np.abs(mu - g["mu"][frame]).max() < 1e-12
 
 
+def test_quasistatic_elasticity_input_matches_oracle(tmp_path):
+    """FFTQuasistaticElasticity (src/tensor_computes/FFTQuasistaticElasticity.C:45-104: 3x3 solve per wavevector, here
+    through mrl_coupled_solve on generated coefficient fields) and FFTElasticChemicalPotential
+    (FFTElasticChemicalPotential.C:46-61) through the host objects vs the oracle (no gold file in the reference)."""
+    run(tmp_path, "pf_mech_quasistatic.i", dump=("disp_x", "disp_y", "disp_z", "mumech"))
+    shape, L = (16, 12, 10), 4 * math.pi
+    d = om.Domain(3, list(shape), (0, 0, 0), (L, L, L))
+    p = om.Problem(d)
+    p.ics = [om.RandomTensor(p, "c", 0.44, 0.56, 0)]
+    p.computes = [om.ForwardFFT(p, "cbar", "c"),
+                  om.FFTQuasistaticElasticity(p, ["disp_x", "disp_y", "disp_z"], "cbar", 50.0, 100.0, 0.02),
+                  om.FFTElasticChemicalPotential(p, "mumechbar", ["disp_x", "disp_y", "disp_z"], "cbar", 50.0, 100.0, 0.02),
+                  om.InverseFFT(p, "mumech", "mumechbar")]
+    p.initial()
+    p.step(1.0)
+    for k in ("disp_x", "disp_y", "disp_z", "mumech"):
+        ref = p.buf[k].numpy()
+        got = field(tmp_path, k, shape)
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-11, k
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""
