@@ -26,3 +26,15 @@ protected:
   const marlin::Tensor &_u;
   int _execute_on;
 };
+
+// [VectorPostprocessors] acting on tensor buffers (src/vectorpostprocessors/TensorVectorPostprocessor.C): named
+// vectors instead of one value; the driver writes them to <file_base>_<name>_<step>.csv like MOOSE's CSV output.
+class TensorVectorPostprocessor : public TensorPostprocessor {
+public:
+  using TensorPostprocessor::TensorPostprocessor;
+  Real getValue() const override { return 0.0; }
+  const std::map<std::string, std::vector<Real>> &vectors() const { return _vectors; }
+
+protected:
+  std::map<std::string, std::vector<Real>> _vectors;
+};

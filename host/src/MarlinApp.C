@@ -73,6 +73,8 @@ private:
   std::vector<std::string> _skipped;
   std::ofstream _csv;
   std::vector<std::shared_ptr<TensorPostprocessor>> _csv_pps;
+  std::vector<std::shared_ptr<TensorVectorPostprocessor>> _vpps;  // [VectorPostprocessors]
+  void runVectorPostprocessors(int flag, bool csv, const std::string &file_base);
 };
 
 InputParameters MarlinApp::fill(const std::string &type, const hit::Node &block, const std::string &name, const std::set<std::string> &also_allowed) {
@@ -126,7 +128,7 @@ void MarlinApp::addComputes(const hit::Node &parent, int task, int depth) {
 }
 
 void MarlinApp::buildObjects() {
-  static const std::set<std::string> known = {"Domain", "GlobalParams", "TensorBuffers", "TensorComputes", "TensorSolver", "Problem", "Postprocessors", "Executioner", "Outputs", "Functions", "TensorOutputs"};
+  static const std::set<std::string> known = {"Domain", "GlobalParams", "TensorBuffers", "TensorComputes", "TensorSolver", "Problem", "Postprocessors", "VectorPostprocessors", "Executioner", "Outputs", "Functions", "TensorOutputs"};
   for (hit::Node *s : _root->sections())
     if (!known.count(s->name)) _skipped.push_back(s->name);
 
@@ -232,6 +234,19 @@ void MarlinApp::buildObjects() {
       if (!out) mooseError(b->fullpath(), ": '", tf->value, "' is not a TensorOutput");
       _problem->addTensorOutput(out);
     }
+  // [VectorPostprocessors] on tensor buffers (TensorHistogram)
+  if (const hit::Node *vb = _root->find("VectorPostprocessors"))
+    for (hit::Node *b : vb->sections()) {
+      const hit::Node *tf = b->field("type");
+      if (!tf) mooseError(b->fullpath(), ": missing 'type'");
+      if (!Factory::instance().isRegistered(tf->value)) {
+        _skipped.push_back(b->fullpath() + " (type " + tf->value + ")");
+        continue;
+      }
+      auto vpp = std::dynamic_pointer_cast<TensorVectorPostprocessor>(Factory::instance().create(tf->value, fill(tf->value, *b, b->name)));
+      if (!vpp) mooseError(b->fullpath(), ": '", tf->value, "' is not a VectorPostprocessor");
+      _vpps.push_back(vpp);
+    }
   // [Postprocessors]
   if (const hit::Node *pps = _root->find("Postprocessors"))
     for (hit::Node *b : pps->sections()) {
@@ -259,6 +274,40 @@ void MarlinApp::writeCSVRow(bool header) {
   for (const auto &pp : _csv_pps) _csv << "," << std::setprecision(14) << pp->getValue();
   _csv << "\n";
   _csv.flush();
+}
+
+// VectorPostprocessors scheduled for `flag`; MOOSE's CSV output writes one file per object and time step:
+// <file_base>_<name>_<step, 4 digits>.csv with the vectors as columns in name order
+void MarlinApp::runVectorPostprocessors(int flag, bool csv, const std::string &file_base) {
+  for (auto &vpp : _vpps) {
+    if (!(vpp->executeOn() & flag)) continue;
+    vpp->initialize();
+    vpp->execute();
+    vpp->finalize();
+    if (!csv) continue;
+    char tag[16];
+    std::snprintf(tag, sizeof tag, "%04d", _problem->timeStep());
+    std::ofstream f(file_base + "_" + vpp->name() + "_" + tag + ".csv");
+    if (!f) mooseError("cannot write the CSV file of VectorPostprocessor '", vpp->name(), "'");
+    const auto &vecs = vpp->vectors();
+    std::size_t rows = 0;
+    bool first = true;
+    for (const auto &kv : vecs) {
+      f << (first ? "" : ",") << kv.first;
+      rows = std::max(rows, kv.second.size());
+      first = false;
+    }
+    f << "\n";
+    for (std::size_t r = 0; r < rows; ++r) {
+      first = true;
+      for (const auto &kv : vecs) {
+        f << (first ? "" : ",");
+        if (r < kv.second.size()) f << std::setprecision(14) << kv.second[r];
+        first = false;
+      }
+      f << "\n";
+    }
+  }
 }
 
 void MarlinApp::dumpBuffers() {
@@ -368,6 +417,7 @@ void MarlinApp::transient() {
   time = time_old = start_time;
   t_step = 0;
   _problem->execute(EXEC_INITIAL);
+  runVectorPostprocessors(EXEC_INITIAL, csv && (out_on & EXEC_INITIAL), file_base);
   if (out_on & EXEC_INITIAL) writeCSVRow(false);
 
   double next_dt = dt0;
@@ -386,6 +436,7 @@ void MarlinApp::transient() {
     time = time_old + dt;
     _problem->execute(EXEC_TIMESTEP_BEGIN);
     _problem->execute(EXEC_TIMESTEP_END);
+    runVectorPostprocessors(EXEC_TIMESTEP_END, csv && (out_on & EXEC_TIMESTEP_END), file_base);
     if (out_on & EXEC_TIMESTEP_END) writeCSVRow(false);
     if (!_opt.quiet) std::cerr << "Time Step " << t_step << ", time = " << std::setprecision(8) << time << ", dt = " << dt << "\n";
     if (iteration_feedback) {

@@ -1,6 +1,7 @@
 // Postprocessors on tensor buffers (reference citations in include/TensorPostprocessor.h).
 #include "TensorPostprocessor.h"
 
+#include <algorithm>
 #include <cmath>
 
 #include "TensorComputes.h"
@@ -178,6 +179,54 @@ protected:
   Real _velocity = 0;
 };
 
+// src/vectorpostprocessors/TensorHistogram.C:31-84 ([VectorPostprocessors]): counts of the buffer values in `bins`
+// equal bins between min and max.  The reference evaluates at::native::histogramdd on the CPU copy of the buffer
+// (there is no CUDA histogramdd); so does this class: half-open bins [e_i, e_i+1), the last one closed, edges
+// = linspace(min, max, bins + 1) with ATen's symmetric evaluation.
+class TensorHistogram : public TensorVectorPostprocessor {
+public:
+  static InputParameters validParams() {
+    InputParameters params = TensorPostprocessor::validParams();
+    params.addClassDescription("Compute a histogram of the given tensor.");
+    params.addRequiredParam<Real>("min", "Lower bound of the histogram.");
+    params.addRequiredParam<Real>("max", "Upper bound of the histogram.");
+    params.addRequiredParam<std::size_t>("bins", "Number of histogram bins.");
+    return params;
+  }
+  explicit TensorHistogram(const InputParameters &p)
+    : TensorVectorPostprocessor(p), _min(getParam<Real>("min")), _max(getParam<Real>("max")), _bins(getParam<std::size_t>("bins")) {
+    if (_bins == 0) paramError("bins", "bins>0");
+    if (_min > _max) paramError("min", "max must be greater than min");
+    const std::size_t steps = _bins + 1;
+    const Real step = (_max - _min) / Real(steps - 1);
+    _edges.resize(steps);
+    for (std::size_t i = 0; i < steps; ++i) _edges[i] = i < steps / 2 ? _min + step * Real(i) : _max - step * Real(steps - 1 - i);
+    auto &bin = _vectors["bin"];
+    bin.resize(_bins);
+    _vectors["count"].assign(_bins, 0.0);
+    const Real w = (_max - _min) / Real(_bins);
+    for (std::size_t i = 0; i < _bins; ++i) bin[i] = _min + w / 2.0 + w * Real(i);
+  }
+  void execute() override {
+    if (!_u.defined()) mooseError("buffer '", _buffer_name, "' is not defined");
+    const std::vector<double> host = _domain.toHost(_u);
+    auto &count = _vectors["count"];
+    count.assign(_bins, 0.0);
+    for (double v : host) {
+      if (!(v >= _edges.front() && v <= _edges.back())) continue;
+      std::size_t pos = std::size_t(std::upper_bound(_edges.begin(), _edges.end(), v) - _edges.begin());
+      pos = pos == 0 ? 0 : pos - 1;
+      if (pos >= _bins) pos = _bins - 1;  // v == max belongs to the last bin
+      count[pos] += 1.0;
+    }
+  }
+
+protected:
+  const Real _min, _max;
+  const std::size_t _bins;
+  std::vector<Real> _edges;
+};
+
 // src/postprocessors/ReciprocalIntegral.C:31-52: Re(ubar[0,0,0]) / #cells * volume
 class ReciprocalIntegral : public TensorPostprocessor {
 public:
@@ -237,6 +286,7 @@ protected:
 
 }  // namespace
 
+registerMooseObject("MarlinApp", TensorHistogram);
 registerMooseObject("MarlinApp", TensorInterfaceVelocityPostprocessor);
 registerMooseObject("MarlinApp", ReciprocalIntegral);
 registerMooseObject("MarlinApp", ComputeGroupExecutionCount);

@@ -1156,3 +1156,13 @@ def pp_interface_velocity(problem, name, old):
         v = torch.where(torch.abs(grad) > 1e-3, du / grad, 0.0)
         vsq = v * v if vsq is None else vsq + v * v
     return math.sqrt(float(torch.max(vsq)))
+
+
+def vpp_histogram(problem, name, mn, mx, bins):
+    """src/vectorpostprocessors/TensorHistogram.C:31-84: (bin centres, counts); edges = linspace(min, max, bins+1),
+    at::native::histogramdd on the CPU (the reference falls back to the CPU as well: no CUDA histogramdd)."""
+    edges = torch.linspace(mn, mx, bins + 1, dtype=problem.domain.dtype)
+    u = problem.buf[name].expand(problem.domain.shape).reshape(-1, 1)
+    hist = torch.histogramdd(u, [edges])[0]
+    step = (mx - mn) / bins
+    return [mn + step / 2.0 + step * i for i in range(bins)], hist.tolist()

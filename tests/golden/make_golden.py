@@ -111,7 +111,8 @@ def solver_csvs():
                     ("test/tests/tensor_compute/gold/backandforth_out.csv", "backandforth_out"),
                     ("test/tests/parsed_tensor/gold/local_vars_derivative_out.csv",
                      "local_vars_derivative_out"),
-                    ("test/tests/postprocessors/gold/interface_velocity_out.csv", "interface_velocity_out")]:
+                    ("test/tests/postprocessors/gold/interface_velocity_out.csv", "interface_velocity_out"),
+                    ("test/tests/histogram/gold/test_out_hist_0001.csv", "histogram_out_hist_0001")]:
         if os.path.exists(f"{REF}/{fn}"):
             h, a = read_csv(f"{REF}/{fn}")
             out[key] = a

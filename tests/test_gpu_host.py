@@ -382,6 +382,15 @@ def test_quasistatic_elasticity_input_matches_oracle(tmp_path):
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-11, k
 
 
+def test_histogram_input_matches_csv_gold(tmp_path):
+    """test/tests/histogram/test.i ([VectorPostprocessors] TensorHistogram) -> gold test_out_hist_0001.csv."""
+    gold = np.load(f"{G}/csv_golds.npz")["histogram_out_hist_0001"]
+    run(tmp_path, "histogram.i")
+    head, rows = csv(f"{tmp_path}/histogram_out_hist_0001.csv")
+    assert head == ["bin", "count"] and rows.shape == gold.shape
+    assert np.abs(rows[:, 0] - gold[:, 0]).max() < 1e-13 and np.array_equal(rows[:, 1], gold[:, 1])
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

@@ -217,6 +217,16 @@ def test_interface_velocity_matches_csv_gold():
     assert np.abs(np.array(rows) - gold).max() < 1e-11, (rows, gold)
 
 
+def test_histogram_matches_csv_gold():
+    """test/tests/histogram/test.i -> gold test_out_hist_0001.csv (bin centres, counts)."""
+    gold = np.load(f"{G}/csv_golds.npz")["histogram_out_hist_0001"]
+    d = om.Domain(3, [10, 10, 10], (0, 0, 0), (1.0, 1.0, 1.0))
+    p = om.Problem(d)
+    om.ParsedCompute(p, "c", "0.1*x^2+0.2*y^2+0.3*z^2", extra_symbols=True).compute()
+    centres, counts = om.vpp_histogram(p, "c", 0.0, 1.0, 20)
+    assert np.abs(np.array(centres) - gold[:, 0]).max() < 1e-14 and list(counts) == list(gold[:, 1])
+
+
 def test_fft_roundtrip_even_odd():
     """test/tests/tensor_compute/backandforth.i: fft->ifft is the identity for the even/odd
     1-3-D sizes used there (gold difference exactly 0 at CSV precision)."""
