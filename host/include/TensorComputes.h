@@ -152,6 +152,20 @@ protected:
   ExprKernel _kernel;
 };
 
+// src/tensor_computes/SmoothRectangleCompute.C: box indicator blended between `inside` and `outside`
+// (sharp, half-sine or tanh profile of the distance to the nearest face)
+class SmoothRectangleCompute : public TensorOperator<> {
+public:
+  static InputParameters validParams();
+  explicit SmoothRectangleCompute(const InputParameters &parameters);
+  void computeBuffer() override;
+  // the generated-kernel expression over x, y, z and the constants x1..z2, w, w2 = w/2, vin, vout, pi
+  static std::string expression(unsigned int dim, Real w, const std::string &profile);
+
+protected:
+  ExprKernel _kernel;
+};
+
 // src/tensor_computes/MooseFunctionTensor.C: a MOOSE Function ([Functions], type ParsedFunction)
 // sampled at the cell centres
 class MooseFunctionTensor : public TensorOperator<> {

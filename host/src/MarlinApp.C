@@ -558,7 +558,12 @@ int main(int argc, char **argv) {
       opt.dump_dir = need("--dump-dir");
     else if (a == "--xdmf-selftest")
       return xdmfSelfTest(need("--xdmf-selftest"));
-    else if (a == "--quiet")
+    else if (a == "--smooth-rectangle-expr") {  // DIM WIDTH PROFILE: the kernel expression (CPU test-suite)
+      const unsigned int dim = std::stoul(need("--smooth-rectangle-expr"));
+      const double w = std::stod(need("--smooth-rectangle-expr"));
+      std::cout << SmoothRectangleCompute::expression(dim, w, need("--smooth-rectangle-expr")) << "\n";
+      return 0;
+    } else if (a == "--quiet")
       opt.quiet = true;
     else if (a == "--n-threads" || a == "--color")
       need(a.c_str());

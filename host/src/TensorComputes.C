@@ -463,6 +463,65 @@ SwiftHohenbergLinear::SwiftHohenbergLinear(const InputParameters &parameters) : 
 }
 void SwiftHohenbergLinear::computeBuffer() { _u = _kernel.eval(_domain, {}, _time); }
 
+// ------------------------------------------------------------------------- SmoothRectangleCompute
+registerMooseObject("MarlinApp", SmoothRectangleCompute);
+
+InputParameters SmoothRectangleCompute::validParams() {
+  InputParameters params = TensorOperator<>::validParams();
+  params.addClassDescription("Interpolate a value between the inside and outside of a rectangle smoothly.");
+  params.addRequiredParam<Real>("x1", "The x coordinate of the lower left-hand corner of the box.");
+  params.addRequiredParam<Real>("x2", "The x coordinate of the upper right-hand corner of the box.");
+  params.addRequiredParam<Real>("y1", "The y coordinate of the lower left-hand corner of the box.");
+  params.addRequiredParam<Real>("y2", "The y coordinate of the upper right-hand corner of the box.");
+  params.addParam<Real>("z1", 0, "The z coordinate of the lower left-hand corner of the box.");
+  params.addParam<Real>("z2", 0, "The z coordinate of the upper right-hand corner of the box.");
+  params.addParam<MooseEnum>("profile", MooseEnum("COS TANH"), "Functional dependence for the interface profile");
+  params.addParam<Real>("int_width", 0, "The width of the diffuse interface. Set to 0 for sharp interface.");
+  params.addParam<Real>("inside", 1, "The value inside the rectangle.");
+  params.addParam<Real>("outside", 0, "The value outside the rectangle.");
+  return params;
+}
+
+// src/tensor_computes/SmoothRectangleCompute.C:60-131 as ONE generated kernel over the cell-centre
+// axes: per used axis the distance d to the nearest face, h = [d inside] (sharp), 0.5 + 0.5 sin(pi
+// clamp(d, -w/2, w/2) / w) (COS) or 0.5 + 0.5 tanh(4 d / w) (TANH); u = H inside + (1 - H) outside
+// with H the product over the axes.  The reference's fill values for the unused axes (w/2, 10 w,
+// 5 w) give a factor of exactly one, so those factors are left out.
+std::string SmoothRectangleCompute::expression(unsigned int dim, Real w, const std::string &profile) {
+  static const char *ax[3] = {"x", "y", "z"};
+  std::string expr;
+  if (w <= 0.0) {
+    std::string cond;
+    for (unsigned int d = 0; d < dim; ++d)
+      cond += std::string(d ? " & " : "") + ax[d] + " >= " + ax[d] + "1 & " + ax[d] + " <= " + ax[d] + "2";
+    return "if(" + cond + ", vin, vout)";
+  }
+  if (profile != "COS" && profile != "TANH") return "vout";  // no profile chosen: the reference leaves the indicator at zero
+  std::string prod;
+  for (unsigned int d = 0; d < dim; ++d) {
+    const std::string a = ax[d], dist = "dist_" + a, h = "blend_" + a;
+    expr += dist + " := min(" + a + " - " + a + "1, " + a + "2 - " + a + "); ";
+    if (profile == "COS")
+      expr += h + " := 0.5 + 0.5*sin(pi*max(-w2, min(w2, " + dist + "))/w); ";
+    else
+      expr += h + " := 0.5 + 0.5*tanh(4*" + dist + "/w); ";
+    prod += (d ? "*" : "") + h;
+  }
+  return expr + "blend := " + prod + "; blend*vin + (1 - blend)*vout";
+}
+
+SmoothRectangleCompute::SmoothRectangleCompute(const InputParameters &parameters) : TensorOperator<>(parameters) {
+  const Real w = getParam<Real>("int_width");
+  if (w < 0.0) mooseError("Interface width must be a non-negative real number.");
+  const std::string profile = isParamValid("profile") ? std::string(getParam<MooseEnum>("profile")) : std::string();
+  _kernel.configure(expression(_dim, w, profile), {}, {},
+                    {"x1", "x2", "y1", "y2", "z1", "z2", "w", "w2", "vin", "vout", "pi"},
+                    {getParam<Real>("x1"), getParam<Real>("x2"), getParam<Real>("y1"), getParam<Real>("y2"), getParam<Real>("z1"), getParam<Real>("z2"), w,
+                     w / 2.0, getParam<Real>("inside"), getParam<Real>("outside"), M_PI},
+                    true, MRL_EXPAND_REAL);
+}
+void SmoothRectangleCompute::computeBuffer() { _u = _kernel.eval(_domain, {}, _time); }
+
 // ---------------------------------------------------------------------------- MooseFunctionTensor
 registerMooseObject("MarlinApp", MooseFunctionTensor);
 

@@ -584,6 +584,43 @@ class SwiftHohenbergLinear(Op):
         self.set(self.r - self.alpha * self.alpha * (1.0 - k2) * (1.0 - k2))
 
 
+class SmoothRectangleCompute(Op):
+    """src/tensor_computes/SmoothRectangleCompute.C:60-131: `inside` within the box [x1,x2]x[y1,y2](x[z1,z2]),
+    `outside` elsewhere, blended over int_width by a half sine (COS) or tanh(4 d / w) (TANH) of the
+    distance d to the nearest face per axis; int_width <= 0 is the sharp indicator."""
+
+    def __init__(self, problem, buffer, x1, x2, y1, y2, z1=0.0, z2=0.0, profile="COS", int_width=0.0,
+                 inside=1.0, outside=0.0):
+        super().__init__(problem, buffer)
+        if int_width < 0.0:
+            raise ValueError("Interface width must be a non-negative real number.")
+        self.lo, self.hi = (x1, y1, z1), (x2, y2, z2)
+        self.profile, self.w, self.inside, self.outside = profile, int_width, inside, outside
+
+    def compute(self):
+        d, w = self.d, self.w
+        ax = [d.axis[a].reshape(-1) for a in range(3)]
+        if w <= 0.0:
+            h = [((ax[a] >= self.lo[a]) & (ax[a] <= self.hi[a])) if a < d.dim else torch.ones_like(ax[a], dtype=torch.bool)
+                 for a in range(3)]
+            cond = torch.logical_and(h[0].reshape(-1, 1, 1), torch.logical_and(h[1].reshape(1, -1, 1), h[2].reshape(1, 1, -1)))
+            box = torch.zeros(cond.shape, dtype=d.dtype)
+            box[cond] = 1.0
+        else:
+            dist = [torch.minimum(ax[a] - self.lo[a], self.hi[a] - ax[a]) for a in range(3)]
+            if self.profile == "COS":
+                m = [dist[a].clamp(-w / 2.0, w / 2.0) if a < d.dim else torch.full_like(ax[a], w / 2.0) for a in range(3)]
+                h = [0.5 + 0.5 * torch.sin(math.pi * m[a] / w) for a in range(3)]
+            elif self.profile == "TANH":
+                far = (None, 10 * w, 10 * w / 2.0)
+                m = [dist[a] if a < d.dim else torch.full_like(ax[a], far[a]) for a in range(3)]
+                h = [0.5 + 0.5 * torch.tanh(4 * m[a] / w) for a in range(3)]
+            else:
+                raise ValueError(f"profile {self.profile}")
+            box = h[0].reshape(-1, 1, 1) * h[1].reshape(1, -1, 1) * h[2].reshape(1, 1, -1)
+        self.set((box * self.inside + (1 - box) * self.outside).reshape(d.shape).to(d.dtype))
+
+
 class MooseFunctionTensor(Op):
     """src/tensor_computes/MooseFunctionTensor.C:31-72: a MOOSE Function sampled at the cell centres
     i*dx + dx/2 (note: not the linspace axis of DomainAction).  `functions` maps a ParsedFunction

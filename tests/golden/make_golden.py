@@ -201,6 +201,16 @@ def rotating_grain():
     print("rotating_grain_secant_h5", psi.shape)
 
 
+def smooth_rectangle():
+    """test/tests/tensor_compute/gold/smooth_rectangle.h5: rectangle_cos, rectangle_sharp, rectangle_tanh (100^2,
+    datasets in HDF5 name order)."""
+    streams = zlib_streams(f"{REF}/test/tests/tensor_compute/gold/smooth_rectangle.h5")
+    assert len(streams) == 3
+    cos, sharp, tanh = [np.frombuffer(s, dtype="<f8").reshape(100, 100) for s in streams]
+    np.savez_compressed(f"{OUT}/smooth_rectangle_h5.npz", cos=cos, sharp=sharp, tanh=tanh)
+    print("smooth_rectangle_h5", cos.shape)
+
+
 def kks_no_flux():
     """test/tests/kks/gold/KKS_no_flux_bc.h5 (20^2, transpose = false; per frame c, eta, mu, psi in
     std::map key order) and KKS_no_flux_bc_out.csv."""
@@ -233,6 +243,7 @@ if __name__ == "__main__":
     mech3d()
     mech2d()
     rotating_grain()
+    smooth_rectangle()
     kks_no_flux()
     exodus_more()
     xmf_gold()

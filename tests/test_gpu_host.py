@@ -391,6 +391,18 @@ def test_histogram_input_matches_csv_gold(tmp_path):
     assert np.abs(rows[:, 0] - gold[:, 0]).max() < 1e-13 and np.array_equal(rows[:, 1], gold[:, 1])
 
 
+def test_smooth_rectangle_input_matches_hdf5_gold(tmp_path):
+    """test/tests/tensor_compute/smooth_rectangle.i (SmoothRectangleCompute sharp / COS / TANH as generated kernels)
+    -> gold smooth_rectangle.h5."""
+    g = np.load(f"{G}/smooth_rectangle_h5.npz")
+    names = ("rectangle_sharp", "rectangle_cos", "rectangle_tanh")
+    run(tmp_path, "smooth_rectangle.i", dump=names)
+    for name in names:
+        got = field(tmp_path, name, (100, 100))
+        assert np.abs(got - g[name.split("_")[1]]).max() < 1e-13, name
+    assert np.array_equal(field(tmp_path, "rectangle_sharp", (100, 100)), g["sharp"])
+
+
 def test_ch3d_input_matches_oracle(tmp_path):
     """examples/cahn_hilliard/cahnhilliard2.i-style 3-D run (32^3, 2 steps x 10 substeps) through
     the host objects vs the oracle, rel L2 <= 1e-10 (BASELINE.json north_star)."""

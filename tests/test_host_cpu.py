@@ -163,3 +163,27 @@ def test_every_repository_input_parses_and_names_registered_types():
             top = path.split("/")[0]
             if top in ("TensorComputes", "TensorSolver", "TensorOutputs") or (top == "Postprocessors" and typ.startswith(("Tensor", "Reciprocal", "SemiImplicit", "ComputeGroup"))):
                 assert typ in registered, f"{f}: {path} uses unregistered type {typ}"
+
+
+def test_smooth_rectangle_kernel_expression_matches_gold():
+    """SmoothRectangleCompute (src/tensor_computes/SmoothRectangleCompute.C:60-131) is ONE generated kernel on the
+    device; its expression, as the host object builds it, must (a) compile with NVRTC for sm_100a and (b) give the
+    values of the reference's gold smooth_rectangle.h5 when the C++ expression evaluator (the AST the code generator
+    walks) is run at the cell centres of that case."""
+    import numpy as np
+
+    from marlin_b200 import capi
+    g = np.load(os.path.join(ROOT, "tests", "golden", "smooth_rectangle_h5.npz"))
+    consts = dict(x1=5.0, x2=15.0, y1=5.0, y2=15.0, z1=0.0, z2=0.0, w=1.0, w2=0.5, vin=-1.0, vout=3.0)
+    centre = np.linspace(0.1, 19.9, 100)                      # linspace(min + dx/2, max - dx/2, n), DomainAction.C:227-338
+    pts = [(i, j) for i in (0, 22, 23, 24, 25, 26, 27, 50, 73, 74, 75, 76, 77, 99) for j in (3, 23, 25, 26, 50, 74, 75, 77)]
+    for name, w, profile in [("sharp", 0.0, "NONE"), ("cos", 1.0, "COS"), ("tanh", 1.0, "TANH")]:
+        expr = run("--smooth-rectangle-expr", "2", str(w), profile).stdout.strip()
+        src = capi.expr_check(expr, constants={**consts, "w": w, "w2": w / 2, "pi": np.pi}, extra_symbols=True, expand=capi.EXPAND_REAL)
+        assert "mrl_expr_u32" in src
+        for i, j in pts:
+            v = capi.expr_constant(expr, {**consts, "w": w, "w2": w / 2, "x": centre[i], "y": centre[j]})
+            assert abs(v - g[name][i, j]) < 1e-13, (name, i, j, v, g[name][i, j])
+    e3 = run("--smooth-rectangle-expr", "3", "0.5", "TANH").stdout.strip()
+    assert "dist_z" in e3 and capi.expr_check(e3, constants={**consts, "pi": np.pi}, extra_symbols=True, expand=capi.EXPAND_REAL)
+    assert run("--smooth-rectangle-expr", "2", "1", "NONE").stdout.strip() == "vout"

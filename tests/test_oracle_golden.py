@@ -140,6 +140,27 @@ def test_rotating_grain_secant_matches_hdf5_gold():
     assert np.abs(p2.buf["psi"].numpy() - g[0]).max() < 1e-14
 
 
+def test_smooth_rectangle_matches_hdf5_gold():
+    """test/tests/tensor_compute/smooth_rectangle.i (SmoothRectangleCompute sharp / COS / TANH, 100^2 on [0,20]^2,
+    inside = -1, outside = 3) vs gold/smooth_rectangle.h5 (HDF5Diff): bit for bit."""
+    g = np.load(f"{G}/smooth_rectangle_h5.npz")
+    p = om.Problem(om.Domain(2, [100, 100], maxs=(20.0, 20.0, 1.0)))
+    for name, kw in [("sharp", {}), ("cos", dict(profile="COS", int_width=1.0)), ("tanh", dict(profile="TANH", int_width=1.0))]:
+        om.SmoothRectangleCompute(p, name, 5, 15, 5, 15, inside=-1, outside=3, **kw).compute()
+        assert np.array_equal(p.buf[name].numpy(), g[name]), name
+    # 1-D and 3-D: the unused axes contribute a factor of exactly one
+    p1 = om.Problem(om.Domain(1, [100], maxs=(20.0, 1.0, 1.0)))
+    p3 = om.Problem(om.Domain(3, [100, 12, 10], maxs=(20.0, 6.0, 5.0)))
+    for kw in [{}, dict(profile="COS", int_width=1.0), dict(profile="TANH", int_width=1.0)]:
+        om.SmoothRectangleCompute(p1, "r", 5, 15, 5, 15, inside=-1, outside=3, **kw).compute()
+        assert np.array_equal(p1.buf["r"].numpy(), p.buf["sharp" if not kw else kw["profile"].lower()].numpy()[:, 50])
+        om.SmoothRectangleCompute(p3, "r", 5, 15, 1, 5, z1=1, z2=4, inside=-1, outside=3, **kw).compute()
+        r = p3.buf["r"].numpy()
+        assert r.shape == (100, 12, 10) and abs(r[50, 6, 5] + 1) < 1e-3 and abs(r[0, 0, 0] - 3) < 1e-6
+    with pytest.raises(ValueError):
+        om.SmoothRectangleCompute(p, "r", 5, 15, 5, 15, int_width=-1.0)
+
+
 def test_kks_no_flux_matches_gold():
     """test/tests/kks/KKS_no_flux_bc.i (ReciprocalMatDiffusion, ReciprocalAllenCahn, smoothed-boundary
     mask from a ParsedFunction, AB3, 1000 substeps per step) vs gold KKS_no_flux_bc.h5 (abs_tol 1e-10)
