@@ -40,6 +40,7 @@ CORPUS = [
     ("if(x<=1 & y>2, x*x, 3*y)", ["x", "y"], (), {}),
     ("r2:=x^2+y^2; sqrt(r2)", ["x", "y"], ("x",), {}),
     ("x2:=x^2; sinx2:=sin(x2); 4*sinx2", ["x"], ("x",), {}),
+    ("r:=sqrt(a^2+1); r^2", ["a"], ("a",), {}),     # test/tests/parsed_tensor/local_vars_derivative.i
     ("a:=sin(x^2); a + 2*a + 3*a", ["x"], ("x",), {}),
     ("x^y", ["x", "y"], ("x",), {}),
     ("x^y", ["x", "y"], ("y",), {}),

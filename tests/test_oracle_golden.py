@@ -140,6 +140,26 @@ def test_rotating_grain_secant_matches_hdf5_gold():
     assert np.abs(p2.buf["psi"].numpy() - g[0]).max() < 1e-14
 
 
+def test_local_variable_derivative_matches_csv_gold():
+    """test/tests/parsed_tensor/local_vars_derivative.i: d/da of `r:=sqrt(a^2+1); r^2` through the local binding
+    equals 2a; the gold local_vars_derivative_out.csv holds the integral of the absolute difference, exactly 0 (the
+    simplifier collapses the chain-rule product: 2*r*(a/r) folds to the same roundings as 2*a is NOT guaranteed in
+    general - the gold says it is here)."""
+    gold = np.load(f"{G}/csv_golds.npz")["local_vars_derivative_out"]
+    p = om.Problem(om.Domain(2, [20, 20], maxs=(2.0, 2.0, 1.0)))
+    ops = [om.ParsedCompute(p, "a", "x + 0.5*y", extra_symbols=True),
+           om.ParsedCompute(p, "df_da", "r:=sqrt(a^2+1); r^2", inputs=["a"], derivatives=["a"]),
+           om.ParsedCompute(p, "df_da_exact", "2*a", inputs=["a"]),
+           om.ParsedCompute(p, "error", "abs(df_da - df_da_exact)", inputs=["df_da", "df_da_exact"])]
+    for o in ops:
+        o.compute()
+    assert p.buf["df_da"].shape == (20, 20)
+    integral = om.pp_integral(p, "error")
+    # MOOSE's CSVDiff compares with rel_err 5.5e-6 / abs_zero 1e-10
+    assert abs(integral - gold[0, 1]) < 1e-10, integral
+    assert float(p.buf["error"].abs().max()) < 1e-14
+
+
 def test_smooth_rectangle_matches_hdf5_gold():
     """test/tests/tensor_compute/smooth_rectangle.i (SmoothRectangleCompute sharp / COS / TANH, 100^2 on [0,20]^2,
     inside = -1, outside = 3) vs gold/smooth_rectangle.h5 (HDF5Diff): bit for bit."""
