@@ -165,6 +165,7 @@ private:
   const bool _debug;
   std::map<std::string, std::shared_ptr<TensorBuffer<marlin::Tensor>>> _tensor_buffer;
   std::map<std::string, Real> _constants;
+  mutable std::set<std::string> _fetched_constants;  // requested by name, never declared
   std::vector<std::shared_ptr<TensorOperatorBase>> _ics, _computes, _pps;
   std::shared_ptr<TensorSolver> _solver;
   std::vector<std::shared_ptr<TensorPostprocessor>> _postprocessors;

@@ -67,7 +67,11 @@ Real TensorProblem::getConstant(const std::string &name_or_number, const std::st
   const char *b = name_or_number.c_str();
   char *e = nullptr;
   const double v = std::strtod(b, &e);
-  if (e == b || *e) ::mooseError(what, ": constant '", name_or_number, "' was requested but never declared.");
+  if (e == b || *e) {
+    // reported at EXEC_INITIAL, all at once, like the reference (src/problems/TensorProblem.C:157-165)
+    _fetched_constants.insert(name_or_number);
+    return 0.0;
+  }
   return v;
 }
 
@@ -125,6 +129,12 @@ void TensorProblem::execute(ExecFlagType exec_type) {
       if (out->shouldRun(exec_type)) out->output();
   };
   if (exec_type == EXEC_INITIAL) {
+    if (!_fetched_constants.empty()) {
+      std::string names;
+      for (const auto &n : _fetched_constants) names += (names.empty() ? "" : ", ") + n;
+      ::mooseError(_fetched_constants.size() == 1 ? "Constant " : "Constants ", names, _fetched_constants.size() == 1 ? " was" : " were",
+                   " requested but never declared.");
+    }
     _sub_time = _time;
     for (auto &ic : _ics) ic->computeBuffer();
     run_pps();
