@@ -187,3 +187,35 @@ def test_smooth_rectangle_kernel_expression_matches_gold():
     e3 = run("--smooth-rectangle-expr", "3", "0.5", "TANH").stdout.strip()
     assert "dist_z" in e3 and capi.expr_check(e3, constants={**consts, "pi": np.pi}, extra_symbols=True, expand=capi.EXPAND_REAL)
     assert run("--smooth-rectangle-expr", "2", "1", "NONE").stdout.strip() == "vout"
+
+
+# object types the reference's inputs use that this drop-in leaves out ("out of scope"), with why
+OUT_OF_SCOPE_TYPES = {
+    "FiniteDifferenceLaplacian": "real-space finite differences (test/tests/real_space), not the spectral path",
+    "RealSpaceForwardEuler": "real-space finite differences",
+    "PlainTensorBuffer": "real-space ghost-layer buffers",
+    "GradientTensor": "needs NEML2 (mooseError without it, src/tensor_computes/GradientTensor.C:42-44)",
+    "NEML2TensorCompute": "needs NEML2 (un-vendored)",
+    "LibtorchGibbsEnergy": "TorchScript model file",
+    "ParsedTensor": "not registered in the reference either (stale inputs test.i / sineic.i)",
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_every_spectral_object_type_of_the_reference_inputs_is_registered():
+    """Every `type =` under [TensorComputes] / [TensorSolver] / [TensorOutputs] / [TensorBuffers] in the inputs the
+    reference ships (examples, benchmarks, test/tests) is registered with this driver's factory, except the lattice
+    Boltzmann objects (LBM*) and the short list above."""
+    import re
+    registered = set(run("--list-objects").stdout.split())
+    missing = {}
+    for d in ("examples", "benchmarks", "test/tests"):
+        for f in glob.glob(f"{REF}/{d}/**/*.i", recursive=True):
+            r = subprocess.run([APP, "-i", f, "--parse-only", "ss=10", "cs=0", "order=2"], capture_output=True, text=True, timeout=60)
+            for line in r.stdout.splitlines():
+                m = re.match(r"(\S+)/type = (\S+)$", line)
+                if m and m.group(1).split("/")[0] in ("TensorComputes", "TensorSolver", "TensorOutputs", "TensorBuffers"):
+                    typ = m.group(2)
+                    if typ not in registered and not typ.startswith("LBM") and typ not in OUT_OF_SCOPE_TYPES:
+                        missing.setdefault(typ, f)
+    assert not missing, missing
