@@ -201,6 +201,17 @@ def rotating_grain():
     print("rotating_grain_secant_h5", psi.shape)
 
 
+def ch2d_slab_rank1():
+    """test/tests/cahnhilliard/gold/cahnhilliard.rank0001.h5 (xdmf_output_hdf5_parallel: 2 ranks, FFT_SLAB, CELL, transpose =
+    false): rank 1's local part of c, [20][10] (real space is split along y), at the initial condition and after
+    each of the 10 steps, in time order."""
+    streams = zlib_streams(f"{REF}/test/tests/cahnhilliard/gold/cahnhilliard.rank0001.h5")
+    assert len(streams) == 11
+    c = np.stack([np.frombuffer(s, dtype="<f8").reshape(20, 10) for s in streams])
+    np.savez_compressed(f"{OUT}/ch2d_slab_rank1_h5.npz", c=c)
+    print("ch2d_slab_rank1_h5", c.shape)
+
+
 def smooth_rectangle():
     """test/tests/tensor_compute/gold/smooth_rectangle.h5: rectangle_cos, rectangle_sharp, rectangle_tanh (100^2,
     datasets in HDF5 name order)."""
@@ -244,6 +255,7 @@ if __name__ == "__main__":
     mech2d()
     rotating_grain()
     smooth_rectangle()
+    ch2d_slab_rank1()
     kks_no_flux()
     exodus_more()
     xmf_gold()

@@ -140,6 +140,29 @@ def test_rotating_grain_secant_matches_hdf5_gold():
     assert np.abs(p2.buf["psi"].numpy() - g[0]).max() < 1e-14
 
 
+def test_ch2d_two_rank_slab_gold_equals_serial_run():
+    """test/tests/cahnhilliard/tests:58-70 (xdmf_output_hdf5_parallel: cahnhilliard.i on 2 ranks, parallel_mode =
+    FFT_SLAB, HDF5Diff abs_tol 1e-13 against gold/cahnhilliard.rank0001.h5 = rank 1's local part of c).  The gold pins
+    three facts the multi-GPU slab path relies on: real space is split along y (local shape [20][10]); every rank
+    draws the SAME random numbers for its local block (RandomTensor seeds identically, so the parallel initial condition
+    is the local block repeated along y, not the serial one); and the distributed run equals the serial algorithm on
+    that initial condition - which is how this repository checks its own slab decomposition (parallel == serial)."""
+    g = np.load(f"{G}/ch2d_slab_rank1_h5.npz")["c"]
+    assert g.shape == (11, 20, 10)
+    torch.manual_seed(0)
+    local = torch.rand(20, 10, dtype=torch.float64) * (0.56 - 0.44) + 0.44       # what each rank generates
+    assert np.abs(local.numpy() - g[0]).max() < 1e-15
+    p = oc.ch_problem(2, 20, 3.0, substeps=10)
+    p.ics.insert(1, om.ConstantTensor(p, "mu", 0.0))
+    p.initial()
+    p.buf["c"] = torch.cat([local, local], dim=1)
+    for step in range(1, 11):
+        p.step(1e-3)
+        c = p.buf["c"].numpy()
+        assert np.abs(c[:, 10:] - g[step]).max() < 1e-13, step
+        assert np.array_equal(c[:, :10], c[:, 10:])                               # the two slabs stay identical
+
+
 def test_local_variable_derivative_matches_csv_gold():
     """test/tests/parsed_tensor/local_vars_derivative.i: d/da of `r:=sqrt(a^2+1); r^2` through the local binding
     equals 2a; the gold local_vars_derivative_out.csv holds the integral of the absolute difference, exactly 0 (the
