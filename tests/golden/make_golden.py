@@ -212,6 +212,18 @@ def ch2d_slab_rank1():
     print("ch2d_slab_rank1_h5", c.shape)
 
 
+def ch2d_xdmf_h5():
+    """test/tests/cahnhilliard/gold/cahnhilliard.h5 (xdmf_output_hdf5: c as NODE data [21][21], mu as CELL data [20][20],
+    transpose = false, per frame c then mu): frames 0, 1 and 10."""
+    streams = zlib_streams(f"{REF}/test/tests/cahnhilliard/gold/cahnhilliard.h5")
+    assert [len(s) // 8 for s in streams] == [441, 400] * 11
+    keep = [0, 1, 10]
+    c = np.stack([np.frombuffer(streams[2 * k], dtype="<f8").reshape(21, 21) for k in keep])
+    mu = np.stack([np.frombuffer(streams[2 * k + 1], dtype="<f8").reshape(20, 20) for k in keep])
+    np.savez_compressed(f"{OUT}/ch2d_xdmf_h5.npz", c_node=c, mu_cell=mu, frames=np.array(keep))
+    print("ch2d_xdmf_h5", c.shape, mu.shape)
+
+
 def smooth_rectangle():
     """test/tests/tensor_compute/gold/smooth_rectangle.h5: rectangle_cos, rectangle_sharp, rectangle_tanh (100^2,
     datasets in HDF5 name order)."""
@@ -255,6 +267,7 @@ if __name__ == "__main__":
     mech2d()
     rotating_grain()
     smooth_rectangle()
+    ch2d_xdmf_h5()
     ch2d_slab_rank1()
     kks_no_flux()
     exodus_more()

@@ -140,6 +140,27 @@ def test_rotating_grain_secant_matches_hdf5_gold():
     assert np.abs(p2.buf["psi"].numpy() - g[0]).max() < 1e-14
 
 
+def test_xdmf_node_data_convention_matches_hdf5_gold():
+    """test/tests/cahnhilliard/tests:46-57 (xdmf_output_hdf5, abs_tol 1e-13, gold/cahnhilliard.h5): NODE output of a
+    periodic cell field is the field extended by its first row / column (XDMFTensorOutput.C:529-553), CELL output is
+    the field itself.  host/src/TensorOutputs.C writes the same arrays as raw binary files (tests/test_host_cpu.py::
+    test_xdmf_writer_selftest builds the extension the same way)."""
+    g = np.load(f"{G}/ch2d_xdmf_h5.npz")
+    p = oc.ch_problem(2, 20, 3.0, substeps=10)
+    p.ics.insert(1, om.ConstantTensor(p, "mu", 0.0))
+    p.initial()
+    step = 0
+    for k, frame in enumerate(g["frames"]):
+        while step < frame:
+            p.step(1e-3)
+            step += 1
+        c = p.buf["c"].numpy()
+        ext = np.concatenate([c, c[:1]], 0)
+        ext = np.concatenate([ext, ext[:, :1]], 1)
+        assert np.abs(ext - g["c_node"][k]).max() < 1e-13, frame
+        assert np.abs(p.buf["mu"].numpy() - g["mu_cell"][k]).max() < 1e-13, frame
+
+
 def test_ch2d_two_rank_slab_gold_equals_serial_run():
     """test/tests/cahnhilliard/tests:58-70 (xdmf_output_hdf5_parallel: cahnhilliard.i on 2 ranks, parallel_mode =
     FFT_SLAB, HDF5Diff abs_tol 1e-13 against gold/cahnhilliard.rank0001.h5 = rank 1's local part of c).  The gold pins
