@@ -39,6 +39,7 @@ struct Options {
   std::vector<std::string> dump;
   std::string dump_dir = ".";
   bool quiet = false;
+  bool allow_unused = false;  // --allow-unused / -w: unused input-file parameters are warnings (MooseApp.C:1294-1297)
 };
 
 std::string dirName(const std::string &p) {
@@ -92,7 +93,14 @@ InputParameters MarlinApp::fill(const std::string &type, const hit::Node &block,
     }
     if (!p.have(f->name) || p.entries().at(f->name).is_private) {
       if (also_allowed.count(f->name)) continue;
-      mooseError(_opt.input, ":", f->line, ": unused parameter '", block.fullpath(), "/", f->name, "' (object type ", type, ")");
+      // MOOSE's default is to error on unused parameters (MooseApp.C:477 ERROR_UNUSED, Builder.C:361-399)
+      if (_opt.allow_unused) {
+        std::cerr << _opt.input << ":" << f->line << ": warning: unused parameter '" << block.fullpath() << "/" << f->name << "' (object type "
+                  << type << ")\n";
+        continue;
+      }
+      mooseError(_opt.input, ":", f->line, ": unused parameter '", block.fullpath(), "/", f->name, "' (object type ", type,
+                 ")\n\nAppend --allow-unused (or -w) on the command line to ignore unused parameters.");
     }
     p.setFromInput(f->name, f->value);
   }
@@ -567,9 +575,13 @@ int main(int argc, char **argv) {
       opt.quiet = true;
     else if (a == "--n-threads" || a == "--color")
       need(a.c_str());
+    else if (a.rfind("--compute-device=", 0) == 0 || a.rfind("--n-threads=", 0) == 0)
+      continue;  // the device is always the rank's B200 (TestHarness passes --compute-device=cuda)
     else if (a.find('=') != std::string::npos)
       opt.overrides.push_back(a);
-    else if (a.rfind("--n-threads=", 0) == 0 || a == "--error" || a == "--allow-unused")
+    else if (a == "--allow-unused" || a == "-w")
+      opt.allow_unused = true;
+    else if (a == "--error" || a == "--error-unused" || a == "-e")
       continue;
     else {
       std::cerr << "unknown argument '" << a << "'\nusage: marlin_b200-opt -i input.i [Block/param=value ...] [--check-input] [--output-dir DIR] [--dump buf1,buf2 --dump-dir DIR]\n";

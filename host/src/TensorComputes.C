@@ -428,8 +428,8 @@ FFTSemiImplicit::FFTSemiImplicit(const InputParameters &parameters)
     _old_non_linear_reciprocal(_tensor_problem.getBufferOld(getParam<TensorInputBufferName>("nonlinear_reciprocal"), _history_size)) {}
 
 void FFTSemiImplicit::computeBuffer() {
-  // the legacy integrator is used as a plain compute: the sub step equals the MOOSE step unless a solver set it
-  const Real dt = _sub_dt != 0.0 ? _sub_dt : _tensor_problem.dt();
+  // FFTSemiImplicit.C:43-62: the sub step is whatever the TensorSolver wrote into TensorProblem::subDt()
+  const Real dt = _sub_dt;
   const auto n_old = std::min(_old_reciprocal_buffer.size(), _old_non_linear_reciprocal.size());
   Tensor ubar = _domain.empty(Space::RECIPROCAL, true, 1);
   if (n_old == 0) {

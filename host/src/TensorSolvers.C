@@ -950,7 +950,7 @@ void ETDRK4Solver::substep() {
                          "Ldt := L*t; E := exp(Ldt); den := Ldt*Ldt*Ldt;"
                          "p1 := if(Ldt == 0, t, t*(-4 - 3*Ldt + E*(4 - Ldt))/den);"
                          "p2 := if(Ldt == 0, t*t/2, t*(2 + Ldt + E*(-2 + Ldt))/den);"
-                         "p3 := if(Ldt == 0, t*t*t/6, t*(-4 - 3*Ldt - Ldt*Ldt + E*(4 - Ldt))/den);"
+                         "p3 := if(Ldt == 0, t*t/6, t*(-4 - 3*Ldt - Ldt*Ldt + E*(4 - Ldt))/den);"  // dt^2/6 as coded, ETDRK4Solver.C:89
                          "E*un + p1*N1 + 2*p2*(N2 + N3) + p3*N4",
                          {"L", "un", "N1", "N2", "N3", "N4"}, {LR, LC, LC, LC, LC, LC});
 

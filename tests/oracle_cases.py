@@ -294,3 +294,38 @@ def bm1_problem(n=200, substeps=1000):
                         om.ForwardFFT(p, "cbar", "c")])
     p.solver = om.AdamsBashforthMoulton(p, root, ["c"], ["cbar"], ["kappabarbar"], ["Mbarmubar"], substeps=substeps)
     return p
+
+
+def fft_semi_implicit_problem():
+    """tests/inputs/fft_semi_implicit.i: FFTSemiImplicit as an operator under a forwarding ForwardEulerSolver."""
+    d = om.Domain(2, [32, 24], (0, 0, 0), (4.0, 3.0, 1.0))
+    p = om.Problem(d)
+    p.ics = [om.RandomTensor(p, "c", 0.44, 0.56, 0),
+             om.ReciprocalLaplacianFactor(p, "Mbar", 0.2),
+             om.ReciprocalLaplacianSquareFactor(p, "kappabarbar", -0.001)]
+    root = om.Group(p, [
+        om.ParsedCompute(p, "mu", "0.1*c^2*(c-1)^2", inputs=["c"], derivatives=["c"]),
+        om.ForwardFFT(p, "mubar", "mu"),
+        om.ParsedCompute(p, "Mbarmubar", "Mbar*mubar", inputs=["Mbar", "mubar"]),
+        om.ForwardFFT(p, "cbar", "c"),
+        om.FFTSemiImplicit(p, "cnew", "cbar", "kappabarbar", "Mbarmubar"),
+    ])
+    p.solver = om.ForwardEulerSolver(p, root, substeps=5, forward=[("c", "cnew")])
+    return p
+
+
+def etdrk4_ch_problem():
+    """tests/inputs/etdrk4_cahnhilliard.i: ETDRK4Solver with a non-zero nonlinear term (k = 0 mode included)."""
+    d = om.Domain(2, [32, 32], (0, 0, 0), (4.0, 4.0, 1.0))
+    p = om.Problem(d)
+    p.ics = [om.RandomTensor(p, "c", 0.44, 0.56, 0),
+             om.ReciprocalLaplacianFactor(p, "Mbar", 0.2),
+             om.ReciprocalLaplacianSquareFactor(p, "kappabarbar", -0.5)]
+    root = om.Group(p, [
+        om.ParsedCompute(p, "mu", "0.1*c^2*(c-1)^2", inputs=["c"], derivatives=["c"]),
+        om.ForwardFFT(p, "mubar", "mu"),
+        om.ForwardFFT(p, "cbar", "c"),
+        om.ParsedCompute(p, "Nbar", "Mbar*mubar + 0.5*cbar", inputs=["Mbar", "mubar", "cbar"]),
+    ])
+    p.solver = om.ETDRK4Solver(p, root, ["c"], ["cbar"], ["kappabarbar"], ["Nbar"], substeps=4)
+    return p

@@ -105,6 +105,42 @@ def test_every_reference_input_parses():
         assert r.returncode == 0, f + "\n" + r.stderr
 
 
+# tests/inputs/ref/<file> -> path below the reference root
+VERBATIM = {
+    "cahnhilliard.i": "test/tests/cahnhilliard", "cahnhilliard_explicit.i": "test/tests/cahnhilliard",
+    "diagonal.i": "test/tests/solvers", "coupled.i": "test/tests/solvers", "nl_coupled.i": "test/tests/solvers",
+    "etdrk4_diffusion.i": "test/tests/solvers", "mech3d.i": "test/tests/mechanics", "mech.i": "test/tests/mechanics",
+    "1a_solver.i": "benchmarks/01_spinodal_decomposition", "2a.i": "benchmarks/02_oswald_ripening",
+    "cahnhilliard2.i": "examples/cahn_hilliard", "gradient.i": "test/tests/gradient",
+    "rotating_grain_secant.i": "test/tests/tensor_compute", "KKS_no_flux_bc.i": "test/tests/kks",
+    "postprocessors.i": "test/tests/postprocessors",
+}
+
+
+def test_vendored_reference_inputs_parse_and_are_listed():
+    """tests/inputs/ref/ holds exactly the files of VERBATIM, and the reader resolves each of them."""
+    have = sorted(os.path.basename(f) for f in glob.glob(f"{INP}/ref/*.i"))
+    assert have == sorted(VERBATIM)
+    for f in have:
+        run("-i", f"{INP}/ref/{f}", "--parse-only", "ss=10", "cs=0", "order=2")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_vendored_reference_inputs_are_verbatim():
+    """Byte for byte the reference's files (tests/test_gpu_ref_inputs.py runs them on the GPU)."""
+    for f, d in VERBATIM.items():
+        assert open(f"{INP}/ref/{f}", "rb").read() == open(f"{REF}/{d}/{f}", "rb").read(), f
+
+
+def test_unused_parameters_error_unless_allowed():
+    """MOOSE's default ERROR_UNUSED (moose/framework/src/base/MooseApp.C:477, Builder.C:361-399): the stale
+    `history_size` / `spectral_solve_substeps` of benchmarks/01_spinodal_decomposition/1a_solver.i are rejected when the
+    objects are built, with the reference's hint; --allow-unused / -w turn them into warnings.  Needs no device up to
+    the error: parameters are filled before the context is created - checked on the GPU box in test_gpu_ref_inputs.py."""
+    r = run("-i", f"{INP}/ref/1a_solver.i", "--parse-only", "-w")
+    assert r.returncode == 0
+
+
 def test_xdmf_writer_selftest(tmp_path):
     """XDMFTensorOutput's writer (src/tensor_outputs/XDMFTensorOutput.C:118-221 skeleton, :266-355 data, :358-426
     per-frame XML, :529-553 periodic continuation for NODE, buildAttributeNames :654-668) on synthetic host data:
