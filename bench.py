@@ -26,6 +26,20 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "steps/s for 3D FFT Cahn-Hilliard 512^3 float64 semi-implicit substep"
+PARITY_SUBSTEPS = 5   # 1 at AB1 (quirk Q1) + 4 at AB2: what the cpu_baseline leg runs on the oracle anyway
+
+
+def workload(n):
+    """config.workload: the SAME string in both arms and at every N (the driver compares it)."""
+    return f"CH-3D-{n}: examples/cahn_hilliard/cahnhilliard2.i at n={n} (dx kept), AB2 steady state, float64"
+
+
+def lib_sha256():
+    import hashlib
+    try:
+        return hashlib.sha256(open(os.path.join(ROOT, "marlin_b200", "libmarlin_b200.so"), "rb").read()).hexdigest()[:16]
+    except Exception:
+        return None
 
 
 def algorithmic_bytes(n, nold):
@@ -133,7 +147,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "substeps/s", "n_gpus": args.gpus,
         "steps": k, "warmup": warm + 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CH-3D-{n}: cahnhilliard2.i at n={n}, AB2, libTorch CPU path (oracle port)",
+        "config": {"workload": workload(n), "impl_detail": "libTorch CPU path (oracle port of the reference's operators)",
                    "requested_steps": args.steps},
         "cpu_baseline": {"value": val, "unit": "substeps/s", "cores": cores, "kind": "port",
                          "sample": f"{k} full {n}^3 substeps after {warm + 1} warm-up"},
@@ -295,6 +309,33 @@ def bm1_bench():
     return out
 
 
+def host_driver_bench(n, substeps=50, steps=3):
+    """The path a reference input takes: marlin_b200-opt -i examples/cahn_hilliard/cahnhilliard2.i (verbatim copy under
+    tests/inputs/ref) at n^3 with the file's own dx, constant dt so that every substep is 1e-3 like the headline, XDMF
+    output off.  Host AdamsBashforthMoulton -> automatic fusion -> MRL_NONLIN_EXPR plan (NVRTC-compiled first pass),
+    steady-state substeps batched through mrl_split_substeps.  Reports the device-synchronised solve time of the last
+    step (all substeps at AB2) per substep."""
+    import re
+    app = os.path.join(ROOT, "marlin_b200", "marlin_b200-opt")
+    inp = os.path.join(ROOT, "tests", "inputs", "ref", "cahnhilliard2.i")
+    L = n * 8 * math.pi / 200
+    cmd = [app, "-i", inp, "--timing", "--allow-unused", "--output-dir", "/tmp", f"Domain/nx={n}", f"Domain/ny={n}", f"Domain/nz={n}",
+           f"Domain/xmax={L!r}", f"Domain/ymax={L!r}", f"Domain/zmax={L!r}", f"TensorSolver/substeps={substeps}",
+           f"Executioner/num_steps={steps}", f"Executioner/TimeStepper/dt={substeps * 1e-3!r}", "Executioner/TimeStepper/growth_factor=1",
+           "TensorOutputs/active=", "Outputs/csv=false", "Problem/print_debug_output=true"]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError((r.stdout + r.stderr)[-600:])
+    ms = [float(m) for m in re.findall(r"step \d+ solve ([0-9.e+-]+) ms", r.stderr)]
+    return {"command": "marlin_b200-opt -i tests/inputs/ref/cahnhilliard2.i (verbatim examples/cahn_hilliard/cahnhilliard2.i) "
+                       f"Domain/n*={n} TensorSolver/substeps={substeps} dt={substeps * 1e-3:g} TensorOutputs/active=''",
+            "fused_plan": "fused five-pass plan" in r.stderr + r.stdout,
+            "ms_per_substep_last_step": round(ms[-1] / substeps, 4), "step_solve_ms": [round(v, 2) for v in ms],
+            "process_wall_s": round(wall, 1)}
+
+
 def run_ours(args, rank, world):
     import torch
     from marlin_b200 import capi
@@ -342,6 +383,46 @@ def run_ours(args, rank, world):
     ms = total_ms / args.steps
     value = 1e3 / ms
 
+    # the same substep with the nonlinearity given as the input file's ParsedCompute expression (MRL_NONLIN_EXPR:
+    # symbolic derivative, NVRTC-compiled INTO the first pass) - the plan the host AdamsBashforthMoulton builds
+    expr_leg = None
+    try:
+        ex = capi.Expr(ctx, "0.1*c^2*(c-1)^2", inputs=["c"], derivatives=["c"])
+        c_e = host_c.cuda()
+        plan_e = ctx.split_plan(expr=ex, expr_var=0, expr_inputs=[c_e], M_factor=0.2, L_factor=-0.001, history=1)
+        plan_e.substep(c_e, dt, AB_BETA[0], 0)
+        plan_e.advance_state()
+        for _ in range(3):
+            plan_e.substep(c_e, dt, AB_BETA[1], 1)
+            plan_e.advance_state()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            plan_e.substep(c_e, dt, AB_BETA[1], 1)
+            plan_e.advance_state()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e = e0.elapsed_time(e1) / args.steps
+        expr_leg = {"ms_per_step": round(ms_e, 4), "value": round(1e3 / ms_e, 2), "ratio_to_builtin_double_well": round(ms_e / ms, 4),
+                    "nonlinearity": "d/dc[0.1*c^2*(c-1)^2] compiled by NVRTC into pass P1"}
+        plan_e.close()
+        del c_e
+    except Exception as exn:
+        print(f"# expression-plan leg skipped: {exn}", file=sys.stderr)
+
+    # parity at the bench's own size: PARITY_SUBSTEPS substeps from the seed-0 initial condition (1 x AB1, then AB2),
+    # compared further down with the oracle's field after the same substeps (the cpu_baseline leg runs them anyway)
+    c_par = host_c.cuda()
+    plan_p = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
+    plan_p.substep(c_par, dt, AB_BETA[0], 0)
+    plan_p.advance_state()
+    for _ in range(PARITY_SUBSTEPS - 1):
+        plan_p.substep(c_par, dt, AB_BETA[1], 1)
+        plan_p.advance_state()
+    c_par_host = c_par.cpu()
+    plan_p.close()
+    del c_par
+
     # per-pass device times (CUDA events on the launching stream), still under the clock sampler
     reps = max(3, min(10, args.steps))
     acc = None
@@ -380,6 +461,22 @@ def run_ours(args, rank, world):
     e2e_ms = e2e_run(e2e_steps) / e2e_steps
     # un-overlapped latency of ONE step (upload -> substep -> download -> host sees the result)
     e2e_single_ms = min(e2e_run(1) for _ in range(3))
+
+    # one MOOSE time step as the reference's Transient loop sees it: the field goes up once, `substeps` substeps run on
+    # the device, the field comes down once for the outputs (TensorProblem::execute, src/problems/TensorProblem.C:176-248)
+    moose_sub = 50
+
+    def moose_step():
+        t0 = time.perf_counter()
+        ctx.upload_staged(cbuf[0], host_c)
+        plan.substeps(cbuf[0], dt, AB_BETA[1], 1, moose_sub)
+        ctx.download_staged(out_host[0], cbuf[0])
+        ctx.staged_wait()
+        ctx.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    moose_step()
+    moose_ms = min(moose_step() for _ in range(2))
     clocks = sampler.stop()
 
     s_r, s_c, per_pass = algorithmic_bytes(n, 1)
@@ -397,13 +494,21 @@ def run_ours(args, rank, world):
         passes.append({"pass": nm, "ms": round(t, 4), "alg_gb": round(per_pass[nm] / 1e9, 4),
                        "gbs": round(per_pass[nm] / 1e9 / (t / 1e3), 1)})
     dom = max(range(len(pass_ms)), key=lambda i: pass_ms[i])
-    traffic = None
+    # DRAM traffic per launch: ncu cannot run inside a timed bench, so tools/measure_traffic.py captures all five passes of
+    # THIS library build (dram__bytes_read.sum + dram__bytes_write.sum per launch) into profiles/traffic.json together
+    # with the library's hash; a number recorded for another build is not reported
+    traffic, traffic_note = None, "profiles/traffic.json missing"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(names[dom])
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("lib_sha256") == lib_sha256():
+            traffic = tj["passes"].get(names[dom])
+            traffic_note = {"source": tj.get("_source"), "all_passes": tj["passes"], "kernels": tj.get("kernels")}
+        else:
+            traffic_note = f"profiles/traffic.json was measured on another build (lib {tj.get('lib_sha256')}, this one {lib_sha256()})"
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": names[dom], "achieved": passes[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": round(passes[dom]["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            "frac": round(passes[dom]["gbs"] / peak, 4), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
             "step_achieved": round(b_alg / 1e9 / (ms / 1e3), 1), "step_frac": round(b_alg / 1e9 / (ms / 1e3) / peak, 4),
             "step_alg_gb": round(b_alg / 1e9, 3), "passes": passes}
 
@@ -430,9 +535,16 @@ def run_ours(args, rank, world):
         bm1 = None
         print(f"# BM1a measurement skipped: {ex}", file=sys.stderr)
 
-    cpu = None
+    try:
+        host_leg = host_driver_bench(n)
+        host_leg["ratio_to_builtin_double_well"] = round(host_leg["ms_per_substep_last_step"] / ms, 4)
+    except Exception as ex:
+        host_leg = None
+        print(f"# host-driver leg skipped: {ex}", file=sys.stderr)
+
+    cpu, parity = None, {"status": "not run (--no-cpu)"}
     if not args.no_cpu:
-        p, ostep = oracle_substep_fn(n)
+        p, ostep = oracle_substep_fn(n)     # 2 substeps: AB1, AB2
         ostep()
         ts = []
         for _ in range(2):
@@ -442,21 +554,32 @@ def run_ours(args, rank, world):
         import torch as _t
         cpu = {"value": 1.0 / (sum(ts) / len(ts)), "unit": "substeps/s", "cores": _t.get_num_threads(), "kind": "port",
                "sample": f"2 full {n}^3 substeps after 3 warm-up substeps (libTorch CPU restatement of the reference path)"}
+        assert p.t_step == PARITY_SUBSTEPS
+        ref = p.buf["c"]
+        rel = float(_t.linalg.norm((c_par_host - ref).reshape(-1)) / _t.linalg.norm(ref.reshape(-1)))
+        parity = {"status": "green" if rel <= 1e-10 else "RED", "rel_l2_c_vs_oracle": rel, "tolerance": 1e-10,
+                  "substeps": PARITY_SUBSTEPS, "grid": [n, n, n],
+                  "what": "fused five-pass CUDA plan vs the libTorch-CPU oracle from the same seed-0 initial condition"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "substeps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CH-3D-{n}: examples/cahn_hilliard/cahnhilliard2.i at n={n} (dx kept), AB2 steady state, "
-                               "semi-implicit substep fused into 5 HBM passes",
+        "config": {"workload": workload(n), "impl_detail": "semi-implicit substep fused into 5 HBM passes, built-in double-well nonlinearity",
                    "l2": f"inputs larger than L2 (each field {s_r / 1e9:.2f} GB vs 126 MB L2)", "parallelism": "1 GPU"},
         "clocks": clocks,
         "e2e": {"value": 1e3 / e2e_ms, "unit": "substeps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": nbytes,
                 "d2h_bytes_per_step": nbytes, "single_step_latency_ms": e2e_single_ms,
-                "note": "host wall clock over the pipelined steps; uploads/downloads of neighbouring steps overlap"},
+                "note": "host wall clock over the pipelined steps; uploads/downloads of neighbouring steps overlap",
+                "moose_step": {"substeps": moose_sub, "ms": round(moose_ms, 2), "substeps_per_s": round(moose_sub / moose_ms * 1e3, 1),
+                               "what": "upload c once, 50 substeps through mrl_split_substeps, download c once: one MOOSE time step of "
+                                       "the reference's Transient loop"}},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "parity": parity,
+        "nonlin_expr_plan": expr_leg,
+        "host_driver": host_leg,
         "libtorch_cuda_ms_per_step": cufft_ms,
         "mechanics": mech,
         "bm1a_2d": bm1,

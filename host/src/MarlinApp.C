@@ -17,6 +17,7 @@
 #include <fstream>
 #include <functional>
 #include <iomanip>
+#include <chrono>
 #include <iostream>
 #include <sstream>
 
@@ -39,6 +40,7 @@ struct Options {
   std::vector<std::string> dump;
   std::string dump_dir = ".";
   bool quiet = false;
+  bool timing = false;        // --timing: device-synchronised wall time of every step's solve, on stderr
   bool allow_unused = false;  // --allow-unused / -w: unused input-file parameters are warnings (MooseApp.C:1294-1297)
 };
 
@@ -442,7 +444,17 @@ void MarlinApp::transient() {
     dt_old = t_step > 1 ? dt : step;
     dt = step;
     time = time_old + dt;
+    std::chrono::steady_clock::time_point t0;
+    if (_opt.timing) {
+      _domain->synchronize();
+      t0 = std::chrono::steady_clock::now();
+    }
     _problem->execute(EXEC_TIMESTEP_BEGIN);
+    if (_opt.timing) {
+      _domain->synchronize();
+      std::cerr << "marlin_b200: step " << t_step << " solve " << std::setprecision(9)
+                << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() << " ms\n";
+    }
     _problem->execute(EXEC_TIMESTEP_END);
     runVectorPostprocessors(EXEC_TIMESTEP_END, csv && (out_on & EXEC_TIMESTEP_END), file_base);
     if (out_on & EXEC_TIMESTEP_END) writeCSVRow(false);
@@ -573,6 +585,8 @@ int main(int argc, char **argv) {
       return 0;
     } else if (a == "--quiet")
       opt.quiet = true;
+    else if (a == "--timing")
+      opt.timing = true;
     else if (a == "--n-threads" || a == "--color")
       need(a.c_str());
     else if (a.rfind("--compute-device=", 0) == 0 || a.rfind("--n-threads=", 0) == 0)

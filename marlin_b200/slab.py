@@ -167,7 +167,7 @@ def bench(args, rank, world, metric):
     import sys
     import time
 
-    from bench import ClockSampler, algorithmic_bytes  # noqa: E402 (bench.py is on sys.path)
+    from bench import ClockSampler, algorithmic_bytes, workload  # noqa: E402 (bench.py is on sys.path)
 
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -190,6 +190,45 @@ def bench(args, rank, world, metric):
     dt = 1e-3
     plan.substep(c, dt, AB_BETA[0], 0)
     plan.advance_state()
+
+    # parity inside this very run: every rank repeats the first 6 substeps (1 x AB1, 5 x AB2) of the GLOBAL field with the
+    # single-GPU fused plan on its own device (the plan tests/test_gpu_parity.py::test_ch3d_512_matches_oracle and the
+    # 1-GPU bench line's `parity` object pin to the oracle at this size) and compares its y-slab; max over ranks
+    par_sub = 6
+    for _ in range(par_sub - 1):
+        plan.substep(c, dt, AB_BETA[1], 1)
+        plan.advance_state()
+    parity = None
+    try:
+        ctx1 = capi.Context(local, capi.F64)
+        ctx1.use_torch_stream()
+        ctx1.domain_set(3, (n, n, n), (0,) * 3, (L,) * 3)
+        torch.manual_seed(0)
+        cfull = (torch.rand((n, n, n), dtype=torch.float64) * 0.12 + 0.44).cuda()
+        p1 = ctx1.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
+        p1.substep(cfull, dt, AB_BETA[0], 0)
+        p1.advance_state()
+        for _ in range(par_sub - 1):
+            p1.substep(cfull, dt, AB_BETA[1], 1)
+            p1.advance_state()
+        ref = cfull[:, y0:y0 + nyl, :]
+        num = (c - ref).double().pow(2).sum().reshape(1)
+        den = ref.double().pow(2).sum().reshape(1)
+        mx = (c - ref).abs().max().reshape(1)
+        dist.all_reduce(num)
+        dist.all_reduce(den)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        rel = float((num / den).sqrt().item())
+        parity = {"status": "green" if rel <= 1e-10 else "RED", "rel_l2_c_vs_single_gpu_plan": rel, "max_abs": float(mx.item()),
+                  "tolerance": 1e-10, "substeps": par_sub, "ranks": world,
+                  "what": "slab-decomposed substeps on all ranks vs the single-GPU fused plan (itself pinned to the oracle at "
+                          "this size) on the same global seed-0 initial condition; L2 over the whole grid, max over ranks"}
+        p1.close()
+        ctx1.close()
+        del cfull, ref, p1, ctx1
+        torch.cuda.empty_cache()
+    except Exception as exn:  # e.g. a grid that does not fit one GPU (1024^3 does: 27 GB)
+        parity = {"status": "not run", "why": str(exn)[:200]}
 
     def step():
         plan.substep(c, dt, AB_BETA[1], 1)
@@ -270,10 +309,10 @@ def bench(args, rank, world, metric):
             "metric": metric, "value": 1e3 / ms, "unit": "substeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"CH-3D-{n}: cahnhilliard2.i at n={n}, AB2 steady state, slab-decomposed "
-                                   f"(y real / x reciprocal) over {world} GPUs, half spectrum on the wire, "
-                                   + (f"all-to-all fused into the passes (peer stores over NVLink), {plan.barrier_kind} barrier" if mode == "peer"
-                                      else "NCCL all-to-all between the phases"),
+            "config": {"workload": workload(n),
+                       "impl_detail": f"slab-decomposed (y real / x reciprocal) over {world} GPUs, half spectrum on the wire, "
+                                      + (f"all-to-all fused into the passes (peer stores over NVLink), {plan.barrier_kind} barrier" if mode == "peer"
+                                         else "NCCL all-to-all between the phases"),
                        "l2": "inputs larger than L2" if s_r / world > 126e6 else "per-GPU slab comparable to L2",
                        "parallelism": f"slab{world}"},
             "clocks": clocks,
@@ -289,6 +328,7 @@ def bench(args, rank, world, metric):
                                    "barrier 2", "inverse (x inv, z c2r)"], phases_ms)),
             "forward_chunks": os.environ.get("MRL_SLAB_CHUNKS", "4 (default)"),
             "cpu_baseline": None,
+            "parity": parity,
         }
         print(json.dumps(line), flush=True)
     plan.close()

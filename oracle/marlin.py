@@ -1059,6 +1059,47 @@ class FFTMechanics(Op):
         self.newton_iterations = iiter + 1
 
 
+def green_project_lowmem(d, A2):
+    """G(A) = ifft(ddot42(Ghat4, fft(A))) of FFTMechanics.C:74-84,104-105 WITHOUT materialising Ghat4 (81 complex
+    fields: 11 GB at 256^3).  With Ghat4_ijlm = delta_im q_j q_l / |q|^2 (0 at q = 0) and ddot42(A, B)_ij = A_ijkl B_lk:
+        ddot42(Ghat4, Ahat)_ij = sum_kl delta_il q_j q_k / Q * Ahat_lk = q_j * (sum_k q_k Ahat_ik) / Q.
+    Same arithmetic, contracted row by row; pinned to the materialised form by tests/test_oracle_mech_lowmem.py."""
+    dm = d.dim
+    q = d.kgrid                                   # [..., dm]
+    Q = d.k2
+    Ah = d.fft(A2)                                # [..., dm, dm] complex
+    out = torch.empty_like(Ah)
+    for i in range(dm):
+        s = torch.zeros_like(Ah[..., 0, 0])
+        for k in range(dm):
+            s = s + q[..., k] * Ah[..., i, k]
+        s = torch.where(Q == 0, torch.zeros_like(s), s / torch.where(Q == 0, torch.ones_like(Q), Q))
+        for j in range(dm):
+            out[..., i, j] = q[..., j] * s
+    return d.ifft(out)
+
+
+def tangent_apply_chunked(hyper_cls, d, F, K, mu, x, chunk=32):
+    """K_dF(x) = trans2(ddot42(K4, trans2(x))) (FFTMechanics.C:107-110) with K4 from HyperElasticIsotropic.C:42-52,
+    evaluated on x-chunks of `chunk` planes so that the 81-component tangent (10.9 GB at 256^3) never exists at once.
+    The constitutive law is pointwise in space, so this is the same arithmetic on sub-blocks; returns (P, K_dF)."""
+    P = torch.empty_like(F)
+    out = torch.empty_like(x)
+    for x0 in range(0, F.shape[0], chunk):
+        sl = slice(x0, min(x0 + chunk, F.shape[0]))
+        n_sub = list(F.shape[:d.dim])
+        n_sub[0] = sl.stop - sl.start
+        sub = Domain(d.dim, n_sub + [1] * (3 - d.dim), d.min, d.max, d.dtype)
+        pr = Problem(sub)
+        pr.buf.update(F=F[sl], K=K[sl], mu=mu[sl])
+        h = hyper_cls(pr, "stress", "F", "K", "mu")
+        h.compute()
+        P[sl] = pr.buf["stress"]
+        out[sl] = trans2(ddot42(pr.buf["dstressdstrain"], trans2(x[sl])))
+        del pr, h
+    return P, out
+
+
 class ComputeVonMisesStress(Op):
     """src/tensor_computes/ComputeVonMisesStress.C:30-67 (3-D and 2-D forms as coded)."""
 

@@ -98,8 +98,9 @@ def mech2d_problem(n=32):
     return mech3d_problem(n, substeps=3, l_tol=1e-5, nl_rel_tol=2e-4, nl_abs_tol=2e-3, dim=2, l_max_its=40)
 
 
-def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2, dim=3, l_max_its=None):
-    """test/tests/mechanics/mech3d.i."""
+def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2, dim=3, l_max_its=None, ics_only=False):
+    """test/tests/mechanics/mech3d.i.  ics_only: just the initial fields (phase, K, mu, F) - the FFTMechanics object
+    materialises Ghat4, 11 GB at 256^3."""
     L = 2 * math.pi
     d = om.Domain(dim, [n] * dim, (0, 0, 0), (L, L, L))
     p = om.Problem(d)
@@ -112,6 +113,8 @@ def mech3d_problem(n=16, substeps=10, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e
                          constant_names=["mua", "mub"], constant_expressions=["0.5", "5"]),
         om.RankTwoIdentity(p, "F"),
     ]
+    if ics_only:
+        return p
     hyper = om.HyperElasticIsotropic(p, "stress", "Fnew", "K", "mu")
     mech = om.FFTMechanics(p, "Fnew", hyper, "K", "mu", F="F", stress="stress",
                            applied_macroscopic_strain="applied_strain", l_tol=l_tol,

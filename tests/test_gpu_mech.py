@@ -39,9 +39,9 @@ def ctx():
     c.close()
 
 
-def _setup(ctx, n):
+def _setup(ctx, n, ics_only=False):
     from marlin_b200 import capi
-    p = oc.mech3d_problem(n=n)
+    p = oc.mech3d_problem(n=n, ics_only=ics_only)
     p.initial()
     L = 2 * math.pi
     ctx.domain_set(3, (n, n, n), (0,) * 3, (L,) * 3)
@@ -50,9 +50,10 @@ def _setup(ctx, n):
     return p, plan
 
 
-@pytest.mark.parametrize("n", [16, 20, 32])
+@pytest.mark.parametrize("n", [16, 20, 32, 64, 128])
 def test_mech_operators_match_oracle(ctx, n):
-    """constitutive law, Green-operator projection and the CG operator on random states."""
+    """constitutive law, Green-operator projection and the CG operator on random states (128: the TMA-pipelined
+    passes and the fused Green-projection pass k_mech_fused_tma, against the oracle's materialised Ghat4 / K4)."""
     p, plan = _setup(ctx, n)
     torch.manual_seed(4)
     F = torch.eye(3, dtype=torch.float64).expand(n, n, n, 3, 3) + 0.1 * torch.rand(n, n, n, 3, 3, dtype=torch.float64)
@@ -93,6 +94,51 @@ def test_mech3d_matches_gold_and_oracle_iterations(ctx):
         assert rel_l2(aos(ctx, F), p.buf["F"]) < 1e-10
         assert rel_l2(aos(ctx, P), p.buf["stress"]) < 1e-10
         assert oracle_its[0] == p.mech.newton_iterations and oracle_its[1] == p.mech.cg_iterations, (oracle_its, p.mech.cg_iterations)
+    plan.close()
+
+
+@pytest.mark.parametrize("n", [64, 128])
+def test_mech3d_substep_matches_oracle_on_tma_sizes(ctx, n):
+    """One MOOSE step of test/tests/mechanics/mech3d.i at n = 64 / 128 (two substeps: the first has a zero applied shear
+    and returns at once, the second runs the full Newton-CG solve) against the oracle: F, stress, Newton and
+    per-solve CG iteration counts.  128^3 runs every FFT pass, the fused Green projection and the 128-bit CG kernels
+    the 256^3 bench line times."""
+    p, plan = _setup(ctx, n)
+    F = soa(ctx, p.buf["F"])
+    dt, substeps = 0.02, 2
+    p.solver.substeps = substeps
+    p.step(dt)
+    for s in range(substeps):
+        sub_time = s * dt / substeps
+        avg = [ctx.reduce(0, F[c]) / n ** 3 for c in range(9)]
+        applied = [(1.0 if c in (0, 4, 8) else 0.0) - avg[c] for c in range(9)]
+        applied[1] += sub_time
+        P, st = plan.solve(F, applied)
+    its = (st.newton_iterations, list(st.cg_iterations[:st.cg_solves]))
+    assert rel_l2(aos(ctx, F), p.buf["F"]) < 1e-10
+    assert rel_l2(aos(ctx, P), p.buf["stress"]) < 1e-10
+    assert its[0] == p.mech.newton_iterations and its[1] == p.mech.cg_iterations, (its, p.mech.cg_iterations)
+    assert sum(its[1]) > 20      # a real solve, not the trivial first substep
+    plan.close()
+
+
+def test_mech_256_operators_match_oracle(ctx):
+    """BASELINE.json north_star size of the mechanics (256^3): constitutive law, G and G(K4:x) of the FFTCfg<256,...>
+    TMA instantiations against the oracle evaluated WITHOUT materialising Ghat4 / K4 (11 GB each at this size):
+    oracle.green_project_lowmem / tangent_apply_chunked, which tests/test_oracle_mech_lowmem.py pins to the
+    materialised forms."""
+    n = 256
+    p, plan = _setup(ctx, n, ics_only=True)
+    d = p.domain
+    torch.manual_seed(4)
+    F = (torch.eye(3, dtype=torch.float64).expand(n, n, n, 3, 3) + 0.1 * torch.rand(n, n, n, 3, 3, dtype=torch.float64)).contiguous()
+    x = torch.rand(n, n, n, 3, 3, dtype=torch.float64) - 0.5
+    Fs, xs = soa(ctx, F), soa(ctx, x)
+    P_ref, KdF = om.tangent_apply_chunked(om.HyperElasticIsotropic, d, F, p.buf["K"], p.buf["mu"], x, chunk=16)
+    assert rel_l2(aos(ctx, plan.constitutive(Fs)), P_ref) < 1e-13
+    del P_ref
+    assert rel_l2(aos(ctx, plan.apply_G(xs)), om.green_project_lowmem(d, x)) < 1e-12
+    assert rel_l2(aos(ctx, plan.apply_GK(Fs, xs)), om.green_project_lowmem(d, KdF)) < 1e-12
     plan.close()
 
 

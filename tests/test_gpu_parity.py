@@ -417,6 +417,65 @@ def test_substeps_graph_replay_is_bit_identical(dim, n, history):
         c2.close()
 
 
+# ------------------------------------------------------------------ BASELINE's full size against the oracle
+_ORACLE_512 = {}
+
+
+def _oracle_512(substeps):
+    """CH-3D-512 (examples/cahn_hilliard/cahnhilliard2.i at n = 512, dx kept), 2 MOOSE steps x `substeps` on the oracle
+    (about 1.6 s per substep on the GPU box's 16 host threads); cached for the parametrised test."""
+    if substeps not in _ORACLE_512:
+        n = 512
+        p = oc.ch_problem(3, n, n * 8 * math.pi / 200, substeps=substeps)
+        p.initial()
+        c0 = p.buf["c"].clone()
+        for _ in range(2):
+            p.step(substeps * 1e-3)
+        _ORACLE_512[substeps] = (p.domain, c0, p.buf["c"].clone(), p.buf["mu"].clone())
+        del p
+    return _ORACLE_512[substeps]
+
+
+@pytest.mark.parametrize("nonlin", ["double_well", "expr"])
+def test_ch3d_512_matches_oracle(ctx, nonlin):
+    """BASELINE.json north_star size: the FFTCfg<512,...> TMA instantiations of all five passes against the ORACLE
+    (not against another GPU path): 2 MOOSE steps x 3 substeps from the seed-0 initial condition of the bench
+    (3 substeps at AB1 by quirk Q1, 3 at AB2), relative L2 <= 1e-10 on c, and on mu = f'(c) of the last substep
+    for the expression plan.  `double_well` is the built-in nonlinearity the bench times, `expr` the
+    ParsedCompute expression of the input file compiled into the first pass (MRL_NONLIN_EXPR, the path a
+    reference input takes through the host AdamsBashforthMoulton)."""
+    from marlin_b200 import capi
+    sub = 3
+    d, c0, c_ref, mu_ref = _oracle_512(sub)
+    ctx.domain_set(3, d.n[:3], d.min, d.max)
+    c = c0.cuda().contiguous()
+    mu = None
+    if nonlin == "expr":
+        e = capi.Expr(ctx, "0.1*c^2*(c-1)^2", inputs=["c"], derivatives=["c"])
+        mu = torch.empty_like(c)
+        plan = ctx.split_plan(expr=e, expr_var=0, expr_inputs=[c], M_factor=0.2, L_factor=-0.001, history=1, g_out=mu)
+    else:
+        plan = ctx.split_plan(double_well=(0.1, 0.0, 1.0), M_factor=0.2, L_factor=-0.001, history=1)
+    drv = SplitDriver(plan, c, sub, predictor_order=2)
+    for _ in range(2):
+        drv.step(sub * 1e-3)
+    assert rel_l2(c.cpu(), c_ref) < 1e-10
+    if mu is not None:
+        assert rel_l2(mu.cpu(), mu_ref) < 1e-10
+    plan.close()
+
+
+def test_ch3d_256_matches_oracle(ctx):
+    """256^3 (FFTCfg<256,...> TMA instantiations), 2 x 5 substeps, AB3, mobility / linear operator from buffers."""
+    n = 256
+    p = oc.ch_problem(3, n, n * 8 * math.pi / 200, substeps=5, predictor_order=3)
+    p.initial()
+    got = _run_split(ctx, p, 2, 5e-3, 5, closed=False, order=3)
+    for _ in range(2):
+        p.step(5e-3)
+    assert rel_l2(got, p.buf["c"]) < 1e-10
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_512_properties(ctx):
     """At BASELINE's 512^3 the oracle is too slow for a test; check size-independent
