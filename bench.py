@@ -387,6 +387,8 @@ def run_ours(args, rank, world):
     # symbolic derivative, NVRTC-compiled INTO the first pass) - the plan the host AdamsBashforthMoulton builds
     expr_leg = None
     try:
+        if args.fast:
+            raise RuntimeError("--fast")
         ex = capi.Expr(ctx, "0.1*c^2*(c-1)^2", inputs=["c"], derivatives=["c"])
         c_e = host_c.cuda()
         plan_e = ctx.split_plan(expr=ex, expr_var=0, expr_inputs=[c_e], M_factor=0.2, L_factor=-0.001, history=1)
@@ -518,24 +520,32 @@ def run_ours(args, rank, world):
     del c
     torch.cuda.empty_cache()
     try:
+        if args.fast:
+            raise RuntimeError("--fast")
         cufft_ms = libtorch_cuda_substep_ms(n, L)
     except Exception as ex:  # e.g. out of memory for the un-fused temporaries
         cufft_ms = None
         print(f"# libtorch-cuda comparison skipped: {ex}", file=sys.stderr)
 
     try:
+        if args.fast:
+            raise RuntimeError("--fast")
         mech = mechanics_bench(256, peak)
     except Exception as ex:
         mech = None
         print(f"# mechanics measurement skipped: {ex}", file=sys.stderr)
 
     try:
+        if args.fast:
+            raise RuntimeError("--fast")
         bm1 = bm1_bench()
     except Exception as ex:
         bm1 = None
         print(f"# BM1a measurement skipped: {ex}", file=sys.stderr)
 
     try:
+        if args.fast:
+            raise RuntimeError("--fast")
         host_leg = host_driver_bench(n)
         host_leg["ratio_to_builtin_double_well"] = round(host_leg["ms_per_substep_last_step"] / ms, 4)
     except Exception as ex:
@@ -597,6 +607,7 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("MRL_BENCH_N", "512")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fast", action="store_true", help="development: headline timing and per-pass times only (no side legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -40,6 +40,7 @@ struct Options {
   std::vector<std::string> dump;
   std::string dump_dir = ".";
   bool quiet = false;
+  std::string compute_device;  // --compute-device=<dev> (moose TestHarness; src/base/MarlinInit.C:12-18)
   bool timing = false;        // --timing: device-synchronised wall time of every step's solve, on stderr
   bool allow_unused = false;  // --allow-unused / -w: unused input-file parameters are warnings (MooseApp.C:1294-1297)
 };
@@ -144,7 +145,11 @@ void MarlinApp::buildObjects() {
 
   const hit::Node *dom = _root->find("Domain");
   if (!dom || !dom->is_section) mooseError(_opt.input, ": missing [Domain] block");
-  _domain = std::make_unique<DomainAction>(fill("DomainAction", *dom, "Domain"));
+  {
+    InputParameters dp = fill("DomainAction", *dom, "Domain");
+    if (!_opt.compute_device.empty()) dp.set<std::string>("_cli_compute_device", _opt.compute_device);
+    _domain = std::make_unique<DomainAction>(dp);
+  }
 
   // [Problem]
   {
@@ -589,8 +594,10 @@ int main(int argc, char **argv) {
       opt.timing = true;
     else if (a == "--n-threads" || a == "--color")
       need(a.c_str());
-    else if (a.rfind("--compute-device=", 0) == 0 || a.rfind("--n-threads=", 0) == 0)
-      continue;  // the device is always the rank's B200 (TestHarness passes --compute-device=cuda)
+    else if (a.rfind("--compute-device=", 0) == 0)
+      opt.compute_device = a.substr(17);
+    else if (a.rfind("--n-threads=", 0) == 0)
+      continue;
     else if (a.find('=') != std::string::npos)
       opt.overrides.push_back(a);
     else if (a == "--allow-unused" || a == "-w")

@@ -3,7 +3,7 @@
 #include <cstring>
 
 #include "k_common.cuh"
-#include "mrl_passes_tma.cuh"
+#include "mrl_passes_slab.cuh"
 
 namespace mrl {
 
@@ -69,6 +69,29 @@ static cudaError_t make_map4(CUtensorMap *tm, const void *base, unsigned long lo
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// General tiled map of rank `rank` (<= 5) over scalars of type T: dims / box fastest first, strides in bytes for dims 1..
+template <class T>
+static cudaError_t make_mapn(CUtensorMap *tm, const void *base, int rank, const unsigned long long *dims, const unsigned long long *strides,
+                             const unsigned *box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  if ((unsigned long long)base & 15ull) return cudaErrorNotSupported;
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    if (box[i] > 256 || box[i] == 0) return cudaErrorNotSupported;
+    if (i > 0) {
+      st[i - 1] = strides[i - 1];
+      if (strides[i - 1] & 15ull) return cudaErrorNotSupported;
+    }
+  }
+  const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(tm, dt, rank, const_cast<void *>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
 
 bool tma_enabled() {
   static int on = [] {
@@ -155,13 +178,14 @@ template <class T> cudaError_t launch_strided_tma(const LaunchCtx &lc, const Str
 }
 
 // ------------------------------------------------------------------ fused P3
-template <class T, class C, int TK, int NG>
-static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, const SpectralUpdate<T> &up0, const cx<T> *tw) {
+template <class T, class C, int TK, int NG, int SLAB>
+static cudaError_t fused_tma_go1(const LaunchCtx &lc, const FusedIO<T> &io0, const SpectralUpdate<T> &up0, const cx<T> *tw) {
   constexpr size_t smem = (size_t)(NG * 3 * C::N * TK) * sizeof(cx<T>) + NG * 3 * 8 + 128;
   static_assert(smem <= kSmemBudget, "fused_tma: shared memory budget");
   static_assert(NG * TK * C::TP <= 1024, "fused_tma: block size");
   if (!io0.slab && io0.nouter != 1) return cudaErrorNotSupported;
   if (io0.slab && (io0.nyl * io0.nranks != io0.n || io0.pitch != io0.ncols)) return cudaErrorNotSupported;
+  if (io0.slab == 2 && (io0.ncols % TK || io0.nouter > 256 || !io0.peer_tab)) return cudaErrorNotSupported;
   FusedTmaIO<T> io;
   io.outU = io0.outU;
   io.n = io0.n;
@@ -174,6 +198,13 @@ static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, cons
   io.nyl = io0.nyl;
   io.peer_tab = io0.slab ? io0.peer_tab : nullptr;
   io.peer_x0 = io0.peer_x0;
+  io.kzb_major = io0.kzb_major;
+  io.nx = io0.nx;
+  io.rank = io0.rank;
+  io.nranks = io0.nranks;
+  io.flag_wait = io0.slab == 2 ? io0.flag_wait : nullptr;
+  io.flag_expect = io0.flag_expect;
+  io.flag_tab = io0.slab == 2 ? io0.flag_tab : nullptr;
   SpectralUpdate2<T> up;
   memset(&up, 0, sizeof up);
   up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz;
@@ -190,7 +221,17 @@ static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, cons
   CUtensorMap tmC, tmG, tmO;
   const void *oldp = up0.nold > 0 ? (const void *)up0.Nold[0] : (const void *)io0.inC;
   cudaError_t e;
-  if (io.slab) {
+  if (io.slab == 2) {
+    // blocked staging R = [source][ncb][nyl][nxl][W]: one box = (W columns, one xl, all yl, one block, all sources)
+    const unsigned long long W2 = 2ull * TK, es = sizeof(T);
+    const unsigned long long dims[5] = {W2, (unsigned long long)io.nouter, (unsigned long long)io.nyl, (unsigned long long)io.ncb,
+                                        (unsigned long long)io0.nranks};
+    const unsigned long long st[4] = {W2 * es, W2 * es * io.nouter, W2 * es * io.nouter * io.nyl, W2 * es * io.nouter * io.nyl * io.ncb};
+    const unsigned box[5] = {(unsigned)W2, 1u, (unsigned)io.nyl, 1u, (unsigned)io0.nranks};
+    e = make_mapn<T>(&tmC, io0.inC, 5, dims, st, box);
+    if (e == cudaSuccess) e = make_mapn<T>(&tmG, io0.inG, 5, dims, st, box);
+    if (e == cudaSuccess) e = make_map4<T>(&tmO, up0.nold > 0 ? (const void *)up0.Nold[0] : io0.ring_old, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
+  } else if (io.slab) {
     e = make_map4<T>(&tmC, io0.inC, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
     if (e == cudaSuccess) e = make_map4<T>(&tmG, io0.inG, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
     if (e == cudaSuccess) e = make_map4<T>(&tmO, oldp, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
@@ -200,7 +241,7 @@ static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, cons
     if (e == cudaSuccess) e = make_map3<T>(&tmO, oldp, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
   }
   if (e != cudaSuccess) return e;
-  auto k = k_fused_tma<T, C, TK, NG>;
+  auto k = k_fused_tma<T, C, TK, NG, SLAB>;
   int per_sm = 0;
   e = kernel_prep((const void *)k, NG * TK * C::TP, smem, &per_sm);
   if (e != cudaSuccess) return e;
@@ -208,6 +249,15 @@ static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io0, cons
   const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
   k<<<grid, NG * TK * C::TP, smem, lc.stream>>>(tmC, tmG, tmO, io, up, tw);
   return cudaGetLastError();
+}
+template <class T, class C, int TK, int NG>
+static cudaError_t fused_tma_go(const LaunchCtx &lc, const FusedIO<T> &io, const SpectralUpdate<T> &up, const cx<T> *tw) {
+  switch (io.slab) {
+    case 0: return fused_tma_go1<T, C, TK, NG, 0>(lc, io, up, tw);
+    case 1: return fused_tma_go1<T, C, TK, NG, 1>(lc, io, up, tw);
+    case 2: return fused_tma_go1<T, C, TK, NG, 2>(lc, io, up, tw);
+    default: return cudaErrorNotSupported;
+  }
 }
 
 template <class T>
@@ -429,6 +479,103 @@ cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp,
   }
 }
 
+// ------------------------------------------------------------------ slab x passes with bulk peer stores
+template <class T, class C, int TK, int NG, int NS>
+static cudaError_t slab_xfwd_go(const LaunchCtx &lc, const cx<T> *in, const SlabXIO<T> &io, const cx<T> *tw) {
+  constexpr size_t smem = (size_t)((NS + NG) * C::N * TK) * sizeof(cx<T>) + NS * 8 + 128;
+  static_assert(smem <= kSmemBudget, "slab_xfwd: shared memory budget");
+  static_assert(NG * TK * C::TP <= 1024, "slab_xfwd: block size");
+  if (io.n != C::N || io.nxl * io.nranks != io.n) return cudaErrorNotSupported;
+  const int ncp = io.kb * TK;
+  CUtensorMap tm;
+  const unsigned long long rowb = (unsigned long long)io.nyl * ncp * sizeof(cx<T>);
+  cudaError_t e = make_map3<T>(&tm, in, 2ull * io.nyl * ncp, io.n, io.nf, rowb, rowb * io.n, 2 * TK, C::N < 256 ? C::N : 256);
+  if (e != cudaSuccess) return e;
+  auto k = k_slab_xfwd<T, C, TK, NG, NS>;
+  int per_sm = 0;
+  e = kernel_prep((const void *)k, NG * TK * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (long long)io.nf * io.ych * io.kb;
+  const int grid = (int)(ntiles < lc.sm_count ? ntiles : lc.sm_count);
+  k<<<grid, NG * TK * C::TP, smem, lc.stream>>>(tm, io, tw);
+  return cudaGetLastError();
+}
+
+// Forward x pass of io.nf fields of the natural slab `in` = [nf][nx][nyl][ncp]; the result rows go to the peers' blocked
+// staging R (io.peer_tab) as bulk copies.  The column-block width of every size equals fused_tma_tk().
+template <class T> cudaError_t launch_slab_xfwd(const LaunchCtx &lc, const cx<T> *in, const SlabXIO<T> &io, const cx<T> *tw, int n) {
+  if (!tma_enabled()) return cudaErrorNotSupported;
+  if constexpr (sizeof(T) == 8) {
+    switch (n) {
+      case 128: return slab_xfwd_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 6>(lc, in, io, tw);
+      case 256: return slab_xfwd_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 2, 4>(lc, in, io, tw);
+      case 512: return slab_xfwd_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1, 2>(lc, in, io, tw);
+      case 1024: return slab_xfwd_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 1, 2>(lc, in, io, tw);
+      default: return cudaErrorNotSupported;
+    }
+  } else {
+    switch (n) {
+      case 128: return slab_xfwd_go<T, FFTCfg<128, 16, 8, 4, 4>, 16, 2, 6>(lc, in, io, tw);
+      case 256: return slab_xfwd_go<T, FFTCfg<256, 32, 8, 8, 4>, 16, 2, 4>(lc, in, io, tw);
+      case 512: return slab_xfwd_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 2, 4>(lc, in, io, tw);
+      case 1024: return slab_xfwd_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 8, 1, 2>(lc, in, io, tw);
+      default: return cudaErrorNotSupported;
+    }
+  }
+}
+
+template <class T, class C, int TK, int NG, int NS>
+static cudaError_t slab_xinv_go(const LaunchCtx &lc, const cx<T> *S, const SlabXIO<T> &io, const cx<T> *tw) {
+  constexpr size_t smem = (size_t)(NS * C::N * TK) * sizeof(cx<T>) + NS * 8 + 128;
+  static_assert(smem <= kSmemBudget, "slab_xinv: shared memory budget");
+  static_assert(NG * TK * C::TP <= 1024, "slab_xinv: block size");
+  if (io.n != C::N) return cudaErrorNotSupported;
+  // S = [kb][nx][nyl][W]
+  const unsigned long long W2 = 2ull * TK, es = sizeof(T);
+  const unsigned long long dims[4] = {W2, (unsigned long long)io.nyl, (unsigned long long)io.n, (unsigned long long)io.kb};
+  const unsigned long long st[3] = {W2 * es, W2 * es * io.nyl, W2 * es * io.nyl * io.n};
+  const unsigned box[4] = {(unsigned)W2, 1u, (unsigned)(C::N < 256 ? C::N : 256), 1u};
+  CUtensorMap tm;
+  cudaError_t e = make_mapn<T>(&tm, S, 4, dims, st, box);
+  if (e != cudaSuccess) return e;
+  auto k = k_slab_xinv<T, C, TK, NG, NS>;
+  int per_sm = 0;
+  e = kernel_prep((const void *)k, NG * TK * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (long long)io.nyl * io.kb;
+  const int grid = (int)(ntiles < lc.sm_count ? ntiles : lc.sm_count);
+  k<<<grid, NG * TK * C::TP, smem, lc.stream>>>(tm, io, tw);
+  return cudaGetLastError();
+}
+
+// Inverse x pass: blocked return staging S -> natural slab io.out = [nx][nyl][ncp]
+template <class T> cudaError_t launch_slab_xinv(const LaunchCtx &lc, const cx<T> *S, const SlabXIO<T> &io, const cx<T> *tw, int n) {
+  if (!tma_enabled()) return cudaErrorNotSupported;
+  if constexpr (sizeof(T) == 8) {
+    switch (n) {
+      case 128: return slab_xinv_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 8>(lc, S, io, tw);
+      case 256: return slab_xinv_go<T, FFTCfg<256, 32, 8, 8, 4>, 8, 2, 6>(lc, S, io, tw);
+      case 512: return slab_xinv_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 1, 3>(lc, S, io, tw);
+      case 1024: return slab_xinv_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 4, 1, 3>(lc, S, io, tw);
+      default: return cudaErrorNotSupported;
+    }
+  } else {
+    switch (n) {
+      case 128: return slab_xinv_go<T, FFTCfg<128, 16, 8, 4, 4>, 16, 4, 8>(lc, S, io, tw);
+      case 256: return slab_xinv_go<T, FFTCfg<256, 32, 8, 8, 4>, 16, 2, 6>(lc, S, io, tw);
+      case 512: return slab_xinv_go<T, FFTCfg<512, 64, 8, 8, 8>, 8, 2, 6>(lc, S, io, tw);
+      case 1024: return slab_xinv_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 8, 1, 3>(lc, S, io, tw);
+      default: return cudaErrorNotSupported;
+    }
+  }
+}
+
+// column-block width (TK) of the fused pass for a transform length (the blocked layouts need the same width on all passes)
+template <class T> int fused_tma_tk(int n) {
+  if constexpr (sizeof(T) == 8) return n == 1024 ? 4 : (n == 128 || n == 256 || n == 512) ? 8 : 0;
+  else return n == 128 || n == 256 ? 16 : (n == 512 || n == 1024) ? 8 : 0;
+}
+
 #define INST(T)                                                                                                          \
   template cudaError_t launch_mech_fused_tma<T>(const LaunchCtx &, cx<T> *, const T *, const T *, const T *, int, int, int, int, \
                                                 const cx<T> *);                                                          \
@@ -438,6 +585,9 @@ cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp,
   template cudaError_t launch_zfwd_nonlin_tma<T>(const LaunchCtx &, const T *, T *, cx<T> *, cx<T> *, long long, int,    \
                                                  int, const NonlinDesc &, const cx<T> *, const RowMap &);                \
   template cudaError_t launch_zfwd_pairs_tma<T>(const LaunchCtx &, const T *, cx<T> *, long long, int, int, const cx<T> *);  \
+  template cudaError_t launch_slab_xfwd<T>(const LaunchCtx &, const cx<T> *, const SlabXIO<T> &, const cx<T> *, int);        \
+  template cudaError_t launch_slab_xinv<T>(const LaunchCtx &, const cx<T> *, const SlabXIO<T> &, const cx<T> *, int);         \
+  template int fused_tma_tk<T>(int);                                                                                       \
   template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, int, T *, long long, int, T, const cx<T> *);
 INST(double)
 INST(float)

@@ -15,6 +15,7 @@
 
 #include "../../include/marlin_b200.h"
 #include "mrl_internal.h"
+#include "mrl_passes_slab.cuh"
 
 using namespace mrl;
 
@@ -1078,28 +1079,49 @@ extern "C" int mrl_slab_plan_destroy(mrl_slab_plan *p) {
   for (void *q : p->opened) cudaIpcCloseMemHandle(q);
   cudaFree(p->peer_recv_tab);
   cudaFree(p->peer_send_tab);
+  cudaFree(p->flag1_tab);
+  cudaFree(p->flag2_tab);
   if (p->owns) {
     cudaFree(p->send_fwd);
     cudaFree(p->recv_fwd);
+    cudaFree(p->ret_stage);
   }
   delete p;
   return MRL_OK;
 }
 
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
 extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc *d, mrl_slab_plan **out) {
   if (!ctx || !d || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create_peer: bad arguments");
   if (ctx->dim != 3 || !ctx->nyl) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create_peer: slab domain not set");
   CK(cudaSetDevice(ctx->device));
-  const size_t esz = ctx->precision == MRL_F64 ? 16 : 8;
-  const size_t fbytes = (size_t)ctx->n[0] * ctx->nyl * slab_pitch(ctx) * esz;
-  void *sf = nullptr, *rf = nullptr;
-  CK(cudaMalloc(&sf, 2 * fbytes));
-  // recv_fwd carries the cross-rank barrier flags (one 8-byte slot per rank) behind the spectra
-  const size_t flag_off = (2 * fbytes + 255) & ~(size_t)255, flag_bytes = 256 * sizeof(unsigned long long);
-  cudaError_t e = cudaMalloc(&rf, flag_off + flag_bytes);
-  if (e == cudaSuccess) e = cudaMemset((char *)rf + flag_off, 0, flag_bytes);
+  const bool f64 = ctx->precision == MRL_F64;
+  const size_t esz = f64 ? 16 : 8;
+  const int ncp = slab_pitch(ctx);
+  // the blocked staging layouts are cut into column blocks of the fused pass's tile width, the same for both axes
+  const int wx = f64 ? fused_tma_tk<double>(ctx->n[0]) : fused_tma_tk<float>(ctx->n[0]);
+  const int wy = f64 ? fused_tma_tk<double>(ctx->n[1]) : fused_tma_tk<float>(ctx->n[1]);
+  if (!wx || wx != wy || ncp % wx)
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan (peer mode): nx = %d and ny = %d need pipelined configurations of the same tile width", ctx->n[0],
+                    ctx->n[1]);
+  if (ctx->nxl > 256) return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan (peer mode): nx/P <= 256");
+  const int kb = ncp / wx;
+  const size_t fbytes = (size_t)ctx->n[0] * ctx->nyl * ncp * esz;
+  void *sf = nullptr, *rf = nullptr, *rs = nullptr;
+  // behind the spectra recv_fwd carries the barrier flags (one 8-byte slot per rank) and the arrival counters
+  // counters1 / counters2 [nranks][kb] of the forward / return exchange
+  const size_t flag_off = align256(2 * fbytes), c1_off = flag_off + 256 * sizeof(unsigned long long);
+  const size_t cbytes = align256((size_t)ctx->nranks * kb * sizeof(unsigned long long)), c2_off = c1_off + cbytes;
+  cudaError_t e = cudaMalloc(&sf, 2 * fbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&rf, c2_off + cbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&rs, fbytes);
+  if (e == cudaSuccess) e = cudaMemset((char *)rf + flag_off, 0, c2_off + cbytes - flag_off);
+  if (e == cudaSuccess) e = cudaMemset(rs, 0, fbytes);
   if (e != cudaSuccess) {
     cudaFree(sf);
+    cudaFree(rf);
+    cudaFree(rs);
     return mrl_fail(MRL_ERR_CUDA, "slab plan allocation failed: %s", cudaGetErrorString(e));
   }
   // send_bwd is not used in peer mode: pass recv_fwd as a placeholder for the argument check
@@ -1107,18 +1129,34 @@ extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc 
   if (rc) {
     cudaFree(sf);
     cudaFree(rf);
+    cudaFree(rs);
     return rc;
   }
-  (*out)->owns = true;
-  (*out)->send_bwd = nullptr;
-  (*out)->flag_off = (long long)flag_off;
-  if (const char *v = getenv("MRL_SLAB_CHUNKS")) (*out)->chunks = atoi(v) > 0 ? atoi(v) : 1;
-  if (const char *v = getenv("MRL_SLAB_XCTAS")) (*out)->x_ctas = atoi(v) > 0 ? atoi(v) : 96;
+  mrl_slab_plan *p = *out;
+  p->owns = true;
+  p->send_bwd = nullptr;
+  p->ret_stage = rs;
+  p->tk = wx;
+  p->kb = kb;
+  p->flag_off = (long long)flag_off;
+  p->c1_off = (long long)c1_off;
+  p->c2_off = (long long)c2_off;
+  if (const char *v = getenv("MRL_SLAB_CHUNKS")) p->chunks = atoi(v) > 0 ? atoi(v) : 1;
+  if (const char *v = getenv("MRL_SLAB_XCTAS")) p->x_ctas = atoi(v) > 0 ? atoi(v) : 96;
+  // MRL_SLAB_SYNC = flags: arrival counters per column block instead of the two barriers of a substep; the tiles then
+  // run column-block major so that a phase can trail the one that feeds it
+  const char *sy = getenv("MRL_SLAB_SYNC");
+  p->sync_flags = sy && !strcmp(sy, "flags");
+  p->kzb_major = p->sync_flags ? 1 : 0;
+  if (const char *v = getenv("MRL_SLAB_KZB_MAJOR")) p->kzb_major = atoi(v) != 0;
+  if (const char *v = getenv("MRL_SLAB_INV_CTAS")) p->inv_ctas = atoi(v) > 0 ? atoi(v) : 0;
+  if (!p->sync_flags) p->inv_ctas = 0;
   return MRL_OK;
 }
 
 extern "C" int mrl_slab_barrier(mrl_slab_plan *p) {
   if (!p || !p->peer) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_barrier: needs a peer-mode plan with imported handles");
+  if (p->sync_flags) return MRL_OK;  // the phases synchronise through the arrival counters
   if (p->ctx->nranks > 32) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_slab_barrier: at most 32 ranks");
   CK(cudaSetDevice(p->ctx->device));
   p->ctx->launches++;
@@ -1131,7 +1169,7 @@ extern "C" int mrl_slab_ipc_export(mrl_slab_plan *p, void *handles) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   CK(cudaSetDevice(p->ctx->device));
   cudaIpcMemHandle_t h[2];
-  CK(cudaIpcGetMemHandle(&h[0], p->send_fwd));
+  CK(cudaIpcGetMemHandle(&h[0], p->ret_stage));
   CK(cudaIpcGetMemHandle(&h[1], p->recv_fwd));
   memcpy(handles, h, sizeof h);
   return MRL_OK;
@@ -1142,26 +1180,33 @@ extern "C" int mrl_slab_ipc_import(mrl_slab_plan *p, const void *all) {
   mrl_context *ctx = p->ctx;
   CK(cudaSetDevice(ctx->device));
   const int P = ctx->nranks;
-  std::vector<unsigned long long> sendp(P), recvp(P);
+  std::vector<unsigned long long> sendp(P), recvp(P), f1(P), f2(P);
   const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all;
   for (int s = 0; s < P; ++s) {
     if (s == ctx->rank) {
-      sendp[s] = (unsigned long long)p->send_fwd;
+      sendp[s] = (unsigned long long)p->ret_stage;
       recvp[s] = (unsigned long long)p->recv_fwd;
-      continue;
+    } else {
+      void *a = nullptr, *b = nullptr;
+      CK(cudaIpcOpenMemHandle(&a, h[2 * s], cudaIpcMemLazyEnablePeerAccess));
+      p->opened.push_back(a);
+      CK(cudaIpcOpenMemHandle(&b, h[2 * s + 1], cudaIpcMemLazyEnablePeerAccess));
+      p->opened.push_back(b);
+      sendp[s] = (unsigned long long)a;
+      recvp[s] = (unsigned long long)b;
     }
-    void *a = nullptr, *b = nullptr;
-    CK(cudaIpcOpenMemHandle(&a, h[2 * s], cudaIpcMemLazyEnablePeerAccess));
-    p->opened.push_back(a);
-    CK(cudaIpcOpenMemHandle(&b, h[2 * s + 1], cudaIpcMemLazyEnablePeerAccess));
-    p->opened.push_back(b);
-    sendp[s] = (unsigned long long)a;
-    recvp[s] = (unsigned long long)b;
+    f1[s] = recvp[s] + (unsigned long long)p->c1_off;
+    f2[s] = recvp[s] + (unsigned long long)p->c2_off;
   }
-  CK(cudaMalloc(&p->peer_send_tab, P * sizeof(unsigned long long)));
-  CK(cudaMalloc(&p->peer_recv_tab, P * sizeof(unsigned long long)));
-  CK(cudaMemcpy(p->peer_send_tab, sendp.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(p->peer_recv_tab, recvp.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  const size_t tb = P * sizeof(unsigned long long);
+  CK(cudaMalloc(&p->peer_send_tab, tb));
+  CK(cudaMalloc(&p->peer_recv_tab, tb));
+  CK(cudaMalloc(&p->flag1_tab, tb));
+  CK(cudaMalloc(&p->flag2_tab, tb));
+  CK(cudaMemcpy(p->peer_send_tab, sendp.data(), tb, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->peer_recv_tab, recvp.data(), tb, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->flag1_tab, f1.data(), tb, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->flag2_tab, f2.data(), tb, cudaMemcpyHostToDevice));
   p->peer = true;
   return MRL_OK;
 }
@@ -1177,25 +1222,16 @@ extern "C" int mrl_slab_advance_state(mrl_slab_plan *p, int *stored) {
   return MRL_OK;
 }
 
-// x pass (axis 0) on the local [nx][nyl][ncp] slabs of send_fwd
-// y0, ych: restrict the pass to the columns of the y-chunk [y0, y0 + ych) (ych = 0: all); lc: stream and
-// CTA budget of the launch
-template <class T> static int slab_xpass(mrl_slab_plan *p, int nfields, int inverse, int y0 = 0, int ych = 0, const LaunchCtx *lcp = nullptr) {
+// x pass (axis 0) on the local [nx][nyl][ncp] slabs of send_fwd (staged mode: the exchange is the caller's all-to-all)
+template <class T> static int slab_xpass(mrl_slab_plan *p, int nfields, int inverse) {
   mrl_context *ctx = p->ctx;
-  const long long col0 = (long long)y0 * p->ncp;
-  cx<T> *A = (cx<T> *)p->send_fwd + col0;
+  cx<T> *A = (cx<T> *)p->send_fwd;
   StridedIO<T> sio;
   memset(&sio, 0, sizeof sio);
-  if (p->peer && !inverse) {  // forward x pass: scatter the rows to the ranks that own them
-    sio.peer_tab = (const unsigned long long *)p->peer_recv_tab;
-    sio.peer_rows = ctx->nxl;
-    sio.peer_field = p->field;
-    sio.peer_off = (long long)ctx->rank * p->chunk + col0;
-  }
   for (int f = 0; f < nfields; ++f) sio.in[f] = sio.out[f] = A + f * p->field;
   sio.nfields = nfields;
   sio.n = ctx->n[0];
-  sio.ncols = (ych ? ych : ctx->nyl) * p->ncp;
+  sio.ncols = ctx->nyl * p->ncp;
   sio.nouter = 1;
   sio.pitch = (long long)ctx->nyl * p->ncp;
   sio.outer_stride = (long long)sio.n * sio.pitch;
@@ -1205,7 +1241,76 @@ template <class T> static int slab_xpass(mrl_slab_plan *p, int nfields, int inve
   int rc = ctx->twiddles(sio.n, &tw);
   if (rc) return rc;
   ctx->launches++;
-  CK(launch_strided_tma<T>(lcp ? *lcp : ctx->lc(), sio, (const cx<T> *)tw, sio.n));
+  CK(launch_strided_tma<T>(ctx->lc(), sio, (const cx<T> *)tw, sio.n));
+  return MRL_OK;
+}
+
+// peer mode: forward x pass of both spectra of the y-chunk [y0, y0 + ych), rows pushed into the peers' staging R
+template <class T> static int slab_xfwd_peer(mrl_slab_plan *p, int y0, int ych, const LaunchCtx &lc) {
+  mrl_context *ctx = p->ctx;
+  SlabXIO<T> io;
+  memset(&io, 0, sizeof io);
+  io.n = ctx->n[0];
+  io.nyl = ctx->nyl;
+  io.kb = p->kb;
+  io.nf = 2;
+  io.nranks = ctx->nranks;
+  io.rank = ctx->rank;
+  io.nxl = ctx->nxl;
+  io.y0 = y0;
+  io.ych = ych;
+  io.kzb_major = p->kzb_major;
+  io.scale = T(1);
+  io.peer_tab = (const unsigned long long *)p->peer_recv_tab;
+  io.field = p->field;
+  io.flag_tab = p->sync_flags ? (const unsigned long long *)p->flag1_tab : nullptr;
+  const void *tw;
+  int rc = ctx->twiddles(io.n, &tw);
+  if (rc) return rc;
+  ctx->launches++;
+  CK(launch_slab_xfwd<T>(lc, (const cx<T> *)p->send_fwd, io, (const cx<T> *)tw, io.n));
+  return MRL_OK;
+}
+
+// peer mode: inverse x pass from the return staging S into the natural slab (field 0 of send_fwd)
+template <class T> static int slab_xinv_peer(mrl_slab_plan *p, const LaunchCtx &lc) {
+  mrl_context *ctx = p->ctx;
+  SlabXIO<T> io;
+  memset(&io, 0, sizeof io);
+  io.n = ctx->n[0];
+  io.nyl = ctx->nyl;
+  io.kb = p->kb;
+  io.nf = 1;
+  io.nranks = ctx->nranks;
+  io.rank = ctx->rank;
+  io.nxl = ctx->nxl;
+  io.kzb_major = p->kzb_major;
+  io.scale = T(1);
+  io.out = (cx<T> *)p->send_fwd;
+  io.out_pitch = (long long)ctx->nyl * p->ncp;
+  if (p->sync_flags) {
+    io.flag_wait = (const unsigned long long *)((const char *)p->recv_fwd + p->c2_off);
+    io.flag_expect = p->n_update * (unsigned long long)ctx->nxl;  // one arrival per (source, x of the source) and column block
+  }
+  const void *tw;
+  int rc = ctx->twiddles(io.n, &tw);
+  if (rc) return rc;
+  ctx->launches++;
+  CK(launch_slab_xinv<T>(lc, (const cx<T> *)p->ret_stage, io, (const cx<T> *)tw, io.n));
+  return MRL_OK;
+}
+
+static int slab_aux_init(mrl_slab_plan *p, int nchunks) {
+  if (!p->s_aux) {
+    CK(cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+  }
+  while ((int)p->ev_chunk.size() < nchunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    p->ev_chunk.push_back(e);
+  }
   return MRL_OK;
 }
 
@@ -1219,17 +1324,12 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
   if (rc) return rc;
   NonlinDesc nlz{0, {d.nonlin_params[0], d.nonlin_params[1], d.nonlin_params[2], 0}};
   const int C = p->chunks, nyl = ctx->nyl;
+  if (p->peer) p->n_forward++;
   if (C > 1 && p->peer && nyl % C == 0 && (nyl / C) % 8 == 0) {
     // z pass of chunk i+1 on the main stream while the x pass of chunk i pushes its rows over NVLink
     // from a few SMs on the aux stream (that pass is bound by the link, not by the SMs)
     const int ych = nyl / C;
-    if (!p->s_aux) {
-      CK(cudaStreamCreateWithFlags(&p->s_aux, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
-      p->ev_chunk.resize(C);
-      for (auto &e : p->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    if ((rc = slab_aux_init(p, C))) return rc;
     const int xc = p->x_ctas < ctx->sm_count ? p->x_ctas : ctx->sm_count / 2;
     CK(cudaEventRecord(p->ev_begin, ctx->stream));
     CK(cudaStreamWaitEvent(p->s_aux, p->ev_begin, 0));
@@ -1241,7 +1341,7 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
                                    (const cx<T> *)twl, RowMap{ych, nyl, i * ych}));
       CK(cudaEventRecord(p->ev_chunk[i], ctx->stream));
       CK(cudaStreamWaitEvent(p->s_aux, p->ev_chunk[i], 0));
-      if ((rc = slab_xpass<T>(p, 2, 0, i * ych, ych, &lx))) return rc;
+      if ((rc = slab_xfwd_peer<T>(p, i * ych, ych, lx))) return rc;
     }
     CK(cudaEventRecord(p->ev_done, p->s_aux));
     CK(cudaStreamWaitEvent(ctx->stream, p->ev_done, 0));
@@ -1250,6 +1350,7 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
   ctx->launches++;
   CK(launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ctx->nyl, nl, p->ncp, nlz,
                                (const cx<T> *)twl));
+  if (p->peer) return slab_xfwd_peer<T>(p, 0, nyl, ctx->lc());
   return slab_xpass<T>(p, 2, 0);
 }
 
@@ -1270,9 +1371,20 @@ template <class T> static int slab_update_impl(mrl_slab_plan *p, double dt, cons
   io.slab = 1;
   io.nyl = ctx->nyl;
   io.nranks = ctx->nranks;
-  if (p->peer) {  // rows of the updated field go straight back into the owners' y slabs
+  if (p->peer) {  // rows of the updated field go straight back into the owners' return staging
+    p->n_update++;
+    io.slab = 2;
     io.peer_tab = (const unsigned long long *)p->peer_send_tab;
     io.peer_x0 = ctx->x0;
+    io.kzb_major = p->kzb_major;
+    io.nx = ctx->n[0];
+    io.rank = ctx->rank;
+    io.ring_old = p->ring.empty() ? p->recv_fwd : p->ring[0];
+    if (p->sync_flags) {
+      io.flag_wait = (const unsigned long long *)((const char *)p->recv_fwd + p->c1_off);
+      io.flag_expect = p->n_forward * 2ull * (unsigned long long)ctx->nyl;  // two spectra x nyl tiles per source and column block
+      io.flag_tab = (const unsigned long long *)p->flag2_tab;
+    }
   }
   SpectralUpdate<T> up;
   memset(&up, 0, sizeof up);
@@ -1300,6 +1412,20 @@ template <class T> static int slab_update_impl(mrl_slab_plan *p, double dt, cons
   const void *tw;
   int rc = ctx->twiddles(io.n, &tw);
   if (rc) return rc;
+  p->inverse_issued = false;
+  if (p->peer && p->sync_flags && p->inv_ctas > 0 && p->inv_ctas < ctx->sm_count) {
+    // the x inverse pass trails the fused y pass column block by column block on its own SMs: both kernels are resident
+    // together (one CTA per SM each), the inverse one waiting on the arrival counters of the return exchange
+    if ((rc = slab_aux_init(p, 0))) return rc;
+    CK(cudaEventRecord(p->ev_begin, ctx->stream));
+    ctx->launches++;
+    CK(launch_fused_tma<T>(LaunchCtx{ctx->stream, ctx->sm_count - p->inv_ctas}, io, up, (const cx<T> *)tw, io.n));
+    CK(cudaStreamWaitEvent(p->s_aux, p->ev_begin, 0));
+    if ((rc = slab_xinv_peer<T>(p, LaunchCtx{p->s_aux, p->inv_ctas}))) return rc;
+    CK(cudaEventRecord(p->ev_done, p->s_aux));
+    p->inverse_issued = true;
+    return MRL_OK;
+  }
   ctx->launches++;
   CK(launch_fused_tma<T>(ctx->lc(), io, up, (const cx<T> *)tw, io.n));
   return MRL_OK;
@@ -1307,8 +1433,17 @@ template <class T> static int slab_update_impl(mrl_slab_plan *p, double dt, cons
 
 template <class T> static int slab_inverse_impl(mrl_slab_plan *p, T *c) {
   mrl_context *ctx = p->ctx;
-  int rc = slab_xpass<T>(p, 1, 1);
-  if (rc) return rc;
+  int rc;
+  if (p->peer) {
+    if (p->inverse_issued) {
+      CK(cudaStreamWaitEvent(ctx->stream, p->ev_done, 0));
+      p->inverse_issued = false;
+    } else if ((rc = slab_xinv_peer<T>(p, ctx->lc()))) {
+      return rc;
+    }
+  } else if ((rc = slab_xpass<T>(p, 1, 1))) {
+    return rc;
+  }
   const int nl = ctx->n[2];
   const void *twl;
   if ((rc = ctx->twiddles(nl, &twl))) return rc;

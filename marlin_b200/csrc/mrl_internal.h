@@ -81,11 +81,22 @@ struct mrl_slab_plan {
   int cur = 0, stored = 0;
   int ncp = 0;
   long long field = 0, chunk = 0;
-  // peer mode
+  // peer mode: the exchanges are bulk stores into the peers' blocked staging arrays (mrl_passes_slab.cuh)
   bool owns = false, peer = false;
+  void *ret_stage = nullptr;           // S: blocked return staging [kb][nx][nyl][W], written by every rank's fused y pass
+  int tk = 0, kb = 0;                  // column-block width W of the blocked layouts, blocks per z row
   std::vector<void *> opened;          // pointers from cudaIpcOpenMemHandle
-  void *peer_recv_tab = nullptr;       // device arrays of nranks base pointers
-  void *peer_send_tab = nullptr;
+  void *peer_recv_tab = nullptr;       // device arrays of nranks base pointers: R (recv_fwd) ...
+  void *peer_send_tab = nullptr;       // ... and S (ret_stage)
+  // arrival counters instead of barriers between the phases (MRL_SLAB_SYNC=flags)
+  bool sync_flags = false;
+  int kzb_major = 0;
+  long long c1_off = 0, c2_off = 0;    // byte offsets of counters1 / counters2 [nranks][kb] behind recv_fwd
+  void *flag1_tab = nullptr, *flag2_tab = nullptr;  // device arrays: the peers' counters1 / counters2 bases
+  unsigned long long n_forward = 0, n_update = 0;   // phases issued so far (expected counter values)
+  // x inverse pass of column block k overlapped with the fused y pass (flags mode): CTAs given to the inverse pass
+  int inv_ctas = 0;
+  bool inverse_issued = false;
   // forward phase split into y-chunks: the z pass of chunk i+1 (main stream) overlaps the x pass +
   // peer stores of chunk i (aux stream); 1 = one pass each
   int chunks = 4, x_ctas = 96;  // measured on 2 B200: forward phase 1.25 -> 1.11 ms at 512^3 (profiles/r1w_*)

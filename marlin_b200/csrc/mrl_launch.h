@@ -83,6 +83,11 @@ cudaError_t launch_zfwd_pairs_tma(const LaunchCtx &lc, const T *in, cx<T> *out, 
 template <class T>
 cudaError_t launch_mech_fused_tma(const LaunchCtx &lc, cx<T> *spec, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzv,
                                   int ncp, const cx<T> *tw);
+// slab x passes with bulk peer stores into the blocked staging layouts (mrl_passes_slab.cuh)
+template <class T> struct SlabXIO;
+template <class T> cudaError_t launch_slab_xfwd(const LaunchCtx &lc, const cx<T> *in, const SlabXIO<T> &io, const cx<T> *tw, int n);
+template <class T> cudaError_t launch_slab_xinv(const LaunchCtx &lc, const cx<T> *S, const SlabXIO<T> &io, const cx<T> *tw, int n);
+template <class T> int fused_tma_tk(int n);  // column-block width of the fused pass (0: no TMA configuration)
 bool tma_enabled();
 template <class T>
 cudaError_t launch_kfactor(const LaunchCtx &lc, T *out, const T *kx, const T *ky, const T *kz, int n0, int n1, int n2,

@@ -404,6 +404,12 @@ template <class T> struct FusedIO {
   // array at x = peer_x0 + o (peer_tab: device array of nranks base pointers; null = staged store)
   const unsigned long long *peer_tab;
   int peer_x0;
+  // slab == 2: blocked staging + bulk peer stores + optional arrival counters (mrl_passes_slab.cuh)
+  int kzb_major, nx, rank;
+  const unsigned long long *flag_wait;
+  unsigned long long flag_expect;
+  const unsigned long long *flag_tab;
+  const void *ring_old;  // slab == 2: base the tensor map of the newest old nonlinear term is built on
 };
 
 template <class T, class C, int TK>

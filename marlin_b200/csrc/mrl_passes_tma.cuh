@@ -163,6 +163,14 @@ template <class T> struct FusedTmaIO {
   int slab, nouter, nyl;
   const unsigned long long *peer_tab;  // slab: store the result rows into the owning ranks' arrays
   int peer_x0;
+  // slab == 2 (mrl_passes_slab.cuh): variable / nonlinearity tiles through 5-D maps over the blocked staging R, result rows
+  // pushed with bulk copies into the peers' blocked return staging S; the ring of old nonlinear terms keeps the
+  // [nranks][nouter][nyl][ncols] layout of slab == 1
+  int kzb_major;                        // tile order: column block slowest
+  int nx, rank, nranks;
+  const unsigned long long *flag_wait;  // this rank's arrival counters [source][ncb] of the forward exchange (null: none)
+  unsigned long long flag_expect;
+  const unsigned long long *flag_tab;   // bases of the peers' arrival counters of the return exchange
   MRL_DI long long row_off(int o, int row) const {
     if (!slab) return (long long)row * pitch;
     const int s = row / nyl, yl = row - s * nyl;
@@ -235,7 +243,9 @@ template <class T> struct SpectralUpdate2 {
   }
 };
 
-template <class T, class C, int TK, int NG>
+// SLAB: 0 = one outer slice in the plain layout, 1 = slab staging with per-thread stores, 2 = blocked staging with bulk
+// peer stores (compile-time so that the single-GPU instantiation carries none of the exchange code)
+template <class T, class C, int TK, int NG, int SLAB = 0>
 __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     k_fused_tma(const MRL_GRID_CONSTANT TensorMap tmC, const MRL_GRID_CONSTANT TensorMap tmG,
                 const MRL_GRID_CONSTANT TensorMap tmO, FusedTmaIO<T> io, SpectralUpdate2<T> up, const cx<T> *tw_g) {
@@ -259,11 +269,29 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
   cx<T> *sG = slots + (size_t)(g * 3 + 0) * TILE, *sC = slots + (size_t)(g * 3 + 1) * TILE, *sO = slots + (size_t)(g * 3 + 2) * TILE;
   uint64_t *bG = &full[g * 3 + 0], *bC = &full[g * 3 + 1], *bO = &full[g * 3 + 2];
 
-  auto issue = [&](const TensorMap *tm, cx<T> *dst, uint64_t *b, int j) {
-    const int tile = first + j * stride;
-    const int o = tile / io.ncb, cb = tile - o * io.ncb;
+  auto decode = [&](int tile, int &o, int &cb) {
+    if (SLAB == 2 && io.kzb_major) {
+      cb = tile / io.nouter;
+      o = tile - cb * io.nouter;
+    } else {
+      o = tile / io.ncb;
+      cb = tile - o * io.ncb;
+    }
+  };
+  // blocked: the tile comes from the blocked staging R (5-D map); waitf: first load of a tile, wait for its arrivals
+  auto issue = [&](const TensorMap *tm, cx<T> *dst, uint64_t *b, int j, bool blocked = false, bool waitf = false) {
+    int o, cb;
+    decode(first + j * stride, o, cb);
+    if constexpr (SLAB == 2) {
+      if (waitf && io.flag_wait) {
+        for (int q = 0; q < io.nranks; ++q) wait_counter(io.flag_wait + (size_t)q * io.ncb + cb, io.flag_expect);
+        fence_proxy_async();
+      }
+    }
     mbar_expect_tx(b, (uint32_t)(TILE * sizeof(cx<T>)));
-    if (io.slab) {
+    if (SLAB == 2 && blocked) {
+      tma_load_5d(dst, tm, b, 0, o, 0, cb, 0);
+    } else if (SLAB != 0) {
       tma_load_4d(dst, tm, b, cb * TK * 2, 0, o, 0);
     } else {
       MRL_UNROLL
@@ -276,18 +304,27 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     mbar_init_fence();
   }
   __syncthreads();
+  constexpr bool blk = SLAB == 2;
   if (gt == 0 && nloc > 0) {
-    issue(&tmG, sG, bG, 0);
-    issue(&tmC, sC, bC, 0);
+    issue(&tmG, sG, bG, 0, blk, true);
+    issue(&tmC, sC, bC, 0, blk);
     if (use_old) issue(&tmO, sO, bO, 0);
   }
+  auto signal = [&](int cb) {  // this thread's bulk writes of a tile of column block cb have completed
+    fence_proxy_async_global();
+    for (int i = 0; i < io.nranks; ++i) {
+      const int d = (io.rank + 1 + i) % io.nranks;
+      red_release_sys_add(reinterpret_cast<unsigned long long *>(io.flag_tab[d]) + (size_t)io.rank * io.ncb + cb, 1ull);
+    }
+  };
+  int prev_cb = -1;
 
   const GroupBarrier bar{1 + g, GT};
   for (int j = 0; j < nloc; ++j) {
     const uint32_t par = (uint32_t)(j & 1);
-    const int tile = first + j * stride;
-    const int o = tile / io.ncb;
-    const int c = (tile - o * io.ncb) * TK + col;
+    int o, cbt;
+    decode(first + j * stride, o, cbt);
+    const int c = cbt * TK + col;
     const bool ok = c < io.ncols && (up.kmode == MRL_KMODE_2D || (c % up.nzc) < up.nzv);
     const bool more = j + 1 < nloc;
     cx<T> a[E], gh[E];
@@ -299,7 +336,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       for (int e = 0; e < E; ++e) gh[e] = sm.ld(t + TP * e);
       bar.sync();
       fft_or_skip<T, C>(nofft, gh, t, sm, twr, bar, [&] {
-        if (gt == 0 && more) issue(&tmG, sG, bG, j + 1);
+        if (gt == 0 && more) issue(&tmG, sG, bG, j + 1, blk, true);
       });
     }
     // ---- variable: forward transform; its slot is re-armed as soon as the transform has left it
@@ -310,7 +347,7 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       for (int e = 0; e < E; ++e) a[e] = smc.ld(t + TP * e);
       bar.sync();
       fft_or_skip<T, C>(nofft, a, t, smc, twr, bar, [&] {
-        if (gt == 0 && more) issue(&tmC, sC, bC, j + 1);
+        if (gt == 0 && more) issue(&tmC, sC, bC, j + 1, blk);
       });
     }
     // ---- k-space update (newest old nonlinear term from its slot)
@@ -331,9 +368,33 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
     bar.sync();  // every thread has taken its old-term values: the O slot becomes the exchange buffer
     // ---- inverse transform of the updated variable (exchange through the O slot)
     fft_or_skip<T, C>(nofft, a, t, smo, twr, bar, [&] {
-      if (gt == 0 && more && use_old) issue(&tmO, sO, bO, j + 1);
+      if (gt == 0 && more && use_old && !blk) issue(&tmO, sO, bO, j + 1);
     });
-    if (ok && io.peer_tab) {
+    if constexpr (blk) {
+      // fused return all-to-all, bulk form: the O slot (its last reader has passed the exchange) stages the result
+      // tile; the nyl rows that belong to rank d are contiguous there and in d's blocked staging S = [ncb][nx][nyl][W]
+      MRL_UNROLL
+      for (int e = 0; e < E; ++e) smo.st(t + TP * e, mk<T>(a[e].x * io.scale, -a[e].y * io.scale));
+      bar.sync_release();
+      if (gt == 0) {
+        const size_t chunk = (size_t)io.nyl * TK;
+        for (int i = 0; i < io.nranks; ++i) {
+          const int d = (io.rank + 1 + i) % io.nranks;
+          cx<T> *dst = reinterpret_cast<cx<T> *>(io.peer_tab[d]) + ((long long)cbt * io.nx + io.peer_x0 + o) * (long long)chunk;
+          bulk_store_1d(dst, sO + (size_t)d * chunk, (uint32_t)(chunk * sizeof(cx<T>)));
+        }
+        bulk_commit();
+        if (io.flag_tab) {
+          if (prev_cb >= 0) {
+            bulk_wait_done<1>();
+            signal(prev_cb);
+          }
+          prev_cb = cbt;
+        }
+        bulk_wait_read_all();  // the staging tile has been read: the slot may take the next old-term tile
+        if (more && use_old) issue(&tmO, sO, bO, j + 1);
+      }
+    } else if (SLAB == 1 && ok && io.peer_tab) {
       // fused return all-to-all: row y belongs to rank y / nyl, at x = peer_x0 + o of its slab
       MRL_UNROLL
       for (int e = 0; e < E; ++e) {
@@ -346,6 +407,11 @@ __global__ void __launch_bounds__(NG *TK *C::TP, 1)
       MRL_UNROLL
       for (int e = 0; e < E; ++e) dst[io.row_off(o, t + TP * e)] = mk<T>(a[e].x * io.scale, -a[e].y * io.scale);
     }
+  }
+  if constexpr (blk) if (gt == 0) {
+    bulk_wait_done<0>();  // the kernel's completion implies the peers hold the rows
+    if (io.flag_tab && prev_cb >= 0) signal(prev_cb);
+    fence_proxy_async_global();
   }
 }
 

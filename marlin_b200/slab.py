@@ -48,14 +48,18 @@ class SlabPlan:
     with the FFTs of DomainAction::fftSlab / ifftSlab)."""
 
     def __init__(self, ctx, double_well, M_factor, L_factor=None, history=1, group=None, mode="peer"):
-        """mode "peer": the all-to-all is fused into the passes (stores to NVLink-mapped peer
-        memory, CUDA IPC); mode "nccl": the three phases with torch.distributed all-to-all calls
-        between them (the baseline the fused mode is measured against)."""
+        """mode "peer": the all-to-all is fused into the passes (bulk cp.async stores from shared memory into
+        NVLink-mapped peer memory, CUDA IPC; blocked staging layouts, marlin_b200/csrc/mrl_passes_slab.cuh).
+        MRL_SLAB_SYNC=flags replaces the two barriers of a substep by per-column-block arrival counters (the
+        barrier calls below become no-ops), MRL_SLAB_INV_CTAS=n lets the x inverse pass trail the fused y pass
+        on n SMs.  mode "nccl": the three phases with torch.distributed all-to-all calls between them (the
+        baseline the fused mode is measured against)."""
         self.ctx, self.group, self.mode = ctx, group, mode
         # barrier between the phases in peer mode: "dev" = flags in peer memory (mrl_slab_barrier),
         # "nccl" = a 1-element all-reduce
         import os
         self.barrier_kind = os.environ.get("MRL_SLAB_BARRIER", "dev")
+        self.sync = os.environ.get("MRL_SLAB_SYNC", "barrier")
         dev = ctx.device
         f = ctx.field_elems
         d = capi.SplitDesc()
@@ -311,7 +315,9 @@ def bench(args, rank, world, metric):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload(n),
                        "impl_detail": f"slab-decomposed (y real / x reciprocal) over {world} GPUs, half spectrum on the wire, "
-                                      + (f"all-to-all fused into the passes (peer stores over NVLink), {plan.barrier_kind} barrier" if mode == "peer"
+                                      + (f"all-to-all fused into the passes (bulk stores from shared memory into peer HBM over NVLink), "
+                                         + (f"per-column-block arrival counters, inverse x pass on {os.environ.get('MRL_SLAB_INV_CTAS', '0')} SMs beside the fused y pass"
+                                            if plan.sync == "flags" else f"{plan.barrier_kind} barrier between the phases") if mode == "peer"
                                          else "NCCL all-to-all between the phases"),
                        "l2": "inputs larger than L2" if s_r / world > 126e6 else "per-GPU slab comparable to L2",
                        "parallelism": f"slab{world}"},

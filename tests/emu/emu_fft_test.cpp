@@ -1,7 +1,7 @@
 // Host-emulated run of the product's FFT kernels against a naive long-double DFT.
 // TEST TOOL: compiled with g++ -DMRL_EMU; validates index math / barriers without a GPU.
 #define MRL_EMU 1
-#include "../../marlin_b200/csrc/mrl_passes_tma.cuh"
+#include "../../marlin_b200/csrc/mrl_passes_slab.cuh"
 
 #include <complex>
 #include <random>
@@ -228,9 +228,9 @@ static TensorMap emu_map(const void *base, int esize, long long d0, long long d1
   TensorMap m;
   m.base = (const unsigned char *)base;
   m.esize = esize;
-  m.dim[0] = d0; m.dim[1] = d1; m.dim[2] = d2; m.dim[3] = 1;
-  m.stride[0] = esize; m.stride[1] = s1; m.stride[2] = s2; m.stride[3] = 0;
-  m.box[0] = b0; m.box[1] = b1; m.box[2] = 1; m.box[3] = 1;
+  m.dim[0] = d0; m.dim[1] = d1; m.dim[2] = d2; m.dim[3] = 1; m.dim[4] = 1;
+  m.stride[0] = esize; m.stride[1] = s1; m.stride[2] = s2; m.stride[3] = 0; m.stride[4] = 0;
+  m.box[0] = b0; m.box[1] = b1; m.box[2] = 1; m.box[3] = 1; m.box[4] = 1;
   return m;
 }
 
@@ -366,6 +366,7 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
   FusedTmaIO<double> io;
   io.outU = Us.data(); io.n = ny; io.ncols = nzc; io.ncb = (nzc + TK - 1) / TK; io.pitch = nzc; io.scale = 1.0 / ny;
   io.slab = 1; io.nouter = nxl; io.nyl = nyl; io.peer_tab = nullptr; io.peer_x0 = 0;
+  io.kzb_major = 0; io.nx = 0; io.rank = 0; io.nranks = P; io.flag_wait = nullptr; io.flag_expect = 0; io.flag_tab = nullptr;
   SpectralUpdate2<double> up{};
   up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = MRL_KMODE_3D_SLAB; up.nzc = nzc; up.nzv = nzc; up.x0 = x0;
   up.closed_M = 1; up.closed_L = 1; up.has_L = 1; up.Mfac = 0.2; up.Lfac = -0.001; up.dt = 0.01;
@@ -376,6 +377,7 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
     m.dim[0] = 2LL * nzc; m.dim[1] = nyl; m.dim[2] = nxl; m.dim[3] = P;
     m.stride[0] = 8; m.stride[1] = 16LL * nzc; m.stride[2] = 16LL * nzc * nyl; m.stride[3] = 16LL * nzc * nyl * nxl;
     m.box[0] = 2 * TK; m.box[1] = nyl; m.box[2] = 1; m.box[3] = P;
+    m.dim[4] = 1; m.stride[4] = 0; m.box[4] = 1;
     return m;
   };
   TensorMap tmC = mk4(Cs.data()), tmG = mk4(Gs.data()), tmO = mk4(Os.data());
@@ -387,7 +389,7 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
   for (int q = 0; q < P; ++q) tab[q] = (unsigned long long)peerbuf[q].data();
   if (peer) { io.peer_tab = tab.data(); io.peer_x0 = x0; }
   size_t smem = (size_t)(NG * 3 * C::N * TK) * 16 + NG * 3 * 8 + 128;
-  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG>(tmC, tmG, tmO, io, up, twp); }, 64 * 1024);
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG, 1>(tmC, tmG, tmO, io, up, twp); }, 64 * 1024);
   if (peer)
     for (int x = 0; x < nxl; ++x)
       for (int y = 0; y < ny; ++y)
@@ -584,6 +586,191 @@ template <class C, int TK, int NG> static void test_fused_padded_buffers(const c
   report(name, err, 1e-12 * n);
 }
 
+// ---- multi-GPU slab passes with bulk peer stores into the blocked staging layouts (mrl_passes_slab.cuh)
+// forward x pass of `me`: R_d[f][me][kzb][yl][xl][W] = DFT_x(in)[f][d*nxl + xl][yl][kzb*W + w]
+template <class C, int TK, int NG, int NS> static void test_slab_xfwd(const char *name, int P, int nyl, int kb, int kzb_major, int chunks, int grid) {
+  constexpr int nx = C::N;
+  const int nxl = nx / P, me = 1 % P, ncp = kb * TK;
+  std::mt19937_64 rng(31);
+  std::uniform_real_distribution<double> U(-1, 1);
+  const size_t field = (size_t)nx * nyl * ncp;
+  std::vector<cx<double>> in(2 * field);
+  for (auto &v : in) v = mk<double>(U(rng), U(rng));
+  std::vector<std::vector<cx<double>>> R(P, std::vector<cx<double>>(2 * field));
+  std::vector<std::vector<unsigned long long>> cnt(P, std::vector<unsigned long long>((size_t)P * kb, 0));
+  std::vector<unsigned long long> tab(P), ftab(P);
+  for (int q = 0; q < P; ++q) { tab[q] = (unsigned long long)R[q].data(); ftab[q] = (unsigned long long)cnt[q].data(); }
+  auto tw = make_tw(nx);
+  const cx<double> *twp = tw.data();
+  const long long rowb = (long long)nyl * ncp * 16;
+  TensorMap tm = emu_map(in.data(), 8, 2LL * nyl * ncp, nx, 2, rowb, rowb * nx, 2 * TK, nx < 256 ? nx : 256);
+  size_t smem = (size_t)((NS + NG) * nx * TK) * 16 + NS * 8 + 128;
+  const int ych = nyl / chunks;
+  for (int ci = 0; ci < chunks; ++ci) {
+    SlabXIO<double> io{};
+    io.n = nx; io.nyl = nyl; io.kb = kb; io.nf = 2; io.nranks = P; io.rank = me; io.nxl = nxl; io.y0 = ci * ych; io.ych = ych;
+    io.kzb_major = kzb_major; io.scale = 1.0; io.peer_tab = tab.data(); io.field = (long long)field; io.flag_tab = ftab.data();
+    emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_slab_xfwd<double, C, TK, NG, NS>(tm, io, twp); }, 64 * 1024);
+  }
+  double err = 0;
+  for (int f = 0; f < 2; ++f)
+    for (int yl = 0; yl < nyl; ++yl)
+      for (int c = 0; c < ncp; ++c) {
+        std::vector<lc> x(nx);
+        for (int j = 0; j < nx; ++j) {
+          auto v = in[f * field + ((size_t)j * nyl + yl) * ncp + c];
+          x[j] = lc(v.x, v.y);
+        }
+        auto y = dft(x, -1);
+        for (int j = 0; j < nx; ++j) {
+          const int d = j / nxl, xl = j % nxl, kzb = c / TK, w = c % TK;
+          auto v = R[d][f * field + ((((size_t)me * kb + kzb) * nyl + yl) * nxl + xl) * TK + w];
+          err = std::max(err, (double)std::abs(lc(v.x, v.y) - y[j]));
+        }
+      }
+  report(name, err, 1e-12 * nx);
+  // every destination has seen 2 * nyl arrivals from `me` for every column block
+  bool ok = true;
+  for (int d = 0; d < P; ++d)
+    for (int q = 0; q < P; ++q)
+      for (int k = 0; k < kb; ++k) ok = ok && cnt[d][(size_t)q * kb + k] == (q == me ? 2ull * nyl : 0ull);
+  char nm[160];
+  snprintf(nm, sizeof nm, "%s arrival counters", name);
+  report(nm, ok ? 0.0 : 1.0, 0.5);
+}
+
+// inverse x pass: S = [kb][nx][nyl][W] -> natural [nx][nyl][ncp]
+template <class C, int TK, int NG, int NS> static void test_slab_xinv(const char *name, int nyl, int kb, int kzb_major, int grid) {
+  constexpr int nx = C::N;
+  const int ncp = kb * TK;
+  std::mt19937_64 rng(37);
+  std::uniform_real_distribution<double> U(-1, 1);
+  const size_t field = (size_t)nx * nyl * ncp;
+  std::vector<cx<double>> S(field), out(field);
+  for (auto &v : S) v = mk<double>(U(rng), U(rng));
+  std::vector<unsigned long long> cnt((size_t)2 * kb, 5);
+  auto tw = make_tw(nx);
+  const cx<double> *twp = tw.data();
+  TensorMap tm;
+  tm.base = (const unsigned char *)S.data(); tm.esize = 8;
+  tm.dim[0] = 2 * TK; tm.dim[1] = nyl; tm.dim[2] = nx; tm.dim[3] = kb; tm.dim[4] = 1;
+  tm.stride[0] = 8; tm.stride[1] = 16LL * TK; tm.stride[2] = 16LL * TK * nyl; tm.stride[3] = 16LL * TK * nyl * nx; tm.stride[4] = 0;
+  tm.box[0] = 2 * TK; tm.box[1] = 1; tm.box[2] = nx < 256 ? nx : 256; tm.box[3] = 1; tm.box[4] = 1;
+  SlabXIO<double> io{};
+  io.n = nx; io.nyl = nyl; io.kb = kb; io.nf = 1; io.nranks = 2; io.rank = 0; io.nxl = nx / 2; io.kzb_major = kzb_major; io.scale = 0.5;
+  io.out = out.data(); io.out_pitch = (long long)nyl * ncp; io.flag_wait = cnt.data(); io.flag_expect = 5;
+  size_t smem = (size_t)(NS * nx * TK) * 16 + NS * 8 + 128;
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_slab_xinv<double, C, TK, NG, NS>(tm, io, twp); }, 64 * 1024);
+  double err = 0;
+  for (int yl = 0; yl < nyl; ++yl)
+    for (int c = 0; c < ncp; ++c) {
+      std::vector<lc> x(nx);
+      for (int j = 0; j < nx; ++j) {
+        auto v = S[(((size_t)(c / TK) * nx + j) * nyl + yl) * TK + c % TK];
+        x[j] = lc(v.x, v.y);
+      }
+      auto y = dft(x, +1);
+      for (int j = 0; j < nx; ++j) {
+        auto v = out[((size_t)j * nyl + yl) * ncp + c];
+        err = std::max(err, (double)std::abs(lc(v.x, v.y) - y[j] * 0.5L));
+      }
+    }
+  report(name, err, 1e-12 * nx);
+}
+
+// fused y pass on the blocked staging: inputs R = [P][kb][nyl][nxl][W], old term / new term in the staged layout
+// [P][nxl][nyl][ncp], result rows into the P return stagings S_d = [kb][nxtot][nyl][W] at x = x0 + o
+template <class C, int TK, int NG> static void test_fused_slab2(const char *name, int P, int nxl, int kb, int x0, int kzb_major, int grid, int nold = 1) {
+  constexpr int ny = C::N;
+  const int nyl = ny / P, ncp = kb * TK, me = P - 1;
+  std::mt19937_64 rng(41);
+  std::uniform_real_distribution<double> U(-1, 1);
+  const size_t total = (size_t)nxl * ny * ncp;
+  std::vector<cx<double>> Cl(total), Gl(total), Ol(total), Cb(total), Gb(total), Os(total), Ns(total);
+  for (auto &v : Cl) v = mk<double>(U(rng), U(rng));
+  for (auto &v : Gl) v = mk<double>(U(rng), U(rng));
+  for (auto &v : Ol) v = mk<double>(U(rng), U(rng));
+  auto sidx = [&](int x, int y, int kz) { return (((size_t)(y / nyl) * nxl + x) * nyl + (y % nyl)) * ncp + kz; };
+  auto bidx = [&](int x, int y, int kz) { return ((((size_t)(y / nyl) * kb + kz / TK) * nyl + (y % nyl)) * nxl + x) * TK + kz % TK; };
+  for (int x = 0; x < nxl; ++x)
+    for (int y = 0; y < ny; ++y)
+      for (int kz = 0; kz < ncp; ++kz) {
+        size_t l = ((size_t)x * ny + y) * ncp + kz;
+        Cb[bidx(x, y, kz)] = Cl[l]; Gb[bidx(x, y, kz)] = Gl[l]; Os[sidx(x, y, kz)] = Ol[l];
+      }
+  std::vector<double> kx(x0 + nxl + 3), ky(ny), kz(ncp);
+  for (auto &v : kx) v = U(rng);
+  for (auto &v : ky) v = U(rng);
+  for (auto &v : kz) v = U(rng);
+  auto tw = make_tw(ny);
+  const int nxtot = x0 + nxl + 1;
+  std::vector<std::vector<cx<double>>> Sd(P, std::vector<cx<double>>((size_t)kb * nxtot * nyl * TK));
+  std::vector<std::vector<unsigned long long>> cnt2(P, std::vector<unsigned long long>((size_t)P * kb, 0));
+  std::vector<unsigned long long> tab(P), ftab(P), cnt1((size_t)P * kb, 7);
+  for (int q = 0; q < P; ++q) { tab[q] = (unsigned long long)Sd[q].data(); ftab[q] = (unsigned long long)cnt2[q].data(); }
+  FusedTmaIO<double> io;
+  io.outU = nullptr; io.n = ny; io.ncols = ncp; io.ncb = kb; io.pitch = ncp; io.scale = 1.0 / ny;
+  io.slab = 2; io.nouter = nxl; io.nyl = nyl; io.peer_tab = tab.data(); io.peer_x0 = x0;
+  io.kzb_major = kzb_major; io.nx = nxtot; io.rank = me; io.nranks = P; io.flag_wait = cnt1.data(); io.flag_expect = 7; io.flag_tab = ftab.data();
+  SpectralUpdate2<double> up{};
+  up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = MRL_KMODE_3D_SLAB; up.nzc = ncp; up.nzv = ncp; up.x0 = x0;
+  up.closed_M = 1; up.closed_L = 1; up.has_L = 1; up.Mfac = 0.2; up.Lfac = -0.001; up.dt = 0.01;
+  up.b0 = 1.5 * up.dt; up.nold = nold; up.bold0 = -0.5 * up.dt; up.Nout = Ns.data();
+  auto mk5 = [&](const void *base) {
+    TensorMap m;
+    m.base = (const unsigned char *)base; m.esize = 8;
+    m.dim[0] = 2 * TK; m.dim[1] = nxl; m.dim[2] = nyl; m.dim[3] = kb; m.dim[4] = P;
+    m.stride[0] = 8; m.stride[1] = 16LL * TK; m.stride[2] = 16LL * TK * nxl; m.stride[3] = 16LL * TK * nxl * nyl; m.stride[4] = 16LL * TK * nxl * nyl * kb;
+    m.box[0] = 2 * TK; m.box[1] = 1; m.box[2] = nyl; m.box[3] = 1; m.box[4] = P;
+    return m;
+  };
+  TensorMap tmO;
+  tmO.base = (const unsigned char *)Os.data(); tmO.esize = 8;
+  tmO.dim[0] = 2LL * ncp; tmO.dim[1] = nyl; tmO.dim[2] = nxl; tmO.dim[3] = P; tmO.dim[4] = 1;
+  tmO.stride[0] = 8; tmO.stride[1] = 16LL * ncp; tmO.stride[2] = 16LL * ncp * nyl; tmO.stride[3] = 16LL * ncp * nyl * nxl; tmO.stride[4] = 0;
+  tmO.box[0] = 2 * TK; tmO.box[1] = nyl; tmO.box[2] = 1; tmO.box[3] = P; tmO.box[4] = 1;
+  TensorMap tmC = mk5(Cb.data()), tmG = mk5(Gb.data());
+  const cx<double> *twp = tw.data();
+  size_t smem = (size_t)(NG * 3 * C::N * TK) * 16 + NG * 3 * 8 + 128;
+  emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG, 2>(tmC, tmG, tmO, io, up, twp); }, 64 * 1024);
+  double err = 0, errN = 0;
+  for (int x = 0; x < nxl; ++x)
+    for (int q = 0; q < ncp; ++q) {
+      std::vector<lc> xc(ny), xg(ny);
+      for (int y = 0; y < ny; ++y) {
+        auto a = Cl[((size_t)x * ny + y) * ncp + q], b = Gl[((size_t)x * ny + y) * ncp + q];
+        xc[y] = lc(a.x, a.y); xg[y] = lc(b.x, b.y);
+      }
+      auto yc = dft(xc, -1), yg = dft(xg, -1);
+      std::vector<lc> u(ny);
+      for (int y = 0; y < ny; ++y) {
+        long double a = kx[x0 + x], b = ky[y], d = kz[q];
+        long double kk = a * a + b * b + d * d;
+        lc N = (-kk * 0.2L) * yg[y];
+        auto no = Ol[((size_t)x * ny + y) * ncp + q];
+        u[y] = (yc[y] + (long double)up.b0 * N + (nold ? (long double)up.bold0 * lc(no.x, no.y) : lc(0, 0))) / (1.0L - (long double)up.dt * (kk * kk * -0.001L));
+        auto nn = Ns[sidx(x, y, q)];
+        errN = std::max(errN, (double)std::abs(lc(nn.x, nn.y) - N));
+      }
+      auto r = dft(u, +1);
+      for (int y = 0; y < ny; ++y) {
+        auto v = Sd[y / nyl][(((size_t)(q / TK) * nxtot + x0 + x) * nyl + (y % nyl)) * TK + q % TK];
+        err = std::max(err, (double)std::abs(lc(v.x, v.y) - r[y] / (long double)ny));
+      }
+    }
+  char nm[160];
+  snprintf(nm, sizeof nm, "%s u", name);
+  report(nm, err, 1e-12 * ny);
+  snprintf(nm, sizeof nm, "%s N", name);
+  report(nm, errN, 1e-12 * ny);
+  bool ok = true;
+  for (int d = 0; d < P; ++d)
+    for (int q = 0; q < P; ++q)
+      for (int k = 0; k < kb; ++k) ok = ok && cnt2[d][(size_t)q * kb + k] == (q == me ? (unsigned long long)nxl : 0ull);
+  snprintf(nm, sizeof nm, "%s arrival counters", name);
+  report(nm, ok ? 0.0 : 1.0, 0.5);
+}
+
 static void tma_tests() {
   test_fused_padded_buffers<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma 64 3D padded pitch, M/L from buffers", MRL_KMODE_3D, 3, 5, 8, 2);
   test_fused_padded_buffers<FFTCfg<64, 8, 8, 8>, 8, 1>("fused tma 64 2D padded pitch, M/L from buffers", MRL_KMODE_2D, 1, 33, 40, 1);
@@ -605,6 +792,13 @@ static void tma_tests() {
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 1>("fused tma slab 64 P2 nxl2 nzc9", 2, 2, 9, 0, 1);
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 peer stores", 4, 3, 5, 6, 2, true);
   test_strided_peer<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("strided tma 64 peer scatter P4", 4, 11);
+  test_slab_xfwd<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("slab xfwd bulk 64 P4 nyl3 kb2 y-major", 4, 3, 2, 0, 1, 2);
+  test_slab_xfwd<FFTCfg<64, 8, 8, 8>, 8, 1, 2>("slab xfwd bulk 64 P2 nyl4 kb3 kzb-major 2 chunks", 2, 4, 3, 1, 2, 3);
+  test_slab_xfwd<FFTCfg<512, 64, 8, 8, 8>, 4, 1, 2>("slab xfwd bulk 512 P8 nyl1 kb1 (2 boxes)", 8, 1, 1, 1, 1, 1);
+  test_slab_xinv<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("slab xinv 64 nyl3 kb2 kzb-major", 3, 2, 1, 2);
+  test_slab_xinv<FFTCfg<64, 8, 8, 8>, 4, 1, 3>("slab xinv 64 nyl2 kb3 y-major", 2, 3, 0, 1);
+  test_fused_slab2<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab2 64 P4 nxl3 kb2 kzb-major", 4, 3, 2, 5, 1, 2);
+  test_fused_slab2<FFTCfg<64, 8, 8, 8>, 8, 1>("fused tma slab2 64 P2 nxl2 kb1 x-major nold=0", 2, 2, 1, 0, 0, 1, 0);
   test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 3, 2>("zfwd tma 64 PPB4 NG3 NS2 rows=21", 21, 2);
   test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 2, 2>("zfwd tma 64 PPB4 y-chunks of 4 in a [5][12] slab", 60, 2, 12, 4);
   test_zfwd_tma<FFTCfg<64, 8, 8, 8>, 4, 1, 2>("zfwd tma 64 PPB4 y-chunks of 8 (last 4) in a [3][12] slab", 36, 1, 12, 8);

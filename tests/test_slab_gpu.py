@@ -10,11 +10,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, nsub, mode, q, chunks=1):
+def _worker(rank, world, port, n, nsub, mode, q, chunks=1, sync="barrier", inv_ctas=0):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["MRL_SLAB_CHUNKS"] = str(chunks)   # read at plan creation: forward phase in y-chunks
+    os.environ["MRL_SLAB_SYNC"] = sync            # barrier between the phases / arrival counters per column block
+    os.environ["MRL_SLAB_INV_CTAS"] = str(inv_ctas)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from marlin_b200 import capi, slab
@@ -62,16 +64,23 @@ def _worker(rank, world, port, n, nsub, mode, q, chunks=1):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,mode,chunks", [(128, "nccl", 1), (128, "peer", 1), (256, "peer", 1), (128, "peer", 2), (256, "peer", 4)])
-def test_slab_matches_single_gpu(n, mode, chunks):
+CASES = [(128, "nccl", 1, "barrier", 0), (128, "peer", 1, "barrier", 0), (256, "peer", 1, "barrier", 0), (128, "peer", 2, "barrier", 0),
+         (256, "peer", 4, "barrier", 0), (128, "peer", 1, "flags", 0), (256, "peer", 4, "flags", 0), (256, "peer", 1, "flags", 40),
+         (512, "peer", 4, "flags", 48)]
+
+
+@pytest.mark.parametrize("n,mode,chunks,sync,inv_ctas", CASES)
+def test_slab_matches_single_gpu(n, mode, chunks, sync, inv_ctas):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    world = 2
+    world = min(torch.cuda.device_count(), 8 if n >= 256 else 4)
+    if world == 3 or 4 < world < 8:
+        world = 2 if world == 3 else 4
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + (7 if mode == "peer" else 0) + n // 128 + 11 * chunks
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, 6, mode, q, chunks)) for r in range(world)]
+    port = 29700 + (os.getpid() % 1000) + (7 if mode == "peer" else 0) + n // 128 + 11 * chunks + (23 if sync == "flags" else 0) + inv_ctas
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, 6, mode, q, chunks, sync, inv_ctas)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in range(world))
