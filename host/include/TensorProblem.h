@@ -139,6 +139,8 @@ public:
 
   // time bookkeeping (FEProblemBase::time() etc.; owned here because MOOSE is not linked)
   Real &time() { return _time; }
+  void waitForOutputs();  // joins the output threads (end of run; TensorProblem.C:66-72)
+  const Real &outputTime() const { return _output_time; }  // time of the frame the output threads are writing
   Real &timeOld() { return _time_old; }
   Real &dt() { return _dt; }
   Real &dtOld() { return _dt_old; }
@@ -171,6 +173,6 @@ private:
   std::vector<std::shared_ptr<TensorPostprocessor>> _postprocessors;
   std::vector<Real> _old_dt;
   std::vector<std::function<void()>> _advance_hooks;
-  Real _time = 0, _time_old = 0, _dt = 0, _dt_old = 0, _sub_dt = 0, _sub_time = 0;
+  Real _time = 0, _time_old = 0, _dt = 0, _dt_old = 0, _sub_dt = 0, _sub_time = 0, _output_time = 0;
   int _t_step = 0;
 };

@@ -77,14 +77,19 @@ DomainAction::DomainAction(const InputParameters &parameters)
     _min_global({getParam<Real>("xmin"), getParam<Real>("ymin"), getParam<Real>("zmin")}),
     _max_global({getParam<Real>("xmax"), getParam<Real>("ymax"), getParam<Real>("zmax")}),
     _parallel_mode(getParam<MooseEnum>("parallel_mode").getEnum<ParallelMode>()),
-    _debug(getParam<bool>("debug")) {
-  if (_parallel_mode != ParallelMode::NONE)
-    paramError("parallel_mode", "The single-process host driver runs ParallelMode NONE; the slab-decomposed path is driven one "
-                                "process per GPU through mrl_slab_* (see marlin_b200/slab.py).");
-  // [Domain] device_names: "cuda", "cuda:1" (src/base/MarlinApp.C:27-54).  There is no CPU path.
+    _debug(getParam<bool>("debug")),
+    _comm(Comm::world()) {
+  if (_parallel_mode == ParallelMode::REAL_SPACE)
+    paramError("parallel_mode", "REAL_SPACE (halo exchange for the finite-difference / lattice-Boltzmann operators) is outside the spectral "
+                                "time-step path this build covers; use NONE, FFT_SLAB or FFT_PENCIL.");
+  const int n_rank = _comm.size(), local_rank = _comm.localRank();
+  // [Domain] device_names: "cuda", "cuda:1" (src/base/MarlinApp.C:27-54); with several processes the entry is picked by the
+  // local rank (DomainAction.C:196-197).  A name without an index means the local rank's GPU.  There is no CPU path.
   const auto names = getParam<std::vector<std::string>>("device_names");
+  _device = n_rank > 1 ? local_rank : 0;
+  bool explicit_index = false;
   if (!names.empty()) {
-    const std::string &d = names[0];
+    const std::string &d = names[size_t(local_rank) % names.size()];
     std::string use = d;
     if (d.rfind("cuda", 0) != 0) {
       // The reference gives [Domain] device_names priority over --compute-device (DomainAction.C:154-155).  This build has
@@ -94,13 +99,29 @@ DomainAction::DomainAction(const InputParameters &parameters)
       if (cli.rfind("cuda", 0) != 0)
         paramError("device_names", "marlin_b200 runs on CUDA devices only (sm_100a); got '", d,
                    "'. There is no CPU fallback (pass --compute-device=cuda to run this input on the GPU).");
-      std::cerr << "marlin_b200: warning: [Domain] device_names = '" << d << "' overridden by --compute-device=" << cli
-                << " (this build has no CPU path)\n";
+      if (_comm.rank() == 0)
+        std::cerr << "marlin_b200: warning: [Domain] device_names = '" << d << "' overridden by --compute-device=" << cli
+                  << " (this build has no CPU path)\n";
       use = cli;
     }
     const size_t colon = use.find(':');
-    if (colon != std::string::npos) _device = std::atoi(use.c_str() + colon + 1);
+    if (colon != std::string::npos) {
+      _device = std::atoi(use.c_str() + colon + 1);
+      explicit_index = true;
+    }
   }
+  int n_dev = 0;
+  mrl_device_count(&n_dev);
+  if (!explicit_index && n_dev > 0 && _device >= n_dev) {
+    // more processes than GPUs: the ranks share devices (slow - the device-side barriers then wait for the
+    // driver's time slicing - but correct; used to exercise the multi-process path on a one-GPU box)
+    if (_comm.rank() == 0)
+      std::cerr << "marlin_b200: warning: " << n_rank << " processes on " << n_dev << " GPU(s): ranks share devices\n";
+    _device %= n_dev;
+  }
+  // device weights by local rank (DomainAction.C:164-189; the ranks of this driver share one host)
+  const auto weights = getParam<std::vector<unsigned int>>("device_weights");
+  for (int r = 0; r < n_rank; ++r) _local_weights.push_back(weights.empty() || n_rank == 1 ? 1.0 : double(weights[size_t(r) % weights.size()]));
   // DEVICE_DEFAULT / DOUBLE -> float64 on CUDA (src/utils/MarlinUtils.C:42)
   _single = getParam<MooseEnum>("floating_precision") == "SINGLE";
   for (unsigned int d = _dim; d < 3; ++d)
@@ -113,6 +134,15 @@ DomainAction::DomainAction(const InputParameters &parameters)
 
 DomainAction::~DomainAction() {
   _pool.reset();
+  if (_dist) {
+    // the peers may still be reading this rank's staging buffers
+    if (_ctx) mrl_synchronize(_ctx);
+    try {
+      _comm.barrier();
+    } catch (const std::exception &) {
+    }
+    mrl_dist_destroy(_dist);
+  }
   if (_ctx) mrl_destroy(_ctx);
 }
 
@@ -121,7 +151,39 @@ void DomainAction::check(int rc, const char *what) const {
 }
 
 void DomainAction::gridChanged() {
-  check(mrl_domain_set(_ctx, (int)_dim, _n_global.data(), _min_global.data(), _max_global.data()), "mrl_domain_set");
+  const int n_rank = _comm.size();
+  if (isParallelFFT()) {
+    if (_dist) {
+      synchronize();
+      _comm.barrier();
+      mrl_dist_destroy(_dist);
+      _dist = nullptr;
+    }
+    if (_parallel_mode == ParallelMode::FFT_SLAB) {
+      // partitionSlabs (DomainAction.C:511-566): real space split along y, reciprocal space along x
+      if (_dim < 2) paramError("dim", "Dimension must be 2 or 3 for slab decomposition.");
+      check(mrl_domain_set_dist(_ctx, (int)_dim, _n_global.data(), _min_global.data(), _max_global.data(), _comm.rank(), n_rank, _local_weights.data()),
+            "mrl_domain_set_dist");
+    } else {
+      // partitionPencils (DomainAction.C:569-742): real space split along y and z, reciprocal space along x and y
+      if (_dim < 3) paramError("dim", "Dimension must be 3 for pencil decomposition.");
+      if (mrl_domain_set_pencil(_ctx, (int)_dim, _n_global.data(), _min_global.data(), _max_global.data(), _comm.rank(), n_rank) != MRL_OK)
+        paramError("parallel_mode", mrl_last_error());
+    }
+    check(mrl_dist_create(_ctx, &_dist), "mrl_dist_create");
+    if (n_rank > 1) {
+      // the exchange buffers of every rank, mapped through CUDA IPC (where the reference posts MPI_Isend / MPI_Recv)
+      unsigned char mine[MRL_DIST_IPC_BYTES];
+      check(mrl_dist_ipc_export(_dist, mine), "mrl_dist_ipc_export");
+      std::vector<unsigned char> all(size_t(MRL_DIST_IPC_BYTES) * n_rank);
+      _comm.allgather(mine, sizeof mine, all.data());
+      check(mrl_dist_ipc_import(_dist, all.data()), "mrl_dist_ipc_import");
+      _comm.barrier();
+    }
+  } else {
+    // partitionSerial (DomainAction.C:345-365): every rank holds the full grid
+    check(mrl_domain_set(_ctx, (int)_dim, _n_global.data(), _min_global.data(), _max_global.data()), "mrl_domain_set");
+  }
   check(mrl_domain_shape(_ctx, _shape.data(), _reciprocal_shape.data()), "mrl_domain_shape");
   _volume = 1.0;
   for (unsigned int d = 0; d < 3; ++d) {
@@ -141,8 +203,9 @@ void DomainAction::gridChanged() {
 }
 
 Tensor DomainAction::empty(Space space, bool is_complex, int ncomp) const {
-  int64_t count = space == Space::SCALAR ? 1 : (space == Space::REAL ? getNumberOfCells() : getNumberOfReciprocalCells());
+  int64_t count = space == Space::SCALAR ? 1 : (space == Space::REAL ? getNumberOfLocalCells() : getNumberOfReciprocalCells());
   if (space == Space::NODAL) {
+    if (_dist) ::mooseError("nodal fields are not available on a slab-decomposed domain");
     count = 1;
     for (unsigned int d = 0; d < _dim; ++d) count *= _n_global[d] + 1;
   }
@@ -196,7 +259,10 @@ Tensor DomainAction::fft(const Tensor &t) const {
   if (!t.defined()) ::mooseError("fft of an undefined tensor");
   if (t.space() != Space::REAL || t.is_complex()) ::mooseError("fft expects a real tensor in real space");
   Tensor out = empty(Space::RECIPROCAL, true, t.ncomp());
-  check(mrl_rfftn(_ctx, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_rfftn");
+  if (_dist)  // fftSlab (DomainAction.C:870-938)
+    check(mrl_dist_rfftn(_dist, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_dist_rfftn");
+  else
+    check(mrl_rfftn(_ctx, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_rfftn");
   return out;
 }
 
@@ -204,7 +270,10 @@ Tensor DomainAction::ifft(const Tensor &t) const {
   if (!t.defined()) ::mooseError("ifft of an undefined tensor");
   if (t.space() != Space::RECIPROCAL || !t.is_complex()) ::mooseError("ifft expects a complex tensor in reciprocal space");
   Tensor out = empty(Space::REAL, false, t.ncomp());
-  check(mrl_irfftn(_ctx, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_irfftn");
+  if (_dist)  // ifftSlab (DomainAction.C:941-1019)
+    check(mrl_dist_irfftn(_dist, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_dist_irfftn");
+  else
+    check(mrl_irfftn(_ctx, t.data_ptr(), out.data_ptr(), t.ncomp()), "mrl_irfftn");
   return out;
 }
 
@@ -217,5 +286,15 @@ Real DomainAction::reduce(int op, const Tensor &t) const {
 }
 
 Real DomainAction::sum(const Tensor &t) const { return reduce(MRL_SUM, t); }
+
+void DomainAction::getLocalBounds(unsigned int rank, std::array<int64_t, 3> &begin, std::array<int64_t, 3> &end) const {
+  if (rank >= nRanks()) ::mooseError("Requested local bounds for invalid rank ", rank, " (n_rank=", nRanks(), ").");
+  if (!_dist) {
+    begin = {0, 0, 0};
+    end = _n_global;
+    return;
+  }
+  check(mrl_dist_bounds(_ctx, (int)rank, begin.data(), end.data(), nullptr, nullptr), "mrl_dist_bounds");
+}
 
 void DomainAction::synchronize() const { check(mrl_synchronize(_ctx), "mrl_synchronize"); }

@@ -278,7 +278,7 @@ void MarlinApp::buildObjects() {
 }
 
 void MarlinApp::writeCSVRow(bool header) {
-  if (!_csv.is_open()) return;
+  if (!_csv.is_open()) return;  // rank 0 only in parallel runs
   if (header) {
     _csv << "time";
     for (const auto &pp : _csv_pps) _csv << "," << pp->name();
@@ -299,7 +299,7 @@ void MarlinApp::runVectorPostprocessors(int flag, bool csv, const std::string &f
     vpp->initialize();
     vpp->execute();
     vpp->finalize();
-    if (!csv) continue;
+    if (!csv || _domain->rank() != 0) continue;
     char tag[16];
     std::snprintf(tag, sizeof tag, "%04d", _problem->timeStep());
     std::ofstream f(file_base + "_" + vpp->name() + "_" + tag + ".csv");
@@ -332,7 +332,10 @@ void MarlinApp::dumpBuffers() {
     if (!t.defined()) mooseError("--dump: buffer '", name, "' is not defined");
     const std::vector<double> host = _domain->toHost(t);
     // little-endian float64, C order; complex tensors interleaved; rank-two fields component major
-    std::ofstream f(_opt.dump_dir + "/" + name + ".f64", std::ios::binary);
+    // parallel runs: one file per rank holding its part (real space: [nx][ny_local](,[nz]))
+    char tag[32] = "";
+    if (_domain->nRanks() > 1) std::snprintf(tag, sizeof tag, ".rank%04u", _domain->rank());
+    std::ofstream f(_opt.dump_dir + "/" + name + tag + ".f64", std::ios::binary);
     f.write(reinterpret_cast<const char *>(host.data()), std::streamsize(host.size() * sizeof(double)));
   }
 }
@@ -397,6 +400,7 @@ void MarlinApp::transient() {
   }
   if (!_opt.output_dir.empty()) file_base = _opt.output_dir + "/" + file_base.substr(file_base.rfind('/') + 1);
 
+  if (_domain->rank() != 0) _opt.quiet = true;  // one console
   if (!_skipped.empty() && !_opt.quiet) {
     std::cerr << "marlin_b200: blocks outside the spectral time-step path were skipped:";
     for (const auto &s : _skipped) std::cerr << " [" << s << "]";
@@ -418,7 +422,7 @@ void MarlinApp::transient() {
 
   _csv_pps = _problem->getPostprocessors();
   std::sort(_csv_pps.begin(), _csv_pps.end(), [](const auto &a, const auto &b) { return a->name() < b->name(); });
-  if (csv && !_csv_pps.empty()) {
+  if (csv && !_csv_pps.empty() && _domain->rank() == 0) {
     _csv.open(file_base + ".csv");
     if (!_csv) mooseError("cannot write '", file_base, ".csv'");
     writeCSVRow(true);
@@ -484,6 +488,7 @@ void MarlinApp::transient() {
   }
   _problem->execute(EXEC_FINAL);
   if ((out_on & EXEC_FINAL) && !(out_on & EXEC_TIMESTEP_END)) writeCSVRow(false);
+  _problem->waitForOutputs();
   _domain->synchronize();
   dumpBuffers();
   if (!_opt.quiet) {
@@ -549,6 +554,19 @@ static int xdmfSelfTest(const std::string &dir) {
       w.addFrame(0.001 * 3 * f, {{"c", XDMFWriter::Mode::NODE, 1, c.data()},
                                  {"disp", XDMFWriter::Mode::OVERSIZED_NODAL, 2, disp.data()},
                                  {"mu", XDMFWriter::Mode::CELL, 1, mu.data()}});
+    }
+  }
+  // a 4 x 5 grid split along y over two ranks (2 + 3 rows): each rank writes its part, rank 0 the document
+  {
+    const std::array<int64_t, 3> ng = {4, 5, 1};
+    std::vector<XDMFWriter::Bounds> bounds = {{{0, 0, 0}, {4, 2, 1}}, {{0, 2, 0}, {4, 5, 1}}};
+    for (unsigned int r = 0; r < 2; ++r) {
+      XDMFWriter w(2, ng, dx, mn, true, dir + "/selftest_par", r, bounds);
+      const int64_t nyl = bounds[r].second[1] - bounds[r].first[1];
+      std::vector<double> part(size_t(4 * nyl));
+      for (int64_t i = 0; i < 4; ++i)
+        for (int64_t j = 0; j < nyl; ++j) part[size_t(i * nyl + j)] = 100 * i + (bounds[r].first[1] + j);
+      for (int f = 0; f < 2; ++f) w.addFrame(0.5 * f, {{"c", XDMFWriter::Mode::CELL, 1, part.data()}});
     }
   }
   return 0;

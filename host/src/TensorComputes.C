@@ -225,7 +225,7 @@ void RandomTensor::computeBuffer() {
   int seed = 0;
   const bool has_seed = isParamValid("seed");
   if (has_seed) seed = getParam<int>("seed");
-  marlinTorchRand(host, size_t(_domain.getNumberOfCells()), _domain.single(), getParam<Real>("min"), getParam<Real>("max"), has_seed ? &seed : nullptr);
+  marlinTorchRand(host, size_t(_domain.getNumberOfLocalCells()), _domain.single(), getParam<Real>("min"), getParam<Real>("max"), has_seed ? &seed : nullptr);
   _u = _domain.fromHost(host, Space::REAL, false, 1);
 }
 

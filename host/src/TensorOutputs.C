@@ -21,6 +21,7 @@ TensorOutput::TensorOutput(const InputParameters &parameters)
   : MooseObject(parameters),
     _tensor_problem(*getCheckedPointerParam<TensorProblem>("_tensor_problem")),
     _domain(_tensor_problem.domain()),
+    _time(_tensor_problem.outputTime()),
     _file_base(isParamValid("file_base") ? getParam<std::string>("file_base") : getParam<std::string>("_default_file_base")),
     _execute_on(parseExecFlags(getParam<std::string>("execute_on"), _path + "/execute_on")) {
   auto names = getParam<std::vector<TensorInputBufferName>>("buffer");
@@ -29,6 +30,28 @@ TensorOutput::TensorOutput(const InputParameters &parameters)
   for (const auto &name : names) {
     TensorBufferBase &b = _tensor_problem.getBufferBase(name);
     _out_buffers.push_back(Source{name, &b, &b.getRawCPUTensor()});
+  }
+}
+
+void TensorOutput::startOutput() {
+  prepareForOutput();
+  if (_output_thread.joinable())
+    mooseError("Output thread is already running. Must call waitForCompletion() first. This is a code error.");
+  _output_thread = std::thread([this]() {
+    try {
+      output();
+    } catch (...) {
+      _thread_error = std::current_exception();
+    }
+  });
+}
+
+void TensorOutput::waitForCompletion() {
+  if (_output_thread.joinable()) _output_thread.join();
+  if (_thread_error) {
+    std::exception_ptr e = _thread_error;
+    _thread_error = nullptr;
+    std::rethrow_exception(e);
   }
 }
 
@@ -52,9 +75,13 @@ std::string g17(double v) {  // pugixml's attribute = double
 }  // namespace
 
 XDMFWriter::XDMFWriter(unsigned int dim, const std::array<int64_t, 3> &n, const std::array<double, 3> &dx, const std::array<double, 3> &min,
-                       bool transpose, std::string file_base)
-  : _dim(dim), _n(n), _transpose(transpose), _file_base(std::move(file_base)) {
+                       bool transpose, std::string file_base, unsigned int rank, std::vector<Bounds> bounds)
+  : _dim(dim), _n(n), _dx(dx), _min(min), _rank(rank), _bounds(std::move(bounds)), _transpose(transpose), _file_base(std::move(file_base)) {
   if (dim != 2 && dim != 3) ::mooseError("XDMFTensorOutput: Unsupported tensor dimension");
+  if (parallel()) {
+    if (_rank >= _bounds.size()) ::mooseError("XDMFWriter: rank ", _rank, " outside the ", _bounds.size(), " parts");
+    for (unsigned int d = 0; d < 3; ++d) _n[d] = d < dim ? _bounds[_rank].second[d] - _bounds[_rank].first[d] : 1;
+  }
   std::vector<int64_t> cells, nodes;
   std::vector<double> origin, dgrid;
   for (unsigned int i = 0; i < dim; ++i) {
@@ -128,7 +155,77 @@ std::vector<double> XDMFWriter::arrange(const Field &f, int component) const {
   return dst;
 }
 
+std::string XDMFWriter::rankTag(unsigned int rank) const {
+  if (!parallel()) return "";
+  char buf[32];
+  std::snprintf(buf, sizeof buf, ".rank%04u", rank);
+  return buf;
+}
+
+// writeLocalData (:266-355), then the frame's XML by rank 0
 void XDMFWriter::addFrame(double time, const std::vector<Field> &fields) {
+  for (const Field &f : fields) {
+    if (parallel() && f.mode != Mode::CELL) ::mooseError("XDMFTensorOutput currently supports only CELL output mode in parallel.");
+    const auto names = attributeNames(f.name, f.ncomp);
+    for (int c = 0; c < f.ncomp; ++c) {
+      const std::string fname = binaryFileName(names[c] + "." + std::to_string(_frame), _rank);
+      const std::vector<double> data = arrange(f, c);
+      std::ofstream file(fname, std::ios::out | std::ios::binary);
+      if (!file) ::mooseError("XDMFTensorOutput: cannot write '", fname, "'");
+      file.write(reinterpret_cast<const char *>(data.data()), std::streamsize(data.size() * sizeof(double)));
+    }
+  }
+  if (!parallel() || _rank == 0) {
+    _frames += parallel() ? parallelFrame(time, fields) : serialFrame(time, fields);
+    std::ofstream x(_file_base + ".xmf");
+    if (!x) ::mooseError("XDMFTensorOutput: cannot write '", _file_base, ".xmf'");
+    x << xml();
+  }
+  _frame++;
+}
+
+// writeParallelXMF (:429-527): a spatial collection with one uniform sub-grid per rank
+std::string XDMFWriter::parallelFrame(double time, const std::vector<Field> &fields) const {
+  static const char *dxyz[] = {"DX", "DY", "DZ"};
+  std::string geometry = "ORIGIN_";
+  for (unsigned int i = 0; i < _dim; ++i) geometry += dxyz[i];
+  const std::string sdim = std::to_string(_dim);
+  std::vector<double> spacing;
+  for (unsigned int i = 0; i < _dim; ++i) spacing.push_back(_dx[_transpose ? _dim - i - 1 : i]);
+  std::ostringstream g;
+  g << "\t\t\t<Grid Name=\"T" << _frame << "\" GridType=\"Collection\" CollectionType=\"Spatial\">\n"
+    << "\t\t\t\t<Time Value=\"" << g17(time) << "\" />\n";
+  for (unsigned int r = 0; r < _bounds.size(); ++r) {
+    std::vector<int64_t> cells, nodes;
+    std::vector<double> origin;
+    for (unsigned int i = 0; i < _dim; ++i) {
+      const unsigned int j = _transpose ? _dim - i - 1 : i;
+      cells.push_back(_bounds[r].second[j] - _bounds[r].first[j]);
+      nodes.push_back(cells.back() + 1);
+      origin.push_back(_min[j] + _bounds[r].first[j] * _dx[j]);
+    }
+    g << "\t\t\t\t<Grid Name=\"Rank" << r << "\" GridType=\"Uniform\">\n"
+      << "\t\t\t\t\t<Topology TopologyType=\"" << sdim << "DCoRectMesh\" Dimensions=\"" << join(nodes) << "\" />\n"
+      << "\t\t\t\t\t<Geometry Type=\"" << geometry << "\">\n"
+      << "\t\t\t\t\t\t<DataItem Format=\"XML\" Dimensions=\"" << sdim << "\">" << joinReal(origin) << "</DataItem>\n"
+      << "\t\t\t\t\t\t<DataItem Format=\"XML\" Dimensions=\"" << sdim << "\">" << joinReal(spacing) << "</DataItem>\n"
+      << "\t\t\t\t\t</Geometry>\n";
+    for (const Field &f : fields) {
+      const auto names = attributeNames(f.name, f.ncomp);
+      for (int c = 0; c < f.ncomp; ++c)
+        g << "\t\t\t\t\t<Attribute Name=\"" << names[c] << "\" Center=\"Cell\">\n"
+          << "\t\t\t\t\t\t<DataItem DataType=\"Float\" Dimensions=\"" << join(cells) << "\" Format=\"Binary\" Endian=\"Little\" Precision=\"8\">"
+          << binaryFileName(names[c] + "." + std::to_string(_frame), r) << "</DataItem>\n"
+          << "\t\t\t\t\t</Attribute>\n";
+    }
+    g << "\t\t\t\t</Grid>\n";
+  }
+  g << "\t\t\t</Grid>\n";
+  return g.str();
+}
+
+// writeSerialXMF (:358-426)
+std::string XDMFWriter::serialFrame(double time, const std::vector<Field> &fields) const {
   std::ostringstream g;
   g << "\t\t\t<Grid Name=\"T" << _frame << "\" GridType=\"Uniform\">\n"
     << "\t\t\t\t<Time Value=\"" << g17(time) << "\" />\n"
@@ -139,22 +236,14 @@ void XDMFWriter::addFrame(double time, const std::vector<Field> &fields) {
     const auto names = attributeNames(f.name, f.ncomp);
     for (int c = 0; c < f.ncomp; ++c) {
       const std::string dataset = names[c] + "." + std::to_string(_frame);
-      const std::vector<double> data = arrange(f, c);
-      std::ofstream file(binaryFileName(dataset), std::ios::out | std::ios::binary);
-      if (!file) ::mooseError("XDMFTensorOutput: cannot write '", binaryFileName(dataset), "'");
-      file.write(reinterpret_cast<const char *>(data.data()), std::streamsize(data.size() * sizeof(double)));
       g << "\t\t\t\t<Attribute Name=\"" << names[c] << "\" Center=\"" << (is_cell ? "Cell" : "Node") << "\">\n"
         << "\t\t\t\t\t<DataItem DataType=\"Float\" Dimensions=\"" << (is_cell ? _cell_dims : _node_dims)
-        << "\" Format=\"Binary\" Endian=\"Little\" Precision=\"8\">" << binaryFileName(dataset) << "</DataItem>\n"
+        << "\" Format=\"Binary\" Endian=\"Little\" Precision=\"8\">" << binaryFileName(dataset, 0) << "</DataItem>\n"
         << "\t\t\t\t</Attribute>\n";
     }
   }
   g << "\t\t\t</Grid>\n";
-  _frames += g.str();
-  _frame++;
-  std::ofstream x(_file_base + ".xmf");
-  if (!x) ::mooseError("XDMFTensorOutput: cannot write '", _file_base, ".xmf'");
-  x << xml();
+  return g.str();
 }
 
 // ============================================================================================ XDMFTensorOutput
@@ -186,6 +275,9 @@ XDMFTensorOutput::XDMFTensorOutput(const InputParameters &parameters) : TensorOu
       else if (m == "OVERSIZED_NODAL") _output_mode[names[i]] = XDMFWriter::Mode::OVERSIZED_NODAL;
       else paramError("output_mode", "Invalid option \"", modes[i], "\" (CELL NODE OVERSIZED_NODAL)");
     }
+  if (_domain.nRanks() > 1)
+    for (const auto &m : _output_mode)
+      if (m.second != XDMFWriter::Mode::CELL) mooseError("XDMFTensorOutput currently supports only CELL output mode in parallel.");
   if (getParam<bool>("enable_hdf5")) mooseWarning("XDMFTensorOutput: this build has no HDF5 library; writing raw binary data files instead.");
 }
 
@@ -195,14 +287,20 @@ void XDMFTensorOutput::init() {
     dx[d] = _domain.getGridSpacing()[d];
     mn[d] = _domain.getDomainMin()[d];
   }
-  _writer = std::make_unique<XDMFWriter>(_domain.getDim(), _domain.getGridSize(), dx, mn, _transpose, _file_base);
+  std::vector<XDMFWriter::Bounds> bounds;
+  if (_domain.nRanks() > 1) {
+    bounds.resize(_domain.nRanks());
+    for (unsigned int r = 0; r < _domain.nRanks(); ++r) _domain.getLocalBounds(r, bounds[r].first, bounds[r].second);
+  }
+  _writer = std::make_unique<XDMFWriter>(_domain.getDim(), _domain.getGridSize(), dx, mn, _transpose, _file_base, _domain.rank(), bounds);
 }
 
-void XDMFTensorOutput::output() {
+// the buffers' metadata is read here, on the main thread; the output thread only touches the CPU copies
+void XDMFTensorOutput::prepareForOutput() {
   if (!_writer) init();
-  std::vector<XDMFWriter::Field> fields;
-  int64_t cells = _domain.getNumberOfCells(), nodes = 1;
-  for (unsigned int d = 0; d < _domain.getDim(); ++d) nodes *= _domain.getGridSize()[d] + 1;
+  _fields.clear();
+  int64_t cells = _domain.getNumberOfLocalCells(), nodes = 1;
+  for (unsigned int d = 0; d < _domain.getDim(); ++d) nodes *= _domain.getShape()[d] + 1;
   for (const auto &s : _out_buffers) {
     const marlin::Tensor &t = s.buffer->getRawTensor();
     if (!t.defined()) continue;  // :270-271
@@ -211,7 +309,8 @@ void XDMFTensorOutput::output() {
     const int64_t expect = (mode == XDMFWriter::Mode::OVERSIZED_NODAL ? nodes : cells) * t.ncomp();
     if ((int64_t)s.cpu->size() != expect)
       mooseError("XDMFTensorOutput: buffer '", s.name, "' has ", s.cpu->size(), " values, output mode expects ", expect);
-    fields.push_back(XDMFWriter::Field{s.name, mode, t.ncomp(), s.cpu->data()});
+    _fields.push_back(XDMFWriter::Field{s.name, mode, t.ncomp(), s.cpu->data()});
   }
-  _writer->addFrame(_tensor_problem.time(), fields);
 }
+
+void XDMFTensorOutput::output() { _writer->addFrame(_time, _fields); }

@@ -31,6 +31,9 @@ TensorPostprocessor::TensorPostprocessor(const InputParameters &parameters)
 
 namespace {
 
+// gatherSum / gatherMin / gatherMax of MOOSE's postprocessors, over the process group of the domain
+void gather(const DomainAction &domain, Real &v, Comm::Op op) { domain.comm().allreduce(&v, 1, op); }
+
 class TensorAveragePostprocessor : public TensorPostprocessor {
 public:
   static InputParameters validParams() {
@@ -44,7 +47,12 @@ public:
     _sum = _domain.sum(_u);
     _numel = Real(_u.numel());
   }
-  void finalize() override { _average = _sum / _numel; }
+  void finalize() override {
+    // src/postprocessors/TensorAveragePostprocessor.C:41-48
+    gather(_domain, _sum, Comm::SUM);
+    gather(_domain, _numel, Comm::SUM);
+    _average = _sum / _numel;
+  }
   Real getValue() const override { return _average; }
 
 protected:
@@ -84,6 +92,7 @@ public:
     if (!_u.defined()) mooseError("buffer '", _buffer_name, "' is not defined");
     _value = _domain.reduce(_is_min ? MRL_MIN : MRL_MAX, _u);
   }
+  void finalize() override { gather(_domain, _value, _is_min ? Comm::MIN : Comm::MAX); }  // TensorExtremeValuePostprocessor.C:38-44
   Real getValue() const override { return _value; }
 
 protected:
@@ -108,6 +117,7 @@ public:
     _integral = _domain.sum(d);
     for (unsigned int dd = 0; dd < _domain.getDim(); ++dd) _integral *= _domain.getGridSpacing()[dd];
   }
+  void finalize() override { gather(_domain, _integral, Comm::SUM); }
   Real getValue() const override { return _integral; }
 
 protected:
@@ -133,6 +143,7 @@ public:
     const Real max_norm_k = std::sqrt(_domain.reduce(MRL_MAX, _norm.eval(_domain, {&_u}, 0.0)));
     _critical_dt = max_norm_k > 0.0 ? 1.0 / max_norm_k : 1e30;
   }
+  void finalize() override { gather(_domain, _critical_dt, Comm::MIN); }  // SemiImplicitCriticalTimeStep.C:39
   Real getValue() const override { return _critical_dt; }
 
 protected:
@@ -171,6 +182,7 @@ public:
     }
     _velocity = std::sqrt(_domain.reduce(MRL_MAX, vsq));
   }
+  void finalize() override { gather(_domain, _velocity, Comm::MAX); }
   Real getValue() const override { return _velocity; }
 
 protected:
@@ -220,6 +232,10 @@ public:
       count[pos] += 1.0;
     }
   }
+  void finalize() override {
+    auto &count = _vectors["count"];
+    _domain.comm().allreduce(count.data(), count.size(), Comm::SUM);
+  }
 
 protected:
   const Real _min, _max;
@@ -249,7 +265,9 @@ public:
       z[0] = zf[0];
     }
     _integral = z[0] / Real(_domain.getNumberOfCells()) * _domain.getVolume();
+    if (_domain.rank() != 0) _integral = 0.0;  // the zero wavevector is in rank 0's x slab
   }
+  void finalize() override { gather(_domain, _integral, Comm::SUM); }
   Real getValue() const override { return _integral; }
 
 protected:

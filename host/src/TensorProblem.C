@@ -32,7 +32,18 @@ TensorProblem::TensorProblem(const InputParameters &parameters)
   for (const auto &[name, value] : getParam<std::string, Real>("scalar_constant_names", "scalar_constant_values")) declareConstant(name, value);
 }
 
+void TensorProblem::waitForOutputs() {
+  for (auto &out : _outputs) out->waitForCompletion();
+}
+
 TensorProblem::~TensorProblem() {
+  // the output threads read the buffers' CPU copies (TensorProblem.C:66-72)
+  try {
+    waitForOutputs();
+  } catch (const std::exception &e) {
+    std::cerr << "marlin_b200: output failed: " << e.what() << "\n";
+  }
+  _outputs.clear();
   // operators and buffers hold device memory that must go back to the pool before the domain dies
   _solver.reset();
   _postprocessors.clear();
@@ -124,9 +135,13 @@ void TensorProblem::execute(ExecFlagType exec_type) {
   // buffers the outputs asked for, then the outputs scheduled for this flag
   auto run_pps = [&]() {
     for (auto &pp : _pps) pp->computeBuffer();
+    // wait for the threads still writing the previous frame, then refresh the CPU copies (the device
+    // synchronisation point) and start this frame's outputs in their threads
+    for (auto &out : _outputs) out->waitForCompletion();
+    _output_time = _time;
     for (auto &kv : _tensor_buffer) kv.second->makeCPUCopy(_domain);
     for (auto &out : _outputs)
-      if (out->shouldRun(exec_type)) out->output();
+      if (out->shouldRun(exec_type)) out->startOutput();
   };
   if (exec_type == EXEC_INITIAL) {
     if (!_fetched_constants.empty()) {

@@ -708,6 +708,7 @@ SecantSolver::SecantSolver(const InputParameters &parameters)
 Real SecantSolver::complexNorm(const Tensor &t) const {
   double s = 0;
   checkC(mrl_reduce(_domain.context(), MRL_SUMSQ, t.data_ptr(), t.numel() * (t.is_complex() ? 2 : 1), &s), "mrl_reduce");
+  _domain.comm().allreduce(&s, 1, Comm::SUM);  // every rank takes the same convergence decision
   return std::sqrt(s);
 }
 
@@ -811,6 +812,7 @@ Real BroydenSolver::stackedNorm(const std::vector<Tensor> &R) const {
     checkC(mrl_reduce(_domain.context(), MRL_SUMSQ, t.data_ptr(), t.numel() * (t.is_complex() ? 2 : 1), &s), "mrl_reduce");
     total += s;
   }
+  _domain.comm().allreduce(&total, 1, Comm::SUM);
   return std::sqrt(total);
 }
 

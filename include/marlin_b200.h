@@ -46,6 +46,8 @@ int mrl_create(int device, int precision, mrl_context **out);
 int mrl_destroy(mrl_context *ctx);
 const char *mrl_last_error(void);
 const char *mrl_version(void);
+int mrl_device_count(int *count); /* CUDA devices visible to this process (device_names / local-rank assignment,
+                                     src/actions/DomainAction.C:196-197)                                         */
 int mrl_set_stream(mrl_context *ctx, void *cuda_stream); /* run on a caller-owned stream */
 int mrl_own_stream(mrl_context *ctx);                    /* create a stream owned by the context and run on it
                                                             (capturable: enables the CUDA-graph paths)        */
@@ -312,6 +314,49 @@ int mrl_domain_set_slab(mrl_context *ctx, int dim, const int64_t *n, const doubl
 /* local shapes and first global index: real [nx][ny/P][nz], reciprocal [nx/P][ny][nz/2+1] */
 int mrl_domain_local(const mrl_context *ctx, int64_t *real_shape, int64_t *real_begin, int64_t *recip_shape,
                      int64_t *recip_begin);
+
+/* ---- generic decomposed transforms (any grid size, unequal parts) -------------------------------------
+ * Behind DomainAction::fft / ifft for [Domain] parallel_mode = FFT_SLAB and FFT_PENCIL: one process per GPU.
+ *
+ * FFT_SLAB  (DomainAction::partitionSlabs / fftSlab / ifftSlab, src/actions/DomainAction.C:511-566, :870-938,
+ *   :941-1019; 2-D and 3-D): real space split along y, reciprocal space along x with the slab sizes of partitionHepler
+ *   (include/actions/DomainAction.h:249-280; `weights` = [Domain] device_weights, NULL = equal).
+ *   mrl_domain_set_dist makes the context's domain the LOCAL one: real shape [nx][ny_local](,[nz]), reciprocal
+ *   shape [nx_local][ny](,[nz/2+1]) - an x-slice of the serial-mode layout (half spectrum on the last axis; the
+ *   reference exchanges the full c2c spectrum, twice the bytes, same fields).
+ * FFT_PENCIL (partitionPencils / fftPencil / ifftPencil, :569-742, :1022-1047, :1106-1404; 3-D, nranks = Py * Pz with
+ *   the reference's choice of factors): rank = iz * Py + iy holds real [nx][ny / Py][nz / Pz] and reciprocal
+ *   [(nx/2+1) / Py][ny / Pz][nz], half spectrum on x, exactly the reference's layout and k-axes.
+ *
+ * In both modes the device axes are the local slices, so that every pointwise entry point (mrl_kfactor,
+ * mrl_expr_eval, mrl_ab_update, mrl_reduce ...) works on a rank's part unchanged.  mrl_rfftn / mrl_irfftn are
+ * refused on such a context; the transforms are mrl_dist_rfftn / mrl_dist_irfftn, whose exchanges are strided
+ * peer-to-peer copies over NVLink into staging buffers shared through CUDA IPC, bracketed by device-side barriers. */
+typedef struct mrl_dist mrl_dist;
+int mrl_domain_set_dist(mrl_context *ctx, int dim, const int64_t *n, const double *min, const double *max, int rank,
+                        int nranks, const double *weights);
+int mrl_domain_set_pencil(mrl_context *ctx, int dim, const int64_t *n, const double *min, const double *max, int rank,
+                          int nranks);
+/* slab mode: global grid size and the slab table: counts / begins of the real-space y slabs and the reciprocal x
+ * slabs of every rank (each array nranks entries; any pointer may be NULL)                                  */
+int mrl_dist_partition(const mrl_context *ctx, int64_t *n_global, int64_t *y_count, int64_t *y_begin, int64_t *x_count,
+                       int64_t *x_begin);
+/* any mode: [begin, end) of `rank`'s part in real and in reciprocal space, 3 entries each (DomainAction::getLocalBounds,
+ * :1543-1556; any pointer may be NULL)                                                                      */
+int mrl_dist_bounds(const mrl_context *ctx, int rank, int64_t *real_begin, int64_t *real_end, int64_t *recip_begin,
+                    int64_t *recip_end);
+int mrl_dist_create(mrl_context *ctx, mrl_dist **out);
+int mrl_dist_destroy(mrl_dist *d);
+/* This rank's record for the peers (CUDA IPC handle of its shared staging allocation + the offsets of the staging
+ * areas: MRL_DIST_IPC_BYTES bytes) / import of all ranks' records in rank order (nranks x MRL_DIST_IPC_BYTES); the
+ * host objects exchange them over their rendezvous (host/shim/comm.h)                                        */
+#define MRL_DIST_IPC_BYTES 128
+int mrl_dist_ipc_export(mrl_dist *d, void *record);
+int mrl_dist_ipc_import(mrl_dist *d, const void *all_records);
+/* DomainAction::fft / ifft on `batch` fields (batch slowest): local real <-> local reciprocal part; forward
+ * unnormalised, inverse scaled by 1/N.  Collective: every rank must call with the same batch.               */
+int mrl_dist_rfftn(mrl_dist *d, const void *in_real_dev, void *out_cplx_dev, int batch);
+int mrl_dist_irfftn(mrl_dist *d, const void *in_cplx_dev, void *out_real_dev, int batch);
 
 typedef struct mrl_slab_plan mrl_slab_plan;
 /* Element counts (complex elements) of the exchange buffers the caller must allocate:

@@ -488,3 +488,84 @@ class MechPlan:
             self.close()
         except Exception:
             pass
+
+
+class DistContext(Context):
+    """A context whose domain is one rank's part of a slab-decomposed grid (mrl_domain_set_dist): real space split
+    along y, reciprocal space along x with the slab sizes of partitionHepler (include/actions/DomainAction.h:249-280)."""
+
+    def domain_set_dist(self, dim, n, mins, maxs, rank, nranks, weights=None):
+        n3 = (C.c_int64 * 3)(*[int(n[d]) if d < dim else 1 for d in range(3)])
+        mn = (C.c_double * 3)(*[float(mins[d]) if d < len(mins) else 0.0 for d in range(3)])
+        mx = (C.c_double * 3)(*[float(maxs[d]) if d < len(maxs) else 1.0 for d in range(3)])
+        w = (C.c_double * nranks)(*[float(v) for v in weights]) if weights is not None else None
+        _ck(lib().mrl_domain_set_dist(self.h, int(dim), n3, mn, mx, int(rank), int(nranks), w))
+        self.dim, self.rank, self.nranks = dim, rank, nranks
+        rs, rb, ks, kb = [(C.c_int64 * 3)() for _ in range(4)]
+        _ck(lib().mrl_domain_local(self.h, rs, rb, ks, kb))
+        self.shape, self.rbegin = [rs[d] for d in range(dim)], [rb[d] for d in range(dim)]
+        self.rshape, self.kbegin = [ks[d] for d in range(dim)], [kb[d] for d in range(dim)]
+
+    def domain_set_pencil(self, n, mins, maxs, rank, nranks):
+        """FFT_PENCIL (partitionPencils, src/actions/DomainAction.C:569-742): real [nx][ny / Py][nz / Pz], reciprocal
+        [(nx/2+1) / Py][ny / Pz][nz], rank = iz * Py + iy."""
+        n3 = (C.c_int64 * 3)(*[int(v) for v in n])
+        mn = (C.c_double * 3)(*[float(v) for v in mins])
+        mx = (C.c_double * 3)(*[float(v) for v in maxs])
+        _ck(lib().mrl_domain_set_pencil(self.h, 3, n3, mn, mx, int(rank), int(nranks)))
+        self.dim, self.rank, self.nranks = 3, rank, nranks
+        rs, rb, ks, kb = [(C.c_int64 * 3)() for _ in range(4)]
+        _ck(lib().mrl_domain_local(self.h, rs, rb, ks, kb))
+        self.shape, self.rbegin = list(rs), list(rb)
+        self.rshape, self.kbegin = list(ks), list(kb)
+
+    def rfftn(self, t):
+        raise MarlinError("decomposed domain: use Dist.rfftn")
+
+    irfftn = rfftn
+
+
+class Dist:
+    """DomainAction::fftSlab / ifftSlab (src/actions/DomainAction.C:870-938, :941-1019) through mrl_dist_*; the IPC
+    handles travel over torch.distributed (any backend)."""
+
+    def __init__(self, ctx, group=None):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _ck(lib().mrl_dist_create(ctx.h, C.byref(self.h)))
+        if ctx.nranks > 1:
+            mine = (C.c_ubyte * 128)()  # MRL_DIST_IPC_BYTES
+            _ck(lib().mrl_dist_ipc_export(self.h, mine))
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=ctx.device if dist.get_backend(group) == "nccl" else "cpu")
+            alls = [torch.empty_like(t) for _ in range(ctx.nranks)]
+            dist.all_gather(alls, t, group=group)
+            _ck(lib().mrl_dist_ipc_import(self.h, bytes(torch.cat(alls).cpu().tolist())))
+            dist.barrier(group=group)
+
+    def rfftn(self, t):
+        c = self.ctx
+        assert t.is_cuda and t.dtype == c.rdtype and t.is_contiguous()
+        b, lead = c._batch(t, c.shape)
+        out = torch.empty(lead + c.rshape, dtype=c.cdtype, device=t.device)
+        _ck(lib().mrl_dist_rfftn(self.h, _p(t), _p(out), b))
+        return out
+
+    def irfftn(self, t):
+        c = self.ctx
+        assert t.is_cuda and t.dtype == c.cdtype and t.is_contiguous()
+        b, lead = c._batch(t, c.rshape)
+        out = torch.empty(lead + c.shape, dtype=c.rdtype, device=t.device)
+        _ck(lib().mrl_dist_irfftn(self.h, _p(t), _p(out), b))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().mrl_dist_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

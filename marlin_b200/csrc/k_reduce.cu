@@ -53,7 +53,8 @@ template cudaError_t launch_reduce<float>(const LaunchCtx &, int, const float *,
 // slot.  Launched after a pass whose peer stores must be visible before the next pass reads them: the
 // stream order + the release/acquire pair give that.  A peer that never arrives trips the timeout
 // (~4 s) and traps instead of hanging the device.
-__global__ void k_slab_barrier(const unsigned long long *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch) {
+__global__ void k_slab_barrier(const unsigned long long *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch,
+                               long long timeout_cycles) {
   const int s = threadIdx.x;
   if (s >= nranks) return;
   unsigned long long *theirs = reinterpret_cast<unsigned long long *>(recv_tab[s] + flag_off) + rank;
@@ -64,11 +65,12 @@ __global__ void k_slab_barrier(const unsigned long long *recv_tab, long long fla
   unsigned long long v;
   do {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-    if (v < epoch && clock64() - t0 > 8000000000ll) __trap();
+    if (v < epoch && clock64() - t0 > timeout_cycles) __trap();
   } while (v < epoch);
 }
-cudaError_t launch_slab_barrier(const LaunchCtx &lc, const void *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch) {
-  k_slab_barrier<<<1, 32, 0, lc.stream>>>((const unsigned long long *)recv_tab, flag_off, rank, nranks, epoch);
+cudaError_t launch_slab_barrier(const LaunchCtx &lc, const void *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch,
+                                long long timeout_cycles) {
+  k_slab_barrier<<<1, 32, 0, lc.stream>>>((const unsigned long long *)recv_tab, flag_off, rank, nranks, epoch, timeout_cycles);
   return cudaGetLastError();
 }
 

@@ -32,6 +32,13 @@ int mrl_fail(int code, const char *fmt, ...) {
 }
 extern "C" const char *mrl_last_error(void) { return g_err.c_str(); }
 extern "C" const char *mrl_version(void) { return "marlin_b200 0.1 (sm_100a)"; }
+extern "C" int mrl_device_count(int *count) {
+  if (!count) return mrl_fail(MRL_ERR_INVALID, "mrl_device_count: null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+  *count = n;
+  return MRL_OK;
+}
 
 #define CK(call)                                                                         \
   do {                                                                                   \
@@ -255,7 +262,13 @@ extern "C" int mrl_domain_set(mrl_context *ctx, int dim, const int64_t *n, const
       return mrl_fail(MRL_ERR_INVALID, "Max coordinate must be larger than the min coordinate in every dimension");
   }
   ctx->dim = dim;
+  ctx->dist = false;
+  ctx->pencil = false;
+  ctx->rank = 0;
+  ctx->nranks = 1;
+  ctx->nyl = ctx->nxl = ctx->y0 = ctx->x0 = 0;
   for (int d = 0; d < 3; ++d) {
+    ctx->gn[d] = d < dim ? (int)n[d] : 1;
     ctx->n[d] = d < dim ? (int)n[d] : 1;
     ctx->min[d] = d < dim ? mn[d] : 0.0;
     ctx->max[d] = d < dim ? mx[d] : 1.0;
@@ -482,6 +495,56 @@ template <class T> static int irfftn_impl(mrl_context *ctx, const cx<T> *in, T *
   return irfftn_impl2<T>(ctx, in, sc, out, batch, 0, 1.0 / N);
 }
 
+// single passes on explicit shapes: see mrl_internal.h
+template <class T> static int pass_strided_t(mrl_context *ctx, const cx<T> *in, cx<T> *out, int n, long long ncols, long long nouter, int inverse) {
+  StridedIO<T> io;
+  memset(&io, 0, sizeof io);
+  io.in[0] = in;
+  io.out[0] = out;
+  io.nfields = 1;
+  io.n = n;
+  io.ncols = (int)ncols;
+  io.nouter = (int)nouter;
+  io.pitch = ncols;
+  io.outer_stride = (long long)n * ncols;
+  io.scale = T(1);
+  io.inverse = inverse;
+  const void *tw;
+  int rc = ctx->twiddles(n, &tw);
+  if (rc) return rc;
+  ctx->launches++;
+  cudaError_t te = launch_strided_tma<T>(ctx->lc(), io, (const cx<T> *)tw, n);
+  if (te == cudaErrorNotSupported) te = launch_strided<T>(ctx->lc(), io, (const cx<T> *)tw, make_fft_plan(n));
+  CK(te);
+  return MRL_OK;
+}
+int mrl_pass_strided(mrl_context *ctx, const void *in, void *out, int n, long long ncols, long long nouter, int inverse) {
+  return ctx->precision == MRL_F64 ? pass_strided_t<double>(ctx, (const cx<double> *)in, (cx<double> *)out, n, ncols, nouter, inverse)
+                                   : pass_strided_t<float>(ctx, (const cx<float> *)in, (cx<float> *)out, n, ncols, nouter, inverse);
+}
+template <class T> static int pass_zfwd_t(mrl_context *ctx, const T *in, cx<T> *out, long long rows, int n) {
+  const void *tw;
+  int rc = ctx->twiddles(n, &tw);
+  if (rc) return rc;
+  ctx->launches++;
+  cudaError_t e = launch_zfwd_pairs_tma<T>(ctx->lc(), in, out, rows, n, n / 2 + 1, (const cx<T> *)tw);
+  if (e == cudaErrorNotSupported) e = launch_zfwd_pairs<T>(ctx->lc(), in, out, rows, n, (const cx<T> *)tw, make_fft_plan(n));
+  CK(e);
+  return MRL_OK;
+}
+int mrl_pass_zfwd(mrl_context *ctx, const void *in, void *out, long long rows, int n) {
+  return ctx->precision == MRL_F64 ? pass_zfwd_t<double>(ctx, (const double *)in, (cx<double> *)out, rows, n)
+                                   : pass_zfwd_t<float>(ctx, (const float *)in, (cx<float> *)out, rows, n);
+}
+int mrl_pass_zinv(mrl_context *ctx, const void *in, void *out, long long rows, int n, double scale) {
+  const void *tw;
+  int rc = ctx->twiddles(n, &tw);
+  if (rc) return rc;
+  if (ctx->precision == MRL_F64) CKL(ctx, zinv_dispatch<double>(ctx, (const cx<double> *)in, (double *)out, rows, n, scale, (const cx<double> *)tw));
+  else CKL(ctx, zinv_dispatch<float>(ctx, (const cx<float> *)in, (float *)out, rows, n, (float)scale, (const cx<float> *)tw));
+  return MRL_OK;
+}
+
 // Internal batched transforms on padded layouts (mechanics): see mrl_internal.h
 int mrl_fftb_pitch(const mrl_context *ctx) {
   const int dim = ctx->dim, nc = ctx->nr[dim - 1];
@@ -508,12 +571,14 @@ int mrl_fftb_inverse(mrl_context *ctx, void *work, void *out, int batch, int ncp
 
 extern "C" int mrl_rfftn(mrl_context *ctx, const void *in, void *out, int batch) {
   if (!ctx || !ctx->dim || !in || !out || batch < 1) return mrl_fail(MRL_ERR_INVALID, "mrl_rfftn: bad arguments / domain not set");
+  if (ctx->dist) return mrl_fail(MRL_ERR_INVALID, "mrl_rfftn: the domain is slab-decomposed (mrl_domain_set_dist): use mrl_dist_rfftn");
   CK(cudaSetDevice(ctx->device));
   return ctx->precision == MRL_F64 ? rfftn_impl<double>(ctx, (const double *)in, (cx<double> *)out, batch)
                                    : rfftn_impl<float>(ctx, (const float *)in, (cx<float> *)out, batch);
 }
 extern "C" int mrl_irfftn(mrl_context *ctx, const void *in, void *out, int batch) {
   if (!ctx || !ctx->dim || !in || !out || batch < 1) return mrl_fail(MRL_ERR_INVALID, "mrl_irfftn: bad arguments / domain not set");
+  if (ctx->dist) return mrl_fail(MRL_ERR_INVALID, "mrl_irfftn: the domain is slab-decomposed (mrl_domain_set_dist): use mrl_dist_irfftn");
   CK(cudaSetDevice(ctx->device));
   return ctx->precision == MRL_F64 ? irfftn_impl<double>(ctx, (const cx<double> *)in, (double *)out, batch)
                                    : irfftn_impl<float>(ctx, (const cx<float> *)in, (float *)out, batch);
@@ -643,6 +708,9 @@ extern "C" int mrl_split_plan_create(mrl_context *ctx, const mrl_split_desc *d, 
   if (!ctx || !ctx->dim || !d || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_split_plan_create: bad arguments");
   if (ctx->dim < 2)
     return mrl_fail(MRL_ERR_UNSUPPORTED, "fused split plan needs dim >= 2 (1-D problems use the un-fused operators)");
+  if (ctx->dist)
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "the single-GPU fused split plan does not run on a slab-decomposed domain (un-fused operators over "
+                                         "mrl_dist_rfftn / mrl_dist_irfftn, or mrl_slab_plan_create_peer)");
   if (d->nonlin_kind != MRL_NONLIN_DOUBLE_WELL && d->nonlin_kind != MRL_NONLIN_EXPR)
     return mrl_fail(MRL_ERR_INVALID, "unknown nonlin_kind");
   if (d->nonlin_kind == MRL_NONLIN_EXPR && !d->nonlin_expr) return mrl_fail(MRL_ERR_INVALID, "nonlin_expr is NULL");
@@ -1003,6 +1071,16 @@ extern "C" int mrl_domain_set_slab(mrl_context *ctx, int dim, const int64_t *n, 
 
 extern "C" int mrl_domain_local(const mrl_context *ctx, int64_t *rs, int64_t *rb, int64_t *ks, int64_t *kb) {
   if (!ctx || !ctx->dim) return mrl_fail(MRL_ERR_INVALID, "domain not set");
+  if (ctx->dist) {
+    int64_t re[3], ke[3], b0[3], b1[3];
+    int rc = mrl_dist_bounds(ctx, ctx->rank, rb ? rb : b0, re, kb ? kb : b1, ke);
+    if (rc) return rc;
+    for (int d = 0; d < 3; ++d) {
+      if (rs) rs[d] = ctx->n[d];
+      if (ks) ks[d] = ctx->nr[d];
+    }
+    return MRL_OK;
+  }
   const bool slab = ctx->nranks > 1 || ctx->nyl;
   for (int d = 0; d < 3; ++d) {
     if (rs) rs[d] = (slab && d == 1) ? ctx->nyl : ctx->n[d];

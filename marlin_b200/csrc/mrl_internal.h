@@ -32,6 +32,14 @@ struct mrl_context {
   // slab decomposition (nranks == 1: serial)
   int rank = 0, nranks = 1;
   int nyl = 0, nxl = 0, y0 = 0, x0 = 0;  // local extents / first global index (y real, x reciprocal)
+  // generic slab decomposition (mrl_domain_set_dist): n / nr above are the LOCAL shapes, gn the global grid
+  bool dist = false;
+  int gn[3] = {1, 1, 1};
+  std::vector<int64_t> ycount, ybegin, xcount, xbegin;  // slab: per rank; pencil: per y-part index (rank % py)
+  // pencil decomposition (mrl_domain_set_pencil): rank = iz * py + iy
+  bool pencil = false;
+  int py = 1, pz = 1;
+  std::vector<int64_t> zcount, zbegin, y2count, y2begin;  // per z-part index (rank / py): real-space z, reciprocal ky
   // caches
   std::map<int, void *> tw;
   void *scratch_ptr = nullptr;
@@ -107,6 +115,13 @@ struct mrl_slab_plan {
   unsigned long long epoch = 0;        // barriers issued so far
 };
 
+// single passes on explicit shapes (generic kernels for any length, pipelined ones where a configuration exists)
+//   complex pass along the middle axis of [nouter][n][ncols] (in == out allowed); inverse: conj . FFT . conj, unnormalised
+int mrl_pass_strided(mrl_context *ctx, const void *in, void *out, int n, long long ncols, long long nouter, int inverse);
+//   last-axis r2c / c2r of `rows` rows of length n (half spectra of n/2+1)
+int mrl_pass_zfwd(mrl_context *ctx, const void *in_real, void *out_cplx, long long rows, int n);
+int mrl_pass_zinv(mrl_context *ctx, const void *in_cplx, void *out_real, long long rows, int n, double scale);
+
 // Internal batched real transforms on [batch][n0][n1][n2] fields with a last-axis spectrum pitch
 // ncp >= n2/2+1 (mrl_fftb_pitch: padded to 128 bytes when every axis runs on the TMA kernels).
 // forward: unnormalised; inverse: `work` is transformed in place (destroyed), result * scale.
@@ -120,7 +135,19 @@ namespace mrl {
 FFTPlanDev make_fft_plan(int n);
 template <class T>
 cudaError_t launch_reduce(const LaunchCtx &lc, int op, const T *in, long long count, double *partials, int nblk);
-cudaError_t launch_slab_barrier(const LaunchCtx &lc, const void *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch);
+// timeout_cycles: a peer that never arrives traps the kernel instead of hanging the device (8e9 ~ 4 s)
+cudaError_t launch_slab_barrier(const LaunchCtx &lc, const void *recv_tab, long long flag_off, int rank, int nranks, unsigned long long epoch,
+                                long long timeout_cycles = 8000000000ll);
+// small layout kernels of the generic distributed transforms (k_dist.cu)
+template <class T> cudaError_t launch_real_to_complex(const LaunchCtx &lc, const T *in, cx<T> *out, long long n);
+template <class T> cudaError_t launch_complex_real_scale(const LaunchCtx &lc, const cx<T> *in, T *out, long long n, T scale);
+template <class T> cudaError_t launch_expand_half(const LaunchCtx &lc, const cx<T> *in, cx<T> *out, long long rows, int n);
+//   dst[i0 * d0 + i1 * d1 + k] = src[i0 * s0 + i1 * s1 + k], i0 < n0, i1 < n1, k < w (strides in elements; dst may be peer memory)
+template <class T>
+cudaError_t launch_copy3d(const LaunchCtx &lc, cx<T> *dst, long long d0, long long d1, const cx<T> *src, long long s0, long long s1, long long n0,
+                          long long n1, long long w);
+//   a[k][c] = conj a[n - k][c] for n/2 < k < n, c < ncols (Hermitian completion of a half spectrum along the slow axis)
+template <class T> cudaError_t launch_hermitian_rows(const LaunchCtx &lc, cx<T> *a, int n, long long ncols);
 }  // namespace mrl
 
 // expression-specialised first pass (mrl_expr_zfwd.cu); returns MRL status

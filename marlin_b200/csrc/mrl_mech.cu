@@ -64,6 +64,7 @@ extern "C" int mrl_mech_plan_destroy(mrl_mech_plan *p) {
 
 extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, const void *K, const void *mu, mrl_mech_plan **out) {
   if (!ctx || !d || !K || !mu || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_plan_create: bad arguments");
+  if (ctx->dist) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_mech_plan_create: the mechanics plan is single-GPU (the domain is slab-decomposed)");
   if (ctx->dim != 3 && ctx->dim != 2)
     return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_mech_plan_create: the CUDA mechanics path is 2-D or 3-D (dim = %d)", ctx->dim);
   CK(cudaSetDevice(ctx->device));
