@@ -77,6 +77,7 @@ protected:
 };
 
 struct mrl_split_plan;
+struct mrl_slab_plan;
 struct mrl_expr;
 
 class AdamsBashforthMoulton : public SplitOperatorBase {
@@ -106,6 +107,7 @@ protected:
   // split-operator pattern; empty = generic operator-by-operator path
   struct FusedVariable {
     mrl_split_plan *plan = nullptr;
+    mrl_slab_plan *slab = nullptr;  // [Domain] parallel_mode = FFT_SLAB: the multi-GPU plan with the exchanges fused into the passes
     mrl_expr *expr = nullptr;
     int stored = 0;  // old nonlinear terms currently held by the plan's ring
     std::string g_name;  // real-space nonlinearity buffer to materialise (observed), or empty

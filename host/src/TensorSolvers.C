@@ -201,8 +201,19 @@ AdamsBashforthMoulton::AdamsBashforthMoulton(const InputParameters &parameters)
 }
 
 AdamsBashforthMoulton::~AdamsBashforthMoulton() {
+  bool slab = false;
+  for (auto &p : _plans) slab = slab || p.slab;
+  if (slab) {
+    // the peers may still be writing into this rank's staging buffers
+    mrl_synchronize(_domain.context());
+    try {
+      _domain.comm().barrier();
+    } catch (const std::exception &) {
+    }
+  }
   for (auto &p : _plans) {
     if (p.plan) mrl_split_plan_destroy(p.plan);
+    if (p.slab) mrl_slab_plan_destroy(p.slab);
     if (p.expr) mrl_expr_destroy(p.expr);
   }
 }
@@ -215,7 +226,8 @@ void AdamsBashforthMoulton::decideFusion() {
   _fusion_decided = true;
   if (_allow_fusion) tryBuildFusedPlans();
   if (_tensor_problem.debugOutput())
-    mooseInfo("AdamsBashforthMoulton '", name(), "': ", fused() ? "fused five-pass plan" : "operator-by-operator path", _fusion_note.empty() ? "" : " (", _fusion_note,
+    mooseInfo("AdamsBashforthMoulton '", name(), "': ", fused() ? (_plans[0].slab ? "fused slab-decomposed plan" : "fused five-pass plan") : "operator-by-operator path",
+              _fusion_note.empty() ? "" : " (", _fusion_note,
               _fusion_note.empty() ? "" : ")");
 }
 
@@ -340,10 +352,12 @@ void AdamsBashforthMoulton::tryBuildFusedPlans() {
   auto fail = [&](const std::string &why) {
     for (auto &p : plans) {
       if (p.plan) mrl_split_plan_destroy(p.plan);
+      if (p.slab) mrl_slab_plan_destroy(p.slab);
       if (p.expr) mrl_expr_destroy(p.expr);
     }
     note(why);
   };
+  const bool parallel = _domain.isParallelFFT();
   for (std::size_t k = 0; k < _variables.size(); ++k) {
     const auto &v = _variables[k];
     const auto &m = matches[k];
@@ -408,7 +422,28 @@ void AdamsBashforthMoulton::tryBuildFusedPlans() {
       sd.g_out_real_dev = g.data_ptr();
       fv.g_name = m.g_name;
     }
-    if (mrl_split_plan_create(_domain.context(), &sd, &fv.plan) != MRL_OK) {
+    if (parallel) {
+      // every rank takes the same decision: a plan any rank cannot build is dropped by all
+      std::string why;
+      if (mrl_slab_plan_create_peer(_domain.context(), &sd, &fv.slab) != MRL_OK) {
+        why = mrl_last_error();
+        fv.slab = nullptr;
+      }
+      double ok = fv.slab ? 1.0 : 0.0;
+      _domain.comm().allreduce(&ok, 1, Comm::MIN);
+      if (ok == 0.0) {
+        if (fv.slab) mrl_slab_plan_destroy(fv.slab);
+        mrl_expr_destroy(fv.expr);
+        return fail("slab plan: " + (why.empty() ? std::string("another rank could not build it") : why));
+      }
+      // the peers' staging buffers (CUDA IPC), where the reference posts its MPI messages
+      unsigned char mine[128];
+      checkC(mrl_slab_ipc_export(fv.slab, mine), "mrl_slab_ipc_export");
+      std::vector<unsigned char> all(sizeof mine * _domain.nRanks());
+      _domain.comm().allgather(mine, sizeof mine, all.data());
+      checkC(mrl_slab_ipc_import(fv.slab, all.data()), "mrl_slab_ipc_import");
+      _domain.comm().barrier();
+    } else if (mrl_split_plan_create(_domain.context(), &sd, &fv.plan) != MRL_OK) {
       const std::string why = mrl_last_error();
       mrl_expr_destroy(fv.expr);
       return fail("plan: " + why);
@@ -419,7 +454,12 @@ void AdamsBashforthMoulton::tryBuildFusedPlans() {
   _fusion_note.clear();
   // the plans keep the history of the nonlinear terms; follow the problem's advanceState
   _tensor_problem.addAdvanceStateHook([this]() {
-    for (auto &p : _plans) checkC(mrl_split_advance_state(p.plan, &p.stored), "mrl_split_advance_state");
+    for (auto &p : _plans) {
+      if (p.slab)
+        checkC(mrl_slab_advance_state(p.slab, &p.stored), "mrl_slab_advance_state");
+      else
+        checkC(mrl_split_advance_state(p.plan, &p.stored), "mrl_split_advance_state");
+    }
   });
 }
 
@@ -432,7 +472,7 @@ void AdamsBashforthMoulton::computeBuffer() {
   if (!_fusion_decided) decideFusion();
   const std::size_t tail = _tensor_problem.maxOldStates() + 1;
   const std::size_t P = _predictor_order;
-  if (!_allow_batching || !fused() || _variables.size() != 1 || _tensor_problem.timeStep() <= 1 || _substeps < tail + P + 4 * (P + 1) + 1)
+  if (!_allow_batching || !fused() || _plans[0].slab || _variables.size() != 1 || _tensor_problem.timeStep() <= 1 || _substeps < tail + P + 4 * (P + 1) + 1)
     return TensorSolver::computeBuffer();
   _sub_dt = _dt / _substeps;
   const bool dt_changed = (_dt != _dt_old);
@@ -473,6 +513,19 @@ void AdamsBashforthMoulton::fusedSubstep() {
       Tensor::swapBlocks(u, copy);
       u = copy;
     }
+  }
+  if (_plans[0].slab) {
+    // z r2c + x forward with the rows pushed into the owners' HBM | y pass + update, result rows pushed back | x inverse + z c2r
+    for (std::size_t k = 0; k < _variables.size(); ++k) checkC(mrl_slab_forward(_plans[k].slab, _variables[k]._buffer.data_ptr()), "mrl_slab_forward");
+    for (std::size_t k = 0; k < _variables.size(); ++k) checkC(mrl_slab_barrier(_plans[k].slab), "mrl_slab_barrier");
+    for (std::size_t k = 0; k < _variables.size(); ++k) {
+      const std::size_t n_old = (std::size_t)_plans[k].stored;
+      const auto order = std::min(_substep < _predictor_order && dt_changed ? std::size_t(0) : n_old, _predictor_order);
+      checkC(mrl_slab_update(_plans[k].slab, _sub_dt, AB_BETA[order], (int)order), "mrl_slab_update");
+    }
+    for (std::size_t k = 0; k < _variables.size(); ++k) checkC(mrl_slab_barrier(_plans[k].slab), "mrl_slab_barrier");
+    for (std::size_t k = 0; k < _variables.size(); ++k) checkC(mrl_slab_inverse(_plans[k].slab, _variables[k]._buffer.data_ptr()), "mrl_slab_inverse");
+    return;
   }
   for (std::size_t k = 0; k < _variables.size(); ++k) {
     checkC(mrl_split_set_time(_plans[k].plan, _sub_time), "mrl_split_set_time");

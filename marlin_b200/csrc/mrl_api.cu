@@ -1109,11 +1109,19 @@ extern "C" int mrl_slab_plan_create(mrl_context *ctx, const mrl_split_desc *d, v
                                     mrl_slab_plan **out) {
   if (!ctx || !d || !send_fwd || !recv_fwd || !send_bwd || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create: bad arguments");
   if (ctx->dim != 3 || !ctx->nyl) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_plan_create: slab domain not set");
-  if (d->nonlin_kind != MRL_NONLIN_DOUBLE_WELL) return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: built-in nonlinearity only");
+  if (ctx->pencil) return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: the domain is pencil-decomposed");
+  if (d->nonlin_kind != MRL_NONLIN_DOUBLE_WELL && d->nonlin_kind != MRL_NONLIN_EXPR) return mrl_fail(MRL_ERR_INVALID, "unknown nonlin_kind");
+  if (d->nonlin_kind == MRL_NONLIN_EXPR && !d->nonlin_expr) return mrl_fail(MRL_ERR_INVALID, "nonlin_expr is NULL");
   if (!d->M_closed_form || (d->has_L && !d->L_closed_form))
     return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: closed-form k-space factors only");
-  if (!tma_enabled() || !tma_size(ctx->n[0]) || !tma_size(ctx->n[1]) || !tma_size(ctx->n[2]) || ctx->nyl > 256)
+  // ctx->gn is the global grid (ctx->n[1] is the local extent on a context set up with mrl_domain_set_dist)
+  if (!tma_enabled() || !tma_size(ctx->gn[0]) || !tma_size(ctx->gn[1]) || !tma_size(ctx->gn[2]) || ctx->nyl > 256)
     return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: every axis must be 128, 256, 512 or 1024 points (ny/P <= 256)");
+  if (ctx->gn[0] != (long long)ctx->nxl * ctx->nranks || ctx->gn[1] != (long long)ctx->nyl * ctx->nranks)
+    return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: the fused exchange needs equal slabs (nx = %d, ny = %d over %d ranks)", ctx->gn[0], ctx->gn[1],
+                    ctx->nranks);
+  for (int r = 0; ctx->dist && r < ctx->nranks; ++r)
+    if (ctx->xcount[r] != ctx->nxl || ctx->ycount[r] != ctx->nyl) return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan: the fused exchange needs equal slabs");
   if (d->history < 0 || d->history > 4) return mrl_fail(MRL_ERR_INVALID, "history must be in [0,4]");
   CK(cudaSetDevice(ctx->device));
   mrl_slab_plan *p = new mrl_slab_plan();
@@ -1179,10 +1187,10 @@ extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc 
   const int ncp = slab_pitch(ctx);
   // the blocked staging layouts are cut into column blocks of the fused pass's tile width, the same for both axes
   const int wx = f64 ? fused_tma_tk<double>(ctx->n[0]) : fused_tma_tk<float>(ctx->n[0]);
-  const int wy = f64 ? fused_tma_tk<double>(ctx->n[1]) : fused_tma_tk<float>(ctx->n[1]);
+  const int wy = f64 ? fused_tma_tk<double>(ctx->gn[1]) : fused_tma_tk<float>(ctx->gn[1]);
   if (!wx || wx != wy || ncp % wx)
     return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan (peer mode): nx = %d and ny = %d need pipelined configurations of the same tile width", ctx->n[0],
-                    ctx->n[1]);
+                    ctx->gn[1]);
   if (ctx->nxl > 256) return mrl_fail(MRL_ERR_UNSUPPORTED, "slab plan (peer mode): nx/P <= 256");
   const int kb = ncp / wx;
   const size_t fbytes = (size_t)ctx->n[0] * ctx->nyl * ncp * esz;
@@ -1415,8 +1423,16 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
       const LaunchCtx lz{ctx->stream, i == 0 ? ctx->sm_count : ctx->sm_count - xc};
       const LaunchCtx lx{p->s_aux, i == C - 1 ? ctx->sm_count : xc};
       ctx->launches++;
-      CK(launch_zfwd_nonlin_tma<T>(lz, c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ych, nl, p->ncp, nlz,
-                                   (const cx<T> *)twl, RowMap{ych, nyl, i * ych}));
+      if (d.nonlin_kind == MRL_NONLIN_EXPR) {
+        const int rowmap[3] = {ych, nyl, i * ych};
+        ctx->launches--;  // counted by the launcher
+        if ((rc = mrl_expr_launch_zfwd_rows(ctx, d.nonlin_expr, d.nonlin_var, d.nonlin_inputs_dev, 0.0, c, d.g_out_real_dev, A, A + p->field,
+                                            (long long)ctx->n[0] * ych, nl, p->ncp, rowmap, lz.stream, lz.sm_count)))
+          return rc;
+      } else {
+        CK(launch_zfwd_nonlin_tma<T>(lz, c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ych, nl, p->ncp, nlz,
+                                     (const cx<T> *)twl, RowMap{ych, nyl, i * ych}));
+      }
       CK(cudaEventRecord(p->ev_chunk[i], ctx->stream));
       CK(cudaStreamWaitEvent(p->s_aux, p->ev_chunk[i], 0));
       if ((rc = slab_xfwd_peer<T>(p, i * ych, ych, lx))) return rc;
@@ -1425,9 +1441,15 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
     CK(cudaStreamWaitEvent(ctx->stream, p->ev_done, 0));
     return MRL_OK;
   }
-  ctx->launches++;
-  CK(launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ctx->nyl, nl, p->ncp, nlz,
-                               (const cx<T> *)twl));
+  if (d.nonlin_kind == MRL_NONLIN_EXPR) {
+    if ((rc = mrl_expr_launch_zfwd(ctx, d.nonlin_expr, d.nonlin_var, d.nonlin_inputs_dev, 0.0, c, d.g_out_real_dev, A, A + p->field,
+                                   (long long)ctx->n[0] * ctx->nyl, nl, p->ncp)))
+      return rc;
+  } else {
+    ctx->launches++;
+    CK(launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ctx->nyl, nl, p->ncp, nlz,
+                                 (const cx<T> *)twl));
+  }
   if (p->peer) return slab_xfwd_peer<T>(p, 0, nyl, ctx->lc());
   return slab_xpass<T>(p, 2, 0);
 }
@@ -1441,7 +1463,7 @@ template <class T> static int slab_update_impl(mrl_slab_plan *p, double dt, cons
   io.inC = S;
   io.inG = S + p->field;
   io.outU = (cx<T> *)p->send_bwd;
-  io.n = ctx->n[1];
+  io.n = ctx->gn[1];
   io.ncols = p->ncp;
   io.nouter = ctx->nxl;
   io.pitch = p->ncp;
@@ -1472,7 +1494,7 @@ template <class T> static int slab_update_impl(mrl_slab_plan *p, double dt, cons
   up.kmode = MRL_KMODE_3D_SLAB;
   up.nzc = p->ncp;
   up.nzv = ctx->nr[2];
-  up.x0 = ctx->x0;
+  up.x0 = ctx->dist ? 0 : ctx->x0;  // a decomposed context holds the local slice of the kx axis
   up.closed_M = 1;
   up.Mfac = (T)d.M_factor;
   up.has_L = d.has_L;
@@ -1525,7 +1547,7 @@ template <class T> static int slab_inverse_impl(mrl_slab_plan *p, T *c) {
   const int nl = ctx->n[2];
   const void *twl;
   if ((rc = ctx->twiddles(nl, &twl))) return rc;
-  const double N = (double)ctx->n[0] * ctx->n[1] * ctx->n[2];
+  const double N = (double)ctx->gn[0] * ctx->gn[1] * ctx->gn[2];
   ctx->launches++;
   CK(launch_zinv_pairs_tma<T>(ctx->lc(), (const cx<T> *)p->send_fwd, p->ncp, c, (long long)ctx->n[0] * ctx->nyl, nl, (T)(1.0 / N),
                               (const cx<T> *)twl));

@@ -154,7 +154,9 @@ static int build_zfwd(mrl_expr *e, int n, int staged_var, bool want_tma, bool pa
 
 template <class T>
 static int launch_typed(mrl_context *ctx, mrl_expr *e, const void *const *inputs, double t, const void *c, void *g_out, void *outC,
-                        void *outG, long long rows, int n, int ncp) {
+                        void *outG, long long rows, int n, int ncp, const int *rowmap, void *stream_or_null, int sm_count) {
+  cudaStream_t stream = stream_or_null ? (cudaStream_t)stream_or_null : ctx->stream;
+  if (sm_count <= 0) sm_count = ctx->sm_count;
   HostF<T> f;
   memset(&f, 0, sizeof f);
   for (size_t v = 0; v < e->pr.vars.size() && v < 16; ++v) f.in[v] = inputs ? inputs[v] : nullptr;
@@ -166,11 +168,13 @@ static int launch_typed(mrl_context *ctx, mrl_expr *e, const void *const *inputs
   if (e->zfwd_kind == ZK_TMA) {
     long long nrows = rows;
     const long long nwork = (rows + e->zfwd_ppb - 1) / e->zfwd_ppb;
-    const unsigned grid = (unsigned)(nwork < ctx->sm_count ? nwork : ctx->sm_count);
+    const unsigned grid = (unsigned)(nwork < sm_count ? nwork : sm_count);
     mrl::RowMap rm{0, 0, 0};
+    if (rowmap) rm = mrl::RowMap{rowmap[0], rowmap[1], rowmap[2]};
     void *params[] = {(void *)&c, &g_out, &outC, &outG, &nrows, &ncp, &f, (void *)&tw, &rm};
-    return mrlx_launch(e->zfwd_fn, grid, e->zfwd_block, e->zfwd_smem, ctx->stream, params);
+    return mrlx_launch(e->zfwd_fn, grid, e->zfwd_block, e->zfwd_smem, stream, params);
   }
+  if (rowmap && rowmap[0]) return mrl_fail(MRL_ERR_UNSUPPORTED, "row-mapped first pass needs the TMA kernel");
   if (ncp != n / 2 + 1) return mrl_fail(MRL_ERR_UNSUPPORTED, "padded work spectra need the TMA first pass");
   HostLoadFused<T> ld;
   memset(&ld, 0, sizeof ld);
@@ -185,15 +189,20 @@ static int launch_typed(mrl_context *ctx, mrl_expr *e, const void *const *inputs
   const unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
   if (e->zfwd_kind == ZK_FAST) {
     void *params[] = {&ld, &st, (void *)&tw, &npencils};
-    return mrlx_launch(e->zfwd_fn, grid, e->zfwd_block, e->zfwd_smem, ctx->stream, params);
+    return mrlx_launch(e->zfwd_fn, grid, e->zfwd_block, e->zfwd_smem, stream, params);
   }
   FFTPlanDev plan = make_fft_plan(n);
   void *params[] = {&ld, &st, (void *)&tw, &plan, &npencils};
-  return mrlx_launch(e->zfwd_fn, grid, e->zfwd_block, e->zfwd_smem, ctx->stream, params);
+  return mrlx_launch(e->zfwd_fn, grid, e->zfwd_block, e->zfwd_smem, stream, params);
 }
 
 int mrl_expr_launch_zfwd(mrl_context *ctx, void *expr, int staged_var, const void *const *inputs, double t, const void *c,
                          void *g_out, void *outC, void *outG, long long rows, int n, int ncp) {
+  return mrl_expr_launch_zfwd_rows(ctx, expr, staged_var, inputs, t, c, g_out, outC, outG, rows, n, ncp, nullptr, nullptr, 0);
+}
+
+int mrl_expr_launch_zfwd_rows(mrl_context *ctx, void *expr, int staged_var, const void *const *inputs, double t, const void *c, void *g_out,
+                              void *outC, void *outG, long long rows, int n, int ncp, const int *rowmap, void *stream, int sm_count) {
   mrl_expr *e = (mrl_expr *)expr;
   if (!e || e->ctx != ctx) return mrl_fail(MRL_ERR_INVALID, "expression belongs to another context");
   const bool padded = ncp != n / 2 + 1;
@@ -204,8 +213,8 @@ int mrl_expr_launch_zfwd(mrl_context *ctx, void *expr, int staged_var, const voi
     int rc = build_zfwd(e, n, staged_var, want_tma, padded);
     if (rc) return rc;
   }
-  return ctx->precision == MRL_F64 ? launch_typed<double>(ctx, e, inputs, t, c, g_out, outC, outG, rows, n, ncp)
-                                   : launch_typed<float>(ctx, e, inputs, t, c, g_out, outC, outG, rows, n, ncp);
+  return ctx->precision == MRL_F64 ? launch_typed<double>(ctx, e, inputs, t, c, g_out, outC, outG, rows, n, ncp, rowmap, stream, sm_count)
+                                   : launch_typed<float>(ctx, e, inputs, t, c, g_out, outC, outG, rows, n, ncp, rowmap, stream, sm_count);
 }
 
 // Dry run for the CPU test-suite: generate + compile the specialised pass without a device.

@@ -153,3 +153,7 @@ template <class T> cudaError_t launch_hermitian_rows(const LaunchCtx &lc, cx<T> 
 // expression-specialised first pass (mrl_expr_zfwd.cu); returns MRL status
 int mrl_expr_launch_zfwd(mrl_context *ctx, void *expr, int staged_var, const void *const *inputs, double t, const void *c,
                          void *g_out, void *outC, void *outG, long long rows, int n, int ncp);
+// the same on a y-chunk of a slab (rowmap = RowMap{ych, nyl, y0} of mrl_passes.cuh, NULL = all rows), on `stream` (NULL = the
+// context's) with a grid of at most sm_count CTAs (0 = all SMs)
+int mrl_expr_launch_zfwd_rows(mrl_context *ctx, void *expr, int staged_var, const void *const *inputs, double t, const void *c, void *g_out,
+                              void *outC, void *outG, long long rows, int n, int ncp, const int *rowmap, void *stream, int sm_count);
