@@ -534,6 +534,11 @@ cudaError_t launch_vec(const LaunchCtx &lc, int op, const T *a, const T *b, T *y
   }
   return e;
 }
+// finish a reduction whose partial sums another kernel left behind (the c2r pass with the fused inner product)
+template <class T> cudaError_t launch_vec_final(const LaunchCtx &lc, int fin, int slot, const double *partials, int nblk, double *scal) {
+  k_vec_final<<<1, 256, 0, lc.stream>>>(fin, slot, partials, nblk, scal);
+  return cudaGetLastError();
+}
 template <class T> cudaError_t launch_add_const9(const LaunchCtx &lc, int dim, T *y, const double *s, long long n) {
   if (dim == 3) {
     MD<T, 3> S;
@@ -554,6 +559,7 @@ template <class T> cudaError_t launch_components(const LaunchCtx &lc, const T *i
 #define INST(T)                                                                                                                   \
   template cudaError_t launch_mech_pointwise<T>(const LaunchCtx &, int, int, const T *, const T *, const T *, const T *, const double *, \
                                                 T *, long long, double, const T *, T *, const double *);                          \
+  template cudaError_t launch_vec_final<T>(const LaunchCtx &, int, int, const double *, int, double *);                            \
   template cudaError_t launch_mech_project<T>(const LaunchCtx &, int, cx<T> *, const T *, const T *, const T *, int, int, int, int); \
   template cudaError_t launch_vec<T>(const LaunchCtx &, int, const T *, const T *, T *, T *, double *, double, long long, int, int, \
                                      double *, int);                                                                              \

@@ -430,7 +430,8 @@ cudaError_t launch_zfwd_pairs_tma(const LaunchCtx &lc, const T *in, cx<T> *out, 
 }
 
 template <class T, class C, int PPB, int NG, int NS>
-static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw) {
+static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw,
+                               const ZinvDot<T> *dot) {
   constexpr int NP = C::N + (C::N >> 3) + 1;
   constexpr int NC = (C::N / 2 + 1 + 15) & ~15;  // slot rows sized for the largest padded pitch
   if (ncp > NC || ncp < C::N / 2 + 1) return cudaErrorNotSupported;
@@ -438,42 +439,51 @@ static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, int ncp, T 
   static_assert(smem <= kSmemBudget, "zinv_tma: shared memory budget");
   static_assert(NG * PPB * C::TP <= 1024 && NG <= 15, "zinv_tma: block size");
   if (((unsigned long long)in & 15ull) || (ncp * sizeof(cx<T>)) % 16) return cudaErrorNotSupported;
-  auto k = k_zinv_tma<T, C, PPB, NG, NS>;
-  int per_sm = 0;
-  cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
-  if (e != cudaSuccess) return e;
   const long long npencils = (nrows + 1) / 2;
   const long long nwork = ((npencils + PPB - 1) / PPB + NG - 1) / NG;
   const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
-  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(in, ncp, out, nrows, scale, tw);
+  int per_sm = 0;
+  if (dot && dot->with) {
+    if (grid > dot->capacity) return cudaErrorInvalidValue;
+    auto k = k_zinv_tma<T, C, PPB, NG, NS, true>;
+    cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
+    if (e != cudaSuccess) return e;
+    k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(in, ncp, out, nrows, scale, tw, dot->with, dot->partials);
+    *dot->count = grid;
+    return cudaGetLastError();
+  }
+  auto k = k_zinv_tma<T, C, PPB, NG, NS, false>;
+  cudaError_t e = kernel_prep((const void *)k, NG * PPB * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  k<<<grid, NG * PPB * C::TP, smem, lc.stream>>>(in, ncp, out, nrows, scale, tw, nullptr, nullptr);
   return cudaGetLastError();
 }
 
 template <class T>
 cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, int n, T scale,
-                                  const cx<T> *tw) {
+                                  const cx<T> *tw, const ZinvDot<T> *dot) {
   if (!tma_enabled()) return cudaErrorNotSupported;
   static int variant = env_int("MRL_ZINV_V", 0);
   if constexpr (sizeof(T) == 8) {
     switch (n) {
-      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 3, 2>(lc, in, ncp, out, nrows, scale, tw);
-      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 2>(lc, in, ncp, out, nrows, scale, tw);
+      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 3, 2>(lc, in, ncp, out, nrows, scale, tw, dot);
+      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 2>(lc, in, ncp, out, nrows, scale, tw, dot);
       case 512:
         switch (variant) {  // measured (profiles/r1z_variants.txt): 4 pencils x 2 groups 0.337 ms, 2 x 4: 0.379 ms
-          case 1: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 2>(lc, in, ncp, out, nrows, scale, tw);
-          case 2: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 2>(lc, in, ncp, out, nrows, scale, tw);
-          case 3: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 3, 3>(lc, in, ncp, out, nrows, scale, tw);
-          default: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 2>(lc, in, ncp, out, nrows, scale, tw);
+          case 1: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 2>(lc, in, ncp, out, nrows, scale, tw, dot);
+          case 2: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 1, 8, 2>(lc, in, ncp, out, nrows, scale, tw, dot);
+          case 3: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 3, 3>(lc, in, ncp, out, nrows, scale, tw, dot);
+          default: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 4, 2, 2>(lc, in, ncp, out, nrows, scale, tw, dot);
         }
-      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 2>(lc, in, ncp, out, nrows, scale, tw);
+      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 2>(lc, in, ncp, out, nrows, scale, tw, dot);
       default: return cudaErrorNotSupported;
     }
   } else {
     switch (n) {
-      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
-      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
-      case 512: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
-      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3>(lc, in, ncp, out, nrows, scale, tw);
+      case 128: return zinv_tma_go<T, FFTCfg<128, 16, 8, 4, 4>, 8, 4, 3>(lc, in, ncp, out, nrows, scale, tw, dot);
+      case 256: return zinv_tma_go<T, FFTCfg<256, 32, 8, 8, 4>, 4, 4, 3>(lc, in, ncp, out, nrows, scale, tw, dot);
+      case 512: return zinv_tma_go<T, FFTCfg<512, 64, 8, 8, 8>, 2, 4, 3>(lc, in, ncp, out, nrows, scale, tw, dot);
+      case 1024: return zinv_tma_go<T, FFTCfg<1024, 128, 8, 8, 4, 4>, 1, 4, 3>(lc, in, ncp, out, nrows, scale, tw, dot);
       default: return cudaErrorNotSupported;
     }
   }
@@ -588,7 +598,8 @@ template <class T> int fused_tma_tk(int n) {
   template cudaError_t launch_slab_xfwd<T>(const LaunchCtx &, const cx<T> *, const SlabXIO<T> &, const cx<T> *, int);        \
   template cudaError_t launch_slab_xinv<T>(const LaunchCtx &, const cx<T> *, const SlabXIO<T> &, const cx<T> *, int);         \
   template int fused_tma_tk<T>(int);                                                                                       \
-  template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, int, T *, long long, int, T, const cx<T> *);
+  template cudaError_t launch_zinv_pairs_tma<T>(const LaunchCtx &, const cx<T> *, int, T *, long long, int, T, const cx<T> *, \
+                                                const ZinvDot<T> *);
 INST(double)
 INST(float)
 

@@ -433,9 +433,10 @@ template <class T> static int strided_axis(mrl_context *ctx, const cx<T> *in, cx
 
 template <class T>
 static cudaError_t zinv_dispatch(mrl_context *ctx, const cx<T> *in, T *out, long long rows, int n, T scale, const cx<T> *tw,
-                                 int ncp = 0) {
+                                 int ncp = 0, const ZinvDot<T> *dot = nullptr) {
   if (!ncp) ncp = n / 2 + 1;
-  cudaError_t e = launch_zinv_pairs_tma<T>(ctx->lc(), in, ncp, out, rows, n, scale, tw);
+  if (dot) *dot->count = 0;  // stays 0 when the pass that runs cannot carry the inner product
+  cudaError_t e = launch_zinv_pairs_tma<T>(ctx->lc(), in, ncp, out, rows, n, scale, tw, dot);
   if (e == cudaErrorNotSupported && ncp == n / 2 + 1) e = launch_zinv_pairs<T>(ctx->lc(), in, out, rows, n, scale, tw, make_fft_plan(n));
   return e;
 }
@@ -463,7 +464,8 @@ template <class T> static int rfftn_impl(mrl_context *ctx, const T *in, cx<T> *o
 // src == nullptr: transform `work` in place (it is destroyed); otherwise src is preserved and
 // `work` receives the partially transformed spectra
 template <class T>
-static int irfftn_impl2(mrl_context *ctx, const cx<T> *src, cx<T> *work, T *out, int batch, int ncp, double scale, int start_axis = 0) {
+static int irfftn_impl2(mrl_context *ctx, const cx<T> *src, cx<T> *work, T *out, int batch, int ncp, double scale, int start_axis = 0,
+                        const ZinvDot<T> *dot = nullptr) {
   const int dim = ctx->dim, nl = ctx->n[dim - 1];
   long long rows = batch;
   for (int d = 0; d < dim - 1; ++d) rows *= ctx->n[d];
@@ -475,7 +477,7 @@ static int irfftn_impl2(mrl_context *ctx, const cx<T> *src, cx<T> *work, T *out,
   }
   const void *tw;
   if ((rc = ctx->twiddles(nl, &tw))) return rc;
-  CKL(ctx, zinv_dispatch<T>(ctx, cur, out, rows, nl, (T)scale, (const cx<T> *)tw, ncp));
+  CKL(ctx, zinv_dispatch<T>(ctx, cur, out, rows, nl, (T)scale, (const cx<T> *)tw, ncp, dot));
   return MRL_OK;
 }
 
@@ -563,10 +565,15 @@ int mrl_fftb_strided(mrl_context *ctx, void *spec, int batch, int ncp, int axis,
              ? strided_axis<double>(ctx, (const cx<double> *)spec, (cx<double> *)spec, 1, 0, axis, batch, inverse, ncp)
              : strided_axis<float>(ctx, (const cx<float> *)spec, (cx<float> *)spec, 1, 0, axis, batch, inverse, ncp);
 }
-int mrl_fftb_inverse(mrl_context *ctx, void *work, void *out, int batch, int ncp, double scale, int first_axis) {
-  return ctx->precision == MRL_F64
-             ? irfftn_impl2<double>(ctx, nullptr, (cx<double> *)work, (double *)out, batch, ncp, scale, first_axis)
-             : irfftn_impl2<float>(ctx, nullptr, (cx<float> *)work, (float *)out, batch, ncp, scale, first_axis);
+int mrl_fftb_inverse(mrl_context *ctx, void *work, void *out, int batch, int ncp, double scale, int first_axis, const void *dot_with,
+                     double *dot_partials, int dot_capacity, int *dot_count) {
+  if (dot_count) *dot_count = 0;
+  if (ctx->precision == MRL_F64) {
+    const ZinvDot<double> dot{(const double *)dot_with, dot_partials, dot_capacity, dot_count};
+    return irfftn_impl2<double>(ctx, nullptr, (cx<double> *)work, (double *)out, batch, ncp, scale, first_axis, dot_with ? &dot : nullptr);
+  }
+  const ZinvDot<float> dot{(const float *)dot_with, dot_partials, dot_capacity, dot_count};
+  return irfftn_impl2<float>(ctx, nullptr, (cx<float> *)work, (float *)out, batch, ncp, scale, first_axis, dot_with ? &dot : nullptr);
 }
 
 extern "C" int mrl_rfftn(mrl_context *ctx, const void *in, void *out, int batch) {

@@ -129,7 +129,10 @@ int mrl_fftb_pitch(const mrl_context *ctx);
 // first_axis > 0: the strided axes below it are skipped (left to a fused pass of the caller).
 int mrl_fftb_forward(mrl_context *ctx, const void *in_real, void *out_cplx, int batch, int ncp, int first_axis = 0);
 int mrl_fftb_strided(mrl_context *ctx, void *spec_cplx, int batch, int ncp, int axis, int inverse);  // one complex pass, in place
-int mrl_fftb_inverse(mrl_context *ctx, void *work_cplx, void *out_real, int batch, int ncp, double scale, int first_axis = 0);
+// dot_with != nullptr: sum(out * dot_with) rides in the store of the last pass where that pass can carry it; *dot_count
+// partial sums land in dot_partials (capacity entries), *dot_count == 0 means the caller has to compute it itself
+int mrl_fftb_inverse(mrl_context *ctx, void *work_cplx, void *out_real, int batch, int ncp, double scale, int first_axis = 0,
+                     const void *dot_with = nullptr, double *dot_partials = nullptr, int dot_capacity = 0, int *dot_count = nullptr);
 
 namespace mrl {
 FFTPlanDev make_fft_plan(int n);

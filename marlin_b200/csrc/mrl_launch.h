@@ -75,9 +75,17 @@ cudaError_t launch_fused_tma(const LaunchCtx &lc, const FusedIO<T> &io, const Sp
 template <class T>
 cudaError_t launch_zfwd_nonlin_tma(const LaunchCtx &lc, const T *c, T *mu_out, cx<T> *outC, cx<T> *outG, long long nrows, int n,
                                    int ncp, const NonlinDesc &nl, const cx<T> *tw, const RowMap &rm = RowMap{0, 0, 0});
+// optional inner product fused into the store of the last-axis c2r pass: sum(result * with) as one partial per CTA
+// (partials[0 .. *count), capacity entries available); with == nullptr: none
+template <class T> struct ZinvDot {
+  const T *with;
+  double *partials;
+  int capacity;
+  int *count;
+};
 template <class T>
 cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, int n, T scale,
-                                  const cx<T> *tw);
+                                  const cx<T> *tw, const ZinvDot<T> *dot = nullptr);
 template <class T>
 cudaError_t launch_zfwd_pairs_tma(const LaunchCtx &lc, const T *in, cx<T> *out, long long nrows, int n, int ncp, const cx<T> *tw);
 template <class T>

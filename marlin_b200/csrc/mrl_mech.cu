@@ -18,6 +18,7 @@ enum { FIN_STORE = 0, FIN_ALPHA = 1, FIN_RES = 2 };
 template <class T>
 cudaError_t launch_mech_pointwise(const LaunchCtx &lc, int dim, int mode, const T *F, const T *K, const T *mu, const T *x, const double *xc,
                                   T *out, long long n, double scale, const T *r = nullptr, T *xw = nullptr, const double *scal = nullptr);
+template <class T> cudaError_t launch_vec_final(const LaunchCtx &lc, int fin, int slot, const double *partials, int nblk, double *scal);
 template <class T>
 cudaError_t launch_mech_project(const LaunchCtx &lc, int dim, cx<T> *A, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzc, int ncp);
 template <class T>
@@ -51,7 +52,10 @@ struct mrl_mech_plan {
   double *scal = nullptr, *partials = nullptr, *host = nullptr;
   int nblk = 0;
   bool fused_x = true;  // x pass fused with the Green projection (sizes with a TMA configuration)
+  int dot_count = 0;    // partial sums the last inverse pass left in `partials` (0: the inner product was not fused)
 };
+
+template <class T> static int project_G_passes(mrl_mech_plan *p, const T *A, T *out, double sign, const T *dot_with);
 
 extern "C" int mrl_mech_plan_destroy(mrl_mech_plan *p) {
   if (!p) return MRL_OK;
@@ -99,9 +103,25 @@ extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, co
 }
 
 // ---------------------------------------------------------------------------- operators
-template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, double sign) {
+template <class T> static int vec(mrl_mech_plan *p, int op, const T *a, const T *b, T *y, T *z, double s, int fin = FIN_STORE, int slot = SC_TMP);
+
+// dot_with != nullptr: alpha = rz / (dot_with . out) follows (FIN_ALPHA), with the inner product riding in the store of
+// the last inverse pass where that pass can carry it
+template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, double sign, const T *dot_with = nullptr) {
+  int rc = project_G_passes<T>(p, A, out, sign, dot_with);
+  if (rc || !dot_with) return rc;
+  if (p->dot_count > 0) {
+    p->ctx->launches++;
+    CK(launch_vec_final<T>(p->ctx->lc(), FIN_ALPHA, SC_TMP, p->partials, p->dot_count, p->scal));
+    return MRL_OK;
+  }
+  return vec<T>(p, VOP_DOT, dot_with, out, nullptr, nullptr, 0, FIN_ALPHA, SC_TMP);
+}
+
+template <class T> static int project_G_passes(mrl_mech_plan *p, const T *A, T *out, double sign, const T *dot_with) {
   // out = sign * irfftn( Ghat4 : rfftn(A) ), FFTMechanics.C:104-105
   mrl_context *ctx = p->ctx;
+  p->dot_count = 0;
   const int nc = p->nc;
   const T *kx = (const T *)ctx->kaxis_dev[0], *ky = (const T *)ctx->kaxis_dev[1], *kz = (const T *)ctx->kaxis_dev[2];
   // 2-D: the half-spectrum axis is y; the projection kernel sees [nc][n0][1][ncp] with q = (kx, ky)
@@ -117,7 +137,7 @@ template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, do
                                              (const cx<T> *)tw);
     if (e == cudaSuccess) {
       ctx->launches++;
-      return mrl_fftb_inverse(ctx, p->spec, out, nc, p->ncp, sign / (double)p->n, 1);
+      return mrl_fftb_inverse(ctx, p->spec, out, nc, p->ncp, sign / (double)p->n, 1, dot_with, p->partials, p->nblk, &p->dot_count);
     }
     if (e != cudaErrorNotSupported) CK(e);
     p->fused_x = false;  // no pipelined configuration for this size: finish with the separate passes
@@ -127,21 +147,23 @@ template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, do
   }
   ctx->launches++;
   CK(launch_mech_project<T>(ctx->lc(), p->dim, (cx<T> *)p->spec, kx, ky, klast, ctx->n[0], n1, nlast, p->ncp));
-  return mrl_fftb_inverse(ctx, p->spec, out, nc, p->ncp, sign / (double)p->n);
+  return mrl_fftb_inverse(ctx, p->spec, out, nc, p->ncp, sign / (double)p->n, 0, dot_with, p->partials, p->nblk, &p->dot_count);
 }
 
-// r_update != nullptr: x is the CG direction, first replaced by r_update + beta x (beta on the device)
+// r_update != nullptr: x is the CG direction, first replaced by r_update + beta x (beta on the device).
+// cg_dot: alpha = rz / (x . out) follows.
 template <class T>
-static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xconst, T *out, double sign, const T *r_update = nullptr) {
+static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xconst, T *out, double sign, const T *r_update = nullptr,
+                    bool cg_dot = false) {
   // out = sign * G( K4(F) : x ), FFTMechanics.C:107-112
   mrl_context *ctx = p->ctx;
   ctx->launches++;
   CK(launch_mech_pointwise<T>(ctx->lc(), p->dim, r_update ? 3 : xconst ? 2 : 1, F, (const T *)p->K, (const T *)p->mu, x, xconst, (T *)p->tmp, p->n,
                               1.0, r_update, const_cast<T *>(x), p->scal));
-  return project_G<T>(p, (const T *)p->tmp, out, sign);
+  return project_G<T>(p, (const T *)p->tmp, out, sign, cg_dot ? x : nullptr);
 }
 
-template <class T> static int vec(mrl_mech_plan *p, int op, const T *a, const T *b, T *y, T *z, double s, int fin = FIN_STORE, int slot = SC_TMP) {
+template <class T> static int vec(mrl_mech_plan *p, int op, const T *a, const T *b, T *y, T *z, double s, int fin, int slot) {
   p->ctx->launches++;
   CK(launch_vec<T>(p->ctx->lc(), op, a, b, y, z, p->scal, s, p->nc * p->n, fin, slot, p->partials, p->nblk));
   return MRL_OK;
@@ -176,10 +198,10 @@ template <class T> static int cg_solve(mrl_mech_plan *p, bool x_zero, int *itera
   if ((rc = vec<T>(p, VOP_DOT, r, r, nullptr, nullptr, 0, FIN_STORE, SC_RZ))) return rc;
   const long long maxit = p->desc.l_max_its;
   for (long long k = 0; k < maxit; ++k) {
-    // p = r + beta p of the previous iteration rides in the load of the tangent kernel
-    if ((rc = apply_GK<T>(p, Fk, pp, nullptr, Ap, 1.0, k > 0 ? r : nullptr))) return rc;
-    if ((rc = vec<T>(p, VOP_DOT, pp, Ap, nullptr, nullptr, 0, FIN_ALPHA))) return rc;  // alpha = rz / p.Ap
-    if ((rc = vec<T>(p, VOP_CG_XR, pp, Ap, x, r, 0, FIN_RES))) return rc;              // x, r, |r|^2, beta
+    // p = r + beta p of the previous iteration rides in the load of the tangent kernel; p.Ap -> alpha rides in the store of
+    // the last inverse pass (no separate pass over p and Ap)
+    if ((rc = apply_GK<T>(p, Fk, pp, nullptr, Ap, 1.0, k > 0 ? r : nullptr, true))) return rc;
+    if ((rc = vec<T>(p, VOP_CG_XR, pp, Ap, x, r, 0, FIN_RES))) return rc;  // x, r, |r|^2, beta
     double res2;
     if ((rc = read_scalar(p, SC_RES2, &res2))) return rc;
     *iterations = (int)(k + 1);

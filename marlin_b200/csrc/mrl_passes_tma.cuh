@@ -701,6 +701,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
 
   const GroupBarrier bar{1 + g, GT};
   const SmPencil<T> sm{xbuf + (size_t)(g * PPB + pl) * NP};
+  [[maybe_unused]] double dacc = 0.0;
   for (int j = 0; j < nloc; ++j) {
     const int s = j % NS;
     const long long p = (first + j * stride) * PPB + pl;
@@ -743,9 +744,11 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
 
 // ======================================================================== P5: z c2r of row pairs
 // A tile is PPB pencils = 2*PPB consecutive half-spectrum rows (one contiguous bulk copy).
-template <class T, class C, int PPB, int NG, int NS>
+// DOT: the inner product of the result with `dotv` (same layout as `out`) rides in the store epilogue; every CTA leaves
+// its partial sum in partials[blockIdx.x] (mechanics: p.Ap of the CG iteration without re-reading Ap).
+template <class T, class C, int PPB, int NG, int NS, bool DOT = false>
 __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
-    k_zinv_tma(const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw_g) {
+    k_zinv_tma(const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw_g, const T *dotv, double *partials) {
   constexpr int N = C::N, TP = C::TP, E = C::E, GT = PPB * TP;
   constexpr int NP = N + (N >> 3) + 1;
   constexpr int NCMAX = (N / 2 + 1 + 15) & ~15;  // largest padded row pitch (ncp <= NCMAX)
@@ -788,6 +791,7 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
 
   const GroupBarrier bar{1 + g, GT};
   const SmPencil<T> sm{xbuf + (size_t)(g * PPB + pl) * NP};
+  [[maybe_unused]] double dacc = 0.0;
   for (int j = 0; j < nloc; ++j) {
     const int s = j % NS;
     const long long p = (first + j * stride) * PPB + pl;
@@ -812,9 +816,28 @@ __global__ void __launch_bounds__(NG *PPB *C::TP, 1)
       MRL_UNROLL
       for (int e = 0; e < E; ++e) {
         const int jj = t + TP * e;
-        out[r0 * N + jj] = v[e].x * scale;
-        if (ok2) out[(r0 + 1) * N + jj] = -v[e].y * scale;
+        const T o0 = v[e].x * scale;
+        out[r0 * N + jj] = o0;
+        if (DOT) dacc += (double)o0 * (double)dotv[r0 * N + jj];
+        if (ok2) {
+          const T o1 = -v[e].y * scale;
+          out[(r0 + 1) * N + jj] = o1;
+          if (DOT) dacc += (double)o1 * (double)dotv[(r0 + 1) * N + jj];
+        }
       }
+    }
+  }
+  if (DOT) {
+    // fixed-order reduction: lanes (butterfly), then the warps in index order
+    __shared__ double red[32];
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int o = 16; o > 0; o >>= 1) dacc += __shfl_sync(0xffffffffu, dacc, lane ^ o);
+    if (lane == 0) red[warp] = dacc;
+    __syncthreads();
+    if (tid == 0) {
+      double r = 0.0;
+      for (int w = 0; w < (NG * PPB * TP + 31) / 32; ++w) r += red[w];
+      partials[blockIdx.x] = r;
     }
   }
 }

@@ -332,11 +332,25 @@ template <class C, int PPB, int NG, int NS> static void test_zinv_tma(const char
   size_t smem = (size_t)(NG * NS * 2 * PPB * ncmax + NG * PPB * NP) * 16 + NG * NS * 8 + 128;
   const cx<double> *sp = spec.data(), *twp = tw.data();
   double *bp = back.data();
-  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem, [=] { k_zinv_tma<double, C, PPB, NG, NS>(sp, ncp, bp, nrows, 1.0 / n, twp); },
+  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem, [=] { k_zinv_tma<double, C, PPB, NG, NS>(sp, ncp, bp, nrows, 1.0 / n, twp, nullptr, nullptr); },
               64 * 1024);
   double err = 0;
   for (size_t i = 0; i < a.size(); ++i) err = std::max(err, std::fabs(a[i] - back[i]));
   report(name, err, 1e-12 * n);
+  // the same pass with the inner product sum(result * w) fused into the store (mechanics: p.Ap)
+  std::vector<double> w(a.size()), back2(a.size()), partials(grid, 0.0);
+  for (auto &v : w) v = U(rng);
+  const double *wp = w.data();
+  double *b2 = back2.data(), *pp = partials.data();
+  emu::launch(dim3(grid), dim3(NG * PPB * C::TP), smem, [=] { k_zinv_tma<double, C, PPB, NG, NS, true>(sp, ncp, b2, nrows, 1.0 / n, twp, wp, pp); },
+              64 * 1024);
+  double want = 0, got = 0, e2 = 0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    want += back[i] * w[i];
+    e2 = std::max(e2, std::fabs(back[i] - back2[i]));
+  }
+  for (double v : partials) got += v;
+  report((std::string(name) + " + dot").c_str(), std::max(e2, std::fabs(want - got)), 1e-12 * n);
 }
 
 // fused pass in the multi-GPU slab layout: data staged as [P][nxl][nyl][nzc], transform along y

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One parameterised GPU session (replaces the per-session scripts of round 1).  Run under gpurun:
 #   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh TAG step [step ...]'
-# steps: tests[:pytest-args]  smoke  bench  bench:N(torchrun N ranks)  launches  ncu:<kernel-regex>  traffic  mech  passes
+# steps: tests[:pytest-args]  testsel:"paths"  smoke  bench  bench:N(torchrun N ranks)  launches  ncu:<kernel-regex>  traffic  mech  passes
 # Everything lands in gpurun_out/<TAG>_*.
 TAG=$1; shift
 O=gpurun_out; mkdir -p $O
@@ -10,6 +10,7 @@ for step in "$@"; do
   kind=${step%%:*}; arg=""; [[ "$step" == *:* ]] && arg=${step#*:}
   case $kind in
     tests)    timeout 1700 python -m pytest tests -m gpu -q --timeout 900 -x $arg 2>&1 | tail -40 > $O/${TAG}_pytest.log; tail -15 $O/${TAG}_pytest.log ;;
+    testsel)  timeout 1700 python -m pytest $arg -m gpu -q --timeout 900 2>&1 | tail -60 > $O/${TAG}_pytest.log; tail -25 $O/${TAG}_pytest.log ;;
     testsall) timeout 1700 python -m pytest tests -m gpu -q --timeout 900 $arg 2>&1 | tail -60 > $O/${TAG}_pytest.log; tail -25 $O/${TAG}_pytest.log ;;
     smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -3 $O/${TAG}_smoke.log ;;
     bench)    if [ -z "$arg" ] || [ "$arg" == 1 ]; then
