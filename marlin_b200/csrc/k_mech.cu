@@ -16,6 +16,7 @@
 // literal 1/3 of the deviatoric split stays 1/3 in 2-D, HyperElasticIsotropic.C:45).
 #include "k_common.cuh"
 #include "mrl_internal.h"
+#include "mrl_mech_point.cuh"
 
 namespace mrl {
 
@@ -23,77 +24,6 @@ static inline int ew_grid_fwd(long long total, const LaunchCtx &lc) {
   long long g = (total + 255) / 256;
   const long long cap = (long long)lc.sm_count * 8;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
-}
-
-template <class T, int D> struct MD {
-  T a[D][D];
-};
-
-template <class T, int D> __device__ __forceinline__ void second_pk(const MD<T, D> &F, T K, T mu, MD<T, D> &S) {
-  T E[D][D];
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-      T s = T(0);
-#pragma unroll
-      for (int k = 0; k < D; ++k) s += F.a[k][i] * F.a[k][j];
-      E[i][j] = T(0.5) * (s - (i == j ? T(1) : T(0)));
-    }
-  T tr = T(0);
-#pragma unroll
-  for (int i = 0; i < D; ++i) tr += E[i][i];
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int j = 0; j < D; ++j) S.a[i][j] = T(2) * mu * E[i][j] + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
-}
-
-// mode 0: R = P = F S.   mode 1-3: R = K4 : X.
-template <class T, int D> __device__ __forceinline__ void mech_point(int mode, const MD<T, D> &Fm, T K, T mu, const MD<T, D> &X, MD<T, D> &R) {
-  MD<T, D> S;
-  second_pk(Fm, K, mu, S);
-  if (mode == 0) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        T s = T(0);
-#pragma unroll
-        for (int k = 0; k < D; ++k) s += Fm.a[i][k] * S.a[k][j];
-        R.a[i][j] = s;
-      }
-  } else {
-    T W[D][D];
-#pragma unroll
-    for (int p = 0; p < D; ++p)
-#pragma unroll
-      for (int l = 0; l < D; ++l) {
-        T s = T(0);
-#pragma unroll
-        for (int k = 0; k < D; ++k) s += Fm.a[k][p] * X.a[k][l];
-        W[p][l] = s;
-      }
-    T tr = T(0);
-#pragma unroll
-    for (int i = 0; i < D; ++i) tr += W[i][i];
-    T Tm[D][D];
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int j = 0; j < D; ++j) Tm[i][j] = mu * (W[i][j] + W[j][i]) + (i == j ? (K - T(2) * mu / T(3)) * tr : T(0));
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        T s = T(0);
-#pragma unroll
-        for (int k = 0; k < D; ++k) s += X.a[i][k] * S.a[k][j];
-#pragma unroll
-        for (int k = 0; k < D; ++k) s += Fm.a[i][k] * Tm[k][j];
-        R.a[i][j] = s;
-      }
-  }
 }
 
 template <class T, int W> struct VecW {};

@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "k_common.cuh"
+#include "mrl_mech_tma.cuh"
 #include "mrl_passes_slab.cuh"
 
 namespace mrl {
@@ -429,6 +430,30 @@ cudaError_t launch_zfwd_pairs_tma(const LaunchCtx &lc, const T *in, cx<T> *out, 
   }
 }
 
+template <class T, class C, int NG> static cudaError_t mech_tangent_go(const LaunchCtx &lc, const MechTangentIO<T> &io, const cx<T> *tw) {
+  constexpr int NP = C::N + (C::N >> 3) + 1;
+  constexpr size_t smem = (size_t)NG * 9 * 2 * C::N * sizeof(T) + (size_t)(NG * 9 * NP) * sizeof(cx<T>) + 128;
+  static_assert(smem <= kSmemBudget, "mech_tangent_zfwd: shared memory budget");
+  static_assert(NG * 9 * C::TP <= 1024 && NG <= 15, "mech_tangent_zfwd: block size");
+  if (io.nrows % 2 || io.n != io.nrows * C::N) return cudaErrorNotSupported;
+  auto k = k_mech_tangent_zfwd<T, C, NG>;
+  int per_sm = 0;
+  cudaError_t e = kernel_prep((const void *)k, NG * 9 * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long nwork = (io.nrows / 2 + NG - 1) / NG;
+  const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
+  k<<<grid, NG * 9 * C::TP, smem, lc.stream>>>(io, tw);
+  return cudaGetLastError();
+}
+template <class T> cudaError_t launch_mech_tangent_zfwd(const LaunchCtx &lc, const MechTangentIO<T> &io, const cx<T> *tw, int n) {
+  if (!tma_enabled() || env_int("MRL_MECH_TANGENT_FUSED", 1) == 0) return cudaErrorNotSupported;
+  switch (n) {
+    case 256: return mech_tangent_go<T, FFTCfg<256, 32, 8, 8, 4>, 2>(lc, io, tw);
+    case 512: return mech_tangent_go<T, FFTCfg<512, 64, 8, 8, 8>, 1>(lc, io, tw);
+    default: return cudaErrorNotSupported;
+  }
+}
+
 template <class T, class C, int PPB, int NG, int NS>
 static cudaError_t zinv_tma_go(const LaunchCtx &lc, const cx<T> *in, int ncp, T *out, long long nrows, T scale, const cx<T> *tw,
                                const ZinvDot<T> *dot) {
@@ -590,6 +615,7 @@ template <class T> int fused_tma_tk(int n) {
   template cudaError_t launch_mech_fused_tma<T>(const LaunchCtx &, cx<T> *, const T *, const T *, const T *, int, int, int, int, \
                                                 const cx<T> *);                                                          \
   template cudaError_t launch_strided_tma<T>(const LaunchCtx &, const StridedIO<T> &, const cx<T> *, int);               \
+  template cudaError_t launch_mech_tangent_zfwd<T>(const LaunchCtx &, const MechTangentIO<T> &, const cx<T> *, int);     \
   template cudaError_t launch_fused_tma<T>(const LaunchCtx &, const FusedIO<T> &, const SpectralUpdate<T> &, const cx<T> *, \
                                            int);                                                                         \
   template cudaError_t launch_zfwd_nonlin_tma<T>(const LaunchCtx &, const T *, T *, cx<T> *, cx<T> *, long long, int,    \

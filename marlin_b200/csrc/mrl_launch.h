@@ -88,6 +88,8 @@ cudaError_t launch_zinv_pairs_tma(const LaunchCtx &lc, const cx<T> *in, int ncp,
                                   const cx<T> *tw, const ZinvDot<T> *dot = nullptr);
 template <class T>
 cudaError_t launch_zfwd_pairs_tma(const LaunchCtx &lc, const T *in, cx<T> *out, long long nrows, int n, int ncp, const cx<T> *tw);
+// first pass of G(K4 : p) with the tangent (and the CG direction update) fused into its load; 3-D, n = 256 or 512
+template <class T> cudaError_t launch_mech_tangent_zfwd(const LaunchCtx &lc, const MechTangentIO<T> &io, const cx<T> *tw, int n);
 template <class T>
 cudaError_t launch_mech_fused_tma(const LaunchCtx &lc, cx<T> *spec, const T *kx, const T *ky, const T *kz, int n0, int n1, int nzv,
                                   int ncp, const cx<T> *tw);

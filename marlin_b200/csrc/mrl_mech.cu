@@ -52,6 +52,7 @@ struct mrl_mech_plan {
   double *scal = nullptr, *partials = nullptr, *host = nullptr;
   int nblk = 0;
   bool fused_x = true;  // x pass fused with the Green projection (sizes with a TMA configuration)
+  bool fused_tangent = true;  // tangent fused into the first FFT pass (3-D, last axis 256 or 512, x pass fused)
   int dot_count = 0;    // partial sums the last inverse pass left in `partials` (0: the inner product was not fused)
 };
 
@@ -81,6 +82,7 @@ extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, co
   p->dim = ctx->dim;
   p->nc = ctx->dim * ctx->dim;
   p->fused_x = ctx->dim == 3;
+  p->fused_tangent = ctx->dim == 3;
   if (p->desc.l_max_its <= 0) p->desc.l_max_its = p->n;  // FFTMechanics.C:63-64: default = number of cells
   p->ncp = mrl_fftb_pitch(ctx);
   const size_t esz = ctx->precision == MRL_F64 ? 8 : 4;
@@ -113,6 +115,26 @@ template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, do
   if (p->dot_count > 0) {
     p->ctx->launches++;
     CK(launch_vec_final<T>(p->ctx->lc(), FIN_ALPHA, SC_TMP, p->partials, p->dot_count, p->scal));
+    return MRL_OK;
+  }
+  return vec<T>(p, VOP_DOT, dot_with, out, nullptr, nullptr, 0, FIN_ALPHA, SC_TMP);
+}
+
+// the part of project_G after the z and y forward passes (3-D fused path only): p->spec holds the partial spectra
+template <class T> static int project_G_from_spec(mrl_mech_plan *p, T *out, double sign, const T *dot_with) {
+  mrl_context *ctx = p->ctx;
+  p->dot_count = 0;
+  const void *tw;
+  int rc = ctx->twiddles(ctx->n[0], &tw);
+  if (rc) return rc;
+  CK(launch_mech_fused_tma<T>(ctx->lc(), (cx<T> *)p->spec, (const T *)ctx->kaxis_dev[0], (const T *)ctx->kaxis_dev[1], (const T *)ctx->kaxis_dev[2],
+                              ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp, (const cx<T> *)tw));
+  ctx->launches++;
+  if ((rc = mrl_fftb_inverse(ctx, p->spec, out, p->nc, p->ncp, sign / (double)p->n, 1, dot_with, p->partials, p->nblk, &p->dot_count))) return rc;
+  if (!dot_with) return MRL_OK;
+  if (p->dot_count > 0) {
+    ctx->launches++;
+    CK(launch_vec_final<T>(ctx->lc(), FIN_ALPHA, SC_TMP, p->partials, p->dot_count, p->scal));
     return MRL_OK;
   }
   return vec<T>(p, VOP_DOT, dot_with, out, nullptr, nullptr, 0, FIN_ALPHA, SC_TMP);
@@ -157,6 +179,31 @@ static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xcon
                     bool cg_dot = false) {
   // out = sign * G( K4(F) : x ), FFTMechanics.C:107-112
   mrl_context *ctx = p->ctx;
+  if (p->fused_tangent && !xconst && x) {
+    // tangent (and direction update) in the load of the first FFT pass: the product never goes through HBM
+    MechTangentIO<T> io;
+    io.F = F;
+    io.K = (const T *)p->K;
+    io.mu = (const T *)p->mu;
+    io.p = const_cast<T *>(x);
+    io.r = r_update;
+    io.scal = p->scal;
+    io.n = p->n;
+    io.nrows = (long long)ctx->n[0] * ctx->n[1];
+    io.out = (cx<T> *)p->spec;
+    io.ncp = p->ncp;
+    const void *twz;
+    int rc = ctx->twiddles(ctx->n[2], &twz);
+    if (rc) return rc;
+    cudaError_t e = launch_mech_tangent_zfwd<T>(ctx->lc(), io, (const cx<T> *)twz, ctx->n[2]);
+    if (e == cudaSuccess) {
+      ctx->launches++;
+      if ((rc = mrl_fftb_strided(ctx, p->spec, p->nc, p->ncp, 1, 0))) return rc;  // y forward
+      return project_G_from_spec<T>(p, out, sign, cg_dot ? x : nullptr);
+    }
+    if (e != cudaErrorNotSupported) CK(e);
+    p->fused_tangent = false;
+  }
   ctx->launches++;
   CK(launch_mech_pointwise<T>(ctx->lc(), p->dim, r_update ? 3 : xconst ? 2 : 1, F, (const T *)p->K, (const T *)p->mu, x, xconst, (T *)p->tmp, p->n,
                               1.0, r_update, const_cast<T *>(x), p->scal));

@@ -26,6 +26,18 @@ struct RowMap {
 };
 
 
+// Arguments of the mechanics' first pass with the tangent fused into its load (k_mech_tangent_zfwd, mrl_mech_tma.cuh)
+template <class T> struct MechTangentIO {
+  const T *F, *K, *mu;  // [9][n], [n], [n]
+  T *p;                 // direction [9][n]: read; replaced by r + beta p when r != nullptr
+  const T *r;           // residual [9][n] or nullptr
+  const double *scal;   // device scalars of the CG recurrence (beta at index 4)
+  long long n;          // voxels
+  long long nrows;      // rows of the last axis per component (n / N, even)
+  cx<T> *out;           // [9][nrows][ncp] half spectra
+  int ncp;
+};
+
 // ======================================================================== strided c2c pass
 // Data is [nfields][nouter][n][ncols] complex, transform along n (stride `pitch`).
 template <class T> struct StridedIO {

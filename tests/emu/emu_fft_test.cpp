@@ -2,6 +2,7 @@
 // TEST TOOL: compiled with g++ -DMRL_EMU; validates index math / barriers without a GPU.
 #define MRL_EMU 1
 #include "../../marlin_b200/csrc/mrl_passes_slab.cuh"
+#include "../../marlin_b200/csrc/mrl_mech_tma.cuh"
 
 #include <complex>
 #include <random>
@@ -351,6 +352,66 @@ template <class C, int PPB, int NG, int NS> static void test_zinv_tma(const char
   }
   for (double v : partials) got += v;
   report((std::string(name) + " + dot").c_str(), std::max(e2, std::fabs(want - got)), 1e-12 * n);
+}
+
+// mechanics: first pass with the tangent K4(F) : p (and the direction update p = r + beta p) fused into its load
+template <class C, int NG> static void test_mech_tangent(const char *name, int nrows, int grid, bool update) {
+  constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1, ncp = (nc + 7) & ~7;
+  const long long nv = (long long)nrows * n;
+  std::mt19937_64 rng(23);
+  std::uniform_real_distribution<double> U(-1, 1);
+  std::vector<double> F(9 * nv), P(9 * nv), R(9 * nv), K(nv), MU(nv), scal(8, 0.0);
+  for (long long v = 0; v < nv; ++v) {
+    for (int c = 0; c < 9; ++c) {
+      F[c * nv + v] = (c / 3 == c % 3 ? 1.0 : 0.0) + 0.1 * U(rng);
+      P[c * nv + v] = U(rng);
+      R[c * nv + v] = U(rng);
+    }
+    K[v] = 0.8 + 0.1 * U(rng);
+    MU[v] = 0.4 + 0.1 * U(rng);
+  }
+  scal[4] = 0.37;
+  // expected: direction update, tangent, r2c per row
+  std::vector<double> pn = P, tmp(9 * nv);
+  for (long long v = 0; v < nv; ++v) {
+    MD<double, 3> Fm, X, Rm;
+    for (int c = 0; c < 9; ++c) {
+      if (update) pn[c * nv + v] = R[c * nv + v] + scal[4] * P[c * nv + v];
+      Fm.a[c / 3][c % 3] = F[c * nv + v];
+      X.a[c / 3][c % 3] = pn[c * nv + v];
+    }
+    mech_point<double, 3>(1, Fm, K[v], MU[v], X, Rm);
+    for (int c = 0; c < 9; ++c) tmp[c * nv + v] = Rm.a[c / 3][c % 3];
+  }
+  std::vector<cx<double>> out((size_t)9 * nrows * ncp, mk<double>(0.0, 0.0));
+  auto tw = make_tw(n);
+  MechTangentIO<double> io;
+  io.F = F.data();
+  io.K = K.data();
+  io.mu = MU.data();
+  io.p = P.data();
+  io.r = update ? R.data() : nullptr;
+  io.scal = scal.data();
+  io.n = nv;
+  io.nrows = nrows;
+  io.out = out.data();
+  io.ncp = ncp;
+  const cx<double> *twp = tw.data();
+  size_t smem = (size_t)NG * 9 * 2 * n * 8 + (size_t)NG * 9 * NP * 16 + 128;
+  emu::launch(dim3(grid), dim3(NG * 9 * C::TP), smem, [=] { k_mech_tangent_zfwd<double, C, NG>(io, twp); }, 64 * 1024);
+  double err = 0;
+  for (size_t i = 0; i < pn.size(); ++i) err = std::max(err, std::fabs(pn[i] - P[i]));
+  for (int c = 0; c < 9; ++c)
+    for (int r = 0; r < nrows; ++r) {
+      std::vector<lc> x(n);
+      for (int j = 0; j < n; ++j) x[j] = tmp[c * nv + (long long)r * n + j];
+      auto y = dft(x, -1);
+      for (int k = 0; k < nc; ++k) {
+        auto a = out[((size_t)c * nrows + r) * ncp + k];
+        err = std::max(err, (double)std::abs(lc(a.x, a.y) - y[k]));
+      }
+    }
+  report(name, err, 1e-11 * n);
 }
 
 // fused pass in the multi-GPU slab layout: data staged as [P][nxl][nyl][nzc], transform along y
@@ -823,6 +884,9 @@ static void tma_tests() {
   test_zinv_tma<FFTCfg<64, 8, 8, 8>, 2, 2, 2>("zinv tma 64 PPB2 NG2 NS2 rows=7", 7, 1);
   test_zinv_tma<FFTCfg<64, 8, 8, 8>, 1, 4, 3>("zinv tma 64 PPB1 NG4 NS3 rows=40", 40, 2);
   test_zinv_tma<FFTCfg<512, 64, 8, 8, 8>, 2, 2, 2>("zinv tma 512 PPB2 NG2 NS2 rows=9", 9, 1);
+  test_mech_tangent<FFTCfg<256, 32, 8, 8, 4>, 2>("mech tangent + zfwd 256 NG2 rows=10 update", 10, 2, true);
+  test_mech_tangent<FFTCfg<256, 32, 8, 8, 4>, 2>("mech tangent + zfwd 256 NG2 rows=6", 6, 1, false);
+  test_mech_tangent<FFTCfg<512, 64, 8, 8, 8>, 1>("mech tangent + zfwd 512 NG1 rows=4 update", 4, 1, true);
 }
 
 int main() {
