@@ -179,6 +179,14 @@ FFTMechanics::FFTMechanics(const InputParameters &parameters)
 void FFTMechanics::check() {
   const auto stress_name = getParam<TensorOutputBufferName>("stress");
   if (!_constitutive_model.getSuppliedItems().count(stress_name)) paramError("constitutive_model", "does not provide stress tensor '", stress_name, "'.");
+  // The solve evaluates the HyperElasticIsotropic law in closed form from THIS object's F / K / mu buffers instead of calling
+  // _constitutive_model.computeBuffer() (FFTMechanics.C:114-116, :139-141): the model block must name the same buffers.
+  for (const char *name : {"F", "K", "mu"}) {
+    const auto mine = getParam<TensorInputBufferName>(name), theirs = _constitutive_model.getParam<TensorInputBufferName>(name);
+    if (mine != theirs)
+      paramError(name, "the constitutive model '", _constitutive_model.name(), "' reads '", theirs, "' for ", name, " but FFTMechanics reads '", mine,
+                 "'; the CUDA mechanics path needs both blocks to name the same buffers.");
+  }
 }
 
 void FFTMechanics::computeBuffer() {

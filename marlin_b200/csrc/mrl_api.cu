@@ -953,7 +953,6 @@ extern "C" int mrl_split_substeps(mrl_split_plan *p, void *c, double dt, const d
     key.dt = dt;
     key.nold = nold;
     key.cur = p->cur;
-    key.time = p->time;
     for (int i = 0; i < 5 && i <= nold; ++i) key.beta[i] = beta[i];
     if (!p->graph || !(key == p->graph_key)) {
       // lazily initialised state (twiddles, kernel attributes, NVRTC modules) must exist before capturing

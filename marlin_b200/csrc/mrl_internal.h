@@ -70,12 +70,12 @@ struct mrl_split_plan {
   cudaGraphExec_t graph = nullptr;
   struct GraphKey {
     const void *c = nullptr;
-    double dt = 0, beta[5] = {0, 0, 0, 0, 0}, time = 0;
+    double dt = 0, beta[5] = {0, 0, 0, 0, 0};  // (not the time: fused plans reject expressions that read it)
     int nold = -1, cur = -1;
     bool operator==(const GraphKey &o) const {
       for (int i = 0; i < 5; ++i)
         if (beta[i] != o.beta[i]) return false;
-      return c == o.c && dt == o.dt && time == o.time && nold == o.nold && cur == o.cur;
+      return c == o.c && dt == o.dt && nold == o.nold && cur == o.cur;
     }
   } graph_key;
   int64_t graph_launches = 0;       // kernel launches inside the captured period

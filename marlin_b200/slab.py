@@ -163,6 +163,42 @@ class SlabPlan:
             pass
 
 
+def bind_host_side(local, world):
+    """Pin this rank's host threads (and, by first touch, the pinned buffers it allocates afterwards) to cores of the NUMA
+    node its GPU hangs off, a distinct core range per rank: eight ranks sharing one node's cores and memory is what kept
+    the end-to-end figure from scaling.  Returns a description for the bench line."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = -1
+        for cand in (bus.lower(), bus[4:].lower()):
+            path = f"/sys/bus/pci/devices/{cand}/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read().strip())
+                break
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if node < 0:
+            node = nodes[local * len(nodes) // max(world, 1)] if len(nodes) > 1 else (nodes[0] if nodes else 0)
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0)) or sorted(os.sched_getaffinity(0))
+        # the ranks whose GPUs share this node split its cores
+        per = max(1, len(allowed) // max(1, world))
+        mine = allowed[(local * per) % len(allowed):][:per] or allowed
+        os.sched_setaffinity(0, mine)
+        info = {"numa_node": node, "cpus": f"{mine[0]}-{mine[-1]}", "nodes": len(nodes)}
+    except Exception as exn:  # binding is an optimisation: never fail the run over it
+        info["error"] = str(exn)[:120]
+    return info
+
+
 def bench(args, rank, world, metric):
     """bench.py leg for N > 1: CH-3D-n slab-decomposed over `world` GPUs (strong scaling)."""
     import json
@@ -174,6 +210,7 @@ def bench(args, rank, world, metric):
     from bench import ClockSampler, algorithmic_bytes, workload  # noqa: E402 (bench.py is on sys.path)
 
     local = int(os.environ.get("LOCAL_RANK", rank))
+    host_binding = bind_host_side(local, world)   # before any pinned allocation
     torch.cuda.set_device(local)
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -323,7 +360,8 @@ def bench(args, rank, world, metric):
                        "parallelism": f"slab{world}"},
             "clocks": clocks,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "substeps/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world},
+                    "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
+                    "host_binding_rank0": host_binding},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(b_alg / world / 1e9 / (ms / 1e3), 1), "peak": peak,
                          "unit": "GB/s", "frac": round(b_alg / world / 1e9 / (ms / 1e3) / peak, 4), "traffic": None,
