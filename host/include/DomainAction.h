@@ -75,6 +75,7 @@ public:
   size_t realBytes() const { return _single ? 4 : 8; }
 
   mrl_context *context() const { return _ctx; }
+  mrl_dist *dist() const { return _dist; }  // the decomposed transforms (nullptr in serial mode)
   void check(int rc, const char *what) const;
 
   // ---- tensors -----------------------------------------------------------------------------

@@ -25,7 +25,7 @@ RankTwoIdentity::RankTwoIdentity(const InputParameters &parameters) : TensorOper
 
 void RankTwoIdentity::computeBuffer() {
   if (_dim != 3 && _dim != 2) mooseError("the CUDA mechanics path is 2-D or 3-D");
-  const size_t n = size_t(_domain.getNumberOfCells());
+  const size_t n = size_t(_domain.getNumberOfLocalCells());
   const int D = (int)_dim, nc = D * D;
   std::vector<double> host(nc * n, 0.0);
   for (int i = 0; i < D; ++i) std::fill(host.begin() + (D * i + i) * n, host.begin() + (D * i + i + 1) * n, 1.0);
@@ -52,6 +52,7 @@ void MacroscopicShearTensor::computeBuffer() {
   for (int c = 0; c < nc; ++c) {
     double s = 0;
     checkC(mrl_reduce(_domain.context(), MRL_SUM, static_cast<const char *>(_tF.data_ptr()) + c * stride, _tF.count(), &s), "mrl_reduce");
+    _domain.comm().allreduce(&s, 1, Comm::SUM);
     applied[c] = ((c / D == c % D) ? 1.0 : 0.0) - s / Real(_domain.getNumberOfCells());
   }
   applied[1] += _time;
@@ -72,14 +73,19 @@ void PhaseMechanicsTest::computeBuffer() {
   const auto &n = _domain.getGridSize();
   const int64_t s = _dim == 2 ? 30 : 9;
   if (_dim != 2 && _dim != 3) mooseError("Unsupported problem dimension");
-  std::vector<double> host(size_t(_domain.getNumberOfCells()), 0.0);
+  // this rank's part [b, e) of the grid (the whole grid in serial runs)
+  std::array<int64_t, 3> b, e;
+  _domain.getLocalBounds(_domain.rank(), b, e);
+  const int64_t ly = e[1] - b[1], lz = _dim == 3 ? e[2] - b[2] : 1;
+  std::vector<double> host(size_t(_domain.getNumberOfLocalCells()), 0.0);
   // phase[-s:, :s, -s:] = 1 (python slicing semantics: clipped to the grid)
   for (int64_t i = std::max<int64_t>(0, n[0] - s); i < n[0]; ++i)
-    for (int64_t j = 0; j < std::min<int64_t>(s, n[1]); ++j) {
+    for (int64_t j = std::max<int64_t>(0, b[1]); j < std::min<int64_t>(std::min<int64_t>(s, n[1]), e[1]); ++j) {
       if (_dim == 2)
-        host[size_t(i * n[1] + j)] = 1.0;
+        host[size_t(i * ly + (j - b[1]))] = 1.0;
       else
-        for (int64_t k = std::max<int64_t>(0, n[2] - s); k < n[2]; ++k) host[size_t((i * n[1] + j) * n[2] + k)] = 1.0;
+        for (int64_t k = std::max<int64_t>(std::max<int64_t>(0, n[2] - s), b[2]); k < std::min<int64_t>(n[2], e[2]); ++k)
+          host[size_t((i * ly + (j - b[1])) * lz + (k - b[2]))] = 1.0;
     }
   _u = _domain.fromHost(host, Space::REAL, false, 1);
 }
@@ -95,6 +101,18 @@ mrl_mech_plan *MechPlanHolder::get(const DomainAction &domain, const mrl_mech_de
   if (_plan && _K == K.data_ptr() && _mu == mu.data_ptr()) return _plan;
   reset();
   if (mrl_mech_plan_create(domain.context(), &desc, K.data_ptr(), mu.data_ptr(), &_plan) != MRL_OK) ::mooseError("marlin_b200: ", mrl_last_error());
+  if (domain.dist()) {
+    // FFT_SLAB / FFT_PENCIL: transforms through the decomposed path, inner products summed over the ranks
+    auto sum = [](void *user, double *v, int count) -> int {
+      try {
+        static_cast<Comm *>(user)->allreduce(v, size_t(count), Comm::SUM);
+      } catch (const std::exception &) {
+        return 1;
+      }
+      return 0;
+    };
+    if (mrl_mech_plan_set_dist(_plan, domain.dist(), sum, &domain.comm()) != MRL_OK) ::mooseError("marlin_b200: ", mrl_last_error());
+  }
   _K = K.data_ptr();
   _mu = mu.data_ptr();
   return _plan;
@@ -179,9 +197,15 @@ FFTMechanics::FFTMechanics(const InputParameters &parameters)
 void FFTMechanics::check() {
   const auto stress_name = getParam<TensorOutputBufferName>("stress");
   if (!_constitutive_model.getSuppliedItems().count(stress_name)) paramError("constitutive_model", "does not provide stress tensor '", stress_name, "'.");
-  // The solve evaluates the HyperElasticIsotropic law in closed form from THIS object's F / K / mu buffers instead of calling
-  // _constitutive_model.computeBuffer() (FFTMechanics.C:114-116, :139-141): the model block must name the same buffers.
-  for (const char *name : {"F", "K", "mu"}) {
+  // The solve evaluates the HyperElasticIsotropic law in closed form on its own iterate with THIS object's K / mu instead of
+  // calling _constitutive_model.computeBuffer() (FFTMechanics.C:114-116, :139-141).  That is the same computation only if the
+  // model block reads the iterate (this object's output buffer, e.g. F = Fnew in mech3d.i) and the same K / mu buffers.
+  const auto iterate = getParam<TensorOutputBufferName>("buffer");
+  const auto model_F = _constitutive_model.getParam<TensorInputBufferName>("F");
+  if (model_F != iterate)
+    paramError("constitutive_model", "'", _constitutive_model.name(), "' evaluates the stress from '", model_F, "' but FFTMechanics iterates on '", iterate,
+               "'; the CUDA mechanics path needs the model to read the iterate.");
+  for (const char *name : {"K", "mu"}) {
     const auto mine = getParam<TensorInputBufferName>(name), theirs = _constitutive_model.getParam<TensorInputBufferName>(name);
     if (mine != theirs)
       paramError(name, "the constitutive model '", _constitutive_model.name(), "' reads '", theirs, "' for ", name, " but FFTMechanics reads '", mine,

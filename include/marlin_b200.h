@@ -273,6 +273,14 @@ typedef struct mrl_mech_stats {
 int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *desc, const void *K_real_dev, const void *mu_real_dev,
                          mrl_mech_plan **out);
 int mrl_mech_plan_destroy(mrl_mech_plan *plan);
+/* Mechanics on a decomposed domain (a context set up with mrl_domain_set_dist / mrl_domain_set_pencil; FFTMechanics over
+ * DomainAction::fft / ifft in FFT_SLAB / FFT_PENCIL mode, src/tensor_computes/FFTMechanics.C:96-163): the transforms of
+ * the plan go through `dist`, the Green projection acts on the rank's wavevectors, and every inner product of the CG /
+ * Newton recurrences (include/utils/MarlinUtils.h:57-131) is summed over the ranks through `allreduce_sum` (in place on
+ * `count` host doubles, 0 = success; the host objects pass their communicator).  Collective: all ranks solve together. */
+typedef int (*mrl_allreduce_fn)(void *user, double *values, int count);
+struct mrl_dist;
+int mrl_mech_plan_set_dist(mrl_mech_plan *plan, struct mrl_dist *dist, mrl_allreduce_fn allreduce_sum, void *user);
 /* P = F . S(F)                      HyperElasticIsotropic::computeBuffer                    */
 int mrl_mech_constitutive(mrl_mech_plan *plan, const void *F_dev, void *P_dev);
 /* out = irfftn( Ghat4 : rfftn(A) )  FFTMechanics.C:104-105                                   */

@@ -369,7 +369,7 @@ template <class T> static int slab_forward_one(mrl_dist *d, const T *in, cx<T> *
   return MRL_OK;
 }
 
-template <class T> static int slab_inverse_one(mrl_dist *d, const cx<T> *in, T *out) {
+template <class T> static int slab_inverse_one(mrl_dist *d, const cx<T> *in, T *out, double scale) {
   mrl_context *ctx = d->ctx;
   const int dim = ctx->dim, P = ctx->nranks, me = ctx->rank;
   const long long nx = ctx->gn[0], ny = ctx->gn[1], nyl = ctx->nyl, nxl = ctx->nxl, ncz = d->ncz;
@@ -396,9 +396,9 @@ template <class T> static int slab_inverse_one(mrl_dist *d, const cx<T> *in, T *
   if ((rc = dist_barrier(d))) return rc;
   // x inverse, then z c2r (3-D) / real part (2-D), normalised by 1/N (:1013-1016)
   if ((rc = mrl_pass_strided(ctx, B, B, (int)nx, nyl * ncz, 1, 1))) return rc;
-  if (dim == 3) return mrl_pass_zinv(ctx, B, out, nx * nyl, ctx->gn[2], 1.0 / N);
+  if (dim == 3) return mrl_pass_zinv(ctx, B, out, nx * nyl, ctx->gn[2], scale / N);
   ctx->launches++;
-  CK(launch_complex_real_scale<T>(ctx->lc(), (const cx<T> *)B, out, nx * nyl, (T)(1.0 / N)));
+  CK(launch_complex_real_scale<T>(ctx->lc(), (const cx<T> *)B, out, nx * nyl, (T)(scale / N)));
   return MRL_OK;
 }
 
@@ -438,7 +438,7 @@ template <class T> static int pencil_forward_one(mrl_dist *d, const T *in, cx<T>
 
 // ifftPencil (:1037-1047): the stages in reverse; the inverse real transform along x expands the half spectrum by
 // the Hermitian symmetry of the partially transformed array, A[nx - k][y][z] = conj A[k][y][z], which is local.
-template <class T> static int pencil_inverse_one(mrl_dist *d, const cx<T> *in, T *out) {
+template <class T> static int pencil_inverse_one(mrl_dist *d, const cx<T> *in, T *out, double scale) {
   mrl_context *ctx = d->ctx;
   const int me = ctx->rank, Py = ctx->py, Pz = ctx->pz, iy = me % Py, iz = me / Py, gbase = iz * Py;
   const long long nx = ctx->gn[0], ny = ctx->gn[1], nz = ctx->gn[2], nyl = ctx->nyl, nzl = ctx->n[2], nxl = ctx->nxl, ny2 = ctx->nr[1];
@@ -467,7 +467,7 @@ template <class T> static int pencil_inverse_one(mrl_dist *d, const cx<T> *in, T
   CK(launch_hermitian_rows<T>(ctx->lc(), B1, (int)nx, nyl * nzl));
   if ((rc = mrl_pass_strided(ctx, B1, B1, (int)nx, nyl * nzl, 1, 1))) return rc;
   ctx->launches++;
-  CK(launch_complex_real_scale<T>(ctx->lc(), (const cx<T> *)B1, out, nx * nyl * nzl, (T)(1.0 / N)));
+  CK(launch_complex_real_scale<T>(ctx->lc(), (const cx<T> *)B1, out, nx * nyl * nzl, (T)(scale / N)));
   return MRL_OK;
 }
 
@@ -491,7 +491,9 @@ extern "C" int mrl_dist_rfftn(mrl_dist *d, const void *in, void *out, int batch)
   return MRL_OK;
 }
 
-extern "C" int mrl_dist_irfftn(mrl_dist *d, const void *in, void *out, int batch) {
+extern "C" int mrl_dist_irfftn(mrl_dist *d, const void *in, void *out, int batch) { return mrl_dist_irfftn_scaled(d, in, out, batch, 1.0); }
+
+int mrl_dist_irfftn_scaled(mrl_dist *d, const void *in, void *out, int batch, double scale) {
   if (!d || !in || !out || batch < 1) return mrl_fail(MRL_ERR_INVALID, "mrl_dist_irfftn: bad arguments");
   if (!d->imported) return mrl_fail(MRL_ERR_INVALID, "mrl_dist_irfftn: peers' buffers not imported (mrl_dist_ipc_import)");
   mrl_context *ctx = d->ctx;
@@ -501,11 +503,11 @@ extern "C" int mrl_dist_irfftn(mrl_dist *d, const void *in, void *out, int batch
   for (int b = 0; b < batch; ++b) {
     int rc;
     if (ctx->pencil)
-      rc = f64 ? pencil_inverse_one<double>(d, (const cx<double> *)in + b * kl, (double *)out + b * rl)
-               : pencil_inverse_one<float>(d, (const cx<float> *)in + b * kl, (float *)out + b * rl);
+      rc = f64 ? pencil_inverse_one<double>(d, (const cx<double> *)in + b * kl, (double *)out + b * rl, scale)
+               : pencil_inverse_one<float>(d, (const cx<float> *)in + b * kl, (float *)out + b * rl, scale);
     else
-      rc = f64 ? slab_inverse_one<double>(d, (const cx<double> *)in + b * kl, (double *)out + b * rl)
-               : slab_inverse_one<float>(d, (const cx<float> *)in + b * kl, (float *)out + b * rl);
+      rc = f64 ? slab_inverse_one<double>(d, (const cx<double> *)in + b * kl, (double *)out + b * rl, scale)
+               : slab_inverse_one<float>(d, (const cx<float> *)in + b * kl, (float *)out + b * rl, scale);
     if (rc) return rc;
   }
   return MRL_OK;

@@ -134,6 +134,9 @@ int mrl_fftb_strided(mrl_context *ctx, void *spec_cplx, int batch, int ncp, int 
 int mrl_fftb_inverse(mrl_context *ctx, void *work_cplx, void *out_real, int batch, int ncp, double scale, int first_axis = 0,
                      const void *dot_with = nullptr, double *dot_partials = nullptr, int dot_capacity = 0, int *dot_count = nullptr);
 
+// mrl_dist_irfftn with an extra factor on the result (mechanics: sign of the projected field)
+int mrl_dist_irfftn_scaled(mrl_dist *d, const void *in_cplx, void *out_real, int batch, double scale);
+
 namespace mrl {
 FFTPlanDev make_fft_plan(int n);
 template <class T>

@@ -52,6 +52,11 @@ struct mrl_mech_plan {
   double *scal = nullptr, *partials = nullptr, *host = nullptr;
   int nblk = 0;
   bool fused_x = true;  // x pass fused with the Green projection (sizes with a TMA configuration)
+  // decomposed domain (mrl_domain_set_dist / _pencil): the transforms go through `dist`, the inner products of the CG and
+  // Newton recurrences are summed over the ranks by the caller's `allreduce` (host side, like the reference's MPI reductions)
+  mrl_dist *dist = nullptr;
+  mrl_allreduce_fn allreduce = nullptr;
+  void *allreduce_user = nullptr;
   bool fused_tangent = true;  // tangent fused into the first FFT pass (3-D, last axis 256 or 512, x pass fused)
   int dot_count = 0;    // partial sums the last inverse pass left in `partials` (0: the inner product was not fused)
 };
@@ -69,7 +74,6 @@ extern "C" int mrl_mech_plan_destroy(mrl_mech_plan *p) {
 
 extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, const void *K, const void *mu, mrl_mech_plan **out) {
   if (!ctx || !d || !K || !mu || !out) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_plan_create: bad arguments");
-  if (ctx->dist) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_mech_plan_create: the mechanics plan is single-GPU (the domain is slab-decomposed)");
   if (ctx->dim != 3 && ctx->dim != 2)
     return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_mech_plan_create: the CUDA mechanics path is 2-D or 3-D (dim = %d)", ctx->dim);
   CK(cudaSetDevice(ctx->device));
@@ -81,13 +85,14 @@ extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, co
   p->n = ctx->total();
   p->dim = ctx->dim;
   p->nc = ctx->dim * ctx->dim;
-  p->fused_x = ctx->dim == 3;
-  p->fused_tangent = ctx->dim == 3;
-  if (p->desc.l_max_its <= 0) p->desc.l_max_its = p->n;  // FFTMechanics.C:63-64: default = number of cells
-  p->ncp = mrl_fftb_pitch(ctx);
+  p->fused_x = ctx->dim == 3 && !ctx->dist;
+  p->fused_tangent = p->fused_x;
+  if (p->desc.l_max_its <= 0) p->desc.l_max_its = (long long)ctx->gn[0] * ctx->gn[1] * ctx->gn[2];  // FFTMechanics.C:63-64: default = number of cells
+  p->ncp = ctx->dist ? ctx->nr[ctx->dim - 1] : mrl_fftb_pitch(ctx);
   const size_t esz = ctx->precision == MRL_F64 ? 8 : 4;
   const size_t vbytes = p->nc * (size_t)p->n * esz;
-  const size_t sbytes = p->nc * (size_t)ctx->n[0] * (ctx->dim == 3 ? ctx->n[1] : 1) * p->ncp * 2 * esz;
+  const size_t sbytes = ctx->dist ? p->nc * (size_t)ctx->nr[0] * ctx->nr[1] * ctx->nr[2] * 2 * esz
+                                  : p->nc * (size_t)ctx->n[0] * (ctx->dim == 3 ? ctx->n[1] : 1) * p->ncp * 2 * esz;
   p->nblk = ctx->sm_count * 4;
   cudaError_t e = cudaMalloc(&p->spec, sbytes);
   if (e == cudaSuccess) e = cudaMemsetAsync(p->spec, 0, sbytes, ctx->stream);
@@ -101,6 +106,15 @@ extern "C" int mrl_mech_plan_create(mrl_context *ctx, const mrl_mech_desc *d, co
     return mrl_fail(MRL_ERR_CUDA, "mechanics plan allocation failed: %s", cudaGetErrorString(e));
   }
   *out = p;
+  return MRL_OK;
+}
+
+extern "C" int mrl_mech_plan_set_dist(mrl_mech_plan *p, mrl_dist *dist, mrl_allreduce_fn allreduce_sum, void *user) {
+  if (!p || !dist || !allreduce_sum) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_plan_set_dist: bad arguments");
+  if (!p->ctx->dist) return mrl_fail(MRL_ERR_INVALID, "mrl_mech_plan_set_dist: the plan's domain is not decomposed");
+  p->dist = dist;
+  p->allreduce = allreduce_sum;
+  p->allreduce_user = user;
   return MRL_OK;
 }
 
@@ -148,8 +162,16 @@ template <class T> static int project_G_passes(mrl_mech_plan *p, const T *A, T *
   const T *kx = (const T *)ctx->kaxis_dev[0], *ky = (const T *)ctx->kaxis_dev[1], *kz = (const T *)ctx->kaxis_dev[2];
   // 2-D: the half-spectrum axis is y; the projection kernel sees [nc][n0][1][ncp] with q = (kx, ky)
   const T *klast = p->dim == 3 ? kz : ky;
-  const int n1 = p->dim == 3 ? ctx->n[1] : 1, nlast = ctx->nr[p->dim - 1];
+  const int n1 = p->dim == 3 ? ctx->nr[1] : 1, nlast = ctx->nr[p->dim - 1];
   int rc;
+  if (ctx->dist) {
+    // decomposed domain: transforms with their exchanges, the projection on this rank's wavevectors (local k-axes)
+    if (!p->dist) return mrl_fail(MRL_ERR_INVALID, "mechanics on a decomposed domain needs mrl_mech_plan_set_dist");
+    if ((rc = mrl_dist_rfftn(p->dist, A, p->spec, nc))) return rc;
+    ctx->launches++;
+    CK(launch_mech_project<T>(ctx->lc(), p->dim, (cx<T> *)p->spec, kx, ky, klast, ctx->nr[0], n1, nlast, p->ncp));
+    return mrl_dist_irfftn_scaled(p->dist, p->spec, out, nc, sign);
+  }
   if (p->fused_x) {
     // z, y forward; x forward + projection + x inverse in ONE pass over the spectra; y, z inverse
     if ((rc = mrl_fftb_forward(ctx, A, p->spec, nc, p->ncp, 1))) return rc;
@@ -168,7 +190,7 @@ template <class T> static int project_G_passes(mrl_mech_plan *p, const T *A, T *
     return rc;
   }
   ctx->launches++;
-  CK(launch_mech_project<T>(ctx->lc(), p->dim, (cx<T> *)p->spec, kx, ky, klast, ctx->n[0], n1, nlast, p->ncp));
+  CK(launch_mech_project<T>(ctx->lc(), p->dim, (cx<T> *)p->spec, kx, ky, klast, ctx->nr[0], n1, nlast, p->ncp));
   return mrl_fftb_inverse(ctx, p->spec, out, nc, p->ncp, sign / (double)p->n, 0, dot_with, p->partials, p->nblk, &p->dot_count);
 }
 
@@ -212,7 +234,19 @@ static int apply_GK(mrl_mech_plan *p, const T *F, const T *x, const double *xcon
 
 template <class T> static int vec(mrl_mech_plan *p, int op, const T *a, const T *b, T *y, T *z, double s, int fin, int slot) {
   p->ctx->launches++;
-  CK(launch_vec<T>(p->ctx->lc(), op, a, b, y, z, p->scal, s, p->nc * p->n, fin, slot, p->partials, p->nblk));
+  const bool reduces = op == VOP_DOT || op == VOP_CG_XR;
+  if (!(p->dist && reduces)) {
+    CK(launch_vec<T>(p->ctx->lc(), op, a, b, y, z, p->scal, s, p->nc * p->n, fin, slot, p->partials, p->nblk));
+    return MRL_OK;
+  }
+  // decomposed domain: this rank's sum -> host -> sum over the ranks -> device, then the dependent scalars
+  CK(launch_vec<T>(p->ctx->lc(), op, a, b, y, z, p->scal, s, p->nc * p->n, FIN_STORE, SC_TMP, p->partials, p->nblk));
+  CK(cudaMemcpyAsync(p->host, p->scal + SC_TMP, sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+  CK(cudaStreamSynchronize(p->ctx->stream));
+  if (p->allreduce(p->allreduce_user, p->host, 1)) return mrl_fail(MRL_ERR_INVALID, "mechanics: the caller's allreduce failed");
+  CK(cudaMemcpyAsync(p->partials, p->host, sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+  CK(launch_vec_final<T>(p->ctx->lc(), fin, slot, p->partials, 1, p->scal));
+  CK(cudaStreamSynchronize(p->ctx->stream));  // p->host is reused by the next reduction
   return MRL_OK;
 }
 static int read_scalar(mrl_mech_plan *p, int slot, double *v) {
