@@ -27,7 +27,7 @@ host/_build/%.o: host/%.C $(HOST_HDR)
 	g++ $(HOST_FLAGS) -c $< -o $@
 
 $(APP): $(HOST_OBJ) $(LIB)
-	g++ -o $@ $(HOST_OBJ) -Lmarlin_b200 -lmarlin_b200 -Wl,-rpath,'$$ORIGIN' -Wl,-rpath-link,/usr/local/cuda/lib64
+	g++ -o $@ $(HOST_OBJ) -Lmarlin_b200 -lmarlin_b200 -lz -pthread -Wl,-rpath,'$$ORIGIN' -Wl,-rpath-link,/usr/local/cuda/lib64
 
 $(EMBED): $(EMBED_SRC) tools/embed_headers.py
 	@mkdir -p $(BUILD)

@@ -4,15 +4,18 @@
 //                      with the output time snapshotted so the next step cannot race it)
 //   XDMFTensorOutput   src/tensor_outputs/XDMFTensorOutput.C:29-761 (XMF skeleton :118-221, writeLocalData :266-355,
 //                      writeSerialXMF :358-426, writeParallelXMF :429-527, extendTensor :529-553,
-//                      buildAttributeNames :654-668, rankTag / binaryFileName :737-761).  Raw little-endian binary
-//                      data files (<file_base>[.rankNNNN].<name>.<frame>.bin, the reference's non-HDF5 format); one
-//                      set of data files per rank and a spatial collection written by rank 0 in parallel runs.
+//                      buildAttributeNames :654-668, rankTag / hdf5FileName / binaryFileName :737-761).  Data either
+//                      as raw little-endian binary files (<file_base>[.rankNNNN].<name>.<frame>.bin) or, with
+//                      enable_hdf5 = true, as deflate-compressed one-chunk datasets of <file_base>[.rankNNNN].h5
+//                      (addDataToHDF5 :572-651; written by host/shim/h5lite - no libhdf5 in this build); one set
+//                      of data files per rank and a spatial collection written by rank 0 in parallel runs.
 #pragma once
 #include <sstream>
 #include <thread>
 #include <utility>
 
 #include "TensorProblem.h"
+#include "h5lite.h"
 
 class TensorOutput : public MooseObject {
 public:
@@ -60,7 +63,7 @@ public:
   // n: global grid.  bounds: one entry per rank in parallel runs (empty: serial); `rank` writes its own part's data
   // files, rank 0 the XMF document.
   XDMFWriter(unsigned int dim, const std::array<int64_t, 3> &n, const std::array<double, 3> &dx, const std::array<double, 3> &min, bool transpose,
-             std::string file_base, unsigned int rank = 0, std::vector<Bounds> bounds = {});
+             std::string file_base, unsigned int rank = 0, std::vector<Bounds> bounds = {}, bool enable_hdf5 = false);
   void addFrame(double time, const std::vector<Field> &fields);  // writes the .bin files and <file_base>.xmf
   std::string xml() const;
   static std::vector<std::string> attributeNames(const std::string &buffer_name, int64_t num_fields);
@@ -69,7 +72,9 @@ private:
   bool parallel() const { return !_bounds.empty(); }
   std::string rankTag(unsigned int rank) const;
   std::string binaryFileName(const std::string &setname, unsigned int rank) const { return _file_base + rankTag(rank) + "." + setname + ".bin"; }
-  std::vector<double> arrange(const Field &f, int component) const;  // extend (NODE) + transpose, one component
+  std::string hdf5FileName(unsigned int rank) const { return _file_base + rankTag(rank) + ".h5"; }
+  std::string dataItem(const std::string &dims, const std::string &dataset, unsigned int rank) const;  // the <DataItem> of one dataset
+  std::vector<double> arrange(const Field &f, int component, std::vector<uint64_t> *dims = nullptr) const;  // extend (NODE) + transpose, one component
   std::string serialFrame(double time, const std::vector<Field> &fields) const;
   std::string parallelFrame(double time, const std::vector<Field> &fields) const;
   unsigned int _dim;
@@ -81,6 +86,7 @@ private:
   std::string _file_base, _head, _frames;
   std::string _cell_dims, _node_dims;
   unsigned int _frame = 0;
+  std::unique_ptr<H5LiteFile> _h5;  // enable_hdf5: this process's data file
 };
 
 class XDMFTensorOutput : public TensorOutput {
@@ -95,5 +101,6 @@ protected:
   std::vector<XDMFWriter::Field> _fields;
   std::map<std::string, XDMFWriter::Mode> _output_mode;
   const bool _transpose;
+  const bool _enable_hdf5;
   std::unique_ptr<XDMFWriter> _writer;
 };

@@ -569,6 +569,23 @@ static int xdmfSelfTest(const std::string &dir) {
       for (int f = 0; f < 2; ++f) w.addFrame(0.5 * f, {{"c", XDMFWriter::Mode::CELL, 1, part.data()}});
     }
   }
+  // the same fields as `selftest`, stored as HDF5 datasets; and a file with enough datasets for a two-level group B-tree
+  {
+    XDMFWriter w(2, n, dx, mn, true, dir + "/selftest_h5", 0, {}, true);
+    for (int f = 0; f < 2; ++f) {
+      for (int i = 0; i < 6; ++i) c[i] = 10 + i + 100 * f;
+      w.addFrame(0.001 * 3 * f, {{"c", XDMFWriter::Mode::NODE, 1, c.data()},
+                                 {"disp", XDMFWriter::Mode::OVERSIZED_NODAL, 2, disp.data()},
+                                 {"mu", XDMFWriter::Mode::CELL, 1, mu.data()}});
+    }
+    H5LiteFile many(dir + "/selftest_many.h5");
+    std::vector<float> v(24);
+    for (int k = 0; k < 300; ++k) {
+      for (int i = 0; i < 24; ++i) v[i] = float(k) + 0.5f * float(i);
+      many.addDataset("field_" + std::to_string(k) + ".0", {2, 3, 4}, 4, v.data());
+      if (k % 50 == 0) many.flush();
+    }
+  }
   return 0;
 }
 

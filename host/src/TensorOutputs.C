@@ -75,9 +75,16 @@ std::string g17(double v) {  // pugixml's attribute = double
 }  // namespace
 
 XDMFWriter::XDMFWriter(unsigned int dim, const std::array<int64_t, 3> &n, const std::array<double, 3> &dx, const std::array<double, 3> &min,
-                       bool transpose, std::string file_base, unsigned int rank, std::vector<Bounds> bounds)
+                       bool transpose, std::string file_base, unsigned int rank, std::vector<Bounds> bounds, bool enable_hdf5)
   : _dim(dim), _n(n), _dx(dx), _min(min), _rank(rank), _bounds(std::move(bounds)), _transpose(transpose), _file_base(std::move(file_base)) {
   if (dim != 2 && dim != 3) ::mooseError("XDMFTensorOutput: Unsupported tensor dimension");
+  if (enable_hdf5) {
+    try {
+      _h5 = std::make_unique<H5LiteFile>(hdf5FileName(_rank));  // H5Fcreate(..., H5F_ACC_TRUNC, ...), :206-216
+    } catch (const std::exception &e) {
+      ::mooseError(e.what());
+    }
+  }
   if (parallel()) {
     if (_rank >= _bounds.size()) ::mooseError("XDMFWriter: rank ", _rank, " outside the ", _bounds.size(), " parts");
     for (unsigned int d = 0; d < 3; ++d) _n[d] = d < dim ? _bounds[_rank].second[d] - _bounds[_rank].first[d] : 1;
@@ -132,7 +139,7 @@ std::vector<std::string> XDMFWriter::attributeNames(const std::string &buffer_na
 
 // one component on the output grid: periodic continuation for NODE (extendTensor), then the x<->y (2-D) or
 // x<->z (3-D) transpose
-std::vector<double> XDMFWriter::arrange(const Field &f, int component) const {
+std::vector<double> XDMFWriter::arrange(const Field &f, int component, std::vector<uint64_t> *dims) const {
   std::array<int64_t, 3> in = {1, 1, 1}, ext = {1, 1, 1};
   for (unsigned int d = 0; d < _dim; ++d) {
     in[d] = f.mode == Mode::OVERSIZED_NODAL ? _n[d] + 1 : _n[d];
@@ -142,6 +149,7 @@ std::vector<double> XDMFWriter::arrange(const Field &f, int component) const {
   const double *src = f.data + (size_t)component * count_in;
   std::array<int64_t, 3> out = ext;
   if (_transpose) std::swap(out[0], out[_dim - 1]);
+  if (dims) dims->assign(out.begin(), out.begin() + _dim);
   std::vector<double> dst((size_t)(ext[0] * ext[1] * ext[2]));
   for (int64_t i = 0; i < ext[0]; ++i)
     for (int64_t j = 0; j < ext[1]; ++j)
@@ -153,6 +161,12 @@ std::vector<double> XDMFWriter::arrange(const Field &f, int component) const {
         dst[(size_t)((o[0] * out[1] + o[1]) * out[2] + o[2])] = v;
       }
   return dst;
+}
+
+std::string XDMFWriter::dataItem(const std::string &dims, const std::string &dataset, unsigned int rank) const {
+  if (_h5) return "<DataItem DataType=\"Float\" Dimensions=\"" + dims + "\" Format=\"HDF\">" + hdf5FileName(rank) + ":/" + dataset + "</DataItem>\n";
+  return "<DataItem DataType=\"Float\" Dimensions=\"" + dims + "\" Format=\"Binary\" Endian=\"Little\" Precision=\"8\">" + binaryFileName(dataset, rank) +
+         "</DataItem>\n";
 }
 
 std::string XDMFWriter::rankTag(unsigned int rank) const {
@@ -168,13 +182,24 @@ void XDMFWriter::addFrame(double time, const std::vector<Field> &fields) {
     if (parallel() && f.mode != Mode::CELL) ::mooseError("XDMFTensorOutput currently supports only CELL output mode in parallel.");
     const auto names = attributeNames(f.name, f.ncomp);
     for (int c = 0; c < f.ncomp; ++c) {
-      const std::string fname = binaryFileName(names[c] + "." + std::to_string(_frame), _rank);
-      const std::vector<double> data = arrange(f, c);
+      const std::string setname = names[c] + "." + std::to_string(_frame);
+      std::vector<uint64_t> dims;
+      const std::vector<double> data = arrange(f, c, &dims);
+      if (_h5) {
+        try {
+          _h5->addDataset(setname, dims, 8, data.data());  // addDataToHDF5 (:572-651): one deflate-9 chunk
+        } catch (const std::exception &e) {
+          ::mooseError(e.what());
+        }
+        continue;
+      }
+      const std::string fname = binaryFileName(setname, _rank);
       std::ofstream file(fname, std::ios::out | std::ios::binary);
       if (!file) ::mooseError("XDMFTensorOutput: cannot write '", fname, "'");
       file.write(reinterpret_cast<const char *>(data.data()), std::streamsize(data.size() * sizeof(double)));
     }
   }
+  if (_h5) _h5->flush();  // H5Fflush (:257-260)
   if (!parallel() || _rank == 0) {
     _frames += parallel() ? parallelFrame(time, fields) : serialFrame(time, fields);
     std::ofstream x(_file_base + ".xmf");
@@ -214,8 +239,7 @@ std::string XDMFWriter::parallelFrame(double time, const std::vector<Field> &fie
       const auto names = attributeNames(f.name, f.ncomp);
       for (int c = 0; c < f.ncomp; ++c)
         g << "\t\t\t\t\t<Attribute Name=\"" << names[c] << "\" Center=\"Cell\">\n"
-          << "\t\t\t\t\t\t<DataItem DataType=\"Float\" Dimensions=\"" << join(cells) << "\" Format=\"Binary\" Endian=\"Little\" Precision=\"8\">"
-          << binaryFileName(names[c] + "." + std::to_string(_frame), r) << "</DataItem>\n"
+          << "\t\t\t\t\t\t" << dataItem(join(cells), names[c] + "." + std::to_string(_frame), r)
           << "\t\t\t\t\t</Attribute>\n";
     }
     g << "\t\t\t\t</Grid>\n";
@@ -237,8 +261,7 @@ std::string XDMFWriter::serialFrame(double time, const std::vector<Field> &field
     for (int c = 0; c < f.ncomp; ++c) {
       const std::string dataset = names[c] + "." + std::to_string(_frame);
       g << "\t\t\t\t<Attribute Name=\"" << names[c] << "\" Center=\"" << (is_cell ? "Cell" : "Node") << "\">\n"
-        << "\t\t\t\t\t<DataItem DataType=\"Float\" Dimensions=\"" << (is_cell ? _cell_dims : _node_dims)
-        << "\" Format=\"Binary\" Endian=\"Little\" Precision=\"8\">" << binaryFileName(dataset, 0) << "</DataItem>\n"
+        << "\t\t\t\t\t" << dataItem(is_cell ? _cell_dims : _node_dims, dataset, 0)
         << "\t\t\t\t</Attribute>\n";
     }
   }
@@ -252,14 +275,15 @@ registerMooseObject("MarlinApp", XDMFTensorOutput);
 InputParameters XDMFTensorOutput::validParams() {
   InputParameters params = TensorOutput::validParams();
   params.addClassDescription("Output a tensor in XDMF format.");
-  params.addParam<bool>("enable_hdf5", false, "Use HDF5 for binary data storage (not available in this build: raw binary files are written).");
+  params.addParam<bool>("enable_hdf5", false, "Use HDF5 for binary data storage.");
   params.addParam<std::vector<std::string>>("output_mode", {}, "Output as cell or node data (CELL NODE OVERSIZED_NODAL), one entry per buffer");
   params.addParam<bool>("transpose", true,
                         "The Paraview XDMF reader swaps x-y (x-z in 3d), so we transpose the tensors before we output to make the data look right in Paraview.");
   return params;
 }
 
-XDMFTensorOutput::XDMFTensorOutput(const InputParameters &parameters) : TensorOutput(parameters), _transpose(getParam<bool>("transpose")) {
+XDMFTensorOutput::XDMFTensorOutput(const InputParameters &parameters)
+  : TensorOutput(parameters), _transpose(getParam<bool>("transpose")), _enable_hdf5(getParam<bool>("enable_hdf5")) {
   auto modes = getParam<std::vector<std::string>>("output_mode");
   const auto names = getParam<std::vector<TensorInputBufferName>>("buffer");
   if (modes.empty())
@@ -278,7 +302,6 @@ XDMFTensorOutput::XDMFTensorOutput(const InputParameters &parameters) : TensorOu
   if (_domain.nRanks() > 1)
     for (const auto &m : _output_mode)
       if (m.second != XDMFWriter::Mode::CELL) mooseError("XDMFTensorOutput currently supports only CELL output mode in parallel.");
-  if (getParam<bool>("enable_hdf5")) mooseWarning("XDMFTensorOutput: this build has no HDF5 library; writing raw binary data files instead.");
 }
 
 void XDMFTensorOutput::init() {
@@ -292,7 +315,7 @@ void XDMFTensorOutput::init() {
     bounds.resize(_domain.nRanks());
     for (unsigned int r = 0; r < _domain.nRanks(); ++r) _domain.getLocalBounds(r, bounds[r].first, bounds[r].second);
   }
-  _writer = std::make_unique<XDMFWriter>(_domain.getDim(), _domain.getGridSize(), dx, mn, _transpose, _file_base, _domain.rank(), bounds);
+  _writer = std::make_unique<XDMFWriter>(_domain.getDim(), _domain.getGridSize(), dx, mn, _transpose, _file_base, _domain.rank(), bounds, _enable_hdf5);
 }
 
 // the buffers' metadata is read here, on the main thread; the output thread only touches the CPU copies

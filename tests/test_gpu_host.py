@@ -378,16 +378,23 @@ def test_xdmf_output_matches_gold_xmf_and_fields(tmp_path):
     run(tmp_path, "ch2d_gold.i", "TensorOutputs/active=xdmf")
     mine = open(f"{tmp_path}/ch2d_gold.xmf").read()
     norm_gold = re.sub(r' Format="HDF">cahnhilliard\.h5:/([a-z]+)\.(\d+)<', r' STORAGE>\1.\2<', gold)
-    norm_mine = re.sub(r' Format="Binary" Endian="Little" Precision="8">[^<]*ch2d_gold\.([a-z]+)\.(\d+)\.bin<', r' STORAGE>\1.\2<', mine)
+    norm_mine = re.sub(r' Format="HDF">[^<]*ch2d_gold\.h5:/([a-z]+)\.(\d+)<', r' STORAGE>\1.\2<', mine)
     assert norm_mine == norm_gold
+    import h5lite
     g = np.load(f"{G}/ch2d_exodus.npz")
+    h = h5lite.H5File(f"{tmp_path}/ch2d_gold.h5")
     for frame in (0, 3, 10):
-        c = np.fromfile(f"{tmp_path}/ch2d_gold.c.{frame}.bin", dtype="<f8").reshape(21, 21)
+        c = h.read(f"c.{frame}")
+        assert c.shape == (21, 21)
         assert np.abs(c[:20, :20] - g["c"][frame]).max() < 1e-12
         assert np.array_equal(c[20, :20], c[0, :20]) and np.array_equal(c[:, 20], c[:, 0])
         if frame:
-            mu = np.fromfile(f"{tmp_path}/ch2d_gold.mu.{frame}.bin", dtype="<f8").reshape(20, 20)
+            mu = h.read(f"mu.{frame}")
             assert np.abs(mu - g["mu"][frame]).max() < 1e-12
+    # enable_hdf5 = false keeps the reference's raw binary storage
+    run(tmp_path, "ch2d_gold.i", "TensorOutputs/active=xdmf", "TensorOutputs/xdmf/enable_hdf5=false")
+    c = np.fromfile(f"{tmp_path}/ch2d_gold.c.3.bin", dtype="<f8").reshape(21, 21)
+    assert np.array_equal(c, h5lite.H5File(f"{tmp_path}/ch2d_gold.h5").read("c.3")) or np.abs(c[:20, :20] - g["c"][3]).max() < 1e-12
 
 
 def test_quasistatic_elasticity_input_matches_oracle(tmp_path):

@@ -55,11 +55,13 @@ def test_cahnhilliard_two_rank_slab_gold(tmp_path):
     import xml.etree.ElementTree as ET
     g = np.load(f"{G}/ch2d_slab_rank1_h5.npz")["c"]
     launch(tmp_path, 2, "cahnhilliard.i", 'TensorOutputs/active=xdmf2', "Domain/parallel_mode=FFT_SLAB", "Domain/device_names=cpu")
+    import h5lite
+    h1, h0 = h5lite.H5File(f"{tmp_path}/cahnhilliard.rank0001.h5"), h5lite.H5File(f"{tmp_path}/cahnhilliard.rank0000.h5")
+    assert h1.keys() == sorted(f"c.{f}" for f in range(11))
     for frame in range(11):
-        got = np.fromfile(f"{tmp_path}/cahnhilliard.rank0001.c.{frame}.bin", dtype=np.float64).reshape(20, 10)
-        assert np.abs(got - g[frame]).max() < 1e-13, frame
-        r0 = np.fromfile(f"{tmp_path}/cahnhilliard.rank0000.c.{frame}.bin", dtype=np.float64).reshape(20, 10)
-        assert np.array_equal(r0, got) or np.abs(r0 - got).max() < 1e-13      # identical random blocks stay identical
+        got = h1.read(f"c.{frame}")
+        assert got.shape == (20, 10) and np.abs(got - g[frame]).max() < 1e-13, frame
+        assert np.abs(h0.read(f"c.{frame}") - got).max() < 1e-13      # identical random blocks stay identical
     root = ET.parse(f"{tmp_path}/cahnhilliard.xmf").getroot()
     series = root.find("Domain").find("Grid")
     frames = series.findall("Grid")
@@ -69,7 +71,7 @@ def test_cahnhilliard_two_rank_slab_gold(tmp_path):
     assert subs[1].find("Topology").get("Dimensions") == "21 11"
     assert subs[1].find("Geometry").findall("DataItem")[0].text == "0 1.5"       # origin of rank 1's part: y = 10 * 0.15
     item = subs[1].find("Attribute").find("DataItem")
-    assert item.get("Dimensions") == "20 10" and item.text.endswith("cahnhilliard.rank0001.c.3.bin")
+    assert item.get("Dimensions") == "20 10" and item.get("Format") == "HDF" and item.text.endswith("cahnhilliard.rank0001.h5:/c.3")
     assert not os.path.exists(f"{tmp_path}/cahnhilliard.rank0001.xmf")
     # the CSV is rank 0's; its postprocessors are gathered over the ranks
     head, rows = csv(f"{tmp_path}/cahnhilliard_out.csv")

@@ -255,3 +255,53 @@ def test_every_spectral_object_type_of_the_reference_inputs_is_registered():
                     if typ not in registered and not typ.startswith("LBM") and typ not in OUT_OF_SCOPE_TYPES:
                         missing.setdefault(typ, f)
     assert not missing, missing
+
+
+def test_hdf5_writer_against_the_reader_that_reads_libhdf5_files(tmp_path):
+    """XDMFTensorOutput with enable_hdf5 = true stores every field as a one-chunk deflate-9 dataset like the reference's
+    addDataToHDF5 (src/tensor_outputs/XDMFTensorOutput.C:572-651).  The image has no libhdf5: host/shim/h5lite.C writes the
+    file structures itself and tests/h5lite.py reads them back - the same reader that parses the gold files libhdf5 wrote
+    (next test) - with the structure versions of those gold files."""
+    import numpy as np
+
+    import h5lite
+    r = subprocess.run([APP, "--xdmf-selftest", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    h = h5lite.H5File(tmp_path / "selftest_h5.h5")
+    assert h.keys() == ["c.0", "c.1", "disp_x.0", "disp_x.1", "disp_y.0", "disp_y.1", "mu.0", "mu.1"]
+    assert (h.leaf_k, h.internal_k) == (4, 16)
+    for name in h.keys():
+        want = np.fromfile(tmp_path / f"selftest_t.{name}.bin", dtype="<f8")      # the binary writer on the same fields
+        d = h.info(name)
+        assert d["dtype"] == "<f8" and d["layout_class"] == 2 and d["filters"] == [(1, (9,))] and d["chunk"][:-1] == d["shape"]
+        assert np.array_equal(h.read(name).ravel(), want)
+    assert h.info("c.0")["shape"] == (3, 4) and h.info("mu.0")["shape"] == (2, 3)
+    text = open(tmp_path / "selftest_h5.xmf").read()
+    assert f'<DataItem DataType="Float" Dimensions="2 3" Format="HDF">{tmp_path}/selftest_h5.h5:/mu.1</DataItem>' in text
+    # 300 float32 datasets: symbol table nodes of 8 entries under a two-level group B-tree, flushed while growing
+    m = h5lite.H5File(tmp_path / "selftest_many.h5")
+    assert len(m.keys()) == 300
+    for k in (0, 7, 150, 299):
+        a = m.read(f"field_{k}.0")
+        assert a.dtype == np.float32 and a.shape == (2, 3, 4)
+        assert np.array_equal(a.ravel(), k + 0.5 * np.arange(24, dtype=np.float32))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_h5lite_reader_parses_the_reference_gold_files():
+    """tests/h5lite.py on the files libhdf5 wrote for the reference's gold results: the datasets equal the fixtures extracted
+    earlier (tests/golden/make_golden.py), and their structure is what host/shim/h5lite.C reproduces."""
+    import numpy as np
+
+    import h5lite
+    g = np.load(f"{ROOT}/tests/golden/ch2d_slab_rank1_h5.npz")["c"]
+    h = h5lite.H5File(f"{REF}/test/tests/cahnhilliard/gold/cahnhilliard.rank0001.h5")
+    assert h.sb_version == 0 and (h.leaf_k, h.internal_k) == (4, 16)
+    for i in range(11):
+        assert np.array_equal(h.read(f"c.{i}"), g[i])
+    d = h.info("c.0")
+    assert (d["dataspace_version"], d["dtype_version"], d["fill_version"], d["filter_version"], d["layout_version"]) == (1, 1, 2, 1, 3)
+    assert d["filters"] == [(1, (9,))] and d["chunk"] == (20, 10, 8)
+    m = h5lite.H5File(f"{REF}/test/tests/mechanics/gold/mech3d.h5")
+    gm = np.load(f"{ROOT}/tests/golden/mech3d_h5.npz")
+    assert np.array_equal(m.read("sV.2"), gm["sV"][2].transpose(2, 1, 0))   # stored with transpose = true (x <-> z)
