@@ -151,7 +151,7 @@ def test_fused_slab_plan_through_the_host_solver(tmp_path):
     L = n * (8 * math.pi / 200)
     args = ["--allow-unused", f"Domain/nx={n}", f"Domain/ny={n}", f"Domain/nz={n}", f"Domain/xmax={L!r}", f"Domain/ymax={L!r}",
             f"Domain/zmax={L!r}", "Executioner/num_steps=2", "TensorComputes/Initialize/c/seed=0", "Domain/parallel_mode=FFT_SLAB",
-            "Problem/print_debug_output=true"]
+            "TensorSolver/substeps=25", "Problem/print_debug_output=true"]   # 2 x 25 substeps: AB1 start-up + steady AB2
     a, b = tmp_path / "fused", tmp_path / "generic"
     a.mkdir(), b.mkdir()
     outs = launch(a, 2, "cahnhilliard2.i", *args, dump=("c",))

@@ -10,8 +10,8 @@ for step in "$@"; do
   kind=${step%%:*}; arg=""; [[ "$step" == *:* ]] && arg=${step#*:}
   case $kind in
     tests)    timeout 1700 python -m pytest tests -m gpu -q --timeout 900 -x $arg 2>&1 | tail -40 > $O/${TAG}_pytest.log; tail -15 $O/${TAG}_pytest.log ;;
-    testsel)  timeout 1700 python -m pytest $arg -m gpu -q --timeout 900 2>&1 | tail -60 > $O/${TAG}_pytest.log; tail -25 $O/${TAG}_pytest.log ;;
-    testsall) timeout 1700 python -m pytest tests -m gpu -q --timeout 900 $arg 2>&1 | tail -60 > $O/${TAG}_pytest.log; tail -25 $O/${TAG}_pytest.log ;;
+    testsel)  timeout 1700 python -m pytest $arg -m gpu -q --timeout 900 --durations=15 2>&1 | tail -60 > $O/${TAG}_pytest.log; tail -25 $O/${TAG}_pytest.log ;;
+    testsall) timeout 1700 python -m pytest tests -m gpu -q --timeout 900 --durations=25 $arg 2>&1 | tail -80 > $O/${TAG}_pytest.log; tail -25 $O/${TAG}_pytest.log ;;
     smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -3 $O/${TAG}_smoke.log ;;
     bench)    if [ -z "$arg" ] || [ "$arg" == 1 ]; then
                 timeout 900 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
