@@ -165,6 +165,11 @@ def test_fused_slab_plan_through_the_host_solver(tmp_path):
         assert np.linalg.norm(ca - cb) / np.linalg.norm(cb) < 1e-10
 
 
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
 @pytest.mark.parametrize("nranks,mode", [(2, "FFT_SLAB"), (4, "FFT_PENCIL")])
 def test_mech3d_decomposed_matches_gold(tmp_path, nranks, mode):
     """test/tests/mechanics/mech3d.i (de Geus finite-strain mechanics: Newton + CG with the Green projection) on a
@@ -178,6 +183,10 @@ def test_mech3d_decomposed_matches_gold(tmp_path, nranks, mode):
     Nyquist wavevectors of x and z carry the opposite sign of the serial mode's; the Green projection q_i q_j / |q|^2 is
     odd in each component, and the solve differs from the serial gold at the 3e-6 level on this 16^3 grid (the
     transforms themselves are exact: tests/test_dist_gpu.py)."""
+    if mode == "FFT_PENCIL" and _gpus() < 4:
+        # ~40 CG iterations x 9 fields x two-stage exchanges = thousands of inter-process barriers; with four processes
+        # time-slicing one GPU that takes minutes.  Runs where every rank has its own GPU (profiles/r2*_8gpu logs).
+        pytest.skip("pencil-decomposed mechanics needs four GPUs to run in reasonable time")
     g = np.load(f"{G}/mech3d_h5.npz")
     launch(tmp_path, nranks, "mech3d.i", f"Domain/parallel_mode={mode}", "Executioner/num_steps=1", "TensorComputes/Postprocess/active=vonmises",
            "TensorOutputs/deformation_tensor/buffer=sV F", "TensorOutputs/deformation_tensor/output_mode=CELL CELL", dump=("F", "sV"))

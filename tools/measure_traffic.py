@@ -23,9 +23,10 @@ def main():
     n = 512
     out_csv = os.path.join(ROOT, "gpurun_out", "traffic_ncu.csv")
     os.makedirs(os.path.dirname(out_csv), exist_ok=True)
-    # pass_times.py: 1 AB1 + 3 AB2 substeps before anything is timed = 20 launches; take the next substep
+    # pass_times.py: 1 AB1 + 3 AB2 substeps before anything is timed = 20 launches of this library's kernels (the filter
+    # keeps torch's own kernels - checksums, fills - out of the count); take the next substep
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
-           "--print-units", "base", "-s", "20", "-c", "5", "--csv", "--log-file", out_csv,
+           "--print-units", "base", "-k", "regex:^k_", "-s", "20", "-c", "5", "--csv", "--log-file", out_csv,
            sys.executable, os.path.join(ROOT, "tools", "pass_times.py"), str(n)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     if r.returncode != 0:
@@ -47,6 +48,8 @@ def main():
     _, _, alg = algorithmic_bytes(n, 1)
     names = list(alg.keys())
     assert len(order) == len(names), (len(order), [per[k]["kernel"] for k in order])
+    expect = ["k_zfwd", "k_strided", "k_fused", "k_strided", "k_zinv"]
+    assert all(e in per[k]["kernel"] for e, k in zip(expect, order)), [per[k]["kernel"] for k in order]
     passes, kernels, detail = {}, {}, {}
     for nm, k in zip(names, order):
         d = per[k]
