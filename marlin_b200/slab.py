@@ -334,6 +334,36 @@ def bench(args, rank, world, metric):
     e2e_ms = float(t.item()) / e2e_steps
     clocks = sampler.stop() if sampler else None
 
+    # the same workload the way a reference input reaches it: every rank runs the host driver on the verbatim
+    # examples/cahn_hilliard/cahnhilliard2.i with [Domain] parallel_mode = FFT_SLAB (the ranks of the driver find each
+    # other through the torchrun environment, host/shim/comm.h); its AdamsBashforthMoulton builds the fused slab plan with
+    # the file's ParsedCompute nonlinearity compiled into the first pass.  Device-synchronised solve time of the last
+    # step per substep, max over ranks.
+    host_driver = None
+    if not getattr(args, "fast", False) and os.environ.get("MRL_BENCH_HOST_DRIVER", "1") != "0":
+        torch.cuda.synchronize()
+        dist.barrier()          # no peer is still pushing rows into this rank's staging buffers
+        plan.close()
+        del c, cbuf
+        torch.cuda.empty_cache()
+        try:
+            from bench import host_driver_bench
+            hd = host_driver_bench(n, substeps=50, steps=3, extra_args=["Domain/parallel_mode=FFT_SLAB"])
+            t = torch.tensor([hd["ms_per_substep_last_step"]], dtype=torch.float64, device="cuda")
+            ok = torch.tensor([1.0 if hd["fused_plan"] else 0.0], dtype=torch.float64, device="cuda")
+        except Exception as exn:
+            hd = {"error": str(exn)[-300:]}
+            t = torch.tensor([float("nan")], dtype=torch.float64, device="cuda")
+            ok = torch.tensor([0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if "error" not in hd:
+            hd["ms_per_substep_last_step"] = round(float(t.item()), 4)
+            hd["fused_plan"] = bool(ok.item())
+            hd["command"] = f"{world} x (" + hd["command"] + " Domain/parallel_mode=FFT_SLAB), one process per GPU"
+            hd["ratio_to_harness"] = round(float(t.item()) / (total_ms / args.steps), 4)
+        host_driver = hd
+
     if rank == 0:
         ms = total_ms / args.steps
         s_r, s_c, _ = algorithmic_bytes(n, 1)
@@ -373,6 +403,7 @@ def bench(args, rank, world, metric):
             "forward_chunks": os.environ.get("MRL_SLAB_CHUNKS", "4 (default)"),
             "cpu_baseline": None,
             "parity": parity,
+            "host_driver": host_driver,
         }
         print(json.dumps(line), flush=True)
     plan.close()
