@@ -139,15 +139,53 @@ protected:
 };
 
 // include/tensor_solver/IterativeTensorSolverInterface.h: what TensorSolveIterationAdaptiveDT reads
+// include/tensor_predictor/TensorPredictor.h, src/tensor_predictor/TensorPredictor.C:14-39: forward-predicts a solver
+// output buffer from its old states ([TensorSolver/Predictors/*])
+class TensorPredictor : public MooseObject {
+public:
+  static InputParameters validParams();
+  explicit TensorPredictor(const InputParameters &parameters);
+  virtual void computeBuffer() = 0;
+  virtual void gridChanged() {}
+
+protected:
+  TensorProblem &_tensor_problem;
+  const DomainAction &_domain;
+  const TensorOutputBufferName _u_name;
+  marlin::Tensor &_u;
+  const std::vector<marlin::Tensor> &_u_old;
+};
+
+// src/tensor_predictor/LinearTensorPredictor.C:11-38: u += scale * (u_old[0] - u_old[1])
+class LinearTensorPredictor : public TensorPredictor {
+public:
+  static InputParameters validParams();
+  explicit LinearTensorPredictor(const InputParameters &parameters);
+  void computeBuffer() override;
+
+protected:
+  const Real _scale;
+  ExprKernel _extrapolate;
+};
+
 class IterativeTensorSolverInterface {
 public:
   virtual ~IterativeTensorSolverInterface() = default;
   const unsigned int &getIterations() const { return _iterations; }
   bool isConverged() const { return _is_converged; }
+  // include/tensor_solver/IterativeTensorSolverInterface.h:27-32.  The reference's AddTensorPredictorAction builds the
+  // predictor objects but leaves `solver.addPredictor()` commented out (src/actions/AddTensorPredictorAction.C:41), so
+  // its applyPredictors() loops over an empty list; the stand-alone driver registers them only when asked to
+  // ([TensorSolver] apply_predictors = true, an option of this build).
+  void addPredictor(std::shared_ptr<TensorPredictor> p) { _predictors.push_back(std::move(p)); }
+  void applyPredictors() {
+    for (const auto &pred : _predictors) pred->computeBuffer();
+  }
 
 protected:
   unsigned int _iterations = 0;
   bool _is_converged = true;
+  std::vector<std::shared_ptr<TensorPredictor>> _predictors;
 };
 
 // src/tensor_solver/SecantSolver.C: implicit Euler, secant iteration per wavevector

@@ -78,6 +78,7 @@ private:
   std::ofstream _csv;
   std::vector<std::shared_ptr<TensorPostprocessor>> _csv_pps;
   std::vector<std::shared_ptr<TensorVectorPostprocessor>> _vpps;  // [VectorPostprocessors]
+  std::vector<std::shared_ptr<TensorPredictor>> _predictors;      // [TensorSolver/Predictors/*]
   void runVectorPostprocessors(int flag, bool csv, const std::string &file_base);
 };
 
@@ -210,7 +211,7 @@ void MarlinApp::buildObjects() {
     const hit::Node *tf = ts->field("type");
     if (!tf) mooseError("[TensorSolver]: missing 'type'");
     if (!Factory::instance().isRegistered(tf->value)) mooseError(_opt.input, ":", ts->line, ": A '", tf->value, "' is not a registered object (block TensorSolver)");
-    InputParameters p = fill(tf->value, *ts, "TensorSolver");
+    InputParameters p = fill(tf->value, *ts, "TensorSolver", {"apply_predictors"});
     if (!p.isParamValid("root_compute")) {
       // CreateTensorSolverAction.C:43-60
       std::vector<TensorComputeName> names;
@@ -227,8 +228,29 @@ void MarlinApp::buildObjects() {
     }
     auto solver = std::dynamic_pointer_cast<TensorSolver>(Factory::instance().create(tf->value, p));
     if (!solver) mooseError("[TensorSolver]: '", tf->value, "' is not a TensorSolver");
-    for (hit::Node *s : ts->sections()) _skipped.push_back("TensorSolver/" + s->name);
     _problem->setSolver(solver);
+    // [TensorSolver/Predictors/*] (AddTensorPredictorAction, src/actions/AddTensorPredictorAction.C:29-42: needs an
+    // iterative solver; the objects are built - which registers the old states they read - and, as in the reference,
+    // handed to the solver only on request)
+    for (hit::Node *s : ts->sections()) {
+      if (s->name != "Predictors") {
+        _skipped.push_back("TensorSolver/" + s->name);
+        continue;
+      }
+      auto *iterative = dynamic_cast<IterativeTensorSolverInterface *>(solver.get());
+      if (!iterative) mooseError("[TensorSolver/Predictors]: the solver '", tf->value, "' is not an iterative tensor solver");
+      bool apply = false;
+      if (const hit::Node *f = ts->field("apply_predictors")) apply = shim_detail::Conv<bool>::from(f->value, "TensorSolver/apply_predictors");
+      for (hit::Node *pb : s->sections()) {
+        const hit::Node *pt = pb->field("type");
+        if (!pt) mooseError(pb->fullpath(), ": missing 'type'");
+        if (!Factory::instance().isRegistered(pt->value)) mooseError(_opt.input, ":", pb->line, ": A '", pt->value, "' is not a registered object (block ", pb->fullpath(), ")");
+        auto pred = std::dynamic_pointer_cast<TensorPredictor>(Factory::instance().create(pt->value, fill(pt->value, *pb, pb->name)));
+        if (!pred) mooseError(pb->fullpath(), ": '", pt->value, "' is not a TensorPredictor");
+        if (apply) iterative->addPredictor(pred);
+        _predictors.push_back(pred);
+      }
+    }
   }
   // [TensorOutputs] (AddTensorOutputAction): XDMFTensorOutput; other types are reported and skipped
   if (const hit::Node *to = _root->find("TensorOutputs"))
@@ -529,6 +551,7 @@ int MarlinApp::run() {
   transient();
   // tear down in dependency order: objects -> buffers -> pool -> context
   _csv_pps.clear();
+  _predictors.clear();
   _problem.reset();
   _domain.reset();
   return 0;

@@ -786,6 +786,9 @@ void SecantSolver::substep() {
     if (_verbose) std::cerr << "|R0|=" << R0norm[i] << std::endl;
   }
 
+  // forward predict (on solver outputs), SecantSolver.C:99-100
+  applyPredictors();
+
   bool all_converged = false;
   for (_iterations = 0; _iterations < _max_iterations; ++_iterations) {
     _compute->computeBuffer();
@@ -1017,4 +1020,46 @@ void ETDRK4Solver::substep() {
   for (std::size_t i = 0; i < n; ++i) stage[i] = run(full, {&linear[i], &ubar_n[i], &N3[i]});
   evaluate_nonlinear(stage, N4);
   for (std::size_t i = 0; i < n; ++i) _variables[i]._buffer = _domain.ifft(run(fin, {&linear[i], &ubar_n[i], &N1[i], &N2[i], &N3[i], &N4[i]}));
+}
+
+// ================================================================================== TensorPredictor
+InputParameters TensorPredictor::validParams() {
+  InputParameters params = MooseObject::validParams();
+  params.registerBase("TensorPredictor");
+  params.addPrivateParam<TensorProblem *>("_tensor_problem", nullptr);
+  params.addPrivateParam<const DomainAction *>("_domain", nullptr);
+  params.addClassDescription("TensorPredictor object.");
+  params.addRequiredParam<TensorOutputBufferName>("buffer", "The buffer this compute is forward predicting");
+  params.addParam<unsigned int>("history_size", 1, "How many old states to use (determines time integration order).");
+  return params;
+}
+
+TensorPredictor::TensorPredictor(const InputParameters &parameters)
+  : MooseObject(parameters),
+    _tensor_problem(*getCheckedPointerParam<TensorProblem>("_tensor_problem")),
+    _domain(_tensor_problem.domain()),
+    _u_name(getParam<TensorOutputBufferName>("buffer")),
+    _u(_tensor_problem.getBuffer(_u_name)),
+    _u_old(_tensor_problem.getBufferOld(_u_name, getParam<unsigned int>("history_size"))) {}
+
+registerMooseObject("MarlinApp", LinearTensorPredictor);
+
+InputParameters LinearTensorPredictor::validParams() {
+  InputParameters params = TensorPredictor::validParams();
+  params.addParam<Real>("scale", 1.0, "The scale factor for the predictor (can range from 0 to 1)");
+  params.set<unsigned int>("history_size", 2);
+  return params;
+}
+
+LinearTensorPredictor::LinearTensorPredictor(const InputParameters &parameters) : TensorPredictor(parameters), _scale(getParam<Real>("scale")) {
+  // one generated kernel for u + (uo0 - uo1) [* scale] (LinearTensorPredictor.C:31-36)
+  if (_scale == 1.0)
+    _extrapolate.configure("u + (uo0 - uo1)", {"u", "uo0", "uo1"}, {}, {}, {}, false, MRL_EXPAND_NONE);
+  else
+    _extrapolate.configure("u + (uo0 - uo1) * scale", {"u", "uo0", "uo1"}, {}, {"scale"}, {_scale}, false, MRL_EXPAND_NONE);
+}
+
+void LinearTensorPredictor::computeBuffer() {
+  if (_u_old.size() > 1 && _u_old[0].defined() && _u_old[1].defined() && _u.defined())
+    _u = _extrapolate.eval(_domain, {&_u, &_u_old[0], &_u_old[1]}, 0.0);
 }

@@ -211,6 +211,25 @@ def test_swift_hohenberg_secant_input_matches_hdf5_gold(tmp_path):
     assert f"dt = {1.4 ** 9:.8g}"[:12] in r.stderr            # the step grew by growth_factor every step
 
 
+def test_linear_tensor_predictor(tmp_path):
+    """[TensorSolver/Predictors/*] with LinearTensorPredictor (src/tensor_predictor/LinearTensorPredictor.C:26-38).  As in
+    the reference - whose AddTensorPredictorAction builds the object but never hands it to the solver
+    (src/actions/AddTensorPredictorAction.C:41) - the block alone changes nothing: the run reproduces the gold of the input
+    without it.  With apply_predictors = true the secant iteration starts from u + (u_old0 - u_old1) and must reach the
+    same implicit-Euler solution to within the solver's tolerance."""
+    g = np.load(f"{G}/rotating_grain_secant_h5.npz")["psi"]
+    r0 = run(tmp_path, "secant_predictor.i", "Executioner/num_steps=4", dump=("psi",))
+    assert np.abs(field(tmp_path, "psi", (40, 40)) - g[4]).max() < 1e-10
+    r1 = run(tmp_path, "secant_predictor.i", "Executioner/num_steps=4", "TensorSolver/apply_predictors=true", dump=("psi",))
+    psi = field(tmp_path, "psi", (40, 40))
+    d = np.abs(psi - g[4]).max()
+    assert 0 < d < 1e-6, d          # another starting point, the same fixed point
+    # an object that is not a predictor, or a solver that cannot take one, is an error
+    r = subprocess.run([APP, "-i", f"{INP}/secant_predictor.i", "--compute-device=cuda", "TensorSolver/type=AdamsBashforthMoulton"],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "not an iterative tensor solver" in r.stderr
+
+
 def test_kks_no_flux_input_matches_gold(tmp_path):
     """test/tests/kks/KKS_no_flux_bc.i -> gold KKS_no_flux_bc.h5 (abs_tol 1e-10) and KKS_no_flux_bc_out.csv:
     ReciprocalMatDiffusion, ReciprocalAllenCahn, mask from a ParsedFunction on a domain with a non-zero
