@@ -445,10 +445,34 @@ template <class T, class C, int NG> static cudaError_t mech_tangent_go(const Lau
   k<<<grid, NG * 9 * C::TP, smem, lc.stream>>>(io, tw);
   return cudaGetLastError();
 }
+// bulk-copy staged variant: one group per CTA, two input stages of 29 rows
+template <class T, class C> static cudaError_t mech_tangent_tma_go(const LaunchCtx &lc, const MechTangentIO<T> &io, const cx<T> *tw) {
+  constexpr int NP = C::N + (C::N >> 3) + 1;
+  constexpr size_t smem = (size_t)(2 * 29 + 9 * 2) * C::N * sizeof(T) + (size_t)(9 * NP) * sizeof(cx<T>) + 2 * 8 + 128;
+  static_assert(smem <= kSmemBudget, "mech_tangent_zfwd_tma: shared memory budget");
+  if (io.nrows % 2 || io.n != io.nrows * C::N || (C::N * sizeof(T)) % 16) return cudaErrorNotSupported;
+  for (const void *q : {(const void *)io.F, (const void *)io.K, (const void *)io.mu, (const void *)io.p, (const void *)io.r})
+    if ((unsigned long long)q & 15ull) return cudaErrorNotSupported;
+  if ((io.n * sizeof(T)) % 16) return cudaErrorNotSupported;
+  auto k = k_mech_tangent_zfwd_tma<T, C>;
+  int per_sm = 0;
+  cudaError_t e = kernel_prep((const void *)k, 9 * C::TP, smem, &per_sm);
+  if (e != cudaSuccess) return e;
+  const long long nwork = io.nrows / 2;
+  const int grid = (int)(nwork < lc.sm_count ? nwork : lc.sm_count);
+  k<<<grid, 9 * C::TP, smem, lc.stream>>>(io, tw);
+  return cudaGetLastError();
+}
 template <class T> cudaError_t launch_mech_tangent_zfwd(const LaunchCtx &lc, const MechTangentIO<T> &io, const cx<T> *tw, int n) {
   if (!tma_enabled() || env_int("MRL_MECH_TANGENT_FUSED", 1) == 0) return cudaErrorNotSupported;
+  static int variant = env_int("MRL_MECH_TANGENT_V", 0);  // 0: bulk-copy staged inputs where they fit, 1: loads to registers
   switch (n) {
-    case 256: return mech_tangent_go<T, FFTCfg<256, 32, 8, 8, 4>, 2>(lc, io, tw);
+    case 256:
+      if (variant == 0) {
+        cudaError_t e = mech_tangent_tma_go<T, FFTCfg<256, 32, 8, 8, 4>>(lc, io, tw);
+        if (e != cudaErrorNotSupported) return e;
+      }
+      return mech_tangent_go<T, FFTCfg<256, 32, 8, 8, 4>, 2>(lc, io, tw);
     case 512: return mech_tangent_go<T, FFTCfg<512, 64, 8, 8, 8>, 1>(lc, io, tw);
     default: return cudaErrorNotSupported;
   }

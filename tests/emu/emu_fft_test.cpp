@@ -355,7 +355,7 @@ template <class C, int PPB, int NG, int NS> static void test_zinv_tma(const char
 }
 
 // mechanics: first pass with the tangent K4(F) : p (and the direction update p = r + beta p) fused into its load
-template <class C, int NG> static void test_mech_tangent(const char *name, int nrows, int grid, bool update) {
+template <class C, int NG> static void test_mech_tangent(const char *name, int nrows, int grid, bool update, bool staged = false) {
   constexpr int n = C::N, nc = n / 2 + 1, NP = n + n / 8 + 1, ncp = (nc + 7) & ~7;
   const long long nv = (long long)nrows * n;
   std::mt19937_64 rng(23);
@@ -398,6 +398,10 @@ template <class C, int NG> static void test_mech_tangent(const char *name, int n
   io.ncp = ncp;
   const cx<double> *twp = tw.data();
   size_t smem = (size_t)NG * 9 * 2 * n * 8 + (size_t)NG * 9 * NP * 16 + 128;
+  if (staged) {
+    smem = (size_t)(2 * 29 + 18) * n * 8 + (size_t)9 * NP * 16 + 16 + 128;
+    emu::launch(dim3(grid), dim3(9 * C::TP), smem, [=] { k_mech_tangent_zfwd_tma<double, C>(io, twp); }, 64 * 1024);
+  } else
   emu::launch(dim3(grid), dim3(NG * 9 * C::TP), smem, [=] { k_mech_tangent_zfwd<double, C, NG>(io, twp); }, 64 * 1024);
   double err = 0;
   for (size_t i = 0; i < pn.size(); ++i) err = std::max(err, std::fabs(pn[i] - P[i]));
@@ -887,6 +891,8 @@ static void tma_tests() {
   test_mech_tangent<FFTCfg<256, 32, 8, 8, 4>, 2>("mech tangent + zfwd 256 NG2 rows=10 update", 10, 2, true);
   test_mech_tangent<FFTCfg<256, 32, 8, 8, 4>, 2>("mech tangent + zfwd 256 NG2 rows=6", 6, 1, false);
   test_mech_tangent<FFTCfg<512, 64, 8, 8, 8>, 1>("mech tangent + zfwd 512 NG1 rows=4 update", 4, 1, true);
+  test_mech_tangent<FFTCfg<256, 32, 8, 8, 4>, 1>("mech tangent + zfwd 256 bulk-staged rows=14 update g2", 14, 2, true, true);
+  test_mech_tangent<FFTCfg<256, 32, 8, 8, 4>, 1>("mech tangent + zfwd 256 bulk-staged rows=6 g1", 6, 1, false, true);
 }
 
 int main() {
