@@ -55,10 +55,11 @@ static cudaError_t make_map3(CUtensorMap *tm, const void *base, unsigned long lo
 // Slab staging [d3 = ranks][d2 = x][d1 = y_local][d0]: one box = all ranks x all local rows of one x
 template <class T>
 static cudaError_t make_map4(CUtensorMap *tm, const void *base, unsigned long long d0, unsigned long long d1,
-                             unsigned long long d2, unsigned long long d3, unsigned b0) {
+                             unsigned long long d2, unsigned long long d3, unsigned b0, unsigned long long d2_full = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return cudaErrorNotSupported;
-  const unsigned long long s1 = d0 * sizeof(T), s2 = s1 * d1, s3 = s2 * d2;
+  // d2_full: the x extent of the array when the map covers an x sub-range of it (the rank blocks keep their distance)
+  const unsigned long long s1 = d0 * sizeof(T), s2 = s1 * d1, s3 = s2 * (d2_full ? d2_full : d2);
   if (((unsigned long long)base & 15ull) || (s1 & 15ull) || d1 > 256 || d3 > 256) return cudaErrorNotSupported;
   cuuint64_t dims[4] = {d0, d1, d2, d3};
   cuuint64_t strides[3] = {s1, s2, s3};
@@ -196,6 +197,7 @@ static cudaError_t fused_tma_go1(const LaunchCtx &lc, const FusedIO<T> &io0, con
   io.scale = io0.scale;
   io.slab = io0.slab;
   io.nouter = io0.slab ? io0.nouter : 1;
+  io.nouter_full = io0.slab == 1 && io0.nouter_full ? io0.nouter_full : io.nouter;
   io.nyl = io0.nyl;
   io.peer_tab = io0.slab ? io0.peer_tab : nullptr;
   io.peer_x0 = io0.peer_x0;
@@ -233,9 +235,9 @@ static cudaError_t fused_tma_go1(const LaunchCtx &lc, const FusedIO<T> &io0, con
     if (e == cudaSuccess) e = make_mapn<T>(&tmG, io0.inG, 5, dims, st, box);
     if (e == cudaSuccess) e = make_map4<T>(&tmO, up0.nold > 0 ? (const void *)up0.Nold[0] : io0.ring_old, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
   } else if (io.slab) {
-    e = make_map4<T>(&tmC, io0.inC, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
-    if (e == cudaSuccess) e = make_map4<T>(&tmG, io0.inG, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
-    if (e == cudaSuccess) e = make_map4<T>(&tmO, oldp, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK);
+    e = make_map4<T>(&tmC, io0.inC, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK, io0.nouter_full);
+    if (e == cudaSuccess) e = make_map4<T>(&tmG, io0.inG, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK, io0.nouter_full);
+    if (e == cudaSuccess) e = make_map4<T>(&tmO, oldp, 2ull * io.ncols, io.nyl, io.nouter, io0.nranks, 2 * TK, io0.nouter_full);
   } else {
     e = make_map3<T>(&tmC, io0.inC, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);
     if (e == cudaSuccess) e = make_map3<T>(&tmG, io0.inG, 2ull * io.ncols, io.n, 1, rowb, rowb * io.n, 2 * TK, boxr);

@@ -1173,10 +1173,16 @@ extern "C" int mrl_slab_plan_destroy(mrl_slab_plan *p) {
   cudaFree(p->peer_send_tab);
   cudaFree(p->flag1_tab);
   cudaFree(p->flag2_tab);
+  for (auto st : p->s_copy) {
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  }
+  for (auto e : p->ev_copy) cudaEventDestroy(e);
   if (p->owns) {
     cudaFree(p->send_fwd);
     cudaFree(p->recv_fwd);
     cudaFree(p->ret_stage);
+    if (p->copy) cudaFree(p->send_bwd);
   }
   delete p;
   return MRL_OK;
@@ -1201,6 +1207,30 @@ extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc 
   const int kb = ncp / wx;
   const size_t fbytes = (size_t)ctx->n[0] * ctx->nyl * ncp * esz;
   void *sf = nullptr, *rf = nullptr, *rs = nullptr;
+  const char *xm = getenv("MRL_SLAB_EXCHANGE");
+  if (!xm || strcmp(xm, "store") != 0) {
+    // exchanges by the copy engines on the plain staged layouts (the default; MRL_SLAB_EXCHANGE=store selects the
+    // exchanges fused into the passes as bulk stores from shared memory)
+    const size_t flag_off = align256(2 * fbytes);
+    cudaError_t e = cudaMalloc(&sf, 2 * fbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&rf, flag_off + 256 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&rs, fbytes);
+    if (e == cudaSuccess) e = cudaMemset((char *)rf + flag_off, 0, 256 * sizeof(unsigned long long));
+    int rc = e == cudaSuccess ? mrl_slab_plan_create(ctx, d, sf, rf, rs, out) : mrl_fail(MRL_ERR_CUDA, "slab plan allocation failed: %s", cudaGetErrorString(e));
+    if (rc) {
+      cudaFree(sf);
+      cudaFree(rf);
+      cudaFree(rs);
+      return rc;
+    }
+    mrl_slab_plan *p = *out;
+    p->owns = true;
+    p->copy = true;
+    p->flag_off = (long long)flag_off;
+    if (const char *v = getenv("MRL_SLAB_CHUNKS")) p->chunks = atoi(v) > 0 ? atoi(v) : 1;
+    if (const char *v = getenv("MRL_SLAB_YCHUNKS")) p->y_chunks = atoi(v) > 0 ? atoi(v) : 1;
+    return MRL_OK;
+  }
   // behind the spectra recv_fwd carries the barrier flags (one 8-byte slot per rank) and the arrival counters
   // counters1 / counters2 [nranks][kb] of the forward / return exchange
   const size_t flag_off = align256(2 * fbytes), c1_off = flag_off + 256 * sizeof(unsigned long long);
@@ -1247,7 +1277,7 @@ extern "C" int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc 
 }
 
 extern "C" int mrl_slab_barrier(mrl_slab_plan *p) {
-  if (!p || !p->peer) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_barrier: needs a peer-mode plan with imported handles");
+  if (!p || !(p->peer || (p->copy && p->peer_recv_tab))) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_barrier: needs a peer-mode plan with imported handles");
   if (p->sync_flags) return MRL_OK;  // the phases synchronise through the arrival counters
   if (p->ctx->nranks > 32) return mrl_fail(MRL_ERR_UNSUPPORTED, "mrl_slab_barrier: at most 32 ranks");
   CK(cudaSetDevice(p->ctx->device));
@@ -1261,7 +1291,7 @@ extern "C" int mrl_slab_ipc_export(mrl_slab_plan *p, void *handles) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   CK(cudaSetDevice(p->ctx->device));
   cudaIpcMemHandle_t h[2];
-  CK(cudaIpcGetMemHandle(&h[0], p->ret_stage));
+  CK(cudaIpcGetMemHandle(&h[0], p->copy ? p->send_fwd : p->ret_stage));  // where the return exchange lands
   CK(cudaIpcGetMemHandle(&h[1], p->recv_fwd));
   memcpy(handles, h, sizeof h);
   return MRL_OK;
@@ -1276,7 +1306,7 @@ extern "C" int mrl_slab_ipc_import(mrl_slab_plan *p, const void *all) {
   const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all;
   for (int s = 0; s < P; ++s) {
     if (s == ctx->rank) {
-      sendp[s] = (unsigned long long)p->ret_stage;
+      sendp[s] = (unsigned long long)(p->copy ? p->send_fwd : p->ret_stage);
       recvp[s] = (unsigned long long)p->recv_fwd;
     } else {
       void *a = nullptr, *b = nullptr;
@@ -1299,6 +1329,19 @@ extern "C" int mrl_slab_ipc_import(mrl_slab_plan *p, const void *all) {
   CK(cudaMemcpy(p->peer_recv_tab, recvp.data(), tb, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->flag1_tab, f1.data(), tb, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->flag2_tab, f2.data(), tb, cudaMemcpyHostToDevice));
+  if (p->copy) {
+    for (int s = 0; s < P; ++s) {
+      p->h_peer_ret.push_back((char *)sendp[s]);
+      p->h_peer_recv.push_back((char *)recvp[s]);
+      cudaStream_t st;
+      cudaEvent_t ev;
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      p->s_copy.push_back(st);
+      p->ev_copy.push_back(ev);
+    }
+    return MRL_OK;  // the passes stay the staged-layout ones: p->peer remains false
+  }
   p->peer = true;
   return MRL_OK;
 }
@@ -1416,6 +1459,56 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
   if (rc) return rc;
   NonlinDesc nlz{0, {d.nonlin_params[0], d.nonlin_params[1], d.nonlin_params[2], 0}};
   const int C = p->chunks, nyl = ctx->nyl;
+  if (p->copy) {
+    if (p->h_peer_recv.empty()) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_forward: peers' buffers not imported (mrl_slab_ipc_import)");
+    // y-chunk by y-chunk: z pass, x pass in place (both local), then the copy engines carry x-block s of the chunk to
+    // rank s while the next chunk is being transformed
+    const int P = ctx->nranks, me = ctx->rank, nxl = ctx->nxl;
+    const int nch = (C > 1 && nyl % C == 0 && (nyl / C) % 8 == 0) ? C : 1, ych = nyl / nch;
+    if ((rc = slab_aux_init(p, nch))) return rc;
+    const size_t esz = sizeof(cx<T>), rowb = (size_t)nyl * p->ncp * esz;
+    const void *twx;
+    if ((rc = ctx->twiddles(ctx->n[0], &twx))) return rc;
+    for (int i = 0; i < nch; ++i) {
+      if (d.nonlin_kind == MRL_NONLIN_EXPR) {
+        const int rowmap[3] = {nch > 1 ? ych : 0, nyl, i * ych};
+        if ((rc = mrl_expr_launch_zfwd_rows(ctx, d.nonlin_expr, d.nonlin_var, d.nonlin_inputs_dev, 0.0, c, d.g_out_real_dev, A, A + p->field,
+                                            (long long)ctx->n[0] * ych, nl, p->ncp, rowmap, ctx->stream, ctx->sm_count)))
+          return rc;
+      } else {
+        ctx->launches++;
+        CK(launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ych, nl, p->ncp, nlz,
+                                     (const cx<T> *)twl, nch > 1 ? RowMap{ych, nyl, i * ych} : RowMap{0, 0, 0}));
+      }
+      StridedIO<T> sio;
+      memset(&sio, 0, sizeof sio);
+      for (int f = 0; f < 2; ++f) sio.in[f] = sio.out[f] = A + f * p->field + (long long)i * ych * p->ncp;
+      sio.nfields = 2;
+      sio.n = ctx->n[0];
+      sio.ncols = ych * p->ncp;
+      sio.nouter = 1;
+      sio.pitch = (long long)nyl * p->ncp;
+      sio.outer_stride = (long long)sio.n * sio.pitch;
+      sio.scale = T(1);
+      ctx->launches++;
+      CK(launch_strided_tma<T>(ctx->lc(), sio, (const cx<T> *)twx, sio.n));
+      CK(cudaEventRecord(p->ev_chunk[i], ctx->stream));
+      for (int k = 0; k < P; ++k) {
+        const int s = (me + 1 + k) % P;  // the own block last
+        CK(cudaStreamWaitEvent(p->s_copy[s], p->ev_chunk[i], 0));
+        for (int f = 0; f < 2; ++f) {
+          const char *src = (const char *)(A + f * p->field + ((long long)s * nxl * nyl + (long long)i * ych) * p->ncp);
+          char *dst = p->h_peer_recv[s] + ((size_t)f * p->field + ((size_t)me * nxl * nyl + (size_t)i * ych) * p->ncp) * esz;
+          CK(cudaMemcpy2DAsync(dst, rowb, src, rowb, (size_t)ych * p->ncp * esz, (size_t)nxl, cudaMemcpyDefault, p->s_copy[s]));
+        }
+      }
+    }
+    for (int s = 0; s < P; ++s) {
+      CK(cudaEventRecord(p->ev_copy[s], p->s_copy[s]));
+      CK(cudaStreamWaitEvent(ctx->stream, p->ev_copy[s], 0));
+    }
+    return MRL_OK;
+  }
   if (p->peer) p->n_forward++;
   if (C > 1 && p->peer && nyl % C == 0 && (nyl / C) % 8 == 0) {
     // z pass of chunk i+1 on the main stream while the x pass of chunk i pushes its rows over NVLink
@@ -1530,6 +1623,47 @@ template <class T> static int slab_update_impl(mrl_slab_plan *p, double dt, cons
     if ((rc = slab_xinv_peer<T>(p, LaunchCtx{p->s_aux, p->inv_ctas}))) return rc;
     CK(cudaEventRecord(p->ev_done, p->s_aux));
     p->inverse_issued = true;
+    return MRL_OK;
+  }
+  if (p->copy) {
+    // the fused y pass in x-chunks; behind every chunk the copy engines carry the y-block of rank s back to rank s (it
+    // lands at x = x0 .. of the array its inverse x pass transforms), while the next chunk is being computed
+    if (p->h_peer_ret.empty()) return mrl_fail(MRL_ERR_INVALID, "mrl_slab_update: peers' buffers not imported (mrl_slab_ipc_import)");
+    const int P = ctx->nranks, me = ctx->rank, nxl = ctx->nxl, nyl = ctx->nyl;
+    const int nch = (p->y_chunks > 1 && nxl % p->y_chunks == 0) ? p->y_chunks : 1, xch = nxl / nch;
+    if ((rc = slab_aux_init(p, nch))) return rc;
+    const size_t esz = sizeof(cx<T>);
+    const long long plane = (long long)nyl * p->ncp;  // elements of one x layer of one rank block
+    const FusedIO<T> io_all = io;
+    const SpectralUpdate<T> up_all = up;
+    for (int i = 0; i < nch; ++i) {
+      const long long sh = (long long)i * xch * plane;
+      FusedIO<T> ioc = io_all;
+      SpectralUpdate<T> upc = up_all;
+      ioc.inC = io_all.inC + sh;
+      ioc.inG = io_all.inG + sh;
+      ioc.outU = io_all.outU + sh;
+      ioc.nouter = xch;
+      ioc.nouter_full = nxl;
+      upc.x0 = up_all.x0 + i * xch;
+      if (upc.Nout) upc.Nout = up_all.Nout + sh;
+      for (int k = 0; k < 4; ++k)
+        if (upc.Nold[k]) upc.Nold[k] = up_all.Nold[k] + sh;
+      ctx->launches++;
+      CK(launch_fused_tma<T>(ctx->lc(), ioc, upc, (const cx<T> *)tw, ioc.n));
+      CK(cudaEventRecord(p->ev_chunk[i], ctx->stream));
+      for (int k = 0; k < P; ++k) {
+        const int s = (me + 1 + k) % P;
+        CK(cudaStreamWaitEvent(p->s_copy[s], p->ev_chunk[i], 0));
+        const char *src = (const char *)((const cx<T> *)p->send_bwd + ((long long)s * nxl + (long long)i * xch) * plane);
+        char *dst = p->h_peer_ret[s] + (size_t)(((long long)me * nxl + (long long)i * xch) * plane) * esz;
+        CK(cudaMemcpyAsync(dst, src, (size_t)xch * plane * esz, cudaMemcpyDefault, p->s_copy[s]));
+      }
+    }
+    for (int s = 0; s < P; ++s) {
+      CK(cudaEventRecord(p->ev_copy[s], p->s_copy[s]));
+      CK(cudaStreamWaitEvent(ctx->stream, p->ev_copy[s], 0));
+    }
     return MRL_OK;
   }
   ctx->launches++;

@@ -422,6 +422,9 @@ template <class T> struct FusedIO {
   unsigned long long flag_expect;
   const unsigned long long *flag_tab;
   const void *ring_old;  // slab == 2: base the tensor map of the newest old nonlinear term is built on
+  // slab == 1: the pass covers the x sub-range [o0, o0 + nouter) of arrays whose x extent is nouter_full (0: the whole
+  // array); the caller shifts every base pointer by o0 * nyl * pitch elements
+  int nouter_full;
 };
 
 template <class T, class C, int TK>

@@ -161,6 +161,7 @@ template <class T> struct FusedTmaIO {
   long long pitch;
   T scale;
   int slab, nouter, nyl;
+  int nouter_full;                     // x extent of the staged arrays (= nouter unless the pass covers an x sub-range)
   const unsigned long long *peer_tab;  // slab: store the result rows into the owning ranks' arrays
   int peer_x0;
   // slab == 2 (mrl_passes_slab.cuh): variable / nonlinearity tiles through 5-D maps over the blocked staging R, result rows
@@ -174,7 +175,7 @@ template <class T> struct FusedTmaIO {
   MRL_DI long long row_off(int o, int row) const {
     if (!slab) return (long long)row * pitch;
     const int s = row / nyl, yl = row - s * nyl;
-    return (((long long)s * nouter + o) * nyl + yl) * pitch;
+    return (((long long)s * nouter_full + o) * nyl + yl) * pitch;
   }
 };
 

@@ -382,7 +382,9 @@ def bench(args, rank, world, metric):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload(n),
                        "impl_detail": f"slab-decomposed (y real / x reciprocal) over {world} GPUs, half spectrum on the wire, "
-                                      + (f"all-to-all fused into the passes (bulk stores from shared memory into peer HBM over NVLink), "
+                                      + (("exchanges by the copy engines (peer-to-peer copies over NVLink, y-chunk by y-chunk behind the passes), "
+                                          if os.environ.get("MRL_SLAB_EXCHANGE", "copy") != "store" else
+                                          "all-to-all fused into the passes (bulk stores from shared memory into peer HBM over NVLink), ")
                                          + (f"per-column-block arrival counters, inverse x pass on {os.environ.get('MRL_SLAB_INV_CTAS', '0')} SMs beside the fused y pass"
                                             if plan.sync == "flags" else f"{plan.barrier_kind} barrier between the phases") if mode == "peer"
                                          else "NCCL all-to-all between the phases"),

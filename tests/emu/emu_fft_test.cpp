@@ -251,7 +251,7 @@ template <class C, int TK, int NG, int NS> static void run_strided_tma(StridedIO
 template <class C, int TK, int NG> static void run_fused_tma(FusedIO<double> io0, SpectralUpdate<double> up0, const cx<double> *tw, int grid) {
   FusedTmaIO<double> io;
   io.outU = io0.outU; io.n = io0.n; io.ncols = io0.ncols; io.ncb = (io0.ncols + TK - 1) / TK; io.pitch = io0.pitch; io.scale = io0.scale;
-  io.slab = 0; io.nouter = 1; io.nyl = 0; io.peer_tab = nullptr; io.peer_x0 = 0;
+  io.slab = 0; io.nouter = 1; io.nouter_full = 1; io.nyl = 0; io.peer_tab = nullptr; io.peer_x0 = 0;
   SpectralUpdate2<double> up{};
   up.kx = up0.kx; up.ky = up0.ky; up.kz = up0.kz; up.kmode = up0.kmode; up.nzc = up0.nzc; up.nzv = up0.nzc; up.x0 = up0.x0;
   up.closed_M = up0.closed_M; up.closed_L = up0.closed_L; up.has_L = up0.has_L; up.Mfac = up0.Mfac; up.Lfac = up0.Lfac;
@@ -419,7 +419,8 @@ template <class C, int NG> static void test_mech_tangent(const char *name, int n
 }
 
 // fused pass in the multi-GPU slab layout: data staged as [P][nxl][nyl][nzc], transform along y
-template <class C, int TK, int NG> static void test_fused_slab(const char *name, int P, int nxl, int nzc, int x0, int grid, bool peer = false) {
+template <class C, int TK, int NG>
+static void test_fused_slab(const char *name, int P, int nxl, int nzc, int x0, int grid, bool peer = false, int xchunks = 1) {
   constexpr int ny = C::N;
   const int nyl = ny / P;
   std::mt19937_64 rng(23);
@@ -444,7 +445,7 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
   auto tw = make_tw(ny);
   FusedTmaIO<double> io;
   io.outU = Us.data(); io.n = ny; io.ncols = nzc; io.ncb = (nzc + TK - 1) / TK; io.pitch = nzc; io.scale = 1.0 / ny;
-  io.slab = 1; io.nouter = nxl; io.nyl = nyl; io.peer_tab = nullptr; io.peer_x0 = 0;
+  io.slab = 1; io.nouter = nxl; io.nouter_full = nxl; io.nyl = nyl; io.peer_tab = nullptr; io.peer_x0 = 0;
   io.kzb_major = 0; io.nx = 0; io.rank = 0; io.nranks = P; io.flag_wait = nullptr; io.flag_expect = 0; io.flag_tab = nullptr;
   SpectralUpdate2<double> up{};
   up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = MRL_KMODE_3D_SLAB; up.nzc = nzc; up.nzv = nzc; up.x0 = x0;
@@ -468,6 +469,20 @@ template <class C, int TK, int NG> static void test_fused_slab(const char *name,
   for (int q = 0; q < P; ++q) tab[q] = (unsigned long long)peerbuf[q].data();
   if (peer) { io.peer_tab = tab.data(); io.peer_x0 = x0; }
   size_t smem = (size_t)(NG * 3 * C::N * TK) * 16 + NG * 3 * 8 + 128;
+  if (xchunks > 1) {
+    // the pass in x sub-ranges (copy-engine exchange mode): every base shifted by o0 layers, the rank blocks keep their distance
+    const int xch = nxl / xchunks;
+    for (int i = 0; i < xchunks; ++i) {
+      const size_t sh = (size_t)i * xch * nyl * nzc;
+      FusedTmaIO<double> ioc = io;
+      SpectralUpdate2<double> upc = up;
+      ioc.outU = io.outU + sh; ioc.nouter = xch; ioc.nouter_full = nxl;
+      upc.x0 = up.x0 + i * xch; upc.Nout = up.Nout + sh;
+      auto sub = [&](TensorMap m) { m.base += sh * 16; m.dim[2] = xch; return m; };
+      TensorMap c = sub(tmC), g = sub(tmG), o = sub(tmO);
+      emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG, 1>(c, g, o, ioc, upc, twp); }, 64 * 1024);
+    }
+  } else
   emu::launch(dim3(grid), dim3(NG * TK * C::TP), smem, [=] { k_fused_tma<double, C, TK, NG, 1>(tmC, tmG, tmO, io, up, twp); }, 64 * 1024);
   if (peer)
     for (int x = 0; x < nxl; ++x)
@@ -625,7 +640,7 @@ template <class C, int TK, int NG> static void test_fused_padded_buffers(const c
   auto tw = make_tw(n);
   FusedTmaIO<double> io;
   io.outU = Uo.data(); io.n = n; io.ncols = ncols; io.ncb = (ncols + TK - 1) / TK; io.pitch = ncols; io.scale = 1.0 / n;
-  io.slab = 0; io.nouter = 1; io.nyl = 0; io.peer_tab = nullptr; io.peer_x0 = 0;
+  io.slab = 0; io.nouter = 1; io.nouter_full = 1; io.nyl = 0; io.peer_tab = nullptr; io.peer_x0 = 0;
   SpectralUpdate2<double> up{};
   up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = kmode; up.nzc = ncp; up.nzv = nzv; up.x0 = 0;
   up.closed_M = 0; up.closed_L = 0; up.has_L = 1; up.Mbuf = Mb.data(); up.Lbuf = Lb.data();
@@ -789,7 +804,7 @@ template <class C, int TK, int NG> static void test_fused_slab2(const char *name
   for (int q = 0; q < P; ++q) { tab[q] = (unsigned long long)Sd[q].data(); ftab[q] = (unsigned long long)cnt2[q].data(); }
   FusedTmaIO<double> io;
   io.outU = nullptr; io.n = ny; io.ncols = ncp; io.ncb = kb; io.pitch = ncp; io.scale = 1.0 / ny;
-  io.slab = 2; io.nouter = nxl; io.nyl = nyl; io.peer_tab = tab.data(); io.peer_x0 = x0;
+  io.slab = 2; io.nouter = nxl; io.nouter_full = nxl; io.nyl = nyl; io.peer_tab = tab.data(); io.peer_x0 = x0;
   io.kzb_major = kzb_major; io.nx = nxtot; io.rank = me; io.nranks = P; io.flag_wait = cnt1.data(); io.flag_expect = 7; io.flag_tab = ftab.data();
   SpectralUpdate2<double> up{};
   up.kx = kx.data(); up.ky = ky.data(); up.kz = kz.data(); up.kmode = MRL_KMODE_3D_SLAB; up.nzc = ncp; up.nzv = ncp; up.x0 = x0;
@@ -870,6 +885,7 @@ static void tma_tests() {
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 nxl3 nzc5", 4, 3, 5, 2, 2);
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 1>("fused tma slab 64 P2 nxl2 nzc9", 2, 2, 9, 0, 1);
   test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 peer stores", 4, 3, 5, 6, 2, true);
+  test_fused_slab<FFTCfg<64, 8, 8, 8>, 8, 2>("fused tma slab 64 P4 nxl6 in 3 x-chunks", 4, 6, 5, 2, 2, false, 3);
   test_strided_peer<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("strided tma 64 peer scatter P4", 4, 11);
   test_slab_xfwd<FFTCfg<64, 8, 8, 8>, 8, 2, 3>("slab xfwd bulk 64 P4 nyl3 kb2 y-major", 4, 3, 2, 0, 1, 2);
   test_slab_xfwd<FFTCfg<64, 8, 8, 8>, 8, 1, 2>("slab xfwd bulk 64 P2 nyl4 kb3 kzb-major 2 chunks", 2, 4, 3, 1, 2, 3);

@@ -17,6 +17,10 @@ def _worker(rank, world, port, n, nsub, mode, q, chunks=1, sync="barrier", inv_c
     os.environ["MRL_SLAB_CHUNKS"] = str(chunks)   # read at plan creation: forward phase in y-chunks
     os.environ["MRL_SLAB_SYNC"] = sync            # barrier between the phases / arrival counters per column block
     os.environ["MRL_SLAB_INV_CTAS"] = str(inv_ctas)
+    # "peer": exchanges fused into the passes as bulk stores; "copy": staged layouts + copy-engine exchanges (the default)
+    os.environ["MRL_SLAB_EXCHANGE"] = "copy" if mode == "copy" else "store"
+    if mode == "copy":
+        mode = "peer"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from marlin_b200 import capi, slab
@@ -66,7 +70,8 @@ def _worker(rank, world, port, n, nsub, mode, q, chunks=1, sync="barrier", inv_c
 
 CASES = [(128, "nccl", 1, "barrier", 0), (128, "peer", 1, "barrier", 0), (256, "peer", 1, "barrier", 0), (128, "peer", 2, "barrier", 0),
          (256, "peer", 4, "barrier", 0), (128, "peer", 1, "flags", 0), (256, "peer", 4, "flags", 0), (256, "peer", 1, "flags", 40),
-         (512, "peer", 4, "flags", 48)]
+         (512, "peer", 4, "flags", 48), (128, "copy", 1, "barrier", 0), (256, "copy", 4, "barrier", 0), (256, "copy", 2, "barrier", 0),
+         (512, "copy", 4, "barrier", 0)]
 
 
 @pytest.mark.parametrize("n,mode,chunks,sync,inv_ctas", CASES)
@@ -79,7 +84,7 @@ def test_slab_matches_single_gpu(n, mode, chunks, sync, inv_ctas):
         world = 2 if world == 3 else 4
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1000) + (7 if mode == "peer" else 0) + n // 128 + 11 * chunks + (23 if sync == "flags" else 0) + inv_ctas
+    port = 29700 + (os.getpid() % 1000) + (7 if mode == "peer" else 3 if mode == "copy" else 0) + n // 128 + 11 * chunks + (23 if sync == "flags" else 0) + inv_ctas
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, 6, mode, q, chunks, sync, inv_ctas)) for r in range(world)]
     for p in procs:
         p.start()
