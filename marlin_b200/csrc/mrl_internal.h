@@ -113,9 +113,9 @@ struct mrl_slab_plan {
   cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
   long long flag_off = 0;              // byte offset of the barrier flags behind recv_fwd (peer mode)
   unsigned long long epoch = 0;        // barriers issued so far
-  // copy mode (MRL_SLAB_EXCHANGE=copy): the passes work on the plain staged layouts and the exchanges are peer-to-peer
-  // copies by the copy engines (measured on this box: 760 GB/s per direction with both directions busy, against ~500 GB/s
-  // for stores issued by the SMs), issued y-chunk by y-chunk behind the passes that produce the data
+  // copy mode (MRL_SLAB_EXCHANGE=copy; an experiment kept behind the switch): the passes work on the plain staged layouts
+  // and the exchanges are peer-to-peer copies by the copy engines (tools/p2p_probe.py: 760 GB/s per direction with both
+  // directions busy, against ~500 GB/s for stores issued by the SMs), issued y-chunk by y-chunk behind the passes
   bool copy = false;
   std::vector<char *> h_peer_recv, h_peer_ret;   // every rank's recv_fwd / landing array of the return exchange (its send_fwd)
   std::vector<cudaStream_t> s_copy;               // one stream per destination rank

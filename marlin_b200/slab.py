@@ -383,7 +383,7 @@ def bench(args, rank, world, metric):
             "config": {"workload": workload(n),
                        "impl_detail": f"slab-decomposed (y real / x reciprocal) over {world} GPUs, half spectrum on the wire, "
                                       + (("exchanges by the copy engines (peer-to-peer copies over NVLink, y-chunk by y-chunk behind the passes), "
-                                          if os.environ.get("MRL_SLAB_EXCHANGE", "copy") != "store" else
+                                          if os.environ.get("MRL_SLAB_EXCHANGE", "store") == "copy" else
                                           "all-to-all fused into the passes (bulk stores from shared memory into peer HBM over NVLink), ")
                                          + (f"per-column-block arrival counters, inverse x pass on {os.environ.get('MRL_SLAB_INV_CTAS', '0')} SMs beside the fused y pass"
                                             if plan.sync == "flags" else f"{plan.barrier_kind} barrier between the phases") if mode == "peer"
