@@ -315,7 +315,7 @@ def bm1_bench():
     return out
 
 
-def host_driver_bench(n, substeps=50, steps=3, extra_args=(), output_dir="/tmp"):
+def host_driver_bench(n, substeps=50, steps=3, extra_args=(), output_dir="/tmp", timeout=600):
     """The path a reference input takes: marlin_b200-opt -i examples/cahn_hilliard/cahnhilliard2.i (verbatim copy under
     tests/inputs/ref) at n^3 with the file's own dx, constant dt so that every substep is 1e-3 like the headline, XDMF
     output off.  Host AdamsBashforthMoulton -> automatic fusion -> MRL_NONLIN_EXPR plan (NVRTC-compiled first pass),
@@ -330,7 +330,7 @@ def host_driver_bench(n, substeps=50, steps=3, extra_args=(), output_dir="/tmp")
            f"Executioner/num_steps={steps}", f"Executioner/TimeStepper/dt={substeps * 1e-3!r}", "Executioner/TimeStepper/growth_factor=1",
            "TensorOutputs/active=", "Outputs/csv=false", "Problem/print_debug_output=true"]
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     wall = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError((r.stdout + r.stderr)[-600:])

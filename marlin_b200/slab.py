@@ -348,7 +348,7 @@ def bench(args, rank, world, metric):
         torch.cuda.empty_cache()
         try:
             from bench import host_driver_bench
-            hd = host_driver_bench(n, substeps=50, steps=3, extra_args=["Domain/parallel_mode=FFT_SLAB"])
+            hd = host_driver_bench(n, substeps=50, steps=3, extra_args=["Domain/parallel_mode=FFT_SLAB"], timeout=150)
             t = torch.tensor([hd["ms_per_substep_last_step"]], dtype=torch.float64, device="cuda")
             ok = torch.tensor([1.0 if hd["fused_plan"] else 0.0], dtype=torch.float64, device="cuda")
         except Exception as exn:
