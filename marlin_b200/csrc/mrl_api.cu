@@ -1470,15 +1470,18 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
     const size_t esz = sizeof(cx<T>), rowb = (size_t)nyl * p->ncp * esz;
     const void *twx;
     if ((rc = ctx->twiddles(ctx->n[0], &twx))) return rc;
+    // MRL_SLAB_COPY_SMS: SMs the passes leave free (in case the driver runs the strided peer copies as kernels)
+    static const int spare = getenv("MRL_SLAB_COPY_SMS") ? atoi(getenv("MRL_SLAB_COPY_SMS")) : 0;
+    const LaunchCtx lcp{ctx->stream, spare > 0 && spare < ctx->sm_count ? ctx->sm_count - spare : ctx->sm_count};
     for (int i = 0; i < nch; ++i) {
       if (d.nonlin_kind == MRL_NONLIN_EXPR) {
         const int rowmap[3] = {nch > 1 ? ych : 0, nyl, i * ych};
         if ((rc = mrl_expr_launch_zfwd_rows(ctx, d.nonlin_expr, d.nonlin_var, d.nonlin_inputs_dev, 0.0, c, d.g_out_real_dev, A, A + p->field,
-                                            (long long)ctx->n[0] * ych, nl, p->ncp, rowmap, ctx->stream, ctx->sm_count)))
+                                            (long long)ctx->n[0] * ych, nl, p->ncp, rowmap, ctx->stream, lcp.sm_count)))
           return rc;
       } else {
         ctx->launches++;
-        CK(launch_zfwd_nonlin_tma<T>(ctx->lc(), c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ych, nl, p->ncp, nlz,
+        CK(launch_zfwd_nonlin_tma<T>(lcp, c, (T *)d.g_out_real_dev, A, A + p->field, (long long)ctx->n[0] * ych, nl, p->ncp, nlz,
                                      (const cx<T> *)twl, nch > 1 ? RowMap{ych, nyl, i * ych} : RowMap{0, 0, 0}));
       }
       StridedIO<T> sio;
@@ -1492,7 +1495,7 @@ template <class T> static int slab_forward_impl(mrl_slab_plan *p, const T *c) {
       sio.outer_stride = (long long)sio.n * sio.pitch;
       sio.scale = T(1);
       ctx->launches++;
-      CK(launch_strided_tma<T>(ctx->lc(), sio, (const cx<T> *)twx, sio.n));
+      CK(launch_strided_tma<T>(lcp, sio, (const cx<T> *)twx, sio.n));
       CK(cudaEventRecord(p->ev_chunk[i], ctx->stream));
       for (int k = 0; k < P; ++k) {
         const int s = (me + 1 + k) % P;  // the own block last
