@@ -35,9 +35,20 @@ def workload(n):
 
 
 def lib_sha256():
+    """Identity of the library build the traffic figures belong to: a hash over the CUDA / C ABI sources it is compiled
+    from (marlin_b200/csrc, include/marlin_b200.h, Makefile), so that a rebuild of the same sources - which need not be
+    bit-identical - keeps the figures and any source change drops them."""
+    import glob
     import hashlib
     try:
-        return hashlib.sha256(open(os.path.join(ROOT, "marlin_b200", "libmarlin_b200.so"), "rb").read()).hexdigest()[:16]
+        h = hashlib.sha256()
+        files = sorted(glob.glob(os.path.join(ROOT, "marlin_b200", "csrc", "*"))) + [os.path.join(ROOT, "include", "marlin_b200.h"),
+                                                                                    os.path.join(ROOT, "Makefile")]
+        for f in files:
+            if os.path.isfile(f):
+                h.update(os.path.basename(f).encode())
+                h.update(open(f, "rb").read())
+        return h.hexdigest()[:16]
     except Exception:
         return None
 
