@@ -612,6 +612,27 @@ static int xdmfSelfTest(const std::string &dir) {
   return 0;
 }
 
+// --comm-selftest: exercises the process-group rendezvous of the stand-alone driver (host/shim/comm.h) without a device:
+// every rank prints what allgather / allreduce / barrier return (used by the CPU test-suite with several processes)
+static int commSelfTest() {
+  Comm &c = Comm::world();
+  const int r = c.rank(), n = c.size();
+  std::vector<int32_t> all(size_t(3) * n);
+  const int32_t mine[3] = {r, 10 * r, 7};
+  c.allgather(mine, sizeof mine, all.data());
+  double v[3] = {double(r + 1), double(r + 1), double(r + 1)};
+  c.allreduce(&v[0], 1, Comm::SUM);
+  c.allreduce(&v[1], 1, Comm::MIN);
+  c.allreduce(&v[2], 1, Comm::MAX);
+  std::vector<double> big(1000, 0.001 * (r + 1));
+  c.allreduce(big.data(), big.size(), Comm::SUM);
+  c.barrier();
+  std::cout << "rank " << r << " of " << n << " local " << c.localRank() << " gathered";
+  for (int32_t x : all) std::cout << ' ' << x;
+  std::cout << " sum " << v[0] << " min " << v[1] << " max " << v[2] << " big " << std::setprecision(12) << big[999] << "\n";
+  return 0;
+}
+
 int main(int argc, char **argv) {
   Options opt;
   for (int i = 1; i < argc; ++i) {
@@ -641,6 +662,14 @@ int main(int argc, char **argv) {
       opt.dump_dir = need("--dump-dir");
     else if (a == "--xdmf-selftest")
       return xdmfSelfTest(need("--xdmf-selftest"));
+    else if (a == "--comm-selftest") {
+      try {
+        return commSelfTest();
+      } catch (const std::exception &e) {
+        std::cerr << "\n*** ERROR ***\n" << e.what() << "\n";
+        return 1;
+      }
+    }
     else if (a == "--smooth-rectangle-expr") {  // DIM WIDTH PROFILE: the kernel expression (CPU test-suite)
       const unsigned int dim = std::stoul(need("--smooth-rectangle-expr"));
       const double w = std::stod(need("--smooth-rectangle-expr"));

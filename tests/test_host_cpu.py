@@ -305,3 +305,23 @@ def test_h5lite_reader_parses_the_reference_gold_files():
     m = h5lite.H5File(f"{REF}/test/tests/mechanics/gold/mech3d.h5")
     gm = np.load(f"{ROOT}/tests/golden/mech3d_h5.npz")
     assert np.array_equal(m.read("sV.2"), gm["sV"][2].transpose(2, 1, 0))   # stored with transpose = true (x <-> z)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_process_group_rendezvous(world):
+    """host/shim/comm: the MPI-free process group of the stand-alone driver ([Domain] parallel_mode = FFT_SLAB / FFT_PENCIL
+    run one process per GPU).  Ranks meet over TCP through the torchrun-style environment; allgather keeps rank order,
+    allreduce sums / minimises / maximises in rank order on every rank (so that all ranks take the same decisions), a rank
+    that never shows up is an error, not a hang."""
+    port = 29400 + (os.getpid() * 3 + world) % 500
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MRL_COMM_PORT=str(port))
+        procs.append(subprocess.Popen([APP, "--comm-selftest"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=60) for p in procs]
+    gathered = " ".join(f"{r} {10 * r} 7" for r in range(world))
+    tri = world * (world + 1) // 2
+    for r, (p, (so, se)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, se
+        assert f"rank {r} of {world} local {r} gathered {gathered} sum {tri} min 1 max {world} big" in so, so
+        assert abs(float(so.split()[-1]) - 0.001 * tri) < 1e-15
