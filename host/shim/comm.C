@@ -3,6 +3,7 @@
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <poll.h>
 #include <sys/socket.h>
 #include <unistd.h>
 
@@ -52,7 +53,15 @@ Comm::Comm() {
     if (::bind(ls, (sockaddr *)&sa, sizeof sa) < 0) fail("bind to port " + std::to_string(port));
     if (::listen(ls, _size) < 0) fail("listen");
     _peers.assign(_size, -1);
+    // a rank that never shows up is an error after MRL_COMM_TIMEOUT seconds (default 120), not a hang
+    const int timeout_ms = envInt("MRL_COMM_TIMEOUT", 120) * 1000;
     for (int i = 1; i < _size; ++i) {
+      pollfd pfd{ls, POLLIN, 0};
+      const int ready = ::poll(&pfd, 1, timeout_ms);
+      if (ready == 0)
+        throw std::runtime_error("Comm: only " + std::to_string(i) + " of " + std::to_string(_size) + " ranks reached the rendezvous on port " +
+                                 std::to_string(port) + " within " + std::to_string(timeout_ms / 1000) + " s");
+      if (ready < 0) fail("poll");
       const int fd = ::accept(ls, nullptr, nullptr);
       if (fd < 0) fail("accept");
       ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);

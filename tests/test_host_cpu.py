@@ -325,3 +325,11 @@ def test_process_group_rendezvous(world):
         assert p.returncode == 0, se
         assert f"rank {r} of {world} local {r} gathered {gathered} sum {tri} min 1 max {world} big" in so, so
         assert abs(float(so.split()[-1]) - 0.001 * tri) < 1e-15
+
+
+def test_process_group_missing_rank_is_an_error():
+    """Rank 0 of a world of two whose peer never starts gives up with a message instead of waiting forever."""
+    port = 29350 + os.getpid() % 40
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MRL_COMM_PORT=str(port), MRL_COMM_TIMEOUT="1")
+    r = subprocess.run([APP, "--comm-selftest"], env=env, capture_output=True, text=True, timeout=30)
+    assert r.returncode != 0 and "only 1 of 2 ranks reached the rendezvous" in r.stderr
