@@ -345,6 +345,10 @@ int mrl_domain_set_dist(mrl_context *ctx, int dim, const int64_t *n, const doubl
                         int nranks, const double *weights);
 int mrl_domain_set_pencil(mrl_context *ctx, int dim, const int64_t *n, const double *min, const double *max, int rank,
                           int nranks);
+/* the factorisation nranks = Py * Pz partitionPencils chooses for an nx x ny x nz grid (DomainAction.C:574-613: both
+ * factors > 1 and fitting the domain, as close to a square as possible, the first such pair in its search order).
+ * Host only; MRL_ERR_INVALID with the reference's message when there is none.                                */
+int mrl_pencil_factors(int nranks, const int64_t *n, int *py, int *pz);
 /* slab mode: global grid size and the slab table: counts / begins of the real-space y slabs and the reciprocal x
  * slabs of every rank (each array nranks entries; any pointer may be NULL)                                  */
 int mrl_dist_partition(const mrl_context *ctx, int64_t *n_global, int64_t *y_count, int64_t *y_begin, int64_t *x_count,
@@ -377,12 +381,18 @@ int mrl_slab_sizes(const mrl_context *ctx, int64_t *field_elems, int64_t *chunk_
 int mrl_slab_plan_create(mrl_context *ctx, const mrl_split_desc *desc, void *send_fwd_dev, void *recv_fwd_dev,
                          void *send_bwd_dev, mrl_slab_plan **out);
 /* Peer mode - the all-to-all fused into the passes: buffers are owned by the library and shared
- * through CUDA IPC; phase 1's x pass stores every result row straight into the HBM of the rank
- * that owns its x block, phase 2's fused pass stores rows straight into the owners' y slabs
- * (plain stores to NVLink-mapped peer memory, overlapped with the pass's own HBM traffic), so
- * no exchange call, no staging copy and no pack/unpack exist.  Protocol per substep:
+ * through CUDA IPC; phase 1's x pass stages every result tile in shared memory and pushes it with bulk
+ * asynchronous copies into a blocked staging layout in the HBM of the rank that owns its x block,
+ * phase 2's fused pass pushes its rows into the owners' y slabs the same way (over NVLink, overlapped
+ * with the pass's own HBM traffic), so no exchange call, no staging copy and no pack/unpack exist.
+ * The nonlinearity may be the built-in double well or a compiled expression (MRL_NONLIN_EXPR: it is
+ * compiled into the first pass as on one GPU); the k-space factors must be closed forms; every axis
+ * 128 / 256 / 512 / 1024 points, equal slabs.  The context may be set up with mrl_domain_set_slab or
+ * with mrl_domain_set_dist (the host objects' FFT_SLAB mode).  Protocol per substep:
  *   mrl_slab_forward -> cross-rank barrier -> mrl_slab_update -> cross-rank barrier -> mrl_slab_inverse
- * handles: 2 x 64 bytes per rank (cudaIpcMemHandle_t of send_fwd, recv_fwd).               */
+ * handles: 2 x 64 bytes per rank (cudaIpcMemHandle_t of the return staging, recv_fwd).
+ * MRL_SLAB_EXCHANGE=copy (environment, read at plan creation) selects an alternative kept for
+ * comparison: plain staged layouts and peer copies by the copy engines (slower on the measured boxes). */
 int mrl_slab_plan_create_peer(mrl_context *ctx, const mrl_split_desc *desc, mrl_slab_plan **out);
 int mrl_slab_ipc_export(mrl_slab_plan *plan, void *handles_128_bytes);
 int mrl_slab_ipc_import(mrl_slab_plan *plan, const void *all_handles /* nranks x 128 bytes, rank order */);

@@ -100,23 +100,18 @@ extern "C" int mrl_domain_set_dist(mrl_context *ctx, int dim, const int64_t *n, 
   return upload_axes(ctx, 0, true);
 }
 
-// partitionPencils (DomainAction.C:569-742).  Rank r = pz * Py + py: real space [nx][ny / Py][nz / Pz] (y part py, z part
-// pz); reciprocal space [(nx/2+1) / Py][ny / Pz][nz] (kx part py, ky part pz) with the half spectrum on x.
-extern "C" int mrl_domain_set_pencil(mrl_context *ctx, int dim, const int64_t *n, const double *mn, const double *mx, int rank, int nranks) {
-  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return mrl_fail(MRL_ERR_INVALID, "mrl_domain_set_pencil: bad arguments");
-  if (dim < 3) return mrl_fail(MRL_ERR_INVALID, "Dimension must be 3 for pencil decomposition.");
-  int rc = mrl_domain_set(ctx, dim, n, mn, mx);
-  if (rc) return rc;
+// the factorisation nranks = Py * Pz closest to a square that fits the domain (DomainAction.C:574-613)
+extern "C" int mrl_pencil_factors(int nranks, const int64_t *n, int *py, int *pz) {
+  if (nranks < 1 || !n || !py || !pz) return mrl_fail(MRL_ERR_INVALID, "mrl_pencil_factors: bad arguments");
   const int64_t nxc = n[0] / 2 + 1;
-  // the factorisation nranks = Py * Pz closest to a square that fits the domain (:574-613)
   int best_py = 0, best_pz = 0, best_cost = 0;
   bool found = false;
-  auto consider = [&](int px, int pz) {
-    if (px < 2 || pz < 2 || px > n[1] || px > nxc || pz > n[2] || pz > n[1]) return;
-    const int cost = std::abs(px - pz);
+  auto consider = [&](int px, int pz_) {
+    if (px < 2 || pz_ < 2 || px > n[1] || px > nxc || pz_ > n[2] || pz_ > n[1]) return;
+    const int cost = std::abs(px - pz_);
     if (!found || cost < best_cost) {
       best_py = px;
-      best_pz = pz;
+      best_pz = pz_;
       best_cost = cost;
       found = true;
     }
@@ -132,6 +127,21 @@ extern "C" int mrl_domain_set_pencil(mrl_context *ctx, int dim, const int64_t *n
                     "FFT_PENCIL requires factoring the number of MPI ranks into two integers greater than one that fit the domain (ranks = %d). "
                     "Use FFT_SLAB or adjust the rank count.",
                     nranks);
+  *py = best_py;
+  *pz = best_pz;
+  return MRL_OK;
+}
+
+// partitionPencils (DomainAction.C:569-742).  Rank r = pz * Py + py: real space [nx][ny / Py][nz / Pz] (y part py, z part
+// pz); reciprocal space [(nx/2+1) / Py][ny / Pz][nz] (kx part py, ky part pz) with the half spectrum on x.
+extern "C" int mrl_domain_set_pencil(mrl_context *ctx, int dim, const int64_t *n, const double *mn, const double *mx, int rank, int nranks) {
+  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return mrl_fail(MRL_ERR_INVALID, "mrl_domain_set_pencil: bad arguments");
+  if (dim < 3) return mrl_fail(MRL_ERR_INVALID, "Dimension must be 3 for pencil decomposition.");
+  int rc = mrl_domain_set(ctx, dim, n, mn, mx);
+  if (rc) return rc;
+  const int64_t nxc = n[0] / 2 + 1;
+  int best_py = 0, best_pz = 0;
+  if ((rc = mrl_pencil_factors(nranks, n, &best_py, &best_pz))) return rc;
   const int Py = best_py, Pz = best_pz;
   ctx->ycount.assign(Py, 0);
   ctx->zcount.assign(Pz, 0);

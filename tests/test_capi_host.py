@@ -81,3 +81,27 @@ def test_partition_matches_reference_rule(lib, total, weights):
     got = capi.partition(total, len(weights), weights)
     assert got == _partition_ref(total, weights) and sum(got) == total
     assert capi.partition(total, len(weights)) == _partition_ref(total, [1] * len(weights))
+
+
+def test_pencil_factorisation_rule():
+    """partitionPencils' choice of Py x Pz (src/actions/DomainAction.C:574-613): both factors > 1, fitting the domain
+    (Py <= ny and <= nx/2+1, Pz <= nz and <= ny), smallest |Py - Pz|, the first pair found for d = 2 .. sqrt(ranks) in the
+    order (d, ranks/d), (ranks/d, d).  Host-only arithmetic."""
+    import ctypes as C
+
+    from marlin_b200 import capi
+
+    def factors(nranks, n):
+        py, pz = C.c_int(), C.c_int()
+        rc = capi.lib().mrl_pencil_factors(nranks, (C.c_int64 * 3)(*n), C.byref(py), C.byref(pz))
+        return (py.value, pz.value) if rc == 0 else capi.lib().mrl_last_error().decode()
+
+    assert factors(4, (40, 40, 40)) == (2, 2)
+    assert factors(8, (40, 40, 40)) == (2, 4)       # cost 2 either way: the first pair considered wins
+    assert factors(6, (40, 40, 40)) == (2, 3)
+    assert factors(16, (64, 64, 64)) == (4, 4)
+    assert factors(12, (64, 64, 64)) == (3, 4)      # d = 2: (2, 6) cost 4; d = 3: (3, 4) cost 1
+    assert factors(8, (4, 40, 3)) == (2, 4) or "FFT_PENCIL requires" in str(factors(8, (4, 40, 3)))
+    assert factors(8, (40, 40, 3)) == (4, 2)        # Pz = 4 does not fit nz = 3
+    for bad in (1, 2, 3, 5, 7):
+        assert "FFT_PENCIL requires factoring the number of MPI ranks" in str(factors(bad, (40, 40, 40)))
