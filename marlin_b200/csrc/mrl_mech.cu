@@ -123,9 +123,15 @@ template <class T> static int vec(mrl_mech_plan *p, int op, const T *a, const T 
 
 // dot_with != nullptr: alpha = rz / (dot_with . out) follows (FIN_ALPHA), with the inner product riding in the store of
 // the last inverse pass where that pass can carry it
+template <class T> static int finish_dot(mrl_mech_plan *p, const T *dot_with, const T *out);
 template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, double sign, const T *dot_with = nullptr) {
   int rc = project_G_passes<T>(p, A, out, sign, dot_with);
-  if (rc || !dot_with) return rc;
+  return rc ? rc : finish_dot<T>(p, dot_with, out);
+}
+
+// alpha = rz / (dot_with . out) after an inverse transform that may have carried the inner product in its store
+template <class T> static int finish_dot(mrl_mech_plan *p, const T *dot_with, const T *out) {
+  if (!dot_with) return MRL_OK;
   if (p->dot_count > 0) {
     p->ctx->launches++;
     CK(launch_vec_final<T>(p->ctx->lc(), FIN_ALPHA, SC_TMP, p->partials, p->dot_count, p->scal));
@@ -134,24 +140,29 @@ template <class T> static int project_G(mrl_mech_plan *p, const T *A, T *out, do
   return vec<T>(p, VOP_DOT, dot_with, out, nullptr, nullptr, 0, FIN_ALPHA, SC_TMP);
 }
 
-// the part of project_G after the z and y forward passes (3-D fused path only): p->spec holds the partial spectra
+// the part of project_G after the z and y forward passes (3-D): p->spec holds the partial spectra
 template <class T> static int project_G_from_spec(mrl_mech_plan *p, T *out, double sign, const T *dot_with) {
   mrl_context *ctx = p->ctx;
   p->dot_count = 0;
-  const void *tw;
-  int rc = ctx->twiddles(ctx->n[0], &tw);
-  if (rc) return rc;
-  CK(launch_mech_fused_tma<T>(ctx->lc(), (cx<T> *)p->spec, (const T *)ctx->kaxis_dev[0], (const T *)ctx->kaxis_dev[1], (const T *)ctx->kaxis_dev[2],
-                              ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp, (const cx<T> *)tw));
-  ctx->launches++;
-  if ((rc = mrl_fftb_inverse(ctx, p->spec, out, p->nc, p->ncp, sign / (double)p->n, 1, dot_with, p->partials, p->nblk, &p->dot_count))) return rc;
-  if (!dot_with) return MRL_OK;
-  if (p->dot_count > 0) {
-    ctx->launches++;
-    CK(launch_vec_final<T>(ctx->lc(), FIN_ALPHA, SC_TMP, p->partials, p->dot_count, p->scal));
-    return MRL_OK;
+  const T *kx = (const T *)ctx->kaxis_dev[0], *ky = (const T *)ctx->kaxis_dev[1], *kz = (const T *)ctx->kaxis_dev[2];
+  int rc;
+  if (p->fused_x) {
+    const void *tw;
+    if ((rc = ctx->twiddles(ctx->n[0], &tw))) return rc;
+    cudaError_t e = launch_mech_fused_tma<T>(ctx->lc(), (cx<T> *)p->spec, kx, ky, kz, ctx->n[0], ctx->n[1], ctx->nr[2], p->ncp, (const cx<T> *)tw);
+    if (e == cudaSuccess) {
+      ctx->launches++;
+      if ((rc = mrl_fftb_inverse(ctx, p->spec, out, p->nc, p->ncp, sign / (double)p->n, 1, dot_with, p->partials, p->nblk, &p->dot_count))) return rc;
+      return finish_dot<T>(p, dot_with, out);
+    }
+    if (e != cudaErrorNotSupported) CK(e);
+    p->fused_x = false;  // no pipelined configuration for the x axis of this grid: separate passes from here on
   }
-  return vec<T>(p, VOP_DOT, dot_with, out, nullptr, nullptr, 0, FIN_ALPHA, SC_TMP);
+  if ((rc = mrl_fftb_strided(ctx, p->spec, p->nc, p->ncp, 0, 0))) return rc;
+  ctx->launches++;
+  CK(launch_mech_project<T>(ctx->lc(), p->dim, (cx<T> *)p->spec, kx, ky, kz, ctx->nr[0], ctx->nr[1], ctx->nr[2], p->ncp));
+  if ((rc = mrl_fftb_inverse(ctx, p->spec, out, p->nc, p->ncp, sign / (double)p->n, 0, dot_with, p->partials, p->nblk, &p->dot_count))) return rc;
+  return finish_dot<T>(p, dot_with, out);
 }
 
 template <class T> static int project_G_passes(mrl_mech_plan *p, const T *A, T *out, double sign, const T *dot_with) {

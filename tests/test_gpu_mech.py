@@ -268,3 +268,34 @@ def test_mech_float32_tma_size():
     assert rel_l2(lin, 2.0 * plan.apply_GK(F, A) - 3.0 * plan.apply_GK(F, B)) < 1e-4
     plan.close()
     c32.close()
+
+
+def test_mech_mixed_grid_falls_back_per_axis(ctx):
+    """A grid whose last axis has the tangent-fused first pass (256) but whose x axis has no fused Green-projection
+    configuration (48): the operator must finish with the separate passes, and agree with the fully un-fused path."""
+    import os
+
+    from marlin_b200 import capi
+    shape = (48, 64, 256)
+    ctx.domain_set(3, shape, (0,) * 3, (1.0, 2.0, 3.0))
+    torch.manual_seed(9)
+    K = (1.0 + torch.rand(shape, dtype=torch.float64)).cuda()
+    mu = (0.5 + torch.rand(shape, dtype=torch.float64)).cuda()
+    F = (torch.eye(3, dtype=torch.float64).reshape(9, 1, 1, 1) + 0.1 * torch.rand((9,) + shape, dtype=torch.float64)).contiguous().cuda()
+    x = (torch.rand((9,) + shape, dtype=torch.float64) - 0.5).cuda()
+    outs = []
+    for fused in ("1", "0"):
+        os.environ["MRL_MECH_TANGENT_FUSED"] = fused
+        try:
+            plan = capi.MechPlan(ctx, K, mu, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2)
+            outs.append(plan.apply_GK(F, x.clone()).clone())
+            plan.close()
+        finally:
+            os.environ.pop("MRL_MECH_TANGENT_FUSED", None)
+    assert float((outs[0] - outs[1]).abs().max() / outs[1].abs().max()) < 1e-13
+    # the projection is idempotent: G(G(a)) = G(a)
+    plan = capi.MechPlan(ctx, K, mu, l_tol=1e-2, nl_rel_tol=2e-2, nl_abs_tol=2e-2)
+    g1 = plan.apply_G(x)
+    g2 = plan.apply_G(g1)
+    assert float((g1 - g2).abs().max() / g1.abs().max()) < 1e-12
+    plan.close()
