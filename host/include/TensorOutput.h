@@ -21,7 +21,7 @@ class TensorOutput : public MooseObject {
 public:
   static InputParameters validParams();
   explicit TensorOutput(const InputParameters &parameters);
-  ~TensorOutput() override { waitForCompletion(); }
+  ~TensorOutput() override;  // joins the output thread; an error it left behind is reported, not thrown
   virtual void init() {}
   bool shouldRun(ExecFlagType flag) const { return (_execute_on & flag) != 0; }
   // TensorOutput.C:66-81: output() in a dedicated thread; an exception it throws is re-thrown by waitForCompletion

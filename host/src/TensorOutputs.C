@@ -33,6 +33,14 @@ TensorOutput::TensorOutput(const InputParameters &parameters)
   }
 }
 
+TensorOutput::~TensorOutput() {
+  try {
+    waitForCompletion();
+  } catch (const std::exception &e) {
+    std::cerr << "marlin_b200: output '" << name() << "' failed: " << e.what() << "\n";
+  }
+}
+
 void TensorOutput::startOutput() {
   prepareForOutput();
   if (_output_thread.joinable())
