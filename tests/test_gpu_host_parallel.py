@@ -19,13 +19,13 @@ REF = os.path.join(ROOT, "tests", "inputs", "ref")
 G = os.path.join(ROOT, "tests", "golden")
 
 
-def launch(tmp, nranks, inp, *args, dump=()):
+def launch(tmp, nranks, inp, *args, dump=(), inp_dir=REF):
     """mpiexec -n nranks marlin-opt -i inp args: one process per rank."""
     port = 29600 + (os.getpid() * 7 + nranks) % 300
     procs = []
     for r in range(nranks):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MRL_COMM_PORT=str(port))
-        cmd = [APP, "-i", f"{REF}/{inp}", "--output-dir", str(tmp), "--compute-device=cuda", *args]
+        cmd = [APP, "-i", f"{inp_dir}/{inp}", "--output-dir", str(tmp), "--compute-device=cuda", *args]
         if dump:
             cmd += ["--dump", ",".join(dump), "--dump-dir", str(tmp)]
         procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
@@ -128,13 +128,7 @@ def test_slab_roundtrip_three_ranks(tmp_path):
     """The check of test/tests/tensor_compute/parallel_roundtrip.i (a 2-D field through fftSlab / ifftSlab on three ranks,
     128 = 42 + 42 + 44, returns unchanged; that file reads a [Solve] output at INITIAL and is not part of the reference's
     test specs) with the transforms in [Initialize]."""
-    port_inp = os.path.join(ROOT, "tests", "inputs", "slab_roundtrip.i")
-    global REF
-    keep, REF = REF, os.path.dirname(port_inp)
-    try:
-        launch(tmp_path, 3, "slab_roundtrip.i")
-    finally:
-        REF = keep
+    launch(tmp_path, 3, "slab_roundtrip.i", inp_dir=os.path.join(ROOT, "tests", "inputs"))
     head, rows = csv(f"{tmp_path}/slab_roundtrip_out.csv")
     assert abs(rows[-1, head.index("max_error")]) < 1e-13
     assert abs(rows[-1, head.index("l2_error")]) < 1e-10
