@@ -20,23 +20,28 @@ G = os.path.join(ROOT, "tests", "golden")
 
 
 def launch(tmp, nranks, inp, *args, dump=(), inp_dir=REF):
-    """mpiexec -n nranks marlin-opt -i inp args: one process per rank."""
-    port = 29600 + (os.getpid() * 7 + nranks) % 300
-    procs = []
-    for r in range(nranks):
-        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MRL_COMM_PORT=str(port))
-        cmd = [APP, "-i", f"{inp_dir}/{inp}", "--output-dir", str(tmp), "--compute-device=cuda", *args]
-        if dump:
-            cmd += ["--dump", ",".join(dump), "--dump-dir", str(tmp)]
-        procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-    outs = []
-    try:
-        for p in procs:
-            outs.append(p.communicate(timeout=600))
-    finally:
-        for p in procs:
-            if p.poll() is None:
-                p.kill()
+    """mpiexec -n nranks marlin-opt -i inp args: one process per rank.  A rendezvous that cannot bind its port (left in
+    use by something else on the box) is retried once on another port."""
+    for attempt in range(2):
+        port = 29600 + (os.getpid() * 7 + nranks + 131 * attempt) % 300
+        procs = []
+        for r in range(nranks):
+            env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(nranks), MASTER_ADDR="127.0.0.1", MRL_COMM_PORT=str(port))
+            cmd = [APP, "-i", f"{inp_dir}/{inp}", "--output-dir", str(tmp), "--compute-device=cuda", *args]
+            if dump:
+                cmd += ["--dump", ",".join(dump), "--dump-dir", str(tmp)]
+            procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        outs = []
+        try:
+            for p in procs:
+                outs.append(p.communicate(timeout=600))
+        finally:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+        if attempt == 0 and any("Comm: bind to port" in se for _, se in outs):
+            continue
+        break
     for r, (p, (so, se)) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r}:\n{so}\n{se}"
     return outs
